@@ -1,0 +1,309 @@
+"""Generate tests/golden/*.npz by executing the REFERENCE's own code on CPU (authoring container only).
+
+    python -m oracle.gen_golden            # writes tests/golden/
+
+What runs from /root/reference, unmodified (see oracle/ref_import.py for the import recipe):
+  * ``OrpheusForCausalLM`` / ``OrpheusModel.forward|sampling|postprocess`` (model/orpheus.py)
+  * ``Sampler`` (sampling.py)                      * ``SNAC`` decoder (tokenizer/snac.py)
+  * ``ModelWorker.prepare_lm_inputs|run_detokenize|free_kv_cache`` (worker/base.py)
+  * ``Scheduler._select_lm_requests|_select_detokenize_requests`` (scheduler/base.py)
+What is substituted: the three CUDA-only FlashInfer ops (oracle/lm_ops.py restatements) and the
+``torch.randn`` NoiseBlock draws (served from a seeded CPU generator so they can be replayed).
+
+Weights are NOT stored: they are re-derived from seeds by ``oracle.orpheus.synth_weights`` /
+``oracle.snac.synth_state_dict`` (torch CPU generator; same torch build on the GPU box).
+"""
+from __future__ import annotations
+
+import asyncio
+import os
+import queue
+import sys
+import types
+
+import numpy as np
+import torch
+
+from . import lm_ops, orpheus as oorph, sampler as osampler, snac as osnac
+from .ref_import import import_reference
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+# ------------------------------------------------------------------------------------------
+def build_ref_orpheus(ref, dims: oorph.OrpheusDims, weights, snac_cfg, snac_sd, cfg):
+    from transformers import LlamaConfig
+
+    hf = LlamaConfig(
+        vocab_size=dims.vocab_size, hidden_size=dims.hidden_size, intermediate_size=dims.intermediate_size,
+        num_hidden_layers=dims.num_hidden_layers, num_attention_heads=dims.num_attention_heads,
+        num_key_value_heads=dims.num_key_value_heads, head_dim=dims.head_dim, rms_norm_eps=dims.rms_norm_eps,
+        hidden_act="silu", attention_bias=False, mlp_bias=False, pad_token_id=None, tie_word_embeddings=False,
+    )
+    hf.rope_theta = dims.rope_theta
+    hf.rope_scaling = {"factor": dims.rope_factor, "low_freq_factor": dims.low_freq_factor,
+                       "high_freq_factor": dims.high_freq_factor,
+                       "original_max_position_embeddings": dims.old_context_len, "rope_type": "llama3"}
+    lm = ref.orpheus.OrpheusForCausalLM(hf)
+    missing = lm.load_state_dict(weights, strict=True)
+    lm = lm.to(torch.bfloat16).eval()
+
+    snac = ref.snac.SNAC(
+        sampling_rate=snac_cfg.sampling_rate, encoder_dim=snac_cfg.encoder_dim,
+        encoder_rates=list(snac_cfg.encoder_rates), decoder_dim=snac_cfg.decoder_dim,
+        decoder_rates=list(snac_cfg.decoder_rates), attn_window_size=None,
+        codebook_size=snac_cfg.codebook_size, codebook_dim=snac_cfg.codebook_dim,
+        vq_strides=list(snac_cfg.vq_strides), noise=True, depthwise=True).eval()
+    r = snac.load_state_dict(snac_sd, strict=False)
+    assert not r.unexpected_keys, r.unexpected_keys
+    assert all(k.startswith("encoder") or ".in_proj" in k for k in r.missing_keys), r.missing_keys
+
+    m = object.__new__(ref.orpheus.OrpheusModel)     # skip from_pretrained (orpheus.py:238-250)
+    m.model_name, m.device, m.dtype = "synthetic-orpheus", "cpu", torch.bfloat16
+    m.enable_torch_compile, m.audio_decoder_device = False, "cpu"
+    m.model, m.audio_decoder = lm, snac
+    m._num_attention_heads, m._num_key_value_heads = dims.num_attention_heads, dims.num_key_value_heads
+    m._num_hidden_layers, m._hidden_size = dims.num_hidden_layers, dims.hidden_size
+    m.stop_token_id = dims.stop_token_id
+    m.default_sampling_config = cfg
+    m.idx_14 = torch.tensor([1, 4], dtype=torch.long)
+    m.idx_2356 = torch.tensor([2, 3, 5, 6], dtype=torch.long)
+    # audio id base differs from 128266 for the tiny vocab: same formula, other constant
+    base = dims.audio_id_base
+    m._turn_token_into_id = lambda ids: (ids - base) % 4096
+    m.preprocess = types.MethodType(_preprocess_ids, m)
+    type(m).max_tokens  # property exists
+    return m
+
+
+def _preprocess_ids(self, prompt=None, audio_path=None, **kw):
+    """Token ids arrive pre-tokenised (no HF tokenizer on disk): same output structure as
+    OrpheusModel.preprocess (orpheus.py:366-396)."""
+    from vox_serve.model.base import PreprocessOutput
+
+    ids = torch.as_tensor(prompt, dtype=torch.int64).view(-1, 1)
+    cfg = self.default_sampling_config
+    rep = None
+    if cfg.repetition_penalty is not None and cfg.repetition_window is not None and cfg.repetition_penalty != 1.0:
+        rep = torch.zeros(cfg.repetition_window if cfg.repetition_window > 0 else 1, 1, self.vocab_size,
+                          dtype=torch.bool)
+    return PreprocessOutput(input_tokens=ids, repetition_cache=rep)
+
+
+def build_ref_worker(ref, model, page_size, max_num_pages, max_batch_size):
+    w = object.__new__(ref.graph_worker.CudaGraphWorker)   # skip CUDA init (worker/base.py:15-125)
+    w.model, w.device, w.detokenizer_device = model, "cpu", "cpu"
+    w.max_batch_size, w.page_size, w.max_num_pages = max_batch_size, page_size, max_num_pages
+    w.empty_pages = queue.Queue()
+    for i in range(max_num_pages):
+        w.empty_pages.put(i)
+    w.needs_watermarking, w.nvtx_enabled = False, False
+    import logging
+    w.logger = logging.getLogger("golden")
+    w.prefill_graph_batch_size, w.cuda_graph_seq_len_buckets = 8, [1024]
+    w.kv_cache = torch.zeros(model.num_hidden_layers, max_num_pages, 2, page_size, model.num_key_value_heads,
+                             model.head_dim, dtype=torch.bfloat16)
+    return w
+
+
+def ref_lm_step(ref, worker, reqs, lm_inputs, stop_mask_id=None):
+    """plan -> model.forward -> last-token gather (cuda_graph_worker.py:900-902) -> model.sampling
+    -> update_req_states, all reference code except the paged wrapper."""
+    if not reqs:
+        return None
+    ps = worker.page_size
+    if lm_inputs["is_prefill"]:
+        wr = lm_ops.PagedWrapperCPU("prefill", ps)
+        wr.plan(lm_inputs["qo_indptr"], lm_inputs["paged_kv_indptr"], lm_inputs["paged_kv_indices"],
+                lm_inputs["paged_kv_last_page_len"])
+    else:
+        wr = lm_ops.PagedWrapperCPU("decode", ps)
+        wr.plan(lm_inputs["paged_kv_indptr"], lm_inputs["paged_kv_indices"], lm_inputs["paged_kv_last_page_len"])
+    logits = worker.model.forward(input_ids=lm_inputs["input_ids"], position_ids=lm_inputs["position_ids"],
+                                  attn_wrapper=wr, kv_cache=worker.kv_cache)
+    if lm_inputs["is_prefill"]:
+        logits = logits[torch.tensor(lm_inputs["qo_indptr"][1:]) - 1]
+    raw = logits.clone()
+    if stop_mask_id is not None:
+        logits = logits.clone()
+        logits[..., stop_mask_id] = float("-inf")
+    ids, task = worker.model.sampling(logits=logits, requests=reqs, repetition_cache=lm_inputs["repetition_cache"])
+    asyncio.run(task)
+    return raw, ids
+
+
+class _NoisePatch:
+    """Serve NoiseBlock's torch.randn((B,1,T), device=, dtype=) from a seeded CPU generator."""
+
+    def __init__(self, seed):
+        self.gen = torch.Generator().manual_seed(seed)
+        self.log = []
+
+    def __enter__(self):
+        self._orig = torch.randn
+
+        def fake(*size, **kw):
+            shape = size[0] if len(size) == 1 and isinstance(size[0], (tuple, list)) else size
+            t = self._orig(tuple(shape), generator=self.gen)
+            self.log.append(t)
+            return t.to(kw.get("dtype", torch.float32))
+
+        torch.randn = fake
+        return self
+
+    def __exit__(self, *a):
+        torch.randn = self._orig
+
+
+# ------------------------------------------------------------------------------------------
+def golden_sampler(ref):
+    g = torch.Generator().manual_seed(11)
+    S = ref.sampling.Sampler
+    out = {}
+    B, V = 5, 97
+    logits = (torch.randn(B, 1, V, generator=g) * 3).to(torch.bfloat16)
+    cache = torch.rand(B, 1, 1, V, generator=g) < 0.3
+    out["pen_logits"], out["pen_cache"] = logits.float().numpy(), cache.numpy()
+    out["pen_out"] = S.apply_repetition_penalty(logits, cache, 1.3).float().numpy()
+    ids = torch.argmax(torch.from_numpy(out["pen_out"]), -1)
+    out["greedy_ids"] = S.run_sampling(torch.from_numpy(out["pen_out"]).to(torch.bfloat16).view(-1, V),
+                                       ref.sampling.SamplingConfig(greedy=True)).numpy()
+    c2 = cache.clone()
+    S.update_repetition_penalty_cache(c2, ids, -1)
+    out["upd_global_ids"], out["upd_global_out"] = ids.numpy(), c2.numpy()
+    # windowed, multi-codebook
+    W, C = 3, 2
+    cw = torch.rand(B, W, C, V, generator=g) < 0.2
+    idw = torch.randint(0, V, (B, C), generator=g)
+    out["upd_win_in"], out["upd_win_ids"] = cw.numpy(), idw.numpy()
+    c3 = cw.clone()
+    S.update_repetition_penalty_cache(c3, idw, W)
+    out["upd_win_out"] = c3.numpy()
+    lw = (torch.randn(B, C, V, generator=g) * 3).to(torch.bfloat16)
+    out["pen_win_logits"] = lw.float().numpy()
+    out["pen_win_out"] = S.apply_repetition_penalty(lw, cw, 1.7).float().numpy()
+    # codebook-0-only logits against a multi-codebook cache (sampling.py:140-141, 167-175)
+    l0 = lw[:, :1]
+    out["pen_cb0_out"] = S.apply_repetition_penalty(l0, cw, 1.7).float().numpy()
+    c4 = cw.clone()
+    S.update_repetition_penalty_cache(c4, idw[:, :1], W)
+    out["upd_cb0_win_out"] = c4.numpy()
+    c5 = cw.clone()
+    S.update_repetition_penalty_cache(c5, idw[:, :1], -1)
+    out["upd_cb0_global_out"] = c5.numpy()
+    np.savez_compressed(os.path.join(OUT, "sampler.npz"), **out)
+    print("sampler.npz", {k: v.shape for k, v in out.items()})
+
+
+def golden_snac(ref):
+    for tag, cfg, B in (("tiny", osnac.SnacConfig.tiny(), 3), ("24khz", osnac.SnacConfig(), 2)):
+        sd = osnac.synth_state_dict(cfg, seed=5)
+        m = ref.snac.SNAC(
+            sampling_rate=cfg.sampling_rate, encoder_dim=cfg.encoder_dim, encoder_rates=list(cfg.encoder_rates),
+            decoder_dim=cfg.decoder_dim, decoder_rates=list(cfg.decoder_rates), attn_window_size=None,
+            codebook_size=cfg.codebook_size, codebook_dim=cfg.codebook_dim, vq_strides=list(cfg.vq_strides),
+            noise=True, depthwise=True).eval()
+        r = m.load_state_dict(sd, strict=False)
+        assert not r.unexpected_keys
+        g = torch.Generator().manual_seed(6)
+        nf = 4
+        codes = [torch.randint(0, cfg.codebook_size, (B, nf * cfg.vq_strides[0] // s), generator=g)
+                 for s in cfg.vq_strides]
+        with _NoisePatch(77) as npatch, torch.inference_mode():
+            wav = m.decode(codes)
+        d = {f"codes{i}": c.numpy() for i, c in enumerate(codes)}
+        d.update({f"noise{i}": n.numpy() for i, n in enumerate(npatch.log)})
+        d["wav"] = wav.numpy()
+        np.savez_compressed(os.path.join(OUT, f"snac_{tag}.npz"), **d)
+        print(f"snac_{tag}.npz", wav.shape, float(wav.abs().mean()), float(wav.abs().max()))
+
+
+def golden_orpheus_e2e(ref):
+    """Tiny Orpheus through the reference's scheduler-selection + worker + adapter code.
+
+    5 requests with ragged prompts (one exactly a page, one crossing a page boundary mid-decode),
+    page_size 16, greedy + repetition penalty 1.3 / window -1 (the parity configuration,
+    model/__init__.py:140-156), stop id masked so lengths are fixed, then windows 28/21 -> SNAC."""
+    dims = oorph.OrpheusDims.tiny()
+    dims.max_tokens = 75
+    weights = oorph.synth_weights(dims, seed=3)
+    snac_cfg = osnac.SnacConfig.tiny()
+    snac_sd = osnac.synth_state_dict(snac_cfg, seed=5)
+    cfg = ref.sampling.SamplingConfig(top_p=0.8, temperature=0.6, repetition_penalty=1.3, repetition_window=-1,
+                                      greedy=True, max_tokens=dims.max_tokens)
+    model = build_ref_orpheus(ref, dims, weights, snac_cfg, snac_sd, cfg)
+    page_size, max_pages, max_bs = 16, 64, 4
+    worker = build_ref_worker(ref, model, page_size, max_pages, max_bs)
+
+    sched = object.__new__(ref.sched_base.Scheduler)
+    sched.model_worker, sched.max_batch_size, sched.active_requests = worker, max_bs, []
+
+    g = torch.Generator().manual_seed(21)
+    prompt_lens = [5, 16, 30, 9, 33]
+    prompts = [torch.randint(10, dims.vocab_size, (n,), generator=g).tolist() for n in prompt_lens]
+    arrivals = {0: [0, 1], 2: [2], 3: [3], 30: [4]}      # step -> request indices joining
+    reqs = [ref.requests.Request(request_id=f"r{i}", prompt=p) for i, p in enumerate(prompts)]
+    for r, n in zip(reqs, prompt_lens):
+        r.input_length = n
+
+    schedule, logits_log, audio = [], [], {r.request_id: [] for r in reqs}
+    step = 0
+    with _NoisePatch(1234), torch.inference_mode():
+        while True:
+            for i in arrivals.get(step, []):
+                sched.active_requests.append(reqs[i])
+            sched.active_requests = [r for r in sched.active_requests if not r.done_all]
+            if not sched.active_requests and step > max(arrivals):
+                break
+            det = sched._select_detokenize_requests()
+            lm = sched._select_lm_requests()
+            lm_inputs = worker.prepare_lm_inputs(lm, det)
+            ref.worker_base.ModelWorker.run_detokenize(worker, det)
+            for r in det:
+                while not r.output_audio.empty():
+                    audio[r.request_id].append(np.frombuffer(r.output_audio.get(), dtype=np.int16))
+                if r.done_all:
+                    worker.free_kv_cache(r)
+            res = ref_lm_step(ref, worker, lm, lm_inputs, stop_mask_id=dims.stop_token_id)
+            schedule.append([int(r.request_id[1:]) for r in lm])
+            if res is not None and step < 12:
+                logits_log.append(res[0][:, 0].float().numpy())
+            step += 1
+            assert step < 500
+
+    d = {"prompt_lens": np.array(prompt_lens), "n_steps": np.array(step)}
+    for i, p in enumerate(prompts):
+        d[f"prompt{i}"] = np.array(p)
+        d[f"tokens{i}"] = np.array([int(t[0, 0]) for t in reqs[i].lm_output_tokens])
+        d[f"audio{i}"] = np.concatenate(audio[f"r{i}"]) if audio[f"r{i}"] else np.zeros(0, np.int16)
+        d[f"audio_chunks{i}"] = np.array([len(a) for a in audio[f"r{i}"]])
+        d[f"finish{i}"] = np.array(reqs[i].finish_reason or "")
+    d["schedule"] = np.array([",".join(map(str, s)) for s in schedule])
+    for k, l in enumerate(logits_log):
+        d[f"logits_step{k}"] = l
+    d["arrival_steps"] = np.array(sorted(arrivals))
+    d["arrival_reqs"] = np.array([",".join(map(str, arrivals[s])) for s in sorted(arrivals)])
+    np.savez_compressed(os.path.join(OUT, "orpheus_tiny_e2e.npz"), **d)
+    print("orpheus_tiny_e2e.npz steps", step, {i: len(d[f'tokens{i}']) for i in range(len(prompts))},
+          {i: d[f'audio{i}'].shape for i in range(len(prompts))})
+    # margins: how robust is the greedy argmax on these weights?
+    tops = [np.sort(l, axis=-1)[:, -2:] for l in logits_log]
+    print("min top1-top2 margin over logged steps:", min(float((t[:, 1] - t[:, 0]).min()) for t in tops))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    ref = import_reference()
+    orig_sync = torch.cuda.synchronize
+    torch.cuda.synchronize = lambda *a, **k: None
+    try:
+        golden_sampler(ref)
+        golden_snac(ref)
+        golden_orpheus_e2e(ref)
+    finally:
+        torch.cuda.synchronize = orig_sync
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,97 @@
+"""The CPU oracle (oracle/*.py restatements) held to the golden vectors that
+oracle/gen_golden.py produced by running the reference's own code (tests/golden/*.npz)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import orpheus as oorph, sampler as osampler, snac as osnac, worker as oworker
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_sampler_penalty_and_greedy(golden_dir):
+    g = _load(golden_dir, "sampler.npz")
+    logits = torch.from_numpy(g["pen_logits"]).to(torch.bfloat16)
+    cache = torch.from_numpy(g["pen_cache"])
+    out = osampler.apply_repetition_penalty(logits, cache, 1.3)
+    assert np.array_equal(out.float().numpy(), g["pen_out"])
+    ids = osampler.greedy(out.view(-1, out.shape[-1]))
+    assert np.array_equal(ids.numpy(), g["greedy_ids"])
+
+
+def test_sampler_cache_update_global_marks_batch_union(golden_dir):
+    g = _load(golden_dir, "sampler.npz")
+    cache = torch.from_numpy(g["pen_cache"]).clone()
+    ids = torch.from_numpy(g["upd_global_ids"])
+    osampler.update_repetition_cache(cache, ids, -1)
+    assert np.array_equal(cache.numpy(), g["upd_global_out"])
+    # the quirk itself: every row carries every row's id
+    for b in range(cache.shape[0]):
+        assert cache[b, 0, 0, ids[:, 0]].all()
+
+
+def test_sampler_windowed_multicodebook(golden_dir):
+    g = _load(golden_dir, "sampler.npz")
+    cw = torch.from_numpy(g["upd_win_in"])
+    idw = torch.from_numpy(g["upd_win_ids"])
+    c = cw.clone()
+    osampler.update_repetition_cache(c, idw, 3)
+    assert np.array_equal(c.numpy(), g["upd_win_out"])
+    lw = torch.from_numpy(g["pen_win_logits"]).to(torch.bfloat16)
+    assert np.array_equal(osampler.apply_repetition_penalty(lw, cw, 1.7).float().numpy(), g["pen_win_out"])
+    assert np.array_equal(osampler.apply_repetition_penalty(lw[:, :1], cw, 1.7).float().numpy(), g["pen_cb0_out"])
+    c = cw.clone()
+    osampler.update_repetition_cache(c, idw[:, :1], 3)
+    assert np.array_equal(c.numpy(), g["upd_cb0_win_out"])
+    c = cw.clone()
+    osampler.update_repetition_cache(c, idw[:, :1], -1)
+    assert np.array_equal(c.numpy(), g["upd_cb0_global_out"])
+
+
+@pytest.mark.parametrize("tag,cfg", [("tiny", osnac.SnacConfig.tiny()), ("24khz", osnac.SnacConfig())])
+def test_snac_decode(golden_dir, tag, cfg):
+    g = _load(golden_dir, f"snac_{tag}.npz")
+    sd = osnac.synth_state_dict(cfg, seed=5)
+    codes = [torch.from_numpy(g[f"codes{i}"]) for i in range(3)]
+    noises = [torch.from_numpy(g[f"noise{i}"]) for i in range(4)]
+    wav = osnac.decode(sd, cfg, codes, noises).numpy()
+    assert wav.shape == g["wav"].shape
+    np.testing.assert_allclose(wav, g["wav"], atol=2e-5, rtol=0)
+
+
+def test_orpheus_tiny_end_to_end(golden_dir):
+    g = _load(golden_dir, "orpheus_tiny_e2e.npz")
+    dims = oorph.OrpheusDims.tiny()
+    dims.max_tokens = 75
+    weights = oorph.synth_weights(dims, seed=3)
+    scfg = osnac.SnacConfig.tiny()
+    ssd = osnac.synth_state_dict(scfg, seed=5)
+    cfg = osampler.SamplingConfig(top_p=0.8, temperature=0.6, repetition_penalty=1.3, repetition_window=-1,
+                                  greedy=True, max_tokens=75)
+    w = oworker.OracleWorker(weights, dims, cfg, page_size=16, max_num_pages=64, snac_sd=ssd, snac_cfg=scfg,
+                             max_batch_size=4, noise_seed=1234, ignore_stop=True)
+    n_req = len(g["prompt_lens"])
+    reqs = [oworker.Req(f"r{i}", torch.from_numpy(g[f"prompt{i}"])) for i in range(n_req)]
+    arrivals = {int(s): [int(x) for x in str(r).split(",")] for s, r in zip(g["arrival_steps"], g["arrival_reqs"])}
+    active, schedule = [], []
+    for step in range(int(g["n_steps"])):
+        for i in arrivals.get(step, []):
+            active.append(reqs[i])
+        active = [r for r in active if not r.done_all]
+        lm, _ = w.step(active)
+        schedule.append(",".join(str(int(r.request_id[1:])) for r in lm))
+        if f"logits_step{step}" in g.files:
+            assert np.array_equal(w.last_logits[:, 0].float().numpy(), g[f"logits_step{step}"]), step
+    assert schedule == list(g["schedule"])
+    for i, r in enumerate(reqs):
+        assert r.lm_output_tokens == g[f"tokens{i}"].tolist(), i
+        assert r.finish_reason == str(g[f"finish{i}"])
+        audio = np.concatenate([np.frombuffer(b, dtype=np.int16) for b in r.output_audio])
+        assert [len(b) // 2 for b in r.output_audio] == g[f"audio_chunks{i}"].tolist()
+        assert audio.shape == g[f"audio{i}"].shape
+        diff = np.abs(audio.astype(np.int32) - g[f"audio{i}"].astype(np.int32))
+        assert diff.max() <= 1, (i, diff.max())
