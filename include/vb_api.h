@@ -1,0 +1,173 @@
+/*
+ * vb_api.h -- C ABI of libvoxb200.so: the B200 (sm_100a) kernels behind VoxServe's operator boundary
+ * (level b4).
+ *
+ * Conventions
+ *   - every pointer named d_* / *_dev is a DEVICE pointer; tensors are dense row-major unless a stride
+ *     is passed; bf16 = 2-byte bfloat16; ids / page tables are int32 unless stated.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued, nothing synchronises, nothing
+ *     allocates: scratch comes from the caller (`*_workspace_bytes` queries), so every entry point is
+ *     CUDA-graph capturable and re-entrant (no global mutable state except the thread-local error text).
+ *   - return 0 on success, <0 on error; vb_last_error() returns the thread-local message.
+ *   - tensor maps: TMA descriptors are 128-byte opaque blobs encoded on the host by vb_tensor_map_*
+ *     into caller memory (64-byte aligned) and passed back by pointer; the library keeps no copy.
+ *
+ * Each group cites the reference interface it replaces (paths relative to the vox-serve tree).
+ */
+#ifndef VB_API_H_
+#define VB_API_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB_TENSOR_MAP_BYTES 128
+
+const char* vb_last_error(void);
+int vb_version(void);
+/* SM count / max dynamic smem of the current device (host query used to size persistent grids). */
+int vb_device_info(int* sm_count, int* max_smem_optin);
+
+/* ---- TMA descriptors ------------------------------------------------------------------------ */
+/* Whole paged KV cache  [n_slabs = layers*pages][2][page_size][n_kv_heads][head_dim] bf16
+ * (layout of vox_serve/worker/base.py:170-179).  Box = [box_tokens x 64 dims] of one head, 128B swizzle. */
+int vb_tensor_map_kv(void* out_map, const void* d_kv, int64_t n_slabs, int page_size, int n_kv_heads,
+                     int head_dim, int box_tokens);
+/* Row-major [rows][cols] bf16 matrix with leading dimension ld (elements); box = [box_rows x 64], 128B swizzle.
+ * Used for GEMM weights (nn.Linear.weight, [out_features][in_features]) and activations. */
+int vb_tensor_map_2d_bf16(void* out_map, const void* d_base, int64_t rows, int64_t cols, int64_t ld,
+                          int box_rows);
+
+/* ---- RMSNorm: vox_serve/flashinfer_utils.py:251-267 ------------------------------------------ */
+int vb_rmsnorm(void* d_out, const void* d_x, const void* d_weight, int rows, int dim, float eps, void* stream);
+
+/* ---- RoPE at position ids: vox_serve/flashinfer_utils.py:270-324 ------------------------------
+ * q [T][n_q][D], k [T][n_kv][D] bf16 -> q_out/k_out (may alias inputs).  d_freq[rotary_dim] is the
+ * per-element frequency table; vb_rope_freqs fills it (llama31 != 0 selects the Llama-3.1 smoothing with
+ * low/high_freq_factor, old_context_len; interleave selects pairwise (2j,2j+1) rotation). */
+int vb_rope_freqs(float* d_freq, int rotary_dim, int interleave, float rope_scale, float rope_theta, int llama31,
+                  float low_freq_factor, float high_freq_factor, float old_context_len, void* stream);
+int vb_rope(void* d_q_out, void* d_k_out, const void* d_q, const void* d_k, const int32_t* d_pos,
+            const float* d_freq, int T, int n_q, int n_kv, int head_dim, int rotary_dim, int interleave,
+            void* stream);
+
+/* ---- paged KV bookkeeping: flashinfer_utils.py:86-124 (prefill), :217-225 (decode) -----------
+ * Device-side "plan": from the page table (indptr [B+1], indices, last_page_len [B]) and, for prefill,
+ * qo_indptr [B+1], derive per query row: owning request, visible kv length, (page, slot) of its new
+ * K/V entry; plus the exclusive prefix of 64-token (or page-sized) attention chunks per row.
+ * qo_indptr == NULL means decode (one row per request).  Rows >= n_rows_valid up to n_rows_padded get
+ * page = -1 (their K/V append is skipped; the reference scatters them into page -1).
+ * Outputs (device int32): row_req[R], row_kvlen[R], row_page[R], row_slot[R], row_chunk_start[R+1]. */
+int vb_plan_rows(const int32_t* d_qo_indptr, const int32_t* d_kv_indptr, const int32_t* d_kv_indices,
+                 const int32_t* d_last_page_len, int n_req, int n_rows_padded, int page_size, int chunk_tokens,
+                 int32_t* d_row_req, int32_t* d_row_kvlen, int32_t* d_row_page, int32_t* d_row_slot,
+                 int32_t* d_row_chunk_start, void* stream);
+
+/* kv[page][0][slot] = k ; kv[page][1][slot] = v : flashinfer_utils.py:144-145, 243-244.
+ * d_layer_kv points at one layer's [pages][2][page_size][n_kv][D]. */
+int vb_kv_append(void* d_layer_kv, const void* d_k, const void* d_v, const int32_t* d_row_page,
+                 const int32_t* d_row_slot, int T, int page_size, int n_kv, int head_dim, void* stream);
+
+/* ---- paged attention: FlashInferDecodeWrapper.run / FlashInferPrefillWrapper.run
+ * (flashinfer_utils.py:132, 228-230).  One query row per entry of the plan; causal by construction
+ * (row_kvlen).  q/out [R][n_q][D] bf16.  kv_map from vb_tensor_map_kv over the WHOLE cache;
+ * slab_base = layer * pages_per_layer.  max_chunks_total bounds row_chunk_start[n_rows] (sizes the
+ * split-KV partials).  d_workspace: vb_paged_attn_workspace_bytes(); it must be zero-filled once before
+ * first use (arrival counters; the kernel restores them to zero).  grid_ctas: persistent grid size. */
+size_t vb_paged_attn_workspace_bytes(int max_rows, int max_chunks_total, int n_q, int n_kv, int head_dim);
+int vb_paged_attn(void* d_out, const void* d_q, const void* kv_map, int64_t slab_base,
+                  const int32_t* d_kv_indptr, const int32_t* d_kv_indices, const int32_t* d_row_req,
+                  const int32_t* d_row_kvlen, const int32_t* d_row_chunk_start, int n_rows, int max_chunks_total,
+                  int n_q, int n_kv, int head_dim, int page_size, int chunk_tokens, float sm_scale,
+                  void* d_workspace, size_t workspace_bytes, int grid_ctas, void* stream);
+
+/* ---- dense projections (nn.Linear, bias-free): model/orpheus.py:41-47, 68-79, 197 -------------
+ * Y[T][N] = X[T][K] * W[N][K]^T on tcgen05 (weights are the 128-row MMA operand, tokens the N side).
+ * w_map: vb_tensor_map_2d_bf16(W, N, K, ldw, 128);  x_map: vb_tensor_map_2d_bf16(X, T, K, ldx, t_tile)
+ * with t_tile = vb_gemm_t_tile(T).
+ * mode 0: Y bf16 [T][ldy]           (split_k must be 1)
+ * mode 1: Y fp32 partials [split_k][T][ldy]   (consumers below sum them in split order)
+ * mode 2: W rows interleaved per 128-tile as 64 gate rows then 64 up rows; Y bf16 [T][ldy] holds
+ *         silu(gate)*up with the reference's bf16 rounding points (orpheus.py:46-48), N_out = N/2. */
+int vb_gemm_t_tile(int T);
+int vb_gemm_bf16(void* d_y, const void* w_map, const void* x_map, int T, int N, int K, int ldy, int mode,
+                 int split_k, void* stream);
+
+/* sum split-K partials -> bf16 Linear output; + residual; then RMSNorm of the new hidden state:
+ * orpheus.py:125-151 (residual adds, next layer's input_layernorm / post_attention_layernorm).
+ * hidden_out = bf16(residual + bf16(sum_s partial[s])) ; normed_out = rmsnorm(hidden_out) * weight.
+ * d_residual may be NULL (no add); d_norm_weight may be NULL (skip the norm output). */
+int vb_reduce_residual_rmsnorm(void* d_hidden_out, void* d_normed_out, const float* d_partials, int split_k,
+                               const void* d_residual, const void* d_norm_weight, int T, int N, float eps,
+                               void* stream);
+/* fused tail of the QKV projection: sum partials -> bf16 q|k|v, RoPE(q,k), write q, scatter k,v into the
+ * layer cache (orpheus.py:91-106 + flashinfer_utils.py:243-244).  partials [split_k][T][(n_q+2 n_kv) D]. */
+int vb_qkv_rope_append(void* d_q_out, void* d_layer_kv, const float* d_partials, int split_k, const int32_t* d_pos,
+                       const float* d_freq, const int32_t* d_row_page, const int32_t* d_row_slot, int T, int n_q,
+                       int n_kv, int head_dim, int page_size, int rotary_dim, int interleave, void* stream);
+/* embedding gather: orpheus.py:408 */
+int vb_embedding(void* d_out, const void* d_table, const int32_t* d_ids, int T, int dim, int vocab, void* stream);
+/* rows out[i] = in[idx[i]] (last-token gather, cuda_graph_worker.py:900-902) */
+int vb_gather_rows(void* d_out, const void* d_in, const int32_t* d_idx, int n, int row_bytes, void* stream);
+
+/* ---- sampler: vox_serve/sampling.py (whole file) ---------------------------------------------
+ * logits [rows][vocab] bf16 with leading dimension ld_logits, rows = batch * logit_codebooks.
+ * d_rep_cache: uint8 (torch.bool) repetition cache [batch][rep_window_slots][rep_codebooks][vocab] or NULL;
+ * a token is "seen" if any window slot has it (sampling.py:137); if logit_codebooks == 1 and
+ * rep_codebooks != 1 codebook 0 is used (sampling.py:140-141).  Penalty: sampling.py:143-144.
+ * strategy: 0 greedy (argmax, first index on ties), 1 top-k, 2 top-p, 3 top-k then top-p, 4 min-p
+ * (dispatch order of sampling.py:97-118 is applied by the host wrapper).  out_ids int64.
+ * Draws use Philox4x32-10(seed, offset, row).  mask_token >= 0 forces that token's logit to -inf
+ * (benchmark hook to pin sequence lengths; -1 = off).  Workspace: vb_sample_workspace_bytes. */
+size_t vb_sample_workspace_bytes(int rows, int vocab);
+int vb_sample(int64_t* d_out_ids, const void* d_logits, int rows, int vocab, int ld_logits,
+              const uint8_t* d_rep_cache, int rep_window_slots, int rep_codebooks, int logit_codebooks,
+              float penalty, int strategy, int top_k, float top_p, float min_p, float temperature, uint64_t seed,
+              uint64_t offset, int mask_token, void* d_workspace, size_t workspace_bytes, void* stream);
+/* penalised logits only (Sampler.apply_repetition_penalty, sampling.py:120-146), bf16 in/out, dense rows */
+int vb_apply_repetition_penalty(void* d_out, const void* d_logits, const uint8_t* d_rep_cache,
+                                int rep_window_slots, int rep_codebooks, int logit_codebooks, float penalty,
+                                int rows, int vocab, void* stream);
+/* cache[b][w][c][ids] = 1 with the reference's batch-union semantics (sampling.py:148-178).
+ * cache uint8 [B][W][C][V]; ids int64 [B][C_ids]; window > 1 shifts the window first. */
+int vb_update_repetition_cache(uint8_t* d_cache, const int64_t* d_ids, int B, int W, int C, int V, int C_ids,
+                               int window, void* stream);
+
+/* ---- SNAC decoder: vox_serve/tokenizer/snac.py:119-267, 297-357, 438-441 ----------------------
+ * fp32, activations [B][C][T] (T contiguous).  Weights arrive weight-norm-folded (snac.py:244-249) --
+ * see vox_serve_b200/tokenizer/snac.py for the fold / repack done once at load.  Every Snake (snac.py:252-258)
+ * is fused into a neighbouring stage through the optional alpha_in / alpha_out [C] pointers. */
+int vb_snac_from_codes(float* d_z, const int32_t* d_codes0, const int32_t* d_codes1, const int32_t* d_codes2,
+                       const float* d_codebooks /*[3][cb_size][cb_dim]*/, const float* d_proj_w /*[3][C][cb_dim]*/,
+                       const float* d_proj_b /*[3][C]*/, int B, int C, int T, int cb_size, int cb_dim, int stride0,
+                       int stride1, int stride2, void* stream);
+/* y = snake_out?( dwconv_k7_dilated( snake_in?(x) ) + bias );  w [C][7] */
+int vb_snac_dwconv7(float* d_y, const float* d_x, const float* d_w, const float* d_bias, const float* d_alpha_in,
+                    const float* d_alpha_out, int B, int C, int T, int dilation, void* stream);
+/* pointwise conv  v = sum_ci W[co][ci] x[b][ci][t] (+ bias[co]);
+ * epilogue 0: v ; 1: v + resid[b][co][t] (ResidualUnit, snac.py:170-176) ; 2: x[b][co][t] + noise[b][t] * v
+ * (NoiseBlock, snac.py:206-212, noise supplied by the caller) ; then snake_out?(.) */
+int vb_snac_pwconv(float* d_y, const float* d_x, const float* d_w /*[Cout][Cin]*/, const float* d_bias,
+                   const float* d_resid, const float* d_noise, const float* d_alpha_out, int epilogue, int B,
+                   int Cin, int Cout, int T, void* stream);
+/* y = snake_out?( conv_transpose1d(x) + bias ), kernel 2*stride, padding ceil(stride/2), output_padding
+ * stride%2 (snac.py:222-231); d_w_packed [stride][Cout][2*Cin] with
+ * w_packed[r][co][tap*Cin + ci] = W_torch[ci][co][r + tap*stride];  y [B][Cout][T*stride] */
+int vb_snac_convtr(float* d_y, const float* d_x, const float* d_w_packed, const float* d_bias,
+                   const float* d_alpha_out, int B, int Cin, int Cout, int T, int stride, void* stream);
+/* y[b][t - t0] = tanh(conv_k7(snake_in?(x))[t] + bias), Cout = 1 (snac.py:152-156), t in [t0, t1) */
+int vb_snac_final(float* d_y, const float* d_x, const float* d_w /*[C][7]*/, const float* d_bias,
+                  const float* d_alpha_in, int B, int C, int T, int t0, int t1, void* stream);
+/* (audio * 32767) truncated toward zero to int16, no clipping: cuda_graph_worker.py:1252-1253 */
+int vb_pcm16(int16_t* d_out, const float* d_audio, int64_t n, void* stream);
+/* LM ids [B][28] -> SNAC codes (orpheus.py:479-500): codes0 [B][4], codes1 [B][8], codes2 [B][16] int32 */
+int vb_orpheus_window_codes(int32_t* d_c0, int32_t* d_c1, int32_t* d_c2, const int64_t* d_ids, int B,
+                            int audio_id_base, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VB_API_H_ */

@@ -1,0 +1,402 @@
+"""Parity of every C-ABI kernel against the CPU oracle (same seeded inputs).  Runs on the B200 box:
+    python -m pytest tests -m gpu -q
+Integer / index / byte results must match exactly; bf16 results to within the stated ulp budget."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lm_ops, sampler as osampler, snac as osnac, orpheus as oorph
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from vox_serve_b200 import ops as _ops
+
+    return _ops
+
+
+def g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def bf16_ulp_diff(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """distance in bf16 code space (sign-magnitude aware)"""
+    def key(x):
+        i = x.contiguous().view(torch.int16).to(torch.int32) & 0xFFFF
+        return torch.where(i >= 0x8000, 0x8000 - i, i)
+    return (key(a.cpu()) - key(b.cpu())).abs()
+
+
+def assert_bf16_close(got, ref, max_ulp=1, max_frac=2e-3, what=""):
+    d = bf16_ulp_diff(got, ref)
+    frac = (d > 0).float().mean().item()
+    assert d.max().item() <= max_ulp, f"{what}: max ulp {d.max().item()} (frac differing {frac:.2e})"
+    assert frac <= max_frac, f"{what}: {frac:.2e} of elements differ"
+
+
+# --------------------------------------------------------------------------------------------
+def test_rmsnorm(ops):
+    for rows, dim, seed in ((32, 3072, 1), (5, 768, 2), (1, 8192, 3), (133, 896, 4)):
+        x = (torch.randn(rows, dim, generator=g(seed)) * 2).to(BF)
+        w = (1 + 0.1 * torch.randn(dim, generator=g(seed + 10))).to(BF)
+        ref = lm_ops.rms_norm(x, w, 1e-5)
+        got = ops.rmsnorm(x.cuda(), w.cuda(), 1e-5)
+        assert_bf16_close(got, ref, 1, 2e-3, f"rmsnorm {rows}x{dim}")
+
+
+@pytest.mark.parametrize("variant", ["llama31", "plain", "interleave_partial"])
+def test_rope(ops, variant):
+    T, hq, hkv, D = 37, 6, 2, 128
+    q = torch.randn(T, hq, D, generator=g(5)).to(BF)
+    k = torch.randn(T, hkv, D, generator=g(6)).to(BF)
+    pos = torch.randint(0, 1400, (T,), generator=g(7), dtype=torch.int32)
+    if variant == "llama31":
+        kw = dict(rope_scale=32.0, rope_theta=500000.0, low_freq_factor=1.0, high_freq_factor=4.0, old_context_len=8192)
+        inter, rd = False, D
+    elif variant == "plain":
+        kw = dict(rope_scale=1.0, rope_theta=10000.0)
+        inter, rd = False, D
+    else:
+        kw = dict(rope_scale=1.0, rope_theta=10000.0)
+        inter, rd = True, 64
+    rq, rk = lm_ops.apply_rope_pos_ids(q, k, pos, interleave=inter, rotary_dim=rd, **kw)
+    freq = ops.rope_freq_table(rd, kw["rope_scale"], kw["rope_theta"], inter, kw.get("low_freq_factor"),
+                               kw.get("high_freq_factor"), kw.get("old_context_len"))
+    ref_freq = lm_ops.rope_freqs(rd, kw["rope_scale"], kw["rope_theta"], inter, kw.get("low_freq_factor"),
+                                 kw.get("high_freq_factor"), kw.get("old_context_len"))
+    np.testing.assert_allclose(freq.cpu().numpy(), ref_freq.numpy(), rtol=2e-6)
+    gq, gk = ops.rope(q.cuda(), k.cuda(), pos.cuda(), freq, interleave=inter)
+    # angles reach ~1400 rad: fp32 pos*freq products differ in the last ulp between powf implementations
+    assert_bf16_close(gq, rq, 2, 2e-2, "rope q")
+    assert_bf16_close(gk, rk, 2, 2e-2, "rope k")
+    q2, k2 = q.cuda().clone(), k.cuda().clone()
+    ops.rope(q2, k2, pos.cuda(), freq, interleave=inter, inplace=True)
+    assert torch.equal(q2, gq) and torch.equal(k2, gk)
+
+
+def _random_page_table(kv_lens, page_size, n_pages, seed):
+    perm = torch.randperm(n_pages, generator=g(seed)).tolist()
+    indptr, indices, last = [0], [], []
+    for L in kv_lens:
+        n = (L + page_size - 1) // page_size
+        indices += [perm.pop() for _ in range(n)]
+        indptr.append(len(indices))
+        last.append(L - (n - 1) * page_size)
+    return indptr, indices, last
+
+
+def _i32(x):
+    return torch.tensor(x, dtype=torch.int32, device="cuda")
+
+
+def test_plan_rows_and_append(ops):
+    page_size, n_pages, hkv, D = 16, 64, 2, 128
+    # decode
+    kv_lens = [1, 16, 17, 33, 48, 5]
+    indptr, indices, last = _random_page_table(kv_lens, page_size, n_pages, 3)
+    plan = ops.RowPlan(64, "cuda")
+    ops.plan_rows(plan, None, _i32(indptr), _i32(indices), _i32(last), len(kv_lens), 8, page_size, 16)
+    pages, slots = lm_ops.decode_slots(indptr, indices, last)
+    n = len(kv_lens)
+    assert plan.row_page[:n].tolist() == pages and plan.row_slot[:n].tolist() == slots
+    assert plan.row_kvlen[:n].tolist() == kv_lens and plan.row_req[:n].tolist() == list(range(n))
+    assert plan.row_page[n:8].tolist() == [-1, -1] and plan.row_kvlen[n:8].tolist() == [0, 0]
+    chunks = [(L + 15) // 16 for L in kv_lens] + [0, 0]
+    assert plan.row_chunk_start[:9].tolist() == [0] + list(np.cumsum(chunks))
+    cache = torch.zeros(n_pages, 2, page_size, hkv, D, dtype=BF)
+    k = torch.randn(8, hkv, D, generator=g(1)).to(BF)
+    v = torch.randn(8, hkv, D, generator=g(2)).to(BF)
+    ref = cache.clone()
+    lm_ops.kv_append(ref, k[:n], v[:n], pages, slots)
+    dc = cache.cuda()
+    ops.kv_append(dc, k.cuda(), v.cuda(), plan, 8)
+    assert torch.equal(dc.cpu(), ref)
+    # prefill (ragged, one request continuing an existing context)
+    qo = [0, 5, 5 + 20, 5 + 20 + 1]
+    kv_lens = [5, 36, 40]
+    indptr, indices, last = _random_page_table(kv_lens, page_size, n_pages, 4)
+    plan2 = ops.RowPlan(2048, "cuda")
+    ops.plan_rows(plan2, _i32(qo), _i32(indptr), _i32(indices), _i32(last), 3, 40, page_size, 16)
+    pages, slots = lm_ops.prefill_slots(qo, indptr, indices, last, page_size)
+    T = qo[-1]
+    assert plan2.row_page[:T].tolist() == pages and plan2.row_slot[:T].tolist() == slots
+    exp_kvlen = [j + 1 for j in range(5)] + [36 - 20 + j + 1 for j in range(20)] + [40]
+    assert plan2.row_kvlen[:T].tolist() == exp_kvlen
+    assert plan2.row_page[T:40].tolist() == [-1] * (40 - T)
+    # > 1024 rows exercises the multi-sweep scan
+    qo = [0, 1500]
+    indptr, indices, last = _random_page_table([1500], 128, 64, 5)
+    ops.plan_rows(plan2, _i32(qo), _i32(indptr), _i32(indices), _i32(last), 1, 1500, 128, 64)
+    cs = plan2.row_chunk_start[:1501].cpu().numpy()
+    exp = np.concatenate([[0], np.cumsum([(j + 1 + 63) // 64 for j in range(1500)])])
+    assert np.array_equal(cs, exp)
+
+
+def _attn_case(ops, kv_lens, page_size, hq, hkv, D, seed, prefill_new=None, n_pages=None):
+    n_pages = n_pages or (sum((L + page_size - 1) // page_size for L in kv_lens) + 3)
+    indptr, indices, last = _random_page_table(kv_lens, page_size, n_pages, seed)
+    L_layers, layer = 2, 1
+    cache = (torch.randn(L_layers, n_pages, 2, page_size, hkv, D, generator=g(seed + 1)) * 1.0).to(BF)
+    chunk = ops.attn_chunk_tokens(page_size)
+    if prefill_new is None:
+        R = len(kv_lens)
+        qo = None
+        q = torch.randn(R, hq, D, generator=g(seed + 2)).to(BF)
+        ref = lm_ops.paged_attention_decode(q, cache[layer], indptr, indices, last, page_size)
+    else:
+        qo = [0] + list(np.cumsum(prefill_new))
+        R = qo[-1]
+        q = torch.randn(R, hq, D, generator=g(seed + 2)).to(BF)
+        ref = lm_ops.paged_attention_prefill(q, cache[layer], qo, indptr, indices, last, page_size)
+    dcache = cache.cuda()
+    kv_map = ops.tensor_map_kv(dcache, chunk)
+    plan = ops.RowPlan(max(R, 8), "cuda")
+    d_indptr, d_indices = _i32(indptr), _i32(indices)
+    ops.plan_rows(plan, None if qo is None else _i32(qo), d_indptr, d_indices, _i32(last), len(kv_lens), R,
+                  page_size, chunk)
+    max_chunks = int(plan.row_chunk_start[R].item())
+    ws = ops.paged_attn_workspace(R, max_chunks, hq, hkv, D, "cuda")
+    out = None
+    for _ in range(2):  # second run checks that the arrival counters were restored
+        out = ops.paged_attn(q.cuda(), kv_map, layer * n_pages, d_indptr, d_indices, plan, R, max_chunks, hkv,
+                             page_size, chunk, ws)
+    torch.cuda.synchronize()
+    got, reff = out.float().cpu(), ref.float()
+    err = (got - reff).abs()
+    scale = reff.abs().mean().item()
+    rel_l2 = (err.pow(2).sum() / reff.pow(2).sum()).sqrt().item()
+    assert rel_l2 < 8e-3, f"rel l2 {rel_l2}"
+    assert err.max().item() < 0.04 * max(scale, 1e-3) * 10, f"max err {err.max().item()} scale {scale}"
+    return rel_l2
+
+
+def test_paged_attention_decode_orpheus_shape(ops):
+    # 24 q heads / 8 kv heads / d128 / page 128: ragged lengths incl. exact page and page+1
+    kv_lens = [1, 63, 64, 65, 128, 129, 134, 300, 728, 1333, 256, 2]
+    _attn_case(ops, kv_lens, 128, 24, 8, 128, 11)
+
+
+def test_paged_attention_decode_batch32(ops):
+    kv_lens = [134 + 7 * i for i in range(32)]
+    _attn_case(ops, kv_lens, 128, 24, 8, 128, 12)
+
+
+@pytest.mark.parametrize("page_size,hq,hkv,D", [(16, 6, 2, 128), (32, 8, 2, 128), (128, 32, 2, 128),
+                                                 (128, 32, 8, 64), (16, 14, 2, 64), (64, 16, 8, 128)])
+def test_paged_attention_decode_variants(ops, page_size, hq, hkv, D):
+    kv_lens = [1, page_size - 1, page_size, page_size + 1, 3 * page_size + 5, 70]
+    _attn_case(ops, kv_lens, page_size, hq, hkv, D, 13)
+
+
+def test_paged_attention_prefill_ragged_causal(ops):
+    # request 0: fresh 133-token prompt; request 1: 1 new token on 200 cached; request 2: 40 new on 100
+    _attn_case(ops, [133, 201, 140], 128, 24, 8, 128, 14, prefill_new=[133, 1, 40])
+    _attn_case(ops, [5, 36, 40], 16, 6, 2, 128, 15, prefill_new=[5, 20, 1])
+
+
+# --------------------------------------------------------------------------------------------
+def _gemm_ref(x, w):
+    return x.float() @ w.float().t()
+
+
+@pytest.mark.parametrize("T,N,K,split", [(32, 3072, 3072, 1), (32, 5120, 3072, 3), (5, 458, 768, 1),
+                                          (1, 1024, 1024, 4), (133, 640, 768, 2), (32, 3072, 8192, 6),
+                                          (300, 384, 512, 1), (17, 130, 200, 1)])
+def test_gemm_partials(ops, T, N, K, split):
+    x = torch.randn(T, K, generator=g(T + N)).to(BF)
+    w = (torch.randn(N, K, generator=g(K)) * 0.05).to(BF)
+    ref = _gemm_ref(x, w)
+    part = ops.gemm(x.cuda(), w.cuda(), mode=1, split_k=split)
+    got = part.sum(0).cpu()
+    tol = 2e-3 * ref.abs().max().item() + 1e-4
+    assert (got - ref).abs().max().item() < tol, (got - ref).abs().max().item()
+    if split == 1:
+        y = ops.gemm(x.cuda(), w.cuda(), mode=0)
+        assert_bf16_close(y, ref.to(BF), 1, 2e-2, "gemm bf16")
+
+
+def test_gemm_lm_head_tail_tile(ops):
+    T, N, K = 32, 128 * 9 + 12, 768   # N not a multiple of 128 like the 156940-row lm_head
+    x = torch.randn(T, K, generator=g(1)).to(BF)
+    w = (torch.randn(N, K, generator=g(2)) * 0.05).to(BF)
+    y = ops.gemm(x.cuda(), w.cuda(), mode=0)
+    assert_bf16_close(y, _gemm_ref(x, w).to(BF), 1, 2e-2, "lm_head")
+
+
+def test_gemm_gate_up_silu(ops):
+    T, I, K = 32, 1024, 768
+    x = torch.randn(T, K, generator=g(3)).to(BF)
+    wg = (torch.randn(I, K, generator=g(4)) * 0.05).to(BF)
+    wu = (torch.randn(I, K, generator=g(5)) * 0.05).to(BF)
+    import torch.nn.functional as F
+
+    ref = F.silu(F.linear(x, wg)) * F.linear(x, wu)
+    wi = ops.interleave_gate_up(wg.cuda(), wu.cuda())
+    got = ops.gemm(x.cuda(), wi, mode=2)
+    assert got.shape == (T, I)
+    assert_bf16_close(got, ref, 2, 3e-2, "gate-up silu")
+
+
+def test_reduce_residual_rmsnorm(ops):
+    S, T, N = 3, 32, 3072
+    parts = torch.randn(S, T, N, generator=g(6))
+    resid = torch.randn(T, N, generator=g(7)).to(BF)
+    w = (1 + 0.1 * torch.randn(N, generator=g(8))).to(BF)
+    lin = (parts[0] + parts[1] + parts[2]).to(BF)
+    h_ref = resid + lin
+    n_ref = lm_ops.rms_norm(h_ref, w, 1e-5)
+    h, n = ops.reduce_residual_rmsnorm(parts.cuda(), resid.cuda(), w.cuda(), 1e-5)
+    assert torch.equal(h.cpu(), h_ref)
+    assert_bf16_close(n, n_ref, 1, 2e-3, "fused norm")
+    h2, n2 = ops.reduce_residual_rmsnorm(parts.cuda(), None, None, 1e-5)
+    assert torch.equal(h2.cpu(), lin) and n2 is None
+
+
+def test_qkv_rope_append(ops):
+    S, T, hq, hkv, D, page_size, n_pages = 2, 6, 6, 2, 128, 16, 32
+    W = (hq + 2 * hkv) * D
+    parts = torch.randn(S, T, W, generator=g(9))
+    qkv = (parts[0] + parts[1]).to(BF)
+    q, k, v = qkv[:, : hq * D].view(T, hq, D), qkv[:, hq * D:(hq + hkv) * D].view(T, hkv, D), \
+        qkv[:, (hq + hkv) * D:].view(T, hkv, D)
+    kv_lens = [3, 16, 17, 33, 40, 1]
+    indptr, indices, last = _random_page_table(kv_lens, page_size, n_pages, 21)
+    pos = torch.tensor([L for L in kv_lens], dtype=torch.int32)
+    kw = dict(rope_scale=32.0, rope_theta=500000.0, low_freq_factor=1.0, high_freq_factor=4.0, old_context_len=8192)
+    rq, rk = lm_ops.apply_rope_pos_ids(q, k, pos, **kw)
+    cache = torch.zeros(n_pages, 2, page_size, hkv, D, dtype=BF)
+    pages, slots = lm_ops.decode_slots(indptr, indices, last)
+    lm_ops.kv_append(cache, rk, v, pages, slots)
+    plan = ops.RowPlan(8, "cuda")
+    ops.plan_rows(plan, None, _i32(indptr), _i32(indices), _i32(last), T, T, page_size, 16)
+    dcache = torch.zeros_like(cache).cuda()
+    freq = ops.rope_freq_table(D, 32.0, 500000.0, False, 1.0, 4.0, 8192)
+    gq = ops.qkv_rope_append(parts.cuda(), dcache, pos.cuda(), freq, plan, hq, hkv, D)
+    assert_bf16_close(gq, rq, 2, 2e-2, "fused rope q")
+    assert_bf16_close(dcache, cache, 2, 2e-2, "fused kv append")
+    # V rows are copied, not rotated: exact
+    pg, sl = torch.tensor(pages), torch.tensor(slots)
+    assert torch.equal(dcache.cpu()[pg, 1, sl], v)
+
+
+def test_embedding_gather_pcm_codes(ops):
+    table = torch.randn(500, 768, generator=g(1)).to(BF)
+    ids = torch.randint(0, 500, (33,), generator=g(2), dtype=torch.int32)
+    assert torch.equal(ops.embedding(table.cuda(), ids.cuda()).cpu(), table[ids.long()])
+    idx = torch.tensor([3, 0, 32, 7], dtype=torch.int32)
+    src = torch.randn(33, 768, generator=g(3)).to(BF)
+    assert torch.equal(ops.gather_rows(src.cuda(), idx.cuda()).cpu(), src[idx.long()])
+    audio = torch.tanh(torch.randn(3, 1, 2048, generator=g(4)) * 2)
+    ref = (audio.numpy() * 32767).astype(np.int16)
+    assert np.array_equal(ops.pcm16(audio.cuda()).cpu().numpy(), ref)
+    dims = oorph.OrpheusDims()
+    tok = torch.randint(128266, 128266 + 7 * 4096, (5, 28), generator=g(5))
+    tok[0, 3] = 128258  # a non-audio id inside a window goes through the same modulo (orpheus.py:481)
+    ref_codes = oorph.audio_codes_from_window(tok.view(5, 28, 1), dims)
+    got = ops.orpheus_window_codes(tok.cuda(), dims.audio_id_base)
+    for a, b in zip(got, ref_codes):
+        assert torch.equal(a.cpu().long(), b)
+
+
+# --------------------------------------------------------------------------------------------
+def test_sampler_golden_penalty_greedy_cache(ops, golden_dir):
+    gd = np.load(os.path.join(golden_dir, "sampler.npz"))
+    logits = torch.from_numpy(gd["pen_logits"]).to(BF)
+    cache = torch.from_numpy(gd["pen_cache"])
+    out = ops.apply_repetition_penalty(logits.cuda(), cache.cuda(), 1.3)
+    assert np.array_equal(out.float().cpu().numpy(), gd["pen_out"])
+    ids = ops.sample(logits.cuda().view(-1, logits.shape[-1]), "greedy", rep_cache=cache.cuda(), penalty=1.3)
+    assert np.array_equal(ids.cpu().numpy(), gd["greedy_ids"])
+    c = cache.clone().cuda()
+    ops.update_repetition_cache(c, torch.from_numpy(gd["upd_global_ids"]).cuda(), -1)
+    assert np.array_equal(c.cpu().numpy(), gd["upd_global_out"])
+    cw = torch.from_numpy(gd["upd_win_in"])
+    idw = torch.from_numpy(gd["upd_win_ids"])
+    c = cw.clone().cuda()
+    ops.update_repetition_cache(c, idw.cuda(), 3)
+    assert np.array_equal(c.cpu().numpy(), gd["upd_win_out"])
+    lw = torch.from_numpy(gd["pen_win_logits"]).to(BF)
+    assert np.array_equal(ops.apply_repetition_penalty(lw.cuda(), cw.cuda(), 1.7).float().cpu().numpy(),
+                          gd["pen_win_out"])
+    assert np.array_equal(ops.apply_repetition_penalty(lw[:, :1].contiguous().cuda(), cw.cuda(), 1.7)
+                          .float().cpu().numpy(), gd["pen_cb0_out"])
+    c = cw.clone().cuda()
+    ops.update_repetition_cache(c, idw[:, :1].contiguous().cuda(), 3)
+    assert np.array_equal(c.cpu().numpy(), gd["upd_cb0_win_out"])
+    c = cw.clone().cuda()
+    ops.update_repetition_cache(c, idw[:, :1].contiguous().cuda(), -1)
+    assert np.array_equal(c.cpu().numpy(), gd["upd_cb0_global_out"])
+
+
+def test_sampler_greedy_full_vocab_ties_first_index(ops):
+    B, V = 32, 156940
+    logits = (torch.randn(B, V, generator=g(9)) * 4).to(BF)
+    logits[3, 100] = logits[3].max()
+    logits[3, 150000] = logits[3].max()      # tie: first index wins
+    cache = torch.rand(B, 1, 1, V, generator=g(10)) < 0.01
+    pen = osampler.apply_repetition_penalty(logits.view(B, 1, V), cache, 1.3)
+    ref = osampler.greedy(pen.view(B, V))
+    got = ops.sample(logits.cuda(), "greedy", rep_cache=cache.cuda(), penalty=1.3)
+    assert torch.equal(got.cpu(), ref)
+    got2 = ops.sample(logits.cuda(), "greedy", mask_token=int(ref[0]))
+    assert int(got2[0]) != int(ref[0])
+
+
+@pytest.mark.parametrize("strategy,kw", [("top_p", dict(top_p=0.8, temperature=0.6)),
+                                          ("top_k", dict(top_k=50, temperature=0.9)),
+                                          ("top_k_top_p", dict(top_k=20, top_p=0.9, temperature=0.8)),
+                                          ("min_p", dict(min_p=0.1, temperature=1.0))])
+def test_sampler_stochastic_distribution(ops, strategy, kw):
+    V, n = 3072, 4096
+    base = (torch.randn(V, generator=g(31)) * 2.5).to(BF)
+    cfg = osampler.SamplingConfig(**kw)
+    p_ref = osampler.filtered_probs(base.view(1, V), cfg)[0].double()
+    logits = base.view(1, V).expand(n, V).contiguous().cuda()
+    counts = torch.zeros(V, dtype=torch.float64)
+    for rep in range(4):
+        ids = ops.sample(logits, strategy, seed=1234, offset=rep, **kw).cpu()
+        counts += torch.bincount(ids, minlength=V).double()
+    total = counts.sum().item()
+    support = p_ref > 0
+    assert counts[~support].sum().item() == 0, "sampled a filtered-out token"
+    # chi-square style check on tokens with expected count >= 5
+    exp = p_ref * total
+    big = exp >= 5
+    chi2 = (((counts - exp) ** 2) / exp.clamp_min(1e-12))[big].sum().item()
+    dof = int(big.sum().item())
+    assert chi2 < dof + 6 * math.sqrt(2 * dof) + 10, (chi2, dof)
+    # determinism: same (seed, offset) -> same ids
+    a = ops.sample(logits, strategy, seed=7, offset=3, **kw)
+    b = ops.sample(logits, strategy, seed=7, offset=3, **kw)
+    assert torch.equal(a, b)
+
+
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,cfg", [("tiny", osnac.SnacConfig.tiny()), ("24khz", osnac.SnacConfig())])
+def test_snac_decode_golden(ops, golden_dir, tag, cfg):
+    from vox_serve_b200.tokenizer.snac import SNAC
+
+    gd = np.load(os.path.join(golden_dir, f"snac_{tag}.npz"))
+    sd = osnac.synth_state_dict(cfg, seed=5)
+    m = SNAC(sampling_rate=cfg.sampling_rate, encoder_dim=cfg.encoder_dim, encoder_rates=cfg.encoder_rates,
+             decoder_dim=cfg.decoder_dim, decoder_rates=cfg.decoder_rates, codebook_size=cfg.codebook_size,
+             codebook_dim=cfg.codebook_dim, vq_strides=cfg.vq_strides)
+    m.load_state_dict(sd)
+    codes = [torch.from_numpy(gd[f"codes{i}"]).cuda() for i in range(3)]
+    noises = [torch.from_numpy(gd[f"noise{i}"]).cuda() for i in range(4)]
+    wav = m.decode(codes, noises).cpu().numpy()
+    ref = gd["wav"]
+    assert wav.shape == ref.shape
+    # north_star: waveform within 1e-3 relative; fp32 kernels land far inside that
+    err = np.abs(wav - ref).max()
+    assert err < 1e-3 * max(1.0, np.abs(ref).max()), err
+    assert err < 2e-4, err
+    sl = m.decode(codes, noises, out_range=(2048, 4096)).cpu().numpy()
+    assert np.array_equal(sl, wav[:, :, 2048:4096])

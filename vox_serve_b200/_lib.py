@@ -1,0 +1,91 @@
+"""ctypes binding of libvoxb200.so (include/vb_api.h).  The product path has no CPU fallback: if the
+library is missing or a call fails, an exception is raised."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libvoxb200.so")
+
+c_void_p, c_int, c_int64, c_float, c_size_t, c_uint64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t, C.c_uint64
+P = c_void_p
+
+# name -> (restype, argtypes); mirrors include/vb_api.h one to one
+SIGNATURES = {
+    "vb_last_error": (C.c_char_p, []),
+    "vb_version": (c_int, []),
+    "vb_device_info": (c_int, [P, P]),
+    "vb_tensor_map_kv": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int]),
+    "vb_tensor_map_2d_bf16": (c_int, [P, P, c_int64, c_int64, c_int64, c_int]),
+    "vb_rmsnorm": (c_int, [P, P, P, c_int, c_int, c_float, P]),
+    "vb_rope_freqs": (c_int, [P, c_int, c_int, c_float, c_float, c_int, c_float, c_float, c_float, P]),
+    "vb_rope": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_plan_rows": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
+    "vb_kv_append": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    "vb_paged_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "vb_paged_attn": (c_int, [P, P, P, c_int64, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                              c_float, P, c_size_t, c_int, P]),
+    "vb_gemm_t_tile": (c_int, [c_int]),
+    "vb_gemm_bf16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_reduce_residual_rmsnorm": (c_int, [P, P, P, c_int, P, P, c_int, c_int, c_float, P]),
+    "vb_qkv_rope_append": (c_int, [P, P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_embedding": (c_int, [P, P, P, c_int, c_int, c_int, P]),
+    "vb_gather_rows": (c_int, [P, P, P, c_int, c_int, P]),
+    "vb_sample_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "vb_sample": (c_int, [P, P, c_int, c_int, c_int, P, c_int, c_int, c_int, c_float, c_int, c_int, c_float,
+                          c_float, c_float, c_uint64, c_uint64, c_int, P, c_size_t, P]),
+    "vb_apply_repetition_penalty": (c_int, [P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, P]),
+    "vb_update_repetition_cache": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_snac_from_codes": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_snac_dwconv7": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    "vb_snac_pwconv": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_snac_convtr": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_snac_final": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_pcm16": (c_int, [P, P, c_int64, P]),
+    "vb_orpheus_window_codes": (c_int, [P, P, P, P, c_int, c_int, P]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class VoxB200Error(RuntimeError):
+    pass
+
+
+def load(build_if_missing: bool = False):
+    """Load the shared library (once).  Never falls back to another implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            if build_if_missing:
+                from .build import build
+
+                build()
+            else:
+                raise VoxB200Error(
+                    f"{LIB_PATH} not found: build it with `python -m vox_serve_b200.build` "
+                    "(no CPU / PyTorch fallback exists for this path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().vb_last_error()
+        raise VoxB200Error(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")
+
+
+def call(name: str, *args):
+    """Invoke an int-returning entry point and raise on error."""
+    check(getattr(load(), name)(*args), name)

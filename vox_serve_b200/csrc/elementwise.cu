@@ -1,0 +1,501 @@
+// Row-wise / bookkeeping kernels of the decode step: RMSNorm, RoPE, page-table plan, KV append,
+// split-K reduction fused with residual + RMSNorm, fused QKV tail (reduce -> RoPE -> cache scatter),
+// embedding / row gathers, PCM16, Orpheus window de-interleave.  All HBM/latency-bound CUDA-core work.
+#include "../../include/vb_api.h"
+#include "common.cuh"
+
+namespace vb {
+
+// ------------------------------------------------------------------------------------------
+// RMSNorm (flashinfer_utils.py:251-267; arithmetic order of norm.cuh:64-101: (x * rcp) * w)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = (lane < nwarp) ? red[lane] : 0.f;
+  t = warp_sum(t);
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(256) rmsnorm_kernel(__nv_bfloat16* __restrict__ out,
+                                                      const __nv_bfloat16* __restrict__ x,
+                                                      const __nv_bfloat16* __restrict__ w, int dim, float eps) {
+  __shared__ float red[32];
+  const size_t row = blockIdx.x;
+  const __nv_bfloat16* xr = x + row * dim;
+  float ss = 0.f;
+  for (int i = threadIdx.x * 8; i < dim; i += blockDim.x * 8) {
+    if (i + 8 <= dim) {
+      uint4 v = *reinterpret_cast<const uint4*>(xr + i);
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = bf16_lo(u[j]), b = bf16_hi(u[j]);
+        ss += a * a + b * b;
+      }
+    } else {
+      for (int j = i; j < dim; ++j) {
+        float a = __bfloat162float(xr[j]);
+        ss += a * a;
+      }
+    }
+  }
+  ss = block_sum(ss, red);
+  const float rcp = rsqrtf(ss / static_cast<float>(dim) + eps);
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+    float v = __bfloat162float(xr[i]) * rcp * __bfloat162float(w[i]);
+    out[row * dim + i] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// RoPE (flashinfer_utils.py:270-324; pos_enc.cuh:129-147, 594-617)
+// freq[e], e < rotary_dim, is the per-element frequency (host: vox_serve_b200.flashinfer_utils).
+// ------------------------------------------------------------------------------------------
+__global__ void rope_freq_kernel(float* freq, int rotary_dim, int interleave, float rope_rcp_scale,
+                                 float rope_rcp_theta, float smooth_a, float smooth_b) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rotary_dim) return;
+  float e = interleave ? float(2 * (i / 2)) / float(rotary_dim) : float(2 * (i % (rotary_dim / 2))) / float(rotary_dim);
+  float f = powf(rope_rcp_theta, e);
+  float smooth = fminf(1.f, fmaxf(0.f, f * smooth_a + smooth_b));
+  freq[i] = (1.f - smooth) * (f * rope_rcp_scale) + smooth * f;
+}
+
+__device__ __forceinline__ int rope_partner(int e, int rotary_dim, int interleave, float& sign) {
+  if (interleave) {
+    sign = (e & 1) ? 1.f : -1.f;
+    return e ^ 1;
+  }
+  const int half = rotary_dim >> 1;
+  sign = (e < half) ? -1.f : 1.f;
+  return (e < half) ? e + half : e - half;
+}
+
+// one block per token; inputs staged in shared memory first so q_out / k_out may alias q / k
+__global__ void __launch_bounds__(256) rope_kernel(__nv_bfloat16* __restrict__ q_out, __nv_bfloat16* __restrict__ k_out,
+                                                   const __nv_bfloat16* q, const __nv_bfloat16* k,
+                                                   const int32_t* __restrict__ pos, const float* __restrict__ freq,
+                                                   int n_q, int n_kv, int D, int rotary_dim, int interleave) {
+  extern __shared__ float sm[];  // cos[rotary_dim], sin[rotary_dim], values[(n_q+n_kv)*D]
+  float* cs = sm;
+  float* val = sm + 2 * rotary_dim;
+  const size_t t = blockIdx.x;
+  const float p = static_cast<float>(pos[t]);
+  for (int e = threadIdx.x; e < rotary_dim; e += blockDim.x) {
+    float s, c;
+    sincosf(p * freq[e], &s, &c);
+    cs[e] = c;
+    cs[rotary_dim + e] = s;
+  }
+  const int nq_el = n_q * D, total = (n_q + n_kv) * D;
+  for (int i = threadIdx.x; i < total; i += blockDim.x)
+    val[i] = __bfloat162float(i < nq_el ? q[t * nq_el + i] : k[t * (total - nq_el) + (i - nq_el)]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int h = i / D, e = i - h * D;
+    float v = val[i];
+    if (e < rotary_dim) {
+      float sign;
+      const int pe = rope_partner(e, rotary_dim, interleave, sign);
+      v = v * cs[e] + sign * val[h * D + pe] * cs[rotary_dim + e];
+    }
+    if (i < nq_el) q_out[t * nq_el + i] = __float2bfloat16_rn(v);
+    else k_out[t * (total - nq_el) + (i - nq_el)] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// plan: page table -> per-row attention / append metadata  (flashinfer_utils.py:86-124, 217-225)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) plan_rows_kernel(const int32_t* __restrict__ qo_indptr,
+                                                         const int32_t* __restrict__ kv_indptr,
+                                                         const int32_t* __restrict__ kv_indices,
+                                                         const int32_t* __restrict__ last_page_len, int n_req,
+                                                         int n_rows_padded, int page_size, int chunk,
+                                                         int32_t* __restrict__ row_req, int32_t* __restrict__ row_kvlen,
+                                                         int32_t* __restrict__ row_page, int32_t* __restrict__ row_slot,
+                                                         int32_t* __restrict__ row_chunk_start) {
+  __shared__ int32_t warp_tot[32];
+  __shared__ int32_t carry;
+  const int tid = threadIdx.x;
+  // pass 1: per request, fill its rows
+  for (int r = tid; r < n_req; r += blockDim.x) {
+    const int row0 = qo_indptr ? qo_indptr[r] : r;
+    const int n_new = qo_indptr ? qo_indptr[r + 1] - row0 : 1;
+    const int p0 = kv_indptr[r];
+    const int kv_len = (kv_indptr[r + 1] - p0 - 1) * page_size + last_page_len[r];
+    for (int j = 0; j < n_new; ++j) {
+      const int row = row0 + j;
+      if (row >= n_rows_padded) break;
+      const int g = kv_len - n_new + j;
+      row_req[row] = r;
+      row_kvlen[row] = g + 1;
+      row_page[row] = kv_indices[p0 + g / page_size];
+      row_slot[row] = g % page_size;
+    }
+  }
+  const int n_valid = qo_indptr ? qo_indptr[n_req] : n_req;
+  for (int row = n_valid + tid; row < n_rows_padded; row += blockDim.x) {
+    row_req[row] = -1;
+    row_kvlen[row] = 0;
+    row_page[row] = -1;
+    row_slot[row] = 0;
+  }
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  // pass 2: exclusive scan of ceil(kvlen / chunk) over rows, 1024 rows per sweep
+  for (int base = 0; base < n_rows_padded; base += blockDim.x) {
+    const int row = base + tid;
+    const int c = (row < n_rows_padded) ? (row_kvlen[row] + chunk - 1) / chunk : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int n = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((tid & 31) >= o) incl += n;
+    }
+    if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+      int v = warp_tot[tid], w = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, w, o);
+        if (tid >= o) w += n;
+      }
+      warp_tot[tid] = w - v;  // exclusive
+    }
+    __syncthreads();
+    const int excl = carry + warp_tot[tid >> 5] + incl - c;
+    if (row < n_rows_padded) row_chunk_start[row] = excl;
+    __syncthreads();
+    if (tid == blockDim.x - 1) carry = excl + c;
+    __syncthreads();
+  }
+  if (tid == 0) row_chunk_start[n_rows_padded] = carry;
+}
+
+// ------------------------------------------------------------------------------------------
+// KV append (flashinfer_utils.py:144-145, 243-244)
+// ------------------------------------------------------------------------------------------
+__global__ void kv_append_kernel(__nv_bfloat16* __restrict__ kv, const __nv_bfloat16* __restrict__ k,
+                                 const __nv_bfloat16* __restrict__ v, const int32_t* __restrict__ row_page,
+                                 const int32_t* __restrict__ row_slot, int page_size, int row_elems /*n_kv*D*/) {
+  const size_t t = blockIdx.x;
+  const int page = row_page[t];
+  if (page < 0) return;
+  const size_t slab = static_cast<size_t>(page_size) * row_elems;
+  __nv_bfloat16* kd = kv + (static_cast<size_t>(page) * 2) * slab + static_cast<size_t>(row_slot[t]) * row_elems;
+  __nv_bfloat16* vd = kd + slab;
+  const uint4* ks = reinterpret_cast<const uint4*>(k + t * row_elems);
+  const uint4* vs = reinterpret_cast<const uint4*>(v + t * row_elems);
+  for (int i = threadIdx.x; i < row_elems / 8; i += blockDim.x) {
+    reinterpret_cast<uint4*>(kd)[i] = ks[i];
+    reinterpret_cast<uint4*>(vd)[i] = vs[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// split-K reduce + residual + RMSNorm (orpheus.py:125-151 rounding points)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) reduce_residual_rmsnorm_kernel(
+    __nv_bfloat16* __restrict__ hidden_out, __nv_bfloat16* __restrict__ normed_out,
+    const float* __restrict__ partials, int split_k, const __nv_bfloat16* __restrict__ residual,
+    const __nv_bfloat16* __restrict__ norm_w, int T, int N, float eps) {
+  extern __shared__ float hs[];  // N floats
+  __shared__ float red[32];
+  const size_t t = blockIdx.x;
+  const size_t plane = static_cast<size_t>(T) * N;
+  float ss = 0.f;
+  for (int n = threadIdx.x * 4; n < N; n += blockDim.x * 4) {
+    float4 acc = *reinterpret_cast<const float4*>(partials + t * N + n);
+    for (int s = 1; s < split_k; ++s) {
+      const float4 p = *reinterpret_cast<const float4*>(partials + s * plane + t * N + n);
+      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    float h[4] = {round_bf16(acc.x), round_bf16(acc.y), round_bf16(acc.z), round_bf16(acc.w)};
+    if (residual) {
+      const uint2 r = *reinterpret_cast<const uint2*>(residual + t * N + n);
+      h[0] = round_bf16(bf16_lo(r.x) + h[0]);
+      h[1] = round_bf16(bf16_hi(r.x) + h[1]);
+      h[2] = round_bf16(bf16_lo(r.y) + h[2]);
+      h[3] = round_bf16(bf16_hi(r.y) + h[3]);
+    }
+    if (hidden_out) {
+      uint2 o;
+      o.x = pack_bf16(h[0], h[1]);
+      o.y = pack_bf16(h[2], h[3]);
+      *reinterpret_cast<uint2*>(hidden_out + t * N + n) = o;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      hs[n + j] = h[j];
+      ss += h[j] * h[j];
+    }
+  }
+  if (!normed_out) return;
+  ss = block_sum(ss, red);
+  const float rcp = rsqrtf(ss / static_cast<float>(N) + eps);
+  for (int n = threadIdx.x * 2; n < N; n += blockDim.x * 2) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(norm_w + n);
+    *reinterpret_cast<uint32_t*>(normed_out + t * N + n) =
+        pack_bf16(hs[n] * rcp * bf16_lo(w), hs[n + 1] * rcp * bf16_hi(w));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused QKV tail: reduce partials -> bf16, RoPE(q, k), q out, K/V scatter into the layer cache
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) qkv_rope_append_kernel(
+    __nv_bfloat16* __restrict__ q_out, __nv_bfloat16* __restrict__ kv, const float* __restrict__ partials,
+    int split_k, const int32_t* __restrict__ pos, const float* __restrict__ freq,
+    const int32_t* __restrict__ row_page, const int32_t* __restrict__ row_slot, int T, int n_q, int n_kv, int D,
+    int page_size, int rotary_dim, int interleave) {
+  extern __shared__ float sm[];  // [2*rotary_dim cos/sin][(n_q+2n_kv)*D values]
+  float* cs = sm;
+  float* val = sm + 2 * rotary_dim;
+  const size_t t = blockIdx.x;
+  const int W = (n_q + 2 * n_kv) * D;
+  const size_t plane = static_cast<size_t>(T) * W;
+  const float p = static_cast<float>(pos[t]);
+  for (int e = threadIdx.x; e < rotary_dim; e += blockDim.x) {
+    float s, c;
+    sincosf(p * freq[e], &s, &c);
+    cs[e] = c;
+    cs[rotary_dim + e] = s;
+  }
+  for (int n = threadIdx.x * 4; n < W; n += blockDim.x * 4) {
+    float4 acc = *reinterpret_cast<const float4*>(partials + t * W + n);
+    for (int s = 1; s < split_k; ++s) {
+      const float4 q4 = *reinterpret_cast<const float4*>(partials + s * plane + t * W + n);
+      acc.x += q4.x; acc.y += q4.y; acc.z += q4.z; acc.w += q4.w;
+    }
+    val[n] = round_bf16(acc.x);
+    val[n + 1] = round_bf16(acc.y);
+    val[n + 2] = round_bf16(acc.z);
+    val[n + 3] = round_bf16(acc.w);
+  }
+  __syncthreads();
+  const int page = row_page[t];
+  const size_t row_elems = static_cast<size_t>(n_kv) * D;
+  const size_t slab = static_cast<size_t>(page_size) * row_elems;
+  __nv_bfloat16* kd = (page >= 0) ? kv + (static_cast<size_t>(page) * 2) * slab + static_cast<size_t>(row_slot[t]) * row_elems
+                                   : nullptr;
+  for (int i = threadIdx.x * 2; i < W; i += blockDim.x * 2) {
+    const int h = i / D, e = i - h * D;
+    float v0 = val[i], v1 = val[i + 1];
+    if (h < n_q + n_kv && e < rotary_dim) {
+      float s0, s1;
+      const int p0 = rope_partner(e, rotary_dim, interleave, s0);
+      const int p1 = rope_partner(e + 1, rotary_dim, interleave, s1);
+      v0 = v0 * cs[e] + s0 * val[h * D + p0] * cs[rotary_dim + e];
+      v1 = v1 * cs[e + 1] + s1 * val[h * D + p1] * cs[rotary_dim + e + 1];
+    }
+    const uint32_t packed = pack_bf16(v0, v1);
+    if (h < n_q) {
+      *reinterpret_cast<uint32_t*>(q_out + t * static_cast<size_t>(n_q) * D + i) = packed;
+    } else if (kd) {
+      const int j = i - n_q * D;  // offset inside [k heads | v heads]
+      if (j < static_cast<int>(row_elems))
+        *reinterpret_cast<uint32_t*>(kd + j) = packed;
+      else
+        *reinterpret_cast<uint32_t*>(kd + slab + (j - row_elems)) = packed;
+    }
+  }
+}
+
+__global__ void embedding_kernel(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ table,
+                                 const int32_t* __restrict__ ids, int dim, int vocab) {
+  const size_t t = blockIdx.x;
+  int id = ids[t];
+  id = min(max(id, 0), vocab - 1);
+  const uint4* src = reinterpret_cast<const uint4*>(table + static_cast<size_t>(id) * dim);
+  uint4* dst = reinterpret_cast<uint4*>(out + t * dim);
+  for (int i = threadIdx.x; i < dim / 8; i += blockDim.x) dst[i] = src[i];
+}
+
+__global__ void gather_rows_kernel(uint8_t* __restrict__ out, const uint8_t* __restrict__ in,
+                                   const int32_t* __restrict__ idx, int row_bytes) {
+  const size_t i = blockIdx.x;
+  const uint4* src = reinterpret_cast<const uint4*>(in + static_cast<size_t>(idx[i]) * row_bytes);
+  uint4* dst = reinterpret_cast<uint4*>(out + i * row_bytes);
+  for (int j = threadIdx.x; j < row_bytes / 16; j += blockDim.x) dst[j] = src[j];
+}
+
+__global__ void pcm16_kernel(int16_t* __restrict__ out, const float* __restrict__ a, int64_t n) {
+  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = static_cast<int16_t>(__float2int_rz(a[i] * 32767.0f));
+}
+
+__global__ void orpheus_window_codes_kernel(int32_t* __restrict__ c0, int32_t* __restrict__ c1,
+                                            int32_t* __restrict__ c2, const int64_t* __restrict__ ids, int B,
+                                            int base) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over B*28
+  if (i >= B * 28) return;
+  const int b = i / 28, r = i % 28, f = r / 7, p = r % 7;
+  long long v = (ids[i] - base) % 4096;
+  if (v < 0) v += 4096;  // python modulo
+  const int code = static_cast<int>(v);
+  if (p == 0) c0[b * 4 + f] = code;
+  else if (p == 1) c1[b * 8 + f * 2 + 0] = code;
+  else if (p == 4) c1[b * 8 + f * 2 + 1] = code;
+  else if (p == 2) c2[b * 16 + f * 4 + 0] = code;
+  else if (p == 3) c2[b * 16 + f * 4 + 1] = code;
+  else if (p == 5) c2[b * 16 + f * 4 + 2] = code;
+  else c2[b * 16 + f * 4 + 3] = code;
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" {
+
+int vb_rmsnorm(void* d_out, const void* d_x, const void* d_weight, int rows, int dim, float eps, void* stream) {
+  VB_CHECK_ARG(d_out && d_x && d_weight, "vb_rmsnorm: null pointer");
+  VB_CHECK_ARG(dim > 0 && dim % 8 == 0, "vb_rmsnorm: dim %d must be a positive multiple of 8", dim);
+  if (rows <= 0) return 0;
+  rmsnorm_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(d_out), static_cast<const __nv_bfloat16*>(d_x),
+      static_cast<const __nv_bfloat16*>(d_weight), dim, eps);
+  VB_CHECK_LAUNCH();
+  return 0;
+}
+
+int vb_rope_freqs(float* d_freq, int rotary_dim, int interleave, float rope_scale, float rope_theta, int llama31,
+                  float low_freq_factor, float high_freq_factor, float old_context_len, void* stream) {
+  VB_CHECK_ARG(d_freq && rotary_dim > 0 && rotary_dim % 2 == 0, "vb_rope_freqs: bad arguments");
+  float a = 0.f, b = 0.f;
+  if (llama31) {
+    a = old_context_len / (2.f * 3.14159265358979323846f * high_freq_factor -
+                           2.f * 3.14159265358979323846f * low_freq_factor);
+    b = -1.0f / (high_freq_factor / low_freq_factor - 1.0f);
+  }
+  rope_freq_kernel<<<(rotary_dim + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_freq, rotary_dim, interleave, 1.0f / rope_scale, 1.0f / rope_theta, a, b);
+  VB_CHECK_LAUNCH();
+  return 0;
+}
+
+int vb_rope(void* d_q_out, void* d_k_out, const void* d_q, const void* d_k, const int32_t* d_pos,
+            const float* d_freq, int T, int n_q, int n_kv, int head_dim, int rotary_dim, int interleave,
+            void* stream) {
+  VB_CHECK_ARG(d_q_out && d_k_out && d_q && d_k && d_pos && d_freq, "vb_rope: null pointer");
+  VB_CHECK_ARG(rotary_dim > 0 && rotary_dim <= head_dim && rotary_dim % 2 == 0, "vb_rope: rotary_dim %d invalid",
+               rotary_dim);
+  if (T <= 0) return 0;
+  rope_kernel<<<T, 256, (2 * rotary_dim + (n_q + n_kv) * head_dim) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(d_q_out), static_cast<__nv_bfloat16*>(d_k_out),
+      static_cast<const __nv_bfloat16*>(d_q), static_cast<const __nv_bfloat16*>(d_k), d_pos, d_freq, n_q, n_kv,
+      head_dim, rotary_dim, interleave);
+  VB_CHECK_LAUNCH();
+  return 0;
+}
+
+int vb_plan_rows(const int32_t* d_qo_indptr, const int32_t* d_kv_indptr, const int32_t* d_kv_indices,
+                 const int32_t* d_last_page_len, int n_req, int n_rows_padded, int page_size, int chunk_tokens,
+                 int32_t* d_row_req, int32_t* d_row_kvlen, int32_t* d_row_page, int32_t* d_row_slot,
+                 int32_t* d_row_chunk_start, void* stream) {
+  VB_CHECK_ARG(d_kv_indptr && d_kv_indices && d_last_page_len && d_row_req && d_row_kvlen && d_row_page &&
+                   d_row_slot && d_row_chunk_start,
+               "vb_plan_rows: null pointer");
+  VB_CHECK_ARG(page_size > 0 && chunk_tokens > 0 && page_size % chunk_tokens == 0,
+               "vb_plan_rows: chunk_tokens %d must divide page_size %d", chunk_tokens, page_size);
+  VB_CHECK_ARG(n_req >= 0 && n_rows_padded >= 0, "vb_plan_rows: negative sizes");
+  plan_rows_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_qo_indptr, d_kv_indptr, d_kv_indices, d_last_page_len, n_req, n_rows_padded, page_size, chunk_tokens,
+      d_row_req, d_row_kvlen, d_row_page, d_row_slot, d_row_chunk_start);
+  VB_CHECK_LAUNCH();
+  return 0;
+}
+
+int vb_kv_append(void* d_layer_kv, const void* d_k, const void* d_v, const int32_t* d_row_page,
+                 const int32_t* d_row_slot, int T, int page_size, int n_kv, int head_dim, void* stream) {
+  VB_CHECK_ARG(d_layer_kv && d_k && d_v && d_row_page && d_row_slot, "vb_kv_append: null pointer");
+  VB_CHECK_ARG((n_kv * head_dim) % 8 == 0, "vb_kv_append: n_kv*head_dim must be a multiple of 8");
+  if (T <= 0) return 0;
+  kv_append_kernel<<<T, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(d_layer_kv), static_cast<const __nv_bfloat16*>(d_k),
+      static_cast<const __nv_bfloat16*>(d_v), d_row_page, d_row_slot, page_size, n_kv * head_dim);
+  VB_CHECK_LAUNCH();
+  return 0;
+}
+
+int vb_reduce_residual_rmsnorm(void* d_hidden_out, void* d_normed_out, const float* d_partials, int split_k,
+                               const void* d_residual, const void* d_norm_weight, int T, int N, float eps,
+                               void* stream) {
+  VB_CHECK_ARG(d_partials && split_k >= 1, "vb_reduce_residual_rmsnorm: bad partials");
+  VB_CHECK_ARG(N % 4 == 0 && N * sizeof(float) <= 160 * 1024, "vb_reduce_residual_rmsnorm: N %d unsupported", N);
+  VB_CHECK_ARG(!d_normed_out || d_norm_weight, "vb_reduce_residual_rmsnorm: norm output needs a weight");
+  if (T <= 0) return 0;
+  const size_t smem = static_cast<size_t>(N) * sizeof(float);
+  if (smem > 48 * 1024)
+    VB_CHECK_CUDA(cudaFuncSetAttribute(reduce_residual_rmsnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+  reduce_residual_rmsnorm_kernel<<<T, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(d_hidden_out), static_cast<__nv_bfloat16*>(d_normed_out), d_partials, split_k,
+      static_cast<const __nv_bfloat16*>(d_residual), static_cast<const __nv_bfloat16*>(d_norm_weight), T, N, eps);
+  VB_CHECK_LAUNCH();
+  return 0;
+}
+
+int vb_qkv_rope_append(void* d_q_out, void* d_layer_kv, const float* d_partials, int split_k, const int32_t* d_pos,
+                       const float* d_freq, const int32_t* d_row_page, const int32_t* d_row_slot, int T, int n_q,
+                       int n_kv, int head_dim, int page_size, int rotary_dim, int interleave, void* stream) {
+  VB_CHECK_ARG(d_q_out && d_layer_kv && d_partials && d_pos && d_freq && d_row_page && d_row_slot,
+               "vb_qkv_rope_append: null pointer");
+  VB_CHECK_ARG(head_dim % 4 == 0 && rotary_dim % 2 == 0 && rotary_dim <= head_dim, "vb_qkv_rope_append: bad dims");
+  if (T <= 0) return 0;
+  const size_t smem = (2 * static_cast<size_t>(rotary_dim) + static_cast<size_t>(n_q + 2 * n_kv) * head_dim) *
+                      sizeof(float);
+  VB_CHECK_ARG(smem <= 200 * 1024, "vb_qkv_rope_append: row too wide for shared memory");
+  if (smem > 48 * 1024)
+    VB_CHECK_CUDA(cudaFuncSetAttribute(qkv_rope_append_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+  qkv_rope_append_kernel<<<T, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(d_q_out), static_cast<__nv_bfloat16*>(d_layer_kv), d_partials, split_k, d_pos,
+      d_freq, d_row_page, d_row_slot, T, n_q, n_kv, head_dim, page_size, rotary_dim, interleave);
+  VB_CHECK_LAUNCH();
+  return 0;
+}
+
+int vb_embedding(void* d_out, const void* d_table, const int32_t* d_ids, int T, int dim, int vocab, void* stream) {
+  VB_CHECK_ARG(d_out && d_table && d_ids && dim % 8 == 0, "vb_embedding: bad arguments");
+  if (T <= 0) return 0;
+  embedding_kernel<<<T, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(d_out), static_cast<const __nv_bfloat16*>(d_table), d_ids, dim, vocab);
+  VB_CHECK_LAUNCH();
+  return 0;
+}
+
+int vb_gather_rows(void* d_out, const void* d_in, const int32_t* d_idx, int n, int row_bytes, void* stream) {
+  VB_CHECK_ARG(d_out && d_in && d_idx && row_bytes % 16 == 0, "vb_gather_rows: bad arguments");
+  if (n <= 0) return 0;
+  gather_rows_kernel<<<n, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<uint8_t*>(d_out), static_cast<const uint8_t*>(d_in), d_idx, row_bytes);
+  VB_CHECK_LAUNCH();
+  return 0;
+}
+
+int vb_pcm16(int16_t* d_out, const float* d_audio, int64_t n, void* stream) {
+  VB_CHECK_ARG(d_out && d_audio, "vb_pcm16: null pointer");
+  if (n <= 0) return 0;
+  pcm16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_out, d_audio, n);
+  VB_CHECK_LAUNCH();
+  return 0;
+}
+
+int vb_orpheus_window_codes(int32_t* d_c0, int32_t* d_c1, int32_t* d_c2, const int64_t* d_ids, int B,
+                            int audio_id_base, void* stream) {
+  VB_CHECK_ARG(d_c0 && d_c1 && d_c2 && d_ids, "vb_orpheus_window_codes: null pointer");
+  if (B <= 0) return 0;
+  orpheus_window_codes_kernel<<<(B * 28 + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_c0, d_c1, d_c2, d_ids, B, audio_id_base);
+  VB_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,388 @@
+"""Tensor-level host wrappers over the C ABI (include/vb_api.h).
+
+PyTorch is used here only for device memory and streams: every function takes CUDA tensors, passes raw
+pointers + sizes to libvoxb200.so on the current stream and returns torch tensors.  There is no fallback
+path: a missing library or a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import VoxB200Error, call
+
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise VoxB200Error("vox_serve_b200 ops need CUDA tensors (there is no CPU path)")
+
+
+_dev_info: Dict[int, Tuple[int, int]] = {}
+
+
+def device_info() -> Tuple[int, int]:
+    dev = torch.cuda.current_device()
+    if dev not in _dev_info:
+        sm, smem = ctypes.c_int(0), ctypes.c_int(0)
+        call("vb_device_info", ctypes.byref(sm), ctypes.byref(smem))
+        _dev_info[dev] = (sm.value, smem.value)
+    return _dev_info[dev]
+
+
+# ----------------------------------------------------------------------------------------------
+# TMA descriptors
+# ----------------------------------------------------------------------------------------------
+class TensorMap:
+    """128-byte CUtensorMap held in 64-byte aligned host memory; keeps the tensor alive."""
+
+    __slots__ = ("_raw", "ptr", "owner")
+
+    def __init__(self, owner: torch.Tensor):
+        self._raw = ctypes.create_string_buffer(128 + 64)
+        base = ctypes.addressof(self._raw)
+        self.ptr = (base + 63) & ~63
+        self.owner = owner
+
+
+def tensor_map_kv(kv_cache: torch.Tensor, box_tokens: int) -> TensorMap:
+    """kv_cache: [layers, pages, 2, page_size, n_kv, head_dim] bf16 (or a single layer [pages, 2, ...])."""
+    _need_cuda(kv_cache)
+    assert kv_cache.dtype == BF16 and kv_cache.is_contiguous()
+    if kv_cache.dim() == 6:
+        n_slabs = kv_cache.shape[0] * kv_cache.shape[1]
+    else:
+        assert kv_cache.dim() == 5
+        n_slabs = kv_cache.shape[0]
+    page_size, n_kv, d = kv_cache.shape[-3], kv_cache.shape[-2], kv_cache.shape[-1]
+    tm = TensorMap(kv_cache)
+    call("vb_tensor_map_kv", tm.ptr, kv_cache.data_ptr(), n_slabs, page_size, n_kv, d, box_tokens)
+    return tm
+
+
+_map2d_cache: Dict[Tuple, TensorMap] = {}
+
+
+def tensor_map_2d(t: torch.Tensor, box_rows: int, cache: bool = True) -> TensorMap:
+    _need_cuda(t)
+    assert t.dtype == BF16 and t.dim() == 2 and t.stride(1) == 1
+    key = (t.data_ptr(), t.shape[0], t.shape[1], t.stride(0), box_rows)
+    if cache and key in _map2d_cache:
+        return _map2d_cache[key]
+    tm = TensorMap(t)
+    call("vb_tensor_map_2d_bf16", tm.ptr, t.data_ptr(), t.shape[0], t.shape[1], t.stride(0), box_rows)
+    if cache:
+        _map2d_cache[key] = tm
+    return tm
+
+
+# ----------------------------------------------------------------------------------------------
+# norm / rope / paging
+# ----------------------------------------------------------------------------------------------
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(x, weight)
+    assert x.dtype == BF16 and weight.dtype == BF16
+    x2 = x.contiguous().view(-1, x.shape[-1])
+    out = torch.empty_like(x2) if out is None else out
+    call("vb_rmsnorm", out.data_ptr(), x2.data_ptr(), weight.data_ptr(), x2.shape[0], x2.shape[1], float(eps), _stream())
+    return out.view(x.shape)
+
+
+_freq_cache: Dict[Tuple, torch.Tensor] = {}
+
+
+def rope_freq_table(rotary_dim: int, rope_scale: float, rope_theta: float, interleave: bool,
+                    low_freq_factor=None, high_freq_factor=None, old_context_len=None,
+                    device=None) -> torch.Tensor:
+    """Per-element frequency table (fp32, [rotary_dim]) with FlashInfer's formula
+    (pos_enc.cuh:594-602, 1399-1400, 1538-1539), computed once on the device by vb_rope_freqs."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    llama31 = any(v is not None for v in (low_freq_factor, high_freq_factor, old_context_len))
+    lo = 1.0 if low_freq_factor is None else float(low_freq_factor)
+    hi = 4.0 if high_freq_factor is None else float(high_freq_factor)
+    ctx = 8192.0 if old_context_len is None else float(old_context_len)
+    key = (int(rotary_dim), float(rope_scale), float(rope_theta), bool(interleave), llama31, lo, hi, ctx, str(device))
+    t = _freq_cache.get(key)
+    if t is None:
+        t = torch.empty(rotary_dim, dtype=torch.float32, device=device)
+        call("vb_rope_freqs", t.data_ptr(), int(rotary_dim), int(bool(interleave)), float(rope_scale),
+             float(rope_theta), int(llama31), lo, hi, ctx, _stream())
+        _freq_cache[key] = t
+    return t
+
+
+def rope(q: torch.Tensor, k: torch.Tensor, pos: torch.Tensor, freq: torch.Tensor, interleave: bool = False,
+         inplace: bool = False):
+    """q [T, Hq, D], k [T, Hkv, D] bf16; pos [T] int32."""
+    _need_cuda(q, k, pos, freq)
+    assert q.dtype == BF16 and k.dtype == BF16 and pos.dtype == torch.int32
+    q, k = q.contiguous(), k.contiguous()
+    qo = q if inplace else torch.empty_like(q)
+    ko = k if inplace else torch.empty_like(k)
+    call("vb_rope", qo.data_ptr(), ko.data_ptr(), q.data_ptr(), k.data_ptr(), pos.data_ptr(), freq.data_ptr(),
+         q.shape[0], q.shape[1], k.shape[1], q.shape[2], freq.numel(), int(bool(interleave)), _stream())
+    return qo, ko
+
+
+def attn_chunk_tokens(page_size: int) -> int:
+    if page_size % 64 == 0:
+        return 64
+    if page_size in (16, 32):
+        return page_size
+    raise VoxB200Error(f"page_size {page_size} unsupported: must be 16, 32 or a multiple of 64")
+
+
+class RowPlan:
+    """Device-side per-row metadata produced by vb_plan_rows (see include/vb_api.h)."""
+
+    def __init__(self, max_rows: int, device):
+        self.max_rows = max_rows
+        self.buf = torch.zeros(5 * max_rows + 8, dtype=torch.int32, device=device)
+        m = max_rows
+        self.row_req, self.row_kvlen = self.buf[0:m], self.buf[m:2 * m]
+        self.row_page, self.row_slot = self.buf[2 * m:3 * m], self.buf[3 * m:4 * m]
+        self.row_chunk_start = self.buf[4 * m:5 * m + 1]
+        self.n_rows = 0
+
+
+def plan_rows(plan: RowPlan, qo_indptr: Optional[torch.Tensor], kv_indptr: torch.Tensor, kv_indices: torch.Tensor,
+              last_page_len: torch.Tensor, n_req: int, n_rows: int, page_size: int, chunk_tokens: int) -> RowPlan:
+    _need_cuda(kv_indptr, kv_indices, last_page_len)
+    assert n_rows <= plan.max_rows
+    call("vb_plan_rows", _p(qo_indptr), kv_indptr.data_ptr(), kv_indices.data_ptr(), last_page_len.data_ptr(),
+         n_req, n_rows, page_size, chunk_tokens, plan.row_req.data_ptr(), plan.row_kvlen.data_ptr(),
+         plan.row_page.data_ptr(), plan.row_slot.data_ptr(), plan.row_chunk_start.data_ptr(), _stream())
+    plan.n_rows = n_rows
+    return plan
+
+
+def kv_append(layer_kv: torch.Tensor, k: torch.Tensor, v: torch.Tensor, plan: RowPlan, n_rows: Optional[int] = None):
+    _need_cuda(layer_kv, k, v)
+    T = k.shape[0] if n_rows is None else n_rows
+    k, v = k.contiguous(), v.contiguous()
+    call("vb_kv_append", layer_kv.data_ptr(), k.data_ptr(), v.data_ptr(), plan.row_page.data_ptr(),
+         plan.row_slot.data_ptr(), T, layer_kv.shape[-3], layer_kv.shape[-2], layer_kv.shape[-1], _stream())
+
+
+def paged_attn_workspace(max_rows: int, max_chunks: int, n_q: int, n_kv: int, head_dim: int, device) -> torch.Tensor:
+    n = _lib.load().vb_paged_attn_workspace_bytes(max_rows, max_chunks, n_q, n_kv, head_dim)
+    return torch.zeros(n, dtype=torch.uint8, device=device)
+
+
+def paged_attn(q: torch.Tensor, kv_map: TensorMap, slab_base: int, kv_indptr: torch.Tensor,
+               kv_indices: torch.Tensor, plan: RowPlan, n_rows: int, max_chunks: int, n_kv: int, page_size: int,
+               chunk_tokens: int, workspace: torch.Tensor, sm_scale: Optional[float] = None,
+               out: Optional[torch.Tensor] = None, grid_ctas: Optional[int] = None) -> torch.Tensor:
+    """q [R, Hq, D] bf16 -> [R, Hq, D]."""
+    _need_cuda(q, kv_indptr, kv_indices, workspace)
+    assert q.dtype == BF16 and q.is_contiguous()
+    n_q, d = q.shape[1], q.shape[2]
+    out = torch.empty_like(q) if out is None else out
+    if grid_ctas is None:
+        grid_ctas = 2 * device_info()[0]
+    sc = 1.0 / math.sqrt(d) if sm_scale is None else float(sm_scale)
+    call("vb_paged_attn", out.data_ptr(), q.data_ptr(), kv_map.ptr, int(slab_base), kv_indptr.data_ptr(),
+         kv_indices.data_ptr(), plan.row_req.data_ptr(), plan.row_kvlen.data_ptr(), plan.row_chunk_start.data_ptr(),
+         n_rows, max_chunks, n_q, n_kv, d, page_size, chunk_tokens, sc, workspace.data_ptr(), workspace.numel(),
+         int(grid_ctas), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# projections
+# ----------------------------------------------------------------------------------------------
+def gemm_t_tile(T: int) -> int:
+    return _lib.load().vb_gemm_t_tile(int(T))
+
+
+def choose_split_k(N: int, K: int, T: int, sms: Optional[int] = None) -> int:
+    """Spread a skinny (weight-streaming) projection over all SMs: CTAs = ceil(N/128) * split_k."""
+    sms = device_info()[0] if sms is None else sms
+    tiles = (N + 127) // 128 * ((T + 255) // 256)
+    num_kb = (K + 63) // 64
+    if tiles >= sms:
+        return 1
+    return max(1, min(num_kb // 4 if num_kb >= 4 else 1, sms // tiles))
+
+
+def gemm(x: torch.Tensor, w: torch.Tensor, mode: int = 0, split_k: int = 1, out: Optional[torch.Tensor] = None,
+         w_map: Optional[TensorMap] = None) -> torch.Tensor:
+    """x [T, K] bf16, w [N, K] bf16 (nn.Linear.weight layout).
+    mode 0 -> bf16 [T, N]; mode 1 -> fp32 partials [split_k, T, N]; mode 2 -> bf16 [T, N/2] = silu(gate)*up
+    with w rows interleaved per 128-row tile (see interleave_gate_up)."""
+    _need_cuda(x, w)
+    assert x.dtype == BF16 and w.dtype == BF16 and x.dim() == 2 and w.dim() == 2 and x.shape[1] == w.shape[1]
+    T, K = x.shape
+    N = w.shape[0]
+    n_out = N // 2 if mode == 2 else N
+    if out is None:
+        if mode == 1:
+            out = torch.empty(split_k, T, n_out, dtype=torch.float32, device=x.device)
+        else:
+            out = torch.empty(T, n_out, dtype=BF16, device=x.device)
+    w_map = tensor_map_2d(w, 128) if w_map is None else w_map
+    x_map = tensor_map_2d(x, gemm_t_tile(T))
+    call("vb_gemm_bf16", out.data_ptr(), w_map.ptr, x_map.ptr, T, N, K, n_out, mode, split_k, _stream())
+    return out
+
+
+def interleave_gate_up(gate_w: torch.Tensor, up_w: torch.Tensor) -> torch.Tensor:
+    """[I, K] x 2 -> [2I, K] with rows grouped per 128-row tile as 64 gate rows then the 64 matching up rows."""
+    I, K = gate_w.shape
+    assert up_w.shape == gate_w.shape and I % 64 == 0
+    g = gate_w.view(I // 64, 64, K)
+    u = up_w.view(I // 64, 64, K)
+    return torch.cat((g, u), dim=1).reshape(2 * I, K).contiguous()
+
+
+def reduce_residual_rmsnorm(partials: torch.Tensor, residual: Optional[torch.Tensor],
+                            norm_weight: Optional[torch.Tensor], eps: float,
+                            hidden_out: Optional[torch.Tensor] = None, normed_out: Optional[torch.Tensor] = None,
+                            want_hidden: bool = True):
+    """partials fp32 [S, T, N] -> (hidden bf16 [T, N], normed bf16 [T, N] or None)."""
+    _need_cuda(partials)
+    S, T, N = partials.shape
+    if want_hidden and hidden_out is None:
+        hidden_out = torch.empty(T, N, dtype=BF16, device=partials.device)
+    if norm_weight is not None and normed_out is None:
+        normed_out = torch.empty(T, N, dtype=BF16, device=partials.device)
+    call("vb_reduce_residual_rmsnorm", _p(hidden_out), _p(normed_out), partials.data_ptr(), S, _p(residual),
+         _p(norm_weight), T, N, float(eps), _stream())
+    return hidden_out, normed_out
+
+
+def qkv_rope_append(partials: torch.Tensor, layer_kv: torch.Tensor, pos: torch.Tensor, freq: torch.Tensor,
+                    plan: RowPlan, n_q: int, n_kv: int, head_dim: int, interleave: bool = False,
+                    q_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(partials, layer_kv, pos, freq)
+    S, T, W = partials.shape
+    assert W == (n_q + 2 * n_kv) * head_dim
+    if q_out is None:
+        q_out = torch.empty(T, n_q, head_dim, dtype=BF16, device=partials.device)
+    call("vb_qkv_rope_append", q_out.data_ptr(), layer_kv.data_ptr(), partials.data_ptr(), S, pos.data_ptr(),
+         freq.data_ptr(), plan.row_page.data_ptr(), plan.row_slot.data_ptr(), T, n_q, n_kv, head_dim,
+         layer_kv.shape[-3], freq.numel(), int(bool(interleave)), _stream())
+    return q_out
+
+
+def embedding(table: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(table, ids)
+    assert ids.dtype == torch.int32 and table.dtype == BF16
+    T = ids.numel()
+    out = torch.empty(T, table.shape[1], dtype=BF16, device=table.device) if out is None else out
+    call("vb_embedding", out.data_ptr(), table.data_ptr(), ids.data_ptr(), T, table.shape[1], table.shape[0], _stream())
+    return out
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(src, idx)
+    assert idx.dtype == torch.int32 and src.dim() == 2 and src.is_contiguous()
+    out = torch.empty(idx.numel(), src.shape[1], dtype=src.dtype, device=src.device) if out is None else out
+    call("vb_gather_rows", out.data_ptr(), src.data_ptr(), idx.data_ptr(), idx.numel(),
+         src.shape[1] * src.element_size(), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# sampler
+# ----------------------------------------------------------------------------------------------
+STRATEGY = {"greedy": 0, "top_k": 1, "top_p": 2, "top_k_top_p": 3, "min_p": 4}
+_sample_ws: Dict[Tuple, torch.Tensor] = {}
+
+
+def sample_workspace(rows: int, vocab: int, device) -> torch.Tensor:
+    key = (rows, str(device))
+    ws = _sample_ws.get(key)
+    if ws is None:
+        n = _lib.load().vb_sample_workspace_bytes(rows, vocab)
+        ws = torch.empty(n, dtype=torch.uint8, device=device)
+        _sample_ws[key] = ws
+    return ws
+
+
+def _cache_u8(rep_cache: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if rep_cache is None:
+        return None
+    assert rep_cache.dim() == 4 and rep_cache.is_contiguous()
+    return rep_cache.view(torch.uint8) if rep_cache.dtype == torch.bool else rep_cache
+
+
+def sample(logits: torch.Tensor, strategy: str, rep_cache: Optional[torch.Tensor] = None, penalty: float = 1.0,
+           logit_codebooks: int = 1, top_k: int = 0, top_p: float = 1.0, min_p: float = 0.0, temperature: float = 1.0,
+           seed: int = 0, offset: int = 0, mask_token: int = -1, out: Optional[torch.Tensor] = None,
+           workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """logits [rows, V] bf16 (row stride arbitrary) -> ids int64 [rows]."""
+    _need_cuda(logits)
+    assert logits.dtype == BF16 and logits.dim() == 2 and logits.stride(1) == 1
+    rows, V = logits.shape
+    out = torch.empty(rows, dtype=torch.int64, device=logits.device) if out is None else out
+    ws = sample_workspace(rows, V, logits.device) if workspace is None else workspace
+    c8 = _cache_u8(rep_cache)
+    W, Cc = (c8.shape[1], c8.shape[2]) if c8 is not None else (0, 0)
+    call("vb_sample", out.data_ptr(), logits.data_ptr(), rows, V, logits.stride(0), _p(c8), W, Cc, logit_codebooks,
+         float(penalty), STRATEGY[strategy], int(top_k or 0), float(top_p if top_p is not None else 1.0),
+         float(min_p or 0.0), float(temperature), int(seed), int(offset), int(mask_token), ws.data_ptr(), ws.numel(),
+         _stream())
+    return out
+
+
+def apply_repetition_penalty(logits: torch.Tensor, rep_cache: torch.Tensor, penalty: float) -> torch.Tensor:
+    """logits [B, C, V] bf16, cache [B, W, Cc, V] bool -> penalised logits (new tensor)."""
+    _need_cuda(logits, rep_cache)
+    B, Cl, V = logits.shape
+    x = logits.contiguous()
+    c8 = _cache_u8(rep_cache)
+    out = torch.empty_like(x)
+    call("vb_apply_repetition_penalty", out.data_ptr(), x.data_ptr(), c8.data_ptr(), c8.shape[1], c8.shape[2], Cl,
+         float(penalty), B * Cl, V, _stream())
+    return out
+
+
+def update_repetition_cache(rep_cache: torch.Tensor, ids: torch.Tensor, window: int) -> None:
+    _need_cuda(rep_cache, ids)
+    c8 = _cache_u8(rep_cache)
+    ids64 = ids.to(torch.int64).contiguous()
+    B, W, Cc, V = c8.shape
+    call("vb_update_repetition_cache", c8.data_ptr(), ids64.data_ptr(), B, W, Cc, V, ids64.shape[1], int(window),
+         _stream())
+
+
+# ----------------------------------------------------------------------------------------------
+# misc
+# ----------------------------------------------------------------------------------------------
+def pcm16(audio: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(audio)
+    a = audio.contiguous()
+    assert a.dtype == torch.float32
+    out = torch.empty(a.shape, dtype=torch.int16, device=a.device) if out is None else out
+    call("vb_pcm16", out.data_ptr(), a.data_ptr(), a.numel(), _stream())
+    return out
+
+
+def orpheus_window_codes(ids: torch.Tensor, audio_id_base: int):
+    """ids int64 [B, 28] -> codes0 [B,4], codes1 [B,8], codes2 [B,16] int32 (orpheus.py:479-500)."""
+    _need_cuda(ids)
+    ids = ids.to(torch.int64).contiguous().view(-1, 28)
+    B = ids.shape[0]
+    c0 = torch.empty(B, 4, dtype=torch.int32, device=ids.device)
+    c1 = torch.empty(B, 8, dtype=torch.int32, device=ids.device)
+    c2 = torch.empty(B, 16, dtype=torch.int32, device=ids.device)
+    call("vb_orpheus_window_codes", c0.data_ptr(), c1.data_ptr(), c2.data_ptr(), ids.data_ptr(), B,
+         int(audio_id_base), _stream())
+    return c0, c1, c2

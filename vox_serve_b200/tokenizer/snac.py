@@ -1,0 +1,177 @@
+"""SNAC decode path on the sm_100a kernels (drop-in for ``vox_serve/tokenizer/snac.py`` decode:
+``SNAC.from_config`` / ``from_pretrained`` / ``load_state_dict`` / ``decode(codes)``, snac.py:438-466).
+
+Only the decoder + RVQ ``from_codes`` exist here (the encoder is not on the serving path).  At load time
+the weight-norm parametrisation is folded once (the reference re-derives ``g*v/||v||`` on every forward,
+snac.py:244-249), transposed-conv weights are repacked per output phase, and every Snake is assigned to
+the epilogue of the stage that produces its input.  ``NoiseBlock`` noise is drawn with ``torch.randn`` on
+the current CUDA generator like the reference (snac.py:208) unless explicit noise tensors are passed.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from .. import ops
+from .._lib import VoxB200Error, call
+
+
+def _fold(sd, prefix: str) -> torch.Tensor:
+    g = sd[prefix + ".parametrizations.weight.original0"].float()
+    v = sd[prefix + ".parametrizations.weight.original1"].float()
+    n = torch.linalg.vector_norm(v, ord=2, dim=tuple(range(1, v.dim())), keepdim=True)
+    return v * (g / n)
+
+
+class SNAC:
+    def __init__(self, sampling_rate=24000, encoder_dim=48, encoder_rates=(2, 4, 8, 8), latent_dim=None,
+                 decoder_dim=1024, decoder_rates=(8, 8, 4, 2), attn_window_size=None, codebook_size=4096,
+                 codebook_dim=8, vq_strides=(4, 2, 1), noise=True, depthwise=True, enable_torch_compile=False,
+                 device="cuda", **_):
+        if attn_window_size is not None:
+            raise VoxB200Error("SNAC variants with LocalMHA (attn_window_size) are not on the Orpheus path")
+        if not depthwise or not noise or len(vq_strides) != 3:
+            raise VoxB200Error("only the depthwise + noise, 3-codebook SNAC configuration (snac_24khz) is built")
+        self.sampling_rate = sampling_rate
+        self.latent_dim = latent_dim or encoder_dim * (2 ** len(encoder_rates))
+        self.decoder_dim, self.decoder_rates = decoder_dim, tuple(decoder_rates)
+        self.codebook_size, self.codebook_dim, self.vq_strides = codebook_size, codebook_dim, tuple(vq_strides)
+        self.hop_length = math.prod(encoder_rates)
+        self.device = torch.device(device)
+        self.w: Dict[str, torch.Tensor] = {}
+        self.loaded = False
+
+    # ---- loading -----------------------------------------------------------------------------
+    @classmethod
+    def from_config(cls, config_path, enable_torch_compile=False, device="cuda"):
+        with open(config_path) as f:
+            cfg = json.load(f)
+        return cls(**cfg, device=device)
+
+    @classmethod
+    def from_pretrained(cls, repo_id, enable_torch_compile=False, device="cuda", **kw):
+        if not os.path.isdir(repo_id):
+            raise VoxB200Error("no network in this build: pass a local directory with config.json + pytorch_model.bin")
+        m = cls.from_config(os.path.join(repo_id, "config.json"), device=device)
+        m.load_state_dict(torch.load(os.path.join(repo_id, "pytorch_model.bin"), map_location="cpu"))
+        return m
+
+    def eval(self):
+        return self
+
+    def to(self, device):
+        if torch.device(device) != self.device and self.loaded:
+            self.w = {k: v.to(device) for k, v in self.w.items()}
+        self.device = torch.device(device)
+        return self
+
+    def load_state_dict(self, sd, strict: bool = False):
+        dev, w = self.device, {}
+        C, nq = self.latent_dim, len(self.vq_strides)
+        w["codebooks"] = torch.stack([sd[f"quantizer.quantizers.{i}.codebook.weight"].float() for i in range(nq)])
+        w["proj_w"] = torch.stack([_fold(sd, f"quantizer.quantizers.{i}.out_proj")[:, :, 0] for i in range(nq)])
+        w["proj_b"] = torch.stack([sd[f"quantizer.quantizers.{i}.out_proj.bias"].float() for i in range(nq)])
+        w["in_dw_w"] = _fold(sd, "decoder.model.0")[:, 0, :]
+        w["in_dw_b"] = sd["decoder.model.0.bias"].float()
+        w["in_pw_w"] = _fold(sd, "decoder.model.1")[:, :, 0]
+        w["in_pw_b"] = sd["decoder.model.1.bias"].float()
+        li = 2
+        for bi, s in enumerate(self.decoder_rates):
+            p = f"decoder.model.{li}"
+            w[f"b{bi}.alpha"] = sd[p + ".block.0.alpha"].float().reshape(-1)
+            wt = _fold(sd, p + ".block.1")                       # [Cin, Cout, 2s]
+            cin, cout, k = wt.shape
+            assert k == 2 * s
+            # packed[r][co][tap*Cin + ci] = W[ci][co][r + tap*s]
+            w[f"b{bi}.ct_w"] = wt.view(cin, cout, 2, s).permute(3, 1, 2, 0).reshape(s, cout, 2 * cin)
+            w[f"b{bi}.ct_b"] = sd[p + ".block.1.bias"].float()
+            w[f"b{bi}.noise_w"] = _fold(sd, p + ".block.2.linear")[:, :, 0]
+            for j in range(3):
+                q = f"{p}.block.{3 + j}"
+                w[f"b{bi}.r{j}.alpha1"] = sd[q + ".block.0.alpha"].float().reshape(-1)
+                w[f"b{bi}.r{j}.dw_w"] = _fold(sd, q + ".block.1")[:, 0, :]
+                w[f"b{bi}.r{j}.dw_b"] = sd[q + ".block.1.bias"].float()
+                w[f"b{bi}.r{j}.alpha2"] = sd[q + ".block.2.alpha"].float().reshape(-1)
+                w[f"b{bi}.r{j}.pw_w"] = _fold(sd, q + ".block.3")[:, :, 0]
+                w[f"b{bi}.r{j}.pw_b"] = sd[q + ".block.3.bias"].float()
+            li += 1
+        w["out.alpha"] = sd[f"decoder.model.{li}.alpha"].float().reshape(-1)
+        w["out.w"] = _fold(sd, f"decoder.model.{li + 1}")[0]     # [C, 7]
+        w["out.b"] = sd[f"decoder.model.{li + 1}.bias"].float()
+        self.w = {k: v.contiguous().to(dev) for k, v in w.items()}
+        self.loaded = True
+        return self
+
+    # ---- decode ------------------------------------------------------------------------------
+    def noise_shapes(self, batch: int, t_latent: int):
+        out, t = [], t_latent
+        for s in self.decoder_rates:
+            t *= s
+            out.append((batch, 1, t))
+        return out
+
+    @torch.no_grad()
+    def decode(self, codes: List[torch.Tensor], noises: Optional[Sequence[torch.Tensor]] = None,
+               out_range: Optional[Sequence[int]] = None) -> torch.Tensor:
+        """codes: 3 int tensors [B, T/stride_i] -> waveform [B, 1, T*prod(rates)] fp32 (snac.py:438-441).
+        out_range=(t0, t1) returns only those samples (what OrpheusModel.postprocess keeps, orpheus.py:506)."""
+        if not self.loaded:
+            raise VoxB200Error("SNAC weights not loaded")
+        w, st = self.w, ops._stream()
+        dev = self.device
+        c = [x.to(device=dev, dtype=torch.int32).contiguous() for x in codes]
+        B = c[0].shape[0]
+        T = c[-1].shape[1] * self.vq_strides[-1]
+        C = self.latent_dim
+        f32 = dict(dtype=torch.float32, device=dev)
+        z = torch.empty(B, C, T, **f32)
+        call("vb_snac_from_codes", z.data_ptr(), c[0].data_ptr(), c[1].data_ptr(), c[2].data_ptr(),
+             w["codebooks"].data_ptr(), w["proj_w"].data_ptr(), w["proj_b"].data_ptr(), B, C, T,
+             self.codebook_size, self.codebook_dim, *self.vq_strides, st)
+        x = torch.empty_like(z)
+        call("vb_snac_dwconv7", x.data_ptr(), z.data_ptr(), w["in_dw_w"].data_ptr(), w["in_dw_b"].data_ptr(), None,
+             None, B, C, T, 1, st)
+        ch = self.decoder_dim
+        y = torch.empty(B, ch, T, **f32)
+        # 1x1 conv 768 -> 1024; its output only feeds block 0's Snake -> fuse that Snake here
+        call("vb_snac_pwconv", y.data_ptr(), x.data_ptr(), w["in_pw_w"].data_ptr(), w["in_pw_b"].data_ptr(), None,
+             None, w["b0.alpha"].data_ptr(), 0, B, C, ch, T, st)
+        x = y
+        nb = len(self.decoder_rates)
+        if noises is None:
+            noises = [torch.randn(s, **f32) for s in self.noise_shapes(B, T)]
+        for bi, s in enumerate(self.decoder_rates):
+            cin, cout = ch, ch // 2
+            u = torch.empty(B, cout, T * s, **f32)
+            call("vb_snac_convtr", u.data_ptr(), x.data_ptr(), w[f"b{bi}.ct_w"].data_ptr(),
+                 w[f"b{bi}.ct_b"].data_ptr(), None, B, cin, cout, T, s, st)
+            T *= s
+            nz = noises[bi].to(device=dev, dtype=torch.float32).contiguous()
+            assert nz.numel() == B * T, "noise tensor shape mismatch"
+            x = torch.empty_like(u)
+            call("vb_snac_pwconv", x.data_ptr(), u.data_ptr(), w[f"b{bi}.noise_w"].data_ptr(), None, None,
+                 nz.data_ptr(), None, 2, B, cout, cout, T, st)
+            for j, dil in enumerate((1, 3, 9)):
+                h = torch.empty_like(x)
+                call("vb_snac_dwconv7", h.data_ptr(), x.data_ptr(), w[f"b{bi}.r{j}.dw_w"].data_ptr(),
+                     w[f"b{bi}.r{j}.dw_b"].data_ptr(), w[f"b{bi}.r{j}.alpha1"].data_ptr(),
+                     w[f"b{bi}.r{j}.alpha2"].data_ptr(), B, cout, T, dil, st)
+                # the last unit's output only feeds the next stage's Snake: fuse it into this epilogue
+                nxt = None
+                if j == 2:
+                    nxt = w[f"b{bi + 1}.alpha"] if bi + 1 < nb else w["out.alpha"]
+                o = torch.empty_like(x)
+                call("vb_snac_pwconv", o.data_ptr(), h.data_ptr(), w[f"b{bi}.r{j}.pw_w"].data_ptr(),
+                     w[f"b{bi}.r{j}.pw_b"].data_ptr(), x.data_ptr(), None, None if nxt is None else nxt.data_ptr(),
+                     1, B, cout, cout, T, st)
+                x = o
+            ch = cout
+        t0, t1 = (0, T) if out_range is None else (int(out_range[0]), int(out_range[1]))
+        wav = torch.empty(B, 1, t1 - t0, **f32)
+        call("vb_snac_final", wav.data_ptr(), x.data_ptr(), w["out.w"].data_ptr(), w["out.b"].data_ptr(), None, B,
+             ch, T, t0, t1, st)
+        return wav
