@@ -58,13 +58,19 @@ int vb_rope(void* d_q_out, void* d_k_out, const void* d_q, const void* d_k, cons
  * Device-side "plan": from the page table (indptr [B+1], indices, last_page_len [B]) and, for prefill,
  * qo_indptr [B+1], derive per query row: owning request, visible kv length, (page, slot) of its new
  * K/V entry; plus the exclusive prefix of 64-token (or page-sized) attention chunks per row.
- * qo_indptr == NULL means decode (one row per request).  Rows >= n_rows_valid up to n_rows_padded get
+ * qo_indptr == NULL means decode (one row per request).  d_kv_len (optional, [B]) gives each request's kv
+ * length explicitly -- then the page table may hold pre-allocated pages beyond it and last_page_len is
+ * ignored (device-resident decode loop; the reference derives the length from the table, :96-97).  Rows >= n_rows_valid up to n_rows_padded get
  * page = -1 (their K/V append is skipped; the reference scatters them into page -1).
- * Outputs (device int32): row_req[R], row_kvlen[R], row_page[R], row_slot[R], row_chunk_start[R+1]. */
+ * Outputs (device int32): row_req[R], row_kvlen[R], row_page[R], row_slot[R], row_chunk_start[R+1], and
+ * rc_meta[max_chunks][8]: one record per (row, chunk) work item of the attention kernel
+ * {row, first token, page, row kv length, chunks of the row, first chunk index of the row, 0, 0}
+ * (32-byte aligned; records beyond max_chunks are not written and vb_paged_attn traps on overflow). */
 int vb_plan_rows(const int32_t* d_qo_indptr, const int32_t* d_kv_indptr, const int32_t* d_kv_indices,
-                 const int32_t* d_last_page_len, int n_req, int n_rows_padded, int page_size, int chunk_tokens,
+                 const int32_t* d_last_page_len, const int32_t* d_kv_len, int n_req, int n_rows_padded, int page_size,
+                 int chunk_tokens,
                  int32_t* d_row_req, int32_t* d_row_kvlen, int32_t* d_row_page, int32_t* d_row_slot,
-                 int32_t* d_row_chunk_start, void* stream);
+                 int32_t* d_row_chunk_start, int32_t* d_rc_meta, int max_chunks, void* stream);
 
 /* kv[page][0][slot] = k ; kv[page][1][slot] = v : flashinfer_utils.py:144-145, 243-244.
  * d_layer_kv points at one layer's [pages][2][page_size][n_kv][D]. */
@@ -73,16 +79,17 @@ int vb_kv_append(void* d_layer_kv, const void* d_k, const void* d_v, const int32
 
 /* ---- paged attention: FlashInferDecodeWrapper.run / FlashInferPrefillWrapper.run
  * (flashinfer_utils.py:132, 228-230).  One query row per entry of the plan; causal by construction
- * (row_kvlen).  q/out [R][n_q][D] bf16.  kv_map from vb_tensor_map_kv over the WHOLE cache;
- * slab_base = layer * pages_per_layer.  max_chunks_total bounds row_chunk_start[n_rows] (sizes the
- * split-KV partials).  d_workspace: vb_paged_attn_workspace_bytes(); it must be zero-filled once before
- * first use (arrival counters; the kernel restores them to zero).  grid_ctas: persistent grid size. */
+ * (row kv length).  q/out [R][n_q][D] bf16.  kv_map from vb_tensor_map_kv over the WHOLE cache;
+ * slab_base = layer * pages_per_layer.  d_row_chunk_start / d_rc_meta come from vb_plan_rows with the
+ * same chunk_tokens and max_chunks_total.  d_workspace: vb_paged_attn_workspace_bytes(); it must be
+ * zero-filled once before first use (arrival counters; the kernel restores them to zero).
+ * grid_ctas: persistent grid size (2 per SM is a good default). */
 size_t vb_paged_attn_workspace_bytes(int max_rows, int max_chunks_total, int n_q, int n_kv, int head_dim);
 int vb_paged_attn(void* d_out, const void* d_q, const void* kv_map, int64_t slab_base,
-                  const int32_t* d_kv_indptr, const int32_t* d_kv_indices, const int32_t* d_row_req,
-                  const int32_t* d_row_kvlen, const int32_t* d_row_chunk_start, int n_rows, int max_chunks_total,
-                  int n_q, int n_kv, int head_dim, int page_size, int chunk_tokens, float sm_scale,
-                  void* d_workspace, size_t workspace_bytes, int grid_ctas, void* stream);
+                  const int32_t* d_row_kvlen, const int32_t* d_row_chunk_start, const int32_t* d_rc_meta,
+                  int n_rows, int max_chunks_total, int n_q, int n_kv, int head_dim, int page_size,
+                  int chunk_tokens, float sm_scale, void* d_workspace, size_t workspace_bytes, int grid_ctas,
+                  void* stream);
 
 /* ---- dense projections (nn.Linear, bias-free): model/orpheus.py:41-47, 68-79, 197 -------------
  * Y[T][N] = X[T][K] * W[N][K]^T on tcgen05 (weights are the 128-row MMA operand, tokens the N side).
@@ -108,6 +115,17 @@ int vb_reduce_residual_rmsnorm(void* d_hidden_out, void* d_normed_out, const flo
 int vb_qkv_rope_append(void* d_q_out, void* d_layer_kv, const float* d_partials, int split_k, const int32_t* d_pos,
                        const float* d_freq, const int32_t* d_row_page, const int32_t* d_row_slot, int T, int n_q,
                        int n_kv, int head_dim, int page_size, int rotary_dim, int interleave, void* stream);
+/* device-resident decode loop (no host work between CUDA-graph replays; the reference does this bookkeeping
+ * in Python every step, worker/base.py:312-325, orpheus.py:447-448):
+ *   vb_decode_advance: kv_len[b] += 1, position[b] += 1 for active slots (d_active NULL = all);
+ *   vb_ids_feedback:   sampled ids (int64) -> next input ids (int32) + token history ring [cap][B], ++*counter;
+ *   vb_gather_windows: windows[b][j] = history[(first_step[b] + j) % cap][b], j < window
+ *                      (the detokenize window of cuda_graph_worker.py:1176-1190). */
+int vb_decode_advance(int32_t* d_kv_len, int32_t* d_pos, const int32_t* d_active, int B, void* stream);
+int vb_ids_feedback(const int64_t* d_ids, int32_t* d_next_input, int32_t* d_history, int32_t* d_step_counter, int B,
+                    int history_cap, void* stream);
+int vb_gather_windows(int64_t* d_windows, const int32_t* d_history, const int32_t* d_first_step, int B,
+                      int history_cap, int window, void* stream);
 /* embedding gather: orpheus.py:408 */
 int vb_embedding(void* d_out, const void* d_table, const int32_t* d_ids, int T, int dim, int vocab, void* stream);
 /* rows out[i] = in[idx[i]] (last-token gather, cuda_graph_worker.py:900-902) */
@@ -120,13 +138,15 @@ int vb_gather_rows(void* d_out, const void* d_in, const int32_t* d_idx, int n, i
  * rep_codebooks != 1 codebook 0 is used (sampling.py:140-141).  Penalty: sampling.py:143-144.
  * strategy: 0 greedy (argmax, first index on ties), 1 top-k, 2 top-p, 3 top-k then top-p, 4 min-p
  * (dispatch order of sampling.py:97-118 is applied by the host wrapper).  out_ids int64.
- * Draws use Philox4x32-10(seed, offset, row).  mask_token >= 0 forces that token's logit to -inf
+* Draws use Philox4x32-10(seed, offset, row); if d_rng_state (device uint64[2] = {seed, offset}) is given it
+ * overrides the immediates and its offset is advanced by one per call (CUDA-graph replays stay random).  mask_token >= 0 forces that token's logit to -inf
  * (benchmark hook to pin sequence lengths; -1 = off).  Workspace: vb_sample_workspace_bytes. */
 size_t vb_sample_workspace_bytes(int rows, int vocab);
 int vb_sample(int64_t* d_out_ids, const void* d_logits, int rows, int vocab, int ld_logits,
               const uint8_t* d_rep_cache, int rep_window_slots, int rep_codebooks, int logit_codebooks,
               float penalty, int strategy, int top_k, float top_p, float min_p, float temperature, uint64_t seed,
-              uint64_t offset, int mask_token, void* d_workspace, size_t workspace_bytes, void* stream);
+              uint64_t offset, uint64_t* d_rng_state, int mask_token, void* d_workspace, size_t workspace_bytes,
+              void* stream);
 /* penalised logits only (Sampler.apply_repetition_penalty, sampling.py:120-146), bf16 in/out, dense rows */
 int vb_apply_repetition_penalty(void* d_out, const void* d_logits, const uint8_t* d_rep_cache,
                                 int rep_window_slots, int rep_codebooks, int logit_codebooks, float penalty,

@@ -34,8 +34,11 @@ def bf16_ulp_diff(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return (key(a.cpu()) - key(b.cpu())).abs()
 
 
-def assert_bf16_close(got, ref, max_ulp=1, max_frac=2e-3, what=""):
+def assert_bf16_close(got, ref, max_ulp=1, max_frac=2e-3, what="", atol=0.0):
     d = bf16_ulp_diff(got, ref)
+    if atol > 0:  # results of cancelling sums: tiny values may sit many codes apart at negligible absolute error
+        small = (got.float().cpu() - ref.float().cpu()).abs() <= atol
+        d = torch.where(small, torch.zeros_like(d), d)
     frac = (d > 0).float().mean().item()
     assert d.max().item() <= max_ulp, f"{what}: max ulp {d.max().item()} (frac differing {frac:.2e})"
     assert frac <= max_frac, f"{what}: {frac:.2e} of elements differ"
@@ -74,8 +77,8 @@ def test_rope(ops, variant):
     np.testing.assert_allclose(freq.cpu().numpy(), ref_freq.numpy(), rtol=2e-6)
     gq, gk = ops.rope(q.cuda(), k.cuda(), pos.cuda(), freq, interleave=inter)
     # angles reach ~1400 rad: fp32 pos*freq products differ in the last ulp between powf implementations
-    assert_bf16_close(gq, rq, 2, 2e-2, "rope q")
-    assert_bf16_close(gk, rk, 2, 2e-2, "rope k")
+    assert_bf16_close(gq, rq, 2, 2e-2, "rope q", atol=4e-3)
+    assert_bf16_close(gk, rk, 2, 2e-2, "rope k", atol=4e-3)
     q2, k2 = q.cuda().clone(), k.cuda().clone()
     ops.rope(q2, k2, pos.cuda(), freq, interleave=inter, inplace=True)
     assert torch.equal(q2, gq) and torch.equal(k2, gk)
@@ -157,16 +160,20 @@ def _attn_case(ops, kv_lens, page_size, hq, hkv, D, seed, prefill_new=None, n_pa
         ref = lm_ops.paged_attention_prefill(q, cache[layer], qo, indptr, indices, last, page_size)
     dcache = cache.cuda()
     kv_map = ops.tensor_map_kv(dcache, chunk)
-    plan = ops.RowPlan(max(R, 8), "cuda")
+    if qo is None:
+        max_chunks = sum((L + chunk - 1) // chunk for L in kv_lens)
+    else:
+        max_chunks = sum((kv_lens[r] - prefill_new[r] + j + chunk) // chunk
+                         for r in range(len(kv_lens)) for j in range(prefill_new[r]))
+    plan = ops.RowPlan(max(R, 8), "cuda", max_chunks)
     d_indptr, d_indices = _i32(indptr), _i32(indices)
     ops.plan_rows(plan, None if qo is None else _i32(qo), d_indptr, d_indices, _i32(last), len(kv_lens), R,
                   page_size, chunk)
-    max_chunks = int(plan.row_chunk_start[R].item())
+    assert int(plan.row_chunk_start[R].item()) == max_chunks
     ws = ops.paged_attn_workspace(R, max_chunks, hq, hkv, D, "cuda")
     out = None
     for _ in range(2):  # second run checks that the arrival counters were restored
-        out = ops.paged_attn(q.cuda(), kv_map, layer * n_pages, d_indptr, d_indices, plan, R, max_chunks, hkv,
-                             page_size, chunk, ws)
+        out = ops.paged_attn(q.cuda(), kv_map, layer * n_pages, plan, R, hkv, page_size, chunk, ws)
     torch.cuda.synchronize()
     got, reff = out.float().cpu(), ref.float()
     err = (got - reff).abs()
@@ -219,7 +226,7 @@ def test_gemm_partials(ops, T, N, K, split):
     assert (got - ref).abs().max().item() < tol, (got - ref).abs().max().item()
     if split == 1:
         y = ops.gemm(x.cuda(), w.cuda(), mode=0)
-        assert_bf16_close(y, ref.to(BF), 1, 2e-2, "gemm bf16")
+        assert_bf16_close(y, ref.to(BF), 1, 2e-2, "gemm bf16", atol=tol)
 
 
 def test_gemm_lm_head_tail_tile(ops):
@@ -227,7 +234,8 @@ def test_gemm_lm_head_tail_tile(ops):
     x = torch.randn(T, K, generator=g(1)).to(BF)
     w = (torch.randn(N, K, generator=g(2)) * 0.05).to(BF)
     y = ops.gemm(x.cuda(), w.cuda(), mode=0)
-    assert_bf16_close(y, _gemm_ref(x, w).to(BF), 1, 2e-2, "lm_head")
+    ref = _gemm_ref(x, w)
+    assert_bf16_close(y, ref.to(BF), 1, 2e-2, "lm_head", atol=2e-3 * ref.abs().max().item())
 
 
 def test_gemm_gate_up_silu(ops):
@@ -279,8 +287,8 @@ def test_qkv_rope_append(ops):
     dcache = torch.zeros_like(cache).cuda()
     freq = ops.rope_freq_table(D, 32.0, 500000.0, False, 1.0, 4.0, 8192)
     gq = ops.qkv_rope_append(parts.cuda(), dcache, pos.cuda(), freq, plan, hq, hkv, D)
-    assert_bf16_close(gq, rq, 2, 2e-2, "fused rope q")
-    assert_bf16_close(dcache, cache, 2, 2e-2, "fused kv append")
+    assert_bf16_close(gq, rq, 2, 2e-2, "fused rope q", atol=4e-3)
+    assert_bf16_close(dcache, cache, 2, 2e-2, "fused kv append", atol=4e-3)
     # V rows are copied, not rotated: exact
     pg, sl = torch.tensor(pages), torch.tensor(slots)
     assert torch.equal(dcache.cpu()[pg, 1, sl], v)

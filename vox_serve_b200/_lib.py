@@ -22,10 +22,13 @@ SIGNATURES = {
     "vb_rmsnorm": (c_int, [P, P, P, c_int, c_int, c_float, P]),
     "vb_rope_freqs": (c_int, [P, c_int, c_int, c_float, c_float, c_int, c_float, c_float, c_float, P]),
     "vb_rope": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
-    "vb_plan_rows": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
+    "vb_plan_rows": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_int, P]),
+    "vb_decode_advance": (c_int, [P, P, P, c_int, P]),
+    "vb_ids_feedback": (c_int, [P, P, P, P, c_int, c_int, P]),
+    "vb_gather_windows": (c_int, [P, P, P, c_int, c_int, c_int, P]),
     "vb_kv_append": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     "vb_paged_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
-    "vb_paged_attn": (c_int, [P, P, P, c_int64, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+    "vb_paged_attn": (c_int, [P, P, P, c_int64, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_float, P, c_size_t, c_int, P]),
     "vb_gemm_t_tile": (c_int, [c_int]),
     "vb_gemm_bf16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
@@ -35,7 +38,7 @@ SIGNATURES = {
     "vb_gather_rows": (c_int, [P, P, P, c_int, c_int, P]),
     "vb_sample_workspace_bytes": (c_size_t, [c_int, c_int]),
     "vb_sample": (c_int, [P, P, c_int, c_int, c_int, P, c_int, c_int, c_int, c_float, c_int, c_int, c_float,
-                          c_float, c_float, c_uint64, c_uint64, c_int, P, c_size_t, P]),
+                          c_float, c_float, c_uint64, c_uint64, P, c_int, P, c_size_t, P]),
     "vb_apply_repetition_penalty": (c_int, [P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, P]),
     "vb_update_repetition_cache": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_snac_from_codes": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),

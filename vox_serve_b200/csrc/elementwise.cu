@@ -114,11 +114,13 @@ __global__ void __launch_bounds__(256) rope_kernel(__nv_bfloat16* __restrict__ q
 __global__ void __launch_bounds__(1024) plan_rows_kernel(const int32_t* __restrict__ qo_indptr,
                                                          const int32_t* __restrict__ kv_indptr,
                                                          const int32_t* __restrict__ kv_indices,
-                                                         const int32_t* __restrict__ last_page_len, int n_req,
+                                                         const int32_t* __restrict__ last_page_len,
+                                                         const int32_t* __restrict__ kv_len_in, int n_req,
                                                          int n_rows_padded, int page_size, int chunk,
                                                          int32_t* __restrict__ row_req, int32_t* __restrict__ row_kvlen,
                                                          int32_t* __restrict__ row_page, int32_t* __restrict__ row_slot,
-                                                         int32_t* __restrict__ row_chunk_start) {
+                                                         int32_t* __restrict__ row_chunk_start,
+                                                         int32_t* __restrict__ rc_meta, int max_chunks) {
   __shared__ int32_t warp_tot[32];
   __shared__ int32_t carry;
   const int tid = threadIdx.x;
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(1024) plan_rows_kernel(const int32_t* __restri
     const int row0 = qo_indptr ? qo_indptr[r] : r;
     const int n_new = qo_indptr ? qo_indptr[r + 1] - row0 : 1;
     const int p0 = kv_indptr[r];
-    const int kv_len = (kv_indptr[r + 1] - p0 - 1) * page_size + last_page_len[r];
+    const int kv_len = kv_len_in ? kv_len_in[r] : (kv_indptr[r + 1] - p0 - 1) * page_size + last_page_len[r];
     for (int j = 0; j < n_new; ++j) {
       const int row = row0 + j;
       if (row >= n_rows_padded) break;
@@ -176,6 +178,27 @@ __global__ void __launch_bounds__(1024) plan_rows_kernel(const int32_t* __restri
     __syncthreads();
   }
   if (tid == 0) row_chunk_start[n_rows_padded] = carry;
+  // pass 3: one record per (row, chunk) so the attention producer resolves a work item with one 32-byte load:
+  // {row, token0, page, kvlen, n_chunks, first_rc, 0, 0}
+  if (rc_meta) {
+    __syncthreads();
+    const int n_rc = min(carry, max_chunks);
+    for (int rc = tid; rc < n_rc; rc += blockDim.x) {
+      int lo = 0, hi = n_rows_padded;  // largest row with row_chunk_start[row] <= rc
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (row_chunk_start[mid] <= rc) lo = mid; else hi = mid;
+      }
+      const int row = lo, first = row_chunk_start[row];
+      const int token0 = (rc - first) * chunk;
+      const int req = row_req[row];
+      int4 a, b;
+      a.x = row; a.y = token0; a.z = kv_indices[kv_indptr[req] + token0 / page_size]; a.w = row_kvlen[row];
+      b.x = row_chunk_start[row + 1] - first; b.y = first; b.z = 0; b.w = 0;
+      reinterpret_cast<int4*>(rc_meta)[rc * 2] = a;
+      reinterpret_cast<int4*>(rc_meta)[rc * 2 + 1] = b;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -396,18 +419,19 @@ int vb_rope(void* d_q_out, void* d_k_out, const void* d_q, const void* d_k, cons
 }
 
 int vb_plan_rows(const int32_t* d_qo_indptr, const int32_t* d_kv_indptr, const int32_t* d_kv_indices,
-                 const int32_t* d_last_page_len, int n_req, int n_rows_padded, int page_size, int chunk_tokens,
+                 const int32_t* d_last_page_len, const int32_t* d_kv_len, int n_req, int n_rows_padded, int page_size,
+                 int chunk_tokens,
                  int32_t* d_row_req, int32_t* d_row_kvlen, int32_t* d_row_page, int32_t* d_row_slot,
-                 int32_t* d_row_chunk_start, void* stream) {
-  VB_CHECK_ARG(d_kv_indptr && d_kv_indices && d_last_page_len && d_row_req && d_row_kvlen && d_row_page &&
-                   d_row_slot && d_row_chunk_start,
+                 int32_t* d_row_chunk_start, int32_t* d_rc_meta, int max_chunks, void* stream) {
+  VB_CHECK_ARG(d_kv_indptr && d_kv_indices && (d_last_page_len || d_kv_len) && d_row_req && d_row_kvlen &&
+                   d_row_page && d_row_slot && d_row_chunk_start,
                "vb_plan_rows: null pointer");
   VB_CHECK_ARG(page_size > 0 && chunk_tokens > 0 && page_size % chunk_tokens == 0,
                "vb_plan_rows: chunk_tokens %d must divide page_size %d", chunk_tokens, page_size);
   VB_CHECK_ARG(n_req >= 0 && n_rows_padded >= 0, "vb_plan_rows: negative sizes");
   plan_rows_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_qo_indptr, d_kv_indptr, d_kv_indices, d_last_page_len, n_req, n_rows_padded, page_size, chunk_tokens,
-      d_row_req, d_row_kvlen, d_row_page, d_row_slot, d_row_chunk_start);
+      d_qo_indptr, d_kv_indptr, d_kv_indices, d_last_page_len, d_kv_len, n_req, n_rows_padded, page_size, chunk_tokens,
+      d_row_req, d_row_kvlen, d_row_page, d_row_slot, d_row_chunk_start, d_rc_meta, max_chunks);
   VB_CHECK_LAUNCH();
   return 0;
 }
@@ -498,4 +522,70 @@ int vb_orpheus_window_codes(int32_t* d_c0, int32_t* d_c1, int32_t* d_c2, const i
   return 0;
 }
 
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// device-resident decode loop helpers: no host work between CUDA-graph replays
+// ------------------------------------------------------------------------------------------
+namespace vb {
+// state = {kv_len[B], position[B]} advance by one token per request (worker/base.py:312-325 does this on
+// the host); active[b] == 0 freezes a slot.
+__global__ void decode_advance_kernel(int32_t* kv_len, int32_t* pos, const int32_t* active, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B && (!active || active[b])) {
+    kv_len[b] += 1;
+    pos[b] += 1;
+  }
+}
+// sampled ids (int64) -> next step's input ids (int32) and the token history ring [cap][B];
+// *step_counter is advanced by thread 0.
+__global__ void ids_feedback_kernel(const int64_t* ids, int32_t* next_input, int32_t* history, int32_t* step_counter,
+                                    int B, int cap) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int step = *step_counter;
+  if (b < B) {
+    const int v = static_cast<int>(ids[b]);
+    next_input[b] = v;
+    if (history) history[static_cast<size_t>(step % cap) * B + b] = v;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *step_counter = step + 1;
+}
+// windows[b][j] = history[(first_step + j) % cap][b] for j < win : the 28-token detokenize window
+// (cuda_graph_worker.py:1176-1190) gathered on the device.  first_step[b] per request.
+__global__ void gather_windows_kernel(int64_t* windows, const int32_t* history, const int32_t* first_step, int B,
+                                      int cap, int win) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * win) return;
+  const int b = i / win, j = i - b * win;
+  windows[i] = history[static_cast<size_t>((first_step[b] + j) % cap) * B + b];
+}
+}  // namespace vb
+
+extern "C" {
+int vb_decode_advance(int32_t* d_kv_len, int32_t* d_pos, const int32_t* d_active, int B, void* stream) {
+  VB_CHECK_ARG(d_kv_len && d_pos, "vb_decode_advance: null pointer");
+  if (B <= 0) return 0;
+  vb::decode_advance_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_kv_len, d_pos, d_active, B);
+  VB_CHECK_LAUNCH();
+  return 0;
+}
+int vb_ids_feedback(const int64_t* d_ids, int32_t* d_next_input, int32_t* d_history, int32_t* d_step_counter, int B,
+                    int history_cap, void* stream) {
+  VB_CHECK_ARG(d_ids && d_next_input && d_step_counter, "vb_ids_feedback: null pointer");
+  VB_CHECK_ARG(B > 0 && B <= 1024 && history_cap > 0, "vb_ids_feedback: bad sizes");
+  vb::ids_feedback_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(d_ids, d_next_input, d_history,
+                                                                            d_step_counter, B, history_cap);
+  VB_CHECK_LAUNCH();
+  return 0;
+}
+int vb_gather_windows(int64_t* d_windows, const int32_t* d_history, const int32_t* d_first_step, int B,
+                      int history_cap, int window, void* stream) {
+  VB_CHECK_ARG(d_windows && d_history && d_first_step, "vb_gather_windows: null pointer");
+  if (B <= 0) return 0;
+  vb::gather_windows_kernel<<<(B * window + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_windows, d_history, d_first_step, B, history_cap, window);
+  VB_CHECK_LAUNCH();
+  return 0;
+}
 }  // extern "C"

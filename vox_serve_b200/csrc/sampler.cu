@@ -26,6 +26,7 @@ struct SampleParams {
   float top_p, min_p;
   int mask_token;
   uint64_t seed, offset;
+  unsigned long long* rng_state;   // optional device {seed, offset}: offset advances by one per vb_sample call
   unsigned long long* packed;  // [rows] greedy result
   uint32_t* hist;              // [rows][65536]
   uint32_t* pick;              // [rows][2]  (key, rank)
@@ -271,7 +272,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const SampleParams p
   }
   excl = block_excl_scan(wpart, sh, &total);
   if (tid == 0) {
-    const double u = philox_uniform(p.seed, p.offset, static_cast<uint32_t>(row));
+    const uint64_t seed = p.rng_state ? p.rng_state[0] : p.seed;
+    const uint64_t offset = p.rng_state ? p.rng_state[1] : p.offset;
+    const double u = philox_uniform(seed, offset, static_cast<uint32_t>(row));
     unsigned long long target = static_cast<unsigned long long>(u * static_cast<double>(total));
     if (target >= total) target = total ? total - 1 : 0;
     sh_u[0] = target;
@@ -313,6 +316,7 @@ __global__ void __launch_bounds__(1024) resolve_kernel(const SampleParams p) {
   unsigned long long total;
   const unsigned long long excl = block_excl_scan(c, sh, &total);
   if (tid == 0 && total == 0ull) p.out[row] = 0;
+  if (tid == 0 && row == 0 && p.rng_state) p.rng_state[1] += 1ull;   // all scan CTAs have finished (stream order)
   if (c != 0ull && excl <= rank && rank < excl + c) {
     unsigned long long run = excl;
     for (int i = i0; i < i1; ++i) {
@@ -377,7 +381,7 @@ size_t vb_sample_workspace_bytes(int rows, int vocab) {
 static int fill_params(SampleParams& p, int64_t* d_out_ids, const void* d_logits, int rows, int vocab, int ld,
                        const uint8_t* d_rep_cache, int W, int C_cache, int C_logits, float penalty, int strategy,
                        int top_k, float top_p, float min_p, float temperature, uint64_t seed, uint64_t offset,
-                       int mask_token, void* ws) {
+                       int mask_token, void* ws, uint64_t* rng_state = nullptr) {
   p.logits = static_cast<const __nv_bfloat16*>(d_logits);
   p.rep_cache = d_rep_cache;
   p.rows = rows; p.vocab = vocab; p.ld = ld;
@@ -385,6 +389,7 @@ static int fill_params(SampleParams& p, int64_t* d_out_ids, const void* d_logits
   p.penalty = penalty; p.temperature = temperature;
   p.strategy = strategy; p.top_k = top_k; p.top_p = top_p; p.min_p = min_p;
   p.mask_token = mask_token; p.seed = seed; p.offset = offset;
+  p.rng_state = reinterpret_cast<unsigned long long*>(rng_state);
   uint8_t* w = static_cast<uint8_t*>(ws);
   p.hist = reinterpret_cast<uint32_t*>(w);
   p.packed = w ? reinterpret_cast<unsigned long long*>(w + static_cast<size_t>(rows) * 65536 * 4) : nullptr;
@@ -397,7 +402,8 @@ static int fill_params(SampleParams& p, int64_t* d_out_ids, const void* d_logits
 int vb_sample(int64_t* d_out_ids, const void* d_logits, int rows, int vocab, int ld_logits,
               const uint8_t* d_rep_cache, int rep_window_slots, int rep_codebooks, int logit_codebooks,
               float penalty, int strategy, int top_k, float top_p, float min_p, float temperature, uint64_t seed,
-              uint64_t offset, int mask_token, void* d_workspace, size_t workspace_bytes, void* stream) {
+              uint64_t offset, uint64_t* d_rng_state, int mask_token, void* d_workspace, size_t workspace_bytes,
+              void* stream) {
   VB_CHECK_ARG(d_out_ids && d_logits && d_workspace, "vb_sample: null pointer");
   VB_CHECK_ARG(strategy >= 0 && strategy <= 4, "vb_sample: strategy %d", strategy);
   VB_CHECK_ARG(workspace_bytes >= vb_sample_workspace_bytes(rows, vocab), "vb_sample: workspace too small");
@@ -409,7 +415,7 @@ int vb_sample(int64_t* d_out_ids, const void* d_logits, int rows, int vocab, int
   SampleParams p;
   fill_params(p, d_out_ids, d_logits, rows, vocab, ld_logits, d_rep_cache, rep_window_slots, rep_codebooks,
               logit_codebooks, penalty, strategy, top_k, top_p, min_p, temperature, seed, offset, mask_token,
-              d_workspace);
+              d_workspace, d_rng_state);
   const int gx = max(1, min(32, (vocab + 256 * 8 - 1) / (256 * 8)));
   if (strategy == 0) {
     VB_CHECK_CUDA(cudaMemsetAsync(p.packed, 0, static_cast<size_t>(rows) * 8, st));

@@ -1,0 +1,182 @@
+"""Llama-shaped LM forward on the sm_100a kernels: the arithmetic of ``OrpheusForCausalLM.forward``
+(vox_serve/model/orpheus.py:125-221) as a fixed sequence of C-ABI launches over preallocated buffers, so
+the whole step is CUDA-graph capturable (no host sync, no allocation).
+
+Per layer (8 launches; the reference issues ~18-20):
+    QKV GEMM (split-K partials)  ->  reduce + RoPE + KV-append  ->  paged attention
+    -> O GEMM (partials) -> reduce + residual + post-attention RMSNorm
+    -> gate/up GEMM with SiLU*up epilogue -> down GEMM (partials) -> reduce + residual + next RMSNorm
+Rounding points follow the reference module graph: every Linear / RMSNorm / RoPE / attention output and
+every residual add is rounded to bf16.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from ._lib import VoxB200Error
+
+BF16 = torch.bfloat16
+
+
+@dataclass
+class LlamaDims:
+    hidden_size: int
+    num_hidden_layers: int
+    num_attention_heads: int
+    num_key_value_heads: int
+    head_dim: int
+    intermediate_size: int
+    vocab_size: int
+    rms_norm_eps: float = 1e-5
+    rope_theta: float = 500000.0
+    rope_factor: float = 32.0
+    low_freq_factor: Optional[float] = 1.0
+    high_freq_factor: Optional[float] = 4.0
+    old_context_len: Optional[float] = 8192
+
+    @classmethod
+    def orpheus_3b(cls):
+        return cls(3072, 28, 24, 8, 128, 8192, 156940)
+
+
+def hf_layer_names(i: int) -> Dict[str, str]:
+    p = f"model.layers.{i}."
+    return {"ln1": p + "input_layernorm.weight", "ln2": p + "post_attention_layernorm.weight",
+            "q": p + "self_attn.q_proj.weight", "k": p + "self_attn.k_proj.weight",
+            "v": p + "self_attn.v_proj.weight", "o": p + "self_attn.o_proj.weight",
+            "gate": p + "mlp.gate_proj.weight", "up": p + "mlp.up_proj.weight", "down": p + "mlp.down_proj.weight"}
+
+
+class LlamaWeights:
+    """Device-resident weights in the layout the kernels stream: q|k|v rows concatenated, gate/up rows
+    interleaved per 128-row tile (ops.interleave_gate_up); built from an HF-named state dict."""
+
+    def __init__(self, dims: LlamaDims, device="cuda"):
+        self.dims, self.device = dims, torch.device(device)
+        self.embed = self.norm = self.lm_head = None
+        self.layers: List[Dict[str, torch.Tensor]] = []
+
+    @classmethod
+    def from_state_dict(cls, sd, dims: LlamaDims, device="cuda"):
+        self = cls(dims, device)
+        dev = self.device
+
+        def put(t):
+            return t.to(device=dev, dtype=BF16).contiguous()
+
+        self.embed = put(sd["model.embed_tokens.weight"])
+        self.norm = put(sd["model.norm.weight"])
+        self.lm_head = put(sd["lm_head.weight"] if "lm_head.weight" in sd else sd["model.embed_tokens.weight"])
+        for i in range(dims.num_hidden_layers):
+            n = hf_layer_names(i)
+            self.layers.append(self.pack_layer(put(sd[n["ln1"]]), put(sd[n["q"]]), put(sd[n["k"]]), put(sd[n["v"]]),
+                                               put(sd[n["o"]]), put(sd[n["ln2"]]), put(sd[n["gate"]]),
+                                               put(sd[n["up"]]), put(sd[n["down"]])))
+        return self
+
+    @staticmethod
+    def pack_layer(ln1, q, k, v, o, ln2, gate, up, down) -> Dict[str, torch.Tensor]:
+        return {"ln1": ln1, "ln2": ln2, "qkv": torch.cat((q, k, v), 0).contiguous(), "o": o,
+                "gu": ops.interleave_gate_up(gate, up), "down": down}
+
+    def nbytes(self) -> int:
+        n = self.embed.numel() + self.norm.numel() + self.lm_head.numel()
+        for l in self.layers:
+            n += sum(t.numel() for t in l.values())
+        return 2 * n
+
+    def streamed_bytes_per_step(self) -> int:
+        """Weight bytes one decode step must read (everything but the embedding table)."""
+        return self.nbytes() - 2 * self.embed.numel()
+
+
+class LlamaEngine:
+    def __init__(self, weights: LlamaWeights, kv_cache: torch.Tensor, page_size: int, max_rows: int,
+                 max_seq_len: int = 2304):
+        d = weights.dims
+        self.w, self.dims, self.kv_cache, self.page_size = weights, d, kv_cache, page_size
+        self.device = kv_cache.device
+        assert kv_cache.shape[0] == d.num_hidden_layers and kv_cache.shape[2] == 2
+        self.pages_per_layer = kv_cache.shape[1]
+        self.chunk = ops.attn_chunk_tokens(page_size)
+        self.kv_map = ops.tensor_map_kv(kv_cache, self.chunk)
+        self.max_rows = max_rows
+        chunks_per_page = page_size // self.chunk
+        # attention work items (row, chunk): decode rows share the cache's pages; prefill rows each see up to
+        # max_seq_len tokens.  The plan / attention kernels trap if a step exceeds this bound.
+        per_row = (max_seq_len + self.chunk - 1) // self.chunk
+        decode_bound = self.pages_per_layer * chunks_per_page
+        self.max_chunks = max(64, min(decode_bound, max_rows * per_row) if max_rows <= 64 else max_rows * per_row)
+        self.sms = ops.device_info()[0]
+        H, I = d.hidden_size, d.intermediate_size
+        hq, hkv, D = d.num_attention_heads, d.num_key_value_heads, d.head_dim
+        self.qkv_w = (hq + 2 * hkv) * D
+        dev = self.device
+        R = max_rows
+        self.split_qkv = ops.choose_split_k(self.qkv_w, H, 32, self.sms)
+        self.split_o = ops.choose_split_k(H, hq * D, 32, self.sms)
+        self.split_down = ops.choose_split_k(H, I, 32, self.sms)
+        smax = max(self.split_qkv, self.split_o, self.split_down)
+        self.hidden = torch.zeros(R, H, dtype=BF16, device=dev)
+        self.normed = torch.zeros(R, H, dtype=BF16, device=dev)
+        self.partials = torch.zeros(max(smax * min(R, 64), R) * max(self.qkv_w, H), dtype=torch.float32, device=dev)
+        self.q = torch.zeros(R, hq, D, dtype=BF16, device=dev)
+        self.attn = torch.zeros(R, hq, D, dtype=BF16, device=dev)
+        self.act = torch.zeros(R, I, dtype=BF16, device=dev)
+        self.max_out_rows = min(R, 64)     # logits are only ever needed for one row per request
+        self.last_normed = torch.zeros(self.max_out_rows, H, dtype=BF16, device=dev)
+        self.logits = torch.zeros(self.max_out_rows, d.vocab_size, dtype=BF16, device=dev)
+        self.attn_ws = ops.paged_attn_workspace(R, self.max_chunks, hq, hkv, D, dev)
+        self.freq = ops.rope_freq_table(D, d.rope_factor, d.rope_theta, False, d.low_freq_factor,
+                                        d.high_freq_factor, d.old_context_len, device=dev)
+        self.plan = ops.RowPlan(R, dev, self.max_chunks)
+        self.attn_grid = 2 * self.sms
+
+    def _partials(self, split: int, rows: int, width: int) -> torch.Tensor:
+        return self.partials[: split * rows * width].view(split, rows, width)
+
+    def _split(self, base: int, rows: int) -> int:
+        # large-T (prefill) problems already fill the machine with token tiles x N tiles
+        return base if rows <= 64 else 1
+
+    def forward(self, input_ids: torch.Tensor, position_ids: torch.Tensor, n_rows: int,
+                last_rows: Optional[torch.Tensor] = None, n_out: Optional[int] = None,
+                plan: Optional[ops.RowPlan] = None) -> torch.Tensor:
+        """input_ids / position_ids int32 [n_rows] on the device; self.plan must hold the step's row plan
+        (ops.plan_rows).  Returns logits [n_out or n_rows, vocab] bf16 (a view of the static buffer).
+        last_rows (int32 [n_out]) selects the rows whose logits are needed (prefill: qo_indptr[1:] - 1)."""
+        d, w, R = self.dims, self.w, n_rows
+        plan = self.plan if plan is None else plan
+        if plan.max_chunks > self.max_chunks:
+            raise VoxB200Error("row plan allows more attention chunks than the engine workspace holds")
+        if R > self.max_rows:
+            raise VoxB200Error(f"{R} rows exceed the engine's max_rows {self.max_rows}")
+        hq, hkv, D, H, I = d.num_attention_heads, d.num_key_value_heads, d.head_dim, d.hidden_size, d.intermediate_size
+        hidden, normed = self.hidden[:R], self.normed[:R]
+        ops.embedding(w.embed, input_ids, out=hidden)
+        ops.rmsnorm(hidden, w.layers[0]["ln1"], d.rms_norm_eps, out=normed)
+        s_qkv, s_o, s_dn = self._split(self.split_qkv, R), self._split(self.split_o, R), self._split(self.split_down, R)
+        q, attn, act = self.q[:R], self.attn[:R], self.act[:R]
+        for i, L in enumerate(w.layers):
+            p = ops.gemm(normed, L["qkv"], mode=1, split_k=s_qkv, out=self._partials(s_qkv, R, self.qkv_w))
+            ops.qkv_rope_append(p, self.kv_cache[i], position_ids, self.freq, plan, hq, hkv, D, q_out=q)
+            ops.paged_attn(q, self.kv_map, i * self.pages_per_layer, plan, R, hkv, self.page_size, self.chunk,
+                           self.attn_ws, out=attn, grid_ctas=self.attn_grid)
+            p = ops.gemm(attn.view(R, hq * D), L["o"], mode=1, split_k=s_o, out=self._partials(s_o, R, H))
+            ops.reduce_residual_rmsnorm(p, hidden, L["ln2"], d.rms_norm_eps, hidden_out=hidden, normed_out=normed)
+            ops.gemm(normed, L["gu"], mode=2, out=act)
+            p = ops.gemm(act, L["down"], mode=1, split_k=s_dn, out=self._partials(s_dn, R, H))
+            nxt = w.layers[i + 1]["ln1"] if i + 1 < len(w.layers) else w.norm
+            ops.reduce_residual_rmsnorm(p, hidden, nxt, d.rms_norm_eps, hidden_out=hidden, normed_out=normed)
+        if last_rows is not None:
+            n_out = last_rows.numel() if n_out is None else n_out
+            x = ops.gather_rows(normed, last_rows, out=self.last_normed[:n_out])
+        else:
+            n_out, x = R, normed
+        if n_out > self.max_out_rows:
+            raise VoxB200Error(f"logits requested for {n_out} rows; pass last_rows (max {self.max_out_rows})")
+        return ops.gemm(x, w.lm_head, mode=0, out=self.logits[:n_out])

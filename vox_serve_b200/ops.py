@@ -149,25 +149,29 @@ def attn_chunk_tokens(page_size: int) -> int:
 
 
 class RowPlan:
-    """Device-side per-row metadata produced by vb_plan_rows (see include/vb_api.h)."""
+    """Device-side per-row / per-chunk metadata produced by vb_plan_rows (see include/vb_api.h)."""
 
-    def __init__(self, max_rows: int, device):
+    def __init__(self, max_rows: int, device, max_chunks: Optional[int] = None):
         self.max_rows = max_rows
+        self.max_chunks = int(max_chunks) if max_chunks is not None else max(64, 4 * max_rows)
         self.buf = torch.zeros(5 * max_rows + 8, dtype=torch.int32, device=device)
         m = max_rows
         self.row_req, self.row_kvlen = self.buf[0:m], self.buf[m:2 * m]
         self.row_page, self.row_slot = self.buf[2 * m:3 * m], self.buf[3 * m:4 * m]
         self.row_chunk_start = self.buf[4 * m:5 * m + 1]
+        self.rc_meta = torch.zeros(self.max_chunks * 8, dtype=torch.int32, device=device)
         self.n_rows = 0
 
 
 def plan_rows(plan: RowPlan, qo_indptr: Optional[torch.Tensor], kv_indptr: torch.Tensor, kv_indices: torch.Tensor,
-              last_page_len: torch.Tensor, n_req: int, n_rows: int, page_size: int, chunk_tokens: int) -> RowPlan:
-    _need_cuda(kv_indptr, kv_indices, last_page_len)
+              last_page_len: Optional[torch.Tensor], n_req: int, n_rows: int, page_size: int, chunk_tokens: int,
+              kv_len: Optional[torch.Tensor] = None) -> RowPlan:
+    _need_cuda(kv_indptr, kv_indices, last_page_len, kv_len)
     assert n_rows <= plan.max_rows
-    call("vb_plan_rows", _p(qo_indptr), kv_indptr.data_ptr(), kv_indices.data_ptr(), last_page_len.data_ptr(),
+    call("vb_plan_rows", _p(qo_indptr), kv_indptr.data_ptr(), kv_indices.data_ptr(), _p(last_page_len), _p(kv_len),
          n_req, n_rows, page_size, chunk_tokens, plan.row_req.data_ptr(), plan.row_kvlen.data_ptr(),
-         plan.row_page.data_ptr(), plan.row_slot.data_ptr(), plan.row_chunk_start.data_ptr(), _stream())
+         plan.row_page.data_ptr(), plan.row_slot.data_ptr(), plan.row_chunk_start.data_ptr(),
+         plan.rc_meta.data_ptr(), plan.max_chunks, _stream())
     plan.n_rows = n_rows
     return plan
 
@@ -185,22 +189,21 @@ def paged_attn_workspace(max_rows: int, max_chunks: int, n_q: int, n_kv: int, he
     return torch.zeros(n, dtype=torch.uint8, device=device)
 
 
-def paged_attn(q: torch.Tensor, kv_map: TensorMap, slab_base: int, kv_indptr: torch.Tensor,
-               kv_indices: torch.Tensor, plan: RowPlan, n_rows: int, max_chunks: int, n_kv: int, page_size: int,
-               chunk_tokens: int, workspace: torch.Tensor, sm_scale: Optional[float] = None,
+def paged_attn(q: torch.Tensor, kv_map: TensorMap, slab_base: int, plan: RowPlan, n_rows: int, n_kv: int,
+               page_size: int, chunk_tokens: int, workspace: torch.Tensor, sm_scale: Optional[float] = None,
                out: Optional[torch.Tensor] = None, grid_ctas: Optional[int] = None) -> torch.Tensor:
-    """q [R, Hq, D] bf16 -> [R, Hq, D]."""
-    _need_cuda(q, kv_indptr, kv_indices, workspace)
+    """q [R, Hq, D] bf16 -> [R, Hq, D].  `plan` must come from plan_rows with the same chunk_tokens; the
+    workspace must be sized for plan.max_chunks (paged_attn_workspace)."""
+    _need_cuda(q, workspace)
     assert q.dtype == BF16 and q.is_contiguous()
     n_q, d = q.shape[1], q.shape[2]
     out = torch.empty_like(q) if out is None else out
     if grid_ctas is None:
         grid_ctas = 2 * device_info()[0]
     sc = 1.0 / math.sqrt(d) if sm_scale is None else float(sm_scale)
-    call("vb_paged_attn", out.data_ptr(), q.data_ptr(), kv_map.ptr, int(slab_base), kv_indptr.data_ptr(),
-         kv_indices.data_ptr(), plan.row_req.data_ptr(), plan.row_kvlen.data_ptr(), plan.row_chunk_start.data_ptr(),
-         n_rows, max_chunks, n_q, n_kv, d, page_size, chunk_tokens, sc, workspace.data_ptr(), workspace.numel(),
-         int(grid_ctas), _stream())
+    call("vb_paged_attn", out.data_ptr(), q.data_ptr(), kv_map.ptr, int(slab_base), plan.row_kvlen.data_ptr(),
+         plan.row_chunk_start.data_ptr(), plan.rc_meta.data_ptr(), n_rows, plan.max_chunks, n_q, n_kv, d,
+         page_size, chunk_tokens, sc, workspace.data_ptr(), workspace.numel(), int(grid_ctas), _stream())
     return out
 
 
@@ -326,7 +329,7 @@ def _cache_u8(rep_cache: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 def sample(logits: torch.Tensor, strategy: str, rep_cache: Optional[torch.Tensor] = None, penalty: float = 1.0,
            logit_codebooks: int = 1, top_k: int = 0, top_p: float = 1.0, min_p: float = 0.0, temperature: float = 1.0,
            seed: int = 0, offset: int = 0, mask_token: int = -1, out: Optional[torch.Tensor] = None,
-           workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+           workspace: Optional[torch.Tensor] = None, rng_state: Optional[torch.Tensor] = None) -> torch.Tensor:
     """logits [rows, V] bf16 (row stride arbitrary) -> ids int64 [rows]."""
     _need_cuda(logits)
     assert logits.dtype == BF16 and logits.dim() == 2 and logits.stride(1) == 1
@@ -337,7 +340,8 @@ def sample(logits: torch.Tensor, strategy: str, rep_cache: Optional[torch.Tensor
     W, Cc = (c8.shape[1], c8.shape[2]) if c8 is not None else (0, 0)
     call("vb_sample", out.data_ptr(), logits.data_ptr(), rows, V, logits.stride(0), _p(c8), W, Cc, logit_codebooks,
          float(penalty), STRATEGY[strategy], int(top_k or 0), float(top_p if top_p is not None else 1.0),
-         float(min_p or 0.0), float(temperature), int(seed), int(offset), int(mask_token), ws.data_ptr(), ws.numel(),
+         float(min_p or 0.0), float(temperature), int(seed), int(offset), _p(rng_state), int(mask_token), ws.data_ptr(),
+         ws.numel(),
          _stream())
     return out
 
@@ -361,6 +365,29 @@ def update_repetition_cache(rep_cache: torch.Tensor, ids: torch.Tensor, window: 
     B, W, Cc, V = c8.shape
     call("vb_update_repetition_cache", c8.data_ptr(), ids64.data_ptr(), B, W, Cc, V, ids64.shape[1], int(window),
          _stream())
+
+
+# ----------------------------------------------------------------------------------------------
+# device-resident decode loop helpers
+# ----------------------------------------------------------------------------------------------
+def decode_advance(kv_len: torch.Tensor, pos: torch.Tensor, active: Optional[torch.Tensor] = None):
+    call("vb_decode_advance", kv_len.data_ptr(), pos.data_ptr(), _p(active), kv_len.numel(), _stream())
+
+
+def ids_feedback(ids: torch.Tensor, next_input: torch.Tensor, history: Optional[torch.Tensor],
+                 step_counter: torch.Tensor):
+    cap = history.shape[0] if history is not None else 1
+    call("vb_ids_feedback", ids.data_ptr(), next_input.data_ptr(), _p(history), step_counter.data_ptr(),
+         ids.numel(), cap, _stream())
+
+
+def gather_windows(history: torch.Tensor, first_step: torch.Tensor, window: int,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    B = first_step.numel()
+    out = torch.empty(B, window, dtype=torch.int64, device=history.device) if out is None else out
+    call("vb_gather_windows", out.data_ptr(), history.data_ptr(), first_step.data_ptr(), B, history.shape[0],
+         window, _stream())
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
