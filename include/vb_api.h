@@ -115,25 +115,36 @@ int vb_reduce_residual_rmsnorm(void* d_hidden_out, void* d_normed_out, const flo
 int vb_qkv_rope_append(void* d_q_out, void* d_layer_kv, const float* d_partials, int split_k, const int32_t* d_pos,
                        const float* d_freq, const int32_t* d_row_page, const int32_t* d_row_slot, int T, int n_q,
                        int n_kv, int head_dim, int page_size, int rotary_dim, int interleave, void* stream);
-/* device-resident decode loop (no host work between CUDA-graph replays; the reference does this bookkeeping
- * in Python every step, worker/base.py:312-325, orpheus.py:447-448):
- *   vb_decode_advance: kv_len[b] += 1, position[b] += 1 for active slots (d_active NULL = all);
- *   vb_ids_feedback:   sampled ids (int64) -> next input ids (int32) + token history ring [cap][B], ++*counter;
- *   vb_gather_windows: windows[b][j] = history[(first_step[b] + j) % cap][b], j < window
- *                      (the detokenize window of cuda_graph_worker.py:1176-1190). */
+/* slot-resident decode state (no host work between CUDA-graph replays; the reference does this bookkeeping
+ * in Python every step, worker/base.py:312-325, orpheus.py:447-458):
+ *   vb_decode_advance:  kv_len[b] += 1, position[b] += 1 for active rows (d_active NULL = all);
+ *   vb_token_feedback:  sampled id of batch row b (int64) -> slot s = d_slots[b] (NULL = b):
+ *                       next_input[s] = id; history[s][n_out[s] % cap] = id; ++n_out[s];
+ *   vb_gather_i32:      out[i] = src[idx[i]] (next step's input ids by slot);
+ *   vb_build_input_ids: out[i] = row_slot[i] >= 0 ? next_input[row_slot[i]] : host_ids[i]  (decode rows feed
+ *                       back the id sampled last step, prefill rows use the uploaded prompt ids; replaces the
+ *                       torch.cat of worker/base.py:329);
+ *   vb_gather_windows:  windows[i][j] = history[slot[i]][(first[i] + min(j, n_valid[i]-1)) % cap], j < window
+ *                       (the detokenize window of cuda_graph_worker.py:1176-1190 incl. last-token padding). */
 int vb_decode_advance(int32_t* d_kv_len, int32_t* d_pos, const int32_t* d_active, int B, void* stream);
-int vb_ids_feedback(const int64_t* d_ids, int32_t* d_next_input, int32_t* d_history, int32_t* d_step_counter, int B,
-                    int history_cap, void* stream);
-int vb_gather_windows(int64_t* d_windows, const int32_t* d_history, const int32_t* d_first_step, int B,
-                      int history_cap, int window, void* stream);
+int vb_token_feedback(const int64_t* d_ids, const int32_t* d_slots, int32_t* d_next_input, int32_t* d_history,
+                      int32_t* d_n_out, int B, int history_cap, void* stream);
+int vb_gather_i32(int32_t* d_out, const int32_t* d_src, const int32_t* d_idx, int n, void* stream);
+int vb_build_input_ids(int32_t* d_out, const int32_t* d_host_ids, const int32_t* d_next_input,
+                       const int32_t* d_row_slot, int n, void* stream);
+int vb_gather_windows(int64_t* d_windows, const int32_t* d_history, const int32_t* d_slot, const int32_t* d_first,
+                      const int32_t* d_n_valid, int n, int history_cap, int window, void* stream);
 /* embedding gather: orpheus.py:408 */
 int vb_embedding(void* d_out, const void* d_table, const int32_t* d_ids, int T, int dim, int vocab, void* stream);
-/* rows out[i] = in[idx[i]] (last-token gather, cuda_graph_worker.py:900-902) */
-int vb_gather_rows(void* d_out, const void* d_in, const int32_t* d_idx, int n, int row_bytes, void* stream);
+/* rows out[i] = in[idx[i] + idx_offset] (last-token gather qo_indptr[1:] - 1, cuda_graph_worker.py:900-902) */
+int vb_gather_rows(void* d_out, const void* d_in, const int32_t* d_idx, int n, int row_bytes, int idx_offset,
+                   void* stream);
 
 /* ---- sampler: vox_serve/sampling.py (whole file) ---------------------------------------------
  * logits [rows][vocab] bf16 with leading dimension ld_logits, rows = batch * logit_codebooks.
  * d_rep_cache: uint8 (torch.bool) repetition cache [batch][rep_window_slots][rep_codebooks][vocab] or NULL;
+ * d_cache_rows (optional int32 [batch]): batch row b uses cache row d_cache_rows[b] (caches kept resident per
+ * batch slot instead of being re-stacked every step as worker/base.py:345 does);
  * a token is "seen" if any window slot has it (sampling.py:137); if logit_codebooks == 1 and
  * rep_codebooks != 1 codebook 0 is used (sampling.py:140-141).  Penalty: sampling.py:143-144.
  * strategy: 0 greedy (argmax, first index on ties), 1 top-k, 2 top-p, 3 top-k then top-p, 4 min-p
@@ -143,7 +154,8 @@ int vb_gather_rows(void* d_out, const void* d_in, const int32_t* d_idx, int n, i
  * (benchmark hook to pin sequence lengths; -1 = off).  Workspace: vb_sample_workspace_bytes. */
 size_t vb_sample_workspace_bytes(int rows, int vocab);
 int vb_sample(int64_t* d_out_ids, const void* d_logits, int rows, int vocab, int ld_logits,
-              const uint8_t* d_rep_cache, int rep_window_slots, int rep_codebooks, int logit_codebooks,
+              const uint8_t* d_rep_cache, const int32_t* d_cache_rows, int rep_window_slots, int rep_codebooks,
+              int logit_codebooks,
               float penalty, int strategy, int top_k, float top_p, float min_p, float temperature, uint64_t seed,
               uint64_t offset, uint64_t* d_rng_state, int mask_token, void* d_workspace, size_t workspace_bytes,
               void* stream);
@@ -153,8 +165,8 @@ int vb_apply_repetition_penalty(void* d_out, const void* d_logits, const uint8_t
                                 int rows, int vocab, void* stream);
 /* cache[b][w][c][ids] = 1 with the reference's batch-union semantics (sampling.py:148-178).
  * cache uint8 [B][W][C][V]; ids int64 [B][C_ids]; window > 1 shifts the window first. */
-int vb_update_repetition_cache(uint8_t* d_cache, const int64_t* d_ids, int B, int W, int C, int V, int C_ids,
-                               int window, void* stream);
+int vb_update_repetition_cache(uint8_t* d_cache, const int32_t* d_cache_rows, const int64_t* d_ids, int B, int W,
+                               int C, int V, int C_ids, int window, void* stream);
 
 /* ---- SNAC decoder: vox_serve/tokenizer/snac.py:119-267, 297-357, 438-441 ----------------------
  * fp32, activations [B][C][T] (T contiguous).  Weights arrive weight-norm-folded (snac.py:244-249) --

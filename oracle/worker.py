@@ -77,6 +77,8 @@ class OracleWorker:
         self.use_rep = (cfg.repetition_penalty is not None and cfg.repetition_window is not None
                         and cfg.repetition_penalty != 1.0)
         self.last_logits = None
+        self.last_penalised = None
+        self.last_own_ids = None
 
     # ---- worker/base.py:210-360 ----
     def prepare_lm_inputs(self, reqs: List[Req]) -> Optional[Dict]:
@@ -118,7 +120,11 @@ class OracleWorker:
                     repetition_cache=rep, is_prefill=is_prefill)
 
     # ---- run_lm_prefill / run_lm_decode + orpheus.py:419-477 ----
-    def run_lm(self, reqs: List[Req], inp: Optional[Dict]) -> Optional[torch.Tensor]:
+    def run_lm(self, reqs: List[Req], inp: Optional[Dict], forced_ids: Optional[torch.Tensor] = None
+               ) -> Optional[torch.Tensor]:
+        """``forced_ids`` ([B, 1] int64): teacher forcing for parity tests -- the oracle's own choice is computed
+        (returned, with its penalised logits kept in ``last_penalised``) but the request state and the repetition
+        cache advance with the forced ids, so one bf16 near-tie does not fork the rest of the comparison."""
         if not reqs:
             return None
         if inp["is_prefill"]:
@@ -135,7 +141,16 @@ class OracleWorker:
         if self.ignore_stop:
             logits = logits.clone()
             logits[..., self.dims.stop_token_id] = float("-inf")
-        ids = oorph.sampling_step(logits, self.cfg, inp["repetition_cache"])
+        rep = inp["repetition_cache"]
+        if forced_ids is not None:
+            self.last_penalised = (osampler.apply_repetition_penalty(logits, rep, self.cfg.repetition_penalty)
+                                   if rep is not None else logits)
+            own = oorph.sampling_step(logits, self.cfg, rep.clone() if rep is not None else None)
+            if rep is not None:
+                osampler.update_repetition_cache(rep, forced_ids, self.cfg.repetition_window)
+            ids, self.last_own_ids = forced_ids, own
+        else:
+            ids = oorph.sampling_step(logits, self.cfg, rep)
         for i, r in enumerate(reqs):
             tok = int(ids[i, 0])
             r.input_tokens = ids[i : i + 1]

@@ -24,8 +24,10 @@ SIGNATURES = {
     "vb_rope": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_plan_rows": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_int, P]),
     "vb_decode_advance": (c_int, [P, P, P, c_int, P]),
-    "vb_ids_feedback": (c_int, [P, P, P, P, c_int, c_int, P]),
-    "vb_gather_windows": (c_int, [P, P, P, c_int, c_int, c_int, P]),
+    "vb_token_feedback": (c_int, [P, P, P, P, P, c_int, c_int, P]),
+    "vb_gather_i32": (c_int, [P, P, P, c_int, P]),
+    "vb_build_input_ids": (c_int, [P, P, P, P, c_int, P]),
+    "vb_gather_windows": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
     "vb_kv_append": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     "vb_paged_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "vb_paged_attn": (c_int, [P, P, P, c_int64, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -35,12 +37,12 @@ SIGNATURES = {
     "vb_reduce_residual_rmsnorm": (c_int, [P, P, P, c_int, P, P, c_int, c_int, c_float, P]),
     "vb_qkv_rope_append": (c_int, [P, P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_embedding": (c_int, [P, P, P, c_int, c_int, c_int, P]),
-    "vb_gather_rows": (c_int, [P, P, P, c_int, c_int, P]),
+    "vb_gather_rows": (c_int, [P, P, P, c_int, c_int, c_int, P]),
     "vb_sample_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "vb_sample": (c_int, [P, P, c_int, c_int, c_int, P, c_int, c_int, c_int, c_float, c_int, c_int, c_float,
+    "vb_sample": (c_int, [P, P, c_int, c_int, c_int, P, P, c_int, c_int, c_int, c_float, c_int, c_int, c_float,
                           c_float, c_float, c_uint64, c_uint64, P, c_int, P, c_size_t, P]),
     "vb_apply_repetition_penalty": (c_int, [P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, P]),
-    "vb_update_repetition_cache": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_update_repetition_cache": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_snac_from_codes": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_snac_dwconv7": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     "vb_snac_pwconv": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
@@ -89,6 +91,13 @@ def check(rc: int, what: str = ""):
         raise VoxB200Error(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")
 
 
+# kernels (+ memset nodes) each entry point enqueues; everything not listed launches exactly one
+LAUNCHES = {"vb_tensor_map_kv": 0, "vb_tensor_map_2d_bf16": 0, "vb_device_info": 0, "vb_sample": 3,
+            "vb_update_repetition_cache": 1}
+launch_counter = [0]
+
+
 def call(name: str, *args):
     """Invoke an int-returning entry point and raise on error."""
     check(getattr(load(), name)(*args), name)
+    launch_counter[0] += LAUNCHES.get(name, 1)

@@ -341,9 +341,9 @@ __global__ void embedding_kernel(__nv_bfloat16* __restrict__ out, const __nv_bfl
 }
 
 __global__ void gather_rows_kernel(uint8_t* __restrict__ out, const uint8_t* __restrict__ in,
-                                   const int32_t* __restrict__ idx, int row_bytes) {
+                                   const int32_t* __restrict__ idx, int row_bytes, int idx_offset) {
   const size_t i = blockIdx.x;
-  const uint4* src = reinterpret_cast<const uint4*>(in + static_cast<size_t>(idx[i]) * row_bytes);
+  const uint4* src = reinterpret_cast<const uint4*>(in + static_cast<size_t>(idx[i] + idx_offset) * row_bytes);
   uint4* dst = reinterpret_cast<uint4*>(out + i * row_bytes);
   for (int j = threadIdx.x; j < row_bytes / 16; j += blockDim.x) dst[j] = src[j];
 }
@@ -495,11 +495,12 @@ int vb_embedding(void* d_out, const void* d_table, const int32_t* d_ids, int T, 
   return 0;
 }
 
-int vb_gather_rows(void* d_out, const void* d_in, const int32_t* d_idx, int n, int row_bytes, void* stream) {
+int vb_gather_rows(void* d_out, const void* d_in, const int32_t* d_idx, int n, int row_bytes, int idx_offset,
+                   void* stream) {
   VB_CHECK_ARG(d_out && d_in && d_idx && row_bytes % 16 == 0, "vb_gather_rows: bad arguments");
   if (n <= 0) return 0;
   gather_rows_kernel<<<n, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<uint8_t*>(d_out), static_cast<const uint8_t*>(d_in), d_idx, row_bytes);
+      static_cast<uint8_t*>(d_out), static_cast<const uint8_t*>(d_in), d_idx, row_bytes, idx_offset);
   VB_CHECK_LAUNCH();
   return 0;
 }
@@ -525,7 +526,7 @@ int vb_orpheus_window_codes(int32_t* d_c0, int32_t* d_c1, int32_t* d_c2, const i
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------
-// device-resident decode loop helpers: no host work between CUDA-graph replays
+// slot-resident decode state: no host work between CUDA-graph replays
 // ------------------------------------------------------------------------------------------
 namespace vb {
 // state = {kv_len[B], position[B]} advance by one token per request (worker/base.py:312-325 does this on
@@ -537,28 +538,42 @@ __global__ void decode_advance_kernel(int32_t* kv_len, int32_t* pos, const int32
     pos[b] += 1;
   }
 }
-// sampled ids (int64) -> next step's input ids (int32) and the token history ring [cap][B];
-// *step_counter is advanced by thread 0.
-__global__ void ids_feedback_kernel(const int64_t* ids, int32_t* next_input, int32_t* history, int32_t* step_counter,
-                                    int B, int cap) {
+// sampled ids of batch row b (int64) -> slot s = slots[b] (identity when null): next input id, token history
+// ring history[s][n_out[s] % cap], ++n_out[s]   (orpheus.py:447-448, 456-458 keep these in Python lists)
+__global__ void token_feedback_kernel(const int64_t* ids, const int32_t* slots, int32_t* next_input,
+                                      int32_t* history, int32_t* n_out, int B, int cap) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  const int step = *step_counter;
-  if (b < B) {
-    const int v = static_cast<int>(ids[b]);
-    next_input[b] = v;
-    if (history) history[static_cast<size_t>(step % cap) * B + b] = v;
-  }
-  __syncthreads();
-  if (blockIdx.x == 0 && threadIdx.x == 0) *step_counter = step + 1;
+  if (b >= B) return;
+  const int s = slots ? slots[b] : b;
+  const int v = static_cast<int>(ids[b]);
+  next_input[s] = v;
+  const int n = n_out[s];
+  if (history) history[static_cast<size_t>(s) * cap + (n % cap)] = v;
+  n_out[s] = n + 1;
 }
-// windows[b][j] = history[(first_step + j) % cap][b] for j < win : the 28-token detokenize window
-// (cuda_graph_worker.py:1176-1190) gathered on the device.  first_step[b] per request.
-__global__ void gather_windows_kernel(int64_t* windows, const int32_t* history, const int32_t* first_step, int B,
-                                      int cap, int win) {
+// next step's input ids gathered by slot: ids[b] = next_input[slots[b]]
+__global__ void gather_i32_kernel(int32_t* out, const int32_t* src, const int32_t* idx, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * win) return;
-  const int b = i / win, j = i - b * win;
-  windows[i] = history[static_cast<size_t>((first_step[b] + j) % cap) * B + b];
+  if (i < n) out[i] = src[idx ? idx[i] : i];
+}
+// step input ids: decode rows take the id sampled last step for their slot, prefill rows the uploaded prompt id
+__global__ void build_input_ids_kernel(int32_t* out, const int32_t* host_ids, const int32_t* next_input,
+                                       const int32_t* row_slot, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = row_slot[i];
+  out[i] = s >= 0 ? next_input[s] : host_ids[i];
+}
+// windows[i][j] = history[slot[i]][(first[i] + min(j, n_valid[i] - 1)) % cap], j < win : the detokenize window
+// of cuda_graph_worker.py:1176-1190 (a short last window repeats its final token, :1183-1185).
+__global__ void gather_windows_kernel(int64_t* windows, const int32_t* history, const int32_t* slot,
+                                      const int32_t* first, const int32_t* n_valid, int n, int cap, int win) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * win) return;
+  const int w = i / win, j = i - w * win;
+  const int nv = n_valid ? n_valid[w] : win;
+  const int jj = j < nv ? j : nv - 1;
+  windows[i] = history[static_cast<size_t>(slot[w]) * cap + ((first[w] + jj) % cap)];
 }
 }  // namespace vb
 
@@ -570,21 +585,38 @@ int vb_decode_advance(int32_t* d_kv_len, int32_t* d_pos, const int32_t* d_active
   VB_CHECK_LAUNCH();
   return 0;
 }
-int vb_ids_feedback(const int64_t* d_ids, int32_t* d_next_input, int32_t* d_history, int32_t* d_step_counter, int B,
-                    int history_cap, void* stream) {
-  VB_CHECK_ARG(d_ids && d_next_input && d_step_counter, "vb_ids_feedback: null pointer");
-  VB_CHECK_ARG(B > 0 && B <= 1024 && history_cap > 0, "vb_ids_feedback: bad sizes");
-  vb::ids_feedback_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(d_ids, d_next_input, d_history,
-                                                                            d_step_counter, B, history_cap);
+int vb_token_feedback(const int64_t* d_ids, const int32_t* d_slots, int32_t* d_next_input, int32_t* d_history,
+                      int32_t* d_n_out, int B, int history_cap, void* stream) {
+  VB_CHECK_ARG(d_ids && d_next_input && d_n_out, "vb_token_feedback: null pointer");
+  VB_CHECK_ARG(history_cap > 0, "vb_token_feedback: history_cap must be positive");
+  if (B <= 0) return 0;
+  vb::token_feedback_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_ids, d_slots, d_next_input, d_history, d_n_out, B, history_cap);
   VB_CHECK_LAUNCH();
   return 0;
 }
-int vb_gather_windows(int64_t* d_windows, const int32_t* d_history, const int32_t* d_first_step, int B,
-                      int history_cap, int window, void* stream) {
-  VB_CHECK_ARG(d_windows && d_history && d_first_step, "vb_gather_windows: null pointer");
-  if (B <= 0) return 0;
-  vb::gather_windows_kernel<<<(B * window + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_windows, d_history, d_first_step, B, history_cap, window);
+int vb_gather_i32(int32_t* d_out, const int32_t* d_src, const int32_t* d_idx, int n, void* stream) {
+  VB_CHECK_ARG(d_out && d_src, "vb_gather_i32: null pointer");
+  if (n <= 0) return 0;
+  vb::gather_i32_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_out, d_src, d_idx, n);
+  VB_CHECK_LAUNCH();
+  return 0;
+}
+int vb_build_input_ids(int32_t* d_out, const int32_t* d_host_ids, const int32_t* d_next_input,
+                       const int32_t* d_row_slot, int n, void* stream) {
+  VB_CHECK_ARG(d_out && d_host_ids && d_next_input && d_row_slot, "vb_build_input_ids: null pointer");
+  if (n <= 0) return 0;
+  vb::build_input_ids_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_out, d_host_ids, d_next_input, d_row_slot, n);
+  VB_CHECK_LAUNCH();
+  return 0;
+}
+int vb_gather_windows(int64_t* d_windows, const int32_t* d_history, const int32_t* d_slot, const int32_t* d_first,
+                      const int32_t* d_n_valid, int n, int history_cap, int window, void* stream) {
+  VB_CHECK_ARG(d_windows && d_history && d_slot && d_first, "vb_gather_windows: null pointer");
+  if (n <= 0) return 0;
+  vb::gather_windows_kernel<<<(n * window + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_windows, d_history, d_slot, d_first, d_n_valid, n, history_cap, window);
   VB_CHECK_LAUNCH();
   return 0;
 }

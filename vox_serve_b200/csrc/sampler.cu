@@ -19,6 +19,7 @@ namespace vb {
 struct SampleParams {
   const __nv_bfloat16* logits;
   const uint8_t* rep_cache;    // [B][W][C][V] or null
+  const int32_t* cache_rows;   // optional: batch row b reads / marks cache row cache_rows[b] (slot-resident caches)
   int rows, vocab, ld;
   int W, C_cache, C_logits;
   float penalty, temperature;
@@ -46,7 +47,8 @@ __device__ __forceinline__ float key_value(uint32_t k) {
 __device__ __forceinline__ float token_value(const SampleParams& p, int row, int i, bool scaled) {
   float l = __bfloat162float(p.logits[static_cast<size_t>(row) * p.ld + i]);
   if (p.rep_cache) {
-    const int b = row / p.C_logits;
+    const int b0 = row / p.C_logits;
+    const int b = p.cache_rows ? p.cache_rows[b0] : b0;
     const int c = (p.C_logits == 1 && p.C_cache != 1) ? 0 : row % p.C_logits;   // sampling.py:140-141
     bool seen = false;
     for (int w = 0; w < p.W; ++w)
@@ -335,19 +337,20 @@ __global__ void penalty_kernel(__nv_bfloat16* out, const SampleParams p) {
 }
 
 // window > 1: cache[:, :-1] = cache[:, 1:]; cache[:, -1] = 0   (sampling.py:166-168)
-__global__ void rep_shift_kernel(uint8_t* cache, int B, int W, size_t plane /*C*V*/) {
+__global__ void rep_shift_kernel(uint8_t* cache, const int32_t* cache_rows, int B, int W, size_t plane /*C*V*/) {
   const size_t n = static_cast<size_t>(B) * plane;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t b = i / plane, r = i - b * plane;
+    const size_t b0 = i / plane, r = i - b0 * plane;
+    const size_t b = cache_rows ? static_cast<size_t>(cache_rows[b0]) : b0;
     uint8_t* base = cache + b * W * plane + r;
     for (int w = 0; w + 1 < W; ++w) base[w * plane] = base[(w + 1) * plane];
     base[(W - 1) * plane] = 0;
   }
 }
 // cache[b, w(s), c(s), ids[b', c']] = 1 for every b and every (b', c')   (sampling.py:169-178)
-__global__ void rep_mark_kernel(uint8_t* cache, const int64_t* ids, int B, int W, int C, int V, int C_ids,
-                                int windowed) {
+__global__ void rep_mark_kernel(uint8_t* cache, const int32_t* cache_rows, const int64_t* ids, int B, int W, int C,
+                                int V, int C_ids, int windowed) {
   const int n_ids = B * C_ids;
   const bool cb0_only = (C_ids == 1 && C != 1);
   const int w_lo = windowed ? W - 1 : 0, w_hi = W;
@@ -356,8 +359,9 @@ __global__ void rep_mark_kernel(uint8_t* cache, const int64_t* ids, int B, int W
   const long long total = static_cast<long long>(B) * per_b;
   for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
        t += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int b = static_cast<int>(t / per_b);
-    int r = static_cast<int>(t - static_cast<long long>(b) * per_b);
+    const int b0 = static_cast<int>(t / per_b);
+    int r = static_cast<int>(t - static_cast<long long>(b0) * per_b);
+    const int b = cache_rows ? cache_rows[b0] : b0;
     const int j = r % n_ids; r /= n_ids;
     const int c = c_lo + r % (c_hi - c_lo); r /= (c_hi - c_lo);
     const int w = w_lo + r;
@@ -381,9 +385,10 @@ size_t vb_sample_workspace_bytes(int rows, int vocab) {
 static int fill_params(SampleParams& p, int64_t* d_out_ids, const void* d_logits, int rows, int vocab, int ld,
                        const uint8_t* d_rep_cache, int W, int C_cache, int C_logits, float penalty, int strategy,
                        int top_k, float top_p, float min_p, float temperature, uint64_t seed, uint64_t offset,
-                       int mask_token, void* ws, uint64_t* rng_state = nullptr) {
+                       int mask_token, void* ws, uint64_t* rng_state = nullptr, const int32_t* cache_rows = nullptr) {
   p.logits = static_cast<const __nv_bfloat16*>(d_logits);
   p.rep_cache = d_rep_cache;
+  p.cache_rows = cache_rows;
   p.rows = rows; p.vocab = vocab; p.ld = ld;
   p.W = W; p.C_cache = C_cache; p.C_logits = C_logits > 0 ? C_logits : 1;
   p.penalty = penalty; p.temperature = temperature;
@@ -400,7 +405,8 @@ static int fill_params(SampleParams& p, int64_t* d_out_ids, const void* d_logits
 }
 
 int vb_sample(int64_t* d_out_ids, const void* d_logits, int rows, int vocab, int ld_logits,
-              const uint8_t* d_rep_cache, int rep_window_slots, int rep_codebooks, int logit_codebooks,
+              const uint8_t* d_rep_cache, const int32_t* d_cache_rows, int rep_window_slots, int rep_codebooks,
+              int logit_codebooks,
               float penalty, int strategy, int top_k, float top_p, float min_p, float temperature, uint64_t seed,
               uint64_t offset, uint64_t* d_rng_state, int mask_token, void* d_workspace, size_t workspace_bytes,
               void* stream) {
@@ -415,7 +421,7 @@ int vb_sample(int64_t* d_out_ids, const void* d_logits, int rows, int vocab, int
   SampleParams p;
   fill_params(p, d_out_ids, d_logits, rows, vocab, ld_logits, d_rep_cache, rep_window_slots, rep_codebooks,
               logit_codebooks, penalty, strategy, top_k, top_p, min_p, temperature, seed, offset, mask_token,
-              d_workspace, d_rng_state);
+              d_workspace, d_rng_state, d_cache_rows);
   const int gx = max(1, min(32, (vocab + 256 * 8 - 1) / (256 * 8)));
   if (strategy == 0) {
     VB_CHECK_CUDA(cudaMemsetAsync(p.packed, 0, static_cast<size_t>(rows) * 8, st));
@@ -449,8 +455,8 @@ int vb_apply_repetition_penalty(void* d_out, const void* d_logits, const uint8_t
   return 0;
 }
 
-int vb_update_repetition_cache(uint8_t* d_cache, const int64_t* d_ids, int B, int W, int C, int V, int C_ids,
-                               int window, void* stream) {
+int vb_update_repetition_cache(uint8_t* d_cache, const int32_t* d_cache_rows, const int64_t* d_ids, int B, int W,
+                               int C, int V, int C_ids, int window, void* stream) {
   VB_CHECK_ARG(d_cache && d_ids, "vb_update_repetition_cache: null pointer");
   VB_CHECK_ARG(B > 0 && W > 0 && C > 0 && V > 0 && C_ids > 0, "vb_update_repetition_cache: bad dims");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -458,10 +464,10 @@ int vb_update_repetition_cache(uint8_t* d_cache, const int64_t* d_ids, int B, in
   if (windowed) {
     const size_t plane = static_cast<size_t>(C) * V;
     size_t nb = (static_cast<size_t>(B) * plane + 255) / 256; if (nb > 4096) nb = 4096; const unsigned blocks = static_cast<unsigned>(nb);
-    rep_shift_kernel<<<blocks, 256, 0, st>>>(d_cache, B, W, plane);
+    rep_shift_kernel<<<blocks, 256, 0, st>>>(d_cache, d_cache_rows, B, W, plane);
     VB_CHECK_LAUNCH();
   }
-  rep_mark_kernel<<<64, 256, 0, st>>>(d_cache, d_ids, B, W, C, V, C_ids, windowed);
+  rep_mark_kernel<<<64, 256, 0, st>>>(d_cache, d_cache_rows, d_ids, B, W, C, V, C_ids, windowed);
   VB_CHECK_LAUNCH();
   return 0;
 }

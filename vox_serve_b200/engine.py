@@ -145,7 +145,7 @@ class LlamaEngine:
 
     def forward(self, input_ids: torch.Tensor, position_ids: torch.Tensor, n_rows: int,
                 last_rows: Optional[torch.Tensor] = None, n_out: Optional[int] = None,
-                plan: Optional[ops.RowPlan] = None) -> torch.Tensor:
+                plan: Optional[ops.RowPlan] = None, last_rows_offset: int = 0) -> torch.Tensor:
         """input_ids / position_ids int32 [n_rows] on the device; self.plan must hold the step's row plan
         (ops.plan_rows).  Returns logits [n_out or n_rows, vocab] bf16 (a view of the static buffer).
         last_rows (int32 [n_out]) selects the rows whose logits are needed (prefill: qo_indptr[1:] - 1)."""
@@ -174,7 +174,7 @@ class LlamaEngine:
             ops.reduce_residual_rmsnorm(p, hidden, nxt, d.rms_norm_eps, hidden_out=hidden, normed_out=normed)
         if last_rows is not None:
             n_out = last_rows.numel() if n_out is None else n_out
-            x = ops.gather_rows(normed, last_rows, out=self.last_normed[:n_out])
+            x = ops.gather_rows(normed, last_rows, out=self.last_normed[:n_out], idx_offset=last_rows_offset)
         else:
             n_out, x = R, normed
         if n_out > self.max_out_rows:

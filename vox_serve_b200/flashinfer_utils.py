@@ -23,7 +23,7 @@ class _PagedWrapper:
     def __init__(self, attn_buffer: Optional[torch.Tensor], n_qo_head: int, n_kv_head: int, n_state: int,
                  page_size: int, batch_size: int = None, max_seq_len: int = None,
                  device: torch.device = torch.device("cuda"), use_cuda_graph: bool = False,
-                 max_pages: int = 2048, **_buffers):
+                 max_pages: int = 2048, max_chunks: Optional[int] = None, **_buffers):
         self.device = torch.device(device)
         self.n_qo_head, self.n_kv_head, self.n_state = n_qo_head, n_kv_head, n_state
         self.head_dim = n_state // n_qo_head
@@ -41,13 +41,22 @@ class _PagedWrapper:
         self.d_last = torch.zeros(self.max_req, dtype=torch.int32, device=dev)
         per_row = (max_pages * page_size // max(1, self.max_req) + self.chunk - 1) // self.chunk
         bound = max_pages * (page_size // self.chunk) if not self.is_prefill else min(self.max_rows * per_row, 1 << 17)
-        self.plan_rows = ops.RowPlan(self.max_rows, dev, max(64, bound))
+        self.plan_rows = ops.RowPlan(self.max_rows, dev, max(64, bound) if max_chunks is None else int(max_chunks))
         self.workspace = None
         self._maps: Dict[Tuple, ops.TensorMap] = {}
         self.n_rows = 0
         self.qo_indptr = None
 
     # -- shared ---------------------------------------------------------------------------------
+    def plan_device(self, d_qo: Optional[torch.Tensor], d_indptr: torch.Tensor, d_indices: torch.Tensor,
+                    d_last: Optional[torch.Tensor], n_req: int, n_rows: int, kv_len: Optional[torch.Tensor] = None):
+        """plan() for page tables that already live on the device (the worker's packed staging buffer): one
+        launch, no upload, CUDA-graph capturable."""
+        self.n_rows = self.n_rows_padded = n_rows
+        self.batch_size = n_req
+        ops.plan_rows(self.plan_rows, d_qo, d_indptr, d_indices, d_last, n_req, n_rows, self.page_size, self.chunk,
+                      kv_len=kv_len)
+
     def _upload(self, dst: torch.Tensor, src) -> torch.Tensor:
         t = src if isinstance(src, torch.Tensor) else torch.tensor(src, dtype=torch.int32)
         n = t.numel()

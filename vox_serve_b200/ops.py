@@ -37,6 +37,11 @@ def _need_cuda(*ts):
 _dev_info: Dict[int, Tuple[int, int]] = {}
 
 
+def launch_count() -> int:
+    """Kernels (and memset nodes) enqueued through the C ABI so far in this process."""
+    return _lib.launch_counter[0]
+
+
 def device_info() -> Tuple[int, int]:
     dev = torch.cuda.current_device()
     if dev not in _dev_info:
@@ -293,12 +298,13 @@ def embedding(table: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tensor
     return out
 
 
-def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None,
+                idx_offset: int = 0) -> torch.Tensor:
     _need_cuda(src, idx)
     assert idx.dtype == torch.int32 and src.dim() == 2 and src.is_contiguous()
     out = torch.empty(idx.numel(), src.shape[1], dtype=src.dtype, device=src.device) if out is None else out
     call("vb_gather_rows", out.data_ptr(), src.data_ptr(), idx.data_ptr(), idx.numel(),
-         src.shape[1] * src.element_size(), _stream())
+         src.shape[1] * src.element_size(), int(idx_offset), _stream())
     return out
 
 
@@ -310,10 +316,12 @@ _sample_ws: Dict[Tuple, torch.Tensor] = {}
 
 
 def sample_workspace(rows: int, vocab: int, device) -> torch.Tensor:
-    key = (rows, str(device))
+    """One workspace per device, sized for at least 64 rows up front so that later (CUDA-graph captured) calls
+    never allocate."""
+    key = str(device)
     ws = _sample_ws.get(key)
-    if ws is None:
-        n = _lib.load().vb_sample_workspace_bytes(rows, vocab)
+    n = _lib.load().vb_sample_workspace_bytes(max(rows, 64), vocab)
+    if ws is None or ws.numel() < n:
         ws = torch.empty(n, dtype=torch.uint8, device=device)
         _sample_ws[key] = ws
     return ws
@@ -329,8 +337,10 @@ def _cache_u8(rep_cache: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 def sample(logits: torch.Tensor, strategy: str, rep_cache: Optional[torch.Tensor] = None, penalty: float = 1.0,
            logit_codebooks: int = 1, top_k: int = 0, top_p: float = 1.0, min_p: float = 0.0, temperature: float = 1.0,
            seed: int = 0, offset: int = 0, mask_token: int = -1, out: Optional[torch.Tensor] = None,
-           workspace: Optional[torch.Tensor] = None, rng_state: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """logits [rows, V] bf16 (row stride arbitrary) -> ids int64 [rows]."""
+           workspace: Optional[torch.Tensor] = None, rng_state: Optional[torch.Tensor] = None,
+           cache_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """logits [rows, V] bf16 (row stride arbitrary) -> ids int64 [rows].
+    cache_rows (int32 [batch]): batch row b reads rep_cache[cache_rows[b]] (slot-resident caches)."""
     _need_cuda(logits)
     assert logits.dtype == BF16 and logits.dim() == 2 and logits.stride(1) == 1
     rows, V = logits.shape
@@ -338,7 +348,8 @@ def sample(logits: torch.Tensor, strategy: str, rep_cache: Optional[torch.Tensor
     ws = sample_workspace(rows, V, logits.device) if workspace is None else workspace
     c8 = _cache_u8(rep_cache)
     W, Cc = (c8.shape[1], c8.shape[2]) if c8 is not None else (0, 0)
-    call("vb_sample", out.data_ptr(), logits.data_ptr(), rows, V, logits.stride(0), _p(c8), W, Cc, logit_codebooks,
+    call("vb_sample", out.data_ptr(), logits.data_ptr(), rows, V, logits.stride(0), _p(c8), _p(cache_rows), W, Cc,
+         logit_codebooks,
          float(penalty), STRATEGY[strategy], int(top_k or 0), float(top_p if top_p is not None else 1.0),
          float(min_p or 0.0), float(temperature), int(seed), int(offset), _p(rng_state), int(mask_token), ws.data_ptr(),
          ws.numel(),
@@ -358,13 +369,17 @@ def apply_repetition_penalty(logits: torch.Tensor, rep_cache: torch.Tensor, pena
     return out
 
 
-def update_repetition_cache(rep_cache: torch.Tensor, ids: torch.Tensor, window: int) -> None:
+def update_repetition_cache(rep_cache: torch.Tensor, ids: torch.Tensor, window: int,
+                            cache_rows: Optional[torch.Tensor] = None) -> None:
+    """ids int64 [B, C_ids]; with cache_rows the B batch rows mark cache rows cache_rows[b] of a larger
+    slot-resident cache."""
     _need_cuda(rep_cache, ids)
     c8 = _cache_u8(rep_cache)
-    ids64 = ids.to(torch.int64).contiguous()
-    B, W, Cc, V = c8.shape
-    call("vb_update_repetition_cache", c8.data_ptr(), ids64.data_ptr(), B, W, Cc, V, ids64.shape[1], int(window),
-         _stream())
+    ids64 = ids if (ids.dtype == torch.int64 and ids.is_contiguous()) else ids.to(torch.int64).contiguous()
+    _, W, Cc, V = c8.shape
+    B = ids64.shape[0]
+    call("vb_update_repetition_cache", c8.data_ptr(), _p(cache_rows), ids64.data_ptr(), B, W, Cc, V, ids64.shape[1],
+         int(window), _stream())
 
 
 # ----------------------------------------------------------------------------------------------
@@ -374,19 +389,32 @@ def decode_advance(kv_len: torch.Tensor, pos: torch.Tensor, active: Optional[tor
     call("vb_decode_advance", kv_len.data_ptr(), pos.data_ptr(), _p(active), kv_len.numel(), _stream())
 
 
-def ids_feedback(ids: torch.Tensor, next_input: torch.Tensor, history: Optional[torch.Tensor],
-                 step_counter: torch.Tensor):
-    cap = history.shape[0] if history is not None else 1
-    call("vb_ids_feedback", ids.data_ptr(), next_input.data_ptr(), _p(history), step_counter.data_ptr(),
+def token_feedback(ids: torch.Tensor, slots: Optional[torch.Tensor], next_input: torch.Tensor,
+                   history: Optional[torch.Tensor], n_out: torch.Tensor):
+    """ids int64 [B] -> per-slot next input id, history ring [slots, cap], token counter."""
+    cap = history.shape[1] if history is not None else 1
+    call("vb_token_feedback", ids.data_ptr(), _p(slots), next_input.data_ptr(), _p(history), n_out.data_ptr(),
          ids.numel(), cap, _stream())
 
 
-def gather_windows(history: torch.Tensor, first_step: torch.Tensor, window: int,
-                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    B = first_step.numel()
-    out = torch.empty(B, window, dtype=torch.int64, device=history.device) if out is None else out
-    call("vb_gather_windows", out.data_ptr(), history.data_ptr(), first_step.data_ptr(), B, history.shape[0],
-         window, _stream())
+def gather_i32(src: torch.Tensor, idx: Optional[torch.Tensor], out: torch.Tensor, n: Optional[int] = None):
+    call("vb_gather_i32", out.data_ptr(), src.data_ptr(), _p(idx), out.numel() if n is None else n, _stream())
+    return out
+
+
+def build_input_ids(out: torch.Tensor, host_ids: torch.Tensor, next_input: torch.Tensor, row_slot: torch.Tensor,
+                    n: int):
+    call("vb_build_input_ids", out.data_ptr(), host_ids.data_ptr(), next_input.data_ptr(), row_slot.data_ptr(), n,
+         _stream())
+    return out
+
+
+def gather_windows(history: torch.Tensor, slot: torch.Tensor, first: torch.Tensor, n_valid: Optional[torch.Tensor],
+                   window: int, out: Optional[torch.Tensor] = None, n: Optional[int] = None) -> torch.Tensor:
+    n = slot.numel() if n is None else n
+    out = torch.empty(n, window, dtype=torch.int64, device=history.device) if out is None else out
+    call("vb_gather_windows", out.data_ptr(), history.data_ptr(), slot.data_ptr(), first.data_ptr(), _p(n_valid), n,
+         history.shape[1], window, _stream())
     return out
 
 

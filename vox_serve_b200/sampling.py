@@ -66,14 +66,15 @@ class Sampler:
 
     @classmethod
     def update_repetition_penalty_cache(cls, repetition_cache: torch.Tensor, output_ids: torch.Tensor,
-                                        window_size: int) -> None:
-        """In place, including the reference's batch-union marking (sampling.py:148-178)."""
-        ops.update_repetition_cache(repetition_cache, output_ids, window_size)
+                                        window_size: int, cache_rows: Optional[torch.Tensor] = None) -> None:
+        """In place, including the reference's batch-union marking (sampling.py:148-178).  ``cache_rows`` maps
+        batch rows onto rows of a larger slot-resident cache."""
+        ops.update_repetition_cache(repetition_cache, output_ids, window_size, cache_rows=cache_rows)
 
     @classmethod
     def sample_fused(cls, logits: torch.Tensor, config: SamplingConfig, repetition_cache: Optional[torch.Tensor],
                      mask_token: int = -1, rng_state: Optional[torch.Tensor] = None,
-                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     out: Optional[torch.Tensor] = None, cache_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
         """penalty + strategy + draw in one call: logits [B, n_cb, V] -> ids [B, n_cb] int64.
         (what orpheus.py:431-438 does in three steps)."""
         B, C, V = logits.shape
@@ -84,5 +85,5 @@ class Sampler:
                          top_p=1.0 if config.top_p is None else config.top_p, min_p=config.min_p or 0.0,
                          temperature=config.temperature if kind != "greedy" else 1.0, seed=seed,
                          offset=next(_offset) if rng_state is None else 0, mask_token=mask_token,
-                         rng_state=rng_state, out=out)
+                         rng_state=rng_state, out=out, cache_rows=cache_rows)
         return ids.view(B, C)

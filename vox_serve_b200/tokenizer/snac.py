@@ -44,6 +44,9 @@ class SNAC:
         self.device = torch.device(device)
         self.w: Dict[str, torch.Tensor] = {}
         self.loaded = False
+        # NoiseBlock input (snac.py:206-212): None = torch.randn on the current CUDA generator like the reference;
+        # a callable(shapes) -> tensors lets tests inject the oracle's noise
+        self.noise_source = None
 
     # ---- loading -----------------------------------------------------------------------------
     @classmethod
@@ -106,6 +109,45 @@ class SNAC:
         self.loaded = True
         return self
 
+    def synthetic_state_dict(self, seed: int = 0) -> Dict[str, torch.Tensor]:
+        """Seeded weights under the reference's state_dict names (weight-norm ``original0`` = g, ``original1`` = v;
+        snac.py:244-249) for runs without the HF checkpoint (no network).  Scales keep activations O(1)."""
+        gen = torch.Generator().manual_seed(seed)
+        sd: Dict[str, torch.Tensor] = {}
+
+        def wn(prefix, shape, fan_in, bias_dim=None, gain=1.0):
+            v = torch.randn(*shape, generator=gen)
+            rowsize = math.prod(shape[1:])
+            jitter = 1.0 + 0.2 * (2 * torch.rand(shape[0], *([1] * (len(shape) - 1)), generator=gen) - 1)
+            sd[prefix + ".parametrizations.weight.original0"] = gain * math.sqrt(rowsize / fan_in) * jitter
+            sd[prefix + ".parametrizations.weight.original1"] = v
+            if bias_dim is not None:
+                sd[prefix + ".bias"] = torch.randn(bias_dim, generator=gen) * 0.05
+
+        L, D, nq = self.latent_dim, self.decoder_dim, len(self.vq_strides)
+        for i in range(nq):
+            p = f"quantizer.quantizers.{i}"
+            sd[p + ".codebook.weight"] = torch.randn(self.codebook_size, self.codebook_dim, generator=gen)
+            wn(p + ".out_proj", (L, self.codebook_dim, 1), self.codebook_dim * nq, L)
+        wn("decoder.model.0", (L, 1, 7), 7, L)
+        wn("decoder.model.1", (D, L, 1), L, D)
+        li, cin = 2, D
+        for s in self.decoder_rates:
+            cout, p = cin // 2, f"decoder.model.{li}"
+            sd[p + ".block.0.alpha"] = 0.5 + torch.rand(1, cin, 1, generator=gen)
+            wn(p + ".block.1", (cin, cout, 2 * s), 2 * cin, cout, gain=0.6)
+            wn(p + ".block.2.linear", (cout, cout, 1), cout, None, gain=0.3)
+            for j in range(3):
+                q = f"{p}.block.{3 + j}"
+                sd[q + ".block.0.alpha"] = 0.5 + torch.rand(1, cout, 1, generator=gen)
+                wn(q + ".block.1", (cout, 1, 7), 7, cout)
+                sd[q + ".block.2.alpha"] = 0.5 + torch.rand(1, cout, 1, generator=gen)
+                wn(q + ".block.3", (cout, cout, 1), cout, cout, gain=0.5)
+            li, cin = li + 1, cout
+        sd[f"decoder.model.{li}.alpha"] = 0.5 + torch.rand(1, cin, 1, generator=gen)
+        wn(f"decoder.model.{li + 1}", (1, cin, 7), 7 * cin, 1, gain=0.25)
+        return sd
+
     # ---- decode ------------------------------------------------------------------------------
     def noise_shapes(self, batch: int, t_latent: int):
         out, t = [], t_latent
@@ -143,7 +185,8 @@ class SNAC:
         x = y
         nb = len(self.decoder_rates)
         if noises is None:
-            noises = [torch.randn(s, **f32) for s in self.noise_shapes(B, T)]
+            shapes = self.noise_shapes(B, T)
+            noises = self.noise_source(shapes) if self.noise_source is not None else [torch.randn(s, **f32) for s in shapes]
         for bi, s in enumerate(self.decoder_rates):
             cin, cout = ch, ch // 2
             u = torch.empty(B, cout, T * s, **f32)

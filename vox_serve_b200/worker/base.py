@@ -1,0 +1,395 @@
+"""B200 worker with the reference worker's public surface (``vox_serve/worker/base.py:14-775`` and
+``worker/cuda_graph_worker.py:12-1280``): same constructor keywords, the five methods the schedulers call
+(``prepare_lm_inputs``, ``run_lm_prefill``, ``run_lm_decode``, ``run_detokenize``, ``free_kv_cache``), the same
+properties / attributes, and the same side effects on ``Request`` objects.
+
+What is re-done underneath (SURVEY.md §3.2 "per step the host issues >= 4 device-wide synchronisations, one
+FlashInfer plan, ~6 small H2D copies"):
+  * every request owns a *batch slot*; its repetition cache row, last sampled id, token history ring and token
+    counter live on the device for the request's lifetime (the reference re-stacks 5 MB of caches and
+    concatenates 32 one-element tensors every step, worker/base.py:329-345);
+  * one packed int32 staging buffer per step (page table, positions, slots) goes H2D in a single copy and the
+    plan is derived on the device (vb_plan_rows) -- no host-side plan, no synchronize;
+  * a decode step is ONE CUDA-graph replay: H2D staging copy -> plan -> input-id gather -> 28 layers -> lm_head
+    -> fused sampler -> cache update -> feedback -> D2H of the sampled ids; graphs are captured per exact batch
+    size on first use (no power-of-two padding with a temp page, cuda_graph_worker.py:966-977);
+  * detokenize windows are gathered from the device-side history ring, SNAC + PCM16 run on the device and one
+    D2H copy returns all chunks (the reference does one ``.cpu()`` per chunk, cuda_graph_worker.py:1252-1253).
+There is no CPU / eager fallback: a missing libvoxb200.so raises at construction.
+"""
+from __future__ import annotations
+
+import queue
+from typing import Coroutine, Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .. import _lib, ops
+from .._lib import VoxB200Error
+from ..flashinfer_utils import FlashInferDecodeWrapper, FlashInferPrefillWrapper
+from ..model import load_model
+from ..requests import LMInputs, Request
+
+I32 = torch.int32
+
+
+class _Staging:
+    """Pinned host buffer + device twin holding one step's integer inputs; layout (int32):
+    qo_indptr[B+1] | kv_indptr[B+1] | last_page_len[B] | slots[B] | position[T] | host_ids[T] | row_slot[T] |
+    kv_indices[P].  Offsets are fixed by (max_req, max_rows) so CUDA graphs can bake the device pointers."""
+
+    def __init__(self, max_req: int, max_rows: int, max_pages: int, device):
+        self.max_req, self.max_rows, self.max_pages = max_req, max_rows, max_pages
+        o = 0
+        self.off = {}
+        for name, n in (("qo", max_req + 1), ("indptr", max_req + 1), ("last", max_req), ("slots", max_req),
+                        ("pos", max_rows), ("ids", max_rows), ("row_slot", max_rows), ("indices", max_pages)):
+            self.off[name] = (o, n)
+            o += (n + 3) // 4 * 4
+        self.n = o
+        self.host = torch.zeros(o, dtype=I32, pin_memory=True)
+        self.np = self.host.numpy()
+        self.dev = torch.zeros(o, dtype=I32, device=device)
+        self.consumed = torch.cuda.Event()
+        self.consumed.record()
+
+    def h(self, name: str) -> np.ndarray:
+        o, n = self.off[name]
+        return self.np[o:o + n]
+
+    def d(self, name: str, n: Optional[int] = None) -> torch.Tensor:
+        o, cap = self.off[name]
+        return self.dev[o:o + (cap if n is None else n)]
+
+    def upload(self, n_ints: Optional[int] = None):
+        n = self.n if n_ints is None else n_ints
+        self.dev[:n].copy_(self.host[:n], non_blocking=True)
+        self.consumed.record()
+
+    def wait_consumed(self):
+        """The host may refill the pinned buffer only after the previous step's H2D copy has executed."""
+        self.consumed.synchronize()
+
+
+class ModelWorker:
+    def __init__(self, model_name: str, max_batch_size: int, max_num_pages: int, page_size: int, top_p: float = None,
+                 top_k: int = None, min_p: float = None, temperature: float = None, max_tokens: int = None,
+                 repetition_penalty: float = None, repetition_window: int = None, cfg_scale: float = None,
+                 greedy: bool = False, enable_nvtx: bool = False, enable_torch_compile: bool = False,
+                 detokenizer_device: Optional[str] = None, dp_rank: int = 0, dp_size: int = 1,
+                 detokenize_interval: int = None, model=None, max_prefill_tokens: int = 1024, **model_kwargs):
+        _lib.load()          # fail loudly here, not at the first step, if the CUDA library is absent
+        if not torch.cuda.is_available():
+            raise VoxB200Error("ModelWorker needs a CUDA device: there is no CPU path")
+        if detokenizer_device not in (None, "cuda", "cuda:0", f"cuda:{torch.cuda.current_device()}"):
+            raise VoxB200Error("LM/detokenizer disaggregation across GPUs is out of scope (SURVEY.md §8): replicas "
+                               "are request-parallel, one full pipeline per GPU")
+        self.device = f"cuda:{torch.cuda.current_device()}"
+        self.detokenizer_device = self.device
+        if model is None:
+            model = load_model(model_name, device=self.device, top_p=top_p, top_k=top_k, min_p=min_p,
+                               temperature=temperature, max_tokens=max_tokens, repetition_penalty=repetition_penalty,
+                               repetition_window=repetition_window, cfg_scale=cfg_scale, greedy=greedy,
+                               enable_torch_compile=enable_torch_compile, audio_decoder_device=self.device,
+                               detokenize_interval=detokenize_interval, **model_kwargs)
+        self.model = model
+        self.max_batch_size, self.dp_rank, self.dp_size = max_batch_size, dp_rank, dp_size
+        self.max_num_pages, self.page_size = max_num_pages, page_size
+        self.nvtx_enabled = enable_nvtx
+        self.top_p, self.top_k, self.min_p, self.temperature = top_p, top_k, min_p, temperature
+        self.repetition_penalty, self.repetition_window, self.cfg_scale = repetition_penalty, repetition_window, cfg_scale
+        import logging
+
+        self.logger = logging.getLogger(__name__)
+        if self.model.has_depth_transformer or self.model.needs_watermarking:
+            raise VoxB200Error("depth-transformer / watermarked models are not on the B200 path yet (SURVEY.md §8f)")
+        self.needs_watermarking = False
+        self.has_depth_transformer = False
+        self.empty_pages: "queue.Queue[int]" = queue.Queue()
+        for i in range(max_num_pages):
+            self.empty_pages.put(i)
+        # attributes the reference schedulers read (scheduler/base.py:243-245)
+        self.prefill_graph_batch_size = max_batch_size      # no prefill-graph row limit here
+        self.max_prefill_tokens = max_prefill_tokens
+        self.cuda_graph_seq_len_buckets = [max_prefill_tokens]
+        self._prepare_attention_wrappers()
+
+    # ---- reference properties (worker/base.py:127-148) ------------------------------------------
+    @property
+    def detokenize_interval(self) -> int:
+        return self.model.detokenize_interval
+
+    @property
+    def detokenize_overlap(self) -> int:
+        return self.model.detokenize_overlap
+
+    @property
+    def supports_audio_input(self) -> bool:
+        return self.model.supports_audio_input
+
+    @property
+    def available_batch_sizes(self) -> Optional[List[int]]:
+        return None      # any batch size up to max_batch_size: graphs are captured per exact size
+
+    # ---- device state ---------------------------------------------------------------------------
+    def _prepare_attention_wrappers(self):
+        m, dev, B = self.model, self.device, self.max_batch_size
+        self.kv_cache = torch.zeros(m.num_hidden_layers, self.max_num_pages, 2, self.page_size, m.num_key_value_heads,
+                                    m.head_dim, dtype=torch.bfloat16, device=dev)
+        self.max_rows = self.max_prefill_tokens + B
+        eng = m.engine_for(self.kv_cache, self.page_size)
+        if eng.max_rows < self.max_rows:
+            raise VoxB200Error(f"model engine holds {eng.max_rows} rows, worker needs {self.max_rows}")
+        common = dict(attn_buffer=None, n_qo_head=m.num_attention_heads, n_kv_head=m.num_key_value_heads,
+                      n_state=m.num_attention_heads * m.head_dim, page_size=self.page_size, device=dev,
+                      max_pages=self.max_num_pages, max_chunks=eng.max_chunks)
+        self.prefill_wrapper = FlashInferPrefillWrapper(batch_size=B, max_seq_len=self.max_rows, **common)
+        self.decode_wrapper = FlashInferDecodeWrapper(batch_size=B, use_cuda_graph=True, **common)
+        self.staging = _Staging(B, self.max_rows, self.max_num_pages, dev)
+        # slot-resident request state
+        self.free_slots = list(range(B - 1, -1, -1))
+        self.slot_of: Dict[str, int] = {}
+        cfg = m.default_sampling_config
+        self.rep_cache = None
+        if m.use_repetition_penalty and cfg.repetition_window is not None:
+            W = cfg.repetition_window if cfg.repetition_window > 0 else 1
+            self.rep_cache = torch.zeros(B, W, m.n_codebooks, m.vocab_size, dtype=torch.bool, device=dev)
+        self.history_cap = 1 << max(6, int(np.ceil(np.log2(m.max_tokens + 64))))
+        self.next_input = torch.zeros(B, dtype=I32, device=dev)
+        self.history = torch.zeros(B, self.history_cap, dtype=I32, device=dev)
+        self.n_out = torch.zeros(B, dtype=I32, device=dev)
+        self.input_ids = torch.zeros(self.max_rows, dtype=I32, device=dev)
+        self.out_ids = torch.zeros(B, m.n_codebooks, dtype=torch.int64, device=dev)
+        # sampled ids come back through a small ring of pinned buffers + events so that a scheduler running one
+        # step ahead (scheduler/base.py:168-215) never reads a later step's ids
+        self.ring = [(torch.zeros(B, m.n_codebooks, dtype=torch.int64, pin_memory=True), torch.cuda.Event())
+                     for _ in range(4)]
+        self.ring_pos = 0
+        self.decode_graphs: Dict[int, torch.cuda.CUDAGraph] = {}
+        self.graph_pool = None
+        self.use_cuda_graph = True
+        # detokenize staging: [chunk] x (slot, first, n_valid)
+        self.max_chunks = 4 * B
+        self.win_host = torch.zeros(3, self.max_chunks, dtype=I32, pin_memory=True)
+        self.win_dev = torch.zeros(3, self.max_chunks, dtype=I32, device=dev)
+        self.pcm_host = torch.zeros(self.max_chunks, m.n_channels, m.output_audio_length, dtype=torch.int16,
+                                    pin_memory=True)
+        self.gpu_launches = 0     # launches issued by this worker's own kernels (graph nodes counted at capture)
+        self._graph_nodes: Dict[int, int] = {}
+
+    # ---- step inputs (worker/base.py:210-360) ---------------------------------------------------
+    def prepare_lm_inputs(self, lm_requests: List[Request], detokenize_requests: List[Request]) -> Optional[LMInputs]:
+        for req in detokenize_requests:
+            req.audio_decode_idx = req.next_audio_decode_idx.copy()
+        if len(lm_requests) == 0:
+            return None
+        st, m = self.staging, self.model
+        st.wait_consumed()
+        qo, ip, last, slots = st.h("qo"), st.h("indptr"), st.h("last"), st.h("slots")
+        pos, ids, row_slot, indices = st.h("pos"), st.h("ids"), st.h("row_slot"), st.h("indices")
+        if len(lm_requests) > self.max_batch_size:
+            raise VoxB200Error(f"{len(lm_requests)} LM requests exceed max_batch_size {self.max_batch_size}")
+        is_prefill = any(not r.done_lm_prefill for r in lm_requests)
+        t = 0         # rows so far
+        npg = 0       # pages so far
+        qo[0] = 0
+        ip[0] = 0
+        for i, req in enumerate(lm_requests):
+            if not req.done_lm_prefill:
+                if req.is_input_streaming and not m.supports_input_streaming:
+                    raise ValueError(f"Input streaming is not supported by model {m.model_name}.")
+                slot = self._acquire_slot(req)
+                kw = dict(req.model_kwargs)
+                if self.rep_cache is not None:
+                    self.rep_cache[slot].zero_()
+                    kw["repetition_cache"] = self.rep_cache[slot]
+                out = m.preprocess(prompt=req.prompt, audio_path=req.audio_path, **kw)
+                req.input_tokens = out.input_tokens
+                n = int(req.input_tokens.shape[0])
+                req.input_length = n
+                if out.repetition_cache is not None:
+                    req.repetition_cache = out.repetition_cache
+                if t + n > self.max_rows:
+                    raise VoxB200Error(f"prefill of {t + n} rows exceeds the worker's max_rows {self.max_rows}")
+                ids[t:t + n] = req.input_tokens[:, 0].numpy() if not req.input_tokens.is_cuda else \
+                    req.input_tokens[:, 0].cpu().numpy()
+                pos[t:t + n] = np.arange(n, dtype=np.int32)
+                row_slot[t:t + n] = -1
+                n_pages = (n + self.page_size - 1) // self.page_size
+                req.kv_token_len = n
+                req.kv_pages = [self.empty_pages.get_nowait() for _ in range(n_pages)]
+                req.kv_last_page_len = n % self.page_size or self.page_size
+                req.next_position_id = n + 1          # position n is skipped, as in worker/base.py:299
+                req.done_lm_prefill = True
+                self.n_out[slot:slot + 1].zero_()
+                t += n
+            else:
+                slot = self.slot_of[req.request_id]
+                req.kv_token_len += 1
+                req.kv_last_page_len += 1
+                if req.kv_last_page_len > self.page_size:
+                    req.kv_pages.append(self.empty_pages.get_nowait())
+                    req.kv_last_page_len = 1
+                ids[t] = 0
+                pos[t] = req.next_position_id
+                row_slot[t] = slot
+                req.next_position_id += 1
+                t += 1
+            k = len(req.kv_pages)
+            indices[npg:npg + k] = req.kv_pages
+            npg += k
+            qo[i + 1] = t
+            ip[i + 1] = npg
+            last[i] = req.kv_last_page_len
+            slots[i] = slot
+        B = len(lm_requests)
+        rep = None
+        if self.rep_cache is not None:
+            rep = self.rep_cache       # slot-resident; rows selected through `slots` (no per-step torch.stack)
+        return {"qo_indptr": qo[:B + 1].tolist(), "paged_kv_indptr": ip[:B + 1].tolist(),
+                "paged_kv_indices": indices[:npg].tolist(),
+                "paged_kv_last_page_len": last[:B].tolist(), "input_ids": self.input_ids[:t].view(t, 1),
+                "position_ids": st.d("pos", t), "input_features": None, "input_masks": None,
+                "repetition_cache": rep, "is_prefill": is_prefill, "n_rows": t, "n_pages": npg}
+
+    def _acquire_slot(self, req: Request) -> int:
+        if req.request_id in self.slot_of:
+            return self.slot_of[req.request_id]
+        if not self.free_slots:
+            raise VoxB200Error("no free batch slot: more concurrent requests than max_batch_size")
+        s = self.free_slots.pop()
+        self.slot_of[req.request_id] = s
+        return s
+
+    # ---- LM steps -------------------------------------------------------------------------------
+    def _device_step(self, B: int, T: int, is_prefill: bool):
+        """Everything a step does on the device after the staging buffer is filled; capturable."""
+        st, m = self.staging, self.model
+        wrapper = self.prefill_wrapper if is_prefill else self.decode_wrapper
+        wrapper.plan_device(st.d("qo", B + 1) if is_prefill else None, st.d("indptr", B + 1), st.d("indices"),
+                            st.d("last", B), B, T)
+        ops.build_input_ids(self.input_ids, st.d("ids"), self.next_input, st.d("row_slot"), T)
+        last_rows = None
+        if is_prefill:
+            last_rows = st.d("qo", B + 1)[1:]         # qo_indptr[1:] (the kernel subtracts 1)
+        logits = m.forward(self.input_ids[:T].view(T, 1), st.d("pos", T), wrapper, self.kv_cache,
+                           logits_rows=last_rows, logits_rows_minus_one=is_prefill, n_rows=T)
+        slots = st.d("slots", B)
+        out = self.out_ids[:B]
+        m.sampling_device(logits[:B], None, self.rep_cache, cache_rows=slots if self.rep_cache is not None else None,
+                          out=out.view(-1))
+        ops.token_feedback(out.view(-1), slots, self.next_input, self.history, self.n_out)
+
+    def _run_step(self, requests: List[Request], lm_inputs: LMInputs) -> Optional[Coroutine]:
+        if len(requests) == 0:
+            return None
+        B, T, is_prefill = len(requests), lm_inputs["n_rows"], lm_inputs["is_prefill"]
+        self.nvtx_range_push(f"lm_{'prefill' if is_prefill else 'decode'}_bs{B}")
+        self.staging.upload()
+        if not is_prefill and self.use_cuda_graph:
+            g = self.decode_graphs.get(B)
+            if g is None:
+                g = self._capture_decode(B)
+            g.replay()
+            self.gpu_launches += self._graph_nodes[B]
+        else:
+            self._device_step(B, T, is_prefill)
+        ids_host, ready = self.ring[self.ring_pos]
+        self.ring_pos = (self.ring_pos + 1) % len(self.ring)
+        ids_host[:B].copy_(self.out_ids[:B], non_blocking=True)
+        ready.record()
+        self.nvtx_range_pop()
+        slots_host = self.staging.h("slots")[:B].tolist()
+        return self.model.sampling_host(self.out_ids[:B], requests, self.rep_cache, ids_host=ids_host, ready=ready,
+                                        cache_rows_host=slots_host)
+
+    def _capture_decode(self, B: int) -> torch.cuda.CUDAGraph:
+        """Warm the kernels once eagerly on the live inputs is not possible (it would advance state twice), so the
+        graph is captured directly: every launch inside is allocation-free and the library's one-time
+        cudaFuncSetAttribute calls are legal during capture."""
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        before = ops.launch_count()
+        with torch.cuda.stream(s):
+            with torch.cuda.graph(g, pool=self.graph_pool, stream=s):
+                self._device_step(B, B, False)
+        torch.cuda.current_stream().wait_stream(s)
+        if self.graph_pool is None:
+            self.graph_pool = g.pool()
+        self._graph_nodes[B] = ops.launch_count() - before
+        self.decode_graphs[B] = g
+        return g
+
+    def run_lm_prefill(self, requests: List[Request], lm_inputs: LMInputs) -> Optional[Coroutine]:
+        return self._run_step(requests, lm_inputs)
+
+    def run_lm_decode(self, requests: List[Request], lm_inputs: LMInputs) -> Optional[Coroutine]:
+        return self._run_step(requests, lm_inputs)
+
+    # ---- detokenize (worker/base.py:616-681, cuda_graph_worker.py:1162-1280) ----------------------
+    def run_detokenize(self, requests: List[Request]):
+        if len(requests) == 0:
+            return
+        interval = self.detokenize_interval
+        wh = self.win_host.numpy()
+        mapping = []
+        n = 0
+        for ri, req in enumerate(requests):
+            for ci, d in enumerate(req.audio_decode_idx):
+                if n >= self.max_chunks:
+                    raise VoxB200Error("more detokenize chunks in one call than the staging buffers hold")
+                n_valid = min(interval, len(req.lm_output_audio_tokens) - d)
+                if n_valid <= 0:
+                    continue
+                wh[0, n], wh[1, n], wh[2, n] = self.slot_of[req.request_id], d, n_valid
+                mapping.append((ri, ci, n_valid))
+                n += 1
+        if n:
+            self.nvtx_range_push(f"detokenize_bs{n}")
+            self.win_dev.copy_(self.win_host, non_blocking=True)
+            windows = ops.gather_windows(self.history, self.win_dev[0], self.win_dev[1], self.win_dev[2], interval, n=n)
+            audio = self.model.postprocess(windows.view(n, interval, 1))
+            pcm = ops.pcm16(audio)
+            self.pcm_host[:n].copy_(pcm, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            self.nvtx_range_pop()
+            pcm_np = self.pcm_host.numpy()
+            for i, (ri, ci, n_valid) in enumerate(mapping):
+                a16 = pcm_np[i]
+                if n_valid < interval:      # drop the audio of the padded tokens (worker/base.py:661-668)
+                    a16 = a16[:, :int(a16.shape[1] * (n_valid - 0.5) / interval)]
+                requests[ri].output_audio.put(a16.tobytes())
+        for req in requests:
+            if req.done_lm_generation and req.audio_decode_idx and \
+                    req.audio_decode_idx[-1] + interval >= len(req.lm_output_audio_tokens):
+                req.done_all = True
+
+    # ---- misc ---------------------------------------------------------------------------------------
+    def free_kv_cache(self, request: Request):
+        if getattr(request, "kv_pages", None):
+            for p in request.kv_pages:
+                self.empty_pages.put(p)
+            request.kv_pages = []
+            request.kv_token_len = 0
+            request.kv_last_page_len = 0
+        s = self.slot_of.pop(request.request_id, None)
+        if s is not None:
+            self.free_slots.append(s)
+
+    def nvtx_range_push(self, name: str):
+        if self.nvtx_enabled:
+            torch.cuda.synchronize()
+            torch.cuda.nvtx.range_push(name)
+
+    def nvtx_range_pop(self):
+        if self.nvtx_enabled:
+            torch.cuda.synchronize()
+            torch.cuda.nvtx.range_pop()
+
+
+class CudaGraphWorker(ModelWorker):
+    """Name kept for ``isinstance(worker, CudaGraphWorker)`` checks (scheduler/base.py:242): the B200 worker
+    always replays decode steps from CUDA graphs."""
