@@ -124,6 +124,7 @@ int vb_qkv_rope_append(void* d_q_out, void* d_layer_kv, const float* d_partials,
  *   vb_build_input_ids: out[i] = row_slot[i] >= 0 ? next_input[row_slot[i]] : host_ids[i]  (decode rows feed
  *                       back the id sampled last step, prefill rows use the uploaded prompt ids; replaces the
  *                       torch.cat of worker/base.py:329);
+ *   vb_latest_window:   first[i] = max(0, n_out[slot[i]] - window)  (start of the newest full window);
  *   vb_gather_windows:  windows[i][j] = history[slot[i]][(first[i] + min(j, n_valid[i]-1)) % cap], j < window
  *                       (the detokenize window of cuda_graph_worker.py:1176-1190 incl. last-token padding). */
 int vb_decode_advance(int32_t* d_kv_len, int32_t* d_pos, const int32_t* d_active, int B, void* stream);
@@ -132,6 +133,8 @@ int vb_token_feedback(const int64_t* d_ids, const int32_t* d_slots, int32_t* d_n
 int vb_gather_i32(int32_t* d_out, const int32_t* d_src, const int32_t* d_idx, int n, void* stream);
 int vb_build_input_ids(int32_t* d_out, const int32_t* d_host_ids, const int32_t* d_next_input,
                        const int32_t* d_row_slot, int n, void* stream);
+int vb_latest_window(int32_t* d_first, const int32_t* d_n_out, const int32_t* d_slot, int n, int window,
+                     void* stream);
 int vb_gather_windows(int64_t* d_windows, const int32_t* d_history, const int32_t* d_slot, const int32_t* d_first,
                       const int32_t* d_n_valid, int n, int history_cap, int window, void* stream);
 /* embedding gather: orpheus.py:408 */

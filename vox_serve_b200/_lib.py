@@ -27,6 +27,7 @@ SIGNATURES = {
     "vb_token_feedback": (c_int, [P, P, P, P, P, c_int, c_int, P]),
     "vb_gather_i32": (c_int, [P, P, P, c_int, P]),
     "vb_build_input_ids": (c_int, [P, P, P, P, c_int, P]),
+    "vb_latest_window": (c_int, [P, P, P, c_int, c_int, P]),
     "vb_gather_windows": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
     "vb_kv_append": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     "vb_paged_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),

@@ -564,6 +564,12 @@ __global__ void build_input_ids_kernel(int32_t* out, const int32_t* host_ids, co
   const int s = row_slot[i];
   out[i] = s >= 0 ? next_input[s] : host_ids[i];
 }
+// newest full window per slot: first[i] = n_out[slot[i]] - window (device-resident loop: the host never
+// sees the token counters between replays)
+__global__ void latest_window_kernel(int32_t* first, const int32_t* n_out, const int32_t* slot, int n, int window) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) first[i] = max(0, n_out[slot ? slot[i] : i] - window);
+}
 // windows[i][j] = history[slot[i]][(first[i] + min(j, n_valid[i] - 1)) % cap], j < win : the detokenize window
 // of cuda_graph_worker.py:1176-1190 (a short last window repeats its final token, :1183-1185).
 __global__ void gather_windows_kernel(int64_t* windows, const int32_t* history, const int32_t* slot,
@@ -608,6 +614,15 @@ int vb_build_input_ids(int32_t* d_out, const int32_t* d_host_ids, const int32_t*
   if (n <= 0) return 0;
   vb::build_input_ids_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       d_out, d_host_ids, d_next_input, d_row_slot, n);
+  VB_CHECK_LAUNCH();
+  return 0;
+}
+int vb_latest_window(int32_t* d_first, const int32_t* d_n_out, const int32_t* d_slot, int n, int window,
+                     void* stream) {
+  VB_CHECK_ARG(d_first && d_n_out, "vb_latest_window: null pointer");
+  if (n <= 0) return 0;
+  vb::latest_window_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_first, d_n_out, d_slot, n,
+                                                                                         window);
   VB_CHECK_LAUNCH();
   return 0;
 }

@@ -180,3 +180,25 @@ class LlamaEngine:
         if n_out > self.max_out_rows:
             raise VoxB200Error(f"logits requested for {n_out} rows; pass last_rows (max {self.max_out_rows})")
         return ops.gemm(x, w.lm_head, mode=0, out=self.logits[:n_out])
+
+    # ---- kernel-isolated passes for the roofline measurement (bench.py) --------------------------------
+    def gemm_pass(self, n_rows: int) -> None:
+        """Every projection launch of one decode step (QKV, O, gate/up, down per layer + lm_head) on the live
+        buffers, nothing else: what bench.py replays to time the GEMM kernel alone."""
+        d, w, R = self.dims, self.w, n_rows
+        hq, D, H = d.num_attention_heads, d.head_dim, d.hidden_size
+        s_qkv, s_o, s_dn = self._split(self.split_qkv, R), self._split(self.split_o, R), self._split(self.split_down, R)
+        normed, attn, act = self.normed[:R], self.attn[:R], self.act[:R]
+        for L in w.layers:
+            ops.gemm(normed, L["qkv"], mode=1, split_k=s_qkv, out=self._partials(s_qkv, R, self.qkv_w))
+            ops.gemm(attn.view(R, hq * D), L["o"], mode=1, split_k=s_o, out=self._partials(s_o, R, H))
+            ops.gemm(normed, L["gu"], mode=2, out=act)
+            ops.gemm(act, L["down"], mode=1, split_k=s_dn, out=self._partials(s_dn, R, H))
+        ops.gemm(normed[:min(R, self.max_out_rows)], w.lm_head, mode=0, out=self.logits[:min(R, self.max_out_rows)])
+
+    def attention_only(self, layer: int, n_rows: int, plan: ops.RowPlan) -> None:
+        """The paged-attention launch of one layer on the live cache and the plan of the last step."""
+        d = self.dims
+        ops.paged_attn(self.q[:n_rows], self.kv_map, layer * self.pages_per_layer, plan, n_rows,
+                       d.num_key_value_heads, self.page_size, self.chunk, self.attn_ws, out=self.attn[:n_rows],
+                       grid_ctas=self.attn_grid)

@@ -409,6 +409,11 @@ def build_input_ids(out: torch.Tensor, host_ids: torch.Tensor, next_input: torch
     return out
 
 
+def latest_window(first: torch.Tensor, n_out: torch.Tensor, slot: Optional[torch.Tensor], n: int, window: int):
+    call("vb_latest_window", first.data_ptr(), n_out.data_ptr(), _p(slot), n, window, _stream())
+    return first
+
+
 def gather_windows(history: torch.Tensor, slot: torch.Tensor, first: torch.Tensor, n_valid: Optional[torch.Tensor],
                    window: int, out: Optional[torch.Tensor] = None, n: Optional[int] = None) -> torch.Tensor:
     n = slot.numel() if n is None else n

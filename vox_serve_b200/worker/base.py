@@ -367,6 +367,133 @@ class ModelWorker:
                     req.audio_decode_idx[-1] + interval >= len(req.lm_output_audio_tokens):
                 req.done_all = True
 
+    # ---- device-resident multi-step decode --------------------------------------------------------
+    def run_lm_decode_resident(self, requests: List[Request], n_steps: int, detokenize: bool = True,
+                               timing: Optional[dict] = None) -> int:
+        """``n_steps`` decode steps for ``requests`` (all past prefill) with NO host work in between: pages for the
+        whole span are allocated up front, kv lengths / positions / input ids / repetition caches / token history
+        advance on the device, and each step is one CUDA-graph replay.  With ``detokenize`` the newest full
+        window of every request is vocoded (SNAC + PCM16, result left in HBM) after every
+        ``interval - overlap`` steps, as the scheduler would schedule it.  Afterwards the requests' host-side
+        fields are brought up to date from the device history (stop ids are honoured only at the end of the span:
+        tokens sampled after a stop id are dropped).  Returns the number of graph replays issued.
+
+        This is the steady-state inner loop the per-step API converges to when nothing joins or leaves the batch;
+        bench.py times it as the device-resident figure (``value``) next to the per-step API (``e2e``)."""
+        B = len(requests)
+        if B == 0 or n_steps <= 0:
+            return 0
+        if any(not r.done_lm_prefill or r.done_lm_generation for r in requests):
+            raise VoxB200Error("resident decode needs requests that are past prefill and still generating")
+        m, st = self.model, self.staging
+        st.wait_consumed()
+        ip, slots, indices, row_slot = st.h("indptr"), st.h("slots"), st.h("indices"), st.h("row_slot")
+        kv0 = np.zeros(B, dtype=np.int32)
+        pos0 = np.zeros(B, dtype=np.int32)
+        npg = 0
+        ip[0] = 0
+        for i, req in enumerate(requests):
+            need = (req.kv_token_len + n_steps + self.page_size - 1) // self.page_size
+            while len(req.kv_pages) < need:
+                req.kv_pages.append(self.empty_pages.get_nowait())
+            k = len(req.kv_pages)
+            indices[npg:npg + k] = req.kv_pages
+            npg += k
+            ip[i + 1] = npg
+            slots[i] = row_slot[i] = self.slot_of[req.request_id]
+            kv0[i], pos0[i] = req.kv_token_len, req.next_position_id - 1
+        st.upload()
+        if not hasattr(self, "res_kv_len"):
+            self.res_kv_len = torch.zeros(self.max_batch_size, dtype=I32, device=self.device)
+            self.res_pos = torch.zeros(self.max_batch_size, dtype=I32, device=self.device)
+            self.res_first = torch.zeros(self.max_batch_size, dtype=I32, device=self.device)
+            self.res_pcm = torch.zeros(self.max_batch_size, m.n_channels, m.output_audio_length, dtype=torch.int16,
+                                       device=self.device)
+            self.res_graphs: Dict[int, tuple] = {}
+        self.res_kv_len[:B].copy_(torch.from_numpy(kv0), non_blocking=False)
+        self.res_pos[:B].copy_(torch.from_numpy(pos0), non_blocking=False)
+
+        def lm_step():
+            ops.decode_advance(self.res_kv_len[:B], self.res_pos[:B])
+            self.decode_wrapper.plan_device(None, st.d("indptr", B + 1), st.d("indices"), None, B, B,
+                                            kv_len=self.res_kv_len)
+            ops.build_input_ids(self.input_ids, st.d("ids"), self.next_input, st.d("row_slot"), B)
+            logits = m.forward(self.input_ids[:B].view(B, 1), self.res_pos[:B], self.decode_wrapper, self.kv_cache,
+                               n_rows=B)
+            sl = st.d("slots", B)
+            out = self.out_ids[:B]
+            m.sampling_device(logits[:B], None, self.rep_cache, cache_rows=sl if self.rep_cache is not None else None,
+                              out=out.view(-1))
+            ops.token_feedback(out.view(-1), sl, self.next_input, self.history, self.n_out)
+
+        def detok_step():
+            sl = st.d("slots", B)
+            ops.latest_window(self.res_first, self.n_out, sl, B, self.detokenize_interval)
+            win = ops.gather_windows(self.history, sl, self.res_first, None, self.detokenize_interval, n=B)
+            audio = m.postprocess(win.view(B, self.detokenize_interval, 1))
+            ops.pcm16(audio, out=self.res_pcm[:B])
+
+        if B not in self.res_graphs:
+            graphs = []
+            for fn in (lm_step, detok_step):
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                before = ops.launch_count()
+                with torch.cuda.stream(s):
+                    with torch.cuda.graph(g, pool=self.graph_pool, stream=s):
+                        fn()
+                torch.cuda.current_stream().wait_stream(s)
+                if self.graph_pool is None:
+                    self.graph_pool = g.pool()
+                graphs.append((g, ops.launch_count() - before))
+            self.res_graphs[B] = tuple(graphs)
+        (g_lm, n_lm), (g_dt, n_dt) = self.res_graphs[B]
+        hop = self.detokenize_interval - self.detokenize_overlap
+        replays = 0
+        if timing is not None:
+            timing["start"].record()
+        for k in range(n_steps):
+            g_lm.replay()
+            self.gpu_launches += n_lm
+            replays += 1
+            if detokenize and (k + 1) % hop == 0:
+                g_dt.replay()
+                self.gpu_launches += n_dt
+                replays += 1
+        if timing is not None:
+            timing["end"].record()
+            timing["lm_nodes"], timing["detok_nodes"] = n_lm, n_dt
+        # ---- bring the host-side request state up to date ----
+        torch.cuda.synchronize()
+        hist = self.history.cpu()
+        n_now = self.n_out.cpu()
+        for i, req in enumerate(requests):
+            s_ = int(slots[i])
+            n_new = n_steps
+            base = int(n_now[s_]) - n_new
+            toks = [int(hist[s_, (base + j) % self.history_cap]) for j in range(n_new)]
+            for j, tok in enumerate(toks):
+                t = torch.tensor([[tok]], dtype=torch.int64)
+                req.lm_output_tokens.append(t)
+                req.lm_output_audio_tokens.append(t)
+                req.kv_token_len += 1
+                req.next_position_id += 1
+                if tok == m.stop_token_id:
+                    req.lm_output_audio_tokens.pop()
+                    req.done_lm_generation, req.finish_reason = True, "stop_id_encountered"
+                    break
+                if req.next_position_id > m.max_tokens:
+                    req.done_lm_generation, req.finish_reason = True, "max_tokens_reached"
+                    break
+            req.kv_last_page_len = req.kv_token_len % self.page_size or self.page_size
+            keep = (req.kv_token_len + self.page_size - 1) // self.page_size
+            while len(req.kv_pages) > keep:          # pages reserved for the span but not reached
+                self.empty_pages.put(req.kv_pages.pop())
+            req.input_tokens = self.out_ids[i:i + 1]
+        return replays
+
     # ---- misc ---------------------------------------------------------------------------------------
     def free_kv_cache(self, request: Request):
         if getattr(request, "kv_pages", None):
