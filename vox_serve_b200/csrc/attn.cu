@@ -334,7 +334,7 @@ static int launch_attn(const AttnParams& p, const CUtensorMap* map, int grid, cu
   using L = AttnSmem<D, CHUNK, STAGES>;
   const int smem = L::bytes(p.G);
   auto kern = paged_attn_kernel<D, CHUNK, STAGES, HI>;
-  VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, VB_MAX_DYN_SMEM));
   kern<<<grid, CHUNK * 2 + 32, smem, stream>>>(p, *map);
   VB_CHECK_LAUNCH();
   return 0;

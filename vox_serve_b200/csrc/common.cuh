@@ -28,6 +28,10 @@ void set_error(const char* fmt, ...);
     }                                                                              \
   } while (0)
 #define VB_CHECK_LAUNCH() VB_CHECK_CUDA(cudaGetLastError())
+// Largest opt-in dynamic shared memory of an sm_100 CTA.  Kernels raise their limit to this ONCE (not to the size
+// of the launch at hand): a per-launch value would be baked into nothing -- CUDA-graph kernel nodes replay
+// against whatever the function attribute was set to last, so a later, smaller launch would break them.
+constexpr int VB_MAX_DYN_SMEM = 227 * 1024;
 
 // ---------------------------------------------------------------------------------------------
 // small device utilities

@@ -458,7 +458,7 @@ int vb_reduce_residual_rmsnorm(void* d_hidden_out, void* d_normed_out, const flo
   const size_t smem = static_cast<size_t>(N) * sizeof(float);
   if (smem > 48 * 1024)
     VB_CHECK_CUDA(cudaFuncSetAttribute(reduce_residual_rmsnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
+                                       VB_MAX_DYN_SMEM));
   reduce_residual_rmsnorm_kernel<<<T, 256, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<__nv_bfloat16*>(d_hidden_out), static_cast<__nv_bfloat16*>(d_normed_out), d_partials, split_k,
       static_cast<const __nv_bfloat16*>(d_residual), static_cast<const __nv_bfloat16*>(d_norm_weight), T, N, eps);
@@ -478,7 +478,7 @@ int vb_qkv_rope_append(void* d_q_out, void* d_layer_kv, const float* d_partials,
   VB_CHECK_ARG(smem <= 200 * 1024, "vb_qkv_rope_append: row too wide for shared memory");
   if (smem > 48 * 1024)
     VB_CHECK_CUDA(cudaFuncSetAttribute(qkv_rope_append_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
+                                       VB_MAX_DYN_SMEM));
   qkv_rope_append_kernel<<<T, 256, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<__nv_bfloat16*>(d_q_out), static_cast<__nv_bfloat16*>(d_layer_kv), d_partials, split_k, d_pos,
       d_freq, d_row_page, d_row_slot, T, n_q, n_kv, head_dim, page_size, rotary_dim, interleave);

@@ -207,7 +207,7 @@ int vb_gemm_bf16(void* d_y, const void* w_map, const void* x_map, int T, int N, 
   VB_CHECK_ARG(stages >= 2, "vb_gemm_bf16: tile too large for shared memory");
   p.stages = stages;
   const int smem = stages * stage_bytes + extra;
-  VB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  VB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VB_MAX_DYN_SMEM));
   dim3 grid((N + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M, split_k, (T + p.t_tile - 1) / p.t_tile);
   gemm_bf16_kernel<<<grid, GEMM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
       p, *static_cast<const CUtensorMap*>(w_map), *static_cast<const CUtensorMap*>(x_map));
