@@ -28,12 +28,17 @@ extern "C" {
 
 const char* vb_last_error(void);
 int vb_version(void);
+/* Programmatic dependent launch between the library's kernels (default on; env VB_PDL=0 turns it off).  Returns the
+ * previous setting.  With it on, consecutive kernels overlap: a kernel streams its weights / old KV while its
+ * predecessor is still running (see csrc/common.cuh). */
+int vb_set_pdl(int enabled);
 /* SM count / max dynamic smem of the current device (host query used to size persistent grids). */
 int vb_device_info(int* sm_count, int* max_smem_optin);
 
 /* ---- TMA descriptors ------------------------------------------------------------------------ */
 /* Whole paged KV cache  [n_slabs = layers*pages][2][page_size][n_kv_heads][head_dim] bf16
- * (layout of vox_serve/worker/base.py:170-179).  Box = [box_tokens x 64 dims] of one head, 128B swizzle. */
+ * (layout of vox_serve/worker/base.py:170-179).  Box = [64 dims x box_tokens x all kv heads], 128B swizzle, with the
+ * dimensions ordered (dim, token, head, k|v, page) so that it lands in shared memory as [head][token][64]. */
 int vb_tensor_map_kv(void* out_map, const void* d_kv, int64_t n_slabs, int page_size, int n_kv_heads,
                      int head_dim, int box_tokens);
 /* Row-major [rows][cols] bf16 matrix with leading dimension ld (elements); box = [box_rows x 64], 128B swizzle.
@@ -57,20 +62,21 @@ int vb_rope(void* d_q_out, void* d_k_out, const void* d_q, const void* d_k, cons
 /* ---- paged KV bookkeeping: flashinfer_utils.py:86-124 (prefill), :217-225 (decode) -----------
  * Device-side "plan": from the page table (indptr [B+1], indices, last_page_len [B]) and, for prefill,
  * qo_indptr [B+1], derive per query row: owning request, visible kv length, (page, slot) of its new
- * K/V entry; plus the exclusive prefix of 64-token (or page-sized) attention chunks per row.
+ * K/V entry; plus the exclusive prefix of chunk_tokens-sized attention tiles per row.
  * qo_indptr == NULL means decode (one row per request).  d_kv_len (optional, [B]) gives each request's kv
  * length explicitly -- then the page table may hold pre-allocated pages beyond it and last_page_len is
  * ignored (device-resident decode loop; the reference derives the length from the table, :96-97).  Rows >= n_rows_valid up to n_rows_padded get
  * page = -1 (their K/V append is skipped; the reference scatters them into page -1).
- * Outputs (device int32): row_req[R], row_kvlen[R], row_page[R], row_slot[R], row_chunk_start[R+1], and
- * rc_meta[max_chunks][8]: one record per (row, chunk) work item of the attention kernel
- * {row, first token, page, row kv length, chunks of the row, first chunk index of the row, 0, 0}
- * (32-byte aligned; records beyond max_chunks are not written and vb_paged_attn traps on overflow). */
+ * Outputs (device int32): row_req[R], row_kvlen[R], row_page[R], row_slot[R], row_chunk_start[R+1] (exclusive
+ * prefix of ceil(kvlen / chunk_tokens): the attention kernel's work list), row_pagebase[R] (= kv_indptr of the
+ * row's request, so the attention kernel resolves a tile's page with one load) and row_old[R] (tokens of the
+ * request that were already in the cache before this step: tiles below it may be fetched before the kernel that
+ * appends the new K/V has finished). */
 int vb_plan_rows(const int32_t* d_qo_indptr, const int32_t* d_kv_indptr, const int32_t* d_kv_indices,
                  const int32_t* d_last_page_len, const int32_t* d_kv_len, int n_req, int n_rows_padded, int page_size,
                  int chunk_tokens,
                  int32_t* d_row_req, int32_t* d_row_kvlen, int32_t* d_row_page, int32_t* d_row_slot,
-                 int32_t* d_row_chunk_start, int32_t* d_rc_meta, int max_chunks, void* stream);
+                 int32_t* d_row_chunk_start, int32_t* d_row_pagebase, int32_t* d_row_old, void* stream);
 
 /* kv[page][0][slot] = k ; kv[page][1][slot] = v : flashinfer_utils.py:144-145, 243-244.
  * d_layer_kv points at one layer's [pages][2][page_size][n_kv][D]. */
@@ -79,17 +85,21 @@ int vb_kv_append(void* d_layer_kv, const void* d_k, const void* d_v, const int32
 
 /* ---- paged attention: FlashInferDecodeWrapper.run / FlashInferPrefillWrapper.run
  * (flashinfer_utils.py:132, 228-230).  One query row per entry of the plan; causal by construction
- * (row kv length).  q/out [R][n_q][D] bf16.  kv_map from vb_tensor_map_kv over the WHOLE cache;
- * slab_base = layer * pages_per_layer.  d_row_chunk_start / d_rc_meta come from vb_plan_rows with the
- * same chunk_tokens and max_chunks_total.  d_workspace: vb_paged_attn_workspace_bytes(); it must be
- * zero-filled once before first use (arrival counters; the kernel restores them to zero).
- * grid_ctas: persistent grid size (2 per SM is a good default). */
-size_t vb_paged_attn_workspace_bytes(int max_rows, int max_chunks_total, int n_q, int n_kv, int head_dim);
-int vb_paged_attn(void* d_out, const void* d_q, const void* kv_map, int64_t slab_base,
-                  const int32_t* d_row_kvlen, const int32_t* d_row_chunk_start, const int32_t* d_rc_meta,
-                  int n_rows, int max_chunks_total, int n_q, int n_kv, int head_dim, int page_size,
+ * (row kv length).  q/out [R][n_q][D] bf16.  d_kv = base of the WHOLE cache [slabs][2][page][n_kv][D];
+ * slab_base = layer * pages_per_layer.  d_row_kvlen / d_row_chunk_start / d_row_pagebase / d_row_old come from vb_plan_rows
+ * with chunk_tokens = vb_attn_tile_tokens(page_size, n_kv); d_kv_indices is the page table the plan was made from.
+ * The linearised (row, tile) list is cut into grid_ctas equal ranges (one CTA per SM is the default).
+ * d_workspace: vb_paged_attn_workspace_bytes(max_rows, ws_grid_ctas, ...) bytes, zero-filled once before first
+ * use (arrival counters; the kernel restores them to zero); grid_ctas <= ws_grid_ctas. */
+/* tile size (tokens) the attention kernel and the plan must use for this geometry: 16 * (8 / n_kv), reduced
+ * until it divides page_size */
+int vb_attn_tile_tokens(int page_size, int n_kv);
+size_t vb_paged_attn_workspace_bytes(int max_rows, int max_grid_ctas, int n_q, int n_kv, int head_dim);
+int vb_paged_attn(void* d_out, const void* d_q, const void* d_kv, int64_t slab_base,
+                  const int32_t* d_row_kvlen, const int32_t* d_row_chunk_start, const int32_t* d_row_pagebase,
+                  const int32_t* d_row_old, const int32_t* d_kv_indices, int n_rows, int n_q, int n_kv, int head_dim, int page_size,
                   int chunk_tokens, float sm_scale, void* d_workspace, size_t workspace_bytes, int grid_ctas,
-                  void* stream);
+                  int ws_grid_ctas, void* stream);
 
 /* ---- dense projections (nn.Linear, bias-free): model/orpheus.py:41-47, 68-79, 197 -------------
  * Y[T][N] = X[T][K] * W[N][K]^T on tcgen05 (weights are the 128-row MMA operand, tokens the N side).

@@ -32,11 +32,12 @@ def timeit(fn, iters=20, warm=5, flush=None):
 
 def main():
     dev = "cuda"
+    which = set(sys.argv[1:]) or {"gemm", "attn", "sampler"}
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     out = []
     # ---- GEMMs, T = 32 ----
     T = 32
-    for name, N, K, mode in (("qkv", 5120, 3072, 1), ("o", 3072, 3072, 1), ("gate_up", 16384, 3072, 2),
+    for name, N, K, mode in () if "gemm" not in which else (("qkv", 5120, 3072, 1), ("o", 3072, 3072, 1), ("gate_up", 16384, 3072, 2),
                              ("down", 3072, 8192, 1), ("lm_head", 156940, 3072, 0)):
         x = torch.randn(T, K, device=dev).to(BF)
         w = (torch.randn(N, K, device=dev) * 0.02).to(BF)
@@ -53,7 +54,7 @@ def main():
             print(json.dumps(out[-1]), flush=True)
     # ---- paged decode attention ----
     hq, hkv, D, ps = 24, 8, 128, 128
-    for kvlen in (160, 728, 1333):
+    for kvlen in () if "attn" not in which else (160, 250, 480, 728, 890, 1333):
         B = 32
         n_pages_req = (kvlen + ps - 1) // ps
         n_pages = B * n_pages_req + 8
@@ -63,14 +64,15 @@ def main():
         last = torch.full((B,), kvlen - (n_pages_req - 1) * ps, dtype=torch.int32, device=dev)
         mc = B * ((kvlen + 63) // 64)
         plan = ops.RowPlan(B, dev, mc)
-        ops.plan_rows(plan, None, indptr, indices, last, B, B, ps, 64)
-        ws = ops.paged_attn_workspace(B, mc, hq, hkv, D, dev)
-        kv_map = ops.tensor_map_kv(cache, 64)
+        TOK = ops.attn_chunk_tokens(ps, hkv)
+        ops.plan_rows(plan, None, indptr, indices, last, B, B, ps, TOK)
+        ws = ops.AttnWorkspace(B, hq, hkv, D, dev, grid_ctas=296)
+        kv_map = ops.tensor_map_kv(cache, TOK)
         q = torch.randn(B, hq, D, device=dev).to(BF)
         o = torch.empty_like(q)
         byt = B * kvlen * 2 * hkv * D * 2 + 2 * q.numel() * 2
-        for grid in (148, 296, 444):
-            fn = lambda: ops.paged_attn(q, kv_map, 0, plan, B, hkv, ps, 64, ws, out=o, grid_ctas=grid)
+        for grid in (74, 148, 296):
+            fn = lambda: ops.paged_attn(q, kv_map, 0, plan, B, hkv, ps, TOK, ws, out=o, grid_ctas=grid)
             med, best = timeit(fn, flush=flush)
             out.append(dict(kernel="paged_attn_decode", kv_len=kvlen, grid=grid, ms=med * 1e3, best_ms=best * 1e3,
                             GBs=byt / med / 1e9, best_GBs=byt / best / 1e9))
@@ -79,7 +81,7 @@ def main():
     V = 156940
     logits = (torch.randn(32, V, device=dev) * 4).to(BF)
     cache = torch.zeros(32, 1, 1, V, dtype=torch.bool, device=dev)
-    for strat, kw in (("greedy", {}), ("top_p", dict(top_p=0.8, temperature=0.6))):
+    for strat, kw in () if "sampler" not in which else (("greedy", {}), ("top_p", dict(top_p=0.8, temperature=0.6))):
         fn = lambda: ops.sample(logits, strat, rep_cache=cache, penalty=1.3, **kw)
         med, best = timeit(fn)
         out.append(dict(kernel=f"sample_{strat}", ms=med * 1e3, best_ms=best * 1e3))

@@ -147,7 +147,7 @@ def _attn_case(ops, kv_lens, page_size, hq, hkv, D, seed, prefill_new=None, n_pa
     indptr, indices, last = _random_page_table(kv_lens, page_size, n_pages, seed)
     L_layers, layer = 2, 1
     cache = (torch.randn(L_layers, n_pages, 2, page_size, hkv, D, generator=g(seed + 1)) * 1.0).to(BF)
-    chunk = ops.attn_chunk_tokens(page_size)
+    chunk = ops.attn_chunk_tokens(page_size, hkv)
     if prefill_new is None:
         R = len(kv_lens)
         qo = None
@@ -171,16 +171,22 @@ def _attn_case(ops, kv_lens, page_size, hq, hkv, D, seed, prefill_new=None, n_pa
                   page_size, chunk)
     assert int(plan.row_chunk_start[R].item()) == max_chunks
     ws = ops.paged_attn_workspace(R, max_chunks, hq, hkv, D, "cuda")
-    out = None
-    for _ in range(2):  # second run checks that the arrival counters were restored
-        out = ops.paged_attn(q.cuda(), kv_map, layer * n_pages, plan, R, hkv, page_size, chunk, ws)
-    torch.cuda.synchronize()
-    got, reff = out.float().cpu(), ref.float()
-    err = (got - reff).abs()
+    reff = ref.float()
     scale = reff.abs().mean().item()
-    rel_l2 = (err.pow(2).sum() / reff.pow(2).sum()).sqrt().item()
-    assert rel_l2 < 8e-3, f"rel l2 {rel_l2}"
-    assert err.max().item() < 0.04 * max(scale, 1e-3) * 10, f"max err {err.max().item()} scale {scale}"
+    rel_l2 = None
+    # the tile list is cut into `grid` equal ranges: 1 = everything in one CTA, small primes = items split across
+    # CTAs at arbitrary points, None = the production grid (2 CTAs per SM, mostly one tile or less per CTA here)
+    for grid in (None, 1, 7, 61):
+        out = None
+        for _ in range(2):  # second run checks that the arrival counters were restored
+            out = ops.paged_attn(q.cuda(), kv_map, layer * n_pages, plan, R, hkv, page_size, chunk, ws, grid_ctas=grid)
+        torch.cuda.synchronize()
+        got = out.float().cpu()
+        err = (got - reff).abs()
+        rel = (err.pow(2).sum() / reff.pow(2).sum()).sqrt().item()
+        assert rel < 8e-3, f"grid {grid}: rel l2 {rel}"
+        assert err.max().item() < 0.04 * max(scale, 1e-3) * 10, f"grid {grid}: max err {err.max().item()} scale {scale}"
+        rel_l2 = rel if rel_l2 is None else rel_l2
     return rel_l2
 
 

@@ -16,13 +16,14 @@ P = c_void_p
 SIGNATURES = {
     "vb_last_error": (C.c_char_p, []),
     "vb_version": (c_int, []),
+    "vb_set_pdl": (c_int, [c_int]),
     "vb_device_info": (c_int, [P, P]),
     "vb_tensor_map_kv": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int]),
     "vb_tensor_map_2d_bf16": (c_int, [P, P, c_int64, c_int64, c_int64, c_int]),
     "vb_rmsnorm": (c_int, [P, P, P, c_int, c_int, c_float, P]),
     "vb_rope_freqs": (c_int, [P, c_int, c_int, c_float, c_float, c_int, c_float, c_float, c_float, P]),
     "vb_rope": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
-    "vb_plan_rows": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_int, P]),
+    "vb_plan_rows": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P]),
     "vb_decode_advance": (c_int, [P, P, P, c_int, P]),
     "vb_token_feedback": (c_int, [P, P, P, P, P, c_int, c_int, P]),
     "vb_gather_i32": (c_int, [P, P, P, c_int, P]),
@@ -30,9 +31,10 @@ SIGNATURES = {
     "vb_latest_window": (c_int, [P, P, P, c_int, c_int, P]),
     "vb_gather_windows": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
     "vb_kv_append": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    "vb_attn_tile_tokens": (c_int, [c_int, c_int]),
     "vb_paged_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
-    "vb_paged_attn": (c_int, [P, P, P, c_int64, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                              c_float, P, c_size_t, c_int, P]),
+    "vb_paged_attn": (c_int, [P, P, P, c_int64, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int,
+                              c_float, P, c_size_t, c_int, c_int, P]),
     "vb_gemm_t_tile": (c_int, [c_int]),
     "vb_gemm_bf16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_reduce_residual_rmsnorm": (c_int, [P, P, P, c_int, P, P, c_int, c_int, c_float, P]),
@@ -93,7 +95,7 @@ def check(rc: int, what: str = ""):
 
 
 # kernels (+ memset nodes) each entry point enqueues; everything not listed launches exactly one
-LAUNCHES = {"vb_tensor_map_kv": 0, "vb_tensor_map_2d_bf16": 0, "vb_device_info": 0, "vb_sample": 3,
+LAUNCHES = {"vb_set_pdl": 0, "vb_tensor_map_kv": 0, "vb_tensor_map_2d_bf16": 0, "vb_device_info": 0, "vb_sample": 3,
             "vb_update_repetition_cache": 1}
 launch_counter = [0]
 

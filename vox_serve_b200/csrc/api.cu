@@ -1,6 +1,7 @@
 // Error plumbing, device queries and host-side TMA descriptor encoding for libvoxb200.so.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include <cudaTypedefs.h>
@@ -15,6 +16,15 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+static int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("VB_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
 }
 
 // cuTensorMapEncodeTiled comes from the driver; resolve it at run time so the library links without
@@ -36,6 +46,11 @@ extern "C" {
 
 const char* vb_last_error(void) { return vb::g_err; }
 int vb_version(void) { return 100; }
+int vb_set_pdl(int enabled) {
+  const int old = vb::pdl_enabled() ? 1 : 0;
+  vb::g_pdl = enabled ? 1 : 0;
+  return old;
+}
 
 int vb_device_info(int* sm_count, int* max_smem_optin) {
   int dev = 0;
@@ -55,9 +70,12 @@ int vb_tensor_map_kv(void* out_map, const void* d_kv, int64_t n_slabs, int page_
   auto fn = vb::encode_fn();
   VB_CHECK_ARG(fn, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   const cuuint64_t D = head_dim, H = n_kv_heads, P = page_size;
-  cuuint64_t dims[5] = {D, H, P, 2, static_cast<cuuint64_t>(n_slabs)};
-  cuuint64_t strides[4] = {D * 2, H * D * 2, P * H * D * 2, 2 * P * H * D * 2};
-  cuuint32_t box[5] = {64, 1, static_cast<cuuint32_t>(box_tokens), 1, 1};
+  // dimension order (dim, token, head, k|v, page): a box of all heads lands in shared memory as [head][token][64],
+  // i.e. every head's rows are contiguous (what the attention consumers' ldmatrix pattern needs) while the
+  // global footprint of the box is one contiguous run of the page
+  cuuint64_t dims[5] = {D, P, H, 2, static_cast<cuuint64_t>(n_slabs)};
+  cuuint64_t strides[4] = {H * D * 2, D * 2, P * H * D * 2, 2 * P * H * D * 2};
+  cuuint32_t box[5] = {64, static_cast<cuuint32_t>(box_tokens), static_cast<cuuint32_t>(H), 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(reinterpret_cast<CUtensorMap*>(out_map), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
                   const_cast<void*>(d_kv), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

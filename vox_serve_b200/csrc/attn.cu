@@ -2,36 +2,55 @@
 // Replaces FlashInferDecodeWrapper.run / FlashInferPrefillWrapper.run (vox_serve/flashinfer_utils.py:132,
 // 228-230) behind the plan produced by vb_plan_rows.
 //
-// Work item = (query row, chunk of CHUNK tokens of that row's KV, kv head).  A persistent grid walks the
-// item list.  Warp roles per CTA: one PRODUCER warp resolves items (one 32-byte record per (row, chunk),
-// written by the plan kernel) and TMA-loads the chunk's K and V tiles (5-D tensor map over the whole
-// cache, 128B-swizzled [CHUNK x 64-dim] boxes) plus the group's Q rows (bulk copy) into a STAGES-deep
-// shared-memory ring behind full/empty mbarriers; CHUNK/16 CONSUMER warps each own 16 tokens:
-// S = Q K^T and O = P V run on mma.sync m16n8k16 with the G grouped query heads as the 16-row operand
-// (the tile is read once for the whole GQA group), softmax max/sum use quad shuffles, fp32 throughout,
-// P rounded to bf16 for the PV product.  Rows spanning several chunks leave (m, l, O) partials; the last
-// CTA to finish a (row, head) merges them in chunk order (deterministic) and restores the counter to 0.
+// HBM-bound by design (decode reads every K/V byte once, ~6 flop per byte).  Structure:
+//  * a TILE is TOK consecutive tokens of one query row's KV with ALL kv heads: one contiguous
+//    TOK * n_kv * D * 2-byte run of the page for K and one for V (64 KiB together for Orpheus), so HBM sees
+//    long sequential bursts; tiles are linearised (row, tile) and cut into gridDim.x equal contiguous ranges
+//    ("stream-K" over KV): every CTA streams the same number of tiles whatever the mix of sequence lengths;
+//  * one PRODUCER warp per CTA walks its range -- 32 tiles of metadata resolved at a time, one lane each, from
+//    shared-memory copies of the plan -- and feeds a STAGES-deep ring behind full/empty mbarriers with the
+//    TMA unit's LINEAR bulk copies (cp.async.bulk.shared.global): one copy per token row (n_kv * D * 2 bytes,
+//    all heads), the 2 * TOK copies of a tile issued by the warp's lanes in parallel.  Rows land with a 16-byte
+//    skew (row stride n_kv * D * 2 + 16) so that the consumers' ldmatrix reads of 8 consecutive tokens are
+//    bank-conflict free without a swizzle.  (A tiled tensor-map box must keep a 128-byte inner extent under the
+//    128B swizzle; measured, the TMA unit then spends ~19 cycles per 128-byte row and caps the kernel below
+//    2 TB/s -- 2 KiB linear rows are 16x fewer requests.)  The row's Q (all heads) is bulk-copied into a double
+//    buffer at each segment start;
+//  * consumer warp w owns kv head (w % n_kv) and 16-token slab (w / n_kv) of every tile and keeps PRIVATE
+//    online-softmax state across tiles.  Tokens are the MMA M dimension: S^T = K Q^T (mma.sync m16n8k16, the G
+//    grouped query heads are the N columns), P^T is transposed in registers with movmatrix, O^T += V^T P^T;
+//    exp2 via ex2.approx, P rounded to bf16 and the denominator summed from the rounded P (FlashInfer FA2
+//    numerics).  No block-wide synchronisation per tile -- only at the end of a segment;
+//  * a row that spans several CTAs leaves one partial per CTA; the last CTA to arrive (one atomic per segment)
+//    merges them in CTA order (deterministic) and restores the arrival counter to 0.
 #include "../../include/vb_api.h"
 #include "common.cuh"
 
 namespace vb {
+
+constexpr int ATTN_MAX_STAGES = 4;
+constexpr int ATTN_QBUF = 2;
 
 struct AttnParams {
   __nv_bfloat16* out;
   const __nv_bfloat16* q;
   const int32_t* row_kvlen;
   const int32_t* row_chunk_start;
-  const int4* rc_meta;  // 2 x int4 per (row, chunk)
-  int32_t* counters;    // [n_rows * n_kv]
-  float* part_ml;       // [chunks][n_kv][G][2]
-  float* part_o;        // [chunks][n_kv][G][D]
+  const int32_t* row_pagebase;   // first entry of the row's request in kv_indices
+  const int32_t* row_old;        // tokens of the row's request that were in the cache before this step
+  const int32_t* kv_indices;
+  const __nv_bfloat16* kv;       // whole cache [slabs][2][page_size][n_kv][D]
+  int32_t* counters;             // [n_rows][n_kv]
+  float* part_ml;                // [grid * 2][n_q][2]
+  float* part_o;                 // [grid * 2][n_q][D]
   int slab_base;
-  int n_rows, n_q, n_kv, G, page_size, max_chunks;
+  int n_rows, n_q, n_kv, G, page_size, tok, stages;
   float scale_log2;
 };
 
-struct ItemMeta {
-  int row, token0, page, kvlen, n_chunks, first_rc, rc, h;
+struct TileMeta {   // 32 bytes, one per ring stage
+  int row, token0, kvlen, flags;   // flags: 1 = segment start, 2 = segment end, 4 = segment covers the whole row
+  int slot, cta_a, n_parts, qslot;
 };
 
 __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -40,222 +59,315 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
                "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
 
-template <int D, int CHUNK, int STAGES>
-struct AttnSmem {
-  static constexpr int NW = CHUNK / 16;              // consumer warps
-  static constexpr int TILE = CHUNK * D * 2;         // bytes of one K (or V) tile
-  static constexpr int QROW = D * 2 + 16;            // padded Q row (bank-conflict-free fragment loads)
-  static constexpr int QBYTES = 16 * QROW;           // up to 16 grouped heads
-  static constexpr int STAGE = (2 * TILE + QBYTES + 1023) / 1024 * 1024;
-  static constexpr int OFF_META = STAGES * STAGE;    // ItemMeta[STAGES]
-  static constexpr int OFF_BAR = OFF_META + STAGES * 32;      // full[STAGES], empty[STAGES]
-  static constexpr int OFF_WRED = OFF_BAR + 2 * STAGES * 8;   // float[2][NW][16]
-  static constexpr int OFF_FLAG = OFF_WRED + 2 * NW * 16 * 4;
-  static constexpr int OFF_ORED = (OFF_FLAG + 16 + 127) / 128 * 128;  // float[NW][G][D]
-  static int bytes(int G) { return OFF_ORED + NW * G * D * 4 + 1024 /*alignment slack*/; }
+// shared-memory carve-up (host and device agree through this one function)
+struct AttnLayout {
+  int stage_bytes, off_q, off_meta, off_bar, off_wml, off_flag, off_ored, off_plan, total;
+  __host__ __device__ AttnLayout(int D, int tok, int n_kv, int n_q, int G, int stages, int n_rows) {
+    stage_bytes = 2 * tok * (n_kv * D * 2 + 16);                // K rows then V rows, each skewed by 16 bytes
+    off_q = stages * stage_bytes;
+    off_meta = off_q + ATTN_QBUF * n_q * D * 2;
+    off_bar = off_meta + ATTN_MAX_STAGES * 32;                  // full[4], empty[4], qfull[2], qempty[2]
+    off_wml = off_bar + (2 * ATTN_MAX_STAGES + 2 * ATTN_QBUF) * 8;   // float[n_warps][16][2]
+    const int n_warps = n_kv * (tok / 16);
+    off_flag = off_wml + n_warps * 16 * 2 * 4;
+    off_ored = (off_flag + 16 + 127) / 128 * 128;               // float[n_warps][G][D]
+    off_plan = off_ored + n_warps * G * D * 4;                  // int[4][n_rows + 1]
+    total = off_plan + 4 * (n_rows + 1) * 4 + 128;              // + alignment slack
+  }
 };
 
-template <int D, int CHUNK, int STAGES, bool HI>
-__global__ void __launch_bounds__(CHUNK * 2 + 32) paged_attn_kernel(const AttnParams p,
-                                                                    const __grid_constant__ CUtensorMap kv_map) {
-  using L = AttnSmem<D, CHUNK, STAGES>;
-  constexpr int NW = L::NW;
-  constexpr int NC = NW * 32;           // consumer threads
-  constexpr int NH = D / 64;            // 64-dim half tiles per row
-  constexpr int HALF = CHUNK * 128;     // bytes of one half tile
+template <int D, bool HI>
+__global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) {
+  constexpr int KS = D / 16;            // k-steps of K Q^T
+  constexpr int MT = D / 16;            // m-tiles of V^T P^T
+  constexpr int NT = HI ? 2 : 1;        // 8-head column tiles of the GQA group
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  ItemMeta* meta = reinterpret_cast<ItemMeta*>(smem + L::OFF_META);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
-  uint64_t* empty = full + STAGES;
-  float* wmax = reinterpret_cast<float*>(smem + L::OFF_WRED);
-  float* wsum = wmax + NW * 16;
-  int* flag = reinterpret_cast<int*>(smem + L::OFF_FLAG);
-  float* ored = reinterpret_cast<float*>(smem + L::OFF_ORED);
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  const int G = p.G, TOK = p.tok, STAGES = p.stages;
+  const AttnLayout L(D, TOK, p.n_kv, p.n_q, G, STAGES, p.n_rows);
+  const int NW = p.n_kv * (TOK / 16);   // consumer warps
+  const int NC = NW * 32;
+  const int ROWB = p.n_kv * D * 2;      // bytes of one token row (all heads) in the cache
+  const int RS = ROWB + 16;             // its stride in shared memory (16-byte skew)
+  const int KVT = TOK * RS;             // bytes of a K (or V) tile in shared memory
+  TileMeta* meta = reinterpret_cast<TileMeta*>(smem + L.off_meta);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+  uint64_t* empty = full + ATTN_MAX_STAGES;
+  uint64_t* qfull = empty + ATTN_MAX_STAGES;
+  uint64_t* qempty = qfull + ATTN_QBUF;
+  float* wml = reinterpret_cast<float*>(smem + L.off_wml);
+  int* flag = reinterpret_cast<int*>(smem + L.off_flag);
+  float* ored = reinterpret_cast<float*>(smem + L.off_ored);
+  int* s_cstart = reinterpret_cast<int*>(smem + L.off_plan);   // [n_rows + 1]
+  int* s_kvlen = s_cstart + p.n_rows + 1;                      // [n_rows]
+  int* s_pbase = s_kvlen + p.n_rows + 1;                       // [n_rows]
+  int* s_old = s_pbase + p.n_rows + 1;                         // [n_rows]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int G = p.G;
-  const int n_rc = p.row_chunk_start[p.n_rows];
-  if (n_rc > p.max_chunks) __trap();   // plan overflowed the workspace the caller sized
-  const int n_items = n_rc * p.n_kv;
 
   if (tid == 0) {
-    prefetch_tmap(&kv_map);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], NW);
     }
+    for (int s = 0; s < ATTN_QBUF; ++s) {
+      mbar_init(&qfull[s], 1);
+      mbar_init(&qempty[s], NW);
+    }
     fence_barrier_init();
   }
+  for (int i = tid; i <= p.n_rows; i += blockDim.x) {
+    s_cstart[i] = p.row_chunk_start[i];
+    if (i < p.n_rows) {
+      s_kvlen[i] = p.row_kvlen[i];
+      s_pbase[i] = p.row_pagebase[i];
+      s_old[i] = p.row_old[i];
+    }
+  }
   __syncthreads();
+  const int total = s_cstart[p.n_rows];
+  const int per = (total + gridDim.x - 1) / gridDim.x;
+  const int c0 = min(total, static_cast<int>(blockIdx.x) * per);
+  const int c1 = min(total, c0 + per);
 
   if (warp == NW) {
-    // ===================== producer warp =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t ph = 0;
-      int item = blockIdx.x;
-      int4 a = make_int4(0, 0, 0, 0), b = a;
-      if (item < n_items) {
-        const int rc = item / p.n_kv;
-        a = __ldg(&p.rc_meta[rc * 2]);
-        b = __ldg(&p.rc_meta[rc * 2 + 1]);
+    // ===================== producer warp (stays converged; lane 0 issues) =====================
+    // PDL: the plan (>= 2 kernels upstream) and the KV of earlier steps are final when this kernel starts, so
+    // tiles that hold only old tokens are requested before the grid dependency resolves; the first tile that
+    // needs the predecessor's output (the new tokens' K/V, or any Q) waits for it.
+    int stage = 0, nseg = 0;
+    uint32_t ph = 0;
+    bool dep_ok = false;
+    int issued = 0, n_pend = 0, pend_row0 = 0, pend_row1 = 0;
+    auto issue_q = [&](int row, int seg) {
+      const int qs = seg & 1;
+      mbar_wait(&qempty[qs], ((seg >> 1) & 1) ^ 1);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&qfull[qs], p.n_q * D * 2);
+        bulk_copy_g2s(smem + L.off_q + qs * p.n_q * D * 2, p.q + static_cast<size_t>(row) * p.n_q * D, p.n_q * D * 2,
+                      &qfull[qs]);
       }
-      while (item < n_items) {
-        const int rc = item / p.n_kv, h = item - rc * p.n_kv;
-        const int nxt = item + gridDim.x;
-        int4 na = a, nb = b;
-        if (nxt < n_items) {   // prefetch the next record while this item's loads are issued
-          const int nrc = nxt / p.n_kv;
-          na = __ldg(&p.rc_meta[nrc * 2]);
-          nb = __ldg(&p.rc_meta[nrc * 2 + 1]);
+      __syncwarp();
+    };
+    for (int base = c0; base < c1; base += 32) {
+      // ---- each lane resolves one tile of the next 32 ----
+      const int Lx = base + lane;
+      int m_row = 0, m_tok = 0, m_kvlen = 0, m_flags = 0, m_slot = 0, m_ctaa = 0, m_parts = 1, m_page = 0, m_old = 0;
+      if (Lx < c1) {
+        int lo = 0, hi = p.n_rows;      // largest row with cstart[row] <= Lx (rows with no tiles are skipped)
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (s_cstart[mid] <= Lx) lo = mid; else hi = mid;
         }
+        const int row = lo, Ls = s_cstart[row], Le = s_cstart[row + 1];
+        const int seg0 = max(Ls, c0), seg1 = min(Le, c1);
+        m_row = row; m_tok = (Lx - Ls) * TOK; m_kvlen = s_kvlen[row]; m_old = s_old[row];
+        m_flags = (Lx == seg0 ? 1 : 0) | (Lx == seg1 - 1 ? 2 : 0) | ((Ls >= c0 && Le <= c1) ? 4 : 0);
+        m_slot = (Ls > c0) ? 1 : 0;
+        m_ctaa = Ls / per;
+        m_parts = (Le - 1) / per - m_ctaa + 1;
+        m_page = __ldg(&p.kv_indices[s_pbase[row] + m_tok / p.page_size]);
+      }
+      const int n_here = min(32, c1 - base);
+      for (int k = 0; k < n_here; ++k) {
+        TileMeta m;
+        m.row = __shfl_sync(0xffffffffu, m_row, k);
+        m.token0 = __shfl_sync(0xffffffffu, m_tok, k);
+        m.kvlen = __shfl_sync(0xffffffffu, m_kvlen, k);
+        m.flags = __shfl_sync(0xffffffffu, m_flags, k);
+        m.slot = __shfl_sync(0xffffffffu, m_slot, k);
+        m.cta_a = __shfl_sync(0xffffffffu, m_ctaa, k);
+        m.n_parts = __shfl_sync(0xffffffffu, m_parts, k);
+        const int page = __shfl_sync(0xffffffffu, m_page, k);
+        const int old = __shfl_sync(0xffffffffu, m_old, k);
+        const bool seg_start = (m.flags & 1) != 0;
+        if (!dep_ok && (m.token0 + TOK > old || issued >= STAGES || (seg_start && n_pend >= ATTN_QBUF))) {
+          pdl_wait();
+          pdl_trigger();
+          dep_ok = true;
+          for (int i = 0; i < n_pend; ++i) issue_q(i == 0 ? pend_row0 : pend_row1, i);
+          n_pend = 0;
+        }
+        if (seg_start) {
+          // the row's Q (all heads) goes into the double buffer; its slot was freed two segments ago
+          m.qslot = nseg;
+          if (dep_ok) {
+            issue_q(m.row, nseg);
+          } else {
+            if (n_pend == 0) pend_row0 = m.row; else pend_row1 = m.row;
+            ++n_pend;
+          }
+          ++nseg;
+        } else {
+          m.qslot = nseg - 1;
+        }
+        ++issued;
         mbar_wait(&empty[stage], ph ^ 1);
-        ItemMeta m;
-        m.row = a.x; m.token0 = a.y; m.page = a.z; m.kvlen = a.w;
-        m.n_chunks = b.x; m.first_rc = b.y; m.rc = rc; m.h = h;
-        meta[stage] = m;
-        uint8_t* dst = smem + stage * L::STAGE;
-        mbar_arrive_expect_tx(&full[stage], 2 * L::TILE + G * D * 2);
-        const int slot0 = m.token0 % p.page_size;
-#pragma unroll
-        for (int kv = 0; kv < 2; ++kv)
-#pragma unroll
-          for (int hh = 0; hh < NH; ++hh)
-            tma_load_5d(dst + kv * L::TILE + hh * HALF, &kv_map, &full[stage], hh * 64, h, slot0, kv,
-                        p.slab_base + m.page);
-        const __nv_bfloat16* qrow = p.q + (static_cast<size_t>(m.row) * p.n_q + h * G) * D;
-        for (int g = 0; g < G; ++g)
-          bulk_copy_g2s(dst + 2 * L::TILE + g * L::QROW, qrow + g * D, D * 2, &full[stage]);
-        a = na; b = nb;
-        item = nxt;
+        if (lane == 0) {
+          meta[stage] = m;
+          mbar_arrive_expect_tx(&full[stage], 2 * TOK * ROWB);
+        }
+        __syncwarp();
+        {
+          // 2 * TOK row copies (K rows then V rows), spread over the lanes
+          uint8_t* dst = smem + stage * L.stage_bytes;
+          const int slot0 = m.token0 % p.page_size;
+          const size_t page_elems = static_cast<size_t>(p.page_size) * p.n_kv * D;
+          const __nv_bfloat16* src0 = p.kv + static_cast<size_t>(p.slab_base + page) * 2 * page_elems +
+                                      static_cast<size_t>(slot0) * p.n_kv * D;
+          for (int c = lane; c < 2 * TOK; c += 32) {
+            const int kvsel = c >= TOK ? 1 : 0, t = c - kvsel * TOK;
+            bulk_copy_g2s(dst + kvsel * KVT + t * RS, src0 + kvsel * page_elems + static_cast<size_t>(t) * p.n_kv * D,
+                          ROWB, &full[stage]);
+          }
+        }
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; ph ^= 1; }
       }
     }
+    if (!dep_ok) {
+      pdl_wait();
+      pdl_trigger();
+      for (int i = 0; i < n_pend; ++i) issue_q(i == 0 ? pend_row0 : pend_row1, i);
+    }
     return;
   }
+  if (warp > NW) return;
 
   // ===================== consumer warps =====================
   // padded / empty rows produce zeros
   for (int row = blockIdx.x; row < p.n_rows; row += gridDim.x) {
-    if (p.row_kvlen[row] == 0) {
+    if (s_kvlen[row] == 0) {
       uint32_t* o = reinterpret_cast<uint32_t*>(p.out + static_cast<size_t>(row) * p.n_q * D);
       for (int i = tid; i < p.n_q * D / 2; i += NC) o[i] = 0u;
     }
   }
-  auto csync = []() { asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory"); };
+  auto csync = [NC]() { asm volatile("bar.sync 1, %0;" ::"r"(NC) : "memory"); };
 
-  const int r0 = lane >> 2;        // head row of c[0], c[1]; r0 + 8 for c[2], c[3]
-  const int cq = (lane & 3) * 2;   // column pair inside an 8-wide n-tile
-  const bool v0 = r0 < G, v1 = HI && (r0 + 8 < G);
+  const int g = lane >> 2;         // C-fragment row (token g, g + 8) / B-fragment column (head g)
+  const int qd = lane & 3;         // C-fragment column pair (heads 2qd, 2qd + 1)
+  const int head = warp % p.n_kv;  // kv head of this warp
+  const int slab = warp / p.n_kv;  // 16-token slab of the tile
+  const int hoff = head * D * 2;   // byte offset of this warp's head inside a token row
+  const int mi = lane >> 3, r8 = lane & 7;
+
+  uint32_t qb[NT][KS][2];
+  float O[MT][NT][4];
+  float mrun[NT][2], lrun[NT][2];   // per head column (2qd, 2qd+1); l: this lane's share until the segment end
 
   int stage = 0;
   uint32_t ph = 0;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  for (int Lx = c0; Lx < c1; ++Lx) {
     mbar_wait(&full[stage], ph);
-    const ItemMeta m = meta[stage];
-    const uint32_t kbase = smem_u32(smem + stage * L::STAGE);
-    const uint32_t vbase = kbase + L::TILE;
-    const uint8_t* qs = smem + stage * L::STAGE + 2 * L::TILE;
-    const int tokw = warp * 16;
+    const TileMeta m = meta[stage];
+    const uint32_t kbase = smem_u32(smem + stage * L.stage_bytes);
+    const uint32_t vbase = kbase + KVT;
 
-    // ---- S = Q K^T : 16 heads x 16 tokens per warp ----
-    float S[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    {
-      const int mi = lane >> 3, r = lane & 7;
-      const int tok = tokw + (mi >> 1) * 8 + r;
+    if (m.flags & 1) {
+      // ---- new segment: reset the running state, pull this head group's Q fragments into registers ----
+      const int qs = m.qslot & 1;
+      mbar_wait(&qfull[qs], (m.qslot >> 1) & 1);
+      const uint8_t* qsm = smem + L.off_q + qs * p.n_q * D * 2 + head * G * D * 2;
 #pragma unroll
-      for (int ks = 0; ks < D / 16; ++ks) {
-        uint32_t qa[4];
-        const int d0 = (ks * 16 + cq) * 2;
-        qa[0] = v0 ? *reinterpret_cast<const uint32_t*>(qs + r0 * L::QROW + d0) : 0u;
-        qa[1] = v1 ? *reinterpret_cast<const uint32_t*>(qs + (r0 + 8) * L::QROW + d0) : 0u;
-        qa[2] = v0 ? *reinterpret_cast<const uint32_t*>(qs + r0 * L::QROW + d0 + 16) : 0u;
-        qa[3] = v1 ? *reinterpret_cast<const uint32_t*>(qs + (r0 + 8) * L::QROW + d0 + 16) : 0u;
-        const int c16 = ks * 2 + (mi & 1);
-        const uint32_t addr = kbase + (c16 >> 3) * HALF + tok * 128 + (((c16 & 7) ^ (tok & 7)) << 4);
-        uint32_t bfr[4];
-        ldmatrix_x4(bfr, addr);
-        mma_bf16_16816(S[0], qa, bfr[0], bfr[1]);
-        mma_bf16_16816(S[1], qa, bfr[2], bfr[3]);
-      }
-    }
-    // ---- mask + row max ----
-    float mx0 = -INFINITY, mx1 = -INFINITY;
+      for (int nt = 0; nt < NT; ++nt) {
+        const int hq = nt * 8 + g;       // B fragment: column n = head within the group
+        const bool ok = hq < G;
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int tok = m.token0 + tokw + nt * 8 + cq + (j & 1);
-        const float s = (tok < m.kvlen) ? S[nt][j] * p.scale_log2 : -INFINITY;
-        S[nt][j] = s;
-        if (j < 2) mx0 = fmaxf(mx0, s); else mx1 = fmaxf(mx1, s);
-      }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    if (HI) {
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    }
-    if ((lane & 3) == 0) {
-      wmax[warp * 16 + r0] = mx0;
-      wmax[warp * 16 + r0 + 8] = mx1;
-    }
-    csync();
-    float M0 = -INFINITY, M1 = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      M0 = fmaxf(M0, wmax[w * 16 + r0]);
-      if (HI) M1 = fmaxf(M1, wmax[w * 16 + r0 + 8]);
-    }
-    if (!HI || M1 == -INFINITY) M1 = 0.f;   // unused head rows
-    if (M0 == -INFINITY) M0 = 0.f;
-    // ---- P = exp2(S - M), rounded to bf16; row sums of the rounded values ----
-    uint32_t pa[4];
-    float l0 = 0.f, l1 = 0.f;
-    {
-      float e[2][4];
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float v = round_bf16(exp2f(S[nt][j] - (j < 2 ? M0 : M1)));
-          e[nt][j] = v;
-          if (j < 2) l0 += v; else l1 += v;
+        for (int ks = 0; ks < KS; ++ks) {
+          const int d0 = (ks * 16 + qd * 2) * 2;
+          qb[nt][ks][0] = ok ? *reinterpret_cast<const uint32_t*>(qsm + hq * (D * 2) + d0) : 0u;
+          qb[nt][ks][1] = ok ? *reinterpret_cast<const uint32_t*>(qsm + hq * (D * 2) + d0 + 16) : 0u;
         }
-      pa[0] = pack_bf16(e[0][0], e[0][1]);
-      pa[1] = pack_bf16(e[0][2], e[0][3]);
-      pa[2] = pack_bf16(e[1][0], e[1][1]);
-      pa[3] = pack_bf16(e[1][2], e[1][3]);
-    }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    if (HI) {
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    }
-    if ((lane & 3) == 0) {
-      wsum[warp * 16 + r0] = l0;
-      wsum[warp * 16 + r0 + 8] = l1;
-    }
-    // ---- O = P V : 16 heads x D dims over this warp's 16 tokens ----
-    float O[D / 8][4];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&qempty[qs]);
 #pragma unroll
-    for (int nt = 0; nt < D / 8; ++nt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) O[nt][j] = 0.f;
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) O[mt][nt][j] = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        mrun[nt][0] = mrun[nt][1] = -INFINITY;
+        lrun[nt][0] = lrun[nt][1] = 0.f;
+      }
+    }
+
+    // ---- S^T = K Q^T : this warp's 16 tokens x the group's heads ----
+    float S[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) S[nt][0] = S[nt][1] = S[nt][2] = S[nt][3] = 0.f;
     {
-      const int mi = lane >> 3, r = lane & 7;
-      const int tok = tokw + (mi & 1) * 8 + r;
+      const int trow = slab * 16 + r8 + (mi & 1) * 8;
+      const uint32_t rbase = kbase + trow * RS + hoff + (mi >> 1) * 16;
 #pragma unroll
-      for (int dn = 0; dn < D / 16; ++dn) {
-        const int c16 = dn * 2 + (mi >> 1);
-        const uint32_t addr = vbase + (c16 >> 3) * HALF + tok * 128 + (((c16 & 7) ^ (tok & 7)) << 4);
-        uint32_t bfr[4];
-        ldmatrix_x4_trans(bfr, addr);
-        mma_bf16_16816(O[2 * dn], pa, bfr[0], bfr[1]);
-        mma_bf16_16816(O[2 * dn + 1], pa, bfr[2], bfr[3]);
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t a[4];
+        ldmatrix_x4(a, rbase + ks * 32);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_bf16_16816(S[nt], a, qb[nt][ks][0], qb[nt][ks][1]);
+      }
+    }
+    // ---- mask, running max, P = exp2(S - m) rounded to bf16, sums of the rounded values ----
+    const int tok_lo = m.token0 + slab * 16 + g;
+    const bool in_lo = tok_lo < m.kvlen, in_hi = tok_lo + 8 < m.kvlen;
+    uint32_t pb[NT][2];
+    float alpha[NT][2];
+    bool rescale = false;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      float s0 = in_lo ? S[nt][0] * p.scale_log2 : -INFINITY, s1 = in_lo ? S[nt][1] * p.scale_log2 : -INFINITY;
+      float s2 = in_hi ? S[nt][2] * p.scale_log2 : -INFINITY, s3 = in_hi ? S[nt][3] * p.scale_log2 : -INFINITY;
+      float mx0 = fmaxf(s0, s2), mx1 = fmaxf(s1, s3);
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
+      }
+      const float n0 = fmaxf(mrun[nt][0], mx0), n1 = fmaxf(mrun[nt][1], mx1);
+      const float u0 = (n0 == -INFINITY) ? 0.f : n0, u1 = (n1 == -INFINITY) ? 0.f : n1;   // all masked so far
+      alpha[nt][0] = ex2_approx(mrun[nt][0] - u0);                                         // ex2(-inf) = 0
+      alpha[nt][1] = ex2_approx(mrun[nt][1] - u1);
+      rescale |= (n0 != mrun[nt][0]) | (n1 != mrun[nt][1]);
+      mrun[nt][0] = n0; mrun[nt][1] = n1;
+      const float p0 = round_bf16(ex2_approx(s0 - u0)), p1 = round_bf16(ex2_approx(s1 - u1));
+      const float p2 = round_bf16(ex2_approx(s2 - u0)), p3 = round_bf16(ex2_approx(s3 - u1));
+      lrun[nt][0] = lrun[nt][0] * alpha[nt][0] + (p0 + p2);
+      lrun[nt][1] = lrun[nt][1] * alpha[nt][1] + (p1 + p3);
+      // C layout (token g | g+8, heads 2qd, 2qd+1) -> B layout (tokens 2qd, 2qd+1 | +8, head g)
+      pb[nt][0] = movmatrix_trans(pack_bf16(p0, p1));
+      pb[nt][1] = movmatrix_trans(pack_bf16(p2, p3));
+    }
+    rescale = __any_sync(0xffffffffu, rescale);
+    // ---- O^T = O^T * alpha + V^T P^T ----
+    {
+      const int trow = slab * 16 + r8 + (mi >> 1) * 8;
+      const uint32_t rbase = vbase + trow * RS + hoff + (mi & 1) * 16;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        uint32_t a[4];
+        ldmatrix_x4_trans(a, rbase + mt * 32);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          float(&o)[4] = O[mt][nt];
+          if (rescale) {
+            o[0] *= alpha[nt][0]; o[1] *= alpha[nt][1];
+            o[2] *= alpha[nt][0]; o[3] *= alpha[nt][1];
+          }
+          mma_bf16_16816(o, a, pb[nt][0], pb[nt][1]);
+        }
       }
     }
     // this warp is done with the stage's tiles: hand the slot back to the producer
@@ -263,80 +375,217 @@ __global__ void __launch_bounds__(CHUNK * 2 + 32) paged_attn_kernel(const AttnPa
     if (lane == 0) mbar_arrive(&empty[stage]);
     if (++stage == STAGES) { stage = 0; ph ^= 1; }
 
-    // ---- cross-warp reduction of O through shared memory ----
-#pragma unroll
-    for (int nt = 0; nt < D / 8; ++nt) {
-      const int d = nt * 8 + cq;
-      if (v0) *reinterpret_cast<float2*>(&ored[(warp * G + r0) * D + d]) = make_float2(O[nt][0], O[nt][1]);
-      if (v1) *reinterpret_cast<float2*>(&ored[(warp * G + r0 + 8) * D + d]) = make_float2(O[nt][2], O[nt][3]);
-    }
-    csync();
+    if (!(m.flags & 2)) continue;
 
-    const bool single = (m.n_chunks == 1);
-    const size_t pbase = static_cast<size_t>(m.rc) * p.n_kv + m.h;
-    for (int i = tid; i < G * D; i += NC) {
-      const int g = i / D;
-      float o = 0.f, l = 0.f;
+    // ================= end of segment =================
 #pragma unroll
-      for (int w = 0; w < NW; ++w) {
-        o += ored[w * G * D + i];
-        l += wsum[w * 16 + g];
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        lrun[nt][0] += __shfl_xor_sync(0xffffffffu, lrun[nt][0], o);
+        lrun[nt][1] += __shfl_xor_sync(0xffffffffu, lrun[nt][1], o);
       }
-      if (single) {
-        p.out[(static_cast<size_t>(m.row) * p.n_q + m.h * G) * D + i] = __float2bfloat16_rn(o / l);
-      } else {
-        p.part_o[pbase * G * D + i] = o;
-        if (i - g * D == 0) {
-          float mm = -INFINITY;
+    if (TOK == 16) {
+      // ---- one slab per tile: this warp owns its kv head outright, no block-level step at all ----
+      const bool complete = (m.flags & 4) != 0;
+      const size_t pslot = static_cast<size_t>(blockIdx.x) * 2 + m.slot;
+      const int hq0 = head * G;
 #pragma unroll
-          for (int w = 0; w < NW; ++w) mm = fmaxf(mm, wmax[w * 16 + g]);
-          p.part_ml[(pbase * G + g) * 2 + 0] = mm;
-          p.part_ml[(pbase * G + g) * 2 + 1] = l;
+      for (int nt = 0; nt < NT; ++nt) {
+        const int h0 = nt * 8 + qd * 2;
+        if (complete) {
+          const float i0 = 1.f / lrun[nt][0], i1 = 1.f / lrun[nt][1];
+          __nv_bfloat16* o0 = p.out + (static_cast<size_t>(m.row) * p.n_q + hq0 + h0) * D;
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const int d = mt * 16 + g;
+            if (h0 < G) {
+              o0[d] = __float2bfloat16_rn(O[mt][nt][0] * i0);
+              o0[d + 8] = __float2bfloat16_rn(O[mt][nt][2] * i0);
+            }
+            if (h0 + 1 < G) {
+              o0[D + d] = __float2bfloat16_rn(O[mt][nt][1] * i1);
+              o0[D + d + 8] = __float2bfloat16_rn(O[mt][nt][3] * i1);
+            }
+          }
+        } else {
+          float* o0 = p.part_o + (pslot * p.n_q + hq0 + h0) * D;
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const int d = mt * 16 + g;
+            if (h0 < G) { o0[d] = O[mt][nt][0]; o0[d + 8] = O[mt][nt][2]; }
+            if (h0 + 1 < G) { o0[D + d] = O[mt][nt][1]; o0[D + d + 8] = O[mt][nt][3]; }
+          }
+          if (g == 0) {
+            float* ml = p.part_ml + (pslot * p.n_q + hq0 + h0) * 2;
+            if (h0 < G) { ml[0] = mrun[nt][0]; ml[1] = lrun[nt][0]; }
+            if (h0 + 1 < G) { ml[2] = mrun[nt][1]; ml[3] = lrun[nt][1]; }
+          }
+        }
+      }
+      if (!complete) {
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+          __threadfence();           // orders the whole warp's partial (fences are cumulative) before the arrival
+          const int old = atomicAdd(&p.counters[m.row * p.n_kv + head], 1);
+          last = (old == m.n_parts - 1);
+          if (last) {
+            p.counters[m.row * p.n_kv + head] = 0;
+            __threadfence();
+          }
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+          // merge this head group's partials in CTA order: slot 1 only if the row starts inside CTA cta_a's range
+          const int Ls = s_cstart[m.row];
+          for (int gg = 0; gg < G; ++gg) {
+            const int hq = hq0 + gg;
+            float Mx = -INFINITY;
+            for (int cb = 0; cb < m.n_parts; cb += 32) {
+              const int c = cb + lane;
+              float mm = -INFINITY;
+              if (c < m.n_parts) {
+                const size_t ps = static_cast<size_t>(m.cta_a + c) * 2 + ((c == 0 && Ls > m.cta_a * per) ? 1 : 0);
+                mm = __ldcg(&p.part_ml[(ps * p.n_q + hq) * 2]);
+              }
+              Mx = fmaxf(Mx, warp_max(mm));
+            }
+            float acc[D / 32];
+#pragma unroll
+            for (int j = 0; j < D / 32; ++j) acc[j] = 0.f;
+            float den = 0.f;
+            for (int cb = 0; cb < m.n_parts; cb += 32) {
+              const int c = cb + lane;
+              float sc = 0.f, ll = 0.f;
+              if (c < m.n_parts) {
+                const size_t ps = static_cast<size_t>(m.cta_a + c) * 2 + ((c == 0 && Ls > m.cta_a * per) ? 1 : 0);
+                const float mm = __ldcg(&p.part_ml[(ps * p.n_q + hq) * 2]);
+                ll = __ldcg(&p.part_ml[(ps * p.n_q + hq) * 2 + 1]);
+                sc = (mm == -INFINITY) ? 0.f : ex2_approx(mm - Mx);
+              }
+              den += warp_sum(sc * ll);
+              const int nc = min(32, m.n_parts - cb);
+#pragma unroll 4
+              for (int k = 0; k < nc; ++k) {
+                const float sk = __shfl_sync(0xffffffffu, sc, k);
+                const size_t ps = static_cast<size_t>(m.cta_a + cb + k) * 2 +
+                                  ((cb + k == 0 && Ls > m.cta_a * per) ? 1 : 0);
+                const float* po = p.part_o + (ps * p.n_q + hq) * D;
+#pragma unroll
+                for (int j = 0; j < D / 32; ++j) acc[j] += sk * __ldcg(&po[j * 32 + lane]);
+              }
+            }
+            const float inv = 1.f / den;
+            __nv_bfloat16* o0 = p.out + (static_cast<size_t>(m.row) * p.n_q + hq) * D;
+#pragma unroll
+            for (int j = 0; j < D / 32; ++j) o0[j * 32 + lane] = __float2bfloat16_rn(acc[j] * inv);
+          }
+        }
+      }
+      continue;
+    }
+
+    // ---- several slabs per tile (n_kv < 8): merge the slabs of each head through shared memory ----
+    // stage (m, l, O) of this warp's head group in shared memory: wml[warp][head 0..15][2], ored[warp][G][D]
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int h0 = nt * 8 + qd * 2;
+      if (g == 0) {
+        wml[(warp * 16 + h0) * 2 + 0] = mrun[nt][0];
+        wml[(warp * 16 + h0) * 2 + 1] = lrun[nt][0];
+        wml[(warp * 16 + h0 + 1) * 2 + 0] = mrun[nt][1];
+        wml[(warp * 16 + h0 + 1) * 2 + 1] = lrun[nt][1];
+      }
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int d = mt * 16 + g;
+        if (h0 < G) {
+          ored[(warp * G + h0) * D + d] = O[mt][nt][0];
+          ored[(warp * G + h0) * D + d + 8] = O[mt][nt][2];
+        }
+        if (h0 + 1 < G) {
+          ored[(warp * G + h0 + 1) * D + d] = O[mt][nt][1];
+          ored[(warp * G + h0 + 1) * D + d + 8] = O[mt][nt][3];
         }
       }
     }
-    if (!single) {
-      __threadfence();
-      csync();
+    csync();
+
+    const bool complete = (m.flags & 4) != 0;
+    const size_t pslot = static_cast<size_t>(blockIdx.x) * 2 + m.slot;
+    const int slabs = TOK / 16;
+    for (int i = tid; i < p.n_q * D; i += NC) {
+      const int hq = i / D, d = i - hq * D;
+      const int hk = hq / G, gg = hq - hk * G;
+      float Mg = -INFINITY;
+      for (int s = 0; s < slabs; ++s) Mg = fmaxf(Mg, wml[((s * p.n_kv + hk) * 16 + gg) * 2]);
+      float o = 0.f, l = 0.f;
+      for (int s = 0; s < slabs; ++s) {
+        const int w = s * p.n_kv + hk;
+        const float mw = wml[(w * 16 + gg) * 2];
+        const float sc = (mw == -INFINITY) ? 0.f : ex2_approx(mw - Mg);
+        o += ored[(w * G + gg) * D + d] * sc;
+        l += wml[(w * 16 + gg) * 2 + 1] * sc;
+      }
+      if (complete) {
+        p.out[static_cast<size_t>(m.row) * p.n_q * D + i] = __float2bfloat16_rn(o / l);
+      } else {
+        p.part_o[pslot * p.n_q * D + i] = o;
+        if (d == 0) {
+          p.part_ml[(pslot * p.n_q + hq) * 2 + 0] = Mg;
+          p.part_ml[(pslot * p.n_q + hq) * 2 + 1] = l;
+        }
+      }
+    }
+    if (!complete) {
+      csync();                       // every partial of this CTA is written ...
       if (tid == 0) {
-        const int old = atomicAdd(&p.counters[m.row * p.n_kv + m.h], 1);
-        const int last = (old == m.n_chunks - 1);
-        if (last) p.counters[m.row * p.n_kv + m.h] = 0;
+        __threadfence();             // ... and ordered before the arrival (fences are cumulative)
+        const int old = atomicAdd(&p.counters[m.row * p.n_kv], 1);
+        const int last = (old == m.n_parts - 1);
+        if (last) {
+          p.counters[m.row * p.n_kv] = 0;
+          __threadfence();
+        }
         *flag = last;
       }
       csync();
       if (*flag) {
-        __threadfence();
-        const size_t first = static_cast<size_t>(m.first_rc) * p.n_kv + m.h;   // chunk 0 of this row
-        const size_t cstride = static_cast<size_t>(p.n_kv);
-        for (int i = tid; i < G * D; i += NC) {
-          const int g = i / D;
+        // partial of CTA c for this row: slot 1 only if the row starts inside CTA cta_a's range
+        const int Ls = s_cstart[m.row];
+        for (int i = tid; i < p.n_q * D; i += NC) {
+          const int hq = i / D;
           float Mx = -INFINITY;
-          for (int c = 0; c < m.n_chunks; ++c)
-            Mx = fmaxf(Mx, __ldcg(&p.part_ml[((first + c * cstride) * G + g) * 2]));
-          float num = 0.f, den = 0.f;
-          for (int c = 0; c < m.n_chunks; ++c) {
-            const size_t pb = first + c * cstride;
-            const float sc = exp2f(__ldcg(&p.part_ml[(pb * G + g) * 2]) - Mx);
-            den += sc * __ldcg(&p.part_ml[(pb * G + g) * 2 + 1]);
-            num += sc * __ldcg(&p.part_o[pb * G * D + i]);
+          for (int c = 0; c < m.n_parts; ++c) {
+            const size_t ps = static_cast<size_t>(m.cta_a + c) * 2 + ((c == 0 && Ls > m.cta_a * per) ? 1 : 0);
+            Mx = fmaxf(Mx, __ldcg(&p.part_ml[(ps * p.n_q + hq) * 2]));
           }
-          p.out[(static_cast<size_t>(m.row) * p.n_q + m.h * G) * D + i] = __float2bfloat16_rn(num / den);
+          float num = 0.f, den = 0.f;
+          for (int c = 0; c < m.n_parts; ++c) {
+            const size_t ps = static_cast<size_t>(m.cta_a + c) * 2 + ((c == 0 && Ls > m.cta_a * per) ? 1 : 0);
+            const float mm = __ldcg(&p.part_ml[(ps * p.n_q + hq) * 2]);
+            const float sc = (mm == -INFINITY) ? 0.f : ex2_approx(mm - Mx);
+            den += sc * __ldcg(&p.part_ml[(ps * p.n_q + hq) * 2 + 1]);
+            num += sc * __ldcg(&p.part_o[ps * p.n_q * D + i]);
+          }
+          p.out[static_cast<size_t>(m.row) * p.n_q * D + i] = __float2bfloat16_rn(num / den);
         }
       }
     }
-    csync();   // wmax / wsum / ored / flag reusable
+    csync();   // wml / ored / flag reusable
   }
 }
 
-template <int D, int CHUNK, int STAGES, bool HI>
-static int launch_attn(const AttnParams& p, const CUtensorMap* map, int grid, cudaStream_t stream) {
-  using L = AttnSmem<D, CHUNK, STAGES>;
-  const int smem = L::bytes(p.G);
-  auto kern = paged_attn_kernel<D, CHUNK, STAGES, HI>;
+template <int D, bool HI>
+static int launch_attn(const AttnParams& p, int grid, cudaStream_t stream) {
+  const AttnLayout L(D, p.tok, p.n_kv, p.n_q, p.G, p.stages, p.n_rows);
+  VB_CHECK_ARG(L.total <= VB_MAX_DYN_SMEM, "vb_paged_attn: %d rows / %d-token tiles need %d bytes of shared memory",
+               p.n_rows, p.tok, L.total);
+  auto kern = paged_attn_kernel<D, HI>;
   VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, VB_MAX_DYN_SMEM));
-  kern<<<grid, CHUNK * 2 + 32, smem, stream>>>(p, *map);
-  VB_CHECK_LAUNCH();
+  const int threads = (p.n_kv * (p.tok / 16) + 1) * 32;
+  VB_LAUNCH_PDL(kern, grid, threads, L.total, stream, p);
   return 0;
 }
 
@@ -346,65 +595,66 @@ using namespace vb;
 
 extern "C" {
 
-size_t vb_paged_attn_workspace_bytes(int max_rows, int max_chunks_total, int n_q, int n_kv, int head_dim) {
-  const size_t G = static_cast<size_t>(n_q / (n_kv > 0 ? n_kv : 1));
-  size_t counters = (static_cast<size_t>(max_rows) * n_kv * sizeof(int32_t) + 255) / 256 * 256;
-  size_t ml = (static_cast<size_t>(max_chunks_total) * n_kv * G * 2 * sizeof(float) + 255) / 256 * 256;
-  size_t po = static_cast<size_t>(max_chunks_total) * n_kv * G * head_dim * sizeof(float);
-  return counters + ml + po;
+int vb_attn_tile_tokens(int page_size, int n_kv) {
+  if (page_size < 16 || page_size % 16 != 0 || n_kv < 1 || n_kv > 8) return -1;
+  int tok = 16 * (8 / n_kv);            // 8 consumer warps: one per (kv head, 16-token slab)
+  while (tok > 16 && (tok > page_size || page_size % tok != 0)) tok -= 16;
+  return tok;
 }
 
-int vb_paged_attn(void* d_out, const void* d_q, const void* kv_map, int64_t slab_base,
-                  const int32_t* d_row_kvlen, const int32_t* d_row_chunk_start, const int32_t* d_rc_meta,
-                  int n_rows, int max_chunks_total, int n_q, int n_kv, int head_dim, int page_size,
+size_t vb_paged_attn_workspace_bytes(int max_rows, int max_grid_ctas, int n_q, int n_kv, int head_dim) {
+  const size_t ml = (static_cast<size_t>(max_grid_ctas) * 2 * n_q * 2 * sizeof(float) + 255) / 256 * 256;
+  const size_t po = (static_cast<size_t>(max_grid_ctas) * 2 * n_q * head_dim * sizeof(float) + 255) / 256 * 256;
+  const size_t counters = (static_cast<size_t>(max_rows) * n_kv * sizeof(int32_t) + 255) / 256 * 256;
+  return ml + po + counters;
+}
+
+int vb_paged_attn(void* d_out, const void* d_q, const void* d_kv, int64_t slab_base,
+                  const int32_t* d_row_kvlen, const int32_t* d_row_chunk_start, const int32_t* d_row_pagebase,
+                  const int32_t* d_row_old, const int32_t* d_kv_indices, int n_rows, int n_q, int n_kv, int head_dim, int page_size,
                   int chunk_tokens, float sm_scale, void* d_workspace, size_t workspace_bytes, int grid_ctas,
-                  void* stream) {
-  VB_CHECK_ARG(d_out && d_q && kv_map && d_row_kvlen && d_row_chunk_start && d_rc_meta && d_workspace,
+                  int ws_grid_ctas, void* stream) {
+  VB_CHECK_ARG(d_out && d_q && d_kv && d_row_kvlen && d_row_chunk_start && d_row_pagebase && d_row_old && d_kv_indices &&
+                   d_workspace,
                "vb_paged_attn: null pointer");
-  VB_CHECK_ARG(n_kv > 0 && n_q % n_kv == 0 && n_q / n_kv <= 16, "vb_paged_attn: GQA group %d/%d unsupported (<=16)",
-               n_q, n_kv);
+  VB_CHECK_ARG(n_kv > 0 && n_kv <= 8 && n_q % n_kv == 0 && n_q / n_kv <= 16,
+               "vb_paged_attn: %d query / %d kv heads unsupported (kv heads <= 8, group <= 16)", n_q, n_kv);
   VB_CHECK_ARG(head_dim == 64 || head_dim == 128, "vb_paged_attn: head_dim %d unsupported (64, 128)", head_dim);
-  VB_CHECK_ARG(chunk_tokens == 16 || chunk_tokens == 32 || chunk_tokens == 64,
-               "vb_paged_attn: chunk_tokens %d unsupported (16, 32, 64)", chunk_tokens);
-  VB_CHECK_ARG(page_size % chunk_tokens == 0, "vb_paged_attn: chunk_tokens must divide page_size");
-  VB_CHECK_ARG(workspace_bytes >= vb_paged_attn_workspace_bytes(n_rows, max_chunks_total, n_q, n_kv, head_dim),
-               "vb_paged_attn: workspace too small");
-  VB_CHECK_ARG(grid_ctas > 0, "vb_paged_attn: grid_ctas must be positive");
-  VB_CHECK_ARG((reinterpret_cast<uintptr_t>(d_rc_meta) & 31) == 0, "vb_paged_attn: rc_meta must be 32-byte aligned");
+  VB_CHECK_ARG(chunk_tokens == vb_attn_tile_tokens(page_size, n_kv),
+               "vb_paged_attn: chunk_tokens %d != vb_attn_tile_tokens(%d, %d)", chunk_tokens, page_size, n_kv);
+  VB_CHECK_ARG(grid_ctas > 0 && grid_ctas <= ws_grid_ctas, "vb_paged_attn: grid_ctas %d outside (0, %d]", grid_ctas,
+               ws_grid_ctas);
+  VB_CHECK_ARG(workspace_bytes >= vb_paged_attn_workspace_bytes(n_rows, ws_grid_ctas, n_q, n_kv, head_dim),
+               "vb_paged_attn: workspace too small for %d rows x %d CTAs", n_rows, ws_grid_ctas);
   if (n_rows <= 0) return 0;
-  const int G = n_q / n_kv;
   AttnParams p;
   p.out = static_cast<__nv_bfloat16*>(d_out);
   p.q = static_cast<const __nv_bfloat16*>(d_q);
   p.row_kvlen = d_row_kvlen;
   p.row_chunk_start = d_row_chunk_start;
-  p.rc_meta = reinterpret_cast<const int4*>(d_rc_meta);
+  p.row_pagebase = d_row_pagebase;
+  p.row_old = d_row_old;
+  p.kv_indices = d_kv_indices;
+  p.kv = static_cast<const __nv_bfloat16*>(d_kv);
+  // layout fixed by ws_grid_ctas (what the caller sized the buffer for), not by this launch: counters come last
   uint8_t* ws = static_cast<uint8_t*>(d_workspace);
-  const size_t counters = (static_cast<size_t>(n_rows) * n_kv * sizeof(int32_t) + 255) / 256 * 256;
-  const size_t ml = (static_cast<size_t>(max_chunks_total) * n_kv * G * 2 * sizeof(float) + 255) / 256 * 256;
-  p.counters = reinterpret_cast<int32_t*>(ws);
-  p.part_ml = reinterpret_cast<float*>(ws + counters);
-  p.part_o = reinterpret_cast<float*>(ws + counters + ml);
+  const size_t ml = (static_cast<size_t>(ws_grid_ctas) * 2 * n_q * 2 * sizeof(float) + 255) / 256 * 256;
+  const size_t po = (static_cast<size_t>(ws_grid_ctas) * 2 * n_q * head_dim * sizeof(float) + 255) / 256 * 256;
+  p.part_ml = reinterpret_cast<float*>(ws);
+  p.part_o = reinterpret_cast<float*>(ws + ml);
+  p.counters = reinterpret_cast<int32_t*>(ws + ml + po);
   p.slab_base = static_cast<int>(slab_base);
-  p.n_rows = n_rows; p.n_q = n_q; p.n_kv = n_kv; p.G = G; p.page_size = page_size;
-  p.max_chunks = max_chunks_total;
+  p.n_rows = n_rows; p.n_q = n_q; p.n_kv = n_kv; p.G = n_q / n_kv; p.page_size = page_size;
+  p.tok = chunk_tokens;
   p.scale_log2 = sm_scale * 1.4426950408889634f;
-  const CUtensorMap* map = static_cast<const CUtensorMap*>(kv_map);
+  // deepest ring that fits next to the fixed buffers
+  int stages = ATTN_MAX_STAGES;
+  while (stages > 2 && AttnLayout(head_dim, p.tok, n_kv, n_q, p.G, stages, n_rows).total > VB_MAX_DYN_SMEM) --stages;
+  p.stages = stages;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool hi = G > 8;
-#define VB_ATTN_CASE(DD, CC, SS)                                                  \
-  if (head_dim == DD && chunk_tokens == CC)                                       \
-    return hi ? launch_attn<DD, CC, SS, true>(p, map, grid_ctas, st)              \
-              : launch_attn<DD, CC, SS, false>(p, map, grid_ctas, st);
-  VB_ATTN_CASE(128, 64, 3)
-  VB_ATTN_CASE(128, 32, 4)
-  VB_ATTN_CASE(128, 16, 4)
-  VB_ATTN_CASE(64, 64, 4)
-  VB_ATTN_CASE(64, 32, 4)
-  VB_ATTN_CASE(64, 16, 4)
-#undef VB_ATTN_CASE
-  vb::set_error("vb_paged_attn: no kernel instance");
-  return -1;
+  const bool hi = p.G > 8;
+  if (head_dim == 128) return hi ? launch_attn<128, true>(p, grid_ctas, st) : launch_attn<128, false>(p, grid_ctas, st);
+  return hi ? launch_attn<64, true>(p, grid_ctas, st) : launch_attn<64, false>(p, grid_ctas, st);
 }
 
 }  // extern "C"

@@ -34,6 +34,47 @@ void set_error(const char* fmt, ...);
 constexpr int VB_MAX_DYN_SMEM = 227 * 1024;
 
 // ---------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL)
+// ---------------------------------------------------------------------------------------------
+// Every kernel of the decode chain is launched with cudaLaunchAttributeProgrammaticStreamSerialization, calls
+// pdl_wait() before it touches anything its stream predecessor wrote, and pdl_trigger() right after.  Kernel k+1
+// can therefore start as soon as every CTA of kernel k is past its own wait -- i.e. while k runs, k+1 already does
+// whatever does not depend on k: launch latency, barrier / TMEM set-up, and above all streaming WEIGHTS (GEMM)
+// and the KV of earlier steps (attention) into shared memory.  Because the trigger comes after the wait, when
+// k+1 starts every kernel <= k-1 has completed: pre-wait code may read anything but k's outputs.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// launch as a programmatic dependent of the previous kernel in the stream / as a plain launch (after a memset,
+// or for kernels that do not call pdl_wait)
+#define VB_LAUNCH_PDL(kernel, grid, block, smem, stream, ...)                                                \
+  VB_CHECK_CUDA(::vb::launch_kernel(kernel, dim3(grid), dim3(block), smem, static_cast<cudaStream_t>(stream), \
+                                    true, __VA_ARGS__))
+#define VB_LAUNCH_PLAIN(kernel, grid, block, smem, stream, ...)                                              \
+  VB_CHECK_CUDA(::vb::launch_kernel(kernel, dim3(grid), dim3(block), smem, static_cast<cudaStream_t>(stream), \
+                                    false, __VA_ARGS__))
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// for kernels with nothing to do before their predecessor has finished
+__device__ __forceinline__ void pdl_sync() {
+  pdl_wait();
+  pdl_trigger();
+}
+
+// ---------------------------------------------------------------------------------------------
 // small device utilities
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

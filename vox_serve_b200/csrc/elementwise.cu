@@ -23,6 +23,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 __global__ void __launch_bounds__(256) rmsnorm_kernel(__nv_bfloat16* __restrict__ out,
                                                       const __nv_bfloat16* __restrict__ x,
                                                       const __nv_bfloat16* __restrict__ w, int dim, float eps) {
+  pdl_sync();
   __shared__ float red[32];
   const size_t row = blockIdx.x;
   const __nv_bfloat16* xr = x + row * dim;
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(256) rope_kernel(__nv_bfloat16* __restrict__ q
                                                    const __nv_bfloat16* q, const __nv_bfloat16* k,
                                                    const int32_t* __restrict__ pos, const float* __restrict__ freq,
                                                    int n_q, int n_kv, int D, int rotary_dim, int interleave) {
+  pdl_sync();
   extern __shared__ float sm[];  // cos[rotary_dim], sin[rotary_dim], values[(n_q+n_kv)*D]
   float* cs = sm;
   float* val = sm + 2 * rotary_dim;
@@ -120,7 +122,9 @@ __global__ void __launch_bounds__(1024) plan_rows_kernel(const int32_t* __restri
                                                          int32_t* __restrict__ row_req, int32_t* __restrict__ row_kvlen,
                                                          int32_t* __restrict__ row_page, int32_t* __restrict__ row_slot,
                                                          int32_t* __restrict__ row_chunk_start,
-                                                         int32_t* __restrict__ rc_meta, int max_chunks) {
+                                                         int32_t* __restrict__ row_pagebase,
+                                                         int32_t* __restrict__ row_old) {
+  pdl_sync();
   __shared__ int32_t warp_tot[32];
   __shared__ int32_t carry;
   const int tid = threadIdx.x;
@@ -135,6 +139,8 @@ __global__ void __launch_bounds__(1024) plan_rows_kernel(const int32_t* __restri
       if (row >= n_rows_padded) break;
       const int g = kv_len - n_new + j;
       row_req[row] = r;
+      row_pagebase[row] = p0;
+      row_old[row] = kv_len - n_new;
       row_kvlen[row] = g + 1;
       row_page[row] = kv_indices[p0 + g / page_size];
       row_slot[row] = g % page_size;
@@ -143,6 +149,8 @@ __global__ void __launch_bounds__(1024) plan_rows_kernel(const int32_t* __restri
   const int n_valid = qo_indptr ? qo_indptr[n_req] : n_req;
   for (int row = n_valid + tid; row < n_rows_padded; row += blockDim.x) {
     row_req[row] = -1;
+    row_pagebase[row] = 0;
+    row_old[row] = 0;
     row_kvlen[row] = 0;
     row_page[row] = -1;
     row_slot[row] = 0;
@@ -178,27 +186,6 @@ __global__ void __launch_bounds__(1024) plan_rows_kernel(const int32_t* __restri
     __syncthreads();
   }
   if (tid == 0) row_chunk_start[n_rows_padded] = carry;
-  // pass 3: one record per (row, chunk) so the attention producer resolves a work item with one 32-byte load:
-  // {row, token0, page, kvlen, n_chunks, first_rc, 0, 0}
-  if (rc_meta) {
-    __syncthreads();
-    const int n_rc = min(carry, max_chunks);
-    for (int rc = tid; rc < n_rc; rc += blockDim.x) {
-      int lo = 0, hi = n_rows_padded;  // largest row with row_chunk_start[row] <= rc
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (row_chunk_start[mid] <= rc) lo = mid; else hi = mid;
-      }
-      const int row = lo, first = row_chunk_start[row];
-      const int token0 = (rc - first) * chunk;
-      const int req = row_req[row];
-      int4 a, b;
-      a.x = row; a.y = token0; a.z = kv_indices[kv_indptr[req] + token0 / page_size]; a.w = row_kvlen[row];
-      b.x = row_chunk_start[row + 1] - first; b.y = first; b.z = 0; b.w = 0;
-      reinterpret_cast<int4*>(rc_meta)[rc * 2] = a;
-      reinterpret_cast<int4*>(rc_meta)[rc * 2 + 1] = b;
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -207,6 +194,7 @@ __global__ void __launch_bounds__(1024) plan_rows_kernel(const int32_t* __restri
 __global__ void kv_append_kernel(__nv_bfloat16* __restrict__ kv, const __nv_bfloat16* __restrict__ k,
                                  const __nv_bfloat16* __restrict__ v, const int32_t* __restrict__ row_page,
                                  const int32_t* __restrict__ row_slot, int page_size, int row_elems /*n_kv*D*/) {
+  pdl_sync();
   const size_t t = blockIdx.x;
   const int page = row_page[t];
   if (page < 0) return;
@@ -228,6 +216,7 @@ __global__ void __launch_bounds__(256) reduce_residual_rmsnorm_kernel(
     __nv_bfloat16* __restrict__ hidden_out, __nv_bfloat16* __restrict__ normed_out,
     const float* __restrict__ partials, int split_k, const __nv_bfloat16* __restrict__ residual,
     const __nv_bfloat16* __restrict__ norm_w, int T, int N, float eps) {
+  pdl_sync();
   extern __shared__ float hs[];  // N floats
   __shared__ float red[32];
   const size_t t = blockIdx.x;
@@ -277,6 +266,7 @@ __global__ void __launch_bounds__(256) qkv_rope_append_kernel(
     int split_k, const int32_t* __restrict__ pos, const float* __restrict__ freq,
     const int32_t* __restrict__ row_page, const int32_t* __restrict__ row_slot, int T, int n_q, int n_kv, int D,
     int page_size, int rotary_dim, int interleave) {
+  pdl_sync();
   extern __shared__ float sm[];  // [2*rotary_dim cos/sin][(n_q+2n_kv)*D values]
   float* cs = sm;
   float* val = sm + 2 * rotary_dim;
@@ -332,6 +322,7 @@ __global__ void __launch_bounds__(256) qkv_rope_append_kernel(
 
 __global__ void embedding_kernel(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ table,
                                  const int32_t* __restrict__ ids, int dim, int vocab) {
+  pdl_sync();
   const size_t t = blockIdx.x;
   int id = ids[t];
   id = min(max(id, 0), vocab - 1);
@@ -342,6 +333,7 @@ __global__ void embedding_kernel(__nv_bfloat16* __restrict__ out, const __nv_bfl
 
 __global__ void gather_rows_kernel(uint8_t* __restrict__ out, const uint8_t* __restrict__ in,
                                    const int32_t* __restrict__ idx, int row_bytes, int idx_offset) {
+  pdl_sync();
   const size_t i = blockIdx.x;
   const uint4* src = reinterpret_cast<const uint4*>(in + static_cast<size_t>(idx[i] + idx_offset) * row_bytes);
   uint4* dst = reinterpret_cast<uint4*>(out + i * row_bytes);
@@ -349,6 +341,7 @@ __global__ void gather_rows_kernel(uint8_t* __restrict__ out, const uint8_t* __r
 }
 
 __global__ void pcm16_kernel(int16_t* __restrict__ out, const float* __restrict__ a, int64_t n) {
+  pdl_sync();
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) out[i] = static_cast<int16_t>(__float2int_rz(a[i] * 32767.0f));
 }
@@ -356,6 +349,7 @@ __global__ void pcm16_kernel(int16_t* __restrict__ out, const float* __restrict_
 __global__ void orpheus_window_codes_kernel(int32_t* __restrict__ c0, int32_t* __restrict__ c1,
                                             int32_t* __restrict__ c2, const int64_t* __restrict__ ids, int B,
                                             int base) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over B*28
   if (i >= B * 28) return;
   const int b = i / 28, r = i % 28, f = r / 7, p = r % 7;
@@ -381,10 +375,7 @@ int vb_rmsnorm(void* d_out, const void* d_x, const void* d_weight, int rows, int
   VB_CHECK_ARG(d_out && d_x && d_weight, "vb_rmsnorm: null pointer");
   VB_CHECK_ARG(dim > 0 && dim % 8 == 0, "vb_rmsnorm: dim %d must be a positive multiple of 8", dim);
   if (rows <= 0) return 0;
-  rmsnorm_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<__nv_bfloat16*>(d_out), static_cast<const __nv_bfloat16*>(d_x),
-      static_cast<const __nv_bfloat16*>(d_weight), dim, eps);
-  VB_CHECK_LAUNCH();
+  VB_LAUNCH_PDL(rmsnorm_kernel, rows, 256, 0, stream, static_cast<__nv_bfloat16*>(d_out), static_cast<const __nv_bfloat16*>(d_x), static_cast<const __nv_bfloat16*>(d_weight), dim, eps);
   return 0;
 }
 
@@ -397,9 +388,7 @@ int vb_rope_freqs(float* d_freq, int rotary_dim, int interleave, float rope_scal
                            2.f * 3.14159265358979323846f * low_freq_factor);
     b = -1.0f / (high_freq_factor / low_freq_factor - 1.0f);
   }
-  rope_freq_kernel<<<(rotary_dim + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_freq, rotary_dim, interleave, 1.0f / rope_scale, 1.0f / rope_theta, a, b);
-  VB_CHECK_LAUNCH();
+  VB_LAUNCH_PLAIN(rope_freq_kernel, (rotary_dim + 127) / 128, 128, 0, stream, d_freq, rotary_dim, interleave, 1.0f / rope_scale, 1.0f / rope_theta, a, b);
   return 0;
 }
 
@@ -410,11 +399,7 @@ int vb_rope(void* d_q_out, void* d_k_out, const void* d_q, const void* d_k, cons
   VB_CHECK_ARG(rotary_dim > 0 && rotary_dim <= head_dim && rotary_dim % 2 == 0, "vb_rope: rotary_dim %d invalid",
                rotary_dim);
   if (T <= 0) return 0;
-  rope_kernel<<<T, 256, (2 * rotary_dim + (n_q + n_kv) * head_dim) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<__nv_bfloat16*>(d_q_out), static_cast<__nv_bfloat16*>(d_k_out),
-      static_cast<const __nv_bfloat16*>(d_q), static_cast<const __nv_bfloat16*>(d_k), d_pos, d_freq, n_q, n_kv,
-      head_dim, rotary_dim, interleave);
-  VB_CHECK_LAUNCH();
+  VB_LAUNCH_PDL(rope_kernel, T, 256, (2 * rotary_dim + (n_q + n_kv) * head_dim) * sizeof(float), stream, static_cast<__nv_bfloat16*>(d_q_out), static_cast<__nv_bfloat16*>(d_k_out), static_cast<const __nv_bfloat16*>(d_q), static_cast<const __nv_bfloat16*>(d_k), d_pos, d_freq, n_q, n_kv, head_dim, rotary_dim, interleave);
   return 0;
 }
 
@@ -422,17 +407,14 @@ int vb_plan_rows(const int32_t* d_qo_indptr, const int32_t* d_kv_indptr, const i
                  const int32_t* d_last_page_len, const int32_t* d_kv_len, int n_req, int n_rows_padded, int page_size,
                  int chunk_tokens,
                  int32_t* d_row_req, int32_t* d_row_kvlen, int32_t* d_row_page, int32_t* d_row_slot,
-                 int32_t* d_row_chunk_start, int32_t* d_rc_meta, int max_chunks, void* stream) {
+                 int32_t* d_row_chunk_start, int32_t* d_row_pagebase, int32_t* d_row_old, void* stream) {
   VB_CHECK_ARG(d_kv_indptr && d_kv_indices && (d_last_page_len || d_kv_len) && d_row_req && d_row_kvlen &&
-                   d_row_page && d_row_slot && d_row_chunk_start,
+                   d_row_page && d_row_slot && d_row_chunk_start && d_row_pagebase && d_row_old,
                "vb_plan_rows: null pointer");
   VB_CHECK_ARG(page_size > 0 && chunk_tokens > 0 && page_size % chunk_tokens == 0,
                "vb_plan_rows: chunk_tokens %d must divide page_size %d", chunk_tokens, page_size);
   VB_CHECK_ARG(n_req >= 0 && n_rows_padded >= 0, "vb_plan_rows: negative sizes");
-  plan_rows_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_qo_indptr, d_kv_indptr, d_kv_indices, d_last_page_len, d_kv_len, n_req, n_rows_padded, page_size, chunk_tokens,
-      d_row_req, d_row_kvlen, d_row_page, d_row_slot, d_row_chunk_start, d_rc_meta, max_chunks);
-  VB_CHECK_LAUNCH();
+  VB_LAUNCH_PDL(plan_rows_kernel, 1, 1024, 0, stream, d_qo_indptr, d_kv_indptr, d_kv_indices, d_last_page_len, d_kv_len, n_req, n_rows_padded, page_size, chunk_tokens, d_row_req, d_row_kvlen, d_row_page, d_row_slot, d_row_chunk_start, d_row_pagebase, d_row_old);
   return 0;
 }
 
@@ -441,10 +423,7 @@ int vb_kv_append(void* d_layer_kv, const void* d_k, const void* d_v, const int32
   VB_CHECK_ARG(d_layer_kv && d_k && d_v && d_row_page && d_row_slot, "vb_kv_append: null pointer");
   VB_CHECK_ARG((n_kv * head_dim) % 8 == 0, "vb_kv_append: n_kv*head_dim must be a multiple of 8");
   if (T <= 0) return 0;
-  kv_append_kernel<<<T, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<__nv_bfloat16*>(d_layer_kv), static_cast<const __nv_bfloat16*>(d_k),
-      static_cast<const __nv_bfloat16*>(d_v), d_row_page, d_row_slot, page_size, n_kv * head_dim);
-  VB_CHECK_LAUNCH();
+  VB_LAUNCH_PDL(kv_append_kernel, T, 128, 0, stream, static_cast<__nv_bfloat16*>(d_layer_kv), static_cast<const __nv_bfloat16*>(d_k), static_cast<const __nv_bfloat16*>(d_v), d_row_page, d_row_slot, page_size, n_kv * head_dim);
   return 0;
 }
 
@@ -459,10 +438,7 @@ int vb_reduce_residual_rmsnorm(void* d_hidden_out, void* d_normed_out, const flo
   if (smem > 48 * 1024)
     VB_CHECK_CUDA(cudaFuncSetAttribute(reduce_residual_rmsnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        VB_MAX_DYN_SMEM));
-  reduce_residual_rmsnorm_kernel<<<T, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<__nv_bfloat16*>(d_hidden_out), static_cast<__nv_bfloat16*>(d_normed_out), d_partials, split_k,
-      static_cast<const __nv_bfloat16*>(d_residual), static_cast<const __nv_bfloat16*>(d_norm_weight), T, N, eps);
-  VB_CHECK_LAUNCH();
+  VB_LAUNCH_PDL(reduce_residual_rmsnorm_kernel, T, 256, smem, stream, static_cast<__nv_bfloat16*>(d_hidden_out), static_cast<__nv_bfloat16*>(d_normed_out), d_partials, split_k, static_cast<const __nv_bfloat16*>(d_residual), static_cast<const __nv_bfloat16*>(d_norm_weight), T, N, eps);
   return 0;
 }
 
@@ -479,19 +455,14 @@ int vb_qkv_rope_append(void* d_q_out, void* d_layer_kv, const float* d_partials,
   if (smem > 48 * 1024)
     VB_CHECK_CUDA(cudaFuncSetAttribute(qkv_rope_append_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        VB_MAX_DYN_SMEM));
-  qkv_rope_append_kernel<<<T, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<__nv_bfloat16*>(d_q_out), static_cast<__nv_bfloat16*>(d_layer_kv), d_partials, split_k, d_pos,
-      d_freq, d_row_page, d_row_slot, T, n_q, n_kv, head_dim, page_size, rotary_dim, interleave);
-  VB_CHECK_LAUNCH();
+  VB_LAUNCH_PDL(qkv_rope_append_kernel, T, 256, smem, stream, static_cast<__nv_bfloat16*>(d_q_out), static_cast<__nv_bfloat16*>(d_layer_kv), d_partials, split_k, d_pos, d_freq, d_row_page, d_row_slot, T, n_q, n_kv, head_dim, page_size, rotary_dim, interleave);
   return 0;
 }
 
 int vb_embedding(void* d_out, const void* d_table, const int32_t* d_ids, int T, int dim, int vocab, void* stream) {
   VB_CHECK_ARG(d_out && d_table && d_ids && dim % 8 == 0, "vb_embedding: bad arguments");
   if (T <= 0) return 0;
-  embedding_kernel<<<T, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<__nv_bfloat16*>(d_out), static_cast<const __nv_bfloat16*>(d_table), d_ids, dim, vocab);
-  VB_CHECK_LAUNCH();
+  VB_LAUNCH_PDL(embedding_kernel, T, 128, 0, stream, static_cast<__nv_bfloat16*>(d_out), static_cast<const __nv_bfloat16*>(d_table), d_ids, dim, vocab);
   return 0;
 }
 
@@ -499,17 +470,14 @@ int vb_gather_rows(void* d_out, const void* d_in, const int32_t* d_idx, int n, i
                    void* stream) {
   VB_CHECK_ARG(d_out && d_in && d_idx && row_bytes % 16 == 0, "vb_gather_rows: bad arguments");
   if (n <= 0) return 0;
-  gather_rows_kernel<<<n, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<uint8_t*>(d_out), static_cast<const uint8_t*>(d_in), d_idx, row_bytes, idx_offset);
-  VB_CHECK_LAUNCH();
+  VB_LAUNCH_PDL(gather_rows_kernel, n, 256, 0, stream, static_cast<uint8_t*>(d_out), static_cast<const uint8_t*>(d_in), d_idx, row_bytes, idx_offset);
   return 0;
 }
 
 int vb_pcm16(int16_t* d_out, const float* d_audio, int64_t n, void* stream) {
   VB_CHECK_ARG(d_out && d_audio, "vb_pcm16: null pointer");
   if (n <= 0) return 0;
-  pcm16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_out, d_audio, n);
-  VB_CHECK_LAUNCH();
+  VB_LAUNCH_PDL(pcm16_kernel, static_cast<unsigned>((n + 255) / 256), 256, 0, stream, d_out, d_audio, n);
   return 0;
 }
 
@@ -517,9 +485,7 @@ int vb_orpheus_window_codes(int32_t* d_c0, int32_t* d_c1, int32_t* d_c2, const i
                             int audio_id_base, void* stream) {
   VB_CHECK_ARG(d_c0 && d_c1 && d_c2 && d_ids, "vb_orpheus_window_codes: null pointer");
   if (B <= 0) return 0;
-  orpheus_window_codes_kernel<<<(B * 28 + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_c0, d_c1, d_c2, d_ids, B, audio_id_base);
-  VB_CHECK_LAUNCH();
+  VB_LAUNCH_PDL(orpheus_window_codes_kernel, (B * 28 + 127) / 128, 128, 0, stream, d_c0, d_c1, d_c2, d_ids, B, audio_id_base);
   return 0;
 }
 
@@ -532,6 +498,7 @@ namespace vb {
 // state = {kv_len[B], position[B]} advance by one token per request (worker/base.py:312-325 does this on
 // the host); active[b] == 0 freezes a slot.
 __global__ void decode_advance_kernel(int32_t* kv_len, int32_t* pos, const int32_t* active, int B) {
+  pdl_sync();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B && (!active || active[b])) {
     kv_len[b] += 1;
@@ -542,6 +509,7 @@ __global__ void decode_advance_kernel(int32_t* kv_len, int32_t* pos, const int32
 // ring history[s][n_out[s] % cap], ++n_out[s]   (orpheus.py:447-448, 456-458 keep these in Python lists)
 __global__ void token_feedback_kernel(const int64_t* ids, const int32_t* slots, int32_t* next_input,
                                       int32_t* history, int32_t* n_out, int B, int cap) {
+  pdl_sync();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int s = slots ? slots[b] : b;
@@ -553,12 +521,14 @@ __global__ void token_feedback_kernel(const int64_t* ids, const int32_t* slots, 
 }
 // next step's input ids gathered by slot: ids[b] = next_input[slots[b]]
 __global__ void gather_i32_kernel(int32_t* out, const int32_t* src, const int32_t* idx, int n) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = src[idx ? idx[i] : i];
 }
 // step input ids: decode rows take the id sampled last step for their slot, prefill rows the uploaded prompt id
 __global__ void build_input_ids_kernel(int32_t* out, const int32_t* host_ids, const int32_t* next_input,
                                        const int32_t* row_slot, int n) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int s = row_slot[i];
@@ -567,6 +537,7 @@ __global__ void build_input_ids_kernel(int32_t* out, const int32_t* host_ids, co
 // newest full window per slot: first[i] = n_out[slot[i]] - window (device-resident loop: the host never
 // sees the token counters between replays)
 __global__ void latest_window_kernel(int32_t* first, const int32_t* n_out, const int32_t* slot, int n, int window) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) first[i] = max(0, n_out[slot ? slot[i] : i] - window);
 }
@@ -574,6 +545,7 @@ __global__ void latest_window_kernel(int32_t* first, const int32_t* n_out, const
 // of cuda_graph_worker.py:1176-1190 (a short last window repeats its final token, :1183-1185).
 __global__ void gather_windows_kernel(int64_t* windows, const int32_t* history, const int32_t* slot,
                                       const int32_t* first, const int32_t* n_valid, int n, int cap, int win) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * win) return;
   const int w = i / win, j = i - w * win;
@@ -587,8 +559,7 @@ extern "C" {
 int vb_decode_advance(int32_t* d_kv_len, int32_t* d_pos, const int32_t* d_active, int B, void* stream) {
   VB_CHECK_ARG(d_kv_len && d_pos, "vb_decode_advance: null pointer");
   if (B <= 0) return 0;
-  vb::decode_advance_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_kv_len, d_pos, d_active, B);
-  VB_CHECK_LAUNCH();
+  VB_LAUNCH_PDL(vb::decode_advance_kernel, (B + 127) / 128, 128, 0, stream, d_kv_len, d_pos, d_active, B);
   return 0;
 }
 int vb_token_feedback(const int64_t* d_ids, const int32_t* d_slots, int32_t* d_next_input, int32_t* d_history,
@@ -596,43 +567,34 @@ int vb_token_feedback(const int64_t* d_ids, const int32_t* d_slots, int32_t* d_n
   VB_CHECK_ARG(d_ids && d_next_input && d_n_out, "vb_token_feedback: null pointer");
   VB_CHECK_ARG(history_cap > 0, "vb_token_feedback: history_cap must be positive");
   if (B <= 0) return 0;
-  vb::token_feedback_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_ids, d_slots, d_next_input, d_history, d_n_out, B, history_cap);
-  VB_CHECK_LAUNCH();
+  VB_LAUNCH_PDL(vb::token_feedback_kernel, (B + 127) / 128, 128, 0, stream, d_ids, d_slots, d_next_input, d_history, d_n_out, B, history_cap);
   return 0;
 }
 int vb_gather_i32(int32_t* d_out, const int32_t* d_src, const int32_t* d_idx, int n, void* stream) {
   VB_CHECK_ARG(d_out && d_src, "vb_gather_i32: null pointer");
   if (n <= 0) return 0;
-  vb::gather_i32_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_out, d_src, d_idx, n);
-  VB_CHECK_LAUNCH();
+  VB_LAUNCH_PDL(vb::gather_i32_kernel, (n + 127) / 128, 128, 0, stream, d_out, d_src, d_idx, n);
   return 0;
 }
 int vb_build_input_ids(int32_t* d_out, const int32_t* d_host_ids, const int32_t* d_next_input,
                        const int32_t* d_row_slot, int n, void* stream) {
   VB_CHECK_ARG(d_out && d_host_ids && d_next_input && d_row_slot, "vb_build_input_ids: null pointer");
   if (n <= 0) return 0;
-  vb::build_input_ids_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_out, d_host_ids, d_next_input, d_row_slot, n);
-  VB_CHECK_LAUNCH();
+  VB_LAUNCH_PDL(vb::build_input_ids_kernel, (n + 127) / 128, 128, 0, stream, d_out, d_host_ids, d_next_input, d_row_slot, n);
   return 0;
 }
 int vb_latest_window(int32_t* d_first, const int32_t* d_n_out, const int32_t* d_slot, int n, int window,
                      void* stream) {
   VB_CHECK_ARG(d_first && d_n_out, "vb_latest_window: null pointer");
   if (n <= 0) return 0;
-  vb::latest_window_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_first, d_n_out, d_slot, n,
-                                                                                         window);
-  VB_CHECK_LAUNCH();
+  VB_LAUNCH_PDL(vb::latest_window_kernel, (n + 127) / 128, 128, 0, stream, d_first, d_n_out, d_slot, n, window);
   return 0;
 }
 int vb_gather_windows(int64_t* d_windows, const int32_t* d_history, const int32_t* d_slot, const int32_t* d_first,
                       const int32_t* d_n_valid, int n, int history_cap, int window, void* stream) {
   VB_CHECK_ARG(d_windows && d_history && d_slot && d_first, "vb_gather_windows: null pointer");
   if (n <= 0) return 0;
-  vb::gather_windows_kernel<<<(n * window + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_windows, d_history, d_slot, d_first, d_n_valid, n, history_cap, window);
-  VB_CHECK_LAUNCH();
+  VB_LAUNCH_PDL(vb::gather_windows_kernel, (n * window + 127) / 128, 128, 0, stream, d_windows, d_history, d_slot, d_first, d_n_valid, n, history_cap, window);
   return 0;
 }
 }  // extern "C"

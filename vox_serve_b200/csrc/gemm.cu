@@ -67,9 +67,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
     if (lane == 0) {
       const uint64_t pol_w = policy_evict_first();   // weights are streamed once per step
       const uint64_t pol_x = policy_evict_last();    // activations are re-read by every CTA
-      int s = 0;
-      uint32_t ph = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
+      // The weights do not depend on the previous kernel: fill the whole ring with weight tiles while it is
+      // still running, then wait for it and add the activation tiles to the same stages.
+      const int npre = min(p.stages, kb1 - kb0);
+      for (int i = 0; i < npre; ++i) {
+        mbar_arrive_expect_tx(&full[i], stage_bytes);
+        tma_load_2d_hint(smem + i * stage_bytes, &w_map, &full[i], (kb0 + i) * GEMM_BLOCK_K, n_tile * GEMM_BLOCK_M,
+                         pol_w);
+      }
+      pdl_wait();
+      pdl_trigger();
+      for (int i = 0; i < npre; ++i)
+        tma_load_2d_hint(smem + i * stage_bytes + GEMM_A_STAGE, &x_map, &full[i], (kb0 + i) * GEMM_BLOCK_K,
+                         t_blk * p.t_tile, pol_x);
+      int s = npre == p.stages ? 0 : npre;
+      uint32_t ph = npre == p.stages ? 1 : 0;
+      for (int kb = kb0 + npre; kb < kb1; ++kb) {
         mbar_wait(&empty[s], ph ^ 1);
         uint8_t* a = smem + s * stage_bytes;
         mbar_arrive_expect_tx(&full[s], stage_bytes);
@@ -102,6 +115,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
     }
   } else {
     // ================= epilogue: TMEM -> registers -> global =================
+    // (stores happen after the accumulator is complete, i.e. after activation tiles that were only requested
+    // once the previous kernel had finished: no explicit wait needed on this path)
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) belong to this warp
     const int row = quarter * 32 + lane;          // accumulator row = output feature inside the tile
     mbar_wait(tmem_full, 0);
@@ -209,9 +224,7 @@ int vb_gemm_bf16(void* d_y, const void* w_map, const void* x_map, int T, int N, 
   const int smem = stages * stage_bytes + extra;
   VB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VB_MAX_DYN_SMEM));
   dim3 grid((N + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M, split_k, (T + p.t_tile - 1) / p.t_tile);
-  gemm_bf16_kernel<<<grid, GEMM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
-      p, *static_cast<const CUtensorMap*>(w_map), *static_cast<const CUtensorMap*>(x_map));
-  VB_CHECK_LAUNCH();
+  VB_LAUNCH_PDL(gemm_bf16_kernel, grid, GEMM_THREADS, smem, stream, p, *static_cast<const CUtensorMap*>(w_map), *static_cast<const CUtensorMap*>(x_map));
   return 0;
 }
 

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(256) argmax_kernel(const SampleParams p) {
 }
 
 __global__ void unpack_argmax_kernel(int64_t* out, const unsigned long long* packed, int rows) {
+  pdl_sync();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < rows) out[r] = static_cast<int64_t>(~static_cast<uint32_t>(packed[r] & 0xffffffffull));
 }
@@ -147,6 +148,7 @@ constexpr double Q40 = 1099511627776.0;                 // 2^40
 
 // One CTA per row.  Thread t owns keys [hi - 63, hi], hi = 65535 - 64 t  (descending value order).
 __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const SampleParams p) {
+  pdl_sync();
   __shared__ unsigned long long sh[33];
   __shared__ float sh_f[32];
   __shared__ int sh_i[4];
@@ -308,6 +310,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const SampleParams p
 
 // resolve (key, rank) -> index of the rank-th token (index order) whose value code equals key
 __global__ void __launch_bounds__(1024) resolve_kernel(const SampleParams p) {
+  pdl_sync();
   __shared__ unsigned long long sh[33];
   const int row = blockIdx.x, tid = threadIdx.x;
   const uint32_t key = p.pick[row * 2], rank = p.pick[row * 2 + 1];
@@ -338,6 +341,7 @@ __global__ void penalty_kernel(__nv_bfloat16* out, const SampleParams p) {
 
 // window > 1: cache[:, :-1] = cache[:, 1:]; cache[:, -1] = 0   (sampling.py:166-168)
 __global__ void rep_shift_kernel(uint8_t* cache, const int32_t* cache_rows, int B, int W, size_t plane /*C*V*/) {
+  pdl_sync();
   const size_t n = static_cast<size_t>(B) * plane;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -351,6 +355,7 @@ __global__ void rep_shift_kernel(uint8_t* cache, const int32_t* cache_rows, int 
 // cache[b, w(s), c(s), ids[b', c']] = 1 for every b and every (b', c')   (sampling.py:169-178)
 __global__ void rep_mark_kernel(uint8_t* cache, const int32_t* cache_rows, const int64_t* ids, int B, int W, int C,
                                 int V, int C_ids, int windowed) {
+  pdl_sync();
   const int n_ids = B * C_ids;
   const bool cb0_only = (C_ids == 1 && C != 1);
   const int w_lo = windowed ? W - 1 : 0, w_hi = W;
@@ -425,19 +430,14 @@ int vb_sample(int64_t* d_out_ids, const void* d_logits, int rows, int vocab, int
   const int gx = max(1, min(32, (vocab + 256 * 8 - 1) / (256 * 8)));
   if (strategy == 0) {
     VB_CHECK_CUDA(cudaMemsetAsync(p.packed, 0, static_cast<size_t>(rows) * 8, st));
-    argmax_kernel<<<dim3(gx, rows), 256, 0, st>>>(p);
-    VB_CHECK_LAUNCH();
-    unpack_argmax_kernel<<<(rows + 127) / 128, 128, 0, st>>>(d_out_ids, p.packed, rows);
-    VB_CHECK_LAUNCH();
+    VB_LAUNCH_PLAIN(argmax_kernel, dim3(gx, rows), 256, 0, st, p);
+    VB_LAUNCH_PDL(unpack_argmax_kernel, (rows + 127) / 128, 128, 0, st, d_out_ids, p.packed, rows);
     return 0;
   }
   VB_CHECK_CUDA(cudaMemsetAsync(p.hist, 0, static_cast<size_t>(rows) * 65536 * 4, st));
-  hist_kernel<<<dim3(gx, rows), 256, 0, st>>>(p);
-  VB_CHECK_LAUNCH();
-  scan_kernel<<<rows, SCAN_THREADS, 0, st>>>(p);
-  VB_CHECK_LAUNCH();
-  resolve_kernel<<<rows, 1024, 0, st>>>(p);
-  VB_CHECK_LAUNCH();
+  VB_LAUNCH_PLAIN(hist_kernel, dim3(gx, rows), 256, 0, st, p);
+  VB_LAUNCH_PDL(scan_kernel, rows, SCAN_THREADS, 0, st, p);
+  VB_LAUNCH_PDL(resolve_kernel, rows, 1024, 0, st, p);
   return 0;
 }
 
@@ -450,8 +450,7 @@ int vb_apply_repetition_penalty(void* d_out, const void* d_logits, const uint8_t
   fill_params(p, nullptr, d_logits, rows, vocab, vocab, d_rep_cache, rep_window_slots, rep_codebooks,
               logit_codebooks, penalty, 0, 0, 0.f, 0.f, 1.f, 0, 0, -1, nullptr);
   const int gx = max(1, min(64, (vocab + 255) / 256));
-  penalty_kernel<<<dim3(gx, rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<__nv_bfloat16*>(d_out), p);
-  VB_CHECK_LAUNCH();
+  VB_LAUNCH_PLAIN(penalty_kernel, dim3(gx, rows), 256, 0, stream, static_cast<__nv_bfloat16*>(d_out), p);
   return 0;
 }
 
@@ -464,11 +463,9 @@ int vb_update_repetition_cache(uint8_t* d_cache, const int32_t* d_cache_rows, co
   if (windowed) {
     const size_t plane = static_cast<size_t>(C) * V;
     size_t nb = (static_cast<size_t>(B) * plane + 255) / 256; if (nb > 4096) nb = 4096; const unsigned blocks = static_cast<unsigned>(nb);
-    rep_shift_kernel<<<blocks, 256, 0, st>>>(d_cache, d_cache_rows, B, W, plane);
-    VB_CHECK_LAUNCH();
+    VB_LAUNCH_PDL(rep_shift_kernel, blocks, 256, 0, st, d_cache, d_cache_rows, B, W, plane);
   }
-  rep_mark_kernel<<<64, 256, 0, st>>>(d_cache, d_cache_rows, d_ids, B, W, C, V, C_ids, windowed);
-  VB_CHECK_LAUNCH();
+  VB_LAUNCH_PDL(rep_mark_kernel, 64, 256, 0, st, d_cache, d_cache_rows, d_ids, B, W, C, V, C_ids, windowed);
   return 0;
 }
 

@@ -102,15 +102,9 @@ class LlamaEngine:
         self.device = kv_cache.device
         assert kv_cache.shape[0] == d.num_hidden_layers and kv_cache.shape[2] == 2
         self.pages_per_layer = kv_cache.shape[1]
-        self.chunk = ops.attn_chunk_tokens(page_size)
-        self.kv_map = ops.tensor_map_kv(kv_cache, self.chunk)
+        self.chunk = ops.attn_chunk_tokens(page_size, d.num_key_value_heads)
+        self.kv_map = kv_cache      # the attention kernel reads the cache with linear bulk copies: no tensor map
         self.max_rows = max_rows
-        chunks_per_page = page_size // self.chunk
-        # attention work items (row, chunk): decode rows share the cache's pages; prefill rows each see up to
-        # max_seq_len tokens.  The plan / attention kernels trap if a step exceeds this bound.
-        per_row = (max_seq_len + self.chunk - 1) // self.chunk
-        decode_bound = self.pages_per_layer * chunks_per_page
-        self.max_chunks = max(64, min(decode_bound, max_rows * per_row) if max_rows <= 64 else max_rows * per_row)
         self.sms = ops.device_info()[0]
         H, I = d.hidden_size, d.intermediate_size
         hq, hkv, D = d.num_attention_heads, d.num_key_value_heads, d.head_dim
@@ -130,11 +124,11 @@ class LlamaEngine:
         self.max_out_rows = min(R, 64)     # logits are only ever needed for one row per request
         self.last_normed = torch.zeros(self.max_out_rows, H, dtype=BF16, device=dev)
         self.logits = torch.zeros(self.max_out_rows, d.vocab_size, dtype=BF16, device=dev)
-        self.attn_ws = ops.paged_attn_workspace(R, self.max_chunks, hq, hkv, D, dev)
+        self.attn_ws = ops.AttnWorkspace(R, hq, hkv, D, dev)
         self.freq = ops.rope_freq_table(D, d.rope_factor, d.rope_theta, False, d.low_freq_factor,
                                         d.high_freq_factor, d.old_context_len, device=dev)
-        self.plan = ops.RowPlan(R, dev, self.max_chunks)
-        self.attn_grid = 2 * self.sms
+        self.plan = ops.RowPlan(R, dev)
+        self.attn_grid = self.attn_ws.grid
 
     def _partials(self, split: int, rows: int, width: int) -> torch.Tensor:
         return self.partials[: split * rows * width].view(split, rows, width)
@@ -151,8 +145,6 @@ class LlamaEngine:
         last_rows (int32 [n_out]) selects the rows whose logits are needed (prefill: qo_indptr[1:] - 1)."""
         d, w, R = self.dims, self.w, n_rows
         plan = self.plan if plan is None else plan
-        if plan.max_chunks > self.max_chunks:
-            raise VoxB200Error("row plan allows more attention chunks than the engine workspace holds")
         if R > self.max_rows:
             raise VoxB200Error(f"{R} rows exceed the engine's max_rows {self.max_rows}")
         hq, hkv, D, H, I = d.num_attention_heads, d.num_key_value_heads, d.head_dim, d.hidden_size, d.intermediate_size

@@ -28,7 +28,7 @@ class _PagedWrapper:
         self.n_qo_head, self.n_kv_head, self.n_state = n_qo_head, n_kv_head, n_state
         self.head_dim = n_state // n_qo_head
         self.page_size = page_size
-        self.chunk = ops.attn_chunk_tokens(page_size)
+        self.chunk = ops.attn_chunk_tokens(page_size, n_kv_head)
         self.use_cuda_graph = use_cuda_graph
         self.batch_size = batch_size
         self.max_rows = (max_seq_len or 1024) if self.is_prefill else (batch_size or 64)
@@ -39,11 +39,8 @@ class _PagedWrapper:
         self.d_indptr = torch.zeros(self.max_req + 1, dtype=torch.int32, device=dev)
         self.d_indices = torch.zeros(max_pages, dtype=torch.int32, device=dev)
         self.d_last = torch.zeros(self.max_req, dtype=torch.int32, device=dev)
-        per_row = (max_pages * page_size // max(1, self.max_req) + self.chunk - 1) // self.chunk
-        bound = max_pages * (page_size // self.chunk) if not self.is_prefill else min(self.max_rows * per_row, 1 << 17)
-        self.plan_rows = ops.RowPlan(self.max_rows, dev, max(64, bound) if max_chunks is None else int(max_chunks))
+        self.plan_rows = ops.RowPlan(self.max_rows, dev)
         self.workspace = None
-        self._maps: Dict[Tuple, ops.TensorMap] = {}
         self.n_rows = 0
         self.qo_indptr = None
 
@@ -65,14 +62,6 @@ class _PagedWrapper:
         dst[:n].copy_(t.to(torch.int32), non_blocking=True)
         return dst[:n]
 
-    def _kv_map(self, kv_cache: torch.Tensor) -> ops.TensorMap:
-        key = (kv_cache.data_ptr(), tuple(kv_cache.shape))
-        m = self._maps.get(key)
-        if m is None:
-            m = ops.tensor_map_kv(kv_cache, self.chunk)
-            self._maps[key] = m
-        return m
-
     def set_kv_cache(self, kv_cache: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> None:
         """kv_cache[page, 0, slot] = k ; kv_cache[page, 1, slot] = v (flashinfer_utils.py:144-145, 243-244)."""
         ops.kv_append(kv_cache, k, v, self.plan_rows, n_rows=min(k.shape[0], self.n_rows_padded))
@@ -80,9 +69,9 @@ class _PagedWrapper:
     def run(self, q: torch.Tensor, kv_cache: torch.Tensor) -> torch.Tensor:
         R = q.shape[0]
         if self.workspace is None:
-            self.workspace = ops.paged_attn_workspace(self.max_rows, self.plan_rows.max_chunks, self.n_qo_head,
-                                                      self.n_kv_head, self.head_dim, self.device)
-        return ops.paged_attn(q.contiguous(), self._kv_map(kv_cache), 0, self.plan_rows, R, self.n_kv_head,
+            self.workspace = ops.AttnWorkspace(self.max_rows, self.n_qo_head, self.n_kv_head, self.head_dim,
+                                               self.device)
+        return ops.paged_attn(q.contiguous(), kv_cache, 0, self.plan_rows, R, self.n_kv_head,
                               self.page_size, self.chunk, self.workspace)
 
 

@@ -145,26 +145,29 @@ def rope(q: torch.Tensor, k: torch.Tensor, pos: torch.Tensor, freq: torch.Tensor
     return qo, ko
 
 
-def attn_chunk_tokens(page_size: int) -> int:
-    if page_size % 64 == 0:
-        return 64
-    if page_size in (16, 32):
-        return page_size
-    raise VoxB200Error(f"page_size {page_size} unsupported: must be 16, 32 or a multiple of 64")
+def attn_chunk_tokens(page_size: int, n_kv: int = 8) -> int:
+    """Tokens per attention tile (all kv heads ride in one tile): vb_attn_tile_tokens."""
+    t = _lib.load().vb_attn_tile_tokens(int(page_size), int(n_kv))
+    if t <= 0:
+        raise VoxB200Error(f"page_size {page_size} / {n_kv} kv heads unsupported: page_size must be a multiple of 16, "
+                           "kv heads <= 8")
+    return t
 
 
 class RowPlan:
-    """Device-side per-row / per-chunk metadata produced by vb_plan_rows (see include/vb_api.h)."""
+    """Device-side per-row metadata produced by vb_plan_rows (see include/vb_api.h); also remembers the page
+    table (kv_indices) the plan was made from, which the attention kernel reads."""
 
     def __init__(self, max_rows: int, device, max_chunks: Optional[int] = None):
         self.max_rows = max_rows
-        self.max_chunks = int(max_chunks) if max_chunks is not None else max(64, 4 * max_rows)
-        self.buf = torch.zeros(5 * max_rows + 8, dtype=torch.int32, device=device)
+        self.buf = torch.zeros(7 * max_rows + 8, dtype=torch.int32, device=device)
         m = max_rows
         self.row_req, self.row_kvlen = self.buf[0:m], self.buf[m:2 * m]
         self.row_page, self.row_slot = self.buf[2 * m:3 * m], self.buf[3 * m:4 * m]
-        self.row_chunk_start = self.buf[4 * m:5 * m + 1]
-        self.rc_meta = torch.zeros(self.max_chunks * 8, dtype=torch.int32, device=device)
+        self.row_pagebase = self.buf[4 * m:5 * m]
+        self.row_old = self.buf[5 * m:6 * m]
+        self.row_chunk_start = self.buf[6 * m:7 * m + 1]
+        self.kv_indices: Optional[torch.Tensor] = None
         self.n_rows = 0
 
 
@@ -176,8 +179,9 @@ def plan_rows(plan: RowPlan, qo_indptr: Optional[torch.Tensor], kv_indptr: torch
     call("vb_plan_rows", _p(qo_indptr), kv_indptr.data_ptr(), kv_indices.data_ptr(), _p(last_page_len), _p(kv_len),
          n_req, n_rows, page_size, chunk_tokens, plan.row_req.data_ptr(), plan.row_kvlen.data_ptr(),
          plan.row_page.data_ptr(), plan.row_slot.data_ptr(), plan.row_chunk_start.data_ptr(),
-         plan.rc_meta.data_ptr(), plan.max_chunks, _stream())
+         plan.row_pagebase.data_ptr(), plan.row_old.data_ptr(), _stream())
     plan.n_rows = n_rows
+    plan.kv_indices = kv_indices
     return plan
 
 
@@ -189,26 +193,46 @@ def kv_append(layer_kv: torch.Tensor, k: torch.Tensor, v: torch.Tensor, plan: Ro
          plan.row_slot.data_ptr(), T, layer_kv.shape[-3], layer_kv.shape[-2], layer_kv.shape[-1], _stream())
 
 
-def paged_attn_workspace(max_rows: int, max_chunks: int, n_q: int, n_kv: int, head_dim: int, device) -> torch.Tensor:
-    n = _lib.load().vb_paged_attn_workspace_bytes(max_rows, max_chunks, n_q, n_kv, head_dim)
-    return torch.zeros(n, dtype=torch.uint8, device=device)
+def attn_grid_ctas() -> int:
+    """Persistent grid of the attention kernel: one CTA per SM (a 3-stage ring of 64 KiB tiles each)."""
+    return device_info()[0]
 
 
-def paged_attn(q: torch.Tensor, kv_map: TensorMap, slab_base: int, plan: RowPlan, n_rows: int, n_kv: int,
-               page_size: int, chunk_tokens: int, workspace: torch.Tensor, sm_scale: Optional[float] = None,
+class AttnWorkspace:
+    """Split-KV partials + arrival counters, sized for (max_rows, grid CTAs)."""
+
+    def __init__(self, max_rows: int, n_q: int, n_kv: int, head_dim: int, device, grid_ctas: Optional[int] = None):
+        self.grid = attn_grid_ctas() if grid_ctas is None else int(grid_ctas)
+        self.max_rows = max_rows
+        n = _lib.load().vb_paged_attn_workspace_bytes(max_rows, self.grid, n_q, n_kv, head_dim)
+        self.buf = torch.zeros(n, dtype=torch.uint8, device=device)
+
+
+def paged_attn_workspace(max_rows: int, max_chunks, n_q: int, n_kv: int, head_dim: int, device,
+                         grid_ctas: Optional[int] = None) -> AttnWorkspace:
+    return AttnWorkspace(max_rows, n_q, n_kv, head_dim, device, grid_ctas)
+
+
+def paged_attn(q: torch.Tensor, kv_cache, slab_base: int, plan: RowPlan, n_rows: int, n_kv: int,
+               page_size: int, chunk_tokens: int, workspace: AttnWorkspace, sm_scale: Optional[float] = None,
                out: Optional[torch.Tensor] = None, grid_ctas: Optional[int] = None) -> torch.Tensor:
-    """q [R, Hq, D] bf16 -> [R, Hq, D].  `plan` must come from plan_rows with the same chunk_tokens; the
-    workspace must be sized for plan.max_chunks (paged_attn_workspace)."""
-    _need_cuda(q, workspace)
-    assert q.dtype == BF16 and q.is_contiguous()
+    """q [R, Hq, D] bf16 -> [R, Hq, D].  `kv_cache`: the whole cache tensor [L, pages, 2, P, Hkv, D] (or one layer
+    [pages, 2, P, Hkv, D]); slab_base = layer * pages.  `plan` must come from plan_rows with the same
+    chunk_tokens (= attn_chunk_tokens(page_size, n_kv))."""
+    if isinstance(kv_cache, TensorMap):      # older call sites pass tensor_map_kv(...): use the tensor behind it
+        kv_cache = kv_cache.owner
+    _need_cuda(q, kv_cache)
+    assert kv_cache.dtype == BF16 and kv_cache.is_contiguous()
+    assert q.dtype == BF16 and q.is_contiguous() and plan.kv_indices is not None
     n_q, d = q.shape[1], q.shape[2]
     out = torch.empty_like(q) if out is None else out
-    if grid_ctas is None:
-        grid_ctas = 2 * device_info()[0]
+    grid = workspace.grid if grid_ctas is None else min(int(grid_ctas), workspace.grid)
     sc = 1.0 / math.sqrt(d) if sm_scale is None else float(sm_scale)
-    call("vb_paged_attn", out.data_ptr(), q.data_ptr(), kv_map.ptr, int(slab_base), plan.row_kvlen.data_ptr(),
-         plan.row_chunk_start.data_ptr(), plan.rc_meta.data_ptr(), n_rows, plan.max_chunks, n_q, n_kv, d,
-         page_size, chunk_tokens, sc, workspace.data_ptr(), workspace.numel(), int(grid_ctas), _stream())
+    call("vb_paged_attn", out.data_ptr(), q.data_ptr(), kv_cache.data_ptr(), int(slab_base), plan.row_kvlen.data_ptr(),
+         plan.row_chunk_start.data_ptr(), plan.row_pagebase.data_ptr(), plan.row_old.data_ptr(),
+         plan.kv_indices.data_ptr(), n_rows, n_q, n_kv,
+         d, page_size, chunk_tokens, sc, workspace.buf.data_ptr(), workspace.buf.numel(), grid, workspace.grid,
+         _stream())
     return out
 
 

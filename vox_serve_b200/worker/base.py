@@ -143,7 +143,7 @@ class ModelWorker:
             raise VoxB200Error(f"model engine holds {eng.max_rows} rows, worker needs {self.max_rows}")
         common = dict(attn_buffer=None, n_qo_head=m.num_attention_heads, n_kv_head=m.num_key_value_heads,
                       n_state=m.num_attention_heads * m.head_dim, page_size=self.page_size, device=dev,
-                      max_pages=self.max_num_pages, max_chunks=eng.max_chunks)
+                      max_pages=self.max_num_pages)
         self.prefill_wrapper = FlashInferPrefillWrapper(batch_size=B, max_seq_len=self.max_rows, **common)
         self.decode_wrapper = FlashInferDecodeWrapper(batch_size=B, use_cuda_graph=True, **common)
         self.staging = _Staging(B, self.max_rows, self.max_num_pages, dev)
