@@ -261,36 +261,55 @@ def run_gpu(args):
     sched, reqs, n_setup = fresh_batch("e")
     ttfa = sorted((sched.first_audio_time[r.request_id] - sched.submit_time[r.request_id]) * 1e3 for r in reqs)
     setup_s = time.perf_counter() - t_setup0
-    audio_bytes = [0]
-    d2h = [0]
+    def timed_api_loop(sched, reqs, n_steps, async_mode):
+        """n_steps scheduler iterations through the worker API; returns (ms, audio seconds, launches, h2d, d2h)."""
+        audio_bytes = [0]
 
-    def on_audio(req, chunk, now):
-        audio_bytes[0] += len(chunk)
+        def on_audio(req, chunk, now):
+            audio_bytes[0] += len(chunk)
 
-    for _ in range(W):
-        sched._step()
-    sched.on_audio = on_audio
-    barrier()
+        state = (None, [], [])
+        if async_mode:
+            state = sched.run_async(W + 1, state)      # first call only selects; then W real steps
+        else:
+            for _ in range(W):
+                sched._step()
+        sched.on_audio = on_audio
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0, lc0 = worker.gpu_launches, ops.launch_count()
+        wall0 = time.perf_counter()
+        ev0.record()
+        if async_mode:
+            state = sched.run_async(n_steps, state)
+        else:
+            for _ in range(n_steps):
+                sched._step()
+        ev1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - wall0
+        ms = max(ev0.elapsed_time(ev1), wall * 1e3)
+        sched.on_audio = None
+        if async_mode and state[0] is not None:      # finish the last step's request-state update
+            try:
+                state[0].send(None)
+            except StopIteration:
+                pass
+        # eager launches (detokenize) are counted by the ctypes layer, graph nodes by the worker
+        launches = (worker.gpu_launches - launches0) + (ops.launch_count() - lc0)
+        n_detok = audio_bytes[0] / (BATCH * 4096.0)
+        h2d = worker.staging.n * 4 + n_detok * worker.win_host.numel() * 4 / n_steps
+        d2h = BATCH * 8 + audio_bytes[0] / n_steps
+        return ms, audio_bytes[0] / 48000.0, launches, h2d, d2h
+
     clocks.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = worker.gpu_launches + 0
-    lc0 = ops.launch_count()
-    wall0 = time.perf_counter()
-    ev0.record()
-    n_detok = 0
-    for _ in range(K):
-        _, nd = sched._step()
-        n_detok += 1 if nd else 0
-    ev1.record()
-    torch.cuda.synchronize()
-    wall_e2e = time.perf_counter() - wall0
-    e2e_ms = max(ev0.elapsed_time(ev1), wall_e2e * 1e3)
-    # eager launches (detokenize) are counted by the ctypes layer, graph nodes by the worker
-    e2e_launches = (worker.gpu_launches - launches0) + (ops.launch_count() - lc0)
-    e2e_audio_s = audio_bytes[0] / 48000.0
-    h2d_step = worker.staging.n * 4 + (n_detok * worker.win_host.numel() * 4) / K
-    d2h_step = BATCH * 8 + audio_bytes[0] / K
+    e2e_ms, e2e_audio_s, e2e_launches, h2d_step, d2h_step = timed_api_loop(sched, reqs, K, async_mode=True)
     mean_kv = sum(r.kv_token_len for r in reqs) / BATCH - K / 2
+    drain(sched, reqs)
+    # the same loop with the synchronous Scheduler._step (host bookkeeping serialised with the device)
+    Ks = min(K, 140)
+    sched, reqs, _ = fresh_batch("s")
+    sync_ms, sync_audio_s, _, _, _ = timed_api_loop(sched, reqs, Ks, async_mode=False)
     drain(sched, reqs)
 
     # ------------------------------------------------ device-resident loop ------------------------------------
@@ -336,8 +355,11 @@ def run_gpu(args):
                        "weights": "seeded N(0,0.02) bf16 at Orpheus-3B shapes; SNAC 24 kHz shapes, seeded",
                        "l2": "inputs larger than L2: 6.6 GB of weights stream from HBM every step (126 MB L2)"},
             "e2e": {"value": e2e_audio_s / (e2e_ms / 1e3), "unit": "audio-sec/sec", "h2d_bytes_per_step": int(h2d_step),
-                    "d2h_bytes_per_step": int(d2h_step), "ms_per_step": e2e_ms / K, "api": "Scheduler._step -> "
-                    "ModelWorker.prepare_lm_inputs/run_detokenize/run_lm_decode"},
+                    "d2h_bytes_per_step": int(d2h_step), "ms_per_step": e2e_ms / K,
+                    "api": "Scheduler._step_async (scheduler/base.py:168-215 ordering) -> ModelWorker."
+                           "prepare_lm_inputs/run_detokenize/run_lm_decode; host bookkeeping one step behind the device",
+                    "sync_scheduler": {"value": sync_audio_s / (sync_ms / 1e3) * world, "ms_per_step": sync_ms / Ks,
+                                       "steps": Ks, "api": "Scheduler._step (scheduler/base.py:135-166)"}},
             "gpu_launches": int(res_launches), "gpu_launches_e2e": int(e2e_launches),
             "tokens_per_s": BATCH * world * K / (res_ms / 1e3),
             "ttfa_burst_ms": {"p50": ttfa[len(ttfa) // 2], "min": ttfa[0], "max": ttfa[-1],

@@ -189,20 +189,25 @@ int vb_snac_from_codes(float* d_z, const int32_t* d_codes0, const int32_t* d_cod
                        const float* d_codebooks /*[3][cb_size][cb_dim]*/, const float* d_proj_w /*[3][C][cb_dim]*/,
                        const float* d_proj_b /*[3][C]*/, int B, int C, int T, int cb_size, int cb_dim, int stride0,
                        int stride1, int stride2, void* stream);
-/* y = snake_out?( dwconv_k7_dilated( snake_in?(x) ) + bias );  w [C][7] */
+/* Every stage takes the half-open range of OUTPUT positions to compute (buffers keep their full [.][T] shape):
+ * OrpheusModel.postprocess keeps samples [2048, 4096) of 8192 (orpheus.py:506), so each stage only needs the
+ * receptive field of that slice -- the same values as the full computation at about a third of the work. */
+/* y = snake_out?( dwconv_k7_dilated( snake_in?(x) ) + bias ) on t in [t_lo, t_hi);  w [C][7] */
 int vb_snac_dwconv7(float* d_y, const float* d_x, const float* d_w, const float* d_bias, const float* d_alpha_in,
-                    const float* d_alpha_out, int B, int C, int T, int dilation, void* stream);
+                    const float* d_alpha_out, int B, int C, int T, int dilation, int t_lo, int t_hi, void* stream);
 /* pointwise conv  v = sum_ci W[co][ci] x[b][ci][t] (+ bias[co]);
  * epilogue 0: v ; 1: v + resid[b][co][t] (ResidualUnit, snac.py:170-176) ; 2: x[b][co][t] + noise[b][t] * v
  * (NoiseBlock, snac.py:206-212, noise supplied by the caller) ; then snake_out?(.) */
 int vb_snac_pwconv(float* d_y, const float* d_x, const float* d_w /*[Cout][Cin]*/, const float* d_bias,
                    const float* d_resid, const float* d_noise, const float* d_alpha_out, int epilogue, int B,
-                   int Cin, int Cout, int T, void* stream);
+                   int Cin, int Cout, int T, int t_lo, int t_hi, void* stream);
 /* y = snake_out?( conv_transpose1d(x) + bias ), kernel 2*stride, padding ceil(stride/2), output_padding
  * stride%2 (snac.py:222-231); d_w_packed [stride][Cout][2*Cin] with
- * w_packed[r][co][tap*Cin + ci] = W_torch[ci][co][r + tap*stride];  y [B][Cout][T*stride] */
+ * w_packed[r][co][tap*Cin + ci] = W_torch[ci][co][r + tap*stride];  y [B][Cout][T*stride]; outputs at least
+ * [o_lo, o_hi) are written */
 int vb_snac_convtr(float* d_y, const float* d_x, const float* d_w_packed, const float* d_bias,
-                   const float* d_alpha_out, int B, int Cin, int Cout, int T, int stride, void* stream);
+                   const float* d_alpha_out, int B, int Cin, int Cout, int T, int stride, int o_lo, int o_hi,
+                   void* stream);
 /* y[b][t - t0] = tanh(conv_k7(snake_in?(x))[t] + bias), Cout = 1 (snac.py:152-156), t in [t0, t1) */
 int vb_snac_final(float* d_y, const float* d_x, const float* d_w /*[C][7]*/, const float* d_bias,
                   const float* d_alpha_in, int B, int C, int T, int t0, int t1, void* stream);

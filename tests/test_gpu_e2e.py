@@ -32,3 +32,40 @@ def test_e2e_page128_gqa3():
                                   stop_token_id=128258, audio_id_base=128266)
     _check(__import__("tests.e2e_harness", fromlist=["x"]).run_e2e_parity(
         prompt_lens=(133, 120, 12), n_tokens=36, seed=4, dims=dims, page_size=128, max_pages=16))
+
+
+def test_async_scheduling_matches_sync_schedule_lengths():
+    """Scheduler._step_async ordering (host state one step behind the device): every request still produces the
+    same number of tokens and audio chunks as under the synchronous loop, and PCM sizes agree."""
+    import torch
+
+    from oracle import snac as osnac
+    from tests.e2e_harness import build_models
+    from vox_serve_b200.requests import Request
+    from vox_serve_b200.scheduler import Scheduler
+
+    dims = oorph.OrpheusDims.tiny(vocab_size=156940, stop_token_id=128258, audio_id_base=128266)
+    prompt_lens, n_tokens = (9, 16, 30, 33), 45
+    dims.max_tokens = max(prompt_lens) + n_tokens
+    worker, _ = build_models(dims, osnac.SnacConfig.tiny(), 3, len(prompt_lens), 16, 128)
+    g = torch.Generator().manual_seed(21)
+    prompts = [torch.randint(10, dims.vocab_size, (n - 5,), generator=g).tolist() for n in prompt_lens]
+    out = {}
+    for mode in ("sync", "async"):
+        sched = Scheduler(worker)
+        reqs = [Request(request_id=f"{mode}{i}", prompt=p, model_kwargs={"voice": None}) for i, p in enumerate(prompts)]
+        for r in reqs:
+            sched.submit(r)
+        if mode == "sync":
+            sched.run_until_done(max_steps=4000)
+        else:
+            sched.run_async()
+        torch.cuda.synchronize()
+        assert all(r.done_all for r in reqs), mode
+        out[mode] = [(len(r.lm_output_audio_tokens), [len(c) for c in sched.audio[r.request_id]], r.finish_reason)
+                     for r in reqs]
+        assert worker.empty_pages.qsize() == worker.max_num_pages and len(worker.free_slots) == worker.max_batch_size
+    # the async loop may run one extra LM step per request before it notices max_tokens (reference behaviour)
+    for (ns, cs, fs), (na, ca, fa) in zip(out["sync"], out["async"]):
+        assert fs == fa and 0 <= na - ns <= 1, (ns, na)
+        assert abs(len(ca) - len(cs)) <= 1 and ca[:len(cs) - 1] == cs[:len(cs) - 1]

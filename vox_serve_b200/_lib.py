@@ -47,9 +47,9 @@ SIGNATURES = {
     "vb_apply_repetition_penalty": (c_int, [P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, P]),
     "vb_update_repetition_cache": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_snac_from_codes": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
-    "vb_snac_dwconv7": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
-    "vb_snac_pwconv": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
-    "vb_snac_convtr": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_snac_dwconv7": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_snac_pwconv": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_snac_convtr": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_snac_final": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_pcm16": (c_int, [P, P, c_int64, P]),
     "vb_orpheus_window_codes": (c_int, [P, P, P, P, c_int, c_int, P]),

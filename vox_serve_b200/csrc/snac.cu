@@ -54,9 +54,10 @@ constexpr int DW_TILE = 256;
 __global__ void __launch_bounds__(DW_TILE) dwconv7_kernel(float* __restrict__ y, const float* __restrict__ x,
                                                           const float* __restrict__ w, const float* __restrict__ bias,
                                                           const float* __restrict__ alpha_in,
-                                                          const float* __restrict__ alpha_out, int C, int T, int dil) {
+                                                          const float* __restrict__ alpha_out, int C, int T, int dil,
+                                                          int t_lo, int t_hi) {
   extern __shared__ float tile[];  // DW_TILE + 6*dil
-  const int c = blockIdx.y, b = blockIdx.z, t0 = blockIdx.x * DW_TILE;
+  const int c = blockIdx.y, b = blockIdx.z, t0 = t_lo + blockIdx.x * DW_TILE;
   const float* xr = x + (static_cast<size_t>(b) * C + c) * T;
   const int halo = 3 * dil, n = DW_TILE + 2 * halo;
   const float ain = alpha_in ? alpha_in[c] : 0.f;
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(DW_TILE) dwconv7_kernel(float* __restrict__ y,
   }
   __syncthreads();
   const int t = t0 + threadIdx.x;
-  if (t < T) {
+  if (t < t_hi) {
     float acc = bias ? bias[c] : 0.f;
 #pragma unroll
     for (int k = 0; k < 7; ++k) acc += w[c * 7 + k] * tile[threadIdx.x + k * dil];
@@ -153,14 +154,14 @@ __global__ void __launch_bounds__(256) pwconv_kernel(float* __restrict__ y, cons
                                                      const float* __restrict__ w, const float* __restrict__ bias,
                                                      const float* __restrict__ resid, const float* __restrict__ noise,
                                                      const float* __restrict__ alpha_out, int epi, int Cin, int Cout,
-                                                     int T) {
+                                                     int T, int t_lo, int t_hi) {
   const int b = blockIdx.z;
   const float* xb = x + static_cast<size_t>(b) * Cin * T;
   float* yb = y + static_cast<size_t>(b) * Cout * T;
   const float* rb = resid ? resid + static_cast<size_t>(b) * Cout * T : nullptr;
   const float* nb = noise ? noise + static_cast<size_t>(b) * T : nullptr;
   gemm_tile_f32(
-      w, Cout, Cin, Cin, 0, T, [&](int k, int n) { return xb[static_cast<size_t>(k) * T + n]; },
+      w, Cout, Cin, Cin, t_lo, t_hi, [&](int k, int n) { return xb[static_cast<size_t>(k) * T + n]; },
       [&](int m, int n, float v) {
         if (bias) v += bias[m];
         if (epi == 1) v += rb[static_cast<size_t>(m) * T + n];
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(256) pwconv_kernel(float* __restrict__ y, cons
 __global__ void __launch_bounds__(256) convtr_kernel(float* __restrict__ y, const float* __restrict__ x,
                                                      const float* __restrict__ wp, const float* __restrict__ bias,
                                                      const float* __restrict__ alpha_out, int Cin, int Cout, int T,
-                                                     int s, int pad) {
+                                                     int s, int pad, int n_lo, int n_hi) {
   const int r = blockIdx.z % s, b = blockIdx.z / s;
   const int Tout = T * s;
   const float* xb = x + static_cast<size_t>(b) * Cin * T;
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(256) convtr_kernel(float* __restrict__ y, cons
   const float* wr = wp + static_cast<size_t>(r) * Cout * 2 * Cin;
   // ti ranges over [0, T]: ti = T only receives the tap-1 term (x[T-1])
   gemm_tile_f32(
-      wr, Cout, 2 * Cin, 2 * Cin, 0, T + 1,
+      wr, Cout, 2 * Cin, 2 * Cin, n_lo, n_hi,
       [&](int k, int n) {
         const int tap = k >= Cin, ci = k - tap * Cin, ti = n - tap;
         return (ti >= 0 && ti < T) ? xb[static_cast<size_t>(ci) * T + ti] : 0.f;
@@ -250,42 +251,52 @@ int vb_snac_from_codes(float* d_z, const int32_t* d_codes0, const int32_t* d_cod
 }
 
 int vb_snac_dwconv7(float* d_y, const float* d_x, const float* d_w, const float* d_bias, const float* d_alpha_in,
-                    const float* d_alpha_out, int B, int C, int T, int dilation, void* stream) {
+                    const float* d_alpha_out, int B, int C, int T, int dilation, int t_lo, int t_hi, void* stream) {
   VB_CHECK_ARG(d_y && d_x && d_w, "vb_snac_dwconv7: null pointer");
   VB_CHECK_ARG(dilation >= 1 && dilation <= 64, "vb_snac_dwconv7: dilation %d", dilation);
-  if (B <= 0) return 0;
+  VB_CHECK_ARG(0 <= t_lo && t_lo <= t_hi && t_hi <= T, "vb_snac_dwconv7: range [%d, %d) outside [0, %d)", t_lo, t_hi, T);
+  if (B <= 0 || t_lo == t_hi) return 0;
   const size_t smem = (DW_TILE + 6 * dilation) * sizeof(float);
-  dwconv7_kernel<<<dim3((T + DW_TILE - 1) / DW_TILE, C, B), DW_TILE, smem, static_cast<cudaStream_t>(stream)>>>(
-      d_y, d_x, d_w, d_bias, d_alpha_in, d_alpha_out, C, T, dilation);
+  dwconv7_kernel<<<dim3((t_hi - t_lo + DW_TILE - 1) / DW_TILE, C, B), DW_TILE, smem, static_cast<cudaStream_t>(stream)>>>(
+      d_y, d_x, d_w, d_bias, d_alpha_in, d_alpha_out, C, T, dilation, t_lo, t_hi);
   VB_CHECK_LAUNCH();
   return 0;
 }
 
 int vb_snac_pwconv(float* d_y, const float* d_x, const float* d_w, const float* d_bias, const float* d_resid,
                    const float* d_noise, const float* d_alpha_out, int epilogue, int B, int Cin, int Cout, int T,
-                   void* stream) {
+                   int t_lo, int t_hi, void* stream) {
   VB_CHECK_ARG(d_y && d_x && d_w, "vb_snac_pwconv: null pointer");
   VB_CHECK_ARG(epilogue >= 0 && epilogue <= 2, "vb_snac_pwconv: epilogue %d", epilogue);
   VB_CHECK_ARG(epilogue != 1 || d_resid, "vb_snac_pwconv: residual epilogue needs d_resid");
   VB_CHECK_ARG(epilogue != 2 || (d_noise && Cin == Cout), "vb_snac_pwconv: noise epilogue needs noise and Cin == Cout");
   VB_CHECK_ARG(Cin % 4 == 0, "vb_snac_pwconv: Cin must be a multiple of 4");
-  if (B <= 0) return 0;
-  pwconv_kernel<<<dim3((T + GB_N - 1) / GB_N, (Cout + GB_M - 1) / GB_M, B), 256, 0,
+  VB_CHECK_ARG(0 <= t_lo && t_lo <= t_hi && t_hi <= T, "vb_snac_pwconv: range [%d, %d) outside [0, %d)", t_lo, t_hi, T);
+  if (B <= 0 || t_lo == t_hi) return 0;
+  pwconv_kernel<<<dim3((t_hi - t_lo + GB_N - 1) / GB_N, (Cout + GB_M - 1) / GB_M, B), 256, 0,
                   static_cast<cudaStream_t>(stream)>>>(d_y, d_x, d_w, d_bias, d_resid, d_noise, d_alpha_out, epilogue,
-                                                       Cin, Cout, T);
+                                                       Cin, Cout, T, t_lo, t_hi);
   VB_CHECK_LAUNCH();
   return 0;
 }
 
 int vb_snac_convtr(float* d_y, const float* d_x, const float* d_w_packed, const float* d_bias,
-                   const float* d_alpha_out, int B, int Cin, int Cout, int T, int stride, void* stream) {
+                   const float* d_alpha_out, int B, int Cin, int Cout, int T, int stride, int o_lo, int o_hi,
+                   void* stream) {
   VB_CHECK_ARG(d_y && d_x && d_w_packed, "vb_snac_convtr: null pointer");
   VB_CHECK_ARG(stride >= 1 && Cin % 2 == 0, "vb_snac_convtr: bad dims");
-  if (B <= 0) return 0;
+  VB_CHECK_ARG(0 <= o_lo && o_lo <= o_hi && o_hi <= T * stride, "vb_snac_convtr: output range [%d, %d) outside [0, %d)",
+               o_lo, o_hi, T * stride);
+  if (B <= 0 || o_lo == o_hi) return 0;
   const int pad = (stride + 1) / 2;
-  convtr_kernel<<<dim3((T + 1 + GB_N - 1) / GB_N, (Cout + GB_M - 1) / GB_M, B * stride), 256, 0,
+  // input positions n in [0, T] whose outputs n*stride + r - pad (r < stride) fall inside [o_lo, o_hi)
+  int n_lo = (o_lo + pad - (stride - 1)) / stride;
+  if (o_lo + pad - (stride - 1) < 0) n_lo = 0;
+  int n_hi = (o_hi - 1 + pad) / stride + 1;
+  if (n_hi > T + 1) n_hi = T + 1;
+  convtr_kernel<<<dim3((n_hi - n_lo + GB_N - 1) / GB_N, (Cout + GB_M - 1) / GB_M, B * stride), 256, 0,
                   static_cast<cudaStream_t>(stream)>>>(d_y, d_x, d_w_packed, d_bias, d_alpha_out, Cin, Cout, T, stride,
-                                                       pad);
+                                                       pad, n_lo, n_hi);
   VB_CHECK_LAUNCH();
   return 0;
 }

@@ -128,6 +128,45 @@ class Scheduler:
         self.steps += 1
         return len(lm_requests), len(detokenize_requests)
 
+    def _step_async(self, task, lm_requests: List[Request], detokenize_requests: List[Request]):
+        """``Scheduler._step_async`` (scheduler/base.py:168-215): launch this step's model work first, THEN finish
+        the previous step's request-state update and select the next step's requests, so the host's bookkeeping
+        overlaps the device.  Request state therefore lags one step behind the device, exactly as in the
+        reference's ``--async-scheduling`` mode."""
+        self._prepare_requests()
+        w = self.model_worker
+        lm_inputs = w.prepare_lm_inputs(lm_requests, detokenize_requests)
+        # ---- run_model ----
+        w.run_detokenize(detokenize_requests)
+        self._send_responses(detokenize_requests)
+        if lm_inputs is not None and lm_inputs["is_prefill"]:
+            next_task = w.run_lm_prefill(lm_requests, lm_inputs)
+        else:
+            next_task = w.run_lm_decode(lm_requests, lm_inputs)
+        # ---- run_scheduling ----
+        if task is not None:
+            while True:
+                try:
+                    task.send(None)
+                except StopIteration:
+                    break
+        if self.trace is not None:
+            self.trace.append([(r.request_id, None) for r in lm_requests])
+        next_detokenize_requests = self._select_detokenize_requests()
+        next_lm_requests = self._select_lm_requests()
+        self.steps += 1
+        return next_task, next_lm_requests, next_detokenize_requests
+
+    def run_async(self, n_steps: Optional[int] = None, state=None):
+        """Drive ``_step_async`` (scheduler/base.py:217-221); returns the carried (task, lm, detokenize) state so
+        the loop can be continued."""
+        task, lm, det = state if state is not None else (None, [], [])
+        n = 0
+        while (n_steps is None and (self.has_work() or task is not None)) or (n_steps is not None and n < n_steps):
+            task, lm, det = self._step_async(task, lm, det)
+            n += 1
+        return task, lm, det
+
     def has_work(self) -> bool:
         return bool(self.pending) or any(not r.done_all for r in self.active_requests)
 

@@ -156,11 +156,37 @@ class SNAC:
             out.append((batch, 1, t))
         return out
 
+    def _stage_ranges(self, t_latent: int, out_range):
+        """Receptive field of the kept output slice, walked backwards through the decoder: for every DecoderBlock
+        the output ranges its stages must cover (all half-open, clamped).  Returns a list, first block first, of
+        (convtr_out, [unit0, unit1, unit2]) plus the final conv's input range."""
+        rates = self.decoder_rates
+        lens = [t_latent]
+        for s in rates:
+            lens.append(lens[-1] * s)
+        lo, hi = out_range
+        lo, hi = max(0, lo - 3), min(lens[-1], hi + 3)          # final conv k7, padding 3
+        blocks = [None] * len(rates)
+        for b in reversed(range(len(rates))):
+            T = lens[b + 1]
+            units = [None] * 3
+            cur = (lo, hi)
+            for j, dil in reversed(list(enumerate((1, 3, 9)))):
+                units[j] = cur                                    # unit j output (and its depthwise conv) range
+                cur = (max(0, cur[0] - 3 * dil), min(T, cur[1] + 3 * dil))
+            blocks[b] = (cur, units)                              # cur: convtr / NoiseBlock output range
+            s = rates[b]
+            pad = (s + 1) // 2
+            lo = max(0, (cur[0] + pad - (2 * s - 1)) // s)        # ConvTranspose1d taps: to = ti*s - pad + k
+            hi = min(lens[b], (cur[1] - 1 + pad) // s + 1)
+        return blocks, (lo, hi)
+
     @torch.no_grad()
     def decode(self, codes: List[torch.Tensor], noises: Optional[Sequence[torch.Tensor]] = None,
                out_range: Optional[Sequence[int]] = None) -> torch.Tensor:
         """codes: 3 int tensors [B, T/stride_i] -> waveform [B, 1, T*prod(rates)] fp32 (snac.py:438-441).
-        out_range=(t0, t1) returns only those samples (what OrpheusModel.postprocess keeps, orpheus.py:506)."""
+        out_range=(t0, t1) returns only those samples (what OrpheusModel.postprocess keeps, orpheus.py:506) and
+        computes only their receptive field in every stage -- bit-identical to slicing the full decode."""
         if not self.loaded:
             raise VoxB200Error("SNAC weights not loaded")
         w, st = self.w, ops._stream()
@@ -169,6 +195,9 @@ class SNAC:
         B = c[0].shape[0]
         T = c[-1].shape[1] * self.vq_strides[-1]
         C = self.latent_dim
+        T_out = T * math.prod(self.decoder_rates)
+        t0, t1 = (0, T_out) if out_range is None else (int(out_range[0]), int(out_range[1]))
+        blocks, (in_lo, in_hi) = self._stage_ranges(T, (t0, t1))
         f32 = dict(dtype=torch.float32, device=dev)
         z = torch.empty(B, C, T, **f32)
         call("vb_snac_from_codes", z.data_ptr(), c[0].data_ptr(), c[1].data_ptr(), c[2].data_ptr(),
@@ -176,33 +205,35 @@ class SNAC:
              self.codebook_size, self.codebook_dim, *self.vq_strides, st)
         x = torch.empty_like(z)
         call("vb_snac_dwconv7", x.data_ptr(), z.data_ptr(), w["in_dw_w"].data_ptr(), w["in_dw_b"].data_ptr(), None,
-             None, B, C, T, 1, st)
+             None, B, C, T, 1, in_lo, in_hi, st)
         ch = self.decoder_dim
         y = torch.empty(B, ch, T, **f32)
         # 1x1 conv 768 -> 1024; its output only feeds block 0's Snake -> fuse that Snake here
         call("vb_snac_pwconv", y.data_ptr(), x.data_ptr(), w["in_pw_w"].data_ptr(), w["in_pw_b"].data_ptr(), None,
-             None, w["b0.alpha"].data_ptr(), 0, B, C, ch, T, st)
+             None, w["b0.alpha"].data_ptr(), 0, B, C, ch, T, in_lo, in_hi, st)
         x = y
         nb = len(self.decoder_rates)
         if noises is None:
             shapes = self.noise_shapes(B, T)
             noises = self.noise_source(shapes) if self.noise_source is not None else [torch.randn(s, **f32) for s in shapes]
         for bi, s in enumerate(self.decoder_rates):
+            (c_lo, c_hi), units = blocks[bi]
             cin, cout = ch, ch // 2
             u = torch.empty(B, cout, T * s, **f32)
             call("vb_snac_convtr", u.data_ptr(), x.data_ptr(), w[f"b{bi}.ct_w"].data_ptr(),
-                 w[f"b{bi}.ct_b"].data_ptr(), None, B, cin, cout, T, s, st)
+                 w[f"b{bi}.ct_b"].data_ptr(), None, B, cin, cout, T, s, c_lo, c_hi, st)
             T *= s
             nz = noises[bi].to(device=dev, dtype=torch.float32).contiguous()
             assert nz.numel() == B * T, "noise tensor shape mismatch"
             x = torch.empty_like(u)
             call("vb_snac_pwconv", x.data_ptr(), u.data_ptr(), w[f"b{bi}.noise_w"].data_ptr(), None, None,
-                 nz.data_ptr(), None, 2, B, cout, cout, T, st)
+                 nz.data_ptr(), None, 2, B, cout, cout, T, c_lo, c_hi, st)
             for j, dil in enumerate((1, 3, 9)):
+                u_lo, u_hi = units[j]
                 h = torch.empty_like(x)
                 call("vb_snac_dwconv7", h.data_ptr(), x.data_ptr(), w[f"b{bi}.r{j}.dw_w"].data_ptr(),
                      w[f"b{bi}.r{j}.dw_b"].data_ptr(), w[f"b{bi}.r{j}.alpha1"].data_ptr(),
-                     w[f"b{bi}.r{j}.alpha2"].data_ptr(), B, cout, T, dil, st)
+                     w[f"b{bi}.r{j}.alpha2"].data_ptr(), B, cout, T, dil, u_lo, u_hi, st)
                 # the last unit's output only feeds the next stage's Snake: fuse it into this epilogue
                 nxt = None
                 if j == 2:
@@ -210,10 +241,9 @@ class SNAC:
                 o = torch.empty_like(x)
                 call("vb_snac_pwconv", o.data_ptr(), h.data_ptr(), w[f"b{bi}.r{j}.pw_w"].data_ptr(),
                      w[f"b{bi}.r{j}.pw_b"].data_ptr(), x.data_ptr(), None, None if nxt is None else nxt.data_ptr(),
-                     1, B, cout, cout, T, st)
+                     1, B, cout, cout, T, u_lo, u_hi, st)
                 x = o
             ch = cout
-        t0, t1 = (0, T) if out_range is None else (int(out_range[0]), int(out_range[1]))
         wav = torch.empty(B, 1, t1 - t0, **f32)
         call("vb_snac_final", wav.data_ptr(), x.data_ptr(), w["out.w"].data_ptr(), w["out.b"].data_ptr(), None, B,
              ch, T, t0, t1, st)

@@ -175,6 +175,9 @@ class ModelWorker:
         self.win_dev = torch.zeros(3, self.max_chunks, dtype=I32, device=dev)
         self.pcm_host = torch.zeros(self.max_chunks, m.n_channels, m.output_audio_length, dtype=torch.int16,
                                     pin_memory=True)
+        # the vocoder runs on its own stream: it only needs tokens the host has already seen, so it does not have to
+        # queue behind the LM step that is still in flight when the scheduler runs one step ahead
+        self.detok_stream = torch.cuda.Stream()
         self.gpu_launches = 0     # launches issued by this worker's own kernels (graph nodes counted at capture)
         self._graph_nodes: Dict[int, int] = {}
 
@@ -349,12 +352,17 @@ class ModelWorker:
                 n += 1
         if n:
             self.nvtx_range_push(f"detokenize_bs{n}")
-            self.win_dev.copy_(self.win_host, non_blocking=True)
-            windows = ops.gather_windows(self.history, self.win_dev[0], self.win_dev[1], self.win_dev[2], interval, n=n)
-            audio = self.model.postprocess(windows.view(n, interval, 1))
-            pcm = ops.pcm16(audio)
-            self.pcm_host[:n].copy_(pcm, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            ds = self.detok_stream
+            # no cross-stream wait: every token a window refers to has already been read back by the host (its
+            # step's ids-ready event was synchronised), so the history writes of those steps are complete
+            with torch.cuda.stream(ds):
+                self.win_dev.copy_(self.win_host, non_blocking=True)
+                windows = ops.gather_windows(self.history, self.win_dev[0], self.win_dev[1], self.win_dev[2], interval,
+                                             n=n)
+                audio = self.model.postprocess(windows.view(n, interval, 1))
+                pcm = ops.pcm16(audio)
+                self.pcm_host[:n].copy_(pcm, non_blocking=True)
+            ds.synchronize()
             self.nvtx_range_pop()
             pcm_np = self.pcm_host.numpy()
             for i, (ri, ci, n_valid) in enumerate(mapping):
