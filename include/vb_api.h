@@ -110,8 +110,11 @@ int vb_paged_attn(void* d_out, const void* d_q, const void* d_kv, int64_t slab_b
  * mode 2: W rows interleaved per 128-tile as 64 gate rows then 64 up rows; Y bf16 [T][ldy] holds
  *         silu(gate)*up with the reference's bf16 rounding points (orpheus.py:46-48), N_out = N/2. */
 int vb_gemm_t_tile(int T);
+/* d_prefetch / prefetch_bytes (optional): a byte range -- normally the weights of the projection that runs next --
+ * that the kernel's idle epilogue warps pull into L2 (cp.async.bulk.prefetch.L2) while the accumulators are being
+ * produced, so that HBM keeps streaming across kernel boundaries. */
 int vb_gemm_bf16(void* d_y, const void* w_map, const void* x_map, int T, int N, int K, int ldy, int mode,
-                 int split_k, void* stream);
+                 int split_k, const void* d_prefetch, size_t prefetch_bytes, void* stream);
 
 /* sum split-K partials -> bf16 Linear output; + residual; then RMSNorm of the new hidden state:
  * orpheus.py:125-151 (residual adds, next layer's input_layernorm / post_attention_layernorm).

@@ -36,7 +36,7 @@ SIGNATURES = {
     "vb_paged_attn": (c_int, [P, P, P, c_int64, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_float, P, c_size_t, c_int, c_int, P]),
     "vb_gemm_t_tile": (c_int, [c_int]),
-    "vb_gemm_bf16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_gemm_bf16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_size_t, P]),
     "vb_reduce_residual_rmsnorm": (c_int, [P, P, P, c_int, P, P, c_int, c_int, c_float, P]),
     "vb_qkv_rope_append": (c_int, [P, P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_embedding": (c_int, [P, P, P, c_int, c_int, c_int, P]),

@@ -44,25 +44,44 @@ constexpr int VB_MAX_DYN_SMEM = 227 * 1024;
 // k+1 starts every kernel <= k-1 has completed: pre-wait code may read anything but k's outputs.
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                                 bool pdl, Args... args) {
+inline cudaError_t launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                         cudaStream_t stream, bool pdl, int cluster_x, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl && pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 bool pdl, Args... args) {
+  return launch_kernel_cluster(kernel, grid, block, smem, stream, pdl, 1, args...);
 }
 // launch as a programmatic dependent of the previous kernel in the stream / as a plain launch (after a memset,
 // or for kernels that do not call pdl_wait)
 #define VB_LAUNCH_PDL(kernel, grid, block, smem, stream, ...)                                                \
   VB_CHECK_CUDA(::vb::launch_kernel(kernel, dim3(grid), dim3(block), smem, static_cast<cudaStream_t>(stream), \
                                     true, __VA_ARGS__))
+#define VB_LAUNCH_PDL_CLUSTER(kernel, grid, block, smem, stream, cluster_x, ...)                                      \
+  VB_CHECK_CUDA(::vb::launch_kernel_cluster(kernel, dim3(grid), dim3(block), smem, static_cast<cudaStream_t>(stream), \
+                                            true, cluster_x, __VA_ARGS__))
 #define VB_LAUNCH_PLAIN(kernel, grid, block, smem, stream, ...)                                              \
   VB_CHECK_CUDA(::vb::launch_kernel(kernel, dim3(grid), dim3(block), smem, static_cast<cudaStream_t>(stream), \
                                     false, __VA_ARGS__))
@@ -104,6 +123,52 @@ __device__ __forceinline__ bool elect_one() {
       "{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
       : "=r"(pred));
   return pred != 0;
+}
+
+// L2 prefetch of a linear byte range (fire and forget; size multiple of 16, 16-byte aligned address)
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(p)), "r"(bytes)
+               : "memory");
+}
+// This CTA's share of a [base, base + bytes) prefetch, issued by `nthreads` cooperating threads (index `t`) in
+// 8 KiB pieces.  Used to pull the NEXT projection's weights into L2 while the current kernel is not using HBM.
+__device__ __forceinline__ void prefetch_l2_slice(const void* base, size_t bytes, int cta, int n_ctas, int t,
+                                                  int nthreads) {
+  if (base == nullptr || bytes == 0) return;
+  constexpr size_t PIECE = 8192;
+  const size_t n_pieces = (bytes + PIECE - 1) / PIECE;
+  const size_t per_cta = (n_pieces + n_ctas - 1) / n_ctas;
+  const size_t p0 = static_cast<size_t>(cta) * per_cta, p1 = min(n_pieces, p0 + per_cta);
+  const char* b = static_cast<const char*>(base);
+  for (size_t i = p0 + t; i < p1; i += nthreads) {
+    const size_t off = i * PIECE;
+    const size_t len = min(PIECE, bytes - off) & ~static_cast<size_t>(15);
+    if (len) prefetch_l2(b + off, static_cast<uint32_t>(len));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// thread-block cluster helpers (distributed shared memory)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, uint32_t cta_rank) {
+  uint32_t laddr = static_cast<uint32_t>(__cvta_generic_to_shared(local_ptr)), raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(cta_rank));
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(raddr) : "memory");
+  return v;
 }
 
 // ---------------------------------------------------------------------------------------------

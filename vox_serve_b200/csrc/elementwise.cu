@@ -212,78 +212,113 @@ __global__ void kv_append_kernel(__nv_bfloat16* __restrict__ kv, const __nv_bflo
 // ------------------------------------------------------------------------------------------
 // split-K reduce + residual + RMSNorm (orpheus.py:125-151 rounding points)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) reduce_residual_rmsnorm_kernel(
+// One row is split over the CTAs of a thread-block cluster (blockIdx.x = part): every CTA reduces N / parts
+// columns with all partial loads in flight at once, the row's sum of squares is exchanged through distributed
+// shared memory, and each CTA normalises its own columns.  (One CTA per row left 116 SMs idle and serialised
+// ~70 KB of dependent loads per CTA: 10 us for 400 KB of traffic.)
+constexpr int RR_THREADS = 256;
+constexpr int RR_MAX_ITER = 4;      // columns per CTA <= RR_THREADS * 4 * RR_MAX_ITER
+__global__ void __launch_bounds__(RR_THREADS) reduce_residual_rmsnorm_kernel(
     __nv_bfloat16* __restrict__ hidden_out, __nv_bfloat16* __restrict__ normed_out,
     const float* __restrict__ partials, int split_k, const __nv_bfloat16* __restrict__ residual,
     const __nv_bfloat16* __restrict__ norm_w, int T, int N, float eps) {
   pdl_sync();
-  extern __shared__ float hs[];  // N floats
   __shared__ float red[32];
-  const size_t t = blockIdx.x;
+  __shared__ float part_ss;
+  const int parts = gridDim.x, part = blockIdx.x;
+  const size_t t = blockIdx.y;
+  const int cols = N / parts, c0 = part * cols;
   const size_t plane = static_cast<size_t>(T) * N;
+  float h[RR_MAX_ITER][4];
   float ss = 0.f;
-  for (int n = threadIdx.x * 4; n < N; n += blockDim.x * 4) {
-    float4 acc = *reinterpret_cast<const float4*>(partials + t * N + n);
-    for (int s = 1; s < split_k; ++s) {
-      const float4 p = *reinterpret_cast<const float4*>(partials + s * plane + t * N + n);
-      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
-    }
-    float h[4] = {round_bf16(acc.x), round_bf16(acc.y), round_bf16(acc.z), round_bf16(acc.w)};
-    if (residual) {
-      const uint2 r = *reinterpret_cast<const uint2*>(residual + t * N + n);
-      h[0] = round_bf16(bf16_lo(r.x) + h[0]);
-      h[1] = round_bf16(bf16_hi(r.x) + h[1]);
-      h[2] = round_bf16(bf16_lo(r.y) + h[2]);
-      h[3] = round_bf16(bf16_hi(r.y) + h[3]);
-    }
-    if (hidden_out) {
-      uint2 o;
-      o.x = pack_bf16(h[0], h[1]);
-      o.y = pack_bf16(h[2], h[3]);
-      *reinterpret_cast<uint2*>(hidden_out + t * N + n) = o;
-    }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      hs[n + j] = h[j];
-      ss += h[j] * h[j];
+  for (int it = 0; it < RR_MAX_ITER; ++it) {
+    const int n = c0 + (it * RR_THREADS + threadIdx.x) * 4;
+    if (n < c0 + cols) {
+      const float* src = partials + t * N + n;
+      float4 acc = *reinterpret_cast<const float4*>(src);
+#pragma unroll 8
+      for (int s = 1; s < split_k; ++s) {
+        const float4 p4 = *reinterpret_cast<const float4*>(src + s * plane);
+        acc.x += p4.x; acc.y += p4.y; acc.z += p4.z; acc.w += p4.w;
+      }
+      h[it][0] = round_bf16(acc.x); h[it][1] = round_bf16(acc.y);
+      h[it][2] = round_bf16(acc.z); h[it][3] = round_bf16(acc.w);
+      if (residual) {
+        const uint2 r = *reinterpret_cast<const uint2*>(residual + t * N + n);
+        h[it][0] = round_bf16(bf16_lo(r.x) + h[it][0]);
+        h[it][1] = round_bf16(bf16_hi(r.x) + h[it][1]);
+        h[it][2] = round_bf16(bf16_lo(r.y) + h[it][2]);
+        h[it][3] = round_bf16(bf16_hi(r.y) + h[it][3]);
+      }
+      if (hidden_out) {
+        uint2 o;
+        o.x = pack_bf16(h[it][0], h[it][1]);
+        o.y = pack_bf16(h[it][2], h[it][3]);
+        *reinterpret_cast<uint2*>(hidden_out + t * N + n) = o;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ss += h[it][j] * h[it][j];
     }
   }
-  if (!normed_out) return;
+  if (!normed_out) return;      // uniform across the cluster: no barrier is pending
   ss = block_sum(ss, red);
-  const float rcp = rsqrtf(ss / static_cast<float>(N) + eps);
-  for (int n = threadIdx.x * 2; n < N; n += blockDim.x * 2) {
-    const uint32_t w = *reinterpret_cast<const uint32_t*>(norm_w + n);
-    *reinterpret_cast<uint32_t*>(normed_out + t * N + n) =
-        pack_bf16(hs[n] * rcp * bf16_lo(w), hs[n + 1] * rcp * bf16_hi(w));
+  if (threadIdx.x == 0) part_ss = ss;
+  float total = ss;
+  if (parts > 1) {
+    cluster_sync_all();          // every CTA's part_ss is written
+    total = 0.f;
+    for (int r = 0; r < parts; ++r) total += ld_dsmem_f32(&part_ss, r);   // same order in every CTA
+    cluster_sync_all();          // nobody exits while its shared memory may still be read
+  }
+  const float rcp = rsqrtf(total / static_cast<float>(N) + eps);
+#pragma unroll
+  for (int it = 0; it < RR_MAX_ITER; ++it) {
+    const int n = c0 + (it * RR_THREADS + threadIdx.x) * 4;
+    if (n < c0 + cols) {
+      const uint2 w2 = *reinterpret_cast<const uint2*>(norm_w + n);
+      uint2 o;
+      o.x = pack_bf16(h[it][0] * rcp * bf16_lo(w2.x), h[it][1] * rcp * bf16_hi(w2.x));
+      o.y = pack_bf16(h[it][2] * rcp * bf16_lo(w2.y), h[it][3] * rcp * bf16_hi(w2.y));
+      *reinterpret_cast<uint2*>(normed_out + t * N + n) = o;
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// fused QKV tail: reduce partials -> bf16, RoPE(q, k), q out, K/V scatter into the layer cache
+// fused QKV tail: reduce partials -> bf16, RoPE(q, k), q out, K/V scatter into the layer cache.
+// Heads are independent, so a row is split over gridDim.x CTAs by groups of heads (blockIdx.x).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) qkv_rope_append_kernel(
     __nv_bfloat16* __restrict__ q_out, __nv_bfloat16* __restrict__ kv, const float* __restrict__ partials,
     int split_k, const int32_t* __restrict__ pos, const float* __restrict__ freq,
     const int32_t* __restrict__ row_page, const int32_t* __restrict__ row_slot, int T, int n_q, int n_kv, int D,
-    int page_size, int rotary_dim, int interleave) {
+    int page_size, int rotary_dim, int interleave, int heads_per_cta) {
   pdl_sync();
-  extern __shared__ float sm[];  // [2*rotary_dim cos/sin][(n_q+2n_kv)*D values]
+  extern __shared__ float sm[];  // [2*rotary_dim cos/sin][heads_per_cta * D values]
   float* cs = sm;
   float* val = sm + 2 * rotary_dim;
-  const size_t t = blockIdx.x;
-  const int W = (n_q + 2 * n_kv) * D;
+  const size_t t = blockIdx.y;
+  const int n_heads = n_q + 2 * n_kv;
+  const int h_lo = blockIdx.x * heads_per_cta, h_hi = min(n_heads, h_lo + heads_per_cta);
+  if (h_lo >= h_hi) return;
+  const int W = n_heads * D, w_lo = h_lo * D, w_n = (h_hi - h_lo) * D;
   const size_t plane = static_cast<size_t>(T) * W;
   const float p = static_cast<float>(pos[t]);
-  for (int e = threadIdx.x; e < rotary_dim; e += blockDim.x) {
-    float s, c;
-    sincosf(p * freq[e], &s, &c);
-    cs[e] = c;
-    cs[rotary_dim + e] = s;
+  if (h_lo < n_q + n_kv) {       // groups made only of V heads need no rotation table
+    for (int e = threadIdx.x; e < rotary_dim; e += blockDim.x) {
+      float s, c;
+      sincosf(p * freq[e], &s, &c);
+      cs[e] = c;
+      cs[rotary_dim + e] = s;
+    }
   }
-  for (int n = threadIdx.x * 4; n < W; n += blockDim.x * 4) {
-    float4 acc = *reinterpret_cast<const float4*>(partials + t * W + n);
+  for (int n = threadIdx.x * 4; n < w_n; n += blockDim.x * 4) {
+    const float* src = partials + t * W + w_lo + n;
+    float4 acc = *reinterpret_cast<const float4*>(src);
+#pragma unroll 4
     for (int s = 1; s < split_k; ++s) {
-      const float4 q4 = *reinterpret_cast<const float4*>(partials + s * plane + t * W + n);
+      const float4 q4 = *reinterpret_cast<const float4*>(src + s * plane);
       acc.x += q4.x; acc.y += q4.y; acc.z += q4.z; acc.w += q4.w;
     }
     val[n] = round_bf16(acc.x);
@@ -297,15 +332,16 @@ __global__ void __launch_bounds__(256) qkv_rope_append_kernel(
   const size_t slab = static_cast<size_t>(page_size) * row_elems;
   __nv_bfloat16* kd = (page >= 0) ? kv + (static_cast<size_t>(page) * 2) * slab + static_cast<size_t>(row_slot[t]) * row_elems
                                    : nullptr;
-  for (int i = threadIdx.x * 2; i < W; i += blockDim.x * 2) {
-    const int h = i / D, e = i - h * D;
-    float v0 = val[i], v1 = val[i + 1];
+  for (int il = threadIdx.x * 2; il < w_n; il += blockDim.x * 2) {
+    const int hl = il / D, e = il - hl * D;
+    const int h = h_lo + hl, i = w_lo + il;
+    float v0 = val[il], v1 = val[il + 1];
     if (h < n_q + n_kv && e < rotary_dim) {
       float s0, s1;
       const int p0 = rope_partner(e, rotary_dim, interleave, s0);
       const int p1 = rope_partner(e + 1, rotary_dim, interleave, s1);
-      v0 = v0 * cs[e] + s0 * val[h * D + p0] * cs[rotary_dim + e];
-      v1 = v1 * cs[e + 1] + s1 * val[h * D + p1] * cs[rotary_dim + e + 1];
+      v0 = v0 * cs[e] + s0 * val[hl * D + p0] * cs[rotary_dim + e];
+      v1 = v1 * cs[e + 1] + s1 * val[hl * D + p1] * cs[rotary_dim + e + 1];
     }
     const uint32_t packed = pack_bf16(v0, v1);
     if (h < n_q) {
@@ -431,14 +467,22 @@ int vb_reduce_residual_rmsnorm(void* d_hidden_out, void* d_normed_out, const flo
                                const void* d_residual, const void* d_norm_weight, int T, int N, float eps,
                                void* stream) {
   VB_CHECK_ARG(d_partials && split_k >= 1, "vb_reduce_residual_rmsnorm: bad partials");
-  VB_CHECK_ARG(N % 4 == 0 && N * sizeof(float) <= 160 * 1024, "vb_reduce_residual_rmsnorm: N %d unsupported", N);
+  VB_CHECK_ARG(N % 4 == 0, "vb_reduce_residual_rmsnorm: N %d must be a multiple of 4", N);
   VB_CHECK_ARG(!d_normed_out || d_norm_weight, "vb_reduce_residual_rmsnorm: norm output needs a weight");
   if (T <= 0) return 0;
-  const size_t smem = static_cast<size_t>(N) * sizeof(float);
-  if (smem > 48 * 1024)
-    VB_CHECK_CUDA(cudaFuncSetAttribute(reduce_residual_rmsnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       VB_MAX_DYN_SMEM));
-  VB_LAUNCH_PDL(reduce_residual_rmsnorm_kernel, T, 256, smem, stream, static_cast<__nv_bfloat16*>(d_hidden_out), static_cast<__nv_bfloat16*>(d_normed_out), d_partials, split_k, static_cast<const __nv_bfloat16*>(d_residual), static_cast<const __nv_bfloat16*>(d_norm_weight), T, N, eps);
+  // widest cluster (<= 8, the portable limit) that divides the row into float4-aligned parts; few rows -> more parts
+  int parts = 1;
+  const int want = T <= 64 ? 8 : (T <= 256 ? 4 : 1);
+  for (int c = want; c >= 1; c >>= 1)
+    if (N % (4 * c) == 0) { parts = c; break; }
+  while (N / parts > RR_THREADS * 4 * RR_MAX_ITER) {
+    VB_CHECK_ARG(parts < 8 && N % (8 * parts) == 0, "vb_reduce_residual_rmsnorm: N %d too wide", N);
+    parts *= 2;
+  }
+  VB_LAUNCH_PDL_CLUSTER(reduce_residual_rmsnorm_kernel, dim3(parts, T), RR_THREADS, 0, stream, parts,
+                        static_cast<__nv_bfloat16*>(d_hidden_out), static_cast<__nv_bfloat16*>(d_normed_out),
+                        d_partials, split_k, static_cast<const __nv_bfloat16*>(d_residual),
+                        static_cast<const __nv_bfloat16*>(d_norm_weight), T, N, eps);
   return 0;
 }
 
@@ -449,13 +493,20 @@ int vb_qkv_rope_append(void* d_q_out, void* d_layer_kv, const float* d_partials,
                "vb_qkv_rope_append: null pointer");
   VB_CHECK_ARG(head_dim % 4 == 0 && rotary_dim % 2 == 0 && rotary_dim <= head_dim, "vb_qkv_rope_append: bad dims");
   if (T <= 0) return 0;
-  const size_t smem = (2 * static_cast<size_t>(rotary_dim) + static_cast<size_t>(n_q + 2 * n_kv) * head_dim) *
+  const int n_heads = n_q + 2 * n_kv;
+  // few rows (decode): spread a row's heads over several CTAs; many rows (prefill): one CTA per row is enough
+  int heads_per_cta = T <= 64 ? 4 : (T <= 256 ? 8 : n_heads);
+  while (static_cast<size_t>(2 * rotary_dim + heads_per_cta * head_dim) * sizeof(float) > 96 * 1024 && heads_per_cta > 1)
+    heads_per_cta /= 2;
+  const int parts = (n_heads + heads_per_cta - 1) / heads_per_cta;
+  const size_t smem = (2 * static_cast<size_t>(rotary_dim) + static_cast<size_t>(heads_per_cta) * head_dim) *
                       sizeof(float);
-  VB_CHECK_ARG(smem <= 200 * 1024, "vb_qkv_rope_append: row too wide for shared memory");
   if (smem > 48 * 1024)
     VB_CHECK_CUDA(cudaFuncSetAttribute(qkv_rope_append_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        VB_MAX_DYN_SMEM));
-  VB_LAUNCH_PDL(qkv_rope_append_kernel, T, 256, smem, stream, static_cast<__nv_bfloat16*>(d_q_out), static_cast<__nv_bfloat16*>(d_layer_kv), d_partials, split_k, d_pos, d_freq, d_row_page, d_row_slot, T, n_q, n_kv, head_dim, page_size, rotary_dim, interleave);
+  VB_LAUNCH_PDL(qkv_rope_append_kernel, dim3(parts, T), 256, smem, stream, static_cast<__nv_bfloat16*>(d_q_out),
+                static_cast<__nv_bfloat16*>(d_layer_kv), d_partials, split_k, d_pos, d_freq, d_row_page, d_row_slot, T,
+                n_q, n_kv, head_dim, page_size, rotary_dim, interleave, heads_per_cta);
   return 0;
 }
 

@@ -20,6 +20,8 @@ constexpr int GEMM_THREADS = 192;
 
 struct GemmParams {
   void* y;
+  const void* next_w;       // weights of the projection that runs after this one: pulled into L2 meanwhile
+  size_t next_bytes;
   int T, N, K, ldy, mode, split_k, t_tile, stages, tmem_cols;
 };
 
@@ -115,6 +117,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
     }
   } else {
     // ================= epilogue: TMEM -> registers -> global =================
+    // while the accumulator is being produced these warps are idle: warp 2 pulls this CTA's share of the NEXT
+    // projection's weights into L2 (weights never depend on a predecessor, so this is legal before any wait)
+    if (warp == 2)
+      prefetch_l2_slice(p.next_w, p.next_bytes, blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z),
+                        gridDim.x * gridDim.y * gridDim.z, lane, 32);
     // (stores happen after the accumulator is complete, i.e. after activation tiles that were only requested
     // once the previous kernel had finished: no explicit wait needed on this path)
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) belong to this warp
@@ -199,7 +206,7 @@ int vb_gemm_t_tile(int T) {
 }
 
 int vb_gemm_bf16(void* d_y, const void* w_map, const void* x_map, int T, int N, int K, int ldy, int mode,
-                 int split_k, void* stream) {
+                 int split_k, const void* d_prefetch, size_t prefetch_bytes, void* stream) {
   VB_CHECK_ARG(d_y && w_map && x_map, "vb_gemm_bf16: null pointer");
   VB_CHECK_ARG(T > 0 && N > 0 && K > 0, "vb_gemm_bf16: empty problem T=%d N=%d K=%d", T, N, K);
   VB_CHECK_ARG(mode >= 0 && mode <= 2, "vb_gemm_bf16: mode %d", mode);
@@ -209,7 +216,7 @@ int vb_gemm_bf16(void* d_y, const void* w_map, const void* x_map, int T, int N, 
   VB_CHECK_ARG(mode == 1 || split_k == 1, "vb_gemm_bf16: split_k > 1 needs mode 1 (fp32 partials)");
   VB_CHECK_ARG(mode != 2 || N % 128 == 0, "vb_gemm_bf16: mode 2 needs N %% 128 == 0 (64 gate + 64 up rows per tile)");
   GemmParams p;
-  p.y = d_y; p.T = T; p.N = N; p.K = K; p.ldy = ldy; p.mode = mode; p.split_k = split_k;
+  p.y = d_y; p.next_w = d_prefetch; p.next_bytes = d_prefetch ? prefetch_bytes : 0; p.T = T; p.N = N; p.K = K; p.ldy = ldy; p.mode = mode; p.split_k = split_k;
   p.t_tile = vb_gemm_t_tile(T);
   int cols = 32;
   while (cols < p.t_tile) cols <<= 1;

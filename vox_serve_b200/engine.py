@@ -153,16 +153,26 @@ class LlamaEngine:
         ops.rmsnorm(hidden, w.layers[0]["ln1"], d.rms_norm_eps, out=normed)
         s_qkv, s_o, s_dn = self._split(self.split_qkv, R), self._split(self.split_o, R), self._split(self.split_down, R)
         q, attn, act = self.q[:R], self.attn[:R], self.act[:R]
+        # Optional: every projection can pull the NEXT projection's weights into L2 (vb_gemm_bf16's d_prefetch).
+        # Measured on B200 (tests/bench_prefetch.py) it is a net loss at these shapes -- the prefetching kernel
+        # slows by 4-10 us, the next one gains only ~2 us because skinny GEMMs are latency-, not bandwidth-bound --
+        # so it stays off.
+        pf = False
+        n_layers = len(w.layers)
         for i, L in enumerate(w.layers):
-            p = ops.gemm(normed, L["qkv"], mode=1, split_k=s_qkv, out=self._partials(s_qkv, R, self.qkv_w))
+            p = ops.gemm(normed, L["qkv"], mode=1, split_k=s_qkv, out=self._partials(s_qkv, R, self.qkv_w),
+                         prefetch=L["o"] if pf else None)
             ops.qkv_rope_append(p, self.kv_cache[i], position_ids, self.freq, plan, hq, hkv, D, q_out=q)
             ops.paged_attn(q, self.kv_map, i * self.pages_per_layer, plan, R, hkv, self.page_size, self.chunk,
                            self.attn_ws, out=attn, grid_ctas=self.attn_grid)
-            p = ops.gemm(attn.view(R, hq * D), L["o"], mode=1, split_k=s_o, out=self._partials(s_o, R, H))
+            p = ops.gemm(attn.view(R, hq * D), L["o"], mode=1, split_k=s_o, out=self._partials(s_o, R, H),
+                         prefetch=L["gu"] if pf else None)
             ops.reduce_residual_rmsnorm(p, hidden, L["ln2"], d.rms_norm_eps, hidden_out=hidden, normed_out=normed)
-            ops.gemm(normed, L["gu"], mode=2, out=act)
-            p = ops.gemm(act, L["down"], mode=1, split_k=s_dn, out=self._partials(s_dn, R, H))
-            nxt = w.layers[i + 1]["ln1"] if i + 1 < len(w.layers) else w.norm
+            ops.gemm(normed, L["gu"], mode=2, out=act, prefetch=L["down"] if pf else None)
+            nxt_w = w.layers[i + 1]["qkv"] if i + 1 < n_layers else w.lm_head
+            p = ops.gemm(act, L["down"], mode=1, split_k=s_dn, out=self._partials(s_dn, R, H),
+                         prefetch=nxt_w if pf else None, prefetch_bytes=min(nxt_w.numel() * 2, 96 << 20))
+            nxt = w.layers[i + 1]["ln1"] if i + 1 < n_layers else w.norm
             ops.reduce_residual_rmsnorm(p, hidden, nxt, d.rms_norm_eps, hidden_out=hidden, normed_out=normed)
         if last_rows is not None:
             n_out = last_rows.numel() if n_out is None else n_out
@@ -171,7 +181,7 @@ class LlamaEngine:
             n_out, x = R, normed
         if n_out > self.max_out_rows:
             raise VoxB200Error(f"logits requested for {n_out} rows; pass last_rows (max {self.max_out_rows})")
-        return ops.gemm(x, w.lm_head, mode=0, out=self.logits[:n_out])
+        return ops.gemm(x, w.lm_head, mode=0, out=self.logits[:n_out], prefetch=w.layers[0]["qkv"] if pf else None)
 
     # ---- kernel-isolated passes for the roofline measurement (bench.py) --------------------------------
     def gemm_pass(self, n_rows: int) -> None:

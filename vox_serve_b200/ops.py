@@ -254,7 +254,8 @@ def choose_split_k(N: int, K: int, T: int, sms: Optional[int] = None) -> int:
 
 
 def gemm(x: torch.Tensor, w: torch.Tensor, mode: int = 0, split_k: int = 1, out: Optional[torch.Tensor] = None,
-         w_map: Optional[TensorMap] = None) -> torch.Tensor:
+         w_map: Optional[TensorMap] = None, prefetch: Optional[torch.Tensor] = None,
+         prefetch_bytes: Optional[int] = None) -> torch.Tensor:
     """x [T, K] bf16, w [N, K] bf16 (nn.Linear.weight layout).
     mode 0 -> bf16 [T, N]; mode 1 -> fp32 partials [split_k, T, N]; mode 2 -> bf16 [T, N/2] = silu(gate)*up
     with w rows interleaved per 128-row tile (see interleave_gate_up)."""
@@ -270,7 +271,12 @@ def gemm(x: torch.Tensor, w: torch.Tensor, mode: int = 0, split_k: int = 1, out:
             out = torch.empty(T, n_out, dtype=BF16, device=x.device)
     w_map = tensor_map_2d(w, 128) if w_map is None else w_map
     x_map = tensor_map_2d(x, gemm_t_tile(T))
-    call("vb_gemm_bf16", out.data_ptr(), w_map.ptr, x_map.ptr, T, N, K, n_out, mode, split_k, _stream())
+    pf_ptr, pf_bytes = None, 0
+    if prefetch is not None:      # the next projection's weights: pulled into L2 by this kernel's idle warps
+        pf_ptr = prefetch.data_ptr()
+        pf_bytes = prefetch.numel() * prefetch.element_size() if prefetch_bytes is None else int(prefetch_bytes)
+    call("vb_gemm_bf16", out.data_ptr(), w_map.ptr, x_map.ptr, T, N, K, n_out, mode, split_k, pf_ptr, pf_bytes,
+         _stream())
     return out
 
 

@@ -50,6 +50,11 @@ class Scheduler:
         for req in self.active_requests:
             if len(out) >= self.max_batch_size:
                 break
+            if req.done_all:
+                # only reachable when running one step ahead (_step_async): the request finished in the step that
+                # was just issued and is dropped at the next _prepare_requests; selecting it again would vocode
+                # its last window twice
+                continue
             nxt = req.next_audio_decode_idx[-1] + step if req.next_audio_decode_idx else 0
             if req.done_lm_generation:
                 if nxt < len(req.lm_output_audio_tokens):
