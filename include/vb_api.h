@@ -165,8 +165,10 @@ int vb_gather_rows(void* d_out, const void* d_in, const int32_t* d_idx, int n, i
  * rep_codebooks != 1 codebook 0 is used (sampling.py:140-141).  Penalty: sampling.py:143-144.
  * strategy: 0 greedy (argmax, first index on ties), 1 top-k, 2 top-p, 3 top-k then top-p, 4 min-p
  * (dispatch order of sampling.py:97-118 is applied by the host wrapper).  out_ids int64.
-* Draws use Philox4x32-10(seed, offset, row); if d_rng_state (device uint64[2] = {seed, offset}) is given it
- * overrides the immediates and its offset is advanced by one per call (CUDA-graph replays stay random).  mask_token >= 0 forces that token's logit to -inf
+* Draws use Philox4x32-10(seed, offset, row, round); if d_rng_state (device uint64[3] = {seed, offset, 0}; the
+ * third word is an arrival counter the kernel returns to 0) is given it overrides the immediates and its offset is
+ * advanced by one per call (CUDA-graph replays stay random).  One launch: a thread-block cluster per row keeps the
+ * row on chip (vocab <= 327680).  mask_token >= 0 forces that token's logit to -inf
  * (benchmark hook to pin sequence lengths; -1 = off).  Workspace: vb_sample_workspace_bytes. */
 size_t vb_sample_workspace_bytes(int rows, int vocab);
 int vb_sample(int64_t* d_out_ids, const void* d_logits, int rows, int vocab, int ld_logits,

@@ -392,6 +392,75 @@ def test_sampler_stochastic_distribution(ops, strategy, kw):
     assert torch.equal(a, b)
 
 
+def _ties_kept(logits_row, cfg):
+    """oracle distribution with the top-p boundary tie group kept whole (bf16 probabilities tie in large groups;
+    the pivot-based kernels -- FlashInfer's and ours -- keep or drop equal probabilities together, torch.sort in
+    the oracle cuts the group at an arbitrary member)"""
+    p_ref = osampler.filtered_probs(logits_row, cfg)[0].double()
+    if cfg.top_p is None:
+        return p_ref
+    import dataclasses
+    p_all = osampler.filtered_probs(logits_row, dataclasses.replace(cfg, top_p=1.0))[0].double()
+    thr = p_all[p_ref > 0].min()
+    out = torch.where(p_all >= thr, p_all, torch.zeros_like(p_all))
+    return out / out.sum()
+
+
+@pytest.mark.parametrize("V", [156940, 168960])      # Orpheus (4-CTA cluster per row), GLM-4-Voice (8-CTA cluster)
+@pytest.mark.parametrize("strategy,kw", [("top_p", dict(top_p=0.8, temperature=0.6)),
+                                          ("top_k", dict(top_k=50, temperature=0.9)),
+                                          ("top_k_top_p", dict(top_k=20, top_p=0.9, temperature=0.8)),
+                                          ("min_p", dict(min_p=0.1, temperature=1.0))])
+def test_sampler_stochastic_full_vocab_cluster(ops, strategy, kw, V):
+    """Full-vocabulary rows live across a thread-block cluster: support and frequencies against the oracle's
+    filtered distribution, with repetition penalty and the slot-indirect cache rows in play."""
+    n = 2048
+    base = (torch.randn(V, generator=g(41)) * 1.5 - 6.0)
+    hot = torch.randperm(V, generator=g(42))[:300]
+    base[hot] = torch.randn(300, generator=g(43)) * 2.0 + 6.0     # the mass sits on 300 tokens spread over all CTAs
+    base = base.to(BF)
+    cache = torch.zeros(2, 1, 1, V, dtype=torch.bool)
+    cache[1, 0, 0, hot[:40]] = True
+    cache[1, 0, 0, torch.randperm(V, generator=g(44))[:2000]] = True
+    cfg = osampler.SamplingConfig(**kw)
+    pen = osampler.apply_repetition_penalty(base.view(1, 1, V), cache[1:2], 1.3).view(1, V)
+    p_ref = _ties_kept(pen, cfg)
+    logits = base.view(1, V).expand(n, V).contiguous().cuda()
+    cache_rows = torch.ones(n, dtype=torch.int32).cuda()
+    ids = ops.sample(logits, strategy, rep_cache=cache.cuda(), penalty=1.3, cache_rows=cache_rows, seed=99, offset=5,
+                     **kw).cpu()
+    counts = torch.bincount(ids, minlength=V).double()
+    assert counts[p_ref == 0].sum().item() == 0, "sampled a filtered-out token"
+    exp = p_ref * n
+    big = exp >= 5
+    chi2 = (((counts - exp) ** 2) / exp.clamp_min(1e-12))[big].sum().item()
+    dof = int(big.sum().item())
+    assert dof >= 5 and chi2 < dof + 6 * math.sqrt(2 * dof) + 10, (chi2, dof)
+    again = ops.sample(logits, strategy, rep_cache=cache.cuda(), penalty=1.3, cache_rows=cache_rows, seed=99, offset=5,
+                       **kw).cpu()
+    assert torch.equal(ids, again)
+
+
+def test_sampler_flat_distribution_top_p_and_rng_state(ops):
+    """Near-uniform logits (what seeded synthetic weights produce): the nucleus is most of the vocabulary, the
+    rejection loop still terminates, and the device RNG state advances by exactly one per call."""
+    V, n = 156940, 64
+    logits = (torch.randn(n, V, generator=g(51)) * 0.5).to(BF)
+    cfg = osampler.SamplingConfig(top_p=0.8, temperature=0.6)
+    keep = torch.stack([_ties_kept(logits[r:r + 1], cfg) > 0 for r in range(4)])
+    st = torch.tensor([1234, 7, 0], dtype=torch.int64).cuda()
+    a = ops.sample(logits.cuda(), "top_p", top_p=0.8, temperature=0.6, rng_state=st).cpu()
+    assert st.cpu().tolist() == [1234, 8, 0]
+    b = ops.sample(logits.cuda(), "top_p", top_p=0.8, temperature=0.6, rng_state=st).cpu()
+    assert st.cpu().tolist() == [1234, 9, 0]
+    assert not torch.equal(a, b)
+    c = ops.sample(logits.cuda(), "top_p", top_p=0.8, temperature=0.6, seed=1234, offset=7).cpu()
+    assert torch.equal(a, c), "device state and immediate (seed, offset) must draw the same stream"
+    for r in range(4):
+        assert bool(keep[r, a[r]]) and bool(keep[r, b[r]])
+    assert len(set(a.tolist())) > n // 2
+
+
 # --------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("tag,cfg", [("tiny", osnac.SnacConfig.tiny()), ("24khz", osnac.SnacConfig())])
 def test_snac_decode_golden(ops, golden_dir, tag, cfg):

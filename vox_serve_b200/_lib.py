@@ -95,7 +95,7 @@ def check(rc: int, what: str = ""):
 
 
 # kernels (+ memset nodes) each entry point enqueues; everything not listed launches exactly one
-LAUNCHES = {"vb_set_pdl": 0, "vb_tensor_map_kv": 0, "vb_tensor_map_2d_bf16": 0, "vb_device_info": 0, "vb_sample": 3,
+LAUNCHES = {"vb_set_pdl": 0, "vb_tensor_map_kv": 0, "vb_tensor_map_2d_bf16": 0, "vb_device_info": 0, "vb_sample": 1,
             "vb_update_repetition_cache": 1}
 launch_counter = [0]
 

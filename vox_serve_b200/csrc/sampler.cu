@@ -3,14 +3,11 @@
 // apply_repetition_penalty, update_repetition_penalty_cache) and the FlashInfer sampling kernels it calls.
 //
 // Exact + deterministic by construction:
-//   * logits are bf16, so after penalty and temperature every token's value is one of 65536 bf16 codes and
-//     every token with the same code has the same (bf16-rounded) probability.  One pass turns a row into a
-//     65536-bin integer histogram (monotone 16-bit key) with L2 reductions spread over the whole GPU; one
-//     CTA per row then scans the histogram from the top: max, softmax denominator, filter thresholds and
-//     the sampled (key, rank) pair.  All sums are integer counts times a per-key fixed-point (Q40) mass, so
-//     the result is independent of thread scheduling; a final pass resolves (key, rank) to the token index.
-//   * greedy is a packed 64-bit atomicMax over (key, ~index): largest value, smallest index on ties, exactly
-//     torch.argmax on the penalised bf16 logits.
+//   * logits are bf16, so after penalty and temperature every token's value is one of 65536 bf16 codes (a
+//     monotone 16-bit key) and every token with the same code has the same bf16-rounded probability;
+//   * one thread-block cluster per row keeps the whole row on chip after a single pass (sample_kernel below):
+//     integer masses, fixed reduction trees, no atomics -- the result does not depend on thread scheduling;
+//   * greedy = largest key, smallest index on ties: exactly torch.argmax on the penalised bf16 logits.
 #include "../../include/vb_api.h"
 #include "common.cuh"
 
@@ -27,10 +24,7 @@ struct SampleParams {
   float top_p, min_p;
   int mask_token;
   uint64_t seed, offset;
-  unsigned long long* rng_state;   // optional device {seed, offset}: offset advances by one per vb_sample call
-  unsigned long long* packed;  // [rows] greedy result
-  uint32_t* hist;              // [rows][65536]
-  uint32_t* pick;              // [rows][2]  (key, rank)
+  unsigned long long* rng_state;   // optional device {seed, offset, arrivals}: offset advances by one per call
   int64_t* out;
 };
 
@@ -60,39 +54,6 @@ __device__ __forceinline__ float token_value(const SampleParams& p, int row, int
   return l;
 }
 
-__global__ void __launch_bounds__(256) argmax_kernel(const SampleParams p) {
-  const int row = blockIdx.y;
-  unsigned long long best = 0ull;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.vocab; i += gridDim.x * blockDim.x) {
-    const float v = token_value(p, row, i, false);
-    if (v != v) continue;  // NaN never wins (torch.argmax would propagate; logits are finite here)
-    const unsigned long long pk =
-        (static_cast<unsigned long long>(bf16_key(v)) << 32) | static_cast<uint32_t>(~static_cast<uint32_t>(i));
-    best = pk > best ? pk : best;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-    best = other > best ? other : best;
-  }
-  if ((threadIdx.x & 31) == 0 && best) atomicMax(&p.packed[row], best);
-}
-
-__global__ void unpack_argmax_kernel(int64_t* out, const unsigned long long* packed, int rows) {
-  pdl_sync();
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < rows) out[r] = static_cast<int64_t>(~static_cast<uint32_t>(packed[r] & 0xffffffffull));
-}
-
-__global__ void __launch_bounds__(256) hist_kernel(const SampleParams p) {
-  const int row = blockIdx.y;
-  uint32_t* h = p.hist + static_cast<size_t>(row) * 65536;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.vocab; i += gridDim.x * blockDim.x) {
-    const float v = token_value(p, row, i, true);
-    atomicAdd(&h[bf16_key(v)], 1u);
-  }
-}
-
 // ---- Philox4x32-10 ----
 __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
   const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
@@ -100,8 +61,8 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
   const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
   c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
 }
-__device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t offset, uint32_t stream) {
-  uint32_t c[4] = {static_cast<uint32_t>(offset), static_cast<uint32_t>(offset >> 32), stream, 0u};
+__device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t offset, uint32_t stream, uint32_t sub) {
+  uint32_t c[4] = {static_cast<uint32_t>(offset), static_cast<uint32_t>(offset >> 32), stream, sub};
   uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
@@ -142,193 +103,270 @@ __device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long
   return res;
 }
 
-constexpr int SCAN_THREADS = 1024;
-constexpr int KEYS_PER_THREAD = 65536 / SCAN_THREADS;   // 64
-constexpr double Q40 = 1099511627776.0;                 // 2^40
+// ---------------------------------------------------------------------------------------------------------
+// One thread-block CLUSTER per row.  The row's tokens are spread over S CTAs x 1024 threads x (2 * PAIRS) tokens;
+// after one pass over the logits (+ repetition cache) every token lives on chip -- its 16-bit value key in a
+// register, its fixed-point probability mass in shared memory -- and everything else is on-chip reductions:
+// block tree -> one DSMEM store per peer CTA -> one cluster barrier.  No histogram, no atomics, no second
+// pass over HBM/L2.
+//   max key -> [top-k: 16-step bisection on counts] -> softmax denominator (fp32, fixed summation tree) ->
+//   mass q_i = floor(bf16(p_i) * 2^32) -> [min-p: direct filter] -> draw by inverse CDF in (cta, thread, slot)
+//   order; top-p by REJECTION: the drawn token j is in the nucleus iff mass{p > p_j} < top_p, otherwise
+//   everything with p <= p_j is discarded and the draw repeats on what is left (acceptance >= top_p per round;
+//   conditional on acceptance the draw is the renormalised nucleus -- the scheme of FlashInfer's sorting-free
+//   sampler, with exact integer masses instead of float partial sums, hence scheduling-independent).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SMP_THREADS = 1024;
+constexpr int SMP_PAIRS = 20;            // 40 tokens per thread: 40960 tokens per CTA, 327680 per 8-CTA cluster
+constexpr int SMP_MAX_CLUSTER = 8;
 
-// One CTA per row.  Thread t owns keys [hi - 63, hi], hi = 65535 - 64 t  (descending value order).
-__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const SampleParams p) {
-  pdl_sync();
-  __shared__ unsigned long long sh[33];
-  __shared__ float sh_f[32];
-  __shared__ int sh_i[4];
-  __shared__ unsigned long long sh_u[4];
-  const int row = blockIdx.x, tid = threadIdx.x;
-  const uint32_t* h = p.hist + static_cast<size_t>(row) * 65536;
-  const int khi = 65535 - KEYS_PER_THREAD * tid;
-
-  // ---- max key (skip NaN codes: keys above +inf / below -inf never produced by finite logits) ----
-  int kmax = -1;
-  for (int j = 0; j < KEYS_PER_THREAD; ++j) {
-    if (h[khi - j] != 0u) { kmax = khi - j; break; }
-  }
-  kmax = __reduce_max_sync(0xffffffffu, kmax);
-  if ((tid & 31) == 0) sh_f[tid >> 5] = __int_as_float(kmax);
-  __syncthreads();
-  if (tid < 32) {
-    int v = __float_as_int(sh_f[tid]);
-    v = __reduce_max_sync(0xffffffffu, v);
-    if (tid == 0) sh_i[0] = v;
-  }
-  __syncthreads();
-  kmax = sh_i[0];
-  const float xmax = key_value(kmax);
-
-  // pass A: un-normalised weights.  strategy 3 first restricts to the top-k keys.
-  auto weight = [&](int k) { return expf(key_value(k) - xmax); };   // fp32 softmax numerator
-  unsigned long long total, excl;
-
-  int k_floor = 0;      // keys below k_floor are filtered out before the softmax (top-k-first, strategy 3)
-  if (p.strategy == 3 || p.strategy == 1) {
-    unsigned long long c = 0;
-    for (int j = 0; j < KEYS_PER_THREAD; ++j) c += h[khi - j];
-    excl = block_excl_scan(c, sh, &total);
-    // first key (descending) where cumulative count reaches top_k
-    if (tid == 0) sh_i[1] = 0;
-    __syncthreads();
-    if (excl < static_cast<unsigned long long>(p.top_k) && excl + c >= static_cast<unsigned long long>(p.top_k)) {
-      unsigned long long run = excl;
-      for (int j = 0; j < KEYS_PER_THREAD; ++j) {
-        run += h[khi - j];
-        if (run >= static_cast<unsigned long long>(p.top_k)) { sh_i[1] = khi - j; break; }
-      }
-    }
-    __syncthreads();
-    k_floor = sh_i[1];     // 0 when the row has fewer than top_k tokens: keep everything
-  }
-  // softmax denominator over the keys the reference's softmax sees
-  const int z_floor = (p.strategy == 3) ? k_floor : 0;
-  float zpart = 0.f;
-  for (int j = 0; j < KEYS_PER_THREAD; ++j) {
-    const int k = khi - j;
-    const uint32_t c = h[k];
-    if (c != 0u && k >= z_floor) zpart += static_cast<float>(c) * weight(k);
-  }
-  // deterministic tree: warp shuffle then warp 0
-  zpart = warp_sum(zpart);
-  if ((tid & 31) == 0) sh_f[tid >> 5] = zpart;
-  __syncthreads();
-  if (tid < 32) {
-    float v = sh_f[tid];
-    v = warp_sum(v);
-    if (tid == 0) sh_f[0] = v;
-  }
-  __syncthreads();
-  const float Z = sh_f[0];
-  __syncthreads();
-  auto prob_q40 = [&](int k) -> unsigned long long {   // bf16-rounded softmax output as Q40 fixed point
-    const float pr = round_bf16(weight(k) / Z);
-    return static_cast<unsigned long long>(static_cast<double>(pr) * Q40);
-  };
-
-  // ---- filter: smallest kept key k_keep ----
-  int k_keep = (p.strategy == 1 || p.strategy == 3) ? k_floor : 0;
-  if (p.strategy == 2 || p.strategy == 3) {
-    // keep key k while mass(keys > k) < top_p   (FlashInfer top-p: ties at the boundary all kept)
-    unsigned long long mpart = 0;
-    for (int j = 0; j < KEYS_PER_THREAD; ++j) {
-      const int k = khi - j;
-      const uint32_t c = h[k];
-      if (c != 0u && k >= z_floor) mpart += static_cast<unsigned long long>(c) * prob_q40(k);
-    }
-    excl = block_excl_scan(mpart, sh, &total);
-    const unsigned long long P = static_cast<unsigned long long>(static_cast<double>(p.top_p) * Q40);
-    if (tid == 0) sh_i[2] = z_floor;
-    __syncthreads();
-    if (excl < P && excl + mpart >= P) {
-      unsigned long long run = excl;
-      for (int j = 0; j < KEYS_PER_THREAD; ++j) {
-        const int k = khi - j;
-        const uint32_t c = h[k];
-        if (c != 0u && k >= z_floor) {
-          run += static_cast<unsigned long long>(c) * prob_q40(k);
-          if (run >= P) { sh_i[2] = k; break; }
-        }
-      }
-    }
-    __syncthreads();
-    k_keep = max(k_keep, sh_i[2]);
-  } else if (p.strategy == 4) {
-    const float pmax = round_bf16(weight(kmax) / Z);
-    int mine = 65536;
-    for (int j = 0; j < KEYS_PER_THREAD; ++j) {
-      const int k = khi - j;
-      if (h[k] != 0u && round_bf16(weight(k) / Z) >= p.min_p * pmax) mine = k;   // keeps the smallest passing key
-    }
-    mine = __reduce_min_sync(0xffffffffu, mine);
-    if ((tid & 31) == 0) sh_f[tid >> 5] = __int_as_float(mine);
-    __syncthreads();
-    if (tid < 32) {
-      int v = __float_as_int(sh_f[tid]);
-      v = __reduce_min_sync(0xffffffffu, v);
-      if (tid == 0) sh_i[2] = v;
-    }
-    __syncthreads();
-    k_keep = sh_i[2];
-  }
-
-  // ---- draw from the kept keys, proportional to probability ----
-  unsigned long long wpart = 0;
-  for (int j = 0; j < KEYS_PER_THREAD; ++j) {
-    const int k = khi - j;
-    const uint32_t c = h[k];
-    if (c != 0u && k >= k_keep) wpart += static_cast<unsigned long long>(c) * prob_q40(k);
-  }
-  excl = block_excl_scan(wpart, sh, &total);
-  if (tid == 0) {
-    const uint64_t seed = p.rng_state ? p.rng_state[0] : p.seed;
-    const uint64_t offset = p.rng_state ? p.rng_state[1] : p.offset;
-    const double u = philox_uniform(seed, offset, static_cast<uint32_t>(row));
-    unsigned long long target = static_cast<unsigned long long>(u * static_cast<double>(total));
-    if (target >= total) target = total ? total - 1 : 0;
-    sh_u[0] = target;
-    p.pick[row * 2 + 0] = static_cast<uint32_t>(kmax);   // fallback: degenerate mass -> argmax key, rank 0
-    p.pick[row * 2 + 1] = 0u;
-  }
-  __syncthreads();
-  const unsigned long long target = sh_u[0];
-  if (wpart != 0ull && excl <= target && target < excl + wpart) {
-    unsigned long long run = excl;
-    for (int j = 0; j < KEYS_PER_THREAD; ++j) {
-      const int k = khi - j;
-      const uint32_t c = h[k];
-      if (c != 0u && k >= k_keep) {
-        const unsigned long long q = prob_q40(k);
-        const unsigned long long m = static_cast<unsigned long long>(c) * q;
-        if (target < run + m) {
-          unsigned long long r = q ? (target - run) / q : 0ull;
-          if (r >= c) r = c - 1;
-          p.pick[row * 2 + 0] = static_cast<uint32_t>(k);
-          p.pick[row * 2 + 1] = static_cast<uint32_t>(r);
-          break;
-        }
-        run += m;
-      }
-    }
-  }
+__device__ __forceinline__ void st_dsmem_u64(unsigned long long* local_ptr, uint32_t cta_rank, unsigned long long v) {
+  uint32_t laddr = smem_u32(local_ptr), raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(cta_rank));
+  asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(raddr), "l"(v) : "memory");
 }
 
-// resolve (key, rank) -> index of the rank-th token (index order) whose value code equals key
-__global__ void __launch_bounds__(1024) resolve_kernel(const SampleParams p) {
+struct SmpCtx {
+  int S, rank, buf;
+  unsigned long long (*xch)[SMP_MAX_CLUSTER];   // [2][8] exchange slots, written by the peers
+  unsigned long long* sh;                       // [33]
+  __device__ __forceinline__ void publish(unsigned long long v) {   // one warp: lane r stores into CTA r
+    const int lane = threadIdx.x & 31;
+    if (S == 1) {
+      if (lane == 0) xch[buf][0] = v;
+    } else if (lane < S) {
+      st_dsmem_u64(&xch[buf][rank], lane, v);
+    }
+  }
+  __device__ __forceinline__ void sync() {
+    if (S == 1) __syncthreads(); else cluster_sync_all();
+  }
+};
+enum { SMP_SUM = 0, SMP_MAX = 1, SMP_MIN = 2 };
+template <int OP>
+__device__ __forceinline__ unsigned long long smp_op(unsigned long long a, unsigned long long b) {
+  return OP == SMP_SUM ? a + b : (OP == SMP_MAX ? (a > b ? a : b) : (a < b ? a : b));
+}
+// cluster-wide reduction of one u64 per thread; every thread of every CTA gets the result
+template <int OP>
+__device__ __forceinline__ unsigned long long smp_reduce(unsigned long long v, SmpCtx& c) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = smp_op<OP>(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if (lane == 0) c.sh[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long x = c.sh[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = smp_op<OP>(x, __shfl_xor_sync(0xffffffffu, x, o));
+    c.publish(x);
+  }
+  c.sync();
+  unsigned long long r = c.xch[c.buf][0];
+  for (int i = 1; i < c.S; ++i) r = smp_op<OP>(r, c.xch[c.buf][i]);
+  c.buf ^= 1;
+  return r;
+}
+// fp32 sum with a fixed tree (xor butterfly inside the warp and across warps, CTA partials in rank order)
+__device__ __forceinline__ float smp_sum_f32(float v, SmpCtx& c) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  float* shf = reinterpret_cast<float*>(c.sh);
+  if (lane == 0) shf[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    const float x = warp_sum(shf[lane]);
+    c.publish(static_cast<unsigned long long>(__float_as_uint(x)));
+  }
+  c.sync();
+  float r = 0.f;
+  for (int i = 0; i < c.S; ++i) r += __uint_as_float(static_cast<uint32_t>(c.xch[c.buf][i]));
+  c.buf ^= 1;
+  return r;
+}
+
+__global__ void __launch_bounds__(SMP_THREADS, 1) sample_kernel(const SampleParams p, const int npairs) {
+  extern __shared__ uint32_t q_sm[];                 // [2 * npairs][1024] masses (Q32)
+  __shared__ unsigned long long xch[2][SMP_MAX_CLUSTER];
+  __shared__ unsigned long long pick[2][2];
+  __shared__ unsigned long long sh[34];
+  SmpCtx c;
+  c.S = gridDim.x; c.rank = blockIdx.x; c.buf = 0; c.xch = xch; c.sh = sh;
+  const int S = c.S, rank = c.rank, row = blockIdx.y, tid = threadIdx.x;
+  const bool scaled = p.strategy != 0;
   pdl_sync();
-  __shared__ unsigned long long sh[33];
-  const int row = blockIdx.x, tid = threadIdx.x;
-  const uint32_t key = p.pick[row * 2], rank = p.pick[row * 2 + 1];
-  const int per = (p.vocab + blockDim.x - 1) / blockDim.x;
-  const int i0 = tid * per, i1 = min(p.vocab, i0 + per);
-  unsigned long long c = 0;
-  for (int i = i0; i < i1; ++i) c += (bf16_key(token_value(p, row, i, true)) == key) ? 1ull : 0ull;
-  unsigned long long total;
-  const unsigned long long excl = block_excl_scan(c, sh, &total);
-  if (tid == 0 && total == 0ull) p.out[row] = 0;
-  if (tid == 0 && row == 0 && p.rng_state) p.rng_state[1] += 1ull;   // all scan CTAs have finished (stream order)
-  if (c != 0ull && excl <= rank && rank < excl + c) {
-    unsigned long long run = excl;
-    for (int i = i0; i < i1; ++i) {
-      if (bf16_key(token_value(p, row, i, true)) == key) {
-        if (run == rank) { p.out[row] = i; break; }
-        ++run;
+
+  // ---- one pass over the row: keys (0 = no token / NaN) ----
+  uint32_t kk[SMP_PAIRS];
+#pragma unroll
+  for (int j = 0; j < SMP_PAIRS; ++j) {
+    kk[j] = 0u;
+    if (j < npairs) {
+      const int i0 = 2 * ((j * S + rank) * SMP_THREADS + tid);
+      uint32_t lo = 0u, hi = 0u;
+      if (i0 < p.vocab) { const float v = token_value(p, row, i0, scaled); lo = (v == v) ? bf16_key(v) : 0u; }
+      if (i0 + 1 < p.vocab) { const float v = token_value(p, row, i0 + 1, scaled); hi = (v == v) ? bf16_key(v) : 0u; }
+      kk[j] = lo | (hi << 16);
+    }
+  }
+  auto tok_index = [&](int j, int half) { return 2 * ((j * S + rank) * SMP_THREADS + tid) + half; };
+
+  // ---- max key ----
+  uint32_t kloc = 0u;
+#pragma unroll
+  for (int j = 0; j < SMP_PAIRS; ++j) kloc = max(kloc, max(kk[j] & 0xffffu, kk[j] >> 16));
+  const uint32_t kmax = static_cast<uint32_t>(smp_reduce<SMP_MAX>(kloc, c));
+  // smallest index holding the max key: the greedy answer and the fallback of degenerate rows
+  auto first_max_index = [&]() -> unsigned long long {
+    unsigned long long best = 0xffffffffull;
+#pragma unroll
+    for (int j = SMP_PAIRS - 1; j >= 0; --j) {
+      if ((kk[j] >> 16) == kmax) best = static_cast<unsigned long long>(tok_index(j, 1));
+      if ((kk[j] & 0xffffu) == kmax) best = static_cast<unsigned long long>(tok_index(j, 0));
+    }
+    const unsigned long long r = smp_reduce<SMP_MIN>(kmax ? best : 0xffffffffull, c);
+    return r == 0xffffffffull ? 0ull : r;
+  };
+  if (p.strategy == 0) {
+    const unsigned long long idx = first_max_index();
+    if (rank == 0 && tid == 0) p.out[row] = static_cast<int64_t>(idx);
+    return;
+  }
+
+  // ---- top-k threshold: smallest key k with #{key_i > k} < top_k (ties at the k-th value are kept) ----
+  uint32_t k_floor = 0u;
+  if (p.strategy == 1 || p.strategy == 3) {
+    uint32_t lo = 0u, hi = 65535u;          // invariant: count(> hi) < top_k; count(> lo - 1) >= top_k or lo == 0
+    // bisection over [0, 65535] for the smallest k with count(> k) < top_k
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      uint32_t cnt = 0u;
+#pragma unroll
+      for (int j = 0; j < SMP_PAIRS; ++j) cnt += ((kk[j] & 0xffffu) > mid ? 1u : 0u) + ((kk[j] >> 16) > mid ? 1u : 0u);
+      const unsigned long long tot = smp_reduce<SMP_SUM>(cnt, c);
+      if (tot < static_cast<unsigned long long>(p.top_k)) hi = mid; else lo = mid + 1;
+    }
+    k_floor = lo;
+  }
+  const uint32_t z_floor = (p.strategy == 3) ? k_floor : 0u;   // top-k-first: the softmax only sees the top-k
+
+  // ---- softmax denominator (fp32) ----
+  const float xmax = key_value(kmax);
+  float zpart = 0.f;
+#pragma unroll
+  for (int j = 0; j < SMP_PAIRS; ++j) {
+    const uint32_t a = kk[j] & 0xffffu, b = kk[j] >> 16;
+    if (a != 0u && a >= z_floor) zpart += expf(key_value(a) - xmax);
+    if (b != 0u && b >= z_floor) zpart += expf(key_value(b) - xmax);
+  }
+  const float Z = smp_sum_f32(zpart, c);
+
+  // ---- masses: bf16-rounded softmax output as Q32 fixed point; filtered tokens get 0 ----
+  const uint32_t keep_floor = (p.strategy == 1 || p.strategy == 3) ? k_floor : 0u;
+  const float minp_thr = (p.strategy == 4) ? p.min_p * round_bf16(1.0f / Z) : 0.f;
+  unsigned long long msum = 0ull;
+#pragma unroll
+  for (int j = 0; j < SMP_PAIRS; ++j) {
+    if (j < npairs) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t k = h ? (kk[j] >> 16) : (kk[j] & 0xffffu);
+        uint32_t q = 0u;
+        if (k != 0u && k >= z_floor && k >= keep_floor) {
+          const float pr = round_bf16(expf(key_value(k) - xmax) / Z);
+          if (pr >= minp_thr) q = __float2uint_rz(pr * 4294967296.f);   // saturates at 2^32 - 1
+        }
+        q_sm[(2 * j + h) * SMP_THREADS + tid] = q;
+        msum += q;
       }
+    }
+  }
+  unsigned long long Mc = smp_reduce<SMP_SUM>(msum, c);   // mass of the current candidate set
+  const uint64_t seed = p.rng_state ? p.rng_state[0] : p.seed;
+  const uint64_t offset = p.rng_state ? p.rng_state[1] : p.offset;
+  if (Mc == 0ull || !(Z > 0.f)) {
+    // degenerate row (everything masked / non-finite): argmax, like the reference's fallthrough
+    const unsigned long long idx = first_max_index();
+    if (rank == 0 && tid == 0) p.out[row] = static_cast<int64_t>(idx);
+  } else {
+    const bool nucleus = (p.strategy == 2 || p.strategy == 3);
+    unsigned long long P = static_cast<unsigned long long>(static_cast<double>(p.top_p) * 4294967296.0);
+    if (P == 0ull) P = 1ull;
+    uint32_t pivot = 0u;                     // candidates: key > pivot
+    int pb = 0;
+    unsigned long long result = 0ull;
+    for (uint32_t round = 0; round < 64u; ++round) {
+      // inverse CDF over the candidates in (cta, thread, slot) order
+      unsigned long long mine = 0ull;
+#pragma unroll
+      for (int j = 0; j < SMP_PAIRS; ++j) {
+        if (j < npairs) {
+          if ((kk[j] & 0xffffu) > pivot) mine += q_sm[(2 * j) * SMP_THREADS + tid];
+          if ((kk[j] >> 16) > pivot) mine += q_sm[(2 * j + 1) * SMP_THREADS + tid];
+        }
+      }
+      unsigned long long cta_total;
+      const unsigned long long excl = block_excl_scan(mine, sh, &cta_total);
+      if (tid < 32) c.publish(cta_total);
+      c.sync();
+      unsigned long long base = 0ull;
+      for (int r = 0; r < rank; ++r) base += c.xch[c.buf][r];
+      c.buf ^= 1;
+      const double u = philox_uniform(seed, offset, static_cast<uint32_t>(row), round);
+      unsigned long long target = static_cast<unsigned long long>(u * static_cast<double>(Mc));
+      if (target >= Mc) target = Mc - 1;
+      const unsigned long long lo = base + excl;
+      if (mine != 0ull && lo <= target && target < lo + mine) {
+        unsigned long long run = lo;
+        unsigned long long found = 0ull;
+        bool done = false;
+#pragma unroll
+        for (int j = 0; j < SMP_PAIRS; ++j) {
+          if (j < npairs) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t k = h ? (kk[j] >> 16) : (kk[j] & 0xffffu);
+              if (!done && k > pivot) {
+                const unsigned long long q = q_sm[(2 * j + h) * SMP_THREADS + tid];
+                if (target < run + q) {
+                  found = (static_cast<unsigned long long>(k) << 32) | static_cast<uint32_t>(tok_index(j, h));
+                  done = true;
+                }
+                run += q;
+              }
+            }
+          }
+        }
+        if (S == 1) pick[pb][0] = found;
+        else for (int r = 0; r < S; ++r) st_dsmem_u64(&pick[pb][0], r, found);
+      }
+      c.sync();
+      result = pick[pb][0];
+      pb ^= 1;
+      if (!nucleus) break;
+      const uint32_t kj = static_cast<uint32_t>(result >> 32);
+      unsigned long long above = 0ull;
+#pragma unroll
+      for (int j = 0; j < SMP_PAIRS; ++j) {
+        if (j < npairs) {
+          if ((kk[j] & 0xffffu) > kj) above += q_sm[(2 * j) * SMP_THREADS + tid];
+          if ((kk[j] >> 16) > kj) above += q_sm[(2 * j + 1) * SMP_THREADS + tid];
+        }
+      }
+      above = smp_reduce<SMP_SUM>(above, c);
+      if (above < P) break;                  // j is inside the nucleus: accept
+      pivot = kj;                            // nothing with p <= p_j is: drop it and redraw
+      Mc = above;
+    }
+    if (rank == 0 && tid == 0) p.out[row] = static_cast<int64_t>(result & 0xffffffffull);
+  }
+  // advance the device RNG offset once per call: the last row to get here (every row read the offset above,
+  // before its final cluster barrier)
+  if (p.rng_state && rank == 0 && tid == 0) {
+    const unsigned long long old = atomicAdd(&p.rng_state[2], 1ull);
+    if (old == static_cast<unsigned long long>(gridDim.y) - 1ull) {
+      p.rng_state[2] = 0ull;
+      p.rng_state[1] = offset + 1ull;
     }
   }
 }
@@ -383,8 +421,8 @@ using namespace vb;
 extern "C" {
 
 size_t vb_sample_workspace_bytes(int rows, int vocab) {
-  (void)vocab;
-  return static_cast<size_t>(rows) * (65536 * sizeof(uint32_t) + 64);
+  (void)vocab; (void)rows;
+  return 256;   // the sampler keeps the row on chip; the workspace is kept in the ABI for callers that size it
 }
 
 static int fill_params(SampleParams& p, int64_t* d_out_ids, const void* d_logits, int rows, int vocab, int ld,
@@ -400,11 +438,7 @@ static int fill_params(SampleParams& p, int64_t* d_out_ids, const void* d_logits
   p.strategy = strategy; p.top_k = top_k; p.top_p = top_p; p.min_p = min_p;
   p.mask_token = mask_token; p.seed = seed; p.offset = offset;
   p.rng_state = reinterpret_cast<unsigned long long*>(rng_state);
-  uint8_t* w = static_cast<uint8_t*>(ws);
-  p.hist = reinterpret_cast<uint32_t*>(w);
-  p.packed = w ? reinterpret_cast<unsigned long long*>(w + static_cast<size_t>(rows) * 65536 * 4) : nullptr;
-  p.pick = w ? reinterpret_cast<uint32_t*>(w + static_cast<size_t>(rows) * 65536 * 4 + static_cast<size_t>(rows) * 8)
-             : nullptr;
+  (void)ws;
   p.out = d_out_ids;
   return 0;
 }
@@ -427,17 +461,19 @@ int vb_sample(int64_t* d_out_ids, const void* d_logits, int rows, int vocab, int
   fill_params(p, d_out_ids, d_logits, rows, vocab, ld_logits, d_rep_cache, rep_window_slots, rep_codebooks,
               logit_codebooks, penalty, strategy, top_k, top_p, min_p, temperature, seed, offset, mask_token,
               d_workspace, d_rng_state, d_cache_rows);
-  const int gx = max(1, min(32, (vocab + 256 * 8 - 1) / (256 * 8)));
-  if (strategy == 0) {
-    VB_CHECK_CUDA(cudaMemsetAsync(p.packed, 0, static_cast<size_t>(rows) * 8, st));
-    VB_LAUNCH_PLAIN(argmax_kernel, dim3(gx, rows), 256, 0, st, p);
-    VB_LAUNCH_PDL(unpack_argmax_kernel, (rows + 127) / 128, 128, 0, st, d_out_ids, p.packed, rows);
-    return 0;
-  }
-  VB_CHECK_CUDA(cudaMemsetAsync(p.hist, 0, static_cast<size_t>(rows) * 65536 * 4, st));
-  VB_LAUNCH_PLAIN(hist_kernel, dim3(gx, rows), 256, 0, st, p);
-  VB_LAUNCH_PDL(scan_kernel, rows, SCAN_THREADS, 0, st, p);
-  VB_LAUNCH_PDL(resolve_kernel, rows, 1024, 0, st, p);
+  // smallest cluster (1, 2, 4 or 8 CTAs) whose threads can hold the row on chip
+  int S = 1;
+  while (S < SMP_MAX_CLUSTER && static_cast<long long>(S) * SMP_THREADS * 2 * SMP_PAIRS < vocab) S <<= 1;
+  VB_CHECK_ARG(static_cast<long long>(S) * SMP_THREADS * 2 * SMP_PAIRS >= vocab,
+               "vb_sample: vocab %d exceeds the %d tokens one cluster holds on chip", vocab,
+               SMP_MAX_CLUSTER * SMP_THREADS * 2 * SMP_PAIRS);
+  VB_CHECK_ARG(rows <= 65535, "vb_sample: %d rows exceed the grid limit (65535)", rows);
+  const int npairs = (vocab + S * SMP_THREADS * 2 - 1) / (S * SMP_THREADS * 2);
+  const size_t smem = static_cast<size_t>(2 * npairs) * SMP_THREADS * sizeof(uint32_t);
+  // (static shared memory counts against the same 227 KiB: leave room for it)
+  VB_CHECK_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     2 * SMP_PAIRS * SMP_THREADS * static_cast<int>(sizeof(uint32_t))));
+  VB_LAUNCH_PDL_CLUSTER(sample_kernel, dim3(S, rows), SMP_THREADS, smem, st, S, p, npairs);
   return 0;
 }
 

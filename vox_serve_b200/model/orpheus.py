@@ -130,7 +130,7 @@ class OrpheusModel(BaseLM):
         self.max_rows = 1024 + 64
         # device {seed, offset}: the sampler advances the offset itself, so CUDA-graph replays keep drawing
         seed64 = torch.cuda.default_generators[torch.device(device).index or 0].initial_seed() & ((1 << 63) - 1)
-        self.rng_state = torch.tensor([seed64, 0], dtype=torch.int64, device=device)
+        self.rng_state = torch.tensor([seed64, 0, 0], dtype=torch.int64, device=device)
 
     # ---- static facts (orpheus.py:276-330) --------------------------------------------------------
     n_codebooks = 1

@@ -376,6 +376,8 @@ def sample(logits: torch.Tensor, strategy: str, rep_cache: Optional[torch.Tensor
     rows, V = logits.shape
     out = torch.empty(rows, dtype=torch.int64, device=logits.device) if out is None else out
     ws = sample_workspace(rows, V, logits.device) if workspace is None else workspace
+    if rng_state is not None:
+        assert rng_state.dtype == torch.int64 and rng_state.numel() >= 3, "rng_state: int64 {seed, offset, 0}"
     c8 = _cache_u8(rep_cache)
     W, Cc = (c8.shape[1], c8.shape[2]) if c8 is not None else (0, 0)
     call("vb_sample", out.data_ptr(), logits.data_ptr(), rows, V, logits.stride(0), _p(c8), _p(cache_rows), W, Cc,
