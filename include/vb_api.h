@@ -102,19 +102,54 @@ int vb_paged_attn(void* d_out, const void* d_q, const void* d_kv, int64_t slab_b
                   int ws_grid_ctas, void* stream);
 
 /* ---- dense projections (nn.Linear, bias-free): model/orpheus.py:41-47, 68-79, 197 -------------
- * Y[T][N] = X[T][K] * W[N][K]^T on tcgen05 (weights are the 128-row MMA operand, tokens the N side).
- * w_map: vb_tensor_map_2d_bf16(W, N, K, ldw, 128);  x_map: vb_tensor_map_2d_bf16(X, T, K, ldx, t_tile)
- * with t_tile = vb_gemm_t_tile(T).
+ * Y[T][N] = X[T][K] * W[N][K]^T on tcgen05: a tile of tile_rows (<= 128, multiple of 8; 0 = 128) weight rows is
+ * the M side of the MMA, the tokens are the N side.  tile_rows is free so that a projection can be cut into
+ * ~one CTA per SM whatever its N.
+ * d_w_tiles: the weight matrix re-tiled once at load time by vb_pack_weight_tiles(W, N, K, ldw, tile_rows) into
+ * [n_tile][k_block][tile_rows][64] bf16 with the UMMA 128-byte swizzle applied, so that the (tile, k-block) operand
+ * a CTA needs is ONE contiguous run in HBM (a single linear bulk copy per pipeline stage, sequential DRAM bursts)
+ * and a CTA's k-blocks follow each other; vb_weight_tiles_bytes gives the size (rows padded to the tile, K to 64).
+ * x_map: vb_tensor_map_2d_bf16(X, T, K, ldx, t_tile) with t_tile = vb_gemm_t_tile(T).
  * mode 0: Y bf16 [T][ldy]           (split_k must be 1)
- * mode 1: Y fp32 partials [split_k][T][ldy]   (consumers below sum them in split order)
- * mode 2: W rows interleaved per 128-tile as 64 gate rows then 64 up rows; Y bf16 [T][ldy] holds
- *         silu(gate)*up with the reference's bf16 rounding points (orpheus.py:46-48), N_out = N/2. */
+ * mode 1: Y fp32 partials [split_k][T][ldy]   (vb_reduce_residual_rmsnorm / vb_qkv_rope_append sum them in split order)
+ * mode 2: W rows packed per tile as h = tile_rows/2 gate rows then the h matching up rows (N = packed rows,
+ *         zero-padded to a multiple of tile_rows); Y bf16 [T][ldy] holds silu(gate)*up with the reference's
+ *         bf16 rounding points (orpheus.py:46-48) for the first n_out (0 = N/2) outputs. */
+size_t vb_weight_tiles_bytes(int N, int K, int tile_rows);
+int vb_pack_weight_tiles(void* d_dst, const void* d_w, int N, int K, int64_t ldw, int tile_rows, void* stream);
 int vb_gemm_t_tile(int T);
-/* d_prefetch / prefetch_bytes (optional): a byte range -- normally the weights of the projection that runs next --
- * that the kernel's idle epilogue warps pull into L2 (cp.async.bulk.prefetch.L2) while the accumulators are being
- * produced, so that HBM keeps streaming across kernel boundaries. */
-int vb_gemm_bf16(void* d_y, const void* w_map, const void* x_map, int T, int N, int K, int ldy, int mode,
-                 int split_k, const void* d_prefetch, size_t prefetch_bytes, void* stream);
+int vb_gemm_bf16(void* d_y, const void* d_w_tiles, const void* x_map, int T, int N, int K, int ldy, int mode,
+                 int split_k, int tile_rows, int n_out, void* stream);
+
+/* ---- fused decode projections (T <= 64): one launch each for what orpheus.py:81-151 does between Linears ----
+ * x_map: vb_tensor_map_2d_bf16(X, T, K, ldx, t_tile) with t_tile = 16 / 32 / 64 (smallest >= T).
+ * Split-K sums finish inside the kernel: the split_k (<= 8) CTAs of a tile form a thread-block cluster and add
+ * their partial tiles through distributed shared memory in split order (deterministic); no workspace.
+ *
+ * vb_proj_residual: hidden_out[T][N] = bf16(residual + bf16(X W^T))   (o_proj / down_proj + residual add,
+ *   orpheus.py:139-150; d_residual may alias d_hidden_out, may be NULL) and, if d_ssq_out, the per-tile sums of
+ *   squares of the new hidden rows: ssq_out[tile][T] -- the RMSNorm statistics of the NEXT projection.
+ * vb_proj_norm_gateup_silu: act[T][n_out] = silu(gate(xn)) * up(xn), xn = rmsnorm(hidden) * norm_weight formed
+ *   on the fly: TMA delivers the raw hidden tile (x_map over hidden [T][K]), the kernel scales it in place with the
+ *   row statistics d_ssq [n_ssq_parts][T] (flashinfer norm.cuh rounding); weights packed as for mode 2.
+ * vb_proj_norm_qkv_rope_append: q|k|v = Wqkv xn (rows: q heads, k heads, v heads; one head per tile), RoPE on
+ *   q and k with the step's cos/sin table (vb_rope_table, rotate-half pairs, full head_dim), q -> q_out
+ *   [T][n_q][D], k,v -> the page/slot of each row (row_page < 0: skipped).  orpheus.py:91-106,
+ *   flashinfer_utils.py:243-244. */
+int vb_proj_residual(void* d_hidden_out, float* d_ssq_out, const void* d_w_tiles, const void* x_map,
+                     const void* d_residual, int T, int N, int K, int split_k, int tile_rows, void* stream);
+int vb_proj_norm_gateup_silu(void* d_act_out, const void* d_w_tiles, const void* x_map, const float* d_ssq,
+                             int n_ssq_parts, const void* d_norm_weight, float eps, int T, int N_packed, int K,
+                             int tile_rows, int n_out, void* stream);
+int vb_proj_norm_qkv_rope_append(void* d_q_out, void* d_layer_kv, const void* d_w_tiles, const void* x_map,
+                                 const float* d_ssq, int n_ssq_parts, const void* d_norm_weight, float eps,
+                                 const float* d_rope_cs, const int32_t* d_row_page, const int32_t* d_row_slot, int T,
+                                 int K, int n_q, int n_kv, int head_dim, int page_size, int split_k, void* stream);
+/* cs[T][2][head_dim] = cos | sin of pos[t] * freq[e]: computed once per step, shared by all layers */
+int vb_rope_table(float* d_cs, const int32_t* d_pos, const float* d_freq, int T, int head_dim, void* stream);
+/* ssq[rows] = sum of squares of each bf16 row (RMSNorm statistics of a hidden state that did not come out of
+ * vb_proj_residual: the embedding output) */
+int vb_row_ssq(float* d_ssq, const void* d_x, int rows, int dim, void* stream);
 
 /* sum split-K partials -> bf16 Linear output; + residual; then RMSNorm of the new hidden state:
  * orpheus.py:125-151 (residual adds, next layer's input_layernorm / post_attention_layernorm).

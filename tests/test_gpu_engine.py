@@ -19,7 +19,7 @@ def _i32(x):
     return torch.tensor(x, dtype=torch.int32, device="cuda")
 
 
-def _run(dims, page_size, max_pages, prompt_lens, n_steps, seed, max_bs=4):
+def _run(dims, page_size, max_pages, prompt_lens, n_steps, seed, max_bs=4, force_unfused=False):
     from vox_serve_b200 import ops
     from vox_serve_b200.engine import LlamaDims, LlamaEngine, LlamaWeights
 
@@ -35,6 +35,7 @@ def _run(dims, page_size, max_pages, prompt_lens, n_steps, seed, max_bs=4):
     kv = torch.zeros(dims.num_hidden_layers, max_pages, 2, page_size, dims.num_key_value_heads, dims.head_dim,
                      dtype=BF, device="cuda")
     eng = LlamaEngine(gw, kv, page_size, max_rows=256)
+    eng.force_unfused = force_unfused
     g = torch.Generator().manual_seed(21)
     reqs = [oworker.Req(f"r{i}", torch.randint(10, dims.vocab_size, (n,), generator=g)) for i, n in enumerate(prompt_lens)]
     active = []
@@ -83,10 +84,12 @@ def _run(dims, page_size, max_pages, prompt_lens, n_steps, seed, max_bs=4):
     return stats
 
 
-def test_tiny_orpheus_teacher_forced_greedy():
+@pytest.mark.parametrize("force_unfused", [False, True])      # 5-launch fused layers / 8-launch (prefill-style) layers
+def test_tiny_orpheus_teacher_forced_greedy(force_unfused):
     dims = oorph.OrpheusDims.tiny()
     dims.max_tokens = 400
-    st = _run(dims, page_size=16, max_pages=128, prompt_lens=[5, 16, 30, 33], n_steps=60, seed=3)
+    st = _run(dims, page_size=16, max_pages=128, prompt_lens=[5, 16, 30, 33], n_steps=60, seed=3,
+              force_unfused=force_unfused)
     print(st)
     assert st["max_logit_err"] < 2e-2
     assert st["id_mismatch"] <= max(2, st["rows"] // 50)

@@ -300,6 +300,95 @@ def test_qkv_rope_append(ops):
     assert torch.equal(dcache.cpu()[pg, 1, sl], v)
 
 
+@pytest.mark.parametrize("T,I,K,h", [(32, 1024, 768, 64), (32, 8192, 3072, 56), (5, 520, 256, 24), (64, 1000, 512, 8)])
+def test_gemm_gate_up_silu_tile_rows(ops, T, I, K, h):
+    """gate/up rows packed h + h per tile (zero-padded tail tile): unfused (TMA B operand) and norm-fused variants."""
+    import torch.nn.functional as F
+    x = torch.randn(T, K, generator=g(3)).to(BF)
+    wg = (torch.randn(I, K, generator=g(4)) * 0.05).to(BF)
+    wu = (torch.randn(I, K, generator=g(5)) * 0.05).to(BF)
+    wi = ops.interleave_gate_up(wg.cuda(), wu.cuda(), h)
+    assert wi.shape[0] == 2 * h * ((I + h - 1) // h)
+    ref = F.silu(F.linear(x, wg)) * F.linear(x, wu)
+    got = ops.gemm(x.cuda(), wi, mode=2, tile_rows=2 * h, n_out=I)
+    assert got.shape == (T, I)
+    # (products of two near-cancelling sums: tiny outputs sit many bf16 codes apart at negligible absolute error)
+    assert_bf16_close(got, ref, 2, 3e-2, "gate-up silu", atol=2e-3 * ref.float().abs().max().item())
+    # norm-fused: hidden -> rmsnorm * w -> gate/up -> silu * up
+    hid = (torch.randn(T, K, generator=g(6)) * 3).to(BF)
+    nw = (1 + 0.1 * torch.randn(K, generator=g(7))).to(BF)
+    xn = lm_ops.rms_norm(hid, nw, 1e-5)
+    ref2 = F.silu(F.linear(xn, wg)) * F.linear(xn, wu)
+    parts = 3 if K % 3 == 0 else 2          # statistics arrive as per-tile partial sums of squares
+    cols = K // parts
+    ssq = torch.stack([(hid.float()[:, i * cols:(i + 1) * cols] ** 2).sum(-1) for i in range(parts)])
+    if K % 64 == 0:
+        got2 = ops.proj_norm_gateup_silu(hid.cuda(), ssq.cuda().contiguous(), parts, nw.cuda(), 1e-5, wi, h, I)
+        assert_bf16_close(got2, ref2, 2, 3e-2, "norm + gate-up silu", atol=2e-3 * ref2.float().abs().max().item())
+
+
+@pytest.mark.parametrize("T,N,K,split,tile_rows", [(32, 3072, 3072, 6, 128), (32, 3072, 8192, 6, 128), (7, 384, 512, 2, 128),
+                                                    (64, 200, 256, 1, 40), (1, 3072, 3072, 4, 96), (33, 130, 192, 3, 128)])
+def test_proj_residual(ops, T, N, K, split, tile_rows):
+    """O / down projection with the split-K sum, bf16 rounding, residual add and next-norm statistics in the kernel."""
+    x = torch.randn(T, K, generator=g(T + N)).to(BF)
+    w = (torch.randn(N, K, generator=g(K)) * 0.05).to(BF)
+    resid = torch.randn(T, N, generator=g(7)).to(BF)
+    lin = _gemm_ref(x, w).to(BF)
+    h_ref = resid + lin
+    tiles = (N + tile_rows - 1) // tile_rows
+    for rep in range(2):
+        hid = resid.clone().cuda()
+        h, ssq = ops.proj_residual(x.cuda(), w.cuda(), hid, split, hidden_out=hid, tile_rows=tile_rows)
+        assert h.data_ptr() == hid.data_ptr()
+        tol = 2e-3 * lin.float().abs().max().item() + 1e-4
+        assert_bf16_close(h, h_ref, 1, 2e-2, "proj residual", atol=tol)
+        hf = h.float().cpu()
+        ssq_ref = torch.stack([(hf[:, i * tile_rows:(i + 1) * tile_rows] ** 2).sum(-1) for i in range(tiles)])
+        assert ssq.shape == (tiles, T)
+        assert torch.allclose(ssq.cpu(), ssq_ref, rtol=1e-5, atol=1e-6)
+    h2, _ = ops.proj_residual(x.cuda(), w.cuda(), None, split, tile_rows=tile_rows)
+    assert_bf16_close(h2, lin, 1, 2e-2, "proj no residual", atol=tol)
+
+
+@pytest.mark.parametrize("T,hq,hkv,D,K,split", [(6, 6, 2, 128, 768, 2), (32, 24, 8, 128, 3072, 3), (33, 4, 4, 64, 512, 1),
+                                                 (1, 8, 2, 128, 1024, 4)])
+def test_proj_norm_qkv_rope_append(ops, T, hq, hkv, D, K, split):
+    """RMSNorm -> QKV projection -> RoPE -> q out / K,V page scatter in one launch, against the oracle chain."""
+    page_size, n_pages = 16, 200
+    hid = (torch.randn(T, K, generator=g(11)) * 2).to(BF)
+    nw = (1 + 0.1 * torch.randn(K, generator=g(12))).to(BF)
+    wqkv = (torch.randn((hq + 2 * hkv) * D, K, generator=g(13)) * 0.05).to(BF)
+    xn = lm_ops.rms_norm(hid, nw, 1e-5)
+    qkv = _gemm_ref(xn, wqkv).to(BF)
+    q, k, v = qkv[:, : hq * D].view(T, hq, D), qkv[:, hq * D:(hq + hkv) * D].view(T, hkv, D), \
+        qkv[:, (hq + hkv) * D:].view(T, hkv, D)
+    kv_lens = [int(x) for x in torch.randint(1, 70, (T,), generator=g(14))]
+    indptr, indices, last = _random_page_table(kv_lens, page_size, n_pages, 21)
+    pos = torch.tensor(kv_lens, dtype=torch.int32) - 1 + 1000
+    kw = dict(rope_scale=32.0, rope_theta=500000.0, low_freq_factor=1.0, high_freq_factor=4.0, old_context_len=8192)
+    rq, rk = lm_ops.apply_rope_pos_ids(q, k, pos, **kw)
+    cache = torch.zeros(n_pages, 2, page_size, hkv, D, dtype=BF)
+    pages, slots = lm_ops.decode_slots(indptr, indices, last)
+    lm_ops.kv_append(cache, rk, v, pages, slots)
+    plan = ops.RowPlan(max(T, 8), "cuda")
+    ops.plan_rows(plan, None, _i32(indptr), _i32(indices), _i32(last), T, T, page_size, 16)
+    freq = ops.rope_freq_table(D, 32.0, 500000.0, False, 1.0, 4.0, 8192)
+    cs = ops.rope_table(pos.cuda(), freq, D)
+    ssq = ops.row_ssq(hid.cuda()).view(1, T)
+    assert torch.allclose(ssq.cpu()[0], (hid.float() ** 2).sum(-1), rtol=1e-5)
+    tol = 2e-3 * qkv.float().abs().max().item() + 1e-4
+    for rep in range(2):
+        dcache = torch.zeros_like(cache).cuda()
+        gq = ops.proj_norm_qkv_rope_append(hid.cuda(), ssq, 1, nw.cuda(), 1e-5, wqkv.cuda(), dcache, cs, plan, hq, hkv, D,
+                                           split)
+        assert_bf16_close(gq, rq, 2, 3e-2, "fused qkv: q", atol=2 * tol)
+        assert_bf16_close(dcache, cache, 2, 3e-2, "fused qkv: kv append", atol=2 * tol)
+        untouched = torch.ones(n_pages, page_size, dtype=torch.bool)
+        untouched[torch.tensor(pages), torch.tensor(slots)] = False
+        assert dcache.cpu()[:, 0][untouched].abs().max().item() == 0, "wrote outside the rows' slots"
+
+
 def test_embedding_gather_pcm_codes(ops):
     table = torch.randn(500, 768, generator=g(1)).to(BF)
     ids = torch.randint(0, 500, (33,), generator=g(2), dtype=torch.int32)

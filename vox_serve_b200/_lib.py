@@ -36,7 +36,15 @@ SIGNATURES = {
     "vb_paged_attn": (c_int, [P, P, P, c_int64, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_float, P, c_size_t, c_int, c_int, P]),
     "vb_gemm_t_tile": (c_int, [c_int]),
-    "vb_gemm_bf16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_size_t, P]),
+    "vb_weight_tiles_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "vb_pack_weight_tiles": (c_int, [P, P, c_int, c_int, c_int64, c_int, P]),
+    "vb_gemm_bf16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_proj_residual": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_proj_norm_gateup_silu": (c_int, [P, P, P, P, c_int, P, c_float, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_proj_norm_qkv_rope_append": (c_int, [P, P, P, P, P, c_int, P, c_float, P, P, P, c_int, c_int, c_int, c_int,
+                                             c_int, c_int, c_int, P]),
+    "vb_rope_table": (c_int, [P, P, P, c_int, c_int, P]),
+    "vb_row_ssq": (c_int, [P, P, c_int, c_int, P]),
     "vb_reduce_residual_rmsnorm": (c_int, [P, P, P, c_int, P, P, c_int, c_int, c_float, P]),
     "vb_qkv_rope_append": (c_int, [P, P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_embedding": (c_int, [P, P, P, c_int, c_int, c_int, P]),
@@ -95,7 +103,7 @@ def check(rc: int, what: str = ""):
 
 
 # kernels (+ memset nodes) each entry point enqueues; everything not listed launches exactly one
-LAUNCHES = {"vb_set_pdl": 0, "vb_tensor_map_kv": 0, "vb_tensor_map_2d_bf16": 0, "vb_device_info": 0, "vb_sample": 1,
+LAUNCHES = {"vb_set_pdl": 0, "vb_weight_tiles_bytes": 0, "vb_tensor_map_kv": 0, "vb_tensor_map_2d_bf16": 0, "vb_device_info": 0, "vb_sample": 1,
             "vb_update_repetition_cache": 1}
 launch_counter = [0]
 

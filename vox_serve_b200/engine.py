@@ -2,10 +2,12 @@
 (vox_serve/model/orpheus.py:125-221) as a fixed sequence of C-ABI launches over preallocated buffers, so
 the whole step is CUDA-graph capturable (no host sync, no allocation).
 
-Per layer (8 launches; the reference issues ~18-20):
-    QKV GEMM (split-K partials)  ->  reduce + RoPE + KV-append  ->  paged attention
-    -> O GEMM (partials) -> reduce + residual + post-attention RMSNorm
-    -> gate/up GEMM with SiLU*up epilogue -> down GEMM (partials) -> reduce + residual + next RMSNorm
+Decode-sized steps (<= 64 rows), 5 launches per layer (the reference issues ~18-20):
+    [RMSNorm -> QKV projection -> RoPE -> KV append]  ->  paged attention
+    -> [O projection -> + residual (+ sums of squares for the next norm)]
+    -> [RMSNorm -> gate/up projection -> SiLU * up]  ->  [down projection -> + residual (+ sums of squares)]
+Larger steps (prefill), 8 launches per layer: the same projections leaving fp32 split-K partials, with the
+reduce / RoPE / append and reduce / residual / RMSNorm tails as separate kernels.
 Rounding points follow the reference module graph: every Linear / RMSNorm / RoPE / attention output and
 every residual add is rounded to bf16.
 """
@@ -53,10 +55,12 @@ def hf_layer_names(i: int) -> Dict[str, str]:
 
 class LlamaWeights:
     """Device-resident weights in the layout the kernels stream: q|k|v rows concatenated, gate/up rows
-    interleaved per 128-row tile (ops.interleave_gate_up); built from an HF-named state dict."""
+    packed per tile as h gate rows + the h matching up rows (ops.interleave_gate_up; h is chosen so that the
+    projection splits into about one tile per SM); built from an HF-named state dict."""
 
     def __init__(self, dims: LlamaDims, device="cuda"):
         self.dims, self.device = dims, torch.device(device)
+        self.gu_half = ops.gate_up_tile_half(dims.intermediate_size) if self.device.type == "cuda" else 64
         self.embed = self.norm = self.lm_head = None
         self.layers: List[Dict[str, torch.Tensor]] = []
 
@@ -70,24 +74,32 @@ class LlamaWeights:
 
         self.embed = put(sd["model.embed_tokens.weight"])
         self.norm = put(sd["model.norm.weight"])
-        self.lm_head = put(sd["lm_head.weight"] if "lm_head.weight" in sd else sd["model.embed_tokens.weight"])
+        self.lm_head = ops.pack_weight(put(sd["lm_head.weight"] if "lm_head.weight" in sd
+                                           else sd["model.embed_tokens.weight"]), 128)
         for i in range(dims.num_hidden_layers):
             n = hf_layer_names(i)
             self.layers.append(self.pack_layer(put(sd[n["ln1"]]), put(sd[n["q"]]), put(sd[n["k"]]), put(sd[n["v"]]),
                                                put(sd[n["o"]]), put(sd[n["ln2"]]), put(sd[n["gate"]]),
-                                               put(sd[n["up"]]), put(sd[n["down"]])))
+                                               put(sd[n["up"]]), put(sd[n["down"]]), self.gu_half, dims.head_dim))
         return self
 
     @staticmethod
-    def pack_layer(ln1, q, k, v, o, ln2, gate, up, down) -> Dict[str, torch.Tensor]:
-        return {"ln1": ln1, "ln2": ln2, "qkv": torch.cat((q, k, v), 0).contiguous(), "o": o,
-                "gu": ops.interleave_gate_up(gate, up), "down": down}
+    def pack_layer(ln1, q, k, v, o, ln2, gate, up, down, gu_half: int = 64, head_dim: int = 128) -> Dict[str, object]:
+        """Projection weights leave here re-tiled for the GEMM kernel (ops.pack_weight): one head per QKV tile,
+        128-row O / down tiles, gu_half gate + gu_half up rows per gate/up tile.  The row-major copies are dropped."""
+        return {"ln1": ln1, "ln2": ln2, "qkv": ops.pack_weight(torch.cat((q, k, v), 0).contiguous(), head_dim),
+                "o": ops.pack_weight(o, 128),
+                "gu": ops.pack_weight(ops.interleave_gate_up(gate, up, gu_half), 2 * gu_half),
+                "down": ops.pack_weight(down, 128)}
 
     def nbytes(self) -> int:
-        n = self.embed.numel() + self.norm.numel() + self.lm_head.numel()
+        """logical bf16 bytes (N * K * 2 per projection; the packed tiles add only tail padding)"""
+        def nb(t):
+            return t.logical_bytes() if isinstance(t, ops.PackedWeight) else 2 * t.numel()
+        n = nb(self.embed) + nb(self.norm) + nb(self.lm_head)
         for l in self.layers:
-            n += sum(t.numel() for t in l.values())
-        return 2 * n
+            n += sum(nb(t) for t in l.values())
+        return n
 
     def streamed_bytes_per_step(self) -> int:
         """Weight bytes one decode step must read (everything but the embedding table)."""
@@ -129,6 +141,17 @@ class LlamaEngine:
                                         d.high_freq_factor, d.old_context_len, device=dev)
         self.plan = ops.RowPlan(R, dev)
         self.attn_grid = self.attn_ws.grid
+        # ---- fused decode path (<= FUSED_MAX_ROWS rows) ----
+        self.gu_half = weights.gu_half
+        self.fused_ok = D in (64, 128) and H % 64 == 0
+        # split-K of the fused QKV projection: one head per tile
+        self.fsplit_qkv = ops.proj_split_k(hq + 2 * hkv, H, self.sms)
+        self.fsplit_o = ops.proj_split_k((H + 127) // 128, hq * D, self.sms)
+        self.fsplit_down = ops.proj_split_k((H + 127) // 128, I, self.sms)
+        self.ssq = torch.zeros(max(1, (H + 127) // 128) * self.FUSED_MAX_ROWS, dtype=torch.float32, device=dev)
+        self.rope_cs = torch.zeros(self.FUSED_MAX_ROWS, 2, D, dtype=torch.float32, device=dev)
+
+    FUSED_MAX_ROWS = 64
 
     def _partials(self, split: int, rows: int, width: int) -> torch.Tensor:
         return self.partials[: split * rows * width].view(split, rows, width)
@@ -147,33 +170,13 @@ class LlamaEngine:
         plan = self.plan if plan is None else plan
         if R > self.max_rows:
             raise VoxB200Error(f"{R} rows exceed the engine's max_rows {self.max_rows}")
-        hq, hkv, D, H, I = d.num_attention_heads, d.num_key_value_heads, d.head_dim, d.hidden_size, d.intermediate_size
         hidden, normed = self.hidden[:R], self.normed[:R]
         ops.embedding(w.embed, input_ids, out=hidden)
-        ops.rmsnorm(hidden, w.layers[0]["ln1"], d.rms_norm_eps, out=normed)
-        s_qkv, s_o, s_dn = self._split(self.split_qkv, R), self._split(self.split_o, R), self._split(self.split_down, R)
-        q, attn, act = self.q[:R], self.attn[:R], self.act[:R]
-        # Optional: every projection can pull the NEXT projection's weights into L2 (vb_gemm_bf16's d_prefetch).
-        # Measured on B200 (tests/bench_prefetch.py) it is a net loss at these shapes -- the prefetching kernel
-        # slows by 4-10 us, the next one gains only ~2 us because skinny GEMMs are latency-, not bandwidth-bound --
-        # so it stays off.
-        pf = False
-        n_layers = len(w.layers)
-        for i, L in enumerate(w.layers):
-            p = ops.gemm(normed, L["qkv"], mode=1, split_k=s_qkv, out=self._partials(s_qkv, R, self.qkv_w),
-                         prefetch=L["o"] if pf else None)
-            ops.qkv_rope_append(p, self.kv_cache[i], position_ids, self.freq, plan, hq, hkv, D, q_out=q)
-            ops.paged_attn(q, self.kv_map, i * self.pages_per_layer, plan, R, hkv, self.page_size, self.chunk,
-                           self.attn_ws, out=attn, grid_ctas=self.attn_grid)
-            p = ops.gemm(attn.view(R, hq * D), L["o"], mode=1, split_k=s_o, out=self._partials(s_o, R, H),
-                         prefetch=L["gu"] if pf else None)
-            ops.reduce_residual_rmsnorm(p, hidden, L["ln2"], d.rms_norm_eps, hidden_out=hidden, normed_out=normed)
-            ops.gemm(normed, L["gu"], mode=2, out=act, prefetch=L["down"] if pf else None)
-            nxt_w = w.layers[i + 1]["qkv"] if i + 1 < n_layers else w.lm_head
-            p = ops.gemm(act, L["down"], mode=1, split_k=s_dn, out=self._partials(s_dn, R, H),
-                         prefetch=nxt_w if pf else None, prefetch_bytes=min(nxt_w.numel() * 2, 96 << 20))
-            nxt = w.layers[i + 1]["ln1"] if i + 1 < n_layers else w.norm
-            ops.reduce_residual_rmsnorm(p, hidden, nxt, d.rms_norm_eps, hidden_out=hidden, normed_out=normed)
+        if R <= self.FUSED_MAX_ROWS and self.fused_ok and not self.force_unfused:
+            self._layers_fused(position_ids, R, plan)
+            ops.rmsnorm(hidden, w.norm, d.rms_norm_eps, out=normed)
+        else:
+            self._layers_unfused(position_ids, R, plan)
         if last_rows is not None:
             n_out = last_rows.numel() if n_out is None else n_out
             x = ops.gather_rows(normed, last_rows, out=self.last_normed[:n_out], idx_offset=last_rows_offset)
@@ -181,22 +184,71 @@ class LlamaEngine:
             n_out, x = R, normed
         if n_out > self.max_out_rows:
             raise VoxB200Error(f"logits requested for {n_out} rows; pass last_rows (max {self.max_out_rows})")
-        return ops.gemm(x, w.lm_head, mode=0, out=self.logits[:n_out], prefetch=w.layers[0]["qkv"] if pf else None)
+        return ops.gemm(x, w.lm_head, mode=0, out=self.logits[:n_out])
+
+    force_unfused = False     # tests: run decode-sized steps through the 8-launch path too
+
+    def _layers_fused(self, position_ids: torch.Tensor, R: int, plan: ops.RowPlan) -> None:
+        """5 launches per layer; hidden is updated in place, the RMSNorm statistics travel as per-tile sums of
+        squares written by the residual projections (ssq[parts][R])."""
+        d, w = self.dims, self.w
+        hq, hkv, D, H, I = d.num_attention_heads, d.num_key_value_heads, d.head_dim, d.hidden_size, d.intermediate_size
+        hidden, q, attn, act = self.hidden[:R], self.q[:R], self.attn[:R], self.act[:R]
+        tiles_h = (H + 127) // 128
+        ssq = self.ssq[: tiles_h * R].view(tiles_h, R)
+        cs = ops.rope_table(position_ids[:R], self.freq, D, out=self.rope_cs[:R])
+        ops.row_ssq(hidden, out=ssq[0])
+        parts = 1
+        for i, L in enumerate(w.layers):
+            ops.proj_norm_qkv_rope_append(hidden, ssq, parts, L["ln1"], d.rms_norm_eps, L["qkv"], self.kv_cache[i], cs,
+                                          plan, hq, hkv, D, self.fsplit_qkv, q_out=q)
+            ops.paged_attn(q, self.kv_map, i * self.pages_per_layer, plan, R, hkv, self.page_size, self.chunk,
+                           self.attn_ws, out=attn, grid_ctas=self.attn_grid)
+            ops.proj_residual(attn.view(R, hq * D), L["o"], hidden, self.fsplit_o, hidden_out=hidden,
+                              ssq_out=ssq)
+            parts = tiles_h
+            ops.proj_norm_gateup_silu(hidden, ssq, parts, L["ln2"], d.rms_norm_eps, L["gu"], self.gu_half, I, out=act)
+            ops.proj_residual(act, L["down"], hidden, self.fsplit_down, hidden_out=hidden, ssq_out=ssq)
+
+    def _layers_unfused(self, position_ids: torch.Tensor, R: int, plan: ops.RowPlan) -> None:
+        d, w = self.dims, self.w
+        hq, hkv, D, H, I = d.num_attention_heads, d.num_key_value_heads, d.head_dim, d.hidden_size, d.intermediate_size
+        hidden, normed = self.hidden[:R], self.normed[:R]
+        ops.rmsnorm(hidden, w.layers[0]["ln1"], d.rms_norm_eps, out=normed)
+        s_qkv, s_o, s_dn = self._split(self.split_qkv, R), self._split(self.split_o, R), self._split(self.split_down, R)
+        q, attn, act = self.q[:R], self.attn[:R], self.act[:R]
+        n_layers = len(w.layers)
+        for i, L in enumerate(w.layers):
+            p = ops.gemm(normed, L["qkv"], mode=1, split_k=s_qkv, out=self._partials(s_qkv, R, self.qkv_w), tile_rows=D)
+            ops.qkv_rope_append(p, self.kv_cache[i], position_ids, self.freq, plan, hq, hkv, D, q_out=q)
+            ops.paged_attn(q, self.kv_map, i * self.pages_per_layer, plan, R, hkv, self.page_size, self.chunk,
+                           self.attn_ws, out=attn, grid_ctas=self.attn_grid)
+            p = ops.gemm(attn.view(R, hq * D), L["o"], mode=1, split_k=s_o, out=self._partials(s_o, R, H))
+            ops.reduce_residual_rmsnorm(p, hidden, L["ln2"], d.rms_norm_eps, hidden_out=hidden, normed_out=normed)
+            ops.gemm(normed, L["gu"], mode=2, out=act, tile_rows=2 * self.gu_half, n_out=I)
+            p = ops.gemm(act, L["down"], mode=1, split_k=s_dn, out=self._partials(s_dn, R, H))
+            nxt = w.layers[i + 1]["ln1"] if i + 1 < n_layers else w.norm
+            ops.reduce_residual_rmsnorm(p, hidden, nxt, d.rms_norm_eps, hidden_out=hidden, normed_out=normed)
 
     # ---- kernel-isolated passes for the roofline measurement (bench.py) --------------------------------
     def gemm_pass(self, n_rows: int) -> None:
         """Every projection launch of one decode step (QKV, O, gate/up, down per layer + lm_head) on the live
-        buffers, nothing else: what bench.py replays to time the GEMM kernel alone."""
+        buffers, nothing else: what bench.py replays to time the projection kernel alone (fused decode modes:
+        the norm / RoPE / append / SiLU / residual work rides inside these launches)."""
         d, w, R = self.dims, self.w, n_rows
-        hq, D, H = d.num_attention_heads, d.head_dim, d.hidden_size
-        s_qkv, s_o, s_dn = self._split(self.split_qkv, R), self._split(self.split_o, R), self._split(self.split_down, R)
-        normed, attn, act = self.normed[:R], self.attn[:R], self.act[:R]
-        for L in w.layers:
-            ops.gemm(normed, L["qkv"], mode=1, split_k=s_qkv, out=self._partials(s_qkv, R, self.qkv_w))
-            ops.gemm(attn.view(R, hq * D), L["o"], mode=1, split_k=s_o, out=self._partials(s_o, R, H))
-            ops.gemm(normed, L["gu"], mode=2, out=act)
-            ops.gemm(act, L["down"], mode=1, split_k=s_dn, out=self._partials(s_dn, R, H))
-        ops.gemm(normed[:min(R, self.max_out_rows)], w.lm_head, mode=0, out=self.logits[:min(R, self.max_out_rows)])
+        hq, hkv, D, H, I = d.num_attention_heads, d.num_key_value_heads, d.head_dim, d.hidden_size, d.intermediate_size
+        hidden, q, attn, act = self.hidden[:R], self.q[:R], self.attn[:R], self.act[:R]
+        tiles_h = (H + 127) // 128
+        ssq = self.ssq[: tiles_h * R].view(tiles_h, R)
+        cs = self.rope_cs[:R]
+        for i, L in enumerate(w.layers):
+            ops.proj_norm_qkv_rope_append(hidden, ssq, tiles_h, L["ln1"], d.rms_norm_eps, L["qkv"], self.kv_cache[i], cs,
+                                          self.plan, hq, hkv, D, self.fsplit_qkv, q_out=q)
+            ops.proj_residual(attn.view(R, hq * D), L["o"], hidden, self.fsplit_o, hidden_out=hidden,
+                              ssq_out=ssq)
+            ops.proj_norm_gateup_silu(hidden, ssq, tiles_h, L["ln2"], d.rms_norm_eps, L["gu"], self.gu_half, I, out=act)
+            ops.proj_residual(act, L["down"], hidden, self.fsplit_down, hidden_out=hidden, ssq_out=ssq)
+        ops.gemm(self.normed[:min(R, self.max_out_rows)], w.lm_head, mode=0, out=self.logits[:min(R, self.max_out_rows)])
 
     def attention_only(self, layer: int, n_rows: int, plan: ops.RowPlan) -> None:
         """The paged-attention launch of one layer on the live cache and the plan of the last step."""

@@ -253,40 +253,172 @@ def choose_split_k(N: int, K: int, T: int, sms: Optional[int] = None) -> int:
     return max(1, min(num_kb // 4 if num_kb >= 4 else 1, sms // tiles))
 
 
-def gemm(x: torch.Tensor, w: torch.Tensor, mode: int = 0, split_k: int = 1, out: Optional[torch.Tensor] = None,
-         w_map: Optional[TensorMap] = None, prefetch: Optional[torch.Tensor] = None,
-         prefetch_bytes: Optional[int] = None) -> torch.Tensor:
-    """x [T, K] bf16, w [N, K] bf16 (nn.Linear.weight layout).
-    mode 0 -> bf16 [T, N]; mode 1 -> fp32 partials [split_k, T, N]; mode 2 -> bf16 [T, N/2] = silu(gate)*up
-    with w rows interleaved per 128-row tile (see interleave_gate_up)."""
-    _need_cuda(x, w)
-    assert x.dtype == BF16 and w.dtype == BF16 and x.dim() == 2 and w.dim() == 2 and x.shape[1] == w.shape[1]
+class PackedWeight:
+    """A projection weight [N, K] re-tiled for the GEMM kernel (vb_pack_weight_tiles): [n_tile][k_block][tile_rows][64]
+    bf16, pre-swizzled, every (tile, k-block) operand one contiguous run in HBM."""
+    __slots__ = ("data", "N", "K", "tile_rows")
+
+    def __init__(self, data: torch.Tensor, N: int, K: int, tile_rows: int):
+        self.data, self.N, self.K, self.tile_rows = data, N, K, tile_rows
+
+    @property
+    def shape(self):
+        return (self.N, self.K)
+
+    def logical_bytes(self) -> int:
+        return 2 * self.N * self.K
+
+
+def pack_weight(w: torch.Tensor, tile_rows: int = 128) -> PackedWeight:
+    _need_cuda(w)
+    assert w.dtype == BF16 and w.dim() == 2 and w.stride(1) == 1
+    N, K = w.shape
+    n = _lib.load().vb_weight_tiles_bytes(N, K, tile_rows)
+    assert n > 0, (N, K, tile_rows)
+    dst = torch.empty(n, dtype=torch.uint8, device=w.device)
+    call("vb_pack_weight_tiles", dst.data_ptr(), w.data_ptr(), N, K, w.stride(0), tile_rows, _stream())
+    return PackedWeight(dst, N, K, tile_rows)
+
+
+_pack_cache: Dict[Tuple, PackedWeight] = {}
+
+
+def _packed(w, tile_rows: int) -> PackedWeight:
+    """PackedWeight as is; a plain [N, K] tensor is packed on first use (convenience for tests / one-off calls --
+    the engine packs at load time and drops the row-major copy)."""
+    if isinstance(w, PackedWeight):
+        assert w.tile_rows == tile_rows, f"weight packed for tile_rows {w.tile_rows}, kernel wants {tile_rows}"
+        return w
+    key = (w.data_ptr(), tuple(w.shape), w.stride(0), tile_rows, w._version)
+    pw = _pack_cache.get(key)
+    if pw is None:
+        if len(_pack_cache) > 64:
+            _pack_cache.clear()
+        pw = _pack_cache[key] = pack_weight(w, tile_rows)
+    return pw
+
+
+def gemm(x: torch.Tensor, w, mode: int = 0, split_k: int = 1, out: Optional[torch.Tensor] = None,
+         tile_rows: int = 128, n_out: Optional[int] = None) -> torch.Tensor:
+    """x [T, K] bf16, w [N, K] bf16 (nn.Linear.weight layout, or a PackedWeight).
+    mode 0 -> bf16 [T, N]; mode 1 -> fp32 partials [split_k, T, N]; mode 2 -> bf16 [T, n_out] = silu(gate)*up
+    with w rows packed per tile_rows-row tile (see interleave_gate_up; n_out defaults to N/2)."""
+    _need_cuda(x)
+    pw = _packed(w, tile_rows)
+    assert x.dtype == BF16 and x.dim() == 2 and x.shape[1] == pw.K
     T, K = x.shape
-    N = w.shape[0]
-    n_out = N // 2 if mode == 2 else N
+    N = pw.N
+    n_out = (N // 2 if mode == 2 else N) if n_out is None else n_out
     if out is None:
         if mode == 1:
             out = torch.empty(split_k, T, n_out, dtype=torch.float32, device=x.device)
         else:
             out = torch.empty(T, n_out, dtype=BF16, device=x.device)
-    w_map = tensor_map_2d(w, 128) if w_map is None else w_map
     x_map = tensor_map_2d(x, gemm_t_tile(T))
-    pf_ptr, pf_bytes = None, 0
-    if prefetch is not None:      # the next projection's weights: pulled into L2 by this kernel's idle warps
-        pf_ptr = prefetch.data_ptr()
-        pf_bytes = prefetch.numel() * prefetch.element_size() if prefetch_bytes is None else int(prefetch_bytes)
-    call("vb_gemm_bf16", out.data_ptr(), w_map.ptr, x_map.ptr, T, N, K, n_out, mode, split_k, pf_ptr, pf_bytes,
+    call("vb_gemm_bf16", out.data_ptr(), pw.data.data_ptr(), x_map.ptr, T, N, K, n_out, mode, split_k, tile_rows, n_out,
          _stream())
     return out
 
 
-def interleave_gate_up(gate_w: torch.Tensor, up_w: torch.Tensor) -> torch.Tensor:
-    """[I, K] x 2 -> [2I, K] with rows grouped per 128-row tile as 64 gate rows then the 64 matching up rows."""
+def gate_up_tile_half(I: int, sms: Optional[int] = None) -> int:
+    """Gate rows per tile (h; a tile is h gate rows + the h matching up rows) so that the gate/up projection is cut
+    into about one CTA per SM: the smallest multiple of 8 with ceil(I / h) <= SMs, at most 64."""
+    sms = device_info()[0] if sms is None else sms
+    h = max(8, ((I + sms - 1) // sms + 7) // 8 * 8)
+    return min(h, 64)
+
+
+def interleave_gate_up(gate_w: torch.Tensor, up_w: torch.Tensor, h: int = 64) -> torch.Tensor:
+    """[I, K] x 2 -> [2 * ceil(I/h) * h, K]: per tile h gate rows then the h matching up rows; I is zero-padded to a
+    multiple of h (the padded outputs are never stored)."""
     I, K = gate_w.shape
-    assert up_w.shape == gate_w.shape and I % 64 == 0
-    g = gate_w.view(I // 64, 64, K)
-    u = up_w.view(I // 64, 64, K)
-    return torch.cat((g, u), dim=1).reshape(2 * I, K).contiguous()
+    assert up_w.shape == gate_w.shape and h % 8 == 0
+    tiles = (I + h - 1) // h
+    if tiles * h != I:
+        pad = torch.zeros(tiles * h - I, K, dtype=gate_w.dtype, device=gate_w.device)
+        gate_w, up_w = torch.cat((gate_w, pad), 0), torch.cat((up_w, pad), 0)
+    g = gate_w.view(tiles, h, K)
+    u = up_w.view(tiles, h, K)
+    return torch.cat((g, u), dim=1).reshape(2 * tiles * h, K).contiguous()
+
+
+def fused_t_tile(T: int) -> int:
+    return 16 if T <= 16 else (32 if T <= 32 else 64)
+
+
+def proj_split_k(n_tiles: int, K: int, sms: Optional[int] = None) -> int:
+    """split-K of a fused (cluster-reduced) projection: about one CTA per SM, at most 8 CTAs per tile, at least
+    4 K-blocks per CTA."""
+    sms = device_info()[0] if sms is None else sms
+    num_kb = (K + 63) // 64
+    return max(1, min(8, sms // max(1, n_tiles), max(1, num_kb // 4)))
+
+
+def proj_residual(x: torch.Tensor, w: torch.Tensor, residual: Optional[torch.Tensor], split_k: int,
+                  hidden_out: Optional[torch.Tensor] = None, ssq_out: Optional[torch.Tensor] = None,
+                  tile_rows: int = 128):
+    """hidden_out [T, N] = bf16(residual + bf16(x w^T)); ssq_out fp32 [ceil(N/tile_rows), T] per-tile sums of squares
+    of the new rows.  T <= 64."""
+    _need_cuda(x)
+    pw = _packed(w, tile_rows)
+    T, K = x.shape
+    N = pw.N
+    tiles = (N + tile_rows - 1) // tile_rows
+    hidden_out = torch.empty(T, N, dtype=BF16, device=x.device) if hidden_out is None else hidden_out
+    ssq_out = torch.empty(tiles, T, dtype=torch.float32, device=x.device) if ssq_out is None else ssq_out
+    assert ssq_out.numel() >= tiles * T and K == pw.K
+    x_map = tensor_map_2d(x, fused_t_tile(T))
+    call("vb_proj_residual", hidden_out.data_ptr(), ssq_out.data_ptr(), pw.data.data_ptr(), x_map.ptr, _p(residual), T, N, K,
+         split_k, tile_rows, _stream())
+    return hidden_out, ssq_out
+
+
+def proj_norm_gateup_silu(hidden: torch.Tensor, ssq: torch.Tensor, n_parts: int, norm_w: torch.Tensor, eps: float,
+                          w_packed: torch.Tensor, h: int, n_out: int, out: Optional[torch.Tensor] = None):
+    """act [T, n_out] = silu(gate(xn)) * up(xn) with xn = rmsnorm(hidden) * norm_w formed inside the kernel."""
+    _need_cuda(hidden, ssq, norm_w)
+    pw = _packed(w_packed, 2 * h)
+    T, K = hidden.shape
+    out = torch.empty(T, n_out, dtype=BF16, device=hidden.device) if out is None else out
+    x_map = tensor_map_2d(hidden, fused_t_tile(T))
+    call("vb_proj_norm_gateup_silu", out.data_ptr(), pw.data.data_ptr(), x_map.ptr, ssq.data_ptr(), n_parts,
+         norm_w.data_ptr(), float(eps), T, pw.N, K, 2 * h, n_out, _stream())
+    return out
+
+
+def proj_norm_qkv_rope_append(hidden: torch.Tensor, ssq: torch.Tensor, n_parts: int, norm_w: torch.Tensor, eps: float,
+                              w_qkv: torch.Tensor, layer_kv: torch.Tensor, rope_cs: torch.Tensor, plan: "RowPlan",
+                              n_q: int, n_kv: int, head_dim: int, split_k: int,
+                              q_out: Optional[torch.Tensor] = None):
+    """q [T, n_q, D] (rotated) and the rotated k / v of every row written to its page slot; see vb_api.h."""
+    _need_cuda(hidden, ssq, norm_w, layer_kv, rope_cs)
+    pw = _packed(w_qkv, head_dim)
+    T, K = hidden.shape
+    assert pw.N == (n_q + 2 * n_kv) * head_dim
+    q_out = torch.empty(T, n_q, head_dim, dtype=BF16, device=hidden.device) if q_out is None else q_out
+    x_map = tensor_map_2d(hidden, fused_t_tile(T))
+    page_size = layer_kv.shape[-3]
+    call("vb_proj_norm_qkv_rope_append", q_out.data_ptr(), layer_kv.data_ptr(), pw.data.data_ptr(), x_map.ptr,
+         ssq.data_ptr(), n_parts, norm_w.data_ptr(), float(eps), rope_cs.data_ptr(), plan.row_page.data_ptr(),
+         plan.row_slot.data_ptr(), T, K, n_q, n_kv, head_dim, page_size, split_k, _stream())
+    return q_out
+
+
+def rope_table(pos: torch.Tensor, freq: torch.Tensor, head_dim: int, out: Optional[torch.Tensor] = None):
+    """cos | sin of pos[t] * freq[e]: fp32 [T, 2, D], shared by every layer of the step."""
+    _need_cuda(pos, freq)
+    T = pos.numel()
+    out = torch.empty(T, 2, head_dim, dtype=torch.float32, device=pos.device) if out is None else out
+    call("vb_rope_table", out.data_ptr(), pos.data_ptr(), freq.data_ptr(), T, head_dim, _stream())
+    return out
+
+
+def row_ssq(x: torch.Tensor, out: Optional[torch.Tensor] = None):
+    _need_cuda(x)
+    T, dim = x.shape
+    out = torch.empty(T, dtype=torch.float32, device=x.device) if out is None else out
+    call("vb_row_ssq", out.data_ptr(), x.data_ptr(), T, dim, _stream())
+    return out
 
 
 def reduce_residual_rmsnorm(partials: torch.Tensor, residual: Optional[torch.Tensor],
