@@ -34,6 +34,10 @@ int vb_version(void);
 int vb_set_pdl(int enabled);
 /* SM count / max dynamic smem of the current device (host query used to size persistent grids). */
 int vb_device_info(int* sm_count, int* max_smem_optin);
+/* dev tool: install (or with NULL remove) a device buffer of u64 words -- [0] = records used (zero it), [1] = capacity,
+ * records from word 4 on: {t0, t1 (globaltimer ns), kernel/mark id, aux} -- in which block 0 of the decode-step
+ * kernels logs its start / end and a few internal marks: the in-situ timeline of a CUDA-graph replay. */
+int vb_set_trace(void* d_buffer);
 
 /* ---- TMA descriptors ------------------------------------------------------------------------ */
 /* Whole paged KV cache  [n_slabs = layers*pages][2][page_size][n_kv_heads][head_dim] bf16
@@ -145,6 +149,37 @@ int vb_proj_norm_qkv_rope_append(void* d_q_out, void* d_layer_kv, const void* d_
                                  const float* d_ssq, int n_ssq_parts, const void* d_norm_weight, float eps,
                                  const float* d_rope_cs, const int32_t* d_row_page, const int32_t* d_row_slot, int T,
                                  int K, int n_q, int n_kv, int head_dim, int page_size, int split_k, void* stream);
+/* ---- persistent projection chain (T <= 64): up to 4 dependent fused projections in ONE launch --------------------
+ * The part of a decoder layer between two attention calls -- O-proj + residual -> RMSNorm + gate/up + SiLU*up ->
+ * down-proj + residual -> RMSNorm + QKV(next layer) + RoPE + KV append (orpheus.py:81-151) -- as one kernel of at
+ * most one CTA per SM whose weight stream runs ahead across the phase boundaries (the dependencies are grid-wide
+ * arrival counters in d_flags, the weights of the next phase are already in shared memory when they resolve).
+ * Each phase is one of the fused projections above (same arguments, same arithmetic):
+ *   kind 0 = vb_proj_residual, kind 1 = vb_proj_norm_gateup_silu, kind 2 = vb_proj_norm_qkv_rope_append.
+ * Every phase needs n_tiles * split_k <= SM count.  d_flags (vb_decode_chain_flags_bytes(max_tiles)) must be ZERO at
+ * launch; d_workspace (vb_decode_chain_workspace_bytes(max n_tiles * split_k)) holds the split-K partial tiles. */
+typedef struct vb_chain_phase {
+  int32_t kind;
+  int32_t N, K, tile_rows, split_k;
+  int32_t n_out;             /* kind 1: gate/up outputs (intermediate size); others: 0 */
+  int32_t n_ssq_parts;       /* kinds 1, 2 */
+  float eps;                 /* kinds 1, 2 */
+  const void* w_tiles;       /* vb_pack_weight_tiles(W, N, K, ldw, tile_rows) */
+  const void* x_map;         /* host CUtensorMap of the phase input [T][K], box t_tile (16 / 32 / 64) rows */
+  void* out;                 /* kind 0: hidden_out [T][N]; kind 1: act [T][n_out]; kind 2: q_out [T][n_q][D] */
+  const void* residual;      /* kind 0 (may alias out, may be NULL) */
+  float* ssq_out;            /* kind 0: [tiles][T] or NULL */
+  const float* ssq_in;       /* kinds 1, 2: [n_ssq_parts][T] */
+  const void* norm_weight;   /* kinds 1, 2 */
+  void* layer_kv;            /* kind 2 */
+} vb_chain_phase;
+size_t vb_decode_chain_workspace_bytes(int max_items);
+size_t vb_decode_chain_flags_bytes(int max_tiles);
+int vb_decode_chain(const vb_chain_phase* phases, int n_phases, int T, const float* d_rope_cs,
+                    const int32_t* d_row_page, const int32_t* d_row_slot, int n_q, int n_kv, int page_size,
+                    void* d_workspace, size_t workspace_bytes, void* d_flags, size_t flags_bytes, int max_tiles,
+                    void* stream);
+
 /* cs[T][2][head_dim] = cos | sin of pos[t] * freq[e]: computed once per step, shared by all layers */
 int vb_rope_table(float* d_cs, const int32_t* d_pos, const float* d_freq, int T, int head_dim, void* stream);
 /* ssq[rows] = sum of squares of each bf16 row (RMSNorm statistics of a hidden state that did not come out of

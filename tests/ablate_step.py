@@ -80,6 +80,7 @@ def main():
         if "sample" not in skip:
             sample()
 
+    only = sys.argv[3].split(",") if len(sys.argv) > 3 else None
     variants = {
         "full": lambda: step(),
         "no_sample": lambda: step(("sample",)),
@@ -99,10 +100,18 @@ def main():
         eng.forward(ids, pos, B)
         eng.force_unfused = False
 
+    def nochain():
+        eng.use_chain = False
+        eng.forward(ids, pos, B)
+        eng.use_chain = True
+
     variants["unfused_forward"] = unfused
-    variants["fused_forward"] = lambda: eng.forward(ids, pos, B)
+    variants["fused_forward"] = nochain
+    variants["chain_forward"] = lambda: eng.forward(ids, pos, B)
 
     res = {}
+    if only:
+        variants = {k: v for k, v in variants.items() if k in only}
     for name, fn in variants.items():
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
@@ -125,6 +134,8 @@ def main():
         torch.cuda.synchronize()
         res[name] = e0.elapsed_time(e1) / reps
         print(json.dumps({"variant": name, "ms": round(res[name], 4), "kv_len": kv_len, "batch": B}), flush=True)
+    if "full" not in res:
+        return
     full = res["full"]
     w_bytes = w.streamed_bytes_per_step()
     kv_bytes = d.num_hidden_layers * B * kv_len * 2 * hkv * D * 2

@@ -19,7 +19,7 @@ def _i32(x):
     return torch.tensor(x, dtype=torch.int32, device="cuda")
 
 
-def _run(dims, page_size, max_pages, prompt_lens, n_steps, seed, max_bs=4, force_unfused=False):
+def _run(dims, page_size, max_pages, prompt_lens, n_steps, seed, max_bs=4, mode="chain"):
     from vox_serve_b200 import ops
     from vox_serve_b200.engine import LlamaDims, LlamaEngine, LlamaWeights
 
@@ -35,7 +35,9 @@ def _run(dims, page_size, max_pages, prompt_lens, n_steps, seed, max_bs=4, force
     kv = torch.zeros(dims.num_hidden_layers, max_pages, 2, page_size, dims.num_key_value_heads, dims.head_dim,
                      dtype=BF, device="cuda")
     eng = LlamaEngine(gw, kv, page_size, max_rows=256)
-    eng.force_unfused = force_unfused
+    eng.force_unfused = mode == "unfused"
+    eng.use_chain = mode == "chain"
+    assert eng.chain_ok
     g = torch.Generator().manual_seed(21)
     reqs = [oworker.Req(f"r{i}", torch.randint(10, dims.vocab_size, (n,), generator=g)) for i, n in enumerate(prompt_lens)]
     active = []
@@ -84,23 +86,25 @@ def _run(dims, page_size, max_pages, prompt_lens, n_steps, seed, max_bs=4, force
     return stats
 
 
-@pytest.mark.parametrize("force_unfused", [False, True])      # 5-launch fused layers / 8-launch (prefill-style) layers
-def test_tiny_orpheus_teacher_forced_greedy(force_unfused):
+# persistent chain (2 launches per layer) / one launch per fused projection (5) / prefill-style layers (8)
+@pytest.mark.parametrize("mode", ["chain", "fused", "unfused"])
+def test_tiny_orpheus_teacher_forced_greedy(mode):
     dims = oorph.OrpheusDims.tiny()
     dims.max_tokens = 400
     st = _run(dims, page_size=16, max_pages=128, prompt_lens=[5, 16, 30, 33], n_steps=60, seed=3,
-              force_unfused=force_unfused)
+              mode=mode)
     print(st)
     assert st["max_logit_err"] < 2e-2
     assert st["id_mismatch"] <= max(2, st["rows"] // 50)
 
 
-def test_medium_orpheus_page128_teacher_forced():
+@pytest.mark.parametrize("mode", ["chain", "fused"])
+def test_medium_orpheus_page128_teacher_forced(mode):
     # head_dim 128, GQA 3, page 128: the Orpheus attention geometry with a prompt crossing a page
     dims = oorph.OrpheusDims.tiny(hidden_size=1536, num_hidden_layers=3, num_attention_heads=12,
                                   num_key_value_heads=4, intermediate_size=2048, vocab_size=10 + 7 * 4096)
     dims.max_tokens = 400
-    st = _run(dims, page_size=128, max_pages=16, prompt_lens=[133, 120, 7], n_steps=24, seed=4)
+    st = _run(dims, page_size=128, max_pages=16, prompt_lens=[133, 120, 7], n_steps=24, seed=4, mode=mode)
     print(st)
     assert st["max_logit_err"] < 2e-2
     assert st["id_mismatch"] <= max(2, st["rows"] // 50)

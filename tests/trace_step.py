@@ -1,0 +1,91 @@
+"""Dev tool (GPU): in-situ timeline of one CUDA-graph replay of the decode step (block 0 of every instrumented kernel
+logs %globaltimer through vb_set_trace).  python tests/trace_step.py [kv_len] [mode: chain|fused|unfused] [first] [count]"""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from vox_serve_b200 import _lib, ops  # noqa: E402
+from vox_serve_b200.engine import LlamaDims, LlamaEngine, LlamaWeights  # noqa: E402
+from vox_serve_b200.model.orpheus import synthetic_state_dict  # noqa: E402
+
+NAMES = {1: "gemm", 2: "attn", 3: "chain", 4: "sample", 10: "rope_tab", 20: " gemm:dep-released", 21: " gemm:acc-done"}
+for p in range(4):
+    NAMES[30 + p] = f" chain:x-ready p{p}"
+    NAMES[40 + p] = f" chain:acc-done p{p}"
+    NAMES[50 + p] = f" chain:epi-done p{p}"
+
+
+def main():
+    kv_len = int(sys.argv[1]) if len(sys.argv) > 1 else 728
+    mode = sys.argv[2] if len(sys.argv) > 2 else "chain"
+    first = int(sys.argv[3]) if len(sys.argv) > 3 else 60
+    count = int(sys.argv[4]) if len(sys.argv) > 4 else 60
+    B, dev, ps = 32, "cuda", 128
+    d = LlamaDims.orpheus_3b()
+    w = LlamaWeights.from_state_dict(synthetic_state_dict(d, 0, dev), d, dev)
+    pages_req = (kv_len + ps) // ps + 1
+    n_pages = B * pages_req
+    kv = (torch.randn(d.num_hidden_layers, n_pages, 2, ps, d.num_key_value_heads, d.head_dim, device=dev) * 0.5).to(torch.bfloat16)
+    eng = LlamaEngine(w, kv, ps, max_rows=64)
+    eng.force_unfused = mode == "unfused"
+    eng.use_chain = mode == "chain"
+    npg = (kv_len + ps - 1) // ps
+    indptr = torch.arange(B + 1, dtype=torch.int32, device=dev) * npg
+    perm = torch.randperm(n_pages, device=dev).to(torch.int32)
+    indices = torch.cat([perm[r * pages_req: r * pages_req + npg] for r in range(B)]).contiguous()
+    last = torch.full((B,), kv_len - (npg - 1) * ps, dtype=torch.int32, device=dev)
+    ops.plan_rows(eng.plan, None, indptr, indices, last, B, B, ps, eng.chunk)
+    ids = torch.randint(128266, 156000, (B,), dtype=torch.int32, device=dev)
+    pos = torch.full((B,), kv_len - 1, dtype=torch.int32, device=dev)
+    cap = 4096
+    buf = torch.zeros(4 + 4 * cap + 6 * 256, dtype=torch.int64, device=dev)
+    buf[1] = cap
+    buf[2] = 4 + 4 * cap
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        eng.forward(ids, pos, B)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            eng.forward(ids, pos, B)
+    torch.cuda.current_stream().wait_stream(s)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    _lib.check(_lib.load().vb_set_trace(buf.data_ptr()), "vb_set_trace")
+    g.replay()
+    torch.cuda.synchronize()
+    _lib.check(_lib.load().vb_set_trace(None), "vb_set_trace")
+    h = buf.cpu()
+    n = min(int(h[0]), cap)
+    recs = h[4:4 + 4 * n].view(n, 4).tolist()
+    recs.sort(key=lambda r: r[0])
+    t_first = recs[0][0]
+    t_end = max(r[1] for r in recs)
+    print(f"mode {mode} kv_len {kv_len}: {n} records, step span {(t_end - t_first) / 1e3:.1f} us")
+    prev_end = None
+    for r in recs[first:first + count]:
+        t0, t1, kid, aux = r
+        name = NAMES.get(kid, str(kid))
+        dur = (t1 - t0) / 1e3
+        gap = "" if prev_end is None or name.startswith(" ") else f"  (starts {(t0 - prev_end) / 1e3:+.1f} us vs prev end)"
+        print(f"{(t0 - t_first) / 1e3:9.1f} us  {name:22s} aux {aux:2d}  dur {dur:7.1f} us{gap}")
+        if not name.startswith(" "):
+            prev_end = t1
+
+
+    fine = h[4 + 4 * cap:].view(6, 256)
+    if int(fine.max()) > 0 and len(sys.argv) > 5:
+        roles = ["w-issue", "x-issue", "full-seen", "cfull-seen", "committed", "cfull-arrive"]
+        base = int(fine[fine > 0].min())
+        print("fine marks of the LAST chain launch, block 0 (us since first mark): slot index g ->", roles)
+        for gi in range(256):
+            if int(fine[:, gi].max()) == 0:
+                break
+            print(f"g {gi:3d}  " + "  ".join(f"{(int(fine[r, gi]) - base) / 1e3:8.2f}" if int(fine[r, gi]) else "       -" for r in range(6)))
+
+
+if __name__ == "__main__":
+    main()

@@ -40,9 +40,24 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
   return fn;
 }
+cudaError_t trace_set_elementwise(unsigned long long*);
+cudaError_t trace_set_attn(unsigned long long*);
+cudaError_t trace_set_gemm(unsigned long long*);
+cudaError_t trace_set_chain(unsigned long long*);
+cudaError_t trace_set_sampler(unsigned long long*);
 }  // namespace vb
 
 extern "C" {
+
+int vb_set_trace(void* d_buffer) {
+  unsigned long long* p = static_cast<unsigned long long*>(d_buffer);
+  VB_CHECK_CUDA(vb::trace_set_elementwise(p));
+  VB_CHECK_CUDA(vb::trace_set_attn(p));
+  VB_CHECK_CUDA(vb::trace_set_gemm(p));
+  VB_CHECK_CUDA(vb::trace_set_chain(p));
+  VB_CHECK_CUDA(vb::trace_set_sampler(p));
+  return 0;
+}
 
 const char* vb_last_error(void) { return vb::g_err; }
 int vb_version(void) { return 100; }

@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
   int* s_old = s_pbase + p.n_rows + 1;                         // [n_rows]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tr = (tid == 0 && trace_block0()) ? trace_begin(2) : -1;
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -575,6 +576,7 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
     }
     csync();   // wml / ored / flag reusable
   }
+  trace_end(tr);
 }
 
 template <int D, bool HI>
@@ -658,3 +660,5 @@ int vb_paged_attn(void* d_out, const void* d_q, const void* d_kv, int64_t slab_b
 }
 
 }  // extern "C"
+
+VB_DEFINE_TRACE_SETTER(attn)

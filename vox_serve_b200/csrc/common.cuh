@@ -120,6 +120,46 @@ __device__ __forceinline__ void pdl_sync() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// in-situ timeline (dev tool): with a buffer installed by vb_set_trace, block 0 of the instrumented kernels
+// records %globaltimer at its start / end and at a few internal marks.  Buffer (u64): [0] = records used,
+// [1] = capacity, records from [4] on, 4 words each: t0, t1, id, aux.  One copy of the pointer per translation unit.
+// ---------------------------------------------------------------------------------------------
+static __device__ unsigned long long* g_trace_buf = nullptr;
+#define VB_DEFINE_TRACE_SETTER(name)                                                  \
+  namespace vb {                                                                      \
+  cudaError_t trace_set_##name(unsigned long long* p) {                               \
+    return cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p));                            \
+  }                                                                                   \
+  }
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ int trace_begin(int id, int aux = 0) {
+  unsigned long long* b = g_trace_buf;
+  if (!b) return -1;
+  const unsigned long long i = atomicAdd(b, 1ull);
+  if (i >= b[1]) return -1;
+  unsigned long long* r = b + 4 + 4 * i;
+  r[0] = gtimer(); r[1] = 0ull; r[2] = static_cast<unsigned long long>(id); r[3] = static_cast<unsigned long long>(aux);
+  return static_cast<int>(i);
+}
+__device__ __forceinline__ void trace_end(int rec) {
+  if (rec >= 0) g_trace_buf[4 + 4 * rec + 1] = gtimer();
+}
+__device__ __forceinline__ void trace_mark(int id, int aux = 0) {
+  const int r = trace_begin(id, aux);
+  trace_end(r);
+}
+__device__ __forceinline__ bool trace_block0() { return blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0; }
+// fine-grained marks (no round trip: one plain store): word [2] of the buffer = offset of a [roles][256] u64 area
+__device__ __forceinline__ void trace_fine(int role, unsigned idx) {
+  unsigned long long* b = g_trace_buf;
+  if (b && b[2] && idx < 256u && trace_block0()) b[b[2] + role * 256 + idx] = gtimer();
+}
+
+// ---------------------------------------------------------------------------------------------
 // small device utilities
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

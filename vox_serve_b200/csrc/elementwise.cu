@@ -649,3 +649,5 @@ int vb_gather_windows(int64_t* d_windows, const int32_t* d_history, const int32_
   return 0;
 }
 }  // extern "C"
+
+VB_DEFINE_TRACE_SETTER(elementwise)

@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
   const int kb1 = static_cast<int>(static_cast<long long>(split + 1) * num_kb / p.split_k);
   const bool bnorm = p.norm != 0;
   const bool reducing = p.mode == GM_RESID || p.mode == GM_ROPE;
+  const int tr = (threadIdx.x == 0 && trace_block0()) ? trace_begin(1, p.mode) : -1;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&x_map);
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
       }
       pdl_wait();
       pdl_trigger();
+      if (tr >= 0) trace_mark(20, p.mode);
       for (int i = 0; i < npre; ++i)
         tma_load_2d_hint(smem + i * stage_bytes + a_stage, &x_map, &full[i], (kb0 + i) * GEMM_BLOCK_K,
                          t_blk * p.t_tile, pol_x);
@@ -237,6 +239,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
     const int row = quarter * 32 + lane;          // accumulator row = weight row inside the tile
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    if (et == 0 && trace_block0()) trace_mark(21, p.mode);
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const int t_base = t_blk * p.t_tile;
     if (p.mode == GM_SILU) {
@@ -410,6 +413,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
+  trace_end(tr);
 }
 
 // nn.Linear weight [N][K] (leading dimension ldw) -> [n_tile][k_block][tile_rows][64] bf16 with the 128-byte
@@ -438,6 +442,7 @@ __global__ void __launch_bounds__(256) pack_weight_tiles_kernel(uint4* __restric
 // cos / sin of pos[t] * freq[e] for every row of the step (the same for all layers): [T][2][D]
 __global__ void rope_table_kernel(float* __restrict__ cs, const int32_t* __restrict__ pos,
                                   const float* __restrict__ freq, int D) {
+  const int tr = (threadIdx.x == 0 && trace_block0()) ? trace_begin(10) : -1;
   pdl_sync();
   const size_t t = blockIdx.x;
   const float ps = static_cast<float>(pos[t]);
@@ -447,6 +452,7 @@ __global__ void rope_table_kernel(float* __restrict__ cs, const int32_t* __restr
     cs[t * 2 * D + e] = c;
     cs[t * 2 * D + D + e] = s;
   }
+  trace_end(tr);
 }
 
 // rows of x -> one sum of squares each (the ssq input of the norm-fused projections for a hidden state that
@@ -644,3 +650,5 @@ int vb_row_ssq(float* d_ssq, const void* d_x, int rows, int dim, void* stream) {
 }
 
 }  // extern "C"
+
+VB_DEFINE_TRACE_SETTER(gemm)

@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(SMP_THREADS, 1) sample_kernel(const SamplePara
   c.S = gridDim.x; c.rank = blockIdx.x; c.buf = 0; c.xch = xch; c.sh = sh;
   const int S = c.S, rank = c.rank, row = blockIdx.y, tid = threadIdx.x;
   const bool scaled = p.strategy != 0;
+  const int tr = (tid == 0 && trace_block0()) ? trace_begin(4) : -1;
   pdl_sync();
 
   // ---- one pass over the row: keys (0 = no token / NaN) ----
@@ -369,6 +370,7 @@ __global__ void __launch_bounds__(SMP_THREADS, 1) sample_kernel(const SamplePara
       p.rng_state[1] = offset + 1ull;
     }
   }
+  trace_end(tr);
 }
 
 __global__ void penalty_kernel(__nv_bfloat16* out, const SampleParams p) {
@@ -506,3 +508,5 @@ int vb_update_repetition_cache(uint8_t* d_cache, const int32_t* d_cache_rows, co
 }
 
 }  // extern "C"
+
+VB_DEFINE_TRACE_SETTER(sampler)

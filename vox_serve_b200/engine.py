@@ -148,6 +148,13 @@ class LlamaEngine:
         self.fsplit_qkv = ops.proj_split_k(hq + 2 * hkv, H, self.sms)
         self.fsplit_o = ops.proj_split_k((H + 127) // 128, hq * D, self.sms)
         self.fsplit_down = ops.proj_split_k((H + 127) // 128, I, self.sms)
+        tiles_h = (H + 127) // 128
+        gu_tiles = (I + self.gu_half - 1) // self.gu_half
+        items = [(hq + 2 * hkv) * self.fsplit_qkv, tiles_h * self.fsplit_o, gu_tiles, tiles_h * self.fsplit_down]
+        # persistent chain (one launch for O -> gate/up -> down -> next QKV): every phase must fit one CTA per SM
+        self.chain_ok = self.fused_ok and max(items) <= self.sms
+        self.chain_ws = ops.ChainWorkspace(d.num_hidden_layers, max(hq + 2 * hkv, tiles_h, gu_tiles), max(items), dev) \
+            if self.chain_ok else None
         self.ssq = torch.zeros(max(1, (H + 127) // 128) * self.FUSED_MAX_ROWS, dtype=torch.float32, device=dev)
         self.rope_cs = torch.zeros(self.FUSED_MAX_ROWS, 2, D, dtype=torch.float32, device=dev)
 
@@ -187,10 +194,13 @@ class LlamaEngine:
         return ops.gemm(x, w.lm_head, mode=0, out=self.logits[:n_out])
 
     force_unfused = False     # tests: run decode-sized steps through the 8-launch path too
+    use_chain = True          # tests / ablation: False = one launch per fused projection (5 per layer)
 
     def _layers_fused(self, position_ids: torch.Tensor, R: int, plan: ops.RowPlan) -> None:
-        """5 launches per layer; hidden is updated in place, the RMSNorm statistics travel as per-tile sums of
-        squares written by the residual projections (ssq[parts][R])."""
+        """hidden is updated in place, the RMSNorm statistics travel as per-tile sums of squares written by the
+        residual projections (ssq[parts][R]).  Per layer: paged attention + ONE persistent chain launch
+        (O + residual -> norm + gate/up + SiLU -> down + residual -> norm + next layer's QKV + RoPE + append);
+        without the chain, one launch per fused projection (5 per layer)."""
         d, w = self.dims, self.w
         hq, hkv, D, H, I = d.num_attention_heads, d.num_key_value_heads, d.head_dim, d.hidden_size, d.intermediate_size
         hidden, q, attn, act = self.hidden[:R], self.q[:R], self.attn[:R], self.act[:R]
@@ -198,17 +208,30 @@ class LlamaEngine:
         ssq = self.ssq[: tiles_h * R].view(tiles_h, R)
         cs = ops.rope_table(position_ids[:R], self.freq, D, out=self.rope_cs[:R])
         ops.row_ssq(hidden, out=ssq[0])
-        parts = 1
+        chain = self.chain_ok and self.use_chain
+        if chain:
+            self.chain_ws.zero()
+        n_layers = len(w.layers)
+        eps = d.rms_norm_eps
         for i, L in enumerate(w.layers):
-            ops.proj_norm_qkv_rope_append(hidden, ssq, parts, L["ln1"], d.rms_norm_eps, L["qkv"], self.kv_cache[i], cs,
-                                          plan, hq, hkv, D, self.fsplit_qkv, q_out=q)
+            if i == 0 or not chain:
+                ops.proj_norm_qkv_rope_append(hidden, ssq, 1 if i == 0 else tiles_h, L["ln1"], eps, L["qkv"],
+                                              self.kv_cache[i], cs, plan, hq, hkv, D, self.fsplit_qkv, q_out=q)
             ops.paged_attn(q, self.kv_map, i * self.pages_per_layer, plan, R, hkv, self.page_size, self.chunk,
                            self.attn_ws, out=attn, grid_ctas=self.attn_grid)
-            ops.proj_residual(attn.view(R, hq * D), L["o"], hidden, self.fsplit_o, hidden_out=hidden,
-                              ssq_out=ssq)
-            parts = tiles_h
-            ops.proj_norm_gateup_silu(hidden, ssq, parts, L["ln2"], d.rms_norm_eps, L["gu"], self.gu_half, I, out=act)
-            ops.proj_residual(act, L["down"], hidden, self.fsplit_down, hidden_out=hidden, ssq_out=ssq)
+            if chain:
+                phases = [ops.chain_phase_residual(attn.view(R, hq * D), L["o"], hidden, hidden, ssq, self.fsplit_o),
+                          ops.chain_phase_gateup(hidden, ssq, tiles_h, L["ln2"], eps, L["gu"], I, act),
+                          ops.chain_phase_residual(act, L["down"], hidden, hidden, ssq, self.fsplit_down)]
+                if i + 1 < n_layers:
+                    N = w.layers[i + 1]
+                    phases.append(ops.chain_phase_qkv(hidden, ssq, tiles_h, N["ln1"], eps, N["qkv"], self.kv_cache[i + 1],
+                                                      q, self.fsplit_qkv))
+                ops.decode_chain(phases, R, cs, plan, hq, hkv, self.page_size, self.chain_ws, i)
+            else:
+                ops.proj_residual(attn.view(R, hq * D), L["o"], hidden, self.fsplit_o, hidden_out=hidden, ssq_out=ssq)
+                ops.proj_norm_gateup_silu(hidden, ssq, tiles_h, L["ln2"], eps, L["gu"], self.gu_half, I, out=act)
+                ops.proj_residual(act, L["down"], hidden, self.fsplit_down, hidden_out=hidden, ssq_out=ssq)
 
     def _layers_unfused(self, position_ids: torch.Tensor, R: int, plan: ops.RowPlan) -> None:
         d, w = self.dims, self.w

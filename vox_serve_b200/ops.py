@@ -404,6 +404,68 @@ def proj_norm_qkv_rope_append(hidden: torch.Tensor, ssq: torch.Tensor, n_parts: 
     return q_out
 
 
+class ChainWorkspace:
+    """Scratch of the persistent projection chains of one step: split-K partial tiles (shared by all launches) and
+    one block of arrival counters per launch; `zero()` (one memset) must run before the step's first chain."""
+
+    def __init__(self, n_launches: int, max_tiles: int, max_items: int, device):
+        lib = _lib.load()
+        self.max_tiles, self.max_items, self.n_launches = int(max_tiles), int(max_items), int(n_launches)
+        self.ws = torch.empty(lib.vb_decode_chain_workspace_bytes(self.max_items), dtype=torch.uint8, device=device)
+        self.flag_bytes = (lib.vb_decode_chain_flags_bytes(self.max_tiles) + 255) // 256 * 256
+        self.flags = torch.zeros(self.n_launches * self.flag_bytes, dtype=torch.uint8, device=device)
+
+    def zero(self):
+        self.flags.zero_()
+
+    def flags_ptr(self, launch: int) -> int:
+        assert 0 <= launch < self.n_launches
+        return self.flags.data_ptr() + launch * self.flag_bytes
+
+
+def chain_phase_residual(x: torch.Tensor, w: "PackedWeight", residual: Optional[torch.Tensor], hidden_out: torch.Tensor,
+                         ssq_out: Optional[torch.Tensor], split_k: int) -> "_lib.ChainPhase":
+    ph = _lib.ChainPhase()
+    ph.kind, ph.N, ph.K, ph.tile_rows, ph.split_k = 0, w.N, w.K, w.tile_rows, split_k
+    ph.w_tiles, ph.x_map = w.data.data_ptr(), tensor_map_2d(x, fused_t_tile(x.shape[0])).ptr
+    ph.out, ph.residual, ph.ssq_out = hidden_out.data_ptr(), _p(residual), _p(ssq_out)
+    return ph
+
+
+def chain_phase_gateup(hidden: torch.Tensor, ssq: torch.Tensor, n_parts: int, norm_w: torch.Tensor, eps: float,
+                       w: "PackedWeight", n_out: int, act_out: torch.Tensor) -> "_lib.ChainPhase":
+    ph = _lib.ChainPhase()
+    ph.kind, ph.N, ph.K, ph.tile_rows, ph.split_k, ph.n_out = 1, w.N, w.K, w.tile_rows, 1, n_out
+    ph.n_ssq_parts, ph.eps = n_parts, float(eps)
+    ph.w_tiles, ph.x_map = w.data.data_ptr(), tensor_map_2d(hidden, fused_t_tile(hidden.shape[0])).ptr
+    ph.out, ph.ssq_in, ph.norm_weight = act_out.data_ptr(), ssq.data_ptr(), norm_w.data_ptr()
+    return ph
+
+
+def chain_phase_qkv(hidden: torch.Tensor, ssq: torch.Tensor, n_parts: int, norm_w: torch.Tensor, eps: float,
+                    w: "PackedWeight", layer_kv: torch.Tensor, q_out: torch.Tensor, split_k: int) -> "_lib.ChainPhase":
+    ph = _lib.ChainPhase()
+    ph.kind, ph.N, ph.K, ph.tile_rows, ph.split_k = 2, w.N, w.K, w.tile_rows, split_k
+    ph.n_ssq_parts, ph.eps = n_parts, float(eps)
+    ph.w_tiles, ph.x_map = w.data.data_ptr(), tensor_map_2d(hidden, fused_t_tile(hidden.shape[0])).ptr
+    ph.out, ph.ssq_in, ph.norm_weight, ph.layer_kv = q_out.data_ptr(), ssq.data_ptr(), norm_w.data_ptr(), layer_kv.data_ptr()
+    return ph
+
+
+def decode_chain(phases, T: int, rope_cs: Optional[torch.Tensor], plan: Optional["RowPlan"], n_q: int, n_kv: int,
+                 page_size: int, cws: ChainWorkspace, launch: int) -> None:
+    """One persistent launch running `phases` (1..4 _lib.ChainPhase, each depending on the one before)."""
+    arr = (_lib.ChainPhase * len(phases))(*phases)
+    call("vb_decode_chain", C_addr(arr), len(phases), T, _p(rope_cs), _p(plan.row_page) if plan is not None else None,
+         _p(plan.row_slot) if plan is not None else None, n_q, n_kv, page_size, cws.ws.data_ptr(), cws.ws.numel(),
+         cws.flags_ptr(launch), cws.flag_bytes, cws.max_tiles, _stream())
+
+
+def C_addr(obj) -> int:
+    import ctypes
+    return ctypes.addressof(obj)
+
+
 def rope_table(pos: torch.Tensor, freq: torch.Tensor, head_dim: int, out: Optional[torch.Tensor] = None):
     """cos | sin of pos[t] * freq[e]: fp32 [T, 2, D], shared by every layer of the step."""
     _need_cuda(pos, freq)
