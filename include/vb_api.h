@@ -165,7 +165,8 @@ typedef struct vb_chain_phase {
   int32_t n_ssq_parts;       /* kinds 1, 2 */
   float eps;                 /* kinds 1, 2 */
   const void* w_tiles;       /* vb_pack_weight_tiles(W, N, K, ldw, tile_rows) */
-  const void* x_map;         /* host CUtensorMap of the phase input [T][K], box t_tile (16 / 32 / 64) rows */
+  const void* x;             /* phase input [T][K] bf16, row-major */
+  int64_t ldx;               /* its leading dimension in elements (>= K, multiple of 8) */
   void* out;                 /* kind 0: hidden_out [T][N]; kind 1: act [T][n_out]; kind 2: q_out [T][n_q][D] */
   const void* residual;      /* kind 0 (may alias out, may be NULL) */
   float* ssq_out;            /* kind 0: [tiles][T] or NULL */

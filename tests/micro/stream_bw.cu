@@ -20,7 +20,10 @@ __device__ __forceinline__ void bulk(void* dst, const void* src, uint32_t bytes,
 }
 
 // each CTA streams its contiguous share; `slots` x `slot_bytes` ring; `split` bulk copies per slot issued by `split` lanes
-__global__ void __launch_bounds__(64) bulk_stream(const uint8_t* src, size_t per_cta, int slots, int slot_bytes, int split, unsigned long long* sink) {
+__device__ __forceinline__ void bulk_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)), "l"((uint64_t)src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__global__ void __launch_bounds__(64) bulk_stream(const uint8_t* src, size_t per_cta, int slots, int slot_bytes, int split, unsigned long long* sink, int hint, int delay) {
   extern __shared__ __align__(1024) uint8_t sm[];
   uint64_t* full = (uint64_t*)(sm + (size_t)slots * slot_bytes);
   uint64_t* empty = full + slots;
@@ -36,7 +39,10 @@ __global__ void __launch_bounds__(64) bulk_stream(const uint8_t* src, size_t per
       if (lane == 0) mbar_expect(&full[s], slot_bytes);
       __syncwarp();
       const int piece = slot_bytes / split;
-      if (lane < split) bulk(sm + (size_t)s * slot_bytes + lane * piece, base + (size_t)i * slot_bytes + lane * piece, piece, &full[s]);
+      if (lane < split) {
+        if (hint) { uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol)); bulk_hint(sm + (size_t)s * slot_bytes + lane * piece, base + (size_t)i * slot_bytes + lane * piece, piece, &full[s], pol); }
+        else bulk(sm + (size_t)s * slot_bytes + lane * piece, base + (size_t)i * slot_bytes + lane * piece, piece, &full[s]);
+      }
     }
   } else if (threadIdx.x == 32) {
     unsigned long long acc = 0;
@@ -44,6 +50,7 @@ __global__ void __launch_bounds__(64) bulk_stream(const uint8_t* src, size_t per
       const int s = i % slots; const uint32_t par = (i / slots) & 1;
       mbar_wait(&full[s], par);
       acc += *(volatile unsigned long long*)(sm + (size_t)s * slot_bytes);
+      if (delay) __nanosleep(delay);
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
     }
     if (acc == 0x1234567) *sink = acc;
@@ -69,9 +76,9 @@ int main() {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaFuncSetAttribute(bulk_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   printf("SMs %d\n", sms);
-  struct Cfg { int ctas_per_sm, slots, slot_kb, split; };
-  Cfg cfgs[] = {{1, 5, 16, 1}, {1, 10, 16, 1}, {1, 13, 16, 1}, {1, 6, 32, 1}, {1, 12, 16, 4}, {1, 12, 16, 16}, {1, 24, 8, 1}, {1, 48, 4, 1}, {1, 96, 2, 1},
-                {2, 5, 16, 1}, {2, 6, 16, 4}, {3, 4, 16, 1}, {4, 3, 16, 1}, {1, 3, 64, 32}, {1, 3, 64, 1}};
+  struct Cfg { int ctas_per_sm, slots, slot_kb, split, hint, delay; };
+  Cfg cfgs[] = {{1, 5, 16, 1, 0, 0}, {1, 10, 16, 1, 0, 0}, {1, 10, 14, 1, 0, 0}, {1, 10, 14, 1, 1, 0}, {1, 10, 16, 1, 1, 0}, {1, 10, 14, 1, 1, 200}, {1, 10, 14, 1, 1, 400},
+                {1, 10, 14, 1, 0, 400}, {1, 3, 64, 32, 0, 0}, {1, 3, 64, 32, 1, 0}, {1, 6, 32, 16, 0, 0}, {1, 6, 32, 2, 0, 0}};
   for (auto c : cfgs) {
     const int grid = sms * c.ctas_per_sm;
     const int slot_bytes = c.slot_kb * 1024;
@@ -80,12 +87,12 @@ int main() {
     float best = 1e9;
     for (int r = 0; r < 4; ++r) {
       cudaEventRecord(e0);
-      bulk_stream<<<grid, 64, smem>>>(d, per, c.slots, slot_bytes, c.split, sink);
+      bulk_stream<<<grid, 64, smem>>>(d, per, c.slots, slot_bytes, c.split, sink, c.hint, c.delay);
       cudaEventRecord(e1); cudaEventSynchronize(e1);
       float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
     }
     cudaError_t err = cudaGetLastError();
-    printf("bulk  ctas/sm %d slots %2d x %2d KB split %2d (in flight %4d KB/SM): %7.1f GB/s  %s\n", c.ctas_per_sm, c.slots, c.slot_kb, c.split,
+    printf("bulk  ctas/sm %d slots %2d x %2d KB split %2d hint %d consumer delay %3d ns (in flight %4d KB/SM): %7.1f GB/s  %s\n", c.ctas_per_sm, c.slots, c.slot_kb, c.split, c.hint, c.delay,
            c.ctas_per_sm * c.slots * c.slot_kb, (double)per * grid / best / 1e6, err == cudaSuccess ? "" : cudaGetErrorString(err));
   }
   for (int bps = 1; bps <= 2; ++bps) {

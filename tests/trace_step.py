@@ -39,7 +39,7 @@ def main():
     ids = torch.randint(128266, 156000, (B,), dtype=torch.int32, device=dev)
     pos = torch.full((B,), kv_len - 1, dtype=torch.int32, device=dev)
     cap = 4096
-    buf = torch.zeros(4 + 4 * cap + 6 * 256, dtype=torch.int64, device=dev)
+    buf = torch.zeros(4 + 4 * cap + 10 * 256, dtype=torch.int64, device=dev)
     buf[1] = cap
     buf[2] = 4 + 4 * cap
     g = torch.cuda.CUDAGraph()
@@ -76,15 +76,19 @@ def main():
             prev_end = t1
 
 
-    fine = h[4 + 4 * cap:].view(6, 256)
+    fine = h[4 + 4 * cap:].view(10, 256)
     if int(fine.max()) > 0 and len(sys.argv) > 5:
-        roles = ["w-issue", "x-issue", "full-seen", "cfull-seen", "committed", "cfull-arrive"]
+        roles = ["w-issue", "converted", "x-landed", "mma-ready", "committed", "cfull-arrive", "fenced", "x-issued", "mma-b-ready", "-"]
         base = int(fine[fine > 0].min())
         print("fine marks of the LAST chain launch, block 0 (us since first mark): slot index g ->", roles)
+        print("epilogue marks per phase [acc-done, partial-stored, released, peers-in, tail-done, grid-arrived, next-dep-seen]:")
+        for ph in range(4):
+            row = [int(fine[8, ph * 8 + i]) for i in range(7)]
+            print(f"  p{ph}: " + "  ".join(f"{(v - base) / 1e3:8.2f}" if v else "       -" for v in row))
         for gi in range(256):
-            if int(fine[:, gi].max()) == 0:
+            if int(fine[:8, gi].max()) == 0:
                 break
-            print(f"g {gi:3d}  " + "  ".join(f"{(int(fine[r, gi]) - base) / 1e3:8.2f}" if int(fine[r, gi]) else "       -" for r in range(6)))
+            print(f"g {gi:3d}  " + "  ".join(f"{(int(fine[r, gi]) - base) / 1e3:8.2f}" if int(fine[r, gi]) else "       -" for r in range(8)))
 
 
 if __name__ == "__main__":

@@ -17,7 +17,7 @@ class ChainPhase(C.Structure):
     """vb_chain_phase of include/vb_api.h"""
     _fields_ = [("kind", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("tile_rows", C.c_int32),
                 ("split_k", C.c_int32), ("n_out", C.c_int32), ("n_ssq_parts", C.c_int32), ("eps", C.c_float),
-                ("w_tiles", C.c_void_p), ("x_map", C.c_void_p), ("out", C.c_void_p), ("residual", C.c_void_p),
+                ("w_tiles", C.c_void_p), ("x", C.c_void_p), ("ldx", C.c_int64), ("out", C.c_void_p), ("residual", C.c_void_p),
                 ("ssq_out", C.c_void_p), ("ssq_in", C.c_void_p), ("norm_weight", C.c_void_p),
                 ("layer_kv", C.c_void_p)]
 

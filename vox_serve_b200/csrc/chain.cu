@@ -7,10 +7,12 @@
 // synchronised; the boundary costs (grid-wide dependency, activation reload, epilogue) are paid from the ~180 KiB
 // of weights already on chip instead of from an idle HBM.
 //
-// Roles (224 threads): warp 0 = weight producer (linear bulk copies of pre-tiled, pre-swizzled weight tiles, see
-// vb_pack_weight_tiles), warp 6 = activation loader (TMA tiles of the phase's input, issued once the phase it
-// depends on is complete grid-wide), warp 1 = tcgen05.mma issuer (accumulators in TMEM), warps 2-5 = B-operand
-// finishers (RMSNorm applied in place on the raw activation tile) and epilogue.
+// Roles (192 threads): warp 0 = weight producer (linear bulk copies of pre-tiled, pre-swizzled weight tiles, see
+// vb_pack_weight_tiles -- the only user of the TMA unit, whose issue rate of ~48 GB/s per SM is what bounds the
+// stream), warp 1 = tcgen05.mma issuer (accumulators in TMEM), warps 2-5 = activation loaders / finishers and
+// epilogue: they pull the phase's input tile K-block by K-block with 16-byte cp.async copies (LSU path, four
+// K-blocks in flight, swizzled on the way in), apply the RMSNorm in place where the phase has one, and hand
+// the tile to the MMA.
 // Phases are separated by a grid-wide arrival counter in global memory (all CTAs are co-resident: grid <= SMs,
 // one CTA per SM); split-K partial tiles are exchanged through an L2-resident workspace, every CTA of a tile
 // finishing the tokens t = split, split + S, ... in split order (deterministic).
@@ -20,7 +22,8 @@
 namespace vb {
 
 constexpr int CH_BLOCK_K = 64;
-constexpr int CH_THREADS = 224;
+constexpr int CH_THREADS = 192;
+constexpr int CH_XDEPTH = 2;             // activation tiles in flight per finisher warp (cp.async groups)
 constexpr int CH_EPI_THREADS = 128;
 constexpr int CH_MAX_PHASES = 4;
 constexpr int CH_CHUNK = 8;
@@ -30,6 +33,7 @@ enum { CK_RESID = 0, CK_SILU = 1, CK_ROPE = 2 };
 
 struct ChainPhase {
   const uint8_t* w_tiles;
+  const __nv_bfloat16* x;   // phase input [T][K] row-major (leading dimension ldx)
   void* y;
   const float* n_ssq;
   const __nv_bfloat16* n_w;
@@ -38,7 +42,7 @@ struct ChainPhase {
   __nv_bfloat16* kv;
   int kind, N, K, tile_rows, n_tiles, split_k, n_out, n_ssq_parts;
   float n_eps;
-  int pad_;
+  int ldx;
 };
 struct ChainParams {
   ChainPhase ph[CH_MAX_PHASES];
@@ -91,18 +95,23 @@ __device__ __forceinline__ ChItem ch_item(const ChainPhase& ph) {
   return it;
 }
 
-__global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_constant__ ChainParams P,
-                                                              const __grid_constant__ CUtensorMap xm0,
-                                                              const __grid_constant__ CUtensorMap xm1,
-                                                              const __grid_constant__ CUtensorMap xm2,
-                                                              const __grid_constant__ CUtensorMap xm3) {
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
+  // src-size 0 = zero fill (rows past T, columns past K)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(pred ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int T_TILE>
+__global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_constant__ ChainParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int slot_bytes = CH_A_BYTES + P.t_tile * 128;
+  constexpr int slot_bytes = CH_A_BYTES + T_TILE * 128;
   uint8_t* tail = smem + P.stages * slot_bytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(tail);           // weight + activation bytes of the slot have landed
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);           // the weight tile of the slot has landed
   uint64_t* empty = full + P.stages;                            // the MMAs have read the slot
-  uint64_t* cfull = empty + P.stages;                           // the B tile is final (normalised where needed)
+  uint64_t* cfull = empty + P.stages;                           // the activation tile is in place (normalised)
   uint64_t* tmem_full = cfull + P.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
   float* ssq_sm = reinterpret_cast<float*>(tail + 768);         // [4][CH_CHUNK]
@@ -112,13 +121,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stride = 1 + P.max_tiles;
   const int tr = (threadIdx.x == 0 && trace_block0()) ? trace_begin(3, P.n_phases) : -1;
-  const CUtensorMap* xmaps[CH_MAX_PHASES] = {&xm0, &xm1, &xm2, &xm3};
+  // (dev) per-slot marks by one thread of each role
+  unsigned long long* fine = (lane == 0 && (warp <= 2)) ? trace_fine_base() : nullptr;   // finisher marks: warp 2 only
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) {
-      mbar_init(&full[s], 2);                 // weight producer + activation loader (each with its byte count)
+      mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
-      mbar_init(&cfull[s], CH_EPI_THREADS / 32);
+      mbar_init(&cfull[s], 1);
     }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
@@ -136,7 +146,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
     // ================= weight producer: runs ahead across phase boundaries =================
     if (lane == 0) {
       const uint64_t pol_w = policy_evict_first();
-      uint32_t g = 0;
+      uint32_t g = 0, slot = 0, par = 0;
       for (int p = 0; p < P.n_phases; ++p) {
         const ChainPhase& ph = P.ph[p];
         const ChItem it = ch_item(ph);
@@ -144,55 +154,26 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
         const uint32_t a_bytes = ph.tile_rows * 128;
         const uint8_t* src = ph.w_tiles + (static_cast<size_t>(it.tile) * it.num_kb + it.kb0) * a_bytes;
         for (int kb = it.kb0; kb < it.kb1; ++kb, ++g) {
-          const uint32_t slot = g % P.stages, par = (g / P.stages) & 1;
           mbar_wait(&empty[slot], par ^ 1);
-          trace_fine(0, g);
+          trace_fine(fine, 0, g);
           mbar_arrive_expect_tx(&full[slot], a_bytes);
           ch_bulk_g2s(smem + slot * slot_bytes, src + static_cast<size_t>(kb - it.kb0) * a_bytes, a_bytes, &full[slot],
                       pol_w);
-        }
-      }
-    }
-  } else if (warp == 6) {
-    // ================= activation loader: waits for the producing phase, then feeds the same slots =================
-    if (lane == 0) {
-      const uint64_t pol_x = policy_evict_last();
-      const uint32_t b_bytes = P.t_tile * 128;
-      uint32_t g = 0;
-      for (int p = 0; p < P.n_phases; ++p) {
-        const ChainPhase& ph = P.ph[p];
-        if (p == 0) {
-          prefetch_tmap(xmaps[0]);
-          pdl_wait();           // the kernel in front of the chain (attention / embedding) is complete
-          pdl_trigger();
-        } else {
-          spin_until(&P.flags[(p - 1) * stride], gridDim.x);      // every CTA is past phase p - 1
-          asm volatile("fence.proxy.async;" ::: "memory");        // their generic-proxy writes -> our TMA reads
-        }
-        if (trace_block0()) trace_mark(30 + p);
-        const ChItem it = ch_item(ph);
-        if (!it.has) continue;
-        for (int kb = it.kb0; kb < it.kb1; ++kb, ++g) {
-          const uint32_t slot = g % P.stages, par = (g / P.stages) & 1;
-          mbar_wait(&empty[slot], par ^ 1);
-          trace_fine(1, g);
-          mbar_arrive_expect_tx(&full[slot], b_bytes);
-          tma_load_2d_hint(smem + slot * slot_bytes + CH_A_BYTES, xmaps[p], &full[slot], kb * CH_BLOCK_K, 0, pol_x);
+          if (++slot == static_cast<uint32_t>(P.stages)) { slot = 0; par ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc(128, P.t_tile, 1u);
-      uint32_t g = 0;
+      const uint32_t idesc = umma_idesc(128, T_TILE, 1u);
+      uint32_t g = 0, slot = 0, par = 0;
       for (int p = 0; p < P.n_phases; ++p) {
         const ChItem it = ch_item(P.ph[p]);
         if (!it.has) continue;
         for (int kb = it.kb0; kb < it.kb1; ++kb, ++g) {
-          const uint32_t slot = g % P.stages, par = (g / P.stages) & 1;
-          mbar_wait(&cfull[slot], par);
-          trace_fine(3, g);
+          mbar_wait(&cfull[slot], par);     // weights landed AND activation tile final (the finisher checked both)
+          trace_fine(fine, 3, g);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + slot * slot_bytes);
           const uint64_t a_desc = umma_desc_sw128_kmajor(a_addr);
@@ -201,20 +182,21 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
           for (int k = 0; k < CH_BLOCK_K / 16; ++k)
             umma_bf16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > it.kb0 || k > 0) ? 1u : 0u);
           umma_commit(&empty[slot]);
-          trace_fine(4, g);
+          trace_fine(fine, 4, g);
+          if (++slot == static_cast<uint32_t>(P.stages)) { slot = 0; par ^= 1; }
         }
         umma_commit(tmem_full);
       }
     }
-  } else if (warp >= 2 && warp <= 5) {
-    // ================= B-operand finishers + epilogue =================
+  } else {
+    // ================= activation loaders / finishers + epilogue =================
     const int et = threadIdx.x - 64;
     const int quarter = warp & 3, row = quarter * 32 + lane;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const int tpt = CH_EPI_THREADS / P.t_tile;              // threads per token: 8, 4, 2
-    const int chunks = 8 / tpt;
-    const int ct = et / tpt, cc0 = (et % tpt) * chunks;     // converter token and first 16-byte chunk
-    const uint32_t crow_off = static_cast<uint32_t>(ct) * 128u;
+    // activation tiles: finisher warp cw owns the ring slots g = cw (mod 4); inside a tile a lane owns cpl
+    // consecutive 16-byte chunks of the row-major (token, chunk) order -- whole 128-byte token rows for t_tile 32
+    const int cw = warp - 2;
+    constexpr int cpl = T_TILE / 4;                         // chunks per lane: 4, 8, 16
     uint32_t g = 0, n_done = 0, n_norm = 0;
     for (int p = 0; p < P.n_phases; ++p) {
       const ChainPhase& ph = P.ph[p];
@@ -232,52 +214,117 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
         for (int i = et * 8; i < ph.K; i += CH_EPI_THREADS * 8)
           *reinterpret_cast<uint4*>(wdst + i) = __ldg(reinterpret_cast<const uint4*>(ph.n_w + i));
         ++n_norm;
-        ch_epi_bar();
       }
-      float rstd = 0.f;
-      for (int kb = it.kb0; kb < it.kb1; ++kb, ++g) {
-        const uint32_t slot = g % P.stages, par = (g / P.stages) & 1;
-        mbar_wait(&full[slot], par);
-        if (et == 0) trace_fine(2, g);
-        if (norm) {
-          if (kb == it.kb0 && ct < P.T) {
-            // the phase's input is complete grid-wide (its tiles have just landed): so are its row statistics
-            float ss = 0.f;
-            for (int i = 0; i < ph.n_ssq_parts; ++i) ss += __ldcg(&ph.n_ssq[static_cast<size_t>(i) * P.T + ct]);
-            rstd = rsqrtf(ss / static_cast<float>(ph.K) + ph.n_eps);
-          }
-          uint8_t* b = smem + slot * slot_bytes + CH_A_BYTES + crow_off;
+      // ---- the phase's input must be complete grid-wide ----
+      if (p == 0) {
+        pdl_wait();             // the kernel in front of the chain (attention / embedding) is complete
+        if (et == 0) pdl_trigger();
+      } else {
+        if (et == 0) spin_until(&P.flags[(p - 1) * stride], gridDim.x);
+      }
+      trace_fine(fine, 8, p * 8 + 6);
+      ch_epi_bar();             // (also: w_sm staged by all)
+      if (et == 0 && trace_block0()) trace_mark(30 + p);
+      const uint32_t g0 = g, g1 = g + static_cast<uint32_t>(it.kb1 - it.kb0);
+      auto issue = [&](uint32_t gg) {
+        const uint32_t slot = gg % P.stages, par = (gg / P.stages) & 1;
+        const int kb = it.kb0 + static_cast<int>(gg - g0);
+        mbar_wait(&empty[slot], par ^ 1);
+        const uint32_t b = smem_u32(smem + slot * slot_bytes + CH_A_BYTES);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c < chunks) {
-              uint4* px = reinterpret_cast<uint4*>(b + (((cc0 + c) ^ (ct & 7)) << 4));
-              const uint4 xv = *px;
-              const uint4 wv = *reinterpret_cast<const uint4*>(wbuf + kb * CH_BLOCK_K + (cc0 + c) * 8);
-              const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
-              const uint32_t ws_[4] = {wv.x, wv.y, wv.z, wv.w};
-              uint32_t r[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                r[j] = pack_bf16(bf16_lo(xs[j]) * rstd * bf16_lo(ws_[j]), bf16_hi(xs[j]) * rstd * bf16_hi(ws_[j]));
-              *px = make_uint4(r[0], r[1], r[2], r[3]);
-            }
-          }
-          fence_proxy_async();
+        for (int ci = 0; ci < cpl; ++ci) {
+          const int idx = lane * cpl + ci, t = idx >> 3, c = idx & 7;
+          const int k = kb * CH_BLOCK_K + c * 8;
+          const bool ok = t < P.T && k < ph.K;
+          cp_async16(b + t * 128 + ((c ^ (t & 7)) << 4), ph.x + (ok ? static_cast<size_t>(t) * ph.ldx + k : 0), ok);
         }
+      };
+      const uint32_t my0 = g0 + ((static_cast<uint32_t>(cw) - g0) & 3u);
+#pragma unroll
+      for (int i = 0; i < CH_XDEPTH; ++i) {
+        if (my0 + 4u * i < g1) issue(my0 + 4u * i);
+        cp_async_commit();
+      }
+      float rstd0 = 0.f, rstd1 = 0.f;
+      float res[CH_CHUNK];
+      if (norm) {
+        // row statistics of the input: per-tile partial sums written by the producing phase (all loads in flight)
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int t = (lane * cpl) / 8 + h2;
+          float ss = 0.f;
+          if (t < P.T && (h2 == 0 || cpl > 8)) {
+            for (int i0 = 0; i0 < ph.n_ssq_parts; i0 += 8) {
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                v[i] = (i0 + i < ph.n_ssq_parts) ? __ldcg(&ph.n_ssq[static_cast<size_t>(i0 + i) * P.T + t]) : 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) ss += v[i];
+            }
+            const float r = rsqrtf(ss / static_cast<float>(ph.K) + ph.n_eps);
+            if (h2 == 0) rstd0 = r; else rstd1 = r;
+          }
+        }
+      } else {
+        // residual values of the tokens this CTA will finish: fetched now, used after the reduction
+        const int n = it.tile * ph.tile_rows + row;
+#pragma unroll
+        for (int i = 0; i < CH_CHUNK; ++i) {
+          const int t = it.split + i * ph.split_k;
+          res[i] = 0.f;
+          if (ph.residual && t < P.T && row < ph.tile_rows && n < ph.N) {
+            const unsigned short rb =
+                __ldcg(reinterpret_cast<const unsigned short*>(ph.residual) + static_cast<size_t>(t) * ph.N + n);
+            res[i] = __uint_as_float(static_cast<uint32_t>(rb) << 16);
+          }
+        }
+      }
+      for (uint32_t gg = my0; gg < g1; gg += 4u) {
+        const uint32_t slot = gg % P.stages, par = (gg / P.stages) & 1;
+        const int kb = it.kb0 + static_cast<int>(gg - g0);
+        cp_async_wait<CH_XDEPTH - 1>();      // this lane's chunks of the tile are in shared memory
+        trace_fine(fine, 2, gg);
+        if (norm) {
+          uint8_t* b = smem + slot * slot_bytes + CH_A_BYTES;
+#pragma unroll
+          for (int ci = 0; ci < cpl; ++ci) {
+            const int idx = lane * cpl + ci, t = idx >> 3, c = idx & 7;
+            const float rstd = (ci < 8) ? rstd0 : rstd1;
+            uint4* px = reinterpret_cast<uint4*>(b + t * 128 + ((c ^ (t & 7)) << 4));
+            const uint4 xv = *px;
+            const uint4 wv = *reinterpret_cast<const uint4*>(wbuf + kb * CH_BLOCK_K + c * 8);
+            const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
+            const uint32_t ws_[4] = {wv.x, wv.y, wv.z, wv.w};
+            uint32_t r[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              r[j] = pack_bf16(bf16_lo(xs[j]) * rstd * bf16_lo(ws_[j]), bf16_hi(xs[j]) * rstd * bf16_hi(ws_[j]));
+            *px = make_uint4(r[0], r[1], r[2], r[3]);
+          }
+        }
+        trace_fine(fine, 1, gg);
+        fence_proxy_async();      // generic-proxy writes (cp.async, st.shared) -> the tensor core's async-proxy reads
+        if (lane == 0) mbar_wait(&full[slot], par);      // the slot's weight tile has landed too
         __syncwarp();
         if (lane == 0) mbar_arrive(&cfull[slot]);
-        if (et == 0) trace_fine(5, g);
+        trace_fine(fine, 5, gg);
+        if (gg + 4u * CH_XDEPTH < g1) issue(gg + 4u * CH_XDEPTH);
+        trace_fine(fine, 7, gg);
+        cp_async_commit();
       }
+      g = g1;
       // ---- accumulator complete ----
       mbar_wait(tmem_full, n_done & 1);
       ++n_done;
       tc_fence_after();
       if (et == 0 && trace_block0()) trace_mark(40 + p);
+      trace_fine(fine, 8, p * 8 + 0);
       if (ph.kind == CK_SILU) {
         const int h = ph.tile_rows >> 1;
         const bool is_gate = row < h, is_up = row >= h && row < 2 * h;
         constexpr int ldx = 17;
-        for (int c0 = 0; c0 < P.t_tile; c0 += 16) {
+        for (int c0 = 0; c0 < T_TILE; c0 += 16) {
           uint32_t v[16];
           tmem_ld_32x16(taddr + c0, v);
           tmem_ld_wait();
@@ -306,25 +353,25 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
       } else {
         // ---- split-K: park the partial tile in the L2-resident workspace, meet the other splits of the tile ----
         const int S = ph.split_k;
-        float* mine = P.ws + static_cast<size_t>(blockIdx.x) * P.t_tile * 128;
-        for (int c0 = 0; c0 < P.t_tile; c0 += 16) {
+        float* mine = P.ws + static_cast<size_t>(blockIdx.x) * T_TILE * 128;
+        for (int c0 = 0; c0 < T_TILE; c0 += 16) {
           uint32_t v[16];
           tmem_ld_32x16(taddr + c0, v);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) __stcg(&mine[(c0 + j) * 128 + row], __uint_as_float(v[j]));
         }
-        if (S > 1) {
-          __threadfence();
-          ch_epi_bar();
-          if (et == 0) {
-            unsigned* tflag = &P.flags[p * stride + 1 + it.tile];
-            red_release_gpu(tflag, 1u);
-            spin_until(tflag, static_cast<unsigned>(S));
-          }
+        trace_fine(fine, 8, p * 8 + 1);
+        ch_epi_bar();             // every thread's partial stores happen-before thread 0's release below
+        if (S > 1 && et == 0) {
+          unsigned* tflag = &P.flags[p * stride + 1 + it.tile];
+          red_release_gpu(tflag, 1u);
+          trace_fine(fine, 8, p * 8 + 2);
+          spin_until(tflag, static_cast<unsigned>(S));
+          trace_fine(fine, 8, p * 8 + 3);
         }
         ch_epi_bar();
-        const float* part = P.ws + static_cast<size_t>(it.tile) * S * P.t_tile * 128;
+        const float* part = P.ws + static_cast<size_t>(it.tile) * S * T_TILE * 128;
         const int rank = it.split;
         const int n = it.tile * ph.tile_rows + row;
         const bool valid = row < ph.tile_rows && n < ph.N;
@@ -340,7 +387,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
               for (int i = 0; i < CH_CHUNK; ++i) {
                 const int t = rank + (i0 + i) * S;
                 const float v = (i0 + i < n_mine)
-                                    ? __ldcg(&part[(static_cast<size_t>(s) * P.t_tile + t) * 128 + row]) : 0.f;
+                                    ? __ldcg(&part[(static_cast<size_t>(s) * T_TILE + t) * 128 + row]) : 0.f;
                 a[i] = (s == 0) ? v : a[i] + v;
               }
             }
@@ -355,8 +402,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
                 const size_t idx = static_cast<size_t>(t) * ph.N + n;
                 float hv = round_bf16(a[i]);
                 if (ph.residual) {
-                  const unsigned short rb = __ldcg(reinterpret_cast<const unsigned short*>(ph.residual) + idx);
-                  hv = round_bf16(__uint_as_float(static_cast<uint32_t>(rb) << 16) + hv);
+                  float rv = res[i];
+                  if (i0 > 0) {       // beyond the prefetched chunk (more than CH_CHUNK tokens per CTA)
+                    const unsigned short rb = __ldcg(reinterpret_cast<const unsigned short*>(ph.residual) + idx);
+                    rv = __uint_as_float(static_cast<uint32_t>(rb) << 16);
+                  }
+                  hv = round_bf16(rv + hv);
                 }
                 hid[idx] = __float2bfloat16_rn(hv);
                 sq = hv * hv;
@@ -375,6 +426,18 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
             const int D = ph.tile_rows, half = D >> 1;
             const int head = it.tile;
             const bool rot = head < P.n_q + P.n_kv;
+            // rotation table and page slots of this chunk's tokens: independent loads, issued together
+            float cv[CH_CHUNK], sv[CH_CHUNK];
+            int pg[CH_CHUNK], sl[CH_CHUNK];
+#pragma unroll
+            for (int i = 0; i < CH_CHUNK; ++i) {
+              const int t = rank + (i0 + i) * S;
+              const bool ok = i0 + i < n_mine && row < D;
+              cv[i] = (ok && rot) ? P.rope_cs[static_cast<size_t>(t) * 2 * D + row] : 1.f;
+              sv[i] = (ok && rot) ? P.rope_cs[static_cast<size_t>(t) * 2 * D + D + row] : 0.f;
+              pg[i] = (ok && head >= P.n_q) ? P.row_page[t] : -1;
+              sl[i] = (ok && head >= P.n_q) ? P.row_slot[t] : 0;
+            }
 #pragma unroll
             for (int i = 0; i < CH_CHUNK; ++i) xchg[row * ldx + i] = round_bf16(a[i]);
             ch_epi_bar();
@@ -386,23 +449,17 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
                 const int t = rank + (i0 + i) * S;
                 if (i0 + i < n_mine) {
                   float v = xchg[row * ldx + i];
-                  if (rot) {
-                    const float* cs = P.rope_cs + static_cast<size_t>(t) * 2 * D;
-                    v = v * cs[row] + sign * xchg[prow * ldx + i] * cs[D + row];
-                  }
+                  if (rot) v = v * cv[i] + sign * xchg[prow * ldx + i] * sv[i];
                   const __nv_bfloat16 o = __float2bfloat16_rn(v);
                   if (head < P.n_q) {
                     static_cast<__nv_bfloat16*>(ph.y)[(static_cast<size_t>(t) * P.n_q + head) * D + row] = o;
-                  } else {
-                    const int page = P.row_page[t];
-                    if (page >= 0) {
-                      const size_t row_elems = static_cast<size_t>(P.n_kv) * D;
-                      const size_t slab = static_cast<size_t>(P.page_size) * row_elems;
-                      const int hk = head - P.n_q;
-                      const int is_v = hk >= P.n_kv ? 1 : 0;
-                      ph.kv[(static_cast<size_t>(page) * 2 + is_v) * slab + static_cast<size_t>(P.row_slot[t]) * row_elems +
-                            static_cast<size_t>(hk - is_v * P.n_kv) * D + row] = o;
-                    }
+                  } else if (pg[i] >= 0) {
+                    const size_t row_elems = static_cast<size_t>(P.n_kv) * D;
+                    const size_t slab = static_cast<size_t>(P.page_size) * row_elems;
+                    const int hk = head - P.n_q;
+                    const int is_v = hk >= P.n_kv ? 1 : 0;
+                    ph.kv[(static_cast<size_t>(pg[i]) * 2 + is_v) * slab + static_cast<size_t>(sl[i]) * row_elems +
+                          static_cast<size_t>(hk - is_v * P.n_kv) * D + row] = o;
                   }
                 }
               }
@@ -412,12 +469,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
         }
       }
       // ---- this CTA's share of the phase is in global memory: arrive at the grid-wide counter ----
+      trace_fine(fine, 8, p * 8 + 4);
       tc_fence_before();
-      __threadfence();
-      ch_epi_bar();
+      ch_epi_bar();               // all epilogue stores happen-before the release (cumulative)
       if (et == 0) red_release_gpu(gbar, 1u);
+      trace_fine(fine, 8, p * 8 + 5);
       if (et == 0 && trace_block0()) trace_mark(50 + p);
     }
+    cp_async_wait<0>();
   }
   __syncthreads();
   if (warp == 2) {
@@ -457,12 +516,12 @@ int vb_decode_chain(const vb_chain_phase* phases, int n_phases, int T, const flo
   P.ws = static_cast<float*>(d_workspace); P.flags = static_cast<unsigned int*>(d_flags);
   P.rope_cs = d_rope_cs; P.row_page = d_row_page; P.row_slot = d_row_slot;
   P.n_q = n_q; P.n_kv = n_kv; P.page_size = page_size; P.max_tiles = max_tiles;
-  const CUtensorMap* maps[CH_MAX_PHASES] = {nullptr, nullptr, nullptr, nullptr};
   int grid = 1, norm_k = 0;
   for (int i = 0; i < n_phases; ++i) {
     const vb_chain_phase& in = phases[i];
     ChainPhase& ph = P.ph[i];
-    VB_CHECK_ARG(in.w_tiles && in.x_map && in.out, "vb_decode_chain: phase %d: null pointer", i);
+    VB_CHECK_ARG(in.w_tiles && in.x && in.out, "vb_decode_chain: phase %d: null pointer", i);
+    VB_CHECK_ARG(in.ldx >= in.K && in.ldx % 8 == 0, "vb_decode_chain: phase %d: ldx %d (>= K, multiple of 8)", i, static_cast<int>(in.ldx));
     VB_CHECK_ARG(in.kind >= 0 && in.kind <= 2, "vb_decode_chain: phase %d: kind %d", i, in.kind);
     VB_CHECK_ARG(in.tile_rows >= 8 && in.tile_rows <= 128 && in.tile_rows % 8 == 0,
                  "vb_decode_chain: phase %d: tile_rows %d", i, in.tile_rows);
@@ -474,6 +533,7 @@ int vb_decode_chain(const vb_chain_phase* phases, int n_phases, int T, const flo
     ph.n_tiles = (in.N + in.tile_rows - 1) / in.tile_rows;
     ph.n_out = in.n_out > 0 ? in.n_out : in.N;
     ph.w_tiles = static_cast<const uint8_t*>(in.w_tiles);
+    ph.x = static_cast<const __nv_bfloat16*>(in.x); ph.ldx = static_cast<int>(in.ldx);
     ph.y = in.out;
     ph.residual = static_cast<const __nv_bfloat16*>(in.residual);
     ph.ssq_out = in.ssq_out;
@@ -500,23 +560,22 @@ int vb_decode_chain(const vb_chain_phase* phases, int n_phases, int T, const flo
                  i, items, sms);
     VB_CHECK_ARG(workspace_bytes >= vb_decode_chain_workspace_bytes(items), "vb_decode_chain: workspace too small");
     grid = items > grid ? items : grid;
-    maps[i] = static_cast<const CUtensorMap*>(in.x_map);
   }
-  for (int i = n_phases; i < CH_MAX_PHASES; ++i) maps[i] = maps[0];
   P.norm_k = (norm_k + 63) / 64 * 64;
   const int slot_bytes = CH_A_BYTES + P.t_tile * 128;
   const int fixed = 1024 /*barriers, ssq*/ + 128 * 17 * 4 + 2 * P.norm_k * 2 + 1024 /*alignment*/;
   int stages = (VB_MAX_DYN_SMEM - fixed) / slot_bytes;
   if (const char* e = getenv("VB_CHAIN_STAGES")) {
     const int v = atoi(e);
-    if (v >= 2 && v < stages) stages = v;
+    if (v >= 4 && v < stages) stages = v;
   }
   if (stages > 24) stages = 24;       // barrier block: 3 * 24 * 8 + 16 < 768
-  VB_CHECK_ARG(stages >= 2, "vb_decode_chain: shared memory too small for a 2-slot ring");
+  VB_CHECK_ARG(stages >= 4, "vb_decode_chain: shared memory too small for the ring (%d slots)", stages);
   P.stages = stages;
   const int smem = stages * slot_bytes + fixed;
-  VB_CHECK_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VB_MAX_DYN_SMEM));
-  VB_LAUNCH_PDL(chain_kernel, grid, CH_THREADS, smem, stream, P, *maps[0], *maps[1], *maps[2], *maps[3]);
+  auto kern = P.t_tile == 16 ? chain_kernel<16> : (P.t_tile == 32 ? chain_kernel<32> : chain_kernel<64>);
+  VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, VB_MAX_DYN_SMEM));
+  VB_LAUNCH_PDL(kern, grid, CH_THREADS, smem, stream, P);
   return 0;
 }
 

@@ -153,10 +153,16 @@ __device__ __forceinline__ void trace_mark(int id, int aux = 0) {
   trace_end(r);
 }
 __device__ __forceinline__ bool trace_block0() { return blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0; }
-// fine-grained marks (no round trip: one plain store): word [2] of the buffer = offset of a [roles][256] u64 area
-__device__ __forceinline__ void trace_fine(int role, unsigned idx) {
+// fine-grained marks: word [2] of the buffer = offset of a [roles][256] u64 area.  The base is resolved once per
+// thread (trace_fine_base: the only loads); a mark is then a single predicated store -- no round trip.
+__device__ __forceinline__ unsigned long long* trace_fine_base() {
   unsigned long long* b = g_trace_buf;
-  if (b && b[2] && idx < 256u && trace_block0()) b[b[2] + role * 256 + idx] = gtimer();
+  if (!b || !trace_block0()) return nullptr;
+  const unsigned long long off = b[2];
+  return off ? b + off : nullptr;
+}
+__device__ __forceinline__ void trace_fine(unsigned long long* fine, int role, unsigned idx) {
+  if (fine && idx < 256u) fine[role * 256 + idx] = gtimer();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -427,7 +427,7 @@ def chain_phase_residual(x: torch.Tensor, w: "PackedWeight", residual: Optional[
                          ssq_out: Optional[torch.Tensor], split_k: int) -> "_lib.ChainPhase":
     ph = _lib.ChainPhase()
     ph.kind, ph.N, ph.K, ph.tile_rows, ph.split_k = 0, w.N, w.K, w.tile_rows, split_k
-    ph.w_tiles, ph.x_map = w.data.data_ptr(), tensor_map_2d(x, fused_t_tile(x.shape[0])).ptr
+    ph.w_tiles, ph.x, ph.ldx = w.data.data_ptr(), x.data_ptr(), x.stride(0)
     ph.out, ph.residual, ph.ssq_out = hidden_out.data_ptr(), _p(residual), _p(ssq_out)
     return ph
 
@@ -437,7 +437,7 @@ def chain_phase_gateup(hidden: torch.Tensor, ssq: torch.Tensor, n_parts: int, no
     ph = _lib.ChainPhase()
     ph.kind, ph.N, ph.K, ph.tile_rows, ph.split_k, ph.n_out = 1, w.N, w.K, w.tile_rows, 1, n_out
     ph.n_ssq_parts, ph.eps = n_parts, float(eps)
-    ph.w_tiles, ph.x_map = w.data.data_ptr(), tensor_map_2d(hidden, fused_t_tile(hidden.shape[0])).ptr
+    ph.w_tiles, ph.x, ph.ldx = w.data.data_ptr(), hidden.data_ptr(), hidden.stride(0)
     ph.out, ph.ssq_in, ph.norm_weight = act_out.data_ptr(), ssq.data_ptr(), norm_w.data_ptr()
     return ph
 
@@ -447,7 +447,7 @@ def chain_phase_qkv(hidden: torch.Tensor, ssq: torch.Tensor, n_parts: int, norm_
     ph = _lib.ChainPhase()
     ph.kind, ph.N, ph.K, ph.tile_rows, ph.split_k = 2, w.N, w.K, w.tile_rows, split_k
     ph.n_ssq_parts, ph.eps = n_parts, float(eps)
-    ph.w_tiles, ph.x_map = w.data.data_ptr(), tensor_map_2d(hidden, fused_t_tile(hidden.shape[0])).ptr
+    ph.w_tiles, ph.x, ph.ldx = w.data.data_ptr(), hidden.data_ptr(), hidden.stride(0)
     ph.out, ph.ssq_in, ph.norm_weight, ph.layer_kv = q_out.data_ptr(), ssq.data_ptr(), norm_w.data_ptr(), layer_kv.data_ptr()
     return ph
 
