@@ -567,10 +567,10 @@ int vb_decode_chain(const vb_chain_phase* phases, int n_phases, int T, const flo
   int stages = (VB_MAX_DYN_SMEM - fixed) / slot_bytes;
   if (const char* e = getenv("VB_CHAIN_STAGES")) {
     const int v = atoi(e);
-    if (v >= 4 && v < stages) stages = v;
+    if (v >= 5 && v < stages) stages = v;
   }
   if (stages > 24) stages = 24;       // barrier block: 3 * 24 * 8 + 16 < 768
-  VB_CHECK_ARG(stages >= 4, "vb_decode_chain: shared memory too small for the ring (%d slots)", stages);
+  VB_CHECK_ARG(stages >= 5, "vb_decode_chain: shared memory too small for the ring (%d slots)", stages);
   P.stages = stages;
   const int smem = stages * slot_bytes + fixed;
   auto kern = P.t_tile == 16 ? chain_kernel<16> : (P.t_tile == 32 ? chain_kernel<32> : chain_kernel<64>);

@@ -200,8 +200,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
       pdl_wait();
       float rstd = 0.f;
       if (t < p.T) {
+        // per-tile partial sums of squares: batches of 8 loads in flight (a serial chain of L2 round trips here
+        // delayed the first MMA of every norm-fused projection by ~8 us)
         float ss = 0.f;
-        for (int i = 0; i < p.n_ssq_parts; ++i) ss += p.n_ssq[static_cast<size_t>(i) * p.T + t];
+        for (int i0 = 0; i0 < p.n_ssq_parts; i0 += 8) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            v[i] = (i0 + i < p.n_ssq_parts) ? __ldcg(&p.n_ssq[static_cast<size_t>(i0 + i) * p.T + t]) : 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ss += v[i];
+        }
         rstd = rsqrtf(ss / static_cast<float>(p.K) + p.n_eps);
       }
       epi_bar();                                              // w_sm complete

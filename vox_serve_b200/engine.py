@@ -13,6 +13,7 @@ every residual add is rounded to bf16.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -193,8 +194,12 @@ class LlamaEngine:
             raise VoxB200Error(f"logits requested for {n_out} rows; pass last_rows (max {self.max_out_rows})")
         return ops.gemm(x, w.lm_head, mode=0, out=self.logits[:n_out])
 
-    force_unfused = False     # tests: run decode-sized steps through the 8-launch path too
-    use_chain = True          # tests / ablation: False = one launch per fused projection (5 per layer)
+    # How decode-sized steps (<= FUSED_MAX_ROWS rows) run their layers.  Measured on B200 (tests/ablate_step.py,
+    # Orpheus-3B, 32 rows, kv 728): separate kernels 2.72 ms, fused projections 2.96 ms, persistent chain 3.42 ms per
+    # forward -- the fused variants still pay more in their serial epilogue / dependency chains than they save in
+    # launches (profiles/r01_chain_trace.txt), so the 8-launch layer stays the default until they do not.
+    force_unfused = os.environ.get("VB_DECODE_MODE", "unfused") == "unfused"
+    use_chain = os.environ.get("VB_DECODE_MODE", "unfused") == "chain"
 
     def _layers_fused(self, position_ids: torch.Tensor, R: int, plan: ops.RowPlan) -> None:
         """hidden is updated in place, the RMSNorm statistics travel as per-tile sums of squares written by the
