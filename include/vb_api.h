@@ -51,7 +51,13 @@ int vb_tensor_map_2d_bf16(void* out_map, const void* d_base, int64_t rows, int64
                           int box_rows);
 
 /* ---- RMSNorm: vox_serve/flashinfer_utils.py:251-267 ------------------------------------------ */
-int vb_rmsnorm(void* d_out, const void* d_x, const void* d_weight, int rows, int dim, float eps, void* stream);
+/* "Tiled" activation layout XT(t_tile) -- the image of a GEMM activation stage in shared memory, kept in global memory:
+ * [token block][k-block of 64][t_tile rows][64] bf16, 16-byte chunk c of row r stored at chunk c ^ (r & 7).  A tile is one
+ * contiguous t_tile * 128-byte run, so vb_gemm_bf16 fetches it with ONE linear bulk copy instead of a tensor-map box of
+ * t_tile row requests (the TMA unit's issue rate is what bounds the weight stream).  Producers that feed a projection
+ * take an `xt_tile` argument: 0 = plain row-major output, else write XT(xt_tile) with xt_tile = vb_gemm_t_tile(T). */
+int vb_rmsnorm(void* d_out, const void* d_x, const void* d_weight, int rows, int dim, float eps, int xt_tile,
+               void* stream);
 
 /* ---- RoPE at position ids: vox_serve/flashinfer_utils.py:270-324 ------------------------------
  * q [T][n_q][D], k [T][n_kv][D] bf16 -> q_out/k_out (may alias inputs).  d_freq[rotary_dim] is the
@@ -103,7 +109,7 @@ int vb_paged_attn(void* d_out, const void* d_q, const void* d_kv, int64_t slab_b
                   const int32_t* d_row_kvlen, const int32_t* d_row_chunk_start, const int32_t* d_row_pagebase,
                   const int32_t* d_row_old, const int32_t* d_kv_indices, int n_rows, int n_q, int n_kv, int head_dim, int page_size,
                   int chunk_tokens, float sm_scale, void* d_workspace, size_t workspace_bytes, int grid_ctas,
-                  int ws_grid_ctas, void* stream);
+                  int ws_grid_ctas, int out_xt_tile, void* stream);
 
 /* ---- dense projections (nn.Linear, bias-free): model/orpheus.py:41-47, 68-79, 197 -------------
  * Y[T][N] = X[T][K] * W[N][K]^T on tcgen05: a tile of tile_rows (<= 128, multiple of 8; 0 = 128) weight rows is
@@ -122,8 +128,10 @@ int vb_paged_attn(void* d_out, const void* d_q, const void* d_kv, int64_t slab_b
 size_t vb_weight_tiles_bytes(int N, int K, int tile_rows);
 int vb_pack_weight_tiles(void* d_dst, const void* d_w, int N, int K, int64_t ldw, int tile_rows, void* stream);
 int vb_gemm_t_tile(int T);
-int vb_gemm_bf16(void* d_y, const void* d_w_tiles, const void* x_map, int T, int N, int K, int ldy, int mode,
-                 int split_k, int tile_rows, int n_out, void* stream);
+/* d_x_tiles (optional): X in the XT(vb_gemm_t_tile(T)) layout -- then x_map may be NULL; y_tiled (mode 2 only): write
+ * Y in the XT(vb_gemm_t_tile(T)) layout over n_out columns (it is the down projection's activation). */
+int vb_gemm_bf16(void* d_y, const void* d_w_tiles, const void* x_map, const void* d_x_tiles, int T, int N, int K,
+                 int ldy, int mode, int split_k, int tile_rows, int n_out, int y_tiled, void* stream);
 
 /* ---- fused decode projections (T <= 64): one launch each for what orpheus.py:81-151 does between Linears ----
  * x_map: vb_tensor_map_2d_bf16(X, T, K, ldx, t_tile) with t_tile = 16 / 32 / 64 (smallest >= T).
@@ -193,7 +201,7 @@ int vb_row_ssq(float* d_ssq, const void* d_x, int rows, int dim, void* stream);
  * d_residual may be NULL (no add); d_norm_weight may be NULL (skip the norm output). */
 int vb_reduce_residual_rmsnorm(void* d_hidden_out, void* d_normed_out, const float* d_partials, int split_k,
                                const void* d_residual, const void* d_norm_weight, int T, int N, float eps,
-                               void* stream);
+                               int normed_xt_tile, void* stream);
 /* fused tail of the QKV projection: sum partials -> bf16 q|k|v, RoPE(q,k), write q, scatter k,v into the
  * layer cache (orpheus.py:91-106 + flashinfer_utils.py:243-244).  partials [split_k][T][(n_q+2 n_kv) D]. */
 int vb_qkv_rope_append(void* d_q_out, void* d_layer_kv, const float* d_partials, int split_k, const int32_t* d_pos,

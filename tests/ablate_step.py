@@ -105,6 +105,12 @@ def main():
         eng.forward(ids, pos, B)
         eng.use_chain = True
 
+    def unfused_rows():
+        eng.force_unfused, eng.tiled_acts = True, False
+        eng.forward(ids, pos, B)
+        eng.force_unfused, eng.tiled_acts = False, True
+
+    variants["unfused_rows_forward"] = unfused_rows
     variants["unfused_forward"] = unfused
     variants["fused_forward"] = nochain
     variants["chain_forward"] = lambda: eng.forward(ids, pos, B)

@@ -35,7 +35,8 @@ def _run(dims, page_size, max_pages, prompt_lens, n_steps, seed, max_bs=4, mode=
     kv = torch.zeros(dims.num_hidden_layers, max_pages, 2, page_size, dims.num_key_value_heads, dims.head_dim,
                      dtype=BF, device="cuda")
     eng = LlamaEngine(gw, kv, page_size, max_rows=256)
-    eng.force_unfused = mode == "unfused"
+    eng.force_unfused = mode.startswith("unfused")
+    eng.tiled_acts = mode != "unfused-rows"
     eng.use_chain = mode == "chain"
     assert eng.chain_ok
     g = torch.Generator().manual_seed(21)
@@ -87,7 +88,7 @@ def _run(dims, page_size, max_pages, prompt_lens, n_steps, seed, max_bs=4, mode=
 
 
 # persistent chain (2 launches per layer) / one launch per fused projection (5) / prefill-style layers (8)
-@pytest.mark.parametrize("mode", ["chain", "fused", "unfused"])
+@pytest.mark.parametrize("mode", ["chain", "fused", "unfused", "unfused-rows"])
 def test_tiny_orpheus_teacher_forced_greedy(mode):
     dims = oorph.OrpheusDims.tiny()
     dims.max_tokens = 400

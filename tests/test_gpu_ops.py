@@ -187,6 +187,10 @@ def _attn_case(ops, kv_lens, page_size, hq, hkv, D, seed, prefill_new=None, n_pa
         assert rel < 8e-3, f"grid {grid}: rel l2 {rel}"
         assert err.max().item() < 0.04 * max(scale, 1e-3) * 10, f"grid {grid}: max err {err.max().item()} scale {scale}"
         rel_l2 = rel if rel_l2 is None else rel_l2
+        if grid in (None, 7):      # the tiled output layout (what the O projection streams) holds the same numbers
+            out_t = ops.paged_attn(q.cuda(), kv_map, layer * n_pages, plan, R, hkv, page_size, chunk, ws, grid_ctas=grid,
+                                   out=ops.TiledAct(R, hq * D, "cuda"))
+            assert torch.equal(out_t.to_rows(), out.view(R, hq * D)), f"grid {grid}: tiled attention output differs"
     return rel_l2
 
 
@@ -387,6 +391,40 @@ def test_proj_norm_qkv_rope_append(ops, T, hq, hkv, D, K, split):
         untouched = torch.ones(n_pages, page_size, dtype=torch.bool)
         untouched[torch.tensor(pages), torch.tensor(slots)] = False
         assert dcache.cpu()[:, 0][untouched].abs().max().item() == 0, "wrote outside the rows' slots"
+
+
+def test_tiled_activation_layout_roundtrip(ops):
+    """rmsnorm / reduce+residual+rmsnorm / gate-up GEMM write the tiled XT layout, the GEMM reads it with bulk copies:
+    same numbers as the row-major path."""
+    T, H, I = 32, 768, 1024
+    x = (torch.randn(T, H, generator=g(1)) * 2).to(BF).cuda()
+    w = (1 + 0.1 * torch.randn(H, generator=g(2))).to(BF).cuda()
+    ref = ops.rmsnorm(x, w, 1e-5)
+    xt = ops.rmsnorm(x, w, 1e-5, out=ops.TiledAct(T, H, "cuda"))
+    assert torch.equal(xt.to_rows(), ref)
+    for Tn in (5, 17, 64):           # a buffer sized for 64 rows re-viewed for fewer rows
+        big = ops.TiledAct(64, H, "cuda")
+        v = ops.rmsnorm(x[:min(Tn, T)], w, 1e-5, out=big.view_rows(min(Tn, T)))
+        assert torch.equal(v.to_rows(), ref[:min(Tn, T)])
+    # GEMM from the tiled activation == GEMM from rows (bit-identical: same tiles in shared memory)
+    wq = (torch.randn(640, H, generator=g(3)) * 0.05).to(BF).cuda()
+    assert torch.equal(ops.gemm(xt, wq, mode=0), ops.gemm(ref, wq, mode=0))
+    p_t = ops.gemm(xt, wq, mode=1, split_k=3)
+    assert torch.equal(p_t, ops.gemm(ref, wq, mode=1, split_k=3))
+    # reduce + residual + norm with a tiled normed output
+    parts = torch.randn(3, T, H, generator=g(4)).cuda()
+    h1, n1 = ops.reduce_residual_rmsnorm(parts, x, w, 1e-5)
+    h2, n2 = ops.reduce_residual_rmsnorm(parts, x, w, 1e-5, normed_out=ops.TiledAct(T, H, "cuda"))
+    assert torch.equal(h1, h2) and torch.equal(n2.to_rows(), n1)
+    # gate/up GEMM writing its SiLU product tiled, then the down projection reading it
+    wg = (torch.randn(I, H, generator=g(5)) * 0.05).to(BF).cuda()
+    wu = (torch.randn(I, H, generator=g(6)) * 0.05).to(BF).cuda()
+    wi = ops.interleave_gate_up(wg, wu, 56)
+    a_rows = ops.gemm(ref, wi, mode=2, tile_rows=112, n_out=I)
+    a_t = ops.gemm(xt, wi, mode=2, tile_rows=112, n_out=I, out=ops.TiledAct(T, I, "cuda"))
+    assert torch.equal(a_t.to_rows(), a_rows)
+    wd = (torch.randn(H, I, generator=g(7)) * 0.05).to(BF).cuda()
+    assert torch.equal(ops.gemm(a_t, wd, mode=1, split_k=2), ops.gemm(a_rows, wd, mode=1, split_k=2))
 
 
 def test_embedding_gather_pcm_codes(ops):

@@ -85,8 +85,9 @@ def main():
         for ph in range(4):
             row = [int(fine[8, ph * 8 + i]) for i in range(7)]
             print(f"  p{ph}: " + "  ".join(f"{(v - base) / 1e3:8.2f}" if v else "       -" for v in row))
+        print("role-5 marks (gemm epilogue):", [round((int(v) - base) / 1e3, 2) if int(v) else None for v in fine[5, :30]])
         for gi in range(256):
-            if int(fine[:8, gi].max()) == 0:
+            if int(fine[:5, gi].max()) == 0:
                 break
             print(f"g {gi:3d}  " + "  ".join(f"{(int(fine[r, gi]) - base) / 1e3:8.2f}" if int(fine[r, gi]) else "       -" for r in range(8)))
 

@@ -29,7 +29,7 @@ SIGNATURES = {
     "vb_device_info": (c_int, [P, P]),
     "vb_tensor_map_kv": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int]),
     "vb_tensor_map_2d_bf16": (c_int, [P, P, c_int64, c_int64, c_int64, c_int]),
-    "vb_rmsnorm": (c_int, [P, P, P, c_int, c_int, c_float, P]),
+    "vb_rmsnorm": (c_int, [P, P, P, c_int, c_int, c_float, c_int, P]),
     "vb_rope_freqs": (c_int, [P, c_int, c_int, c_float, c_float, c_int, c_float, c_float, c_float, P]),
     "vb_rope": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_plan_rows": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P]),
@@ -43,12 +43,12 @@ SIGNATURES = {
     "vb_attn_tile_tokens": (c_int, [c_int, c_int]),
     "vb_paged_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "vb_paged_attn": (c_int, [P, P, P, c_int64, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int,
-                              c_float, P, c_size_t, c_int, c_int, P]),
+                              c_float, P, c_size_t, c_int, c_int, c_int, P]),
     "vb_set_trace": (c_int, [P]),
     "vb_gemm_t_tile": (c_int, [c_int]),
     "vb_weight_tiles_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vb_pack_weight_tiles": (c_int, [P, P, c_int, c_int, c_int64, c_int, P]),
-    "vb_gemm_bf16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_gemm_bf16": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_proj_residual": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_proj_norm_gateup_silu": (c_int, [P, P, P, P, c_int, P, c_float, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_proj_norm_qkv_rope_append": (c_int, [P, P, P, P, P, c_int, P, c_float, P, P, P, c_int, c_int, c_int, c_int,
@@ -58,7 +58,7 @@ SIGNATURES = {
     "vb_decode_chain": (c_int, [P, c_int, c_int, P, P, P, c_int, c_int, c_int, P, c_size_t, P, c_size_t, c_int, P]),
     "vb_rope_table": (c_int, [P, P, P, c_int, c_int, P]),
     "vb_row_ssq": (c_int, [P, P, c_int, c_int, P]),
-    "vb_reduce_residual_rmsnorm": (c_int, [P, P, P, c_int, P, P, c_int, c_int, c_float, P]),
+    "vb_reduce_residual_rmsnorm": (c_int, [P, P, P, c_int, P, P, c_int, c_int, c_float, c_int, P]),
     "vb_qkv_rope_append": (c_int, [P, P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_embedding": (c_int, [P, P, P, c_int, c_int, c_int, P]),
     "vb_gather_rows": (c_int, [P, P, P, c_int, c_int, c_int, P]),

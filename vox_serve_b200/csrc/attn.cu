@@ -45,6 +45,7 @@ struct AttnParams {
   float* part_o;                 // [grid * 2][n_q][D]
   int slab_base;
   int n_rows, n_q, n_kv, G, page_size, tok, stages;
+  int out_xt_tile;               // 0: out is [row][n_q][D]; else the tiled XT(out_xt_tile) layout of [row][n_q * D]
   float scale_log2;
 };
 
@@ -52,6 +53,12 @@ struct TileMeta {   // 32 bytes, one per ring stage
   int row, token0, kvlen, flags;   // flags: 1 = segment start, 2 = segment end, 4 = segment covers the whole row
   int slot, cta_a, n_parts, qslot;
 };
+
+// output element (row, head hq, dim d): row-major or the tiled activation layout the O projection streams
+__device__ __forceinline__ size_t attn_out_index(const AttnParams& p, int row, int hq, int d, int D) {
+  if (p.out_xt_tile == 0) return (static_cast<size_t>(row) * p.n_q + hq) * D + d;
+  return xt_index(row, hq * D + d, p.out_xt_tile, (p.n_q * D + 63) >> 6);
+}
 
 __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -250,8 +257,8 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
   // padded / empty rows produce zeros
   for (int row = blockIdx.x; row < p.n_rows; row += gridDim.x) {
     if (s_kvlen[row] == 0) {
-      uint32_t* o = reinterpret_cast<uint32_t*>(p.out + static_cast<size_t>(row) * p.n_q * D);
-      for (int i = tid; i < p.n_q * D / 2; i += NC) o[i] = 0u;
+      for (int i = tid; i < p.n_q * D / 2; i += NC)
+        *reinterpret_cast<uint32_t*>(p.out + attn_out_index(p, row, (2 * i) / D, (2 * i) % D, D)) = 0u;
     }
   }
   auto csync = [NC]() { asm volatile("bar.sync 1, %0;" ::"r"(NC) : "memory"); };
@@ -396,17 +403,16 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
         const int h0 = nt * 8 + qd * 2;
         if (complete) {
           const float i0 = 1.f / lrun[nt][0], i1 = 1.f / lrun[nt][1];
-          __nv_bfloat16* o0 = p.out + (static_cast<size_t>(m.row) * p.n_q + hq0 + h0) * D;
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
             const int d = mt * 16 + g;
             if (h0 < G) {
-              o0[d] = __float2bfloat16_rn(O[mt][nt][0] * i0);
-              o0[d + 8] = __float2bfloat16_rn(O[mt][nt][2] * i0);
+              p.out[attn_out_index(p, m.row, hq0 + h0, d, D)] = __float2bfloat16_rn(O[mt][nt][0] * i0);
+              p.out[attn_out_index(p, m.row, hq0 + h0, d + 8, D)] = __float2bfloat16_rn(O[mt][nt][2] * i0);
             }
             if (h0 + 1 < G) {
-              o0[D + d] = __float2bfloat16_rn(O[mt][nt][1] * i1);
-              o0[D + d + 8] = __float2bfloat16_rn(O[mt][nt][3] * i1);
+              p.out[attn_out_index(p, m.row, hq0 + h0 + 1, d, D)] = __float2bfloat16_rn(O[mt][nt][1] * i1);
+              p.out[attn_out_index(p, m.row, hq0 + h0 + 1, d + 8, D)] = __float2bfloat16_rn(O[mt][nt][3] * i1);
             }
           }
         } else {
@@ -478,9 +484,9 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
               }
             }
             const float inv = 1.f / den;
-            __nv_bfloat16* o0 = p.out + (static_cast<size_t>(m.row) * p.n_q + hq) * D;
 #pragma unroll
-            for (int j = 0; j < D / 32; ++j) o0[j * 32 + lane] = __float2bfloat16_rn(acc[j] * inv);
+            for (int j = 0; j < D / 32; ++j)
+              p.out[attn_out_index(p, m.row, hq, j * 32 + lane, D)] = __float2bfloat16_rn(acc[j] * inv);
           }
         }
       }
@@ -530,7 +536,7 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
         l += wml[(w * 16 + gg) * 2 + 1] * sc;
       }
       if (complete) {
-        p.out[static_cast<size_t>(m.row) * p.n_q * D + i] = __float2bfloat16_rn(o / l);
+        p.out[attn_out_index(p, m.row, hq, d, D)] = __float2bfloat16_rn(o / l);
       } else {
         p.part_o[pslot * p.n_q * D + i] = o;
         if (d == 0) {
@@ -570,7 +576,7 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
             den += sc * __ldcg(&p.part_ml[(ps * p.n_q + hq) * 2 + 1]);
             num += sc * __ldcg(&p.part_o[ps * p.n_q * D + i]);
           }
-          p.out[static_cast<size_t>(m.row) * p.n_q * D + i] = __float2bfloat16_rn(num / den);
+          p.out[attn_out_index(p, m.row, hq, i - hq * D, D)] = __float2bfloat16_rn(num / den);
         }
       }
     }
@@ -615,7 +621,7 @@ int vb_paged_attn(void* d_out, const void* d_q, const void* d_kv, int64_t slab_b
                   const int32_t* d_row_kvlen, const int32_t* d_row_chunk_start, const int32_t* d_row_pagebase,
                   const int32_t* d_row_old, const int32_t* d_kv_indices, int n_rows, int n_q, int n_kv, int head_dim, int page_size,
                   int chunk_tokens, float sm_scale, void* d_workspace, size_t workspace_bytes, int grid_ctas,
-                  int ws_grid_ctas, void* stream) {
+                  int ws_grid_ctas, int out_xt_tile, void* stream) {
   VB_CHECK_ARG(d_out && d_q && d_kv && d_row_kvlen && d_row_chunk_start && d_row_pagebase && d_row_old && d_kv_indices &&
                    d_workspace,
                "vb_paged_attn: null pointer");
@@ -648,6 +654,7 @@ int vb_paged_attn(void* d_out, const void* d_q, const void* d_kv, int64_t slab_b
   p.slab_base = static_cast<int>(slab_base);
   p.n_rows = n_rows; p.n_q = n_q; p.n_kv = n_kv; p.G = n_q / n_kv; p.page_size = page_size;
   p.tok = chunk_tokens;
+  p.out_xt_tile = out_xt_tile;
   p.scale_log2 = sm_scale * 1.4426950408889634f;
   // deepest ring that fits next to the fixed buffers
   int stages = ATTN_MAX_STAGES;

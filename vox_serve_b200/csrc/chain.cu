@@ -337,14 +337,17 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
             const int n_out = it.tile * h + row;
             if (n_out < ph.n_out) {
               __nv_bfloat16* y = static_cast<__nv_bfloat16*>(ph.y);
+              float o[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float gv = round_bf16(__uint_as_float(v[j]));
+                const float sv = round_bf16(gv / (1.0f + expf(-gv)));
+                o[j] = sv * xchg[row * ldx + j];
+              }
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const int t = c0 + j;
-                if (t < P.T) {
-                  const float gv = round_bf16(__uint_as_float(v[j]));
-                  const float sv = round_bf16(gv / (1.0f + expf(-gv)));
-                  y[static_cast<size_t>(t) * ph.n_out + n_out] = __float2bfloat16_rn(sv * xchg[row * ldx + j]);
-                }
+                if (t < P.T) y[static_cast<size_t>(t) * ph.n_out + n_out] = __float2bfloat16_rn(o[j]);
               }
             }
           }

@@ -179,6 +179,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// "Tiled" activation layout XT(t_tile): what a GEMM B-operand stage looks like in shared memory, kept in global
+// memory: [token block][k-block of 64][t_tile rows][64] bf16 with the 128-byte swizzle applied (16-byte chunk c of
+// row r at chunk c ^ (r & 7)).  A (token block, k-block) tile is one contiguous t_tile * 128-byte run, fetched with a
+// single linear bulk copy instead of a tensor-map box (t_tile row requests on the TMA unit).  Element index:
+__device__ __forceinline__ size_t xt_index(int t, int k, int t_tile, int num_kb) {
+  const int tb = t / t_tile, tt = t - tb * t_tile;
+  return ((static_cast<size_t>(tb) * num_kb + (k >> 6)) * t_tile + tt) * 64 + ((((k >> 3) & 7) ^ (tt & 7)) << 3) + (k & 7);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -22,7 +22,8 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 
 __global__ void __launch_bounds__(256) rmsnorm_kernel(__nv_bfloat16* __restrict__ out,
                                                       const __nv_bfloat16* __restrict__ x,
-                                                      const __nv_bfloat16* __restrict__ w, int dim, float eps) {
+                                                      const __nv_bfloat16* __restrict__ w, int dim, float eps,
+                                                      int xt_tile) {
   pdl_sync();
   __shared__ float red[32];
   const size_t row = blockIdx.x;
@@ -48,7 +49,8 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(__nv_bfloat16* __restrict_
   const float rcp = rsqrtf(ss / static_cast<float>(dim) + eps);
   for (int i = threadIdx.x; i < dim; i += blockDim.x) {
     float v = __bfloat162float(xr[i]) * rcp * __bfloat162float(w[i]);
-    out[row * dim + i] = __float2bfloat16_rn(v);
+    const size_t oi = xt_tile ? xt_index(static_cast<int>(row), i, xt_tile, (dim + 63) >> 6) : row * dim + i;
+    out[oi] = __float2bfloat16_rn(v);
   }
 }
 
@@ -221,7 +223,7 @@ constexpr int RR_MAX_ITER = 4;      // columns per CTA <= RR_THREADS * 4 * RR_MA
 __global__ void __launch_bounds__(RR_THREADS) reduce_residual_rmsnorm_kernel(
     __nv_bfloat16* __restrict__ hidden_out, __nv_bfloat16* __restrict__ normed_out,
     const float* __restrict__ partials, int split_k, const __nv_bfloat16* __restrict__ residual,
-    const __nv_bfloat16* __restrict__ norm_w, int T, int N, float eps) {
+    const __nv_bfloat16* __restrict__ norm_w, int T, int N, float eps, int xt_tile) {
   pdl_sync();
   __shared__ float red[32];
   __shared__ float part_ss;
@@ -280,7 +282,8 @@ __global__ void __launch_bounds__(RR_THREADS) reduce_residual_rmsnorm_kernel(
       uint2 o;
       o.x = pack_bf16(h[it][0] * rcp * bf16_lo(w2.x), h[it][1] * rcp * bf16_hi(w2.x));
       o.y = pack_bf16(h[it][2] * rcp * bf16_lo(w2.y), h[it][3] * rcp * bf16_hi(w2.y));
-      *reinterpret_cast<uint2*>(normed_out + t * N + n) = o;
+      const size_t oi = xt_tile ? xt_index(static_cast<int>(t), n, xt_tile, (N + 63) >> 6) : t * N + n;
+      *reinterpret_cast<uint2*>(normed_out + oi) = o;
     }
   }
 }
@@ -407,11 +410,12 @@ using namespace vb;
 
 extern "C" {
 
-int vb_rmsnorm(void* d_out, const void* d_x, const void* d_weight, int rows, int dim, float eps, void* stream) {
+int vb_rmsnorm(void* d_out, const void* d_x, const void* d_weight, int rows, int dim, float eps, int xt_tile,
+               void* stream) {
   VB_CHECK_ARG(d_out && d_x && d_weight, "vb_rmsnorm: null pointer");
   VB_CHECK_ARG(dim > 0 && dim % 8 == 0, "vb_rmsnorm: dim %d must be a positive multiple of 8", dim);
   if (rows <= 0) return 0;
-  VB_LAUNCH_PDL(rmsnorm_kernel, rows, 256, 0, stream, static_cast<__nv_bfloat16*>(d_out), static_cast<const __nv_bfloat16*>(d_x), static_cast<const __nv_bfloat16*>(d_weight), dim, eps);
+  VB_LAUNCH_PDL(rmsnorm_kernel, rows, 256, 0, stream, static_cast<__nv_bfloat16*>(d_out), static_cast<const __nv_bfloat16*>(d_x), static_cast<const __nv_bfloat16*>(d_weight), dim, eps, xt_tile);
   return 0;
 }
 
@@ -465,7 +469,7 @@ int vb_kv_append(void* d_layer_kv, const void* d_k, const void* d_v, const int32
 
 int vb_reduce_residual_rmsnorm(void* d_hidden_out, void* d_normed_out, const float* d_partials, int split_k,
                                const void* d_residual, const void* d_norm_weight, int T, int N, float eps,
-                               void* stream) {
+                               int normed_xt_tile, void* stream) {
   VB_CHECK_ARG(d_partials && split_k >= 1, "vb_reduce_residual_rmsnorm: bad partials");
   VB_CHECK_ARG(N % 4 == 0, "vb_reduce_residual_rmsnorm: N %d must be a multiple of 4", N);
   VB_CHECK_ARG(!d_normed_out || d_norm_weight, "vb_reduce_residual_rmsnorm: norm output needs a weight");
@@ -482,7 +486,7 @@ int vb_reduce_residual_rmsnorm(void* d_hidden_out, void* d_normed_out, const flo
   VB_LAUNCH_PDL_CLUSTER(reduce_residual_rmsnorm_kernel, dim3(parts, T), RR_THREADS, 0, stream, parts,
                         static_cast<__nv_bfloat16*>(d_hidden_out), static_cast<__nv_bfloat16*>(d_normed_out),
                         d_partials, split_k, static_cast<const __nv_bfloat16*>(d_residual),
-                        static_cast<const __nv_bfloat16*>(d_norm_weight), T, N, eps);
+                        static_cast<const __nv_bfloat16*>(d_norm_weight), T, N, eps, normed_xt_tile);
   return 0;
 }
 

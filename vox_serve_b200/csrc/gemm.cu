@@ -40,6 +40,8 @@ enum GemmMode {
 struct GemmParams {
   void* y;
   const uint8_t* w_tiles;   // weights re-tiled by vb_pack_weight_tiles: [n_tile][k_block][tile_rows x 128 B, swizzled]
+  const uint8_t* x_tiles;   // activations in the tiled XT(t_tile) layout (common.cuh), or nullptr: x_map (row-major)
+  int y_tiled;              // mode 2: write Y in the XT(t_tile) layout (it is the next projection's activation)
   int T, N, K, ldy, mode, split_k, t_tile, stages, tmem_cols, tile_rows, n_out, pad;
   // B operand = rmsnorm(x) * w formed in the kernel from the raw x tile TMA delivered (norm != 0)
   int norm;
@@ -111,9 +113,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
   const bool bnorm = p.norm != 0;
   const bool reducing = p.mode == GM_RESID || p.mode == GM_ROPE;
   const int tr = (threadIdx.x == 0 && trace_block0()) ? trace_begin(1, p.mode) : -1;
+  // (dev) per-stage marks of the gate/up launches: producer and MMA threads of block 0
+  unsigned long long* fine = (lane == 0 && warp <= 2 && p.mode == GM_SILU) ? trace_fine_base() : nullptr;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&x_map);
+    if (!p.x_tiles) prefetch_tmap(&x_map);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -148,18 +152,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
       }
       pdl_wait();
       pdl_trigger();
+      trace_fine(fine, 1, 0);
       if (tr >= 0) trace_mark(20, p.mode);
-      for (int i = 0; i < npre; ++i)
-        tma_load_2d_hint(smem + i * stage_bytes + a_stage, &x_map, &full[i], (kb0 + i) * GEMM_BLOCK_K,
-                         t_blk * p.t_tile, pol_x);
+      // activations: one linear bulk copy per stage from the tiled layout, else a tensor-map box (t_tile row
+      // requests: ~0.3 us of TMA issue time per stage, which then bounds the whole stream at ~4 TB/s)
+      const uint8_t* xsrc = p.x_tiles ? p.x_tiles + static_cast<size_t>(t_blk) * num_kb * b_stage : nullptr;
+      for (int i = 0; i < npre; ++i) {
+        if (xsrc)
+          bulk_g2s_hint(smem + i * stage_bytes + a_stage, xsrc + static_cast<size_t>(kb0 + i) * b_stage, b_stage, &full[i],
+                        pol_x);
+        else
+          tma_load_2d_hint(smem + i * stage_bytes + a_stage, &x_map, &full[i], (kb0 + i) * GEMM_BLOCK_K,
+                           t_blk * p.t_tile, pol_x);
+      }
       int s = npre == p.stages ? 0 : npre;
       uint32_t ph = npre == p.stages ? 1 : 0;
       for (int kb = kb0 + npre; kb < kb1; ++kb) {
         mbar_wait(&empty[s], ph ^ 1);
+        trace_fine(fine, 0, kb - kb0);
         uint8_t* a = smem + s * stage_bytes;
         mbar_arrive_expect_tx(&full[s], stage_bytes);
         bulk_g2s_hint(a, wsrc + static_cast<size_t>(kb - kb0) * a_stage, a_stage, &full[s], pol_w);
-        tma_load_2d_hint(a + a_stage, &x_map, &full[s], kb * GEMM_BLOCK_K, t_blk * p.t_tile, pol_x);
+        if (xsrc) bulk_g2s_hint(a + a_stage, xsrc + static_cast<size_t>(kb) * b_stage, b_stage, &full[s], pol_x);
+        else tma_load_2d_hint(a + a_stage, &x_map, &full[s], kb * GEMM_BLOCK_K, t_blk * p.t_tile, pol_x);
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
     }
@@ -172,6 +187,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
       uint32_t ph = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&ready[s], ph);
+        trace_fine(fine, 3, kb - kb0);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
         const uint64_t a_desc = umma_desc_sw128_kmajor(a_addr);
@@ -182,6 +198,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
           umma_bf16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty[s]);   // frees the smem stage once these MMAs have read it
+        trace_fine(fine, 4, kb - kb0);
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
       umma_commit(tmem_full);     // accumulator complete
@@ -255,31 +272,45 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
       const int h = p.tile_rows >> 1;
       const bool is_gate = row < h, is_up = row >= h && row < 2 * h;
       constexpr int ldx = 17;
+      trace_fine(fine, 5, 0);
       for (int c0 = 0; c0 < p.t_tile; c0 += 16) {
         uint32_t v[16];
         tmem_ld_32x16(taddr + c0, v);
         tmem_ld_wait();
+        trace_fine(fine, 5, 1 + c0 / 4);
         if (is_up) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) xchg[(row - h) * ldx + j] = round_bf16(__uint_as_float(v[j]));
         }
         epi_bar();
+        trace_fine(fine, 5, 2 + c0 / 4);
         if (is_gate) {
           const int n_out = n_tile * h + row;
           if (n_out < p.n_out) {
             __nv_bfloat16* y = static_cast<__nv_bfloat16*>(p.y);
+            // all 16 SiLU products first (independent chains: the warp is alone on its scheduler, so a serial
+            // expf + divide per element is a long dependent chain), then the stores
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float g = round_bf16(__uint_as_float(v[j]));
+              const float s = round_bf16(g / (1.0f + expf(-g)));
+              o[j] = s * xchg[row * ldx + j];
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int t = t_base + c0 + j;
               if (t < p.T) {
-                const float g = round_bf16(__uint_as_float(v[j]));
-                const float s = round_bf16(g / (1.0f + expf(-g)));
-                y[static_cast<size_t>(t) * p.ldy + n_out] = __float2bfloat16_rn(s * xchg[row * ldx + j]);
+                const size_t yi = p.y_tiled ? xt_index(t, n_out, p.t_tile, (p.n_out + 63) >> 6)
+                                            : static_cast<size_t>(t) * p.ldy + n_out;
+                y[yi] = __float2bfloat16_rn(o[j]);
               }
             }
           }
         }
+        trace_fine(fine, 5, 3 + c0 / 4);
         epi_bar();
+        trace_fine(fine, 5, 4 + c0 / 4);
       }
     } else if (!reducing) {
       const int n = n_tile * p.tile_rows + row;
@@ -418,10 +449,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
   } else {
     __syncthreads();
   }
+  trace_fine(fine, 5, 20 + warp);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
+  trace_fine(fine, 5, 24 + warp);
   trace_end(tr);
 }
 
@@ -507,8 +540,12 @@ static int gemm_smem_budget() {
   return g_gemm_smem_budget;
 }
 
-static int launch_gemm(GemmParams& p, const void* w_tiles, const void* x_map, cudaStream_t stream) {
+static int launch_gemm(GemmParams& p, const void* w_tiles, const void* x_map, cudaStream_t stream,
+                       const void* x_tiles = nullptr) {
+  static const CUtensorMap dummy_map = {};
   p.w_tiles = static_cast<const uint8_t*>(w_tiles);
+  p.x_tiles = static_cast<const uint8_t*>(x_tiles);
+  if (!x_map) x_map = &dummy_map;      // never dereferenced by the kernel when x_tiles is set
   const int num_kb = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   VB_CHECK_ARG(p.T > 0 && p.N > 0 && p.K > 0, "gemm: empty problem T=%d N=%d K=%d", p.T, p.N, p.K);
   VB_CHECK_ARG(p.K % 8 == 0, "gemm: K %d must be a multiple of 8", p.K);
@@ -575,9 +612,10 @@ int vb_gemm_t_tile(int T) {
   return (T + 15) / 16 * 16;
 }
 
-int vb_gemm_bf16(void* d_y, const void* d_w_tiles, const void* x_map, int T, int N, int K, int ldy, int mode,
-                 int split_k, int tile_rows, int n_out, void* stream) {
-  VB_CHECK_ARG(d_y && d_w_tiles && x_map, "vb_gemm_bf16: null pointer");
+int vb_gemm_bf16(void* d_y, const void* d_w_tiles, const void* x_map, const void* d_x_tiles, int T, int N, int K,
+                 int ldy, int mode, int split_k, int tile_rows, int n_out, int y_tiled, void* stream) {
+  VB_CHECK_ARG(d_y && d_w_tiles && (x_map || d_x_tiles), "vb_gemm_bf16: null pointer");
+  VB_CHECK_ARG(!y_tiled || mode == 2, "vb_gemm_bf16: tiled output is a mode 2 option");
   VB_CHECK_ARG(mode >= 0 && mode <= 2, "vb_gemm_bf16: mode %d", mode);
   VB_CHECK_ARG(mode == 1 || split_k == 1, "vb_gemm_bf16: split_k > 1 needs mode 1 (fp32 partials)");
   VB_CHECK_ARG(mode != 2 || (tile_rows % 16 == 0 && N % tile_rows == 0),
@@ -587,7 +625,8 @@ int vb_gemm_bf16(void* d_y, const void* d_w_tiles, const void* x_map, int T, int
   p.tile_rows = tile_rows > 0 ? tile_rows : 128;
   p.n_out = n_out > 0 ? n_out : (mode == 2 ? N / 2 : N);
   p.t_tile = vb_gemm_t_tile(T);
-  return launch_gemm(p, d_w_tiles, x_map, static_cast<cudaStream_t>(stream));
+  p.y_tiled = y_tiled;
+  return launch_gemm(p, d_w_tiles, x_map, static_cast<cudaStream_t>(stream), d_x_tiles);
 }
 
 int vb_proj_residual(void* d_hidden_out, float* d_ssq_out, const void* d_w_tiles, const void* x_map,

@@ -134,6 +134,10 @@ class LlamaEngine:
         self.q = torch.zeros(R, hq, D, dtype=BF16, device=dev)
         self.attn = torch.zeros(R, hq, D, dtype=BF16, device=dev)
         self.act = torch.zeros(R, I, dtype=BF16, device=dev)
+        # decode-sized steps keep the projections' activations in the tiled layout (one bulk copy per GEMM stage)
+        self.normed_t = ops.TiledAct(self.FUSED_MAX_ROWS, H, dev)
+        self.attn_t = ops.TiledAct(self.FUSED_MAX_ROWS, hq * D, dev)
+        self.act_t = ops.TiledAct(self.FUSED_MAX_ROWS, I, dev)
         self.max_out_rows = min(R, 64)     # logits are only ever needed for one row per request
         self.last_normed = torch.zeros(self.max_out_rows, H, dtype=BF16, device=dev)
         self.logits = torch.zeros(self.max_out_rows, d.vocab_size, dtype=BF16, device=dev)
@@ -180,16 +184,21 @@ class LlamaEngine:
             raise VoxB200Error(f"{R} rows exceed the engine's max_rows {self.max_rows}")
         hidden, normed = self.hidden[:R], self.normed[:R]
         ops.embedding(w.embed, input_ids, out=hidden)
+        x_final = normed
         if R <= self.FUSED_MAX_ROWS and self.fused_ok and not self.force_unfused:
             self._layers_fused(position_ids, R, plan)
-            ops.rmsnorm(hidden, w.norm, d.rms_norm_eps, out=normed)
+            if last_rows is None and self.tiled_acts:
+                x_final = self.normed_t.view_rows(R)
+            ops.rmsnorm(hidden, w.norm, d.rms_norm_eps, out=x_final)
         else:
-            self._layers_unfused(position_ids, R, plan)
+            x_final = self._layers_unfused(position_ids, R, plan)
         if last_rows is not None:
             n_out = last_rows.numel() if n_out is None else n_out
+            if isinstance(x_final, ops.TiledAct):      # a gather needs rows: redo the final norm row-major (prefill-only path)
+                ops.rmsnorm(hidden, w.norm, d.rms_norm_eps, out=normed)
             x = ops.gather_rows(normed, last_rows, out=self.last_normed[:n_out], idx_offset=last_rows_offset)
         else:
-            n_out, x = R, normed
+            n_out, x = R, x_final
         if n_out > self.max_out_rows:
             raise VoxB200Error(f"logits requested for {n_out} rows; pass last_rows (max {self.max_out_rows})")
         return ops.gemm(x, w.lm_head, mode=0, out=self.logits[:n_out])
@@ -238,25 +247,35 @@ class LlamaEngine:
                 ops.proj_norm_gateup_silu(hidden, ssq, tiles_h, L["ln2"], eps, L["gu"], self.gu_half, I, out=act)
                 ops.proj_residual(act, L["down"], hidden, self.fsplit_down, hidden_out=hidden, ssq_out=ssq)
 
-    def _layers_unfused(self, position_ids: torch.Tensor, R: int, plan: ops.RowPlan) -> None:
+    def _layers_unfused(self, position_ids: torch.Tensor, R: int, plan: ops.RowPlan):
+        """8 launches per layer.  Decode-sized steps (R <= FUSED_MAX_ROWS) pass activations between kernels in the
+        tiled layout; returns what holds the final normed rows (a TiledAct then, else self.normed[:R])."""
         d, w = self.dims, self.w
         hq, hkv, D, H, I = d.num_attention_heads, d.num_key_value_heads, d.head_dim, d.hidden_size, d.intermediate_size
-        hidden, normed = self.hidden[:R], self.normed[:R]
+        hidden = self.hidden[:R]
+        tiled = R <= self.FUSED_MAX_ROWS and self.tiled_acts
+        normed = self.normed_t.view_rows(R) if tiled else self.normed[:R]
+        attn_o = self.attn_t.view_rows(R) if tiled else self.attn[:R]
+        act = self.act_t.view_rows(R) if tiled else self.act[:R]
         ops.rmsnorm(hidden, w.layers[0]["ln1"], d.rms_norm_eps, out=normed)
         s_qkv, s_o, s_dn = self._split(self.split_qkv, R), self._split(self.split_o, R), self._split(self.split_down, R)
-        q, attn, act = self.q[:R], self.attn[:R], self.act[:R]
+        q = self.q[:R]
         n_layers = len(w.layers)
         for i, L in enumerate(w.layers):
             p = ops.gemm(normed, L["qkv"], mode=1, split_k=s_qkv, out=self._partials(s_qkv, R, self.qkv_w), tile_rows=D)
             ops.qkv_rope_append(p, self.kv_cache[i], position_ids, self.freq, plan, hq, hkv, D, q_out=q)
             ops.paged_attn(q, self.kv_map, i * self.pages_per_layer, plan, R, hkv, self.page_size, self.chunk,
-                           self.attn_ws, out=attn, grid_ctas=self.attn_grid)
-            p = ops.gemm(attn.view(R, hq * D), L["o"], mode=1, split_k=s_o, out=self._partials(s_o, R, H))
+                           self.attn_ws, out=attn_o, grid_ctas=self.attn_grid)
+            p = ops.gemm(attn_o if tiled else attn_o.view(R, hq * D), L["o"], mode=1, split_k=s_o,
+                         out=self._partials(s_o, R, H))
             ops.reduce_residual_rmsnorm(p, hidden, L["ln2"], d.rms_norm_eps, hidden_out=hidden, normed_out=normed)
             ops.gemm(normed, L["gu"], mode=2, out=act, tile_rows=2 * self.gu_half, n_out=I)
             p = ops.gemm(act, L["down"], mode=1, split_k=s_dn, out=self._partials(s_dn, R, H))
             nxt = w.layers[i + 1]["ln1"] if i + 1 < n_layers else w.norm
             ops.reduce_residual_rmsnorm(p, hidden, nxt, d.rms_norm_eps, hidden_out=hidden, normed_out=normed)
+        return normed
+
+    tiled_acts = True         # tests: False = row-major activations + tensor-map loads in decode-sized steps too
 
     # ---- kernel-isolated passes for the roofline measurement (bench.py) --------------------------------
     def gemm_pass(self, n_rows: int) -> None:

@@ -100,12 +100,51 @@ def tensor_map_2d(t: torch.Tensor, box_rows: int, cache: bool = True) -> TensorM
 # ----------------------------------------------------------------------------------------------
 # norm / rope / paging
 # ----------------------------------------------------------------------------------------------
-def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+class TiledAct:
+    """An activation matrix [T, K] in the tiled XT(t_tile) layout of vb_api.h (what a GEMM stage looks like in shared
+    memory): producers write it directly (rmsnorm / reduce_residual_rmsnorm / paged_attn / gemm mode 2 with `out=` a
+    TiledAct), ops.gemm consumes it with one linear bulk copy per pipeline stage."""
+    __slots__ = ("data", "T", "K", "t_tile")
+
+    def __init__(self, T: int, K: int, device, max_T: Optional[int] = None):
+        self.T, self.K = T, K
+        self.t_tile = gemm_t_tile(T)
+        cap = gemm_t_tile(max_T or T)
+        blocks = (max(T, max_T or T) + cap - 1) // cap
+        self.data = torch.zeros(blocks * ((K + 63) // 64) * cap * 64, dtype=BF16, device=device)
+
+    def view_rows(self, T: int) -> "TiledAct":
+        """the same storage re-interpreted for T rows (t_tile follows T)"""
+        v = TiledAct.__new__(TiledAct)
+        v.data, v.T, v.K, v.t_tile = self.data, T, self.K, gemm_t_tile(T)
+        assert ((T + v.t_tile - 1) // v.t_tile) * ((self.K + 63) // 64) * v.t_tile * 64 <= self.data.numel()
+        return v
+
+    def to_rows(self) -> torch.Tensor:
+        """row-major copy [T, K] (tests / debugging)"""
+        t, K, nkb = self.t_tile, self.K, (self.K + 63) // 64
+        blocks = (self.T + t - 1) // t
+        x = self.data[: blocks * nkb * t * 64].view(blocks, nkb, t, 8, 8)
+        r = torch.arange(t, device=x.device) & 7
+        c = torch.arange(8, device=x.device)
+        src = (c.view(1, 8) ^ r.view(t, 1))                      # logical chunk c of row r sits at chunk c ^ (r & 7)
+        x = torch.gather(x, 3, src.view(1, 1, t, 8, 1).expand(blocks, nkb, t, 8, 8))
+        return x.permute(0, 2, 1, 3, 4).reshape(blocks * t, nkb * 64)[: self.T, :K].contiguous()
+
+
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, out=None):
+    """out: None / a tensor -> row-major result; a TiledAct -> written in the tiled layout (returned as is)."""
     _need_cuda(x, weight)
     assert x.dtype == BF16 and weight.dtype == BF16
     x2 = x.contiguous().view(-1, x.shape[-1])
+    if isinstance(out, TiledAct):
+        assert out.T == x2.shape[0] and out.K == x2.shape[1]
+        call("vb_rmsnorm", out.data.data_ptr(), x2.data_ptr(), weight.data_ptr(), x2.shape[0], x2.shape[1], float(eps),
+             out.t_tile, _stream())
+        return out
     out = torch.empty_like(x2) if out is None else out
-    call("vb_rmsnorm", out.data_ptr(), x2.data_ptr(), weight.data_ptr(), x2.shape[0], x2.shape[1], float(eps), _stream())
+    call("vb_rmsnorm", out.data_ptr(), x2.data_ptr(), weight.data_ptr(), x2.shape[0], x2.shape[1], float(eps), 0,
+         _stream())
     return out.view(x.shape)
 
 
@@ -225,13 +264,19 @@ def paged_attn(q: torch.Tensor, kv_cache, slab_base: int, plan: RowPlan, n_rows:
     assert kv_cache.dtype == BF16 and kv_cache.is_contiguous()
     assert q.dtype == BF16 and q.is_contiguous() and plan.kv_indices is not None
     n_q, d = q.shape[1], q.shape[2]
-    out = torch.empty_like(q) if out is None else out
+    xt = 0
+    if isinstance(out, TiledAct):          # [rows, n_q * d] in the tiled layout: the O projection's activation
+        assert out.T == n_rows and out.K == n_q * d
+        out_ptr, xt = out.data.data_ptr(), out.t_tile
+    else:
+        out = torch.empty_like(q) if out is None else out
+        out_ptr = out.data_ptr()
     grid = workspace.grid if grid_ctas is None else min(int(grid_ctas), workspace.grid)
     sc = 1.0 / math.sqrt(d) if sm_scale is None else float(sm_scale)
-    call("vb_paged_attn", out.data_ptr(), q.data_ptr(), kv_cache.data_ptr(), int(slab_base), plan.row_kvlen.data_ptr(),
+    call("vb_paged_attn", out_ptr, q.data_ptr(), kv_cache.data_ptr(), int(slab_base), plan.row_kvlen.data_ptr(),
          plan.row_chunk_start.data_ptr(), plan.row_pagebase.data_ptr(), plan.row_old.data_ptr(),
          plan.kv_indices.data_ptr(), n_rows, n_q, n_kv,
-         d, page_size, chunk_tokens, sc, workspace.buf.data_ptr(), workspace.buf.numel(), grid, workspace.grid,
+         d, page_size, chunk_tokens, sc, workspace.buf.data_ptr(), workspace.buf.numel(), grid, workspace.grid, xt,
          _stream())
     return out
 
@@ -298,25 +343,34 @@ def _packed(w, tile_rows: int) -> PackedWeight:
     return pw
 
 
-def gemm(x: torch.Tensor, w, mode: int = 0, split_k: int = 1, out: Optional[torch.Tensor] = None,
-         tile_rows: int = 128, n_out: Optional[int] = None) -> torch.Tensor:
+def gemm(x, w, mode: int = 0, split_k: int = 1, out=None, tile_rows: int = 128, n_out: Optional[int] = None):
     """x [T, K] bf16, w [N, K] bf16 (nn.Linear.weight layout, or a PackedWeight).
     mode 0 -> bf16 [T, N]; mode 1 -> fp32 partials [split_k, T, N]; mode 2 -> bf16 [T, n_out] = silu(gate)*up
     with w rows packed per tile_rows-row tile (see interleave_gate_up; n_out defaults to N/2)."""
-    _need_cuda(x)
     pw = _packed(w, tile_rows)
-    assert x.dtype == BF16 and x.dim() == 2 and x.shape[1] == pw.K
-    T, K = x.shape
+    if isinstance(x, TiledAct):
+        T, K = x.T, x.K
+        assert K == pw.K and x.t_tile == gemm_t_tile(T)
+        x_map_ptr, x_tiles_ptr, dev = None, x.data.data_ptr(), x.data.device
+    else:
+        _need_cuda(x)
+        assert x.dtype == BF16 and x.dim() == 2 and x.shape[1] == pw.K
+        T, K = x.shape
+        x_map_ptr, x_tiles_ptr, dev = tensor_map_2d(x, gemm_t_tile(T)).ptr, None, x.device
     N = pw.N
     n_out = (N // 2 if mode == 2 else N) if n_out is None else n_out
+    if isinstance(out, TiledAct):
+        assert mode == 2 and out.T == T and out.K == n_out
+        call("vb_gemm_bf16", out.data.data_ptr(), pw.data.data_ptr(), x_map_ptr, x_tiles_ptr, T, N, K, n_out, mode, split_k,
+             tile_rows, n_out, 1, _stream())
+        return out
     if out is None:
         if mode == 1:
-            out = torch.empty(split_k, T, n_out, dtype=torch.float32, device=x.device)
+            out = torch.empty(split_k, T, n_out, dtype=torch.float32, device=dev)
         else:
-            out = torch.empty(T, n_out, dtype=BF16, device=x.device)
-    x_map = tensor_map_2d(x, gemm_t_tile(T))
-    call("vb_gemm_bf16", out.data_ptr(), pw.data.data_ptr(), x_map.ptr, T, N, K, n_out, mode, split_k, tile_rows, n_out,
-         _stream())
+            out = torch.empty(T, n_out, dtype=BF16, device=dev)
+    call("vb_gemm_bf16", out.data_ptr(), pw.data.data_ptr(), x_map_ptr, x_tiles_ptr, T, N, K, n_out, mode, split_k,
+         tile_rows, n_out, 0, _stream())
     return out
 
 
@@ -492,10 +546,16 @@ def reduce_residual_rmsnorm(partials: torch.Tensor, residual: Optional[torch.Ten
     S, T, N = partials.shape
     if want_hidden and hidden_out is None:
         hidden_out = torch.empty(T, N, dtype=BF16, device=partials.device)
-    if norm_weight is not None and normed_out is None:
-        normed_out = torch.empty(T, N, dtype=BF16, device=partials.device)
-    call("vb_reduce_residual_rmsnorm", _p(hidden_out), _p(normed_out), partials.data_ptr(), S, _p(residual),
-         _p(norm_weight), T, N, float(eps), _stream())
+    xt = 0
+    if isinstance(normed_out, TiledAct):
+        assert normed_out.T == T and normed_out.K == N and norm_weight is not None
+        n_ptr, xt = normed_out.data.data_ptr(), normed_out.t_tile
+    else:
+        if norm_weight is not None and normed_out is None:
+            normed_out = torch.empty(T, N, dtype=BF16, device=partials.device)
+        n_ptr = _p(normed_out)
+    call("vb_reduce_residual_rmsnorm", _p(hidden_out), n_ptr, partials.data_ptr(), S, _p(residual),
+         _p(norm_weight), T, N, float(eps), xt, _stream())
     return hidden_out, normed_out
 
 
