@@ -17,3 +17,6 @@ echo "ncu launches exit $?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:paged_attn -c 3 -o $o/${tag}_attn_full -f \
   python tests/prof_attn.py 728 > $o/${tag}_ncu_attn.log 2>&1
 echo "ncu attn exit $?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -c 3 -o $o/${tag}_gemm_full -f \
+  python tests/prof_gemm.py > $o/${tag}_ncu_gemm.log 2>&1
+echo "ncu gemm exit $?"

@@ -7,7 +7,7 @@ sys.path.insert(0, ".")
 from vox_serve_b200 import ops  # noqa: E402
 
 kvlen = int(sys.argv[1]) if len(sys.argv) > 1 else 728
-grid = int(sys.argv[2]) if len(sys.argv) > 2 else 296
+grid = int(sys.argv[2]) if len(sys.argv) > 2 else 148
 B, hq, hkv, D, ps = 32, 24, 8, 128, 128
 dev = "cuda"
 n_pages_req = (kvlen + ps - 1) // ps

@@ -9,7 +9,7 @@ from vox_serve_b200 import _lib, ops  # noqa: E402
 from vox_serve_b200.engine import LlamaDims, LlamaEngine, LlamaWeights  # noqa: E402
 from vox_serve_b200.model.orpheus import synthetic_state_dict  # noqa: E402
 
-NAMES = {1: "gemm", 2: "attn", 3: "chain", 4: "sample", 10: "rope_tab", 20: " gemm:dep-released", 21: " gemm:acc-done"}
+NAMES = {22: " attn:first-tile", 23: " attn:last-tile", 1: "gemm", 2: "attn", 3: "chain", 4: "sample", 10: "rope_tab", 20: " gemm:dep-released", 21: " gemm:acc-done"}
 for p in range(4):
     NAMES[30 + p] = f" chain:x-ready p{p}"
     NAMES[40 + p] = f" chain:acc-done p{p}"
@@ -45,11 +45,18 @@ def main():
     g = torch.cuda.CUDAGraph()
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
+    def run():
+        if mode == "attn":      # the 28 attention launches of one step, back to back (what bench.py's roofline_attention times)
+            for i in range(d.num_hidden_layers):
+                eng.attention_only(i, B, eng.plan)
+        else:
+            eng.forward(ids, pos, B)
+
     with torch.cuda.stream(s):
-        eng.forward(ids, pos, B)
+        run()
         torch.cuda.synchronize()
         with torch.cuda.graph(g, stream=s):
-            eng.forward(ids, pos, B)
+            run()
     torch.cuda.current_stream().wait_stream(s)
     for _ in range(3):
         g.replay()
@@ -81,6 +88,13 @@ def main():
         roles = ["w-issue", "converted", "x-landed", "mma-ready", "committed", "cfull-arrive", "fenced", "x-issued", "mma-b-ready", "-"]
         base = int(fine[fine > 0].min())
         print("fine marks of the LAST chain launch, block 0 (us since first mark): slot index g ->", roles)
+        if mode == "attn":
+            print("attention tiles of block 0 (last launch): tile -> [producer slot free / issue, tile landed (warp 0), warp 0 done]")
+            for gi in range(64):
+                if int(fine[:3, gi].max()) == 0:
+                    break
+                print(f"tile {gi:3d}  " + "  ".join(f"{(int(fine[r, gi]) - base) / 1e3:8.2f}" if int(fine[r, gi]) else "       -" for r in range(3)))
+            return
         print("epilogue marks per phase [acc-done, partial-stored, released, peers-in, tail-done, grid-arrived, next-dep-seen]:")
         for ph in range(4):
             row = [int(fine[8, ph * 8 + i]) for i in range(7)]

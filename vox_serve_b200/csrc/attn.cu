@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tr = (tid == 0 && trace_block0()) ? trace_begin(2) : -1;
+  unsigned long long* fine = (lane == 0) ? trace_fine_base() : nullptr;    // (dev) per-tile marks, block 0
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
         }
         ++issued;
         mbar_wait(&empty[stage], ph ^ 1);
+        trace_fine(fine, 0, base + k - c0);
         if (lane == 0) {
           meta[stage] = m;
           mbar_arrive_expect_tx(&full[stage], 2 * TOK * ROWB);
@@ -278,6 +280,8 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
   uint32_t ph = 0;
   for (int Lx = c0; Lx < c1; ++Lx) {
     mbar_wait(&full[stage], ph);
+    if (warp == 0) trace_fine(fine, 1, Lx - c0);
+    if (tr >= 0 && Lx == c0) trace_mark(22);          // first tile landed
     const TileMeta m = meta[stage];
     const uint32_t kbase = smem_u32(smem + stage * L.stage_bytes);
     const uint32_t vbase = kbase + KVT;
@@ -381,9 +385,11 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
     // this warp is done with the stage's tiles: hand the slot back to the producer
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[stage]);
+    if (warp == 0) trace_fine(fine, 2, Lx - c0);
     if (++stage == STAGES) { stage = 0; ph ^= 1; }
 
     if (!(m.flags & 2)) continue;
+    if (tr >= 0 && Lx == c1 - 1) trace_mark(23);      // last tile consumed: what follows is the segment tail / merge
 
     // ================= end of segment =================
 #pragma unroll
@@ -444,49 +450,69 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
         }
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last) {
-          // merge this head group's partials in CTA order: slot 1 only if the row starts inside CTA cta_a's range
+          // merge this head group's partials in CTA order (slot 1 only if the row starts inside CTA cta_a's range).
+          // All CTAs reach this point at about the same time, so the merge is pure tail latency: every load of a
+          // step is issued before the first one is used (two L2 round trips per four parts, not two per part).
           const int Ls = s_cstart[m.row];
-          for (int gg = 0; gg < G; ++gg) {
-            const int hq = hq0 + gg;
-            float Mx = -INFINITY;
-            for (int cb = 0; cb < m.n_parts; cb += 32) {
+          const int n = m.n_parts;
+          auto pslot_of = [&](int c) {
+            return static_cast<size_t>(m.cta_a + c) * 2 + ((c == 0 && Ls > m.cta_a * per) ? 1 : 0);
+          };
+          for (int g0 = 0; g0 < G; g0 += 4) {
+            float Mx[4];
+#pragma unroll
+            for (int hh = 0; hh < 4; ++hh) Mx[hh] = -INFINITY;
+            for (int cb = 0; cb < n; cb += 32) {
               const int c = cb + lane;
-              float mm = -INFINITY;
-              if (c < m.n_parts) {
-                const size_t ps = static_cast<size_t>(m.cta_a + c) * 2 + ((c == 0 && Ls > m.cta_a * per) ? 1 : 0);
-                mm = __ldcg(&p.part_ml[(ps * p.n_q + hq) * 2]);
-              }
-              Mx = fmaxf(Mx, warp_max(mm));
+              float mm[4];
+#pragma unroll
+              for (int hh = 0; hh < 4; ++hh)
+                mm[hh] = (c < n && g0 + hh < G) ? __ldcg(&p.part_ml[(pslot_of(c) * p.n_q + hq0 + g0 + hh) * 2]) : -INFINITY;
+#pragma unroll
+              for (int hh = 0; hh < 4; ++hh) Mx[hh] = fmaxf(Mx[hh], warp_max(mm[hh]));
             }
-            float acc[D / 32];
+            float acc[4][D / 32], den[4];
 #pragma unroll
-            for (int j = 0; j < D / 32; ++j) acc[j] = 0.f;
-            float den = 0.f;
-            for (int cb = 0; cb < m.n_parts; cb += 32) {
-              const int c = cb + lane;
-              float sc = 0.f, ll = 0.f;
-              if (c < m.n_parts) {
-                const size_t ps = static_cast<size_t>(m.cta_a + c) * 2 + ((c == 0 && Ls > m.cta_a * per) ? 1 : 0);
-                const float mm = __ldcg(&p.part_ml[(ps * p.n_q + hq) * 2]);
-                ll = __ldcg(&p.part_ml[(ps * p.n_q + hq) * 2 + 1]);
-                sc = (mm == -INFINITY) ? 0.f : ex2_approx(mm - Mx);
+            for (int hh = 0; hh < 4; ++hh) {
+              den[hh] = 0.f;
+#pragma unroll
+              for (int j = 0; j < D / 32; ++j) acc[hh][j] = 0.f;
+            }
+            for (int cb = 0; cb < n; cb += 4) {
+              float mm[4][4], ll[4][4], v[4][4][D / 32];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const bool okc = cb + k < n;
+                const size_t ps = pslot_of(okc ? cb + k : 0);
+#pragma unroll
+                for (int hh = 0; hh < 4; ++hh) {
+                  const bool ok = okc && g0 + hh < G;
+                  const size_t hb = ps * p.n_q + hq0 + g0 + hh;
+                  mm[k][hh] = ok ? __ldcg(&p.part_ml[hb * 2]) : -INFINITY;
+                  ll[k][hh] = ok ? __ldcg(&p.part_ml[hb * 2 + 1]) : 0.f;
+#pragma unroll
+                  for (int j = 0; j < D / 32; ++j) v[k][hh][j] = ok ? __ldcg(&p.part_o[hb * D + j * 32 + lane]) : 0.f;
+                }
               }
-              den += warp_sum(sc * ll);
-              const int nc = min(32, m.n_parts - cb);
-#pragma unroll 4
-              for (int k = 0; k < nc; ++k) {
-                const float sk = __shfl_sync(0xffffffffu, sc, k);
-                const size_t ps = static_cast<size_t>(m.cta_a + cb + k) * 2 +
-                                  ((cb + k == 0 && Ls > m.cta_a * per) ? 1 : 0);
-                const float* po = p.part_o + (ps * p.n_q + hq) * D;
 #pragma unroll
-                for (int j = 0; j < D / 32; ++j) acc[j] += sk * __ldcg(&po[j * 32 + lane]);
+              for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int hh = 0; hh < 4; ++hh) {
+                  const float sc = (mm[k][hh] == -INFINITY) ? 0.f : ex2_approx(mm[k][hh] - Mx[hh]);
+                  den[hh] += sc * ll[k][hh];
+#pragma unroll
+                  for (int j = 0; j < D / 32; ++j) acc[hh][j] += sc * v[k][hh][j];
+                }
+            }
+#pragma unroll
+            for (int hh = 0; hh < 4; ++hh) {
+              if (g0 + hh < G) {
+                const float inv = 1.f / den[hh];
+#pragma unroll
+                for (int j = 0; j < D / 32; ++j)
+                  p.out[attn_out_index(p, m.row, hq0 + g0 + hh, j * 32 + lane, D)] = __float2bfloat16_rn(acc[hh][j] * inv);
               }
             }
-            const float inv = 1.f / den;
-#pragma unroll
-            for (int j = 0; j < D / 32; ++j)
-              p.out[attn_out_index(p, m.row, hq, j * 32 + lane, D)] = __float2bfloat16_rn(acc[j] * inv);
           }
         }
       }

@@ -133,7 +133,7 @@ static __device__ unsigned long long* g_trace_buf = nullptr;
   }
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");   // also a compiler barrier: marks stay in place
   return t;
 }
 __device__ __forceinline__ int trace_begin(int id, int aux = 0) {

@@ -82,6 +82,11 @@ class LlamaWeights:
             self.layers.append(self.pack_layer(put(sd[n["ln1"]]), put(sd[n["q"]]), put(sd[n["k"]]), put(sd[n["v"]]),
                                                put(sd[n["o"]]), put(sd[n["ln2"]]), put(sd[n["gate"]]),
                                                put(sd[n["up"]]), put(sd[n["down"]]), self.gu_half, dims.head_dim))
+        if dev.type == "cuda":
+            # the row-major originals were just dropped: hand their blocks back NOW, not inside the first CUDA-graph
+            # capture on the request path (capture_begin empties the allocator cache: ~1 s for 6.6 GB of blocks)
+            torch.cuda.synchronize(dev)
+            torch.cuda.empty_cache()
         return self
 
     @staticmethod
@@ -280,10 +285,23 @@ class LlamaEngine:
     # ---- kernel-isolated passes for the roofline measurement (bench.py) --------------------------------
     def gemm_pass(self, n_rows: int) -> None:
         """Every projection launch of one decode step (QKV, O, gate/up, down per layer + lm_head) on the live
-        buffers, nothing else: what bench.py replays to time the projection kernel alone (fused decode modes:
-        the norm / RoPE / append / SiLU / residual work rides inside these launches)."""
+        buffers, nothing else: what bench.py replays to time the projection kernel alone.  Follows the engine's
+        decode mode (separate kernels with tiled activations by default; fused projections otherwise)."""
         d, w, R = self.dims, self.w, n_rows
         hq, hkv, D, H, I = d.num_attention_heads, d.num_key_value_heads, d.head_dim, d.hidden_size, d.intermediate_size
+        if self.force_unfused or not self.fused_ok:
+            tiled = R <= self.FUSED_MAX_ROWS and self.tiled_acts
+            normed = self.normed_t.view_rows(R) if tiled else self.normed[:R]
+            attn_o = self.attn_t.view_rows(R) if tiled else self.attn[:R].view(R, hq * D)
+            act = self.act_t.view_rows(R) if tiled else self.act[:R]
+            s_qkv, s_o, s_dn = self._split(self.split_qkv, R), self._split(self.split_o, R), self._split(self.split_down, R)
+            for L in w.layers:
+                ops.gemm(normed, L["qkv"], mode=1, split_k=s_qkv, out=self._partials(s_qkv, R, self.qkv_w), tile_rows=D)
+                ops.gemm(attn_o, L["o"], mode=1, split_k=s_o, out=self._partials(s_o, R, H))
+                ops.gemm(normed, L["gu"], mode=2, out=act, tile_rows=2 * self.gu_half, n_out=I)
+                ops.gemm(act, L["down"], mode=1, split_k=s_dn, out=self._partials(s_dn, R, H))
+            ops.gemm(normed, w.lm_head, mode=0, out=self.logits[:min(R, self.max_out_rows)])
+            return
         hidden, q, attn, act = self.hidden[:R], self.q[:R], self.attn[:R], self.act[:R]
         tiles_h = (H + 127) // 128
         ssq = self.ssq[: tiles_h * R].view(tiles_h, R)
