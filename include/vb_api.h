@@ -122,9 +122,11 @@ int vb_paged_attn(void* d_out, const void* d_q, const void* d_kv, int64_t slab_b
  * x_map: vb_tensor_map_2d_bf16(X, T, K, ldx, t_tile) with t_tile = vb_gemm_t_tile(T).
  * mode 0: Y bf16 [T][ldy]           (split_k must be 1)
  * mode 1: Y fp32 partials [split_k][T][ldy]   (vb_reduce_residual_rmsnorm / vb_qkv_rope_append sum them in split order)
- * mode 2: W rows packed per tile as h = tile_rows/2 gate rows then the h matching up rows (N = packed rows,
- *         zero-padded to a multiple of tile_rows); Y bf16 [T][ldy] holds silu(gate)*up with the reference's
- *         bf16 rounding points (orpheus.py:46-48) for the first n_out (0 = N/2) outputs. */
+ * mode 2: W rows packed per tile (tile_rows = 32, 64, 96 or 128) as [16 gate rows][the 16 matching up rows] per
+ *         epilogue warp -- gate and up of one output sit 16 lanes apart in the same accumulator quarter, so the
+ *         product is one warp shuffle, no shared-memory exchange -- (N = packed rows, zero-padded to a multiple of
+ *         tile_rows); Y bf16 [T][ldy] holds silu(gate)*up with the reference's bf16 rounding points
+ *         (orpheus.py:46-48) for the first n_out (0 = N/2) outputs. */
 size_t vb_weight_tiles_bytes(int N, int K, int tile_rows);
 int vb_pack_weight_tiles(void* d_dst, const void* d_w, int N, int K, int64_t ldw, int tile_rows, void* stream);
 int vb_gemm_t_tile(int T);

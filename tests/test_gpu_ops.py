@@ -304,7 +304,7 @@ def test_qkv_rope_append(ops):
     assert torch.equal(dcache.cpu()[pg, 1, sl], v)
 
 
-@pytest.mark.parametrize("T,I,K,h", [(32, 1024, 768, 64), (32, 8192, 3072, 56), (5, 520, 256, 24), (64, 1000, 512, 8)])
+@pytest.mark.parametrize("T,I,K,h", [(32, 1024, 768, 64), (32, 8192, 3072, 64), (32, 8192, 3072, 48), (5, 520, 256, 32), (64, 1000, 512, 16)])
 def test_gemm_gate_up_silu_tile_rows(ops, T, I, K, h):
     """gate/up rows packed h + h per tile (zero-padded tail tile): unfused (TMA B operand) and norm-fused variants."""
     import torch.nn.functional as F
@@ -419,9 +419,9 @@ def test_tiled_activation_layout_roundtrip(ops):
     # gate/up GEMM writing its SiLU product tiled, then the down projection reading it
     wg = (torch.randn(I, H, generator=g(5)) * 0.05).to(BF).cuda()
     wu = (torch.randn(I, H, generator=g(6)) * 0.05).to(BF).cuda()
-    wi = ops.interleave_gate_up(wg, wu, 56)
-    a_rows = ops.gemm(ref, wi, mode=2, tile_rows=112, n_out=I)
-    a_t = ops.gemm(xt, wi, mode=2, tile_rows=112, n_out=I, out=ops.TiledAct(T, I, "cuda"))
+    wi = ops.interleave_gate_up(wg, wu, 48)
+    a_rows = ops.gemm(ref, wi, mode=2, tile_rows=96, n_out=I)
+    a_t = ops.gemm(xt, wi, mode=2, tile_rows=96, n_out=I, out=ops.TiledAct(T, I, "cuda"))
     assert torch.equal(a_t.to_rows(), a_rows)
     wd = (torch.randn(H, I, generator=g(7)) * 0.05).to(BF).cuda()
     assert torch.equal(ops.gemm(a_t, wd, mode=1, split_k=2), ops.gemm(a_rows, wd, mode=1, split_k=2))

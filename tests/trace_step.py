@@ -49,6 +49,10 @@ def main():
         if mode == "attn":      # the 28 attention launches of one step, back to back (what bench.py's roofline_attention times)
             for i in range(d.num_hidden_layers):
                 eng.attention_only(i, B, eng.plan)
+        elif mode == "gu":      # only the gate/up projections, back to back (instruction cache stays warm)
+            for L in w.layers:
+                ops.gemm(eng.normed_t.view_rows(B), L["gu"], mode=2, out=eng.act_t.view_rows(B), tile_rows=2 * eng.gu_half,
+                         n_out=d.intermediate_size)
         else:
             eng.forward(ids, pos, B)
 
@@ -99,7 +103,9 @@ def main():
         for ph in range(4):
             row = [int(fine[8, ph * 8 + i]) for i in range(7)]
             print(f"  p{ph}: " + "  ".join(f"{(v - base) / 1e3:8.2f}" if v else "       -" for v in row))
-        print("role-5 marks (gemm epilogue):", [round((int(v) - base) / 1e3, 2) if int(v) else None for v in fine[5, :30]])
+        for q in range(4):
+            print(f"epilogue marks, TMEM quarter {q} [start, ld0, bar, store-done, bar, data-seen | +4: chunk 1]:",
+                  [round((int(v) - base) / 1e3, 2) if int(v) else None for v in fine[6 + q, :14]])
         for gi in range(256):
             if int(fine[:5, gi].max()) == 0:
                 break

@@ -321,37 +321,35 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
       if (et == 0 && trace_block0()) trace_mark(40 + p);
       trace_fine(fine, 8, p * 8 + 0);
       if (ph.kind == CK_SILU) {
+        // rows packed per warp: lanes 0..15 gate, lanes 16..31 the matching up rows (ops.interleave_gate_up); lanes
+        // 0..15 finish the even tokens of their output column, lanes 16..31 the odd ones
         const int h = ph.tile_rows >> 1;
-        const bool is_gate = row < h, is_up = row >= h && row < 2 * h;
-        constexpr int ldx = 17;
+        const bool hi = lane >= 16;
+        const int n_out = it.tile * h + quarter * 16 + (lane & 15);
+        const bool live_o = row < ph.tile_rows && n_out < ph.n_out;
+        __nv_bfloat16* y = static_cast<__nv_bfloat16*>(ph.y) + n_out;
         for (int c0 = 0; c0 < T_TILE; c0 += 16) {
           uint32_t v[16];
           tmem_ld_32x16(taddr + c0, v);
           tmem_ld_wait();
-          if (is_up) {
+          float o[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) xchg[(row - h) * ldx + j] = round_bf16(__uint_as_float(v[j]));
+          for (int i = 0; i < 8; ++i) {
+            const float mine = __uint_as_float(v[2 * i + (hi ? 1 : 0)]);
+            const float send = __uint_as_float(v[2 * i + (hi ? 0 : 1)]);
+            const float other = __shfl_xor_sync(0xffffffffu, send, 16);
+            const float gv = round_bf16(hi ? other : mine);
+            const float up = round_bf16(hi ? mine : other);
+            const float sv = round_bf16(gv / (1.0f + expf(-gv)));
+            o[i] = sv * up;
           }
-          ch_epi_bar();
-          if (is_gate) {
-            const int n_out = it.tile * h + row;
-            if (n_out < ph.n_out) {
-              __nv_bfloat16* y = static_cast<__nv_bfloat16*>(ph.y);
-              float o[16];
+          if (live_o) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float gv = round_bf16(__uint_as_float(v[j]));
-                const float sv = round_bf16(gv / (1.0f + expf(-gv)));
-                o[j] = sv * xchg[row * ldx + j];
-              }
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int t = c0 + j;
-                if (t < P.T) y[static_cast<size_t>(t) * ph.n_out + n_out] = __float2bfloat16_rn(o[j]);
-              }
+            for (int i = 0; i < 8; ++i) {
+              const int t = c0 + 2 * i + (hi ? 1 : 0);
+              if (t < P.T) y[static_cast<size_t>(t) * ph.n_out] = __float2bfloat16_rn(o[i]);
             }
           }
-          ch_epi_bar();
         }
       } else {
         // ---- split-K: park the partial tile in the L2-resident workspace, meet the other splits of the tile ----
@@ -550,7 +548,7 @@ int vb_decode_chain(const vb_chain_phase* phases, int n_phases, int T, const flo
       norm_k = in.K > norm_k ? in.K : norm_k;
     }
     if (in.kind == CK_SILU)
-      VB_CHECK_ARG(in.tile_rows % 16 == 0 && in.N % in.tile_rows == 0, "vb_decode_chain: phase %d: gate/up tile_rows %d", i,
+      VB_CHECK_ARG(in.tile_rows % 32 == 0 && in.N % in.tile_rows == 0, "vb_decode_chain: phase %d: gate/up tile_rows %d", i,
                    in.tile_rows);
     if (in.kind == CK_ROPE) {
       VB_CHECK_ARG(in.layer_kv && d_rope_cs && d_row_page && d_row_slot && (in.tile_rows == 64 || in.tile_rows == 128) &&

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
   const bool reducing = p.mode == GM_RESID || p.mode == GM_ROPE;
   const int tr = (threadIdx.x == 0 && trace_block0()) ? trace_begin(1, p.mode) : -1;
   // (dev) per-stage marks of the gate/up launches: producer and MMA threads of block 0
-  unsigned long long* fine = (lane == 0 && warp <= 2 && p.mode == GM_SILU) ? trace_fine_base() : nullptr;
+  unsigned long long* fine = (lane == 0 && warp <= 1 && p.mode == GM_SILU) ? trace_fine_base() : nullptr;
 
   if (warp == 0 && lane == 0) {
     if (!p.x_tiles) prefetch_tmap(&x_map);
@@ -269,48 +269,48 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const int t_base = t_blk * p.t_tile;
     if (p.mode == GM_SILU) {
+      // Rows are packed per warp: lanes 0..15 hold 16 gate rows, lanes 16..31 the 16 matching up rows (see
+      // ops.interleave_gate_up), so no shared-memory exchange and no barrier: each of the four epilogue warps runs
+      // on its own.  Both half-warps work: lanes 0..15 finish the even tokens of their output column, lanes 16..31
+      // the odd ones (gate and up cross over with one shuffle each).  The warp is alone on its scheduler, so the
+      // arithmetic is kept short: the store index is split into a per-thread part and a 3-instruction per-token part.
       const int h = p.tile_rows >> 1;
-      const bool is_gate = row < h, is_up = row >= h && row < 2 * h;
-      constexpr int ldx = 17;
-      trace_fine(fine, 5, 0);
+      const bool hi = lane >= 16;
+      const int n_out = n_tile * h + quarter * 16 + (lane & 15);
+      const bool live = row < p.tile_rows && n_out < p.n_out;
+      __nv_bfloat16* y = static_cast<__nv_bfloat16*>(p.y);
+      // tiled output: element (t, n) of token block t_blk sits at col_base + tt * 64 + ((c ^ (tt & 7)) << 3)
+      const int yc = (n_out >> 3) & 7;
+      const size_t col_base = p.y_tiled
+          ? ((static_cast<size_t>(t_blk) * ((p.n_out + 63) >> 6) + (n_out >> 6)) * p.t_tile) * 64 + (n_out & 7)
+          : static_cast<size_t>(t_base) * p.ldy + n_out;
       for (int c0 = 0; c0 < p.t_tile; c0 += 16) {
         uint32_t v[16];
         tmem_ld_32x16(taddr + c0, v);
         tmem_ld_wait();
-        trace_fine(fine, 5, 1 + c0 / 4);
-        if (is_up) {
+        float o[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) xchg[(row - h) * ldx + j] = round_bf16(__uint_as_float(v[j]));
+        for (int i = 0; i < 8; ++i) {
+          // this lane finishes token c0 + 2 i + hi: gate from the low half-warp, up from the high one
+          const float mine = __uint_as_float(v[2 * i + (hi ? 1 : 0)]);
+          const float send = __uint_as_float(v[2 * i + (hi ? 0 : 1)]);       // what the partner lane needs from here
+          const float other = __shfl_xor_sync(0xffffffffu, send, 16);
+          const float g = round_bf16(hi ? other : mine);
+          const float up = round_bf16(hi ? mine : other);
+          const float s = round_bf16(g / (1.0f + expf(-g)));
+          o[i] = s * up;
         }
-        epi_bar();
-        trace_fine(fine, 5, 2 + c0 / 4);
-        if (is_gate) {
-          const int n_out = n_tile * h + row;
-          if (n_out < p.n_out) {
-            __nv_bfloat16* y = static_cast<__nv_bfloat16*>(p.y);
-            // all 16 SiLU products first (independent chains: the warp is alone on its scheduler, so a serial
-            // expf + divide per element is a long dependent chain), then the stores
-            float o[16];
+        if (live) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float g = round_bf16(__uint_as_float(v[j]));
-              const float s = round_bf16(g / (1.0f + expf(-g)));
-              o[j] = s * xchg[row * ldx + j];
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int t = t_base + c0 + j;
-              if (t < p.T) {
-                const size_t yi = p.y_tiled ? xt_index(t, n_out, p.t_tile, (p.n_out + 63) >> 6)
-                                            : static_cast<size_t>(t) * p.ldy + n_out;
-                y[yi] = __float2bfloat16_rn(o[j]);
-              }
+          for (int i = 0; i < 8; ++i) {
+            const int tt = c0 + 2 * i + (hi ? 1 : 0);
+            if (t_base + tt < p.T) {
+              const size_t yi = p.y_tiled ? col_base + static_cast<size_t>(tt) * 64 + ((yc ^ (tt & 7)) << 3)
+                                          : col_base + static_cast<size_t>(tt) * p.ldy;
+              y[yi] = __float2bfloat16_rn(o[i]);
             }
           }
         }
-        trace_fine(fine, 5, 3 + c0 / 4);
-        epi_bar();
-        trace_fine(fine, 5, 4 + c0 / 4);
       }
     } else if (!reducing) {
       const int n = n_tile * p.tile_rows + row;
@@ -449,12 +449,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
   } else {
     __syncthreads();
   }
-  trace_fine(fine, 5, 20 + warp);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
-  trace_fine(fine, 5, 24 + warp);
   trace_end(tr);
 }
 
@@ -618,8 +616,8 @@ int vb_gemm_bf16(void* d_y, const void* d_w_tiles, const void* x_map, const void
   VB_CHECK_ARG(!y_tiled || mode == 2, "vb_gemm_bf16: tiled output is a mode 2 option");
   VB_CHECK_ARG(mode >= 0 && mode <= 2, "vb_gemm_bf16: mode %d", mode);
   VB_CHECK_ARG(mode == 1 || split_k == 1, "vb_gemm_bf16: split_k > 1 needs mode 1 (fp32 partials)");
-  VB_CHECK_ARG(mode != 2 || (tile_rows % 16 == 0 && N % tile_rows == 0),
-               "vb_gemm_bf16: mode 2 needs tile_rows %% 16 == 0 and N %% tile_rows == 0 (h gate + h up rows per tile)");
+  VB_CHECK_ARG(mode != 2 || (tile_rows % 32 == 0 && N % tile_rows == 0),
+               "vb_gemm_bf16: mode 2 needs tile_rows %% 32 == 0 and N %% tile_rows == 0 (16 gate + 16 up rows per warp)");
   GemmParams p = {};
   p.y = d_y; p.T = T; p.N = N; p.K = K; p.ldy = ldy; p.mode = mode; p.split_k = split_k;
   p.tile_rows = tile_rows > 0 ? tile_rows : 128;
@@ -648,7 +646,7 @@ int vb_proj_norm_gateup_silu(void* d_act_out, const void* d_w_tiles, const void*
                              int tile_rows, int n_out, void* stream) {
   VB_CHECK_ARG(d_act_out && d_w_tiles && x_map && d_ssq && d_norm_weight, "vb_proj_norm_gateup_silu: null pointer");
   VB_CHECK_ARG(T > 0 && T <= 64, "vb_proj_norm_gateup_silu: T %d outside (0, 64]", T);
-  VB_CHECK_ARG(tile_rows % 16 == 0 && N_packed % tile_rows == 0, "vb_proj_norm_gateup_silu: bad tile_rows %d", tile_rows);
+  VB_CHECK_ARG(tile_rows % 32 == 0 && N_packed % tile_rows == 0, "vb_proj_norm_gateup_silu: bad tile_rows %d", tile_rows);
   VB_CHECK_ARG(K % 64 == 0, "vb_proj_norm_gateup_silu: K %d must be a multiple of 64", K);
   GemmParams p = {};
   p.y = d_act_out; p.T = T; p.N = N_packed; p.K = K; p.ldy = n_out; p.mode = GM_SILU; p.split_k = 1;

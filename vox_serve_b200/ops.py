@@ -375,24 +375,25 @@ def gemm(x, w, mode: int = 0, split_k: int = 1, out=None, tile_rows: int = 128, 
 
 
 def gate_up_tile_half(I: int, sms: Optional[int] = None) -> int:
-    """Gate rows per tile (h; a tile is h gate rows + the h matching up rows) so that the gate/up projection is cut
-    into about one CTA per SM: the smallest multiple of 8 with ceil(I / h) <= SMs, at most 64."""
+    """Gate rows per tile (h): a multiple of 16 (each epilogue warp pairs 16 gate with 16 up rows), at most 64, the
+    smallest with ceil(I / h) <= SMs so that the gate/up projection is about one CTA per SM."""
     sms = device_info()[0] if sms is None else sms
-    h = max(8, ((I + sms - 1) // sms + 7) // 8 * 8)
+    h = max(16, ((I + sms - 1) // sms + 15) // 16 * 16)
     return min(h, 64)
 
 
 def interleave_gate_up(gate_w: torch.Tensor, up_w: torch.Tensor, h: int = 64) -> torch.Tensor:
-    """[I, K] x 2 -> [2 * ceil(I/h) * h, K]: per tile h gate rows then the h matching up rows; I is zero-padded to a
-    multiple of h (the padded outputs are never stored)."""
+    """[I, K] x 2 -> [2 * ceil(I/h) * h, K].  A tile holds h gate rows and the h matching up rows, grouped per
+    epilogue warp: [16 gate rows][their 16 up rows] x (h / 16), so that gate and up of one output sit 16 lanes apart in
+    the same warp's accumulator quarter.  I is zero-padded to a multiple of h (the padded outputs are never stored)."""
     I, K = gate_w.shape
-    assert up_w.shape == gate_w.shape and h % 8 == 0
+    assert up_w.shape == gate_w.shape and h % 16 == 0 and 16 <= h <= 64
     tiles = (I + h - 1) // h
     if tiles * h != I:
         pad = torch.zeros(tiles * h - I, K, dtype=gate_w.dtype, device=gate_w.device)
         gate_w, up_w = torch.cat((gate_w, pad), 0), torch.cat((up_w, pad), 0)
-    g = gate_w.view(tiles, h, K)
-    u = up_w.view(tiles, h, K)
+    g = gate_w.view(tiles * (h // 16), 16, K)
+    u = up_w.view(tiles * (h // 16), 16, K)
     return torch.cat((g, u), dim=1).reshape(2 * tiles * h, K).contiguous()
 
 
