@@ -150,13 +150,17 @@ int vb_gemm_bf16(void* d_y, const void* d_w_tiles, const void* x_map, const void
  *   q and k with the step's cos/sin table (vb_rope_table, rotate-half pairs, full head_dim), q -> q_out
  *   [T][n_q][D], k,v -> the page/slot of each row (row_page < 0: skipped).  orpheus.py:91-106,
  *   flashinfer_utils.py:243-244. */
-int vb_proj_residual(void* d_hidden_out, float* d_ssq_out, const void* d_w_tiles, const void* x_map,
-                     const void* d_residual, int T, int N, int K, int split_k, int tile_rows, void* stream);
-int vb_proj_norm_gateup_silu(void* d_act_out, const void* d_w_tiles, const void* x_map, const float* d_ssq,
-                             int n_ssq_parts, const void* d_norm_weight, float eps, int T, int N_packed, int K,
-                             int tile_rows, int n_out, void* stream);
+/* Activations: x_map (row-major, tensor-map boxes) or d_x_tiles (the XT(t_tile) layout, bulk copies; preferred) --
+ * one of the two.  d_hidden_tiles_out (optional): a second copy of the new hidden rows in the XT layout, i.e. the
+ * next norm-fused projection's d_x_tiles; y_tiled: write the gate/up product in the XT layout. */
+int vb_proj_residual(void* d_hidden_out, void* d_hidden_tiles_out, float* d_ssq_out, const void* d_w_tiles,
+                     const void* x_map, const void* d_x_tiles, const void* d_residual, int T, int N, int K, int split_k,
+                     int tile_rows, void* stream);
+int vb_proj_norm_gateup_silu(void* d_act_out, const void* d_w_tiles, const void* x_map, const void* d_x_tiles,
+                             const float* d_ssq, int n_ssq_parts, const void* d_norm_weight, float eps, int T,
+                             int N_packed, int K, int tile_rows, int n_out, int y_tiled, void* stream);
 int vb_proj_norm_qkv_rope_append(void* d_q_out, void* d_layer_kv, const void* d_w_tiles, const void* x_map,
-                                 const float* d_ssq, int n_ssq_parts, const void* d_norm_weight, float eps,
+                                 const void* d_x_tiles, const float* d_ssq, int n_ssq_parts, const void* d_norm_weight, float eps,
                                  const float* d_rope_cs, const int32_t* d_row_page, const int32_t* d_row_slot, int T,
                                  int K, int n_q, int n_kv, int head_dim, int page_size, int split_k, void* stream);
 /* ---- persistent projection chain (T <= 64): up to 4 dependent fused projections in ONE launch --------------------

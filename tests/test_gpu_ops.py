@@ -353,6 +353,15 @@ def test_proj_residual(ops, T, N, K, split, tile_rows):
         assert torch.allclose(ssq.cpu(), ssq_ref, rtol=1e-5, atol=1e-6)
     h2, _ = ops.proj_residual(x.cuda(), w.cuda(), None, split, tile_rows=tile_rows)
     assert_bf16_close(h2, lin, 1, 2e-2, "proj no residual", atol=tol)
+    # tiled activation in, tiled copy of the new hidden rows out: same numbers
+    xt = ops.TiledAct(T, K, "cuda")
+    xt.data.view(-1)[:] = 0
+    ops.rmsnorm(x.cuda(), torch.ones(K, dtype=BF).cuda(), 0.0, out=xt)      # any writer of the layout would do ...
+    ht = ops.TiledAct(T, N, "cuda")
+    xn = ops.rmsnorm(x.cuda(), torch.ones(K, dtype=BF).cuda(), 0.0)         # ... so compare against the same rows
+    h3, _ = ops.proj_residual(xt, w.cuda(), resid.cuda(), split, tile_rows=tile_rows, hidden_tiles_out=ht)
+    h4, _ = ops.proj_residual(xn, w.cuda(), resid.cuda(), split, tile_rows=tile_rows)
+    assert torch.equal(h3, h4) and torch.equal(ht.to_rows(), h3)
 
 
 @pytest.mark.parametrize("T,hq,hkv,D,K,split", [(6, 6, 2, 128, 768, 2), (32, 24, 8, 128, 3072, 3), (33, 4, 4, 64, 512, 1),

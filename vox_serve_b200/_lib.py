@@ -49,9 +49,9 @@ SIGNATURES = {
     "vb_weight_tiles_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vb_pack_weight_tiles": (c_int, [P, P, c_int, c_int, c_int64, c_int, P]),
     "vb_gemm_bf16": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
-    "vb_proj_residual": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
-    "vb_proj_norm_gateup_silu": (c_int, [P, P, P, P, c_int, P, c_float, c_int, c_int, c_int, c_int, c_int, P]),
-    "vb_proj_norm_qkv_rope_append": (c_int, [P, P, P, P, P, c_int, P, c_float, P, P, P, c_int, c_int, c_int, c_int,
+    "vb_proj_residual": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_proj_norm_gateup_silu": (c_int, [P, P, P, P, P, c_int, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_proj_norm_qkv_rope_append": (c_int, [P, P, P, P, P, P, c_int, P, c_float, P, P, P, c_int, c_int, c_int, c_int,
                                              c_int, c_int, c_int, P]),
     "vb_decode_chain_workspace_bytes": (c_size_t, [c_int]),
     "vb_decode_chain_flags_bytes": (c_size_t, [c_int]),

@@ -52,6 +52,7 @@ struct GemmParams {
   // mode 3
   const __nv_bfloat16* residual;
   float* ssq_out;           // [tiles][T]
+  __nv_bfloat16* y_tiles;   // optional second copy of the new hidden rows in the XT(t_tile) layout (next GEMM's input)
   // mode 4 (tile = one head, tile_rows = head_dim)
   __nv_bfloat16* q_out;
   __nv_bfloat16* kv;        // layer cache [pages][2][page_size][n_kv][D]
@@ -135,6 +136,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // operands of the reducing epilogues that do not depend on the accumulator: fetched early, used after the sum
+  float pre_a[GEMM_EPI_CHUNK], pre_b[GEMM_EPI_CHUNK];
+  int pre_pg[GEMM_EPI_CHUNK], pre_sl[GEMM_EPI_CHUNK];
+
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
@@ -206,19 +211,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
   } else {
     const int et = threadIdx.x - 64;              // 0..127
     if (bnorm) {
-      // ============ B-operand finishers: raw x tile (TMA) -> rmsnorm(x) * w in bf16, in place ============
+      // ============ B-operand finishers: raw x tile -> rmsnorm(x) * w in bf16, in place ============
       // the norm weights are parameters: staged in shared memory before the dependency wait
       for (int i = et * 8; i < p.K; i += GEMM_EPI_THREADS * 8)
         *reinterpret_cast<uint4*>(w_sm + i) = __ldg(reinterpret_cast<const uint4*>(p.n_w + i));
-      // tpt threads share a token; each owns `chunks` 16-byte chunks of every 64-wide block
+      pdl_wait();
+      // All four warps finish each tile together (tpt threads share a token, each owns `chunks` 16-byte chunks of the
+      // 64-wide block): the ring is only ~5 stages deep here, so what matters is how LONG a stage waits for its
+      // activation tile, not how many tiles are in flight (one warp per stage measured 26 us for the gate/up
+      // projection against 20 us this way; the 10-slot persistent chain is where warp-per-stage pays).
       const int tpt = GEMM_EPI_THREADS / p.t_tile;            // 8, 4, 2   (t_tile 16, 32, 64)
       const int chunks = 8 / tpt;                             // 1, 2, 4
       const int t = et / tpt, c0 = (et % tpt) * chunks;
-      pdl_wait();
       float rstd = 0.f;
       if (t < p.T) {
-        // per-tile partial sums of squares: batches of 8 loads in flight (a serial chain of L2 round trips here
-        // delayed the first MMA of every norm-fused projection by ~8 us)
+        // per-tile partial sums of squares, 8 loads in flight at a time
         float ss = 0.f;
         for (int i0 = 0; i0 < p.n_ssq_parts; i0 += 8) {
           float v[8];
@@ -256,6 +263,37 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
         __syncwarp();
         if (lane == 0) mbar_arrive(&cfull[s]);
         if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+    if (reducing) {
+      const int quarter_ = warp & 3, row_ = quarter_ * 32 + lane;
+      const int S_ = p.split_k;
+      const int rank_ = S_ > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+      if (p.mode == GM_RESID) {
+        if (!bnorm) pdl_wait();           // the residual may come from the kernel right in front of this one
+        const int n_ = n_tile * p.tile_rows + row_;
+#pragma unroll
+        for (int i = 0; i < GEMM_EPI_CHUNK; ++i) {
+          const int t = rank_ + i * S_;
+          pre_a[i] = 0.f;
+          if (p.residual && t < p.T && row_ < p.tile_rows && n_ < p.N) {
+            const unsigned short rb =
+                __ldcg(reinterpret_cast<const unsigned short*>(p.residual) + static_cast<size_t>(t) * p.N + n_);
+            pre_a[i] = __uint_as_float(static_cast<uint32_t>(rb) << 16);
+          }
+        }
+      } else {
+        const int D_ = p.tile_rows;
+        const bool rot = n_tile < p.n_q + p.n_kv;
+#pragma unroll
+        for (int i = 0; i < GEMM_EPI_CHUNK; ++i) {
+          const int t = rank_ + i * S_;
+          const bool ok = t < p.T && row_ < D_;
+          pre_a[i] = (ok && rot) ? p.rope_cs[static_cast<size_t>(t) * 2 * D_ + row_] : 1.f;
+          pre_b[i] = (ok && rot) ? p.rope_cs[static_cast<size_t>(t) * 2 * D_ + D_ + row_] : 0.f;
+          pre_pg[i] = (ok && n_tile >= p.n_q) ? p.row_page[t] : -1;
+          pre_sl[i] = (ok && n_tile >= p.n_q) ? p.row_slot[t] : 0;
+        }
       }
     }
     // ================= epilogue: TMEM -> registers -> global =================
@@ -383,6 +421,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
         }
         if (p.mode == GM_RESID) {
           __nv_bfloat16* hid = static_cast<__nv_bfloat16*>(p.y);
+          const int nkb_y = (p.N + 63) >> 6;
 #pragma unroll
           for (int i = 0; i < GEMM_EPI_CHUNK; ++i) {
             const int t = rank + (i0 + i) * S;
@@ -390,8 +429,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
             if (valid && i0 + i < n_mine) {
               const size_t idx = static_cast<size_t>(t) * p.N + n;
               float hv = round_bf16(a[i]);
-              if (p.residual) hv = round_bf16(__bfloat162float(p.residual[idx]) + hv);
-              hid[idx] = __float2bfloat16_rn(hv);
+              if (p.residual) {
+                float rv = pre_a[i];
+                if (i0 > 0) rv = __bfloat162float(p.residual[idx]);     // beyond the prefetched chunk
+                hv = round_bf16(rv + hv);
+              }
+              const __nv_bfloat16 hb = __float2bfloat16_rn(hv);
+              hid[idx] = hb;
+              if (p.y_tiles) p.y_tiles[xt_index(t, n, p.t_tile, nkb_y)] = hb;
               sq = hv * hv;
             }
             sq = warp_sum(sq);
@@ -420,20 +465,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
               if (i0 + i < n_mine) {
                 float v = xchg[row * ldx + i];
                 if (rot) {
-                  const float* cs = p.rope_cs + static_cast<size_t>(t) * 2 * D;
-                  v = v * cs[row] + sign * xchg[prow * ldx + i] * cs[D + row];
+                  float cv = pre_a[i], sv = pre_b[i];
+                  if (i0 > 0) {                  // beyond the prefetched chunk
+                    const float* cs = p.rope_cs + static_cast<size_t>(t) * 2 * D;
+                    cv = cs[row]; sv = cs[D + row];
+                  }
+                  v = v * cv + sign * xchg[prow * ldx + i] * sv;
                 }
                 const __nv_bfloat16 o = __float2bfloat16_rn(v);
                 if (head < p.n_q) {
                   p.q_out[(static_cast<size_t>(t) * p.n_q + head) * D + row] = o;
                 } else {
-                  const int page = p.row_page[t];
+                  const int page = i0 > 0 ? p.row_page[t] : pre_pg[i];
                   if (page >= 0) {
                     const size_t row_elems = static_cast<size_t>(p.n_kv) * D;
                     const size_t slab = static_cast<size_t>(p.page_size) * row_elems;
                     const int hk = head - p.n_q;               // 0 .. 2 n_kv - 1: k heads then v heads
                     const int is_v = hk >= p.n_kv ? 1 : 0;
-                    p.kv[(static_cast<size_t>(page) * 2 + is_v) * slab + static_cast<size_t>(p.row_slot[t]) * row_elems +
+                    const int slot_ = i0 > 0 ? p.row_slot[t] : pre_sl[i];
+                    p.kv[(static_cast<size_t>(page) * 2 + is_v) * slab + static_cast<size_t>(slot_) * row_elems +
                          static_cast<size_t>(hk - is_v * p.n_kv) * D + row] = o;
                   }
                 }
@@ -605,7 +655,11 @@ int vb_pack_weight_tiles(void* d_dst, const void* d_w, int N, int K, int64_t ldw
 }
 
 int vb_gemm_t_tile(int T) {
-  if (T <= 0) return 16;
+  // decode-sized steps: 16 / 32 / 64 (what the fused modes and the tiled activation layout use); beyond that the
+  // token tile grows in steps of 16 up to the 256 columns one MMA takes
+  if (T <= 16) return 16;
+  if (T <= 32) return 32;
+  if (T <= 64) return 64;
   if (T >= 256) return 256;
   return (T + 15) / 16 * 16;
 }
@@ -627,9 +681,10 @@ int vb_gemm_bf16(void* d_y, const void* d_w_tiles, const void* x_map, const void
   return launch_gemm(p, d_w_tiles, x_map, static_cast<cudaStream_t>(stream), d_x_tiles);
 }
 
-int vb_proj_residual(void* d_hidden_out, float* d_ssq_out, const void* d_w_tiles, const void* x_map,
-                     const void* d_residual, int T, int N, int K, int split_k, int tile_rows, void* stream) {
-  VB_CHECK_ARG(d_hidden_out && d_w_tiles && x_map, "vb_proj_residual: null pointer");
+int vb_proj_residual(void* d_hidden_out, void* d_hidden_tiles_out, float* d_ssq_out, const void* d_w_tiles,
+                     const void* x_map, const void* d_x_tiles, const void* d_residual, int T, int N, int K, int split_k,
+                     int tile_rows, void* stream) {
+  VB_CHECK_ARG(d_hidden_out && d_w_tiles && (x_map || d_x_tiles), "vb_proj_residual: null pointer");
   VB_CHECK_ARG(T > 0 && T <= 64, "vb_proj_residual: T %d outside (0, 64] (decode-sized batches only)", T);
   GemmParams p = {};
   p.y = d_hidden_out; p.T = T; p.N = N; p.K = K; p.ldy = N; p.mode = GM_RESID; p.split_k = split_k;
@@ -638,13 +693,15 @@ int vb_proj_residual(void* d_hidden_out, float* d_ssq_out, const void* d_w_tiles
   p.t_tile = fused_t_tile(T);
   p.residual = static_cast<const __nv_bfloat16*>(d_residual);
   p.ssq_out = d_ssq_out;
-  return launch_gemm(p, d_w_tiles, x_map, static_cast<cudaStream_t>(stream));
+  p.y_tiles = static_cast<__nv_bfloat16*>(d_hidden_tiles_out);
+  return launch_gemm(p, d_w_tiles, x_map, static_cast<cudaStream_t>(stream), d_x_tiles);
 }
 
-int vb_proj_norm_gateup_silu(void* d_act_out, const void* d_w_tiles, const void* x_map, const float* d_ssq,
-                             int n_ssq_parts, const void* d_norm_weight, float eps, int T, int N_packed, int K,
-                             int tile_rows, int n_out, void* stream) {
-  VB_CHECK_ARG(d_act_out && d_w_tiles && x_map && d_ssq && d_norm_weight, "vb_proj_norm_gateup_silu: null pointer");
+int vb_proj_norm_gateup_silu(void* d_act_out, const void* d_w_tiles, const void* x_map, const void* d_x_tiles,
+                             const float* d_ssq, int n_ssq_parts, const void* d_norm_weight, float eps, int T,
+                             int N_packed, int K, int tile_rows, int n_out, int y_tiled, void* stream) {
+  VB_CHECK_ARG(d_act_out && d_w_tiles && (x_map || d_x_tiles) && d_ssq && d_norm_weight,
+               "vb_proj_norm_gateup_silu: null pointer");
   VB_CHECK_ARG(T > 0 && T <= 64, "vb_proj_norm_gateup_silu: T %d outside (0, 64]", T);
   VB_CHECK_ARG(tile_rows % 32 == 0 && N_packed % tile_rows == 0, "vb_proj_norm_gateup_silu: bad tile_rows %d", tile_rows);
   VB_CHECK_ARG(K % 64 == 0, "vb_proj_norm_gateup_silu: K %d must be a multiple of 64", K);
@@ -654,14 +711,15 @@ int vb_proj_norm_gateup_silu(void* d_act_out, const void* d_w_tiles, const void*
   p.t_tile = fused_t_tile(T);
   p.norm = 1; p.n_ssq = d_ssq; p.n_ssq_parts = n_ssq_parts;
   p.n_w = static_cast<const __nv_bfloat16*>(d_norm_weight); p.n_eps = eps;
-  return launch_gemm(p, d_w_tiles, x_map, static_cast<cudaStream_t>(stream));
+  p.y_tiled = y_tiled;
+  return launch_gemm(p, d_w_tiles, x_map, static_cast<cudaStream_t>(stream), d_x_tiles);
 }
 
 int vb_proj_norm_qkv_rope_append(void* d_q_out, void* d_layer_kv, const void* d_w_tiles, const void* x_map,
-                                 const float* d_ssq, int n_ssq_parts, const void* d_norm_weight, float eps,
+                                 const void* d_x_tiles, const float* d_ssq, int n_ssq_parts, const void* d_norm_weight, float eps,
                                  const float* d_rope_cs, const int32_t* d_row_page, const int32_t* d_row_slot, int T,
                                  int K, int n_q, int n_kv, int head_dim, int page_size, int split_k, void* stream) {
-  VB_CHECK_ARG(d_q_out && d_layer_kv && d_w_tiles && x_map && d_ssq && d_norm_weight && d_rope_cs && d_row_page &&
+  VB_CHECK_ARG(d_q_out && d_layer_kv && d_w_tiles && (x_map || d_x_tiles) && d_ssq && d_norm_weight && d_rope_cs && d_row_page &&
                    d_row_slot,
                "vb_proj_norm_qkv_rope_append: null pointer");
   VB_CHECK_ARG(T > 0 && T <= 64, "vb_proj_norm_qkv_rope_append: T %d outside (0, 64]", T);
@@ -677,7 +735,7 @@ int vb_proj_norm_qkv_rope_append(void* d_q_out, void* d_layer_kv, const void* d_
   p.q_out = static_cast<__nv_bfloat16*>(d_q_out); p.kv = static_cast<__nv_bfloat16*>(d_layer_kv);
   p.rope_cs = d_rope_cs; p.row_page = d_row_page; p.row_slot = d_row_slot;
   p.n_q = n_q; p.n_kv = n_kv; p.page_size = page_size;
-  return launch_gemm(p, d_w_tiles, x_map, static_cast<cudaStream_t>(stream));
+  return launch_gemm(p, d_w_tiles, x_map, static_cast<cudaStream_t>(stream), d_x_tiles);
 }
 
 int vb_rope_table(float* d_cs, const int32_t* d_pos, const float* d_freq, int T, int head_dim, void* stream) {

@@ -143,6 +143,7 @@ class LlamaEngine:
         self.normed_t = ops.TiledAct(self.FUSED_MAX_ROWS, H, dev)
         self.attn_t = ops.TiledAct(self.FUSED_MAX_ROWS, hq * D, dev)
         self.act_t = ops.TiledAct(self.FUSED_MAX_ROWS, I, dev)
+        self.hidden_t = ops.TiledAct(self.FUSED_MAX_ROWS, H, dev)
         self.max_out_rows = min(R, 64)     # logits are only ever needed for one row per request
         self.last_normed = torch.zeros(self.max_out_rows, H, dtype=BF16, device=dev)
         self.logits = torch.zeros(self.max_out_rows, d.vocab_size, dtype=BF16, device=dev)
@@ -228,16 +229,23 @@ class LlamaEngine:
         cs = ops.rope_table(position_ids[:R], self.freq, D, out=self.rope_cs[:R])
         ops.row_ssq(hidden, out=ssq[0])
         chain = self.chain_ok and self.use_chain
+        tiled = self.tiled_acts and not chain
+        hidden_t = self.hidden_t.view_rows(R) if tiled else None
+        attn_x_out = self.attn_t.view_rows(R) if tiled else attn          # what attention writes
+        attn_x = attn_x_out if tiled else attn.view(R, hq * D)           # ... as the O projection reads it
+        act_x = self.act_t.view_rows(R) if tiled else act
         if chain:
             self.chain_ws.zero()
         n_layers = len(w.layers)
         eps = d.rms_norm_eps
         for i, L in enumerate(w.layers):
             if i == 0 or not chain:
-                ops.proj_norm_qkv_rope_append(hidden, ssq, 1 if i == 0 else tiles_h, L["ln1"], eps, L["qkv"],
-                                              self.kv_cache[i], cs, plan, hq, hkv, D, self.fsplit_qkv, q_out=q)
+                # (layer 0 reads the embedding rows through the tensor map; later layers the tiled copy)
+                ops.proj_norm_qkv_rope_append(hidden if (i == 0 or not tiled) else hidden_t, ssq, 1 if i == 0 else tiles_h,
+                                              L["ln1"], eps, L["qkv"], self.kv_cache[i], cs, plan, hq, hkv, D,
+                                              self.fsplit_qkv, q_out=q)
             ops.paged_attn(q, self.kv_map, i * self.pages_per_layer, plan, R, hkv, self.page_size, self.chunk,
-                           self.attn_ws, out=attn, grid_ctas=self.attn_grid)
+                           self.attn_ws, out=attn if chain else attn_x_out, grid_ctas=self.attn_grid)
             if chain:
                 phases = [ops.chain_phase_residual(attn.view(R, hq * D), L["o"], hidden, hidden, ssq, self.fsplit_o),
                           ops.chain_phase_gateup(hidden, ssq, tiles_h, L["ln2"], eps, L["gu"], I, act),
@@ -248,9 +256,12 @@ class LlamaEngine:
                                                       q, self.fsplit_qkv))
                 ops.decode_chain(phases, R, cs, plan, hq, hkv, self.page_size, self.chain_ws, i)
             else:
-                ops.proj_residual(attn.view(R, hq * D), L["o"], hidden, self.fsplit_o, hidden_out=hidden, ssq_out=ssq)
-                ops.proj_norm_gateup_silu(hidden, ssq, tiles_h, L["ln2"], eps, L["gu"], self.gu_half, I, out=act)
-                ops.proj_residual(act, L["down"], hidden, self.fsplit_down, hidden_out=hidden, ssq_out=ssq)
+                ops.proj_residual(attn_x, L["o"], hidden, self.fsplit_o, hidden_out=hidden, ssq_out=ssq,
+                                  hidden_tiles_out=hidden_t)
+                ops.proj_norm_gateup_silu(hidden_t if tiled else hidden, ssq, tiles_h, L["ln2"], eps, L["gu"], self.gu_half,
+                                          I, out=act_x)
+                ops.proj_residual(act_x, L["down"], hidden, self.fsplit_down, hidden_out=hidden, ssq_out=ssq,
+                                  hidden_tiles_out=hidden_t)
 
     def _layers_unfused(self, position_ids: torch.Tensor, R: int, plan: ops.RowPlan):
         """8 launches per layer.  Decode-sized steps (R <= FUSED_MAX_ROWS) pass activations between kernels in the

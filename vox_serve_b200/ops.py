@@ -409,51 +409,67 @@ def proj_split_k(n_tiles: int, K: int, sms: Optional[int] = None) -> int:
     return max(1, min(8, sms // max(1, n_tiles), max(1, num_kb // 4)))
 
 
-def proj_residual(x: torch.Tensor, w: torch.Tensor, residual: Optional[torch.Tensor], split_k: int,
-                  hidden_out: Optional[torch.Tensor] = None, ssq_out: Optional[torch.Tensor] = None,
-                  tile_rows: int = 128):
-    """hidden_out [T, N] = bf16(residual + bf16(x w^T)); ssq_out fp32 [ceil(N/tile_rows), T] per-tile sums of squares
-    of the new rows.  T <= 64."""
+def _act_ptrs(x, t_tile: int):
+    """(x_map ptr or None, x_tiles ptr or None, T, K, device) of a row-major tensor or a TiledAct"""
+    if isinstance(x, TiledAct):
+        assert x.t_tile == t_tile
+        return None, x.data.data_ptr(), x.T, x.K, x.data.device
     _need_cuda(x)
+    assert x.dtype == BF16 and x.dim() == 2
+    return tensor_map_2d(x, t_tile).ptr, None, x.shape[0], x.shape[1], x.device
+
+
+def proj_residual(x, w, residual: Optional[torch.Tensor], split_k: int,
+                  hidden_out: Optional[torch.Tensor] = None, ssq_out: Optional[torch.Tensor] = None,
+                  tile_rows: int = 128, hidden_tiles_out: Optional["TiledAct"] = None):
+    """hidden_out [T, N] = bf16(residual + bf16(x w^T)); ssq_out fp32 [ceil(N/tile_rows), T] per-tile sums of squares
+    of the new rows; hidden_tiles_out: the same rows once more in the tiled layout (the next norm-fused projection's
+    input).  x: [T, K] tensor or TiledAct.  T <= 64."""
     pw = _packed(w, tile_rows)
-    T, K = x.shape
+    T = x.T if isinstance(x, TiledAct) else x.shape[0]
+    x_map, x_tiles, T, K, dev = _act_ptrs(x, fused_t_tile(T))
     N = pw.N
     tiles = (N + tile_rows - 1) // tile_rows
-    hidden_out = torch.empty(T, N, dtype=BF16, device=x.device) if hidden_out is None else hidden_out
-    ssq_out = torch.empty(tiles, T, dtype=torch.float32, device=x.device) if ssq_out is None else ssq_out
+    hidden_out = torch.empty(T, N, dtype=BF16, device=dev) if hidden_out is None else hidden_out
+    ssq_out = torch.empty(tiles, T, dtype=torch.float32, device=dev) if ssq_out is None else ssq_out
     assert ssq_out.numel() >= tiles * T and K == pw.K
-    x_map = tensor_map_2d(x, fused_t_tile(T))
-    call("vb_proj_residual", hidden_out.data_ptr(), ssq_out.data_ptr(), pw.data.data_ptr(), x_map.ptr, _p(residual), T, N, K,
-         split_k, tile_rows, _stream())
+    if hidden_tiles_out is not None:
+        assert hidden_tiles_out.T == T and hidden_tiles_out.K == N
+    call("vb_proj_residual", hidden_out.data_ptr(), hidden_tiles_out.data.data_ptr() if hidden_tiles_out is not None else None,
+         ssq_out.data_ptr(), pw.data.data_ptr(), x_map, x_tiles, _p(residual), T, N, K, split_k, tile_rows, _stream())
     return hidden_out, ssq_out
 
 
-def proj_norm_gateup_silu(hidden: torch.Tensor, ssq: torch.Tensor, n_parts: int, norm_w: torch.Tensor, eps: float,
-                          w_packed: torch.Tensor, h: int, n_out: int, out: Optional[torch.Tensor] = None):
-    """act [T, n_out] = silu(gate(xn)) * up(xn) with xn = rmsnorm(hidden) * norm_w formed inside the kernel."""
-    _need_cuda(hidden, ssq, norm_w)
+def proj_norm_gateup_silu(hidden, ssq: torch.Tensor, n_parts: int, norm_w: torch.Tensor, eps: float,
+                          w_packed, h: int, n_out: int, out=None):
+    """act [T, n_out] = silu(gate(xn)) * up(xn) with xn = rmsnorm(hidden) * norm_w formed inside the kernel.
+    hidden: [T, K] tensor or TiledAct; out: tensor, TiledAct or None."""
+    _need_cuda(ssq, norm_w)
     pw = _packed(w_packed, 2 * h)
-    T, K = hidden.shape
-    out = torch.empty(T, n_out, dtype=BF16, device=hidden.device) if out is None else out
-    x_map = tensor_map_2d(hidden, fused_t_tile(T))
-    call("vb_proj_norm_gateup_silu", out.data_ptr(), pw.data.data_ptr(), x_map.ptr, ssq.data_ptr(), n_parts,
-         norm_w.data_ptr(), float(eps), T, pw.N, K, 2 * h, n_out, _stream())
+    T = hidden.T if isinstance(hidden, TiledAct) else hidden.shape[0]
+    x_map, x_tiles, T, K, dev = _act_ptrs(hidden, fused_t_tile(T))
+    tiled_out = isinstance(out, TiledAct)
+    if out is None:
+        out = torch.empty(T, n_out, dtype=BF16, device=dev)
+    call("vb_proj_norm_gateup_silu", out.data.data_ptr() if tiled_out else out.data_ptr(), pw.data.data_ptr(), x_map, x_tiles,
+         ssq.data_ptr(), n_parts, norm_w.data_ptr(), float(eps), T, pw.N, K, 2 * h, n_out, 1 if tiled_out else 0, _stream())
     return out
 
 
-def proj_norm_qkv_rope_append(hidden: torch.Tensor, ssq: torch.Tensor, n_parts: int, norm_w: torch.Tensor, eps: float,
-                              w_qkv: torch.Tensor, layer_kv: torch.Tensor, rope_cs: torch.Tensor, plan: "RowPlan",
+def proj_norm_qkv_rope_append(hidden, ssq: torch.Tensor, n_parts: int, norm_w: torch.Tensor, eps: float,
+                              w_qkv, layer_kv: torch.Tensor, rope_cs: torch.Tensor, plan: "RowPlan",
                               n_q: int, n_kv: int, head_dim: int, split_k: int,
                               q_out: Optional[torch.Tensor] = None):
-    """q [T, n_q, D] (rotated) and the rotated k / v of every row written to its page slot; see vb_api.h."""
-    _need_cuda(hidden, ssq, norm_w, layer_kv, rope_cs)
+    """q [T, n_q, D] (rotated) and the rotated k / v of every row written to its page slot; see vb_api.h.
+    hidden: [T, K] tensor or TiledAct."""
+    _need_cuda(ssq, norm_w, layer_kv, rope_cs)
     pw = _packed(w_qkv, head_dim)
-    T, K = hidden.shape
+    T = hidden.T if isinstance(hidden, TiledAct) else hidden.shape[0]
+    x_map, x_tiles, T, K, dev = _act_ptrs(hidden, fused_t_tile(T))
     assert pw.N == (n_q + 2 * n_kv) * head_dim
-    q_out = torch.empty(T, n_q, head_dim, dtype=BF16, device=hidden.device) if q_out is None else q_out
-    x_map = tensor_map_2d(hidden, fused_t_tile(T))
+    q_out = torch.empty(T, n_q, head_dim, dtype=BF16, device=dev) if q_out is None else q_out
     page_size = layer_kv.shape[-3]
-    call("vb_proj_norm_qkv_rope_append", q_out.data_ptr(), layer_kv.data_ptr(), pw.data.data_ptr(), x_map.ptr,
+    call("vb_proj_norm_qkv_rope_append", q_out.data_ptr(), layer_kv.data_ptr(), pw.data.data_ptr(), x_map, x_tiles,
          ssq.data_ptr(), n_parts, norm_w.data_ptr(), float(eps), rope_cs.data_ptr(), plan.row_page.data_ptr(),
          plan.row_slot.data_ptr(), T, K, n_q, n_kv, head_dim, page_size, split_k, _stream())
     return q_out
