@@ -6,7 +6,7 @@ o=gpurun_out
 mkdir -p $o
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $o/${tag}_smi.txt 2>&1
 nproc >> $o/${tag}_smi.txt
-timeout 1200 python -m pytest tests -m gpu -x -q --timeout 600 -p no:cacheprovider > $o/${tag}_pytest.log 2>&1
+timeout 1800 python -m pytest tests -m gpu -x -q --timeout 900 -p no:cacheprovider > $o/${tag}_pytest.log 2>&1
 echo "pytest exit $?" >> $o/${tag}_pytest.log
 tail -5 $o/${tag}_pytest.log
 timeout 900 python bench.py --steps 700 --warmup 7 > $o/${tag}_bench.json 2> $o/${tag}_bench.err
