@@ -338,13 +338,10 @@ def run_gpu(args):
     drain(sched, reqs)
 
     # ------------------------------------------------ reduce over ranks ----------------------------------------
-    t = torch.tensor([res_ms, e2e_ms], dtype=torch.float64, device="cuda")
-    a = torch.tensor([res_audio_s, e2e_audio_s, float(res_launches), float(e2e_launches)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(a, op=dist.ReduceOp.SUM)
-    res_ms, e2e_ms = t.tolist()
-    res_audio_s, e2e_audio_s, res_launches, e2e_launches = a.tolist()
+    from vox_serve_b200.router import reduce_job_metrics
+
+    (res_ms, e2e_ms), (res_audio_s, e2e_audio_s, res_launches, e2e_launches) = reduce_job_metrics(
+        [res_ms, e2e_ms], [res_audio_s, e2e_audio_s, float(res_launches), float(e2e_launches)], device="cuda")
     if rank == 0:
         peak, peak_src = peaks()
         line = {
