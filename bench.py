@@ -424,8 +424,15 @@ def kernel_rooflines(worker, model, reqs, torch, ops):
         for i in range(d.num_hidden_layers):
             eng.attention_only(i, B, worker.decode_wrapper.plan_rows)
 
+    def gate_ups():
+        for L in eng.w.layers:
+            eng.gate_up_only(L, B)
+
     g1 = graph_of(gemms)
     gemm_ms = time_graph(g1)
+    g3 = graph_of(gate_ups)
+    gu_ms = time_graph(g3)
+    gu_bytes = d.num_hidden_layers * (2 * I * H * 2 + B * 2 * (H + I))
     g2 = graph_of(attns)
     attn_ms = time_graph(g2)
     w_bytes = eng.w.streamed_bytes_per_step()
@@ -436,7 +443,20 @@ def kernel_rooflines(worker, model, reqs, torch, ops):
     def fill(peak, peak_src):
         ga = gemm_bytes / (gemm_ms * 1e-3) / 1e9
         aa = attn_bytes / (attn_ms * 1e-3) / 1e9
+        gua = gu_bytes / (gu_ms * 1e-3) / 1e9
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                ncu = json.load(f)
+        except Exception:
+            ncu = {}
+        gu_traffic = ncu.get("gemm_gate_up", {}).get("dram_bytes_per_launch")
         return {
+            "roofline_gate_up": {"kernel": "gemm_bf16_kernel, gate/up projection launches only (28 per step, the largest "
+                                           "projection: 100.7 MB of weights each)", "bound": "hbm", "achieved": gua,
+                                 "peak": peak, "unit": "GB/s", "frac": gua / peak, "traffic": gu_traffic,
+                                 "traffic_source": ncu.get("gemm_gate_up", {}).get("source"),
+                                 "avg_launch_us": gu_ms * 1e3 / d.num_hidden_layers,
+                                 "algorithmic_bytes_per_launch": int(gu_bytes / d.num_hidden_layers)},
             "roofline": {"kernel": "gemm_bf16_kernel (all projection launches of one decode step)", "bound": "hbm",
                          "achieved": ga, "peak": peak, "unit": "GB/s", "frac": ga / peak, "traffic": None,
                          "peak_source": peak_src, "launches_per_step": n_gemm[0],

@@ -326,6 +326,14 @@ class LlamaEngine:
             ops.proj_residual(act, L["down"], hidden, self.fsplit_down, hidden_out=hidden, ssq_out=ssq)
         ops.gemm(self.normed[:min(R, self.max_out_rows)], w.lm_head, mode=0, out=self.logits[:min(R, self.max_out_rows)])
 
+    def gate_up_only(self, L: Dict[str, object], n_rows: int) -> None:
+        """One gate/up projection launch (production decode mode) on the live buffers: bench.py's per-launch roofline."""
+        d, R = self.dims, n_rows
+        tiled = R <= self.FUSED_MAX_ROWS and self.tiled_acts
+        normed = self.normed_t.view_rows(R) if tiled else self.normed[:R]
+        act = self.act_t.view_rows(R) if tiled else self.act[:R]
+        ops.gemm(normed, L["gu"], mode=2, out=act, tile_rows=2 * self.gu_half, n_out=d.intermediate_size)
+
     def attention_only(self, layer: int, n_rows: int, plan: ops.RowPlan) -> None:
         """The paged-attention launch of one layer on the live cache and the plan of the last step."""
         d = self.dims
