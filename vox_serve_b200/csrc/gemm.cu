@@ -610,7 +610,15 @@ static int launch_gemm(GemmParams& p, const void* w_tiles, const void* x_map, cu
   const int extra = 1024 /*barriers, ssq*/ + (p.norm ? (p.K * 2 + 1023) / 1024 * 1024 : 0) + 1024 /*alignment slack*/;
   // after the main loop the ring holds the partial tile (t_tile x 128 fp32) and the 128 x 17 exchange buffer
   const int min_ring = p.t_tile * 512 + 128 * 17 * 4;
-  int stages = (gemm_smem_budget() - extra) / stage_bytes;
+  int budget = gemm_smem_budget();
+  if (p.mode == GM_SILU && !p.norm) {
+    // the gate/up stream is the long one (48 stages per CTA) and it follows a small kernel: a 10-stage ring on the
+    // whole SM beats co-residency here (forward 2.68 -> 2.64 ms; VB_GEMM_SMEM_KB_GU overrides)
+    static int gu_kb = -1;
+    if (gu_kb < 0) { const char* e = getenv("VB_GEMM_SMEM_KB_GU"); gu_kb = e ? atoi(e) : 200; }
+    if (gu_kb >= 48 && gu_kb <= 220) budget = gu_kb * 1024;
+  }
+  int stages = (budget - extra) / stage_bytes;
   if (stages > 12) stages = 12;
   if (stages > num_kb) stages = num_kb;
   if (stages < 2) stages = 2;
