@@ -227,6 +227,9 @@ def run_gpu(args):
     pages = max(2048, BATCH * ((max_tokens + 127) // 128 + 1))
     worker = ModelWorker("orpheus-synthetic", max_batch_size=BATCH, max_num_pages=pages, page_size=128, model=model,
                          max_prefill_tokens=1024)
+    t_cap0 = time.perf_counter()
+    n_graphs = worker.capture_decode_graphs()         # start-up work, like the reference's graph initialisation
+    capture_s = time.perf_counter() - t_cap0
     g = torch.Generator().manual_seed(42 + rank)
 
     def barrier():
@@ -337,6 +340,24 @@ def run_gpu(args):
     roof = kernel_rooflines(worker, model, reqs, torch, ops)
     drain(sched, reqs)
 
+    # ------------------------------------------------ TTFA of a lone request on the warm server ----------------
+    ttfa_single = []
+    for i in range(5):
+        s1 = Scheduler(worker)
+        ids = torch.randint(0, 128000, (PROMPT_TOKENS,), generator=g).tolist()
+        r1 = Request(request_id=f"t{i}", prompt=ids, model_kwargs={"voice": None})
+        torch.cuda.synchronize()
+        s1.submit(r1)
+        n = 0
+        while not s1.audio[r1.request_id]:
+            s1._step()
+            n += 1
+            assert n < 200
+        ttfa_single.append((s1.first_audio_time[r1.request_id] - s1.submit_time[r1.request_id]) * 1e3)
+        worker.free_kv_cache(r1)
+        s1.active_requests = []
+    ttfa_single.sort()
+
     # ------------------------------------------------ reduce over ranks ----------------------------------------
     from vox_serve_b200.router import reduce_job_metrics
 
@@ -363,8 +384,11 @@ def run_gpu(args):
             "tokens_per_s": BATCH * world * K / (res_ms / 1e3),
             "ttfa_burst_ms": {"p50": ttfa[len(ttfa) // 2], "min": ttfa[0], "max": ttfa[-1],
                               "note": "32 requests submitted at once, one prefill per step (scheduler/base.py:283-284);"
-                                      " includes first-use CUDA-graph captures"},
-            "setup_s": setup_s, "clocks": clk,
+                                      " decode graphs captured at start-up"},
+            "ttfa_single_ms": {"p50": ttfa_single[len(ttfa_single) // 2], "min": ttfa_single[0], "max": ttfa_single[-1],
+                               "note": "one 133-token request on an otherwise idle, warm replica: prefill + the 28 decode "
+                                       "steps the first SNAC window needs + vocoder + PCM copy"},
+            "setup_s": setup_s, "graph_capture_s": capture_s, "decode_graphs": n_graphs, "clocks": clk,
         }
         line.update(roof(peak, peak_src))
         if world == 1 and not args.no_cpu:
