@@ -185,6 +185,15 @@ __device__ __forceinline__ float smp_sum_f32(float v, SmpCtx& c) {
   return r;
 }
 
+// The kernel is instruction-bound (the whole row is on chip): the softmax uses the hardware exponential
+// (ex2.approx, 2 ulp) -- a sampler's masses do not need expf's last bit.
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float smp_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(SMP_THREADS, 1) sample_kernel(const SampleParams p, const int npairs) {
   extern __shared__ uint32_t q_sm[];                 // [2 * npairs][1024] masses (Q32)
   __shared__ unsigned long long xch[2][SMP_MAX_CLUSTER];
@@ -257,14 +266,15 @@ __global__ void __launch_bounds__(SMP_THREADS, 1) sample_kernel(const SamplePara
 #pragma unroll
   for (int j = 0; j < SMP_PAIRS; ++j) {
     const uint32_t a = kk[j] & 0xffffu, b = kk[j] >> 16;
-    if (a != 0u && a >= z_floor) zpart += expf(key_value(a) - xmax);
-    if (b != 0u && b >= z_floor) zpart += expf(key_value(b) - xmax);
+    if (a != 0u && a >= z_floor) zpart += smp_ex2((key_value(a) - xmax) * kLog2e);
+    if (b != 0u && b >= z_floor) zpart += smp_ex2((key_value(b) - xmax) * kLog2e);
   }
   const float Z = smp_sum_f32(zpart, c);
+  const float log2Z = log2f(Z);
 
   // ---- masses: bf16-rounded softmax output as Q32 fixed point; filtered tokens get 0 ----
   const uint32_t keep_floor = (p.strategy == 1 || p.strategy == 3) ? k_floor : 0u;
-  const float minp_thr = (p.strategy == 4) ? p.min_p * round_bf16(1.0f / Z) : 0.f;
+  const float minp_thr = (p.strategy == 4) ? p.min_p * round_bf16(smp_ex2(-log2Z)) : 0.f;
   unsigned long long msum = 0ull;
 #pragma unroll
   for (int j = 0; j < SMP_PAIRS; ++j) {
@@ -274,7 +284,8 @@ __global__ void __launch_bounds__(SMP_THREADS, 1) sample_kernel(const SamplePara
         const uint32_t k = h ? (kk[j] >> 16) : (kk[j] & 0xffffu);
         uint32_t q = 0u;
         if (k != 0u && k >= z_floor && k >= keep_floor) {
-          const float pr = round_bf16(expf(key_value(k) - xmax) / Z);
+          // softmax output e^(x - max) / Z as ONE exponential: 2^((x - max) log2 e - log2 Z)
+          const float pr = round_bf16(smp_ex2((key_value(k) - xmax) * kLog2e - log2Z));
           if (pr >= minp_thr) q = __float2uint_rz(pr * 4294967296.f);   // saturates at 2^32 - 1
         }
         q_sm[(2 * j + h) * SMP_THREADS + tid] = q;
