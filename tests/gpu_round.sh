@@ -9,6 +9,8 @@ nproc >> $o/${tag}_smi.txt
 timeout 1800 python -m pytest tests -m gpu -x -q --timeout 900 -p no:cacheprovider > $o/${tag}_pytest.log 2>&1
 echo "pytest exit $?" >> $o/${tag}_pytest.log
 tail -5 $o/${tag}_pytest.log
+timeout 600 python __graft_entry__.py smoke > $o/${tag}_smoke.log 2>&1
+echo "smoke exit $?"; tail -2 $o/${tag}_smoke.log
 timeout 900 python bench.py --steps 700 --warmup 7 > $o/${tag}_bench.json 2> $o/${tag}_bench.err
 echo "bench exit $?"; tail -3 $o/${tag}_bench.err; cat $o/${tag}_bench.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \

@@ -224,13 +224,20 @@ __global__ void __launch_bounds__(RR_THREADS) reduce_residual_rmsnorm_kernel(
     __nv_bfloat16* __restrict__ hidden_out, __nv_bfloat16* __restrict__ normed_out,
     const float* __restrict__ partials, int split_k, const __nv_bfloat16* __restrict__ residual,
     const __nv_bfloat16* __restrict__ norm_w, int T, int N, float eps, int xt_tile) {
-  pdl_sync();
   __shared__ float red[32];
-  __shared__ float part_ss;
+  __shared__ float part_ss[8];        // one slot per CTA of the cluster, written by the peers
   const int parts = gridDim.x, part = blockIdx.x;
   const size_t t = blockIdx.y;
   const int cols = N / parts, c0 = part * cols;
   const size_t plane = static_cast<size_t>(T) * N;
+  // the norm weights are parameters: fetched before the dependency resolves
+  uint2 w2[RR_MAX_ITER];
+#pragma unroll
+  for (int it = 0; it < RR_MAX_ITER; ++it) {
+    const int n = c0 + (it * RR_THREADS + threadIdx.x) * 4;
+    w2[it] = (normed_out && n < c0 + cols) ? __ldg(reinterpret_cast<const uint2*>(norm_w + n)) : make_uint2(0u, 0u);
+  }
+  pdl_sync();
   float h[RR_MAX_ITER][4];
   float ss = 0.f;
 #pragma unroll
@@ -265,23 +272,27 @@ __global__ void __launch_bounds__(RR_THREADS) reduce_residual_rmsnorm_kernel(
   }
   if (!normed_out) return;      // uniform across the cluster: no barrier is pending
   ss = block_sum(ss, red);
-  if (threadIdx.x == 0) part_ss = ss;
   float total = ss;
   if (parts > 1) {
-    cluster_sync_all();          // every CTA's part_ss is written
+    // push this CTA's sum into slot `part` of every peer, one barrier, then every CTA adds its own eight slots in
+    // the same order: nobody reads remote memory after the barrier, so nobody has to wait before exiting
+    if (threadIdx.x < parts) {
+      uint32_t laddr = static_cast<uint32_t>(__cvta_generic_to_shared(&part_ss[part])), raddr;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(threadIdx.x));
+      asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(ss) : "memory");
+    }
+    cluster_sync_all();
     total = 0.f;
-    for (int r = 0; r < parts; ++r) total += ld_dsmem_f32(&part_ss, r);   // same order in every CTA
-    cluster_sync_all();          // nobody exits while its shared memory may still be read
+    for (int r = 0; r < parts; ++r) total += part_ss[r];
   }
   const float rcp = rsqrtf(total / static_cast<float>(N) + eps);
 #pragma unroll
   for (int it = 0; it < RR_MAX_ITER; ++it) {
     const int n = c0 + (it * RR_THREADS + threadIdx.x) * 4;
     if (n < c0 + cols) {
-      const uint2 w2 = *reinterpret_cast<const uint2*>(norm_w + n);
       uint2 o;
-      o.x = pack_bf16(h[it][0] * rcp * bf16_lo(w2.x), h[it][1] * rcp * bf16_hi(w2.x));
-      o.y = pack_bf16(h[it][2] * rcp * bf16_lo(w2.y), h[it][3] * rcp * bf16_hi(w2.y));
+      o.x = pack_bf16(h[it][0] * rcp * bf16_lo(w2[it].x), h[it][1] * rcp * bf16_hi(w2[it].x));
+      o.y = pack_bf16(h[it][2] * rcp * bf16_lo(w2[it].y), h[it][3] * rcp * bf16_hi(w2[it].y));
       const size_t oi = xt_tile ? xt_index(static_cast<int>(t), n, xt_tile, (N + 63) >> 6) : t * N + n;
       *reinterpret_cast<uint2*>(normed_out + oi) = o;
     }
