@@ -298,6 +298,21 @@ int vb_snac_pwconv(float* d_y, const float* d_x, const float* d_w /*[Cout][Cin]*
 int vb_snac_convtr(float* d_y, const float* d_x, const float* d_w_packed, const float* d_bias,
                    const float* d_alpha_out, int B, int Cin, int Cout, int T, int stride, int o_lo, int o_hi,
                    void* stream);
+/* Tensor-core variants of the two GEMM-shaped stages (tcgen05 kind::tf32, every fp32 operand split hi + lo and
+ * the product summed as lo*hi + hi*lo + hi*hi into fp32 TMEM accumulators: relative error ~2^-21 per product, fp32
+ * storage everywhere).  Same arguments and results as vb_snac_pwconv / vb_snac_convtr except that the weights come
+ * packed by vb_snac_pack_tf32x3: d_w [phases][M][K] fp32 (pointwise: phases = 1, M = Cout, K = Cin; transposed:
+ * the [stride][Cout][2*Cin] array of vb_snac_convtr) -> [phase][m_tile][k_block][hi|lo][128][32] fp32, rows of 128
+ * bytes with the 128-byte UMMA swizzle.  K (Cin) must be a multiple of 32; the caller keeps the SIMT entry points
+ * for narrower layers.  vb_snac_tf32x3_bytes returns the packed size (-1 for an unsupported shape). */
+long long vb_snac_tf32x3_bytes(int phases, int M, int K);
+int vb_snac_pack_tf32x3(void* d_dst, const float* d_w, int phases, int M, int K, void* stream);
+int vb_snac_pwconv_tc(float* d_y, const float* d_x, const void* d_w_tiles, const float* d_bias, const float* d_resid,
+                      const float* d_noise, const float* d_alpha_out, int epilogue, int B, int Cin, int Cout, int T,
+                      int t_lo, int t_hi, void* stream);
+int vb_snac_convtr_tc(float* d_y, const float* d_x, const void* d_w_tiles, const float* d_bias,
+                      const float* d_alpha_out, int B, int Cin, int Cout, int T, int stride, int o_lo, int o_hi,
+                      void* stream);
 /* y[b][t - t0] = tanh(conv_k7(snake_in?(x))[t] + bias), Cout = 1 (snac.py:152-156), t in [t0, t1) */
 int vb_snac_final(float* d_y, const float* d_x, const float* d_w /*[C][7]*/, const float* d_bias,
                   const float* d_alpha_in, int B, int C, int T, int t0, int t1, void* stream);

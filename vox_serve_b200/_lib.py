@@ -72,6 +72,10 @@ SIGNATURES = {
     "vb_snac_pwconv": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_snac_convtr": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_snac_final": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_snac_tf32x3_bytes": (c_int64, [c_int, c_int, c_int]),
+    "vb_snac_pack_tf32x3": (c_int, [P, P, c_int, c_int, c_int, P]),
+    "vb_snac_pwconv_tc": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_snac_convtr_tc": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_pcm16": (c_int, [P, P, c_int64, P]),
     "vb_orpheus_window_codes": (c_int, [P, P, P, P, c_int, c_int, P]),
 }

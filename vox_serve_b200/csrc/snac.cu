@@ -82,120 +82,141 @@ __global__ void __launch_bounds__(DW_TILE) dwconv7_kernel(float* __restrict__ y,
 }
 
 // ------------------------------------------------------------------------------------------
-// register-tiled fp32 GEMM  C[M][N] = A[M][K] * B[K][N], per batch item, with functor-defined B fetch
-// and C store.  64x64 tile, BK = 16, 256 threads, 4x4 outputs per thread.
+// register-tiled fp32 GEMM  C[M][N] = A[M][K] * B[K][N] with functor-defined B fetch and C store.  The N axis
+// is the batch FOLDED with the position range: column g = b * nr + (n - n_lo), so the early decoder stages
+// (a dozen positions per window) still fill whole tiles and every weight tile is read once per 64 columns of
+// the whole batch rather than once per window.  Tile (16*TM) x 64, BK = 16, 256 threads, TM x 4 outputs per
+// thread (TM = 8: rows ty*4.. and 64+ty*4..), next tile prefetched into registers while the current one is
+// multiplied.  Each output is still one sequential FMA chain over k, so results do not depend on the tiling.
 // ------------------------------------------------------------------------------------------
-constexpr int GB_M = 64, GB_N = 64, GB_K = 16;
+constexpr int GB_N = 64, GB_K = 16;
 
-template <class BLoad, class CStore>
-__device__ __forceinline__ void gemm_tile_f32(const float* __restrict__ A, int M, int K, int lda, int n_lo, int n_hi,
-                                              BLoad bload, CStore cstore) {
-  __shared__ float As[GB_K][GB_M + 4];
+template <int TM, class BLoad, class CStore>
+__device__ __forceinline__ void gemm_tile_f32(const float* __restrict__ A, int M, int K, int lda, int n_lo, int nr,
+                                              int n_total, BLoad bload, CStore cstore) {
+  constexpr int TILE_M = 16 * TM, AV = TM / 4;       // AV float4 of A per thread per k-step
+  __shared__ float As[GB_K][TILE_M + 4];
   __shared__ float Bs[GB_K][GB_N + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.y * GB_M, n0 = n_lo + blockIdx.x * GB_N;
-  float acc[4][4];
+  const int m0 = blockIdx.y * TILE_M, g0 = blockIdx.x * GB_N;
+  // this thread's 4 columns (the same 4 for the B fetch and the C store)
+  int cb[4], cn[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int j = 0; j < 4; ++j) {
+    const int g = g0 + tx * 4 + j;
+    cb[j] = g < n_total ? g / nr : -1;
+    cn[j] = n_lo + g - max(cb[j], 0) * nr;
+  }
+  const int am = tid >> 2, akq = (tid & 3) * 4, bk = tid >> 4;
+  float4 pa[AV];
+  float pb[4];
+  auto fetch = [&](int k0) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += GB_K) {
-    // A tile: 64 x 16, K contiguous in memory -> 4 floats per thread
-    {
-      const int m = tid >> 2, kq = (tid & 3) * 4;
+    for (int h = 0; h < AV; ++h) {
+      const int m = m0 + am + 64 * h;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m0 + m < M) {
-        const float* src = A + static_cast<size_t>(m0 + m) * lda + k0 + kq;
-        if (k0 + kq + 3 < K) v = *reinterpret_cast<const float4*>(src);
+      if (m < M) {
+        const float* src = A + static_cast<size_t>(m) * lda + k0 + akq;
+        if (k0 + akq + 3 < K) v = __ldg(reinterpret_cast<const float4*>(src));
         else {
-          if (k0 + kq + 0 < K) v.x = src[0];
-          if (k0 + kq + 1 < K) v.y = src[1];
-          if (k0 + kq + 2 < K) v.z = src[2];
+          if (k0 + akq + 0 < K) v.x = src[0];
+          if (k0 + akq + 1 < K) v.y = src[1];
+          if (k0 + akq + 2 < K) v.z = src[2];
         }
       }
-      As[kq + 0][m] = v.x; As[kq + 1][m] = v.y; As[kq + 2][m] = v.z; As[kq + 3][m] = v.w;
+      pa[h] = v;
     }
-    // B tile: 16 x 64, N contiguous
-    {
-      const int k = tid >> 4, nq = (tid & 15) * 4;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int n = n0 + nq + j;
-        Bs[k][nq + j] = (k0 + k < K && n < n_hi) ? bload(k0 + k, n) : 0.f;
+    for (int j = 0; j < 4; ++j) pb[j] = (k0 + bk < K && cb[j] >= 0) ? bload(k0 + bk, cb[j], cn[j]) : 0.f;
+  };
+  float acc[TM][4];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += GB_K) {
+#pragma unroll
+    for (int h = 0; h < AV; ++h) {
+      As[akq + 0][am + 64 * h] = pa[h].x; As[akq + 1][am + 64 * h] = pa[h].y;
+      As[akq + 2][am + 64 * h] = pa[h].z; As[akq + 3][am + 64 * h] = pa[h].w;
+    }
+    *reinterpret_cast<float4*>(&Bs[bk][tx * 4]) = make_float4(pb[0], pb[1], pb[2], pb[3]);
+    __syncthreads();
+    if (k0 + GB_K < K) fetch(k0 + GB_K);
+#pragma unroll
+    for (int k = 0; k < GB_K; ++k) {
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int h = 0; h < AV; ++h) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4 + 64 * h]);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[h * 4 + i][j] += av[i] * bv[j];
       }
     }
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < GB_K; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
-    }
-    __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
-    if (m >= M) continue;
+  for (int h = 0; h < AV; ++h)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
-      if (n < n_hi) cstore(m, n, acc[i][j]);
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + 64 * h + i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (m < M && cb[j] >= 0) cstore(m, cb[j], cn[j], acc[h * 4 + i][j]);
     }
-  }
 }
 
 // pointwise conv; epilogue 0 plain, 1 + resid, 2 noise block (x + noise * Wx); optional Snake after
+template <int TM>
 __global__ void __launch_bounds__(256) pwconv_kernel(float* __restrict__ y, const float* __restrict__ x,
                                                      const float* __restrict__ w, const float* __restrict__ bias,
                                                      const float* __restrict__ resid, const float* __restrict__ noise,
-                                                     const float* __restrict__ alpha_out, int epi, int Cin, int Cout,
-                                                     int T, int t_lo, int t_hi) {
-  const int b = blockIdx.z;
-  const float* xb = x + static_cast<size_t>(b) * Cin * T;
-  float* yb = y + static_cast<size_t>(b) * Cout * T;
-  const float* rb = resid ? resid + static_cast<size_t>(b) * Cout * T : nullptr;
-  const float* nb = noise ? noise + static_cast<size_t>(b) * T : nullptr;
-  gemm_tile_f32(
-      w, Cout, Cin, Cin, t_lo, t_hi, [&](int k, int n) { return xb[static_cast<size_t>(k) * T + n]; },
-      [&](int m, int n, float v) {
+                                                     const float* __restrict__ alpha_out, int epi, int B, int Cin,
+                                                     int Cout, int T, int t_lo, int t_hi) {
+  const size_t xs = static_cast<size_t>(Cin) * T, ys = static_cast<size_t>(Cout) * T;
+  gemm_tile_f32<TM>(
+      w, Cout, Cin, Cin, t_lo, t_hi - t_lo, B * (t_hi - t_lo),
+      [=](int k, int b, int n) { return x[b * xs + static_cast<size_t>(k) * T + n]; },
+      [=](int m, int b, int n, float v) {
+        const size_t o = b * ys + static_cast<size_t>(m) * T + n;
         if (bias) v += bias[m];
-        if (epi == 1) v += rb[static_cast<size_t>(m) * T + n];
-        else if (epi == 2) v = xb[static_cast<size_t>(m) * T + n] + nb[n] * v;
+        if (epi == 1) v += resid[o];
+        else if (epi == 2) v = x[o] + noise[static_cast<size_t>(b) * T + n] * v;
         if (alpha_out) v = snake_f(v, alpha_out[m]);
-        yb[static_cast<size_t>(m) * T + n] = v;
+        y[o] = v;
       });
 }
 
 // transposed conv, kernel 2s, stride s, padding ceil(s/2), output_padding s%2 (snac.py:222-231).
 // wp: host-repacked [s][Cout][2*Cin]: wp[r][co][tap*Cin + ci] = W[ci][co][r + tap*s].
-// For phase r = blockIdx.z % s the GEMM N index is q = ti (input position); output to = ti*s + r - pad.
+// For phase r = blockIdx.z the GEMM column is the input position ti; output to = ti*s + r - pad.
+template <int TM>
 __global__ void __launch_bounds__(256) convtr_kernel(float* __restrict__ y, const float* __restrict__ x,
                                                      const float* __restrict__ wp, const float* __restrict__ bias,
-                                                     const float* __restrict__ alpha_out, int Cin, int Cout, int T,
-                                                     int s, int pad, int n_lo, int n_hi) {
-  const int r = blockIdx.z % s, b = blockIdx.z / s;
+                                                     const float* __restrict__ alpha_out, int B, int Cin, int Cout,
+                                                     int T, int s, int pad, int n_lo, int n_hi) {
+  const int r = blockIdx.z;
   const int Tout = T * s;
-  const float* xb = x + static_cast<size_t>(b) * Cin * T;
-  float* yb = y + static_cast<size_t>(b) * Cout * Tout;
+  const size_t xs = static_cast<size_t>(Cin) * T, ys = static_cast<size_t>(Cout) * Tout;
   const float* wr = wp + static_cast<size_t>(r) * Cout * 2 * Cin;
   // ti ranges over [0, T]: ti = T only receives the tap-1 term (x[T-1])
-  gemm_tile_f32(
-      wr, Cout, 2 * Cin, 2 * Cin, n_lo, n_hi,
-      [&](int k, int n) {
+  gemm_tile_f32<TM>(
+      wr, Cout, 2 * Cin, 2 * Cin, n_lo, n_hi - n_lo, B * (n_hi - n_lo),
+      [=](int k, int b, int n) {
         const int tap = k >= Cin, ci = k - tap * Cin, ti = n - tap;
-        return (ti >= 0 && ti < T) ? xb[static_cast<size_t>(ci) * T + ti] : 0.f;
+        return (ti >= 0 && ti < T) ? x[b * xs + static_cast<size_t>(ci) * T + ti] : 0.f;
       },
-      [&](int m, int n, float v) {
+      [=](int m, int b, int n, float v) {
         const int to = n * s + r - pad;
         if (to < 0 || to >= Tout) return;
         if (bias) v += bias[m];
         if (alpha_out) v = snake_f(v, alpha_out[m]);
-        yb[static_cast<size_t>(m) * Tout + to] = v;
+        y[b * ys + static_cast<size_t>(m) * Tout + to] = v;
       });
 }
 
@@ -232,6 +253,20 @@ __global__ void __launch_bounds__(256) final_conv_kernel(float* __restrict__ y, 
 }  // namespace vb
 
 using namespace vb;
+
+static int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      sms = 148;
+  }
+  return sms;
+}
+static bool gemm_wide_tiles(int nx, int M, int nz) {
+  if (M < 128) return false;
+  return static_cast<long long>(nx) * ((M + 127) / 128) * nz >= 2LL * device_sm_count();
+}
 
 extern "C" {
 
@@ -273,9 +308,15 @@ int vb_snac_pwconv(float* d_y, const float* d_x, const float* d_w, const float* 
   VB_CHECK_ARG(Cin % 4 == 0, "vb_snac_pwconv: Cin must be a multiple of 4");
   VB_CHECK_ARG(0 <= t_lo && t_lo <= t_hi && t_hi <= T, "vb_snac_pwconv: range [%d, %d) outside [0, %d)", t_lo, t_hi, T);
   if (B <= 0 || t_lo == t_hi) return 0;
-  pwconv_kernel<<<dim3((t_hi - t_lo + GB_N - 1) / GB_N, (Cout + GB_M - 1) / GB_M, B), 256, 0,
-                  static_cast<cudaStream_t>(stream)>>>(d_y, d_x, d_w, d_bias, d_resid, d_noise, d_alpha_out, epilogue,
-                                                       Cin, Cout, T, t_lo, t_hi);
+  const int cols = B * (t_hi - t_lo), nx = (cols + GB_N - 1) / GB_N;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // 128-row tiles when they still give every SM two CTAs, else 64-row tiles
+  if (gemm_wide_tiles(nx, Cout, 1))
+    pwconv_kernel<8><<<dim3(nx, (Cout + 127) / 128, 1), 256, 0, st>>>(d_y, d_x, d_w, d_bias, d_resid, d_noise,
+                                                                      d_alpha_out, epilogue, B, Cin, Cout, T, t_lo, t_hi);
+  else
+    pwconv_kernel<4><<<dim3(nx, (Cout + 63) / 64, 1), 256, 0, st>>>(d_y, d_x, d_w, d_bias, d_resid, d_noise,
+                                                                    d_alpha_out, epilogue, B, Cin, Cout, T, t_lo, t_hi);
   VB_CHECK_LAUNCH();
   return 0;
 }
@@ -294,9 +335,14 @@ int vb_snac_convtr(float* d_y, const float* d_x, const float* d_w_packed, const 
   if (o_lo + pad - (stride - 1) < 0) n_lo = 0;
   int n_hi = (o_hi - 1 + pad) / stride + 1;
   if (n_hi > T + 1) n_hi = T + 1;
-  convtr_kernel<<<dim3((n_hi - n_lo + GB_N - 1) / GB_N, (Cout + GB_M - 1) / GB_M, B * stride), 256, 0,
-                  static_cast<cudaStream_t>(stream)>>>(d_y, d_x, d_w_packed, d_bias, d_alpha_out, Cin, Cout, T, stride,
-                                                       pad, n_lo, n_hi);
+  const int cols = B * (n_hi - n_lo), nx = (cols + GB_N - 1) / GB_N;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (gemm_wide_tiles(nx, Cout, stride))
+    convtr_kernel<8><<<dim3(nx, (Cout + 127) / 128, stride), 256, 0, st>>>(d_y, d_x, d_w_packed, d_bias, d_alpha_out,
+                                                                           B, Cin, Cout, T, stride, pad, n_lo, n_hi);
+  else
+    convtr_kernel<4><<<dim3(nx, (Cout + 63) / 64, stride), 256, 0, st>>>(d_y, d_x, d_w_packed, d_bias, d_alpha_out, B,
+                                                                         Cin, Cout, T, stride, pad, n_lo, n_hi);
   VB_CHECK_LAUNCH();
   return 0;
 }

@@ -1,0 +1,335 @@
+// SNAC decoder, the two GEMM-shaped stages (1x1 convs, phase-decomposed transposed convs; snac.py:170-231) on the
+// tcgen05 tensor cores with fp32-grade results: every fp32 operand is split into a tf32-exact high part and the
+// remainder (x = hi + lo, hi = x with the 13 low mantissa bits cleared), and the product is accumulated as
+//   lo_w * hi_x + hi_w * lo_x + hi_w * hi_x        (kind::tf32, fp32 accumulators in TMEM)
+// which leaves a relative error of ~2^-21 per product -- the waveform stays inside the 1e-3 the contract allows by
+// three orders of magnitude (the parity test holds it to 2e-4 absolute against the fp32 oracle).
+//
+//   D[m][col] = sum_k W[m][k] * X[k][col],  m = output channel, col = (window b, position n) FOLDED, so a dozen
+//   positions per window still fill 128-column tiles and a weight tile is fetched once per 128 columns of the batch.
+//
+// A (weights): packed once at load by vb_snac_pack_tf32x3 as [phase][m_tile][k_block][hi|lo][128 rows][32 fp32],
+//   K-major rows of 128 bytes with the 128-byte UMMA swizzle applied -> one contiguous 32 KiB bulk copy per stage.
+// B (activations [B][C][T], T contiguous): eight loader warps read 32 channels x 128 columns per stage with
+//   coalesced loads (a warp = 32 consecutive positions of one channel), split hi / lo in registers and store both
+//   tiles K-major + swizzled; two groups of four warps alternate stages so one group's L2 round trip hides behind
+//   the other's stores.  For the transposed conv the second half of K reads the same rows shifted by one position.
+// One MMA thread issues 12 x (128 x 128 x 8) per stage.  Epilogue: TMEM -> registers -> per-warp shared-memory
+// transpose -> lanes along the position axis, so bias / residual / noise / Snake and the store are coalesced.
+#include "../../include/vb_api.h"
+#include "common.cuh"
+
+namespace vb {
+
+constexpr int SM_THREADS = 320;          // warp 0 weight producer, warp 1 MMA issuer, warps 2..9 loaders + epilogue
+constexpr int SM_BLOCK_K = 32;           // fp32 elements per 128-byte row
+constexpr int SM_TILE_N = 128;           // columns per CTA (UMMA N)
+constexpr int SM_A_BYTES = 2 * 128 * 128;        // hi + lo weight tiles
+constexpr int SM_B_BYTES = 2 * SM_TILE_N * 128;  // hi + lo activation tiles
+constexpr int SM_STAGE = SM_A_BYTES + SM_B_BYTES;
+constexpr int SM_STAGES = 3;
+constexpr int SM_SMEM = SM_STAGES * SM_STAGE + 1024 /*barriers*/ + 1024 /*alignment*/;
+
+struct SnacGemmParams {
+  const uint8_t* w_tiles;
+  const float* x;
+  float* y;
+  const float* bias;
+  const float* resid;
+  const float* noise;
+  const float* alpha_out;
+  int kind;      // 0 pointwise conv, 1 transposed conv (grid.z = phase)
+  int epi;       // pointwise: 0 plain, 1 + resid, 2 noise block
+  int B, Cin, Cout, T, K;
+  int n_lo, nr, n_total;
+  int s, pad;
+};
+
+__device__ __forceinline__ float snake_tc(float x, float alpha) {
+  const float s = sinf(alpha * x);
+  return x + (1.0f / (alpha + 1e-9f)) * s * s;
+}
+
+__device__ __forceinline__ void snac_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(SM_THREADS, 1) snac_gemm_tf32x3_kernel(const SnacGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM_STAGES * SM_STAGE);   // weights landed + B tile written
+  uint64_t* empty = full + SM_STAGES;                                           // the MMAs have read the stage
+  uint64_t* tmem_full = empty + SM_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = blockIdx.x * SM_TILE_N, m_tile = blockIdx.y, phase = blockIdx.z;
+  const int num_kb = p.K / SM_BLOCK_K;
+  const int m_tiles = (p.Cout + 127) >> 7;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < SM_STAGES; ++s) {
+      mbar_init(&full[s], 1 + 4);      // the producer's expect_tx arrival + one arrival per loader warp of a group
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, SM_TILE_N);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= weight producer: one 32 KiB bulk copy per stage =================
+    if (lane == 0) {
+      const uint8_t* wsrc = p.w_tiles + (static_cast<size_t>(phase) * m_tiles + m_tile) * num_kb * SM_A_BYTES;
+      for (int it = 0; it < num_kb; ++it) {
+        const int s = it % SM_STAGES;
+        if (it >= SM_STAGES) mbar_wait(&empty[s], ((it / SM_STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[s], SM_A_BYTES);
+        snac_bulk_g2s(smem + s * SM_STAGE, wsrc + static_cast<size_t>(it) * SM_A_BYTES, SM_A_BYTES, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(128, SM_TILE_N, 2u);      // tf32 operands
+      for (int it = 0; it < num_kb; ++it) {
+        const int s = it % SM_STAGES;
+        mbar_wait(&full[s], (it / SM_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + s * SM_STAGE);
+        const uint64_t a_hi = umma_desc_sw128_kmajor(base), a_lo = umma_desc_sw128_kmajor(base + 128 * 128);
+        const uint64_t b_hi = umma_desc_sw128_kmajor(base + SM_A_BYTES);
+        const uint64_t b_lo = umma_desc_sw128_kmajor(base + SM_A_BYTES + SM_TILE_N * 128);
+#pragma unroll
+        for (int k = 0; k < SM_BLOCK_K / 8; ++k) {
+          // +32 bytes per 8-element K step inside the 128-byte swizzle atom (address field is >> 4); small terms first
+          umma_tf32(tmem_base, a_lo + 2 * k, b_hi + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_tf32(tmem_base, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+          umma_tf32(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // ================= activation loaders (two groups of four warps, alternating stages) =================
+    const int lw = warp - 2, group = lw >> 2;
+    const int j = (lw & 3) * 32 + lane;                    // column of the tile this thread fills
+    {
+      const int gcol = col0 + j;
+      const bool colok = gcol < p.n_total;
+      const int b = colok ? gcol / p.nr : 0;
+      const int n = p.n_lo + gcol - b * p.nr;
+      const float* xb = p.x + static_cast<size_t>(b) * p.Cin * p.T;
+      const uint32_t row_off = static_cast<uint32_t>(j) * 128u;
+      const int sw = j & 7;
+      for (int it = group; it < num_kb; it += 2) {
+        const int s = it % SM_STAGES;
+        const int kbase = it * SM_BLOCK_K;
+        const int tap = (p.kind == 1 && kbase >= p.Cin) ? 1 : 0;
+        const int ti = n - tap;
+        const bool ok = colok && ti >= 0 && ti < p.T;
+        const float* src = xb + static_cast<size_t>(kbase - tap * p.Cin) * p.T + ti;
+        float v[SM_BLOCK_K];
+#pragma unroll
+        for (int kk = 0; kk < SM_BLOCK_K; ++kk) v[kk] = ok ? __ldg(src + static_cast<size_t>(kk) * p.T) : 0.f;
+        if (it >= SM_STAGES) mbar_wait(&empty[s], ((it / SM_STAGES) & 1) ^ 1);
+        uint8_t* bh = smem + s * SM_STAGE + SM_A_BYTES + row_off;
+        uint8_t* bl = bh + SM_TILE_N * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            hi[e] = __uint_as_float(__float_as_uint(v[c * 4 + e]) & 0xffffe000u);
+            lo[e] = v[c * 4 + e] - hi[e];
+          }
+          const uint32_t off = static_cast<uint32_t>((c ^ sw) << 4);
+          *reinterpret_cast<float4*>(bh + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(bl + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        fence_proxy_async();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+      }
+    }
+    // ================= epilogue: TMEM -> registers -> per-warp transpose -> coalesced global =================
+    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) belong to this warp
+    const int half = lw >> 2;                     // columns [64*half, +64) of the tile
+    float* st = reinterpret_cast<float*>(smem) + lw * (32 * 33);
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int m_base = m_tile * 128 + quarter * 32;
+    const int rows = max(0, min(32, p.Cout - m_base));
+    const int Tout = p.kind == 1 ? p.T * p.s : p.T;
+    const size_t ys = static_cast<size_t>(p.Cout) * Tout;
+    // Everything the epilogue needs besides the accumulator is requested BEFORE the wait for it: the residual / skip
+    // operands of this warp's 32 rows x 64 columns (lane = column, coalesced), the noise row, bias and alpha (lane =
+    // row, handed out by shuffle).  The L2 round trips then overlap the tail of the main loop.
+    size_t obase[2];
+    bool okc[2];
+    float nz[2], ext[2][32];
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      const int gcol = col0 + half * 64 + ch * 32 + lane;
+      const bool colok = gcol < p.n_total;
+      const int b = colok ? gcol / p.nr : 0;
+      const int n = p.n_lo + gcol - b * p.nr;
+      int to = n;
+      bool ok = colok;
+      if (p.kind == 1) {
+        to = n * p.s + phase - p.pad;
+        ok = ok && to >= 0 && to < Tout;
+      }
+      okc[ch] = ok;
+      obase[ch] = static_cast<size_t>(b) * ys + static_cast<size_t>(m_base) * Tout + to;
+      nz[ch] = (p.epi == 2 && ok) ? p.noise[static_cast<size_t>(b) * p.T + n] : 0.f;
+      const float* e = p.epi == 1 ? p.resid : p.x;
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        ext[ch][r] = (p.epi != 0 && ok && r < rows) ? __ldcg(e + obase[ch] + static_cast<size_t>(r) * Tout) : 0.f;
+    }
+    const float bias_l = (p.bias && lane < rows) ? __ldg(&p.bias[m_base + lane]) : 0.f;
+    const float alpha_l = (p.alpha_out && lane < rows) ? __ldg(&p.alpha_out[m_base + lane]) : 1.f;
+    mbar_wait(tmem_full, 0);          // all MMAs done: the accumulator is complete and the ring is idle
+    tc_fence_after();
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      const int c0 = half * 64 + ch * 32;
+      if (col0 + c0 < p.n_total) {                 // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) st[lane * 33 + c] = __uint_as_float(v[c]);
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const float bias_r = __shfl_sync(0xffffffffu, bias_l, r);
+          const float alpha_r = __shfl_sync(0xffffffffu, alpha_l, r);
+          if (okc[ch] && r < rows) {
+            float val = st[r * 33 + lane] + bias_r;
+            if (p.epi == 1) val += ext[ch][r];
+            else if (p.epi == 2) val = ext[ch][r] + nz[ch] * val;
+            if (p.alpha_out) val = snake_tc(val, alpha_r);
+            p.y[obase[ch] + static_cast<size_t>(r) * Tout] = val;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, SM_TILE_N);
+}
+
+// fp32 weights [phases][M][K] -> [phase][m_tile][k_block][hi|lo][128][32], swizzled; rows past M are zero
+__global__ void __launch_bounds__(256) snac_pack_tf32x3_kernel(float4* __restrict__ dst, const float* __restrict__ w,
+                                                               int M, int K, int m_tiles, int num_kb) {
+  const long long tile = blockIdx.x;            // (phase * m_tiles + m_tile) * num_kb + kb
+  const int kb = static_cast<int>(tile % num_kb);
+  const int m_tile = static_cast<int>((tile / num_kb) % m_tiles);
+  const int phase = static_cast<int>(tile / num_kb / m_tiles);
+  for (int i = threadIdx.x; i < 128 * 8; i += blockDim.x) {
+    const int r = i >> 3, c = i & 7;
+    const int m = m_tile * 128 + r, k = kb * SM_BLOCK_K + c * 4;
+    float hi[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f};
+    if (m < M) {
+      const float4 v = *reinterpret_cast<const float4*>(w + (static_cast<size_t>(phase) * M + m) * K + k);
+      const float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        hi[e] = __uint_as_float(__float_as_uint(a[e]) & 0xffffe000u);
+        lo[e] = a[e] - hi[e];
+      }
+    }
+    const size_t base = static_cast<size_t>(tile) * (2 * 128 * 8);
+    dst[base + r * 8 + (c ^ (r & 7))] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    dst[base + 128 * 8 + r * 8 + (c ^ (r & 7))] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+static int launch_snac_gemm(const SnacGemmParams& p, int phases, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    VB_CHECK_CUDA(cudaFuncSetAttribute(snac_gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM));
+    attr_set = true;
+  }
+  const dim3 grid((p.n_total + SM_TILE_N - 1) / SM_TILE_N, (p.Cout + 127) / 128, phases);
+  snac_gemm_tf32x3_kernel<<<grid, SM_THREADS, SM_SMEM, stream>>>(p);
+  VB_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" {
+
+long long vb_snac_tf32x3_bytes(int phases, int M, int K) {
+  if (phases <= 0 || M <= 0 || K <= 0 || K % SM_BLOCK_K != 0) return -1;
+  return static_cast<long long>(phases) * ((M + 127) / 128) * (K / SM_BLOCK_K) * SM_A_BYTES;
+}
+
+int vb_snac_pack_tf32x3(void* d_dst, const float* d_w, int phases, int M, int K, void* stream) {
+  VB_CHECK_ARG(d_dst && d_w, "vb_snac_pack_tf32x3: null pointer");
+  VB_CHECK_ARG(phases >= 1 && M >= 1 && K >= SM_BLOCK_K && K % SM_BLOCK_K == 0,
+               "vb_snac_pack_tf32x3: K = %d must be a positive multiple of %d", K, SM_BLOCK_K);
+  const int m_tiles = (M + 127) / 128, num_kb = K / SM_BLOCK_K;
+  snac_pack_tf32x3_kernel<<<static_cast<unsigned>(static_cast<long long>(phases) * m_tiles * num_kb), 256, 0,
+                            static_cast<cudaStream_t>(stream)>>>(static_cast<float4*>(d_dst), d_w, M, K, m_tiles, num_kb);
+  VB_CHECK_LAUNCH();
+  return 0;
+}
+
+int vb_snac_pwconv_tc(float* d_y, const float* d_x, const void* d_w_tiles, const float* d_bias, const float* d_resid,
+                      const float* d_noise, const float* d_alpha_out, int epilogue, int B, int Cin, int Cout, int T,
+                      int t_lo, int t_hi, void* stream) {
+  VB_CHECK_ARG(d_y && d_x && d_w_tiles, "vb_snac_pwconv_tc: null pointer");
+  VB_CHECK_ARG(epilogue >= 0 && epilogue <= 2, "vb_snac_pwconv_tc: epilogue %d", epilogue);
+  VB_CHECK_ARG(epilogue != 1 || d_resid, "vb_snac_pwconv_tc: residual epilogue needs d_resid");
+  VB_CHECK_ARG(epilogue != 2 || (d_noise && Cin == Cout), "vb_snac_pwconv_tc: noise epilogue needs noise and Cin == Cout");
+  VB_CHECK_ARG(Cin % SM_BLOCK_K == 0, "vb_snac_pwconv_tc: Cin must be a multiple of %d", SM_BLOCK_K);
+  VB_CHECK_ARG(0 <= t_lo && t_lo <= t_hi && t_hi <= T, "vb_snac_pwconv_tc: range [%d, %d) outside [0, %d)", t_lo, t_hi, T);
+  if (B <= 0 || t_lo == t_hi) return 0;
+  SnacGemmParams p = {};
+  p.w_tiles = static_cast<const uint8_t*>(d_w_tiles);
+  p.x = d_x; p.y = d_y; p.bias = d_bias; p.resid = d_resid; p.noise = d_noise; p.alpha_out = d_alpha_out;
+  p.kind = 0; p.epi = epilogue; p.B = B; p.Cin = Cin; p.Cout = Cout; p.T = T; p.K = Cin;
+  p.n_lo = t_lo; p.nr = t_hi - t_lo; p.n_total = B * (t_hi - t_lo); p.s = 1; p.pad = 0;
+  return launch_snac_gemm(p, 1, static_cast<cudaStream_t>(stream));
+}
+
+int vb_snac_convtr_tc(float* d_y, const float* d_x, const void* d_w_tiles, const float* d_bias,
+                      const float* d_alpha_out, int B, int Cin, int Cout, int T, int stride, int o_lo, int o_hi,
+                      void* stream) {
+  VB_CHECK_ARG(d_y && d_x && d_w_tiles, "vb_snac_convtr_tc: null pointer");
+  VB_CHECK_ARG(stride >= 1 && Cin % SM_BLOCK_K == 0, "vb_snac_convtr_tc: Cin must be a multiple of %d", SM_BLOCK_K);
+  VB_CHECK_ARG(0 <= o_lo && o_lo <= o_hi && o_hi <= T * stride,
+               "vb_snac_convtr_tc: output range [%d, %d) outside [0, %d)", o_lo, o_hi, T * stride);
+  if (B <= 0 || o_lo == o_hi) return 0;
+  const int pad = (stride + 1) / 2;
+  // input positions n in [0, T] whose outputs n*stride + r - pad (r < stride) fall inside [o_lo, o_hi)
+  int n_lo = (o_lo + pad - (stride - 1)) / stride;
+  if (o_lo + pad - (stride - 1) < 0) n_lo = 0;
+  int n_hi = (o_hi - 1 + pad) / stride + 1;
+  if (n_hi > T + 1) n_hi = T + 1;
+  SnacGemmParams p = {};
+  p.w_tiles = static_cast<const uint8_t*>(d_w_tiles);
+  p.x = d_x; p.y = d_y; p.bias = d_bias; p.alpha_out = d_alpha_out;
+  p.kind = 1; p.epi = 0; p.B = B; p.Cin = Cin; p.Cout = Cout; p.T = T; p.K = 2 * Cin;
+  p.n_lo = n_lo; p.nr = n_hi - n_lo; p.n_total = B * (n_hi - n_lo); p.s = stride; p.pad = pad;
+  return launch_snac_gemm(p, stride, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

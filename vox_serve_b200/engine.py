@@ -132,6 +132,10 @@ class LlamaEngine:
         self.split_qkv = ops.choose_split_k(self.qkv_w, H, 32, self.sms)
         self.split_o = ops.choose_split_k(H, hq * D, 32, self.sms)
         self.split_down = ops.choose_split_k(H, I, 32, self.sms)
+        # (tuning hooks: VB_SPLIT_QKV / VB_SPLIT_O / VB_SPLIT_DOWN override the split-K of the decode projections)
+        self.split_qkv = int(os.environ.get("VB_SPLIT_QKV", self.split_qkv))
+        self.split_o = int(os.environ.get("VB_SPLIT_O", self.split_o))
+        self.split_down = int(os.environ.get("VB_SPLIT_DOWN", self.split_down))
         smax = max(self.split_qkv, self.split_o, self.split_down)
         self.hidden = torch.zeros(R, H, dtype=BF16, device=dev)
         self.normed = torch.zeros(R, H, dtype=BF16, device=dev)
@@ -271,7 +275,8 @@ class LlamaEngine:
         hidden = self.hidden[:R]
         tiled = R <= self.FUSED_MAX_ROWS and self.tiled_acts
         normed = self.normed_t.view_rows(R) if tiled else self.normed[:R]
-        attn_o = self.attn_t.view_rows(R) if tiled else self.attn[:R]
+        attn_tiled = tiled and self.attn_tiled
+        attn_o = self.attn_t.view_rows(R) if attn_tiled else self.attn[:R]
         act = self.act_t.view_rows(R) if tiled else self.act[:R]
         ops.rmsnorm(hidden, w.layers[0]["ln1"], d.rms_norm_eps, out=normed)
         s_qkv, s_o, s_dn = self._split(self.split_qkv, R), self._split(self.split_o, R), self._split(self.split_down, R)
@@ -282,7 +287,7 @@ class LlamaEngine:
             ops.qkv_rope_append(p, self.kv_cache[i], position_ids, self.freq, plan, hq, hkv, D, q_out=q)
             ops.paged_attn(q, self.kv_map, i * self.pages_per_layer, plan, R, hkv, self.page_size, self.chunk,
                            self.attn_ws, out=attn_o, grid_ctas=self.attn_grid)
-            p = ops.gemm(attn_o if tiled else attn_o.view(R, hq * D), L["o"], mode=1, split_k=s_o,
+            p = ops.gemm(attn_o if attn_tiled else attn_o.view(R, hq * D), L["o"], mode=1, split_k=s_o,
                          out=self._partials(s_o, R, H))
             ops.reduce_residual_rmsnorm(p, hidden, L["ln2"], d.rms_norm_eps, hidden_out=hidden, normed_out=normed)
             ops.gemm(normed, L["gu"], mode=2, out=act, tile_rows=2 * self.gu_half, n_out=I)
@@ -292,6 +297,10 @@ class LlamaEngine:
         return normed
 
     tiled_acts = True         # tests: False = row-major activations + tensor-map loads in decode-sized steps too
+    # attention output layout in the default mode: tiled (bulk-copy input of the O projection, but ~30 index
+    # instructions per stored element in the attention kernel's result warps) or row-major (cheap stores, tensor-map
+    # loads in the O projection); VB_ATTN_TILED=0/1
+    attn_tiled = os.environ.get("VB_ATTN_TILED", "0") != "0"     # measured: row-major 2.645 ms vs tiled 2.678 ms per forward
 
     # ---- kernel-isolated passes for the roofline measurement (bench.py) --------------------------------
     def gemm_pass(self, n_rows: int) -> None:

@@ -17,6 +17,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from .. import ops
+from .. import _lib
 from .._lib import VoxB200Error, call
 
 
@@ -69,6 +70,8 @@ class SNAC:
     def to(self, device):
         if torch.device(device) != self.device and self.loaded:
             self.w = {k: v.to(device) for k, v in self.w.items()}
+            self.device = torch.device(device)
+            self._pack_tensor_core_weights()
         self.device = torch.device(device)
         return self
 
@@ -106,8 +109,40 @@ class SNAC:
         w["out.w"] = _fold(sd, f"decoder.model.{li + 1}")[0]     # [C, 7]
         w["out.b"] = sd[f"decoder.model.{li + 1}.bias"].float()
         self.w = {k: v.contiguous().to(dev) for k, v in w.items()}
+        self._pack_tensor_core_weights()
         self.loaded = True
         return self
+
+    def _pack_tensor_core_weights(self):
+        """The 1x1 and transposed-conv weights whose input width is a multiple of 32 channels are re-tiled for the
+        tcgen05 tf32 hi/lo kernel (vb_snac_pack_tf32x3); narrower layers (test-sized configs) stay on the SIMT
+        kernels.  VB_SNAC_FP32=1 keeps everything on the SIMT kernels."""
+        self.tc: Dict[str, torch.Tensor] = {}
+        if self.device.type != "cuda" or os.environ.get("VB_SNAC_FP32", "0") == "1":
+            return
+        st = ops._stream()
+        for k, v in self.w.items():
+            if not (k.endswith("pw_w") or k.endswith("noise_w") or k.endswith("ct_w")):
+                continue
+            phases, M, K = (1, *v.shape) if v.dim() == 2 else tuple(v.shape)
+            n = _lib.load().vb_snac_tf32x3_bytes(phases, M, K)
+            if n <= 0 or K < int(os.environ.get("VB_SNAC_TC_MIN_K", "128")):
+                continue
+            dst = torch.empty(n, dtype=torch.uint8, device=self.device)
+            call("vb_snac_pack_tf32x3", dst.data_ptr(), v.data_ptr(), phases, M, K, st)
+            self.tc[k] = dst
+
+    def _pwconv(self, key, y, x, bias, resid, noise, alpha, epi, B, cin, cout, T, lo, hi, st):
+        tc = self.tc.get(key)
+        call("vb_snac_pwconv_tc" if tc is not None else "vb_snac_pwconv", y.data_ptr(), x.data_ptr(),
+             (tc if tc is not None else self.w[key]).data_ptr(), None if bias is None else bias.data_ptr(),
+             None if resid is None else resid.data_ptr(), None if noise is None else noise.data_ptr(),
+             None if alpha is None else alpha.data_ptr(), epi, B, cin, cout, T, lo, hi, st)
+
+    def _convtr(self, key, y, x, bias, B, cin, cout, T, s, lo, hi, st):
+        tc = self.tc.get(key)
+        call("vb_snac_convtr_tc" if tc is not None else "vb_snac_convtr", y.data_ptr(), x.data_ptr(),
+             (tc if tc is not None else self.w[key]).data_ptr(), bias.data_ptr(), None, B, cin, cout, T, s, lo, hi, st)
 
     def synthetic_state_dict(self, seed: int = 0) -> Dict[str, torch.Tensor]:
         """Seeded weights under the reference's state_dict names (weight-norm ``original0`` = g, ``original1`` = v;
@@ -209,8 +244,7 @@ class SNAC:
         ch = self.decoder_dim
         y = torch.empty(B, ch, T, **f32)
         # 1x1 conv 768 -> 1024; its output only feeds block 0's Snake -> fuse that Snake here
-        call("vb_snac_pwconv", y.data_ptr(), x.data_ptr(), w["in_pw_w"].data_ptr(), w["in_pw_b"].data_ptr(), None,
-             None, w["b0.alpha"].data_ptr(), 0, B, C, ch, T, in_lo, in_hi, st)
+        self._pwconv("in_pw_w", y, x, w["in_pw_b"], None, None, w["b0.alpha"], 0, B, C, ch, T, in_lo, in_hi, st)
         x = y
         nb = len(self.decoder_rates)
         if noises is None:
@@ -220,14 +254,12 @@ class SNAC:
             (c_lo, c_hi), units = blocks[bi]
             cin, cout = ch, ch // 2
             u = torch.empty(B, cout, T * s, **f32)
-            call("vb_snac_convtr", u.data_ptr(), x.data_ptr(), w[f"b{bi}.ct_w"].data_ptr(),
-                 w[f"b{bi}.ct_b"].data_ptr(), None, B, cin, cout, T, s, c_lo, c_hi, st)
+            self._convtr(f"b{bi}.ct_w", u, x, w[f"b{bi}.ct_b"], B, cin, cout, T, s, c_lo, c_hi, st)
             T *= s
             nz = noises[bi].to(device=dev, dtype=torch.float32).contiguous()
             assert nz.numel() == B * T, "noise tensor shape mismatch"
             x = torch.empty_like(u)
-            call("vb_snac_pwconv", x.data_ptr(), u.data_ptr(), w[f"b{bi}.noise_w"].data_ptr(), None, None,
-                 nz.data_ptr(), None, 2, B, cout, cout, T, c_lo, c_hi, st)
+            self._pwconv(f"b{bi}.noise_w", x, u, None, None, nz, None, 2, B, cout, cout, T, c_lo, c_hi, st)
             for j, dil in enumerate((1, 3, 9)):
                 u_lo, u_hi = units[j]
                 h = torch.empty_like(x)
@@ -239,9 +271,8 @@ class SNAC:
                 if j == 2:
                     nxt = w[f"b{bi + 1}.alpha"] if bi + 1 < nb else w["out.alpha"]
                 o = torch.empty_like(x)
-                call("vb_snac_pwconv", o.data_ptr(), h.data_ptr(), w[f"b{bi}.r{j}.pw_w"].data_ptr(),
-                     w[f"b{bi}.r{j}.pw_b"].data_ptr(), x.data_ptr(), None, None if nxt is None else nxt.data_ptr(),
-                     1, B, cout, cout, T, u_lo, u_hi, st)
+                self._pwconv(f"b{bi}.r{j}.pw_w", o, h, w[f"b{bi}.r{j}.pw_b"], x, None, nxt, 1, B, cout, cout, T,
+                             u_lo, u_hi, st)
                 x = o
             ch = cout
         wav = torch.empty(B, 1, t1 - t0, **f32)
