@@ -619,3 +619,87 @@ def test_snac_decode_golden(ops, golden_dir, tag, cfg):
     assert err < 2e-4, err
     sl = m.decode(codes, noises, out_range=(2048, 4096)).cpu().numpy()
     assert np.array_equal(sl, wav[:, :, 2048:4096])
+
+
+def _snac_pack_tc(w):
+    """[phases][M][K] or [M][K] fp32 (cuda) -> the tf32 hi/lo tiles of vb_snac_pack_tf32x3"""
+    from vox_serve_b200 import _lib
+    phases, M, K = (1, *w.shape) if w.dim() == 2 else tuple(w.shape)
+    n = _lib.load().vb_snac_tf32x3_bytes(phases, M, K)
+    assert n > 0
+    dst = torch.empty(n, dtype=torch.uint8, device="cuda")
+    _lib.call("vb_snac_pack_tf32x3", dst.data_ptr(), w.data_ptr(), phases, M, K, None)
+    return dst
+
+
+@pytest.mark.parametrize("B,Cin,Cout,T,lo,hi,epi,snake", [
+    (3, 64, 64, 50, 0, 50, 0, False),          # one partial column tile, half-empty row tile
+    (5, 128, 192, 77, 3, 70, 1, True),         # ragged range, row tail (192 = 128 + 64), residual + Snake
+    (32, 96, 96, 40, 7, 33, 2, False),         # noise block, K = 3 blocks, columns fold across 32 windows
+    (2, 256, 128, 300, 11, 289, 1, False),     # several column tiles per window
+])
+def test_snac_pwconv_tensor_core_matches_fp32(ops, B, Cin, Cout, T, lo, hi, epi, snake):
+    """vb_snac_pwconv_tc (tcgen05, tf32 hi/lo split) against vb_snac_pwconv (fp32 FMA) and a float64 reference on
+    ragged position ranges, row / column tails and all three epilogues (snac.py:170-176, 206-212)."""
+    from vox_serve_b200 import _lib
+    if epi == 2:
+        Cout = Cin
+    x = torch.randn(B, Cin, T, generator=g(1)).cuda()
+    w = (torch.randn(Cout, Cin, generator=g(2)) / math.sqrt(Cin)).cuda()
+    bias = None if epi == 2 else (torch.randn(Cout, generator=g(3)) * 0.1).cuda()
+    resid = torch.randn(B, Cout, T, generator=g(4)).cuda() if epi == 1 else None
+    noise = torch.randn(B, 1, T, generator=g(5)).cuda() if epi == 2 else None
+    alpha = (0.5 + torch.rand(Cout, generator=g(6))).cuda() if snake else None
+    ptr = lambda t: None if t is None else t.data_ptr()      # noqa: E731
+    y_tc = torch.full((B, Cout, T), 7.0, device="cuda")
+    y_32 = torch.full((B, Cout, T), 7.0, device="cuda")
+    _lib.call("vb_snac_pwconv_tc", y_tc.data_ptr(), x.data_ptr(), _snac_pack_tc(w).data_ptr(), ptr(bias), ptr(resid),
+              ptr(noise), ptr(alpha), epi, B, Cin, Cout, T, lo, hi, None)
+    _lib.call("vb_snac_pwconv", y_32.data_ptr(), x.data_ptr(), w.data_ptr(), ptr(bias), ptr(resid), ptr(noise),
+              ptr(alpha), epi, B, Cin, Cout, T, lo, hi, None)
+    v = torch.einsum("oc,bct->bot", w.double().cpu(), x.double().cpu())
+    if bias is not None:
+        v += bias.double().cpu()[None, :, None]
+    if epi == 1:
+        v += resid.double().cpu()
+    elif epi == 2:
+        v = x.double().cpu() + noise.double().cpu() * v
+    if snake:
+        a = alpha.double().cpu()[None, :, None]
+        v = v + (1.0 / (a + 1e-9)) * torch.sin(a * v) ** 2
+    for name, y in (("tensor core", y_tc), ("fp32", y_32)):
+        y = y.cpu()
+        assert torch.all(y[:, :, :lo] == 7.0) and torch.all(y[:, :, hi:] == 7.0), name + ": wrote outside the range"
+        err = (y[:, :, lo:hi].double() - v[:, :, lo:hi]).abs().max().item()
+        assert err < 2e-5, (name, err)
+    assert (y_tc - y_32).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("B,Cin,Cout,T,s,o_lo,o_hi", [
+    (3, 64, 32, 12, 8, 0, 96),            # whole output, Cout below one tile
+    (32, 128, 64, 16, 8, 17, 111),        # ragged output slice (the Orpheus first-block shape, narrower)
+    (4, 64, 160, 130, 4, 40, 500),        # several column tiles, row tail
+    (2, 96, 48, 75, 2, 1, 149),           # stride 2, K = 2 * 96
+])
+def test_snac_convtr_tensor_core_matches_fp32(ops, B, Cin, Cout, T, s, o_lo, o_hi):
+    """vb_snac_convtr_tc against vb_snac_convtr and torch's conv_transpose1d in float64 (snac.py:222-231)."""
+    from vox_serve_b200 import _lib
+    x = torch.randn(B, Cin, T, generator=g(1)).cuda()
+    wt = (torch.randn(Cin, Cout, 2 * s, generator=g(2)) / math.sqrt(2 * Cin))
+    bias = (torch.randn(Cout, generator=g(3)) * 0.1).cuda()
+    packed = wt.view(Cin, Cout, 2, s).permute(3, 1, 2, 0).reshape(s, Cout, 2 * Cin).contiguous().cuda()
+    y_tc = torch.full((B, Cout, T * s), 7.0, device="cuda")
+    y_32 = torch.full((B, Cout, T * s), 7.0, device="cuda")
+    _lib.call("vb_snac_convtr_tc", y_tc.data_ptr(), x.data_ptr(), _snac_pack_tc(packed).data_ptr(), bias.data_ptr(), None,
+              B, Cin, Cout, T, s, o_lo, o_hi, None)
+    _lib.call("vb_snac_convtr", y_32.data_ptr(), x.data_ptr(), packed.data_ptr(), bias.data_ptr(), None, B, Cin, Cout, T,
+              s, o_lo, o_hi, None)
+    pad = (s + 1) // 2
+    ref = torch.nn.functional.conv_transpose1d(x.double().cpu(), wt.double(), bias.double().cpu(), stride=s, padding=pad,
+                                               output_padding=s % 2)
+    assert ref.shape[-1] == T * s
+    for name, y in (("tensor core", y_tc), ("fp32", y_32)):
+        err = (y.cpu()[:, :, o_lo:o_hi].double() - ref[:, :, o_lo:o_hi]).abs().max().item()
+        assert err < 2e-5, (name, err)
+    # both kernels write the same superset of the requested slice
+    assert torch.equal(y_tc == 7.0, y_32 == 7.0)
