@@ -22,3 +22,9 @@ echo "ncu attn exit $?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -c 3 -o $o/${tag}_gemm_full -f \
   python tests/prof_gemm.py > $o/${tag}_ncu_gemm.log 2>&1
 echo "ncu gemm exit $?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:snac_gemm_tf32x3 -s 34 -c 4 -o $o/${tag}_snac_full -f \
+  python tests/prof_snac.py 32 1 > $o/${tag}_ncu_snac.log 2>&1
+echo "ncu snac exit $?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:sample_kernel -c 2 -o $o/${tag}_sampler_full -f \
+  python tests/prof_sampler.py > $o/${tag}_ncu_sampler.log 2>&1
+echo "ncu sampler exit $?"

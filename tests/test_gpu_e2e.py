@@ -69,3 +69,59 @@ def test_async_scheduling_matches_sync_schedule_lengths():
     for (ns, cs, fs), (na, ca, fa) in zip(out["sync"], out["async"]):
         assert fs == fa and 0 <= na - ns <= 1, (ns, na)
         assert abs(len(ca) - len(cs)) <= 1 and ca[:len(cs) - 1] == cs[:len(cs) - 1]
+
+
+def test_resident_loop_matches_per_step_api():
+    """ModelWorker.run_lm_decode_resident (device-resident CUDA-graph loop, vocoder graph overlapped on the side
+    stream) against the per-step worker API: identical greedy tokens for every request, and the PCM it leaves in
+    HBM equals the eager vocoder pass over each request's newest 28-token window (same injected noise)."""
+    import torch
+
+    from oracle import snac as osnac
+    from tests.e2e_harness import build_models
+    from vox_serve_b200 import ops
+    from vox_serve_b200.requests import Request
+    from vox_serve_b200.scheduler import Scheduler
+
+    dims = oorph.OrpheusDims.tiny(vocab_size=156940, stop_token_id=128258, audio_id_base=128266)
+    prompt_lens, warm, span = (9, 16, 30, 33), 12, 21
+    dims.max_tokens = max(prompt_lens) + 80
+    g = torch.Generator().manual_seed(21)
+    prompts = [torch.randint(10, dims.vocab_size, (n - 5,), generator=g).tolist() for n in prompt_lens]
+    tokens = {}
+    for mode in ("resident", "per_step"):
+        worker, _ = build_models(dims, osnac.SnacConfig.tiny(), 3, len(prompt_lens), 16, 128)
+        cache = {}
+
+        def fixed_noise(shapes, cache=cache):
+            for s in shapes:
+                if tuple(s) not in cache:
+                    cache[tuple(s)] = torch.randn(s, generator=torch.Generator().manual_seed(sum(s))).cuda()
+            return [cache[tuple(s)] for s in shapes]
+
+        worker.model.audio_decoder.noise_source = fixed_noise
+        sched = Scheduler(worker)
+        reqs = [Request(request_id=f"{mode}{i}", prompt=p, model_kwargs={"voice": None}) for i, p in enumerate(prompts)]
+        for r in reqs:
+            sched.submit(r)
+        for _ in range(warm):
+            sched._step()
+        assert all(r.done_lm_prefill and 7 <= len(r.lm_output_audio_tokens) < 28 for r in reqs)
+        if mode == "per_step":
+            for _ in range(span):
+                sched._step()
+        else:
+            before = [len(r.lm_output_audio_tokens) for r in reqs]
+            # (the noise tensors must exist before the vocoder graph is captured: no host copies inside a capture)
+            fixed_noise(worker.model.audio_decoder.noise_shapes(len(reqs), 16))
+            worker.run_lm_decode_resident(reqs, span, detokenize=True)
+            torch.cuda.synchronize()
+            assert [len(r.lm_output_audio_tokens) for r in reqs] == [b + span for b in before]
+            B, W = len(reqs), worker.detokenize_interval
+            last = torch.tensor([[int(t) for t in r.lm_output_audio_tokens[-W:]] for r in reqs], dtype=torch.int64).cuda()
+            want = ops.pcm16(worker.model.postprocess(last.view(B, W, 1)))
+            torch.cuda.synchronize()
+            assert torch.equal(worker.res_pcm[:B].cpu(), want.cpu())
+            assert worker.res_pcm[:B].abs().max().item() > 0
+        tokens[mode] = [[int(t) for t in r.lm_output_audio_tokens] for r in reqs]
+    assert tokens["resident"] == tokens["per_step"]

@@ -19,6 +19,7 @@ There is no CPU / eager fallback: a missing libvoxb200.so raises at construction
 """
 from __future__ import annotations
 
+import os
 import queue
 from typing import Coroutine, Dict, List, Optional
 
@@ -429,6 +430,8 @@ class ModelWorker:
             self.res_first = torch.zeros(self.max_batch_size, dtype=I32, device=self.device)
             self.res_pcm = torch.zeros(self.max_batch_size, m.n_channels, m.output_audio_length, dtype=torch.int16,
                                        device=self.device)
+            self.res_win = torch.zeros(self.max_batch_size, self.detokenize_interval, dtype=torch.int64,
+                                       device=self.device)
             self.res_graphs: Dict[int, tuple] = {}
         self.res_kv_len[:B].copy_(torch.from_numpy(kv0), non_blocking=False)
         self.res_pos[:B].copy_(torch.from_numpy(pos0), non_blocking=False)
@@ -446,16 +449,23 @@ class ModelWorker:
                               out=out.view(-1))
             ops.token_feedback(out.view(-1), sl, self.next_input, self.history, self.n_out)
 
-        def detok_step():
+        # The vocoder runs on the side stream (as in run_detokenize), overlapped with the following LM steps.  What
+        # must stay ordered with the LM steps is only the selection of the window: token_feedback of the next step
+        # advances n_out / history, so latest_window + gather_windows are replayed in line on the main stream and the
+        # SNAC graph reads the gathered copy.
+        def window_step():
             sl = st.d("slots", B)
             ops.latest_window(self.res_first, self.n_out, sl, B, self.detokenize_interval)
-            win = ops.gather_windows(self.history, sl, self.res_first, None, self.detokenize_interval, n=B)
-            audio = m.postprocess(win.view(B, self.detokenize_interval, 1))
+            ops.gather_windows(self.history, sl, self.res_first, None, self.detokenize_interval, out=self.res_win[:B],
+                               n=B)
+
+        def vocoder_step():
+            audio = m.postprocess(self.res_win[:B].view(B, self.detokenize_interval, 1))
             ops.pcm16(audio, out=self.res_pcm[:B])
 
         if B not in self.res_graphs:
             graphs = []
-            for fn in (lm_step, detok_step):
+            for fn in (lm_step, window_step, vocoder_step):
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 s = torch.cuda.Stream()
@@ -469,9 +479,12 @@ class ModelWorker:
                     self.graph_pool = g.pool()
                 graphs.append((g, ops.launch_count() - before))
             self.res_graphs[B] = tuple(graphs)
-        (g_lm, n_lm), (g_dt, n_dt) = self.res_graphs[B]
+        (g_lm, n_lm), (g_win, n_win), (g_voc, n_voc) = self.res_graphs[B]
         hop = self.detokenize_interval - self.detokenize_overlap
         replays = 0
+        main, side = torch.cuda.current_stream(), self.detok_stream
+        overlap = os.environ.get("VB_RESIDENT_VOCODER_OVERLAP", "1") != "0"
+        side.wait_stream(main)
         if timing is not None:
             timing["start"].record()
         for k in range(n_steps):
@@ -479,12 +492,20 @@ class ModelWorker:
             self.gpu_launches += n_lm
             replays += 1
             if detokenize and (k + 1) % hop == 0:
-                g_dt.replay()
-                self.gpu_launches += n_dt
-                replays += 1
+                main.wait_stream(side)           # the previous vocoder pass has consumed res_win
+                g_win.replay()
+                if overlap:
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        g_voc.replay()
+                else:
+                    g_voc.replay()
+                self.gpu_launches += n_win + n_voc
+                replays += 2
+        main.wait_stream(side)
         if timing is not None:
             timing["end"].record()
-            timing["lm_nodes"], timing["detok_nodes"] = n_lm, n_dt
+            timing["lm_nodes"], timing["detok_nodes"] = n_lm, n_win + n_voc
         # ---- bring the host-side request state up to date ----
         torch.cuda.synchronize()
         hist = self.history.cpu()
