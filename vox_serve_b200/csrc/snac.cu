@@ -50,18 +50,23 @@ __global__ void from_codes_kernel(float* __restrict__ z, const int32_t* __restri
 // ------------------------------------------------------------------------------------------
 // depthwise conv k=7, dilation d, "same" padding; optional Snake on the input tile and on the output
 // ------------------------------------------------------------------------------------------
-constexpr int DW_TILE = 256;
-__global__ void __launch_bounds__(DW_TILE) dwconv7_kernel(float* __restrict__ y, const float* __restrict__ x,
-                                                          const float* __restrict__ w, const float* __restrict__ bias,
-                                                          const float* __restrict__ alpha_in,
-                                                          const float* __restrict__ alpha_out, int C, int T, int dil,
-                                                          int t_lo, int t_hi) {
-  extern __shared__ float tile[];  // DW_TILE + 6*dil
-  const int c = blockIdx.y, b = blockIdx.z, t0 = t_lo + blockIdx.x * DW_TILE;
+constexpr int DW_THREADS = 256;
+// OPT outputs per thread (tile = OPT * 256 positions of one channel of one window): the long late stages use 4 so
+// a launch is a few thousand CTAs instead of tens of thousands of 256-output ones (CTA turnover, not arithmetic or
+// bytes, was what the 30-40 us of those launches paid for)
+template <int OPT>
+__global__ void __launch_bounds__(DW_THREADS) dwconv7_kernel(float* __restrict__ y, const float* __restrict__ x,
+                                                             const float* __restrict__ w, const float* __restrict__ bias,
+                                                             const float* __restrict__ alpha_in,
+                                                             const float* __restrict__ alpha_out, int C, int T, int dil,
+                                                             int t_lo, int t_hi) {
+  extern __shared__ float tile[];  // OPT * DW_THREADS + 6*dil
+  constexpr int TILE = OPT * DW_THREADS;
+  const int c = blockIdx.y, b = blockIdx.z, t0 = t_lo + blockIdx.x * TILE;
   const float* xr = x + (static_cast<size_t>(b) * C + c) * T;
-  const int halo = 3 * dil, n = DW_TILE + 2 * halo;
+  const int halo = 3 * dil, n = min(TILE, t_hi - t0) + 2 * halo;
   const float ain = alpha_in ? alpha_in[c] : 0.f;
-  for (int i = threadIdx.x; i < n; i += DW_TILE) {
+  for (int i = threadIdx.x; i < n; i += DW_THREADS) {
     const int t = t0 - halo + i;
     float v = 0.f;
     if (t >= 0 && t < T) {
@@ -71,13 +76,20 @@ __global__ void __launch_bounds__(DW_TILE) dwconv7_kernel(float* __restrict__ y,
     tile[i] = v;
   }
   __syncthreads();
-  const int t = t0 + threadIdx.x;
-  if (t < t_hi) {
-    float acc = bias ? bias[c] : 0.f;
+  float wk[7];
 #pragma unroll
-    for (int k = 0; k < 7; ++k) acc += w[c * 7 + k] * tile[threadIdx.x + k * dil];
-    if (alpha_out) acc = snake_f(acc, alpha_out[c]);
-    y[(static_cast<size_t>(b) * C + c) * T + t] = acc;
+  for (int k = 0; k < 7; ++k) wk[k] = w[c * 7 + k];
+  const float bv = bias ? bias[c] : 0.f, aout = alpha_out ? alpha_out[c] : 0.f;
+#pragma unroll
+  for (int o = 0; o < OPT; ++o) {
+    const int i = o * DW_THREADS + threadIdx.x, t = t0 + i;
+    if (t < t_hi) {
+      float acc = bv;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) acc += wk[k] * tile[i + k * dil];
+      if (alpha_out) acc = snake_f(acc, aout);
+      y[(static_cast<size_t>(b) * C + c) * T + t] = acc;
+    }
   }
 }
 
@@ -220,34 +232,44 @@ __global__ void __launch_bounds__(256) convtr_kernel(float* __restrict__ y, cons
       });
 }
 
-// final: tanh(conv_k7(x) + bias), Cout = 1; x already carries the last Snake
+// final: tanh(conv_k7(x) + bias), Cout = 1; x already carries the last Snake unless alpha_in is given.  A CTA owns
+// 256 outputs; channels are staged eight at a time as [8][256 + 6] tiles so every input element is loaded (and
+// Snake-activated) once instead of once per tap.
+constexpr int FC_CH = 8;
 __global__ void __launch_bounds__(256) final_conv_kernel(float* __restrict__ y, const float* __restrict__ x,
                                                          const float* __restrict__ w, const float* __restrict__ bias,
                                                          const float* __restrict__ alpha_in, int C, int T, int t0,
                                                          int t1) {
-  extern __shared__ float ws[];  // C*7 weights (+ C alphas)
+  extern __shared__ float ws[];  // C*7 weights, C alphas, FC_CH * 262 tile
+  float* al = ws + C * 7;
+  float* tile = al + C;
   for (int i = threadIdx.x; i < C * 7; i += blockDim.x) ws[i] = w[i];
-  if (alpha_in)
-    for (int i = threadIdx.x; i < C; i += blockDim.x) ws[C * 7 + i] = alpha_in[i];
-  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) al[i] = alpha_in ? alpha_in[i] : 0.f;
   const int b = blockIdx.y;
-  const int t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= t1) return;
+  const int tb = t0 + blockIdx.x * 256, t = tb + threadIdx.x;
   const float* xb = x + static_cast<size_t>(b) * C * T;
   float acc = bias[0];
-  for (int c = 0; c < C; ++c) {
-    const float* xr = xb + static_cast<size_t>(c) * T;
+  for (int c0 = 0; c0 < C; c0 += FC_CH) {
+    __syncthreads();             // weights staged (first pass) / previous tile consumed
+    for (int i = threadIdx.x; i < FC_CH * 262; i += 256) {
+      const int cc = i / 262, j = i - cc * 262, tt = tb - 3 + j;
+      float v = 0.f;
+      if (c0 + cc < C && tt >= 0 && tt < T) {
+        v = xb[static_cast<size_t>(c0 + cc) * T + tt];
+        if (alpha_in) v = snake_f(v, al[c0 + cc]);
+      }
+      tile[i] = v;
+    }
+    __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 7; ++k) {
-      const int tt = t + k - 3;
-      if (tt >= 0 && tt < T) {
-        float v = xr[tt];
-        if (alpha_in) v = snake_f(v, ws[C * 7 + c]);
-        acc += ws[c * 7 + k] * v;
+    for (int cc = 0; cc < FC_CH; ++cc) {
+      if (c0 + cc < C) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) acc += ws[(c0 + cc) * 7 + k] * tile[cc * 262 + threadIdx.x + k];
       }
     }
   }
-  y[static_cast<size_t>(b) * (t1 - t0) + (t - t0)] = tanhf(acc);
+  if (t < t1) y[static_cast<size_t>(b) * (t1 - t0) + (t - t0)] = tanhf(acc);
 }
 
 }  // namespace vb
@@ -291,9 +313,17 @@ int vb_snac_dwconv7(float* d_y, const float* d_x, const float* d_w, const float*
   VB_CHECK_ARG(dilation >= 1 && dilation <= 64, "vb_snac_dwconv7: dilation %d", dilation);
   VB_CHECK_ARG(0 <= t_lo && t_lo <= t_hi && t_hi <= T, "vb_snac_dwconv7: range [%d, %d) outside [0, %d)", t_lo, t_hi, T);
   if (B <= 0 || t_lo == t_hi) return 0;
-  const size_t smem = (DW_TILE + 6 * dilation) * sizeof(float);
-  dwconv7_kernel<<<dim3((t_hi - t_lo + DW_TILE - 1) / DW_TILE, C, B), DW_TILE, smem, static_cast<cudaStream_t>(stream)>>>(
-      d_y, d_x, d_w, d_bias, d_alpha_in, d_alpha_out, C, T, dilation, t_lo, t_hi);
+  const int range = t_hi - t_lo;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (range >= 4 * DW_THREADS) {
+    const size_t smem = (4 * DW_THREADS + 6 * dilation) * sizeof(float);
+    dwconv7_kernel<4><<<dim3((range + 4 * DW_THREADS - 1) / (4 * DW_THREADS), C, B), DW_THREADS, smem, st>>>(
+        d_y, d_x, d_w, d_bias, d_alpha_in, d_alpha_out, C, T, dilation, t_lo, t_hi);
+  } else {
+    const size_t smem = (DW_THREADS + 6 * dilation) * sizeof(float);
+    dwconv7_kernel<1><<<dim3((range + DW_THREADS - 1) / DW_THREADS, C, B), DW_THREADS, smem, st>>>(
+        d_y, d_x, d_w, d_bias, d_alpha_in, d_alpha_out, C, T, dilation, t_lo, t_hi);
+  }
   VB_CHECK_LAUNCH();
   return 0;
 }
@@ -352,7 +382,7 @@ int vb_snac_final(float* d_y, const float* d_x, const float* d_w, const float* d
   VB_CHECK_ARG(d_y && d_x && d_w && d_bias, "vb_snac_final: null pointer");
   VB_CHECK_ARG(0 <= t0 && t0 < t1 && t1 <= T, "vb_snac_final: bad output range [%d, %d) of %d", t0, t1, T);
   if (B <= 0) return 0;
-  const size_t smem = static_cast<size_t>(C) * 8 * sizeof(float);
+  const size_t smem = (static_cast<size_t>(C) * 8 + FC_CH * 262) * sizeof(float);
   final_conv_kernel<<<dim3((t1 - t0 + 255) / 256, B), 256, smem, static_cast<cudaStream_t>(stream)>>>(
       d_y, d_x, d_w, d_bias, d_alpha_in, C, T, t0, t1);
   VB_CHECK_LAUNCH();
