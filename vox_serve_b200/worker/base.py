@@ -390,7 +390,7 @@ class ModelWorker:
 
     # ---- device-resident multi-step decode --------------------------------------------------------
     def run_lm_decode_resident(self, requests: List[Request], n_steps: int, detokenize: bool = True,
-                               timing: Optional[dict] = None) -> int:
+                               timing: Optional[dict] = None, tail_window: bool = False) -> int:
         """``n_steps`` decode steps for ``requests`` (all past prefill) with NO host work in between: pages for the
         whole span are allocated up front, kv lengths / positions / input ids / repetition caches / token history
         advance on the device, and each step is one CUDA-graph replay.  With ``detokenize`` the newest full
@@ -491,7 +491,9 @@ class ModelWorker:
             g_lm.replay()
             self.gpu_launches += n_lm
             replays += 1
-            if detokenize and (k + 1) % hop == 0:
+            if detokenize and ((k + 1) % hop == 0 or (tail_window and k + 1 == n_steps)):
+                # (tail_window: a span that is not a whole number of hops still ends with a vocoder pass, so that
+                # a timed span accounts for at least the vocoder work its tokens need)
                 main.wait_stream(side)           # the previous vocoder pass has consumed res_win
                 g_win.replay()
                 if overlap:
