@@ -207,15 +207,67 @@ __global__ void __launch_bounds__(SMP_THREADS, 1) sample_kernel(const SamplePara
   pdl_sync();
 
   // ---- one pass over the row: keys (0 = no token / NaN) ----
+  // The pass is load-latency-bound (40 tokens per thread, 64 registers per thread), so the loads are batched: ten
+  // token PAIRS at a time -- one 32-bit load for the two logits, one 16-bit load per window slot for their
+  // repetition flags, all twenty-odd requests in flight together -- and only then finished (penalty, mask,
+  // temperature: same operations and rounding points as token_value()).  Rows whose layout does not allow the paired
+  // loads (odd leading dimension / vocabulary, unaligned base) take the scalar path.
   uint32_t kk[SMP_PAIRS];
+  const __nv_bfloat16* lrow = p.logits + static_cast<size_t>(row) * p.ld;
+  const uint8_t* rep0 = nullptr;
+  size_t rep_wstride = 0;
+  if (p.rep_cache) {
+    const int b0 = row / p.C_logits;
+    const int b = p.cache_rows ? p.cache_rows[b0] : b0;
+    const int cc = (p.C_logits == 1 && p.C_cache != 1) ? 0 : row % p.C_logits;   // sampling.py:140-141
+    rep_wstride = static_cast<size_t>(p.C_cache) * p.vocab;
+    rep0 = p.rep_cache + (static_cast<size_t>(b) * p.W * p.C_cache + cc) * p.vocab;
+  }
+  const bool paired = ((p.ld | p.vocab) & 1) == 0 && (reinterpret_cast<uintptr_t>(lrow) & 3) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(rep0) | rep_wstride) & 1) == 0;
+  auto finish = [&](float l, bool seen, int i) -> uint32_t {
+    if (seen) l = (l > 0.f) ? round_bf16(l / p.penalty) : round_bf16(l * p.penalty);   // sampling.py:143-144
+    if (i == p.mask_token) l = -INFINITY;
+    if (scaled) l = round_bf16(l / p.temperature);
+    return (l == l) ? bf16_key(l) : 0u;
+  };
+  constexpr int SMP_BATCH = 5;
 #pragma unroll
-  for (int j = 0; j < SMP_PAIRS; ++j) {
-    kk[j] = 0u;
-    if (j < npairs) {
+  for (int j0 = 0; j0 < SMP_PAIRS; j0 += SMP_BATCH) {
+    uint32_t lw[SMP_BATCH], sb[SMP_BATCH];
+#pragma unroll
+    for (int jj = 0; jj < SMP_BATCH; ++jj) {
+      const int j = j0 + jj;
+      const int i0 = 2 * ((j * S + rank) * SMP_THREADS + tid);
+      lw[jj] = 0u;
+      sb[jj] = 0u;
+      if (j < npairs && i0 < p.vocab) {
+        if (paired) {
+          lw[jj] = __ldg(reinterpret_cast<const uint32_t*>(lrow + i0));
+          for (int w = 0; w < p.W; ++w)
+            if (rep0) sb[jj] |= __ldg(reinterpret_cast<const unsigned short*>(rep0 + w * rep_wstride + i0));
+        } else {
+          lw[jj] = __ldg(reinterpret_cast<const unsigned short*>(lrow + i0));
+          if (i0 + 1 < p.vocab)
+            lw[jj] |= static_cast<uint32_t>(__ldg(reinterpret_cast<const unsigned short*>(lrow + i0 + 1))) << 16;
+          for (int w = 0; w < p.W; ++w) {
+            if (rep0) {
+              sb[jj] |= __ldg(rep0 + w * rep_wstride + i0);
+              if (i0 + 1 < p.vocab) sb[jj] |= static_cast<uint32_t>(__ldg(rep0 + w * rep_wstride + i0 + 1)) << 8;
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < SMP_BATCH; ++jj) {
+      const int j = j0 + jj;
       const int i0 = 2 * ((j * S + rank) * SMP_THREADS + tid);
       uint32_t lo = 0u, hi = 0u;
-      if (i0 < p.vocab) { const float v = token_value(p, row, i0, scaled); lo = (v == v) ? bf16_key(v) : 0u; }
-      if (i0 + 1 < p.vocab) { const float v = token_value(p, row, i0 + 1, scaled); hi = (v == v) ? bf16_key(v) : 0u; }
+      if (j < npairs && i0 < p.vocab) {
+        lo = finish(bf16_lo(lw[jj]), (sb[jj] & 0xffu) != 0u, i0);
+        if (i0 + 1 < p.vocab) hi = finish(bf16_hi(lw[jj]), (sb[jj] & 0xff00u) != 0u, i0 + 1);
+      }
       kk[j] = lo | (hi << 16);
     }
   }
