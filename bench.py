@@ -238,8 +238,8 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def fresh_batch(tag):
-        sched = Scheduler(worker)
+    def fresh_batch(tag, vocoder_batch_steps=1):
+        sched = Scheduler(worker, vocoder_batch_steps=vocoder_batch_steps)
         t_sub = {}
         reqs = []
         for i in range(BATCH):
@@ -322,6 +322,11 @@ def run_gpu(args):
     sched, reqs, _ = fresh_batch("s")
     sync_ms, sync_audio_s, _, _, _ = timed_api_loop(sched, reqs, Ks, async_mode=False)
     drain(sched, reqs)
+    # the async loop with the scheduler's optional vocoder batching (completed windows held until every 7th step so
+    # the vocoder runs on the full batch; first chunks are never held): reported beside the default schedule
+    sched, reqs, _ = fresh_batch("v", vocoder_batch_steps=hop)
+    vb_ms, vb_audio_s, _, _, _ = timed_api_loop(sched, reqs, K, async_mode=True)
+    drain(sched, reqs)
 
     # ------------------------------------------------ device-resident loop ------------------------------------
     sched, reqs, _ = fresh_batch("r")
@@ -387,7 +392,10 @@ def run_gpu(args):
                     "api": "Scheduler._step_async (scheduler/base.py:168-215 ordering) -> ModelWorker."
                            "prepare_lm_inputs/run_detokenize/run_lm_decode; host bookkeeping one step behind the device",
                     "sync_scheduler": {"value": sync_audio_s / (sync_ms / 1e3) * world, "ms_per_step": sync_ms / Ks,
-                                       "steps": Ks, "api": "Scheduler._step (scheduler/base.py:135-166)"}},
+                                       "steps": Ks, "api": "Scheduler._step (scheduler/base.py:135-166)"},
+                    "vocoder_batched": {"value": vb_audio_s / (vb_ms / 1e3) * world, "ms_per_step": vb_ms / K,
+                                        "policy": f"Scheduler(vocoder_batch_steps={hop}): later chunks of a request "
+                                                  "wait up to 6 steps for a full vocoder batch (not the default)"}},
             "gpu_launches": int(res_launches), "gpu_launches_e2e": int(e2e_launches),
             "tokens_per_s": BATCH * world * K / (res_ms / 1e3),
             "ttfa_burst_ms": {"p50": ttfa[len(ttfa) // 2], "min": ttfa[0], "max": ttfa[-1],

@@ -16,8 +16,15 @@ from .requests import Request
 
 class Scheduler:
     def __init__(self, worker, max_batch_size: Optional[int] = None, one_prefill_per_step: bool = True,
-                 on_audio: Optional[Callable[[Request, bytes, float], None]] = None):
+                 on_audio: Optional[Callable[[Request, bytes, float], None]] = None, vocoder_batch_steps: int = 1):
         self.model_worker = worker
+        # 1 = the reference's schedule (every request is vocoded in the step its window completes).  N > 1 holds
+        # completed windows back until every N-th step so that the vocoder runs on a full batch: with staggered
+        # requests the per-step batches are ~batch/7 windows and the early decoder stages cost as much for 5 windows
+        # as for 32.  A request's FIRST chunk and the chunks of finished requests are never held (TTFA unchanged);
+        # later chunks arrive at most N - 1 steps late (a chunk is 85 ms of audio, a step ~3 ms).
+        self.vocoder_batch_steps = max(1, int(vocoder_batch_steps))
+        self._select_no = 0
         self.max_batch_size = max_batch_size or worker.max_batch_size
         self.one_prefill_per_step = one_prefill_per_step
         self.pending: Deque[Request] = deque()
@@ -47,6 +54,8 @@ class Scheduler:
         out: List[Request] = []
         interval, overlap = self.model_worker.detokenize_interval, self.model_worker.detokenize_overlap
         step = interval - overlap
+        self._select_no += 1
+        hold = self.vocoder_batch_steps > 1 and self._select_no % self.vocoder_batch_steps != 0
         for req in self.active_requests:
             if len(out) >= self.max_batch_size:
                 break
@@ -63,6 +72,8 @@ class Scheduler:
                     req.done_all = True
                 out.append(req)
             elif nxt + interval <= len(req.lm_output_audio_tokens):
+                if hold and req.next_audio_decode_idx:
+                    continue
                 req.next_audio_decode_idx = [nxt]
                 out.append(req)
         return out
