@@ -39,6 +39,23 @@ def main():
         g.replay()
     e1.record()
     torch.cuda.synchronize()
+    if len(sys.argv) > 3 and sys.argv[3] == "trace":
+        # in-situ timeline of the tensor-core launches of one replay (block 0 of each: %globaltimer marks)
+        from vox_serve_b200 import _lib
+        cap = 1024
+        buf = torch.zeros(4 + 4 * cap, dtype=torch.int64, device=dev)
+        buf[1] = cap
+        _lib.check(_lib.load().vb_set_trace(buf.data_ptr()), "vb_set_trace")
+        g.replay()
+        torch.cuda.synchronize()
+        _lib.check(_lib.load().vb_set_trace(None), "vb_set_trace")
+        h = buf.cpu()
+        n = min(int(h[0]), cap)
+        recs = sorted(h[4:4 + 4 * n].view(n, 4).tolist())
+        names = {60: "tc kernel", 61: " setup done", 62: " first stage ready", 63: " all MMAs issued", 64: " accumulator done"}
+        t0 = recs[0][0]
+        for a, b, kid, aux in recs:
+            print(f"{(a - t0) / 1e3:9.2f} us  {names.get(kid, kid):22s} k-blocks {aux:3d}  dur {(b - a) / 1e3:7.2f} us")
     print(json.dumps({"snac_decode_ms": round(e0.elapsed_time(e1) / reps, 4), "batch": B,
                       "checksum": float(wav.double().abs().sum())}))
 

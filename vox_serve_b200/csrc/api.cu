@@ -45,6 +45,7 @@ cudaError_t trace_set_attn(unsigned long long*);
 cudaError_t trace_set_gemm(unsigned long long*);
 cudaError_t trace_set_chain(unsigned long long*);
 cudaError_t trace_set_sampler(unsigned long long*);
+cudaError_t trace_set_snac(unsigned long long*);
 }  // namespace vb
 
 extern "C" {
@@ -56,6 +57,7 @@ int vb_set_trace(void* d_buffer) {
   VB_CHECK_CUDA(vb::trace_set_gemm(p));
   VB_CHECK_CUDA(vb::trace_set_chain(p));
   VB_CHECK_CUDA(vb::trace_set_sampler(p));
+  VB_CHECK_CUDA(vb::trace_set_snac(p));
   return 0;
 }
 

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) snac_gemm_tf32x3_kernel(const S
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col0 = blockIdx.x * SM_TILE_N, m_tile = blockIdx.y, phase = blockIdx.z;
+  const int tr = (threadIdx.x == 0 && trace_block0()) ? trace_begin(60, p.K / SM_BLOCK_K) : -1;
   const int num_kb = p.K / SM_BLOCK_K;
   const int m_tiles = (p.Cout + 127) >> 7;
 
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) snac_gemm_tf32x3_kernel(const S
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tr >= 0) trace_mark(61);
 
   if (warp == 0) {
     // ================= weight producer: one 32 KiB bulk copy per stage =================
@@ -104,6 +106,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) snac_gemm_tf32x3_kernel(const S
       for (int it = 0; it < num_kb; ++it) {
         const int s = it % SM_STAGES;
         mbar_wait(&full[s], (it / SM_STAGES) & 1);
+        if (it == 0 && trace_block0()) trace_mark(62);
         tc_fence_after();
         const uint32_t base = smem_u32(smem + s * SM_STAGE);
         const uint64_t a_hi = umma_desc_sw128_kmajor(base), a_lo = umma_desc_sw128_kmajor(base + 128 * 128);
@@ -119,6 +122,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) snac_gemm_tf32x3_kernel(const S
         umma_commit(&empty[s]);
       }
       umma_commit(tmem_full);
+      if (trace_block0()) trace_mark(63);
     }
   } else {
     // ================= activation loaders (two groups of four warps, alternating stages) =================
@@ -132,16 +136,19 @@ __global__ void __launch_bounds__(SM_THREADS, 1) snac_gemm_tf32x3_kernel(const S
       const float* xb = p.x + static_cast<size_t>(b) * p.Cin * p.T;
       const uint32_t row_off = static_cast<uint32_t>(j) * 128u;
       const int sw = j & 7;
-      for (int it = group; it < num_kb; it += 2) {
-        const int s = it % SM_STAGES;
+      // software-pipelined: the 32 loads of this group's NEXT stage are in flight while the current one is split
+      // and stored
+      auto fetch = [&](int it, float (&v)[SM_BLOCK_K]) {
         const int kbase = it * SM_BLOCK_K;
         const int tap = (p.kind == 1 && kbase >= p.Cin) ? 1 : 0;
         const int ti = n - tap;
-        const bool ok = colok && ti >= 0 && ti < p.T;
+        const bool ok = it < num_kb && colok && ti >= 0 && ti < p.T;
         const float* src = xb + static_cast<size_t>(kbase - tap * p.Cin) * p.T + ti;
-        float v[SM_BLOCK_K];
 #pragma unroll
         for (int kk = 0; kk < SM_BLOCK_K; ++kk) v[kk] = ok ? __ldg(src + static_cast<size_t>(kk) * p.T) : 0.f;
+      };
+      auto store = [&](int it, const float (&v)[SM_BLOCK_K]) {
+        const int s = it % SM_STAGES;
         if (it >= SM_STAGES) mbar_wait(&empty[s], ((it / SM_STAGES) & 1) ^ 1);
         uint8_t* bh = smem + s * SM_STAGE + SM_A_BYTES + row_off;
         uint8_t* bl = bh + SM_TILE_N * 128;
@@ -160,6 +167,16 @@ __global__ void __launch_bounds__(SM_THREADS, 1) snac_gemm_tf32x3_kernel(const S
         fence_proxy_async();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);
+      };
+      float va[SM_BLOCK_K], vb_[SM_BLOCK_K];
+      fetch(group, va);
+      for (int it = group; it < num_kb; it += 4) {
+        fetch(it + 2, vb_);
+        store(it, va);
+        if (it + 2 < num_kb) {
+          fetch(it + 4, va);
+          store(it + 2, vb_);
+        }
       }
     }
     // ================= epilogue: TMEM -> registers -> per-warp transpose -> coalesced global =================
@@ -171,15 +188,21 @@ __global__ void __launch_bounds__(SM_THREADS, 1) snac_gemm_tf32x3_kernel(const S
     const int rows = max(0, min(32, p.Cout - m_base));
     const int Tout = p.kind == 1 ? p.T * p.s : p.T;
     const size_t ys = static_cast<size_t>(p.Cout) * Tout;
-    // Everything the epilogue needs besides the accumulator is requested BEFORE the wait for it: the residual / skip
-    // operands of this warp's 32 rows x 64 columns (lane = column, coalesced), the noise row, bias and alpha (lane =
-    // row, handed out by shuffle).  The L2 round trips then overlap the tail of the main loop.
-    size_t obase[2];
-    bool okc[2];
-    float nz[2], ext[2][32];
-#pragma unroll
+    // Rolled on purpose: unrolled over 2 chunks x 32 rows (with Snake inlined) this was ~80 KB of straight-line code
+    // that every warp ran once -- instruction fetch, not arithmetic or memory, made the epilogue 10-37 us.  Rows go in
+    // batches of 16: the batch's residual / skip operands are requested together (lane = column, coalesced), then
+    // the batch is finished and stored.
+    const float bias_l = (p.bias && lane < rows) ? __ldg(&p.bias[m_base + lane]) : 0.f;
+    const float alpha_l = (p.alpha_out && lane < rows) ? __ldg(&p.alpha_out[m_base + lane]) : 1.f;
+    const float* e = p.epi == 1 ? p.resid : p.x;
+    mbar_wait(tmem_full, 0);          // all MMAs done: the accumulator is complete and the ring is idle
+    tc_fence_after();
+    if (warp == 2 && lane == 0 && trace_block0()) trace_mark(64);
+#pragma unroll 1
     for (int ch = 0; ch < 2; ++ch) {
-      const int gcol = col0 + half * 64 + ch * 32 + lane;
+      const int c0 = half * 64 + ch * 32;
+      if (col0 + c0 >= p.n_total) break;            // warp-uniform
+      const int gcol = col0 + c0 + lane;
       const bool colok = gcol < p.n_total;
       const int b = colok ? gcol / p.nr : 0;
       const int n = p.n_lo + gcol - b * p.nr;
@@ -189,47 +212,41 @@ __global__ void __launch_bounds__(SM_THREADS, 1) snac_gemm_tf32x3_kernel(const S
         to = n * p.s + phase - p.pad;
         ok = ok && to >= 0 && to < Tout;
       }
-      okc[ch] = ok;
-      obase[ch] = static_cast<size_t>(b) * ys + static_cast<size_t>(m_base) * Tout + to;
-      nz[ch] = (p.epi == 2 && ok) ? p.noise[static_cast<size_t>(b) * p.T + n] : 0.f;
-      const float* e = p.epi == 1 ? p.resid : p.x;
+      const size_t obase = static_cast<size_t>(b) * ys + static_cast<size_t>(m_base) * Tout + to;
+      const float nz = (p.epi == 2 && ok) ? p.noise[static_cast<size_t>(b) * p.T + n] : 0.f;
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + c0, v);
+      tmem_ld_wait();
 #pragma unroll
-      for (int r = 0; r < 32; ++r)
-        ext[ch][r] = (p.epi != 0 && ok && r < rows) ? __ldcg(e + obase[ch] + static_cast<size_t>(r) * Tout) : 0.f;
-    }
-    const float bias_l = (p.bias && lane < rows) ? __ldg(&p.bias[m_base + lane]) : 0.f;
-    const float alpha_l = (p.alpha_out && lane < rows) ? __ldg(&p.alpha_out[m_base + lane]) : 1.f;
-    mbar_wait(tmem_full, 0);          // all MMAs done: the accumulator is complete and the ring is idle
-    tc_fence_after();
+      for (int c = 0; c < 32; ++c) st[lane * 33 + c] = __uint_as_float(v[c]);
+      __syncwarp();
+#pragma unroll 1
+      for (int r0 = 0; r0 < rows; r0 += 16) {
+        float ext[16];
 #pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      const int c0 = half * 64 + ch * 32;
-      if (col0 + c0 < p.n_total) {                 // warp-uniform
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c0, v);
-        tmem_ld_wait();
+        for (int i = 0; i < 16; ++i)
+          ext[i] = (p.epi != 0 && ok && r0 + i < rows) ? __ldcg(e + obase + static_cast<size_t>(r0 + i) * Tout) : 0.f;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) st[lane * 33 + c] = __uint_as_float(v[c]);
-        __syncwarp();
-#pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          const float bias_r = __shfl_sync(0xffffffffu, bias_l, r);
-          const float alpha_r = __shfl_sync(0xffffffffu, alpha_l, r);
-          if (okc[ch] && r < rows) {
+        for (int i = 0; i < 16; ++i) {
+          const int r = r0 + i;
+          const float bias_r = __shfl_sync(0xffffffffu, bias_l, r & 31);
+          const float alpha_r = __shfl_sync(0xffffffffu, alpha_l, r & 31);
+          if (ok && r < rows) {
             float val = st[r * 33 + lane] + bias_r;
-            if (p.epi == 1) val += ext[ch][r];
-            else if (p.epi == 2) val = ext[ch][r] + nz[ch] * val;
+            if (p.epi == 1) val += ext[i];
+            else if (p.epi == 2) val = ext[i] + nz * val;
             if (p.alpha_out) val = snake_tc(val, alpha_r);
-            p.y[obase[ch] + static_cast<size_t>(r) * Tout] = val;
+            p.y[obase + static_cast<size_t>(r) * Tout] = val;
           }
         }
-        __syncwarp();
       }
+      __syncwarp();
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, SM_TILE_N);
+  trace_end(tr);
 }
 
 // fp32 weights [phases][M][K] -> [phase][m_tile][k_block][hi|lo][128][32], swizzled; rows past M are zero
@@ -271,6 +288,7 @@ static int launch_snac_gemm(const SnacGemmParams& p, int phases, cudaStream_t st
 }
 
 }  // namespace vb
+VB_DEFINE_TRACE_SETTER(snac)
 
 using namespace vb;
 
