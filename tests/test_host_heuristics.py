@@ -66,3 +66,30 @@ def test_gate_up_tile_half_is_a_multiple_of_16():
         h = ops.gate_up_tile_half(inter, 148)
         assert h % 16 == 0 and 16 <= h <= 64
     assert ops.gate_up_tile_half(8192, 148) == 64
+
+
+def test_tf32_hi_lo_split_is_fp32_grade():
+    """The arithmetic identity behind vox_serve_b200/csrc/snac_mma.cu, emulated in numpy: x = hi + lo with hi = x with
+    the 13 low mantissa bits cleared (exactly representable in tf32), lo = x - hi (exact in fp32; the tensor core then
+    reads it with 10 mantissa bits).  lo_w*hi_x + hi_w*lo_x + hi_w*hi_x must reproduce the fp32 dot product to ~2^-20
+    of the operand scale, where hi_w*hi_x alone (plain tf32) is ~2^-11."""
+    rng = np.random.default_rng(0)
+
+    def tf32(a):      # what kind::tf32 keeps of an fp32 operand (truncation; hi parts are unaffected by the mode)
+        return (a.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+    K = 2048
+    w = (rng.standard_normal((64, K)) / np.sqrt(K)).astype(np.float32)
+    x = rng.standard_normal((K, 48)).astype(np.float32)
+    w_hi, x_hi = tf32(w), tf32(x)
+    w_lo, x_lo = tf32(w - w_hi), tf32(x - x_hi)
+    assert np.array_equal(w_hi + (w - w_hi), w) and np.array_equal(x_hi + (x - x_hi), x)      # the split is exact
+    exact = w.astype(np.float64) @ x.astype(np.float64)
+    f64 = lambda a: a.astype(np.float64)      # noqa: E731
+    split3 = f64(w_lo) @ f64(x_hi) + f64(w_hi) @ f64(x_lo) + f64(w_hi) @ f64(x_hi)
+    plain = f64(w_hi) @ f64(x_hi)
+    scale = np.sqrt((f64(w) ** 2).sum(1, keepdims=True) * (f64(x) ** 2).sum(0, keepdims=True))   # |w||x| per output
+    err3 = np.abs(split3 - exact) / scale
+    err1 = np.abs(plain - exact) / scale
+    assert err3.max() < 2.0 ** -19, err3.max()
+    assert err1.max() > 50 * err3.max()
