@@ -703,3 +703,49 @@ def test_snac_convtr_tensor_core_matches_fp32(ops, B, Cin, Cout, T, s, o_lo, o_h
         assert err < 2e-5, (name, err)
     # both kernels write the same superset of the requested slice
     assert torch.equal(y_tc == 7.0, y_32 == 7.0)
+
+
+# --------------------------------------------------------------------------------------------
+# size-independent properties at the full Orpheus / SNAC sizes (where the oracle is too slow to be the checker)
+# --------------------------------------------------------------------------------------------
+def test_sampler_full_vocab_degenerate_filters_pick_the_maximum(ops):
+    """32 rows x 156 940 logits with repetition penalty and temperature: a nucleus of ~0, top-k 1 and min-p 1 all
+    leave only the maximum (its tie group, which the filters keep whole), so whatever is drawn must carry the row's
+    largest penalised value; greedy must return the FIRST such index (torch.argmax)."""
+    B, V = 32, 156940
+    logits = (torch.randn(B, V, generator=g(31)) * 1.3).to(BF)
+    rep = torch.rand(B, 1, 1, V, generator=g(32)) < 0.01
+    pen, T = 1.3, 0.6
+    x = logits.float()
+    x = torch.where(rep[:, 0, 0], torch.where(x > 0, x / pen, x * pen), x).to(BF)       # sampling.py:143-144
+    xs = (x.float() / T).to(BF)
+    dl, dr = logits.cuda(), rep.cuda()
+    greedy = ops.sample(dl, "greedy", rep_cache=dr, penalty=pen).cpu()
+    assert torch.equal(greedy, torch.argmax(x.float(), dim=-1))
+    top = xs.float().max(dim=-1).values
+    for strategy, kw in (("top_p", dict(top_p=1e-6)), ("top_k", dict(top_k=1)), ("min_p", dict(min_p=1.0)),
+                         ("top_k_top_p", dict(top_k=1, top_p=0.5))):
+        ids = ops.sample(dl, strategy, rep_cache=dr, penalty=pen, temperature=T, seed=7, offset=3, **kw).cpu()
+        got = xs.float().gather(1, ids.view(B, 1)).view(B)
+        assert torch.equal(got, top), (strategy, (got != top).nonzero().flatten().tolist())
+
+
+def test_snac_decode_is_independent_of_the_batch(ops):
+    """Windows are independent: decoding three windows together (columns of all windows folded into the same GEMM
+    tiles) must give bit-identical audio to decoding each alone -- 24 kHz configuration, tensor-core and SIMT stages."""
+    from vox_serve_b200.tokenizer.snac import SNAC
+
+    cfg = osnac.SnacConfig()
+    m = SNAC(sampling_rate=cfg.sampling_rate, encoder_dim=cfg.encoder_dim, encoder_rates=cfg.encoder_rates,
+             decoder_dim=cfg.decoder_dim, decoder_rates=cfg.decoder_rates, codebook_size=cfg.codebook_size,
+             codebook_dim=cfg.codebook_dim, vq_strides=cfg.vq_strides)
+    m.load_state_dict(osnac.synth_state_dict(cfg, seed=5))
+    assert m.tc, "the 24 kHz configuration must use the tensor-core stages"
+    B = 3
+    codes = [torch.randint(0, cfg.codebook_size, (B, 4 * k), generator=g(41 + k)).cuda() for k in (1, 2, 4)]
+    noises = [torch.randn(s, generator=g(50 + i)).cuda() for i, s in enumerate(m.noise_shapes(B, 16))]
+    both = m.decode(codes, noises, out_range=(2048, 4096))
+    assert both.shape == (B, 1, 2048) and bool(torch.isfinite(both).all())
+    for b in range(B):
+        one = m.decode([c[b:b + 1] for c in codes], [n[b:b + 1] for n in noises], out_range=(2048, 4096))
+        assert torch.equal(one, both[b:b + 1]), b
