@@ -749,3 +749,37 @@ def test_snac_decode_is_independent_of_the_batch(ops):
     for b in range(B):
         one = m.decode([c[b:b + 1] for c in codes], [n[b:b + 1] for n in noises], out_range=(2048, 4096))
         assert torch.equal(one, both[b:b + 1]), b
+
+
+def test_paged_attention_is_invariant_to_physical_page_placement(ops):
+    """Batch 32 at Orpheus geometry with kv lengths up to ~1500: the same logical K/V scattered over two different
+    physical page assignments must give bit-identical outputs (the work partition only sees logical tiles)."""
+    B, hq, hkv, D, ps = 32, 24, 8, 128, 128
+    gen = g(61)
+    kv_lens = torch.randint(100, 1500, (B,), generator=gen).tolist()
+    n_req_pages = [(L + ps - 1) // ps for L in kv_lens]
+    n_pages = sum(n_req_pages) + 5
+    logical = [(torch.randn(n, 2, ps, hkv, D, generator=gen) * 0.8).to(BF) for n in n_req_pages]
+    q = torch.randn(B, hq, D, generator=gen).to(BF).cuda()
+    chunk = ops.attn_chunk_tokens(ps, hkv)
+    outs = []
+    for seed in (1, 2):
+        perm = torch.randperm(n_pages, generator=g(70 + seed)).tolist()
+        cache = torch.zeros(1, n_pages, 2, ps, hkv, D, dtype=BF)
+        indptr, indices, last = [0], [], []
+        for r in range(B):
+            pages = [perm.pop() for _ in range(n_req_pages[r])]
+            for j, pg in enumerate(pages):
+                cache[0, pg] = logical[r][j]
+            indices += pages
+            indptr.append(len(indices))
+            last.append(kv_lens[r] - (n_req_pages[r] - 1) * ps)
+        max_chunks = sum((L + chunk - 1) // chunk for L in kv_lens)
+        plan = ops.RowPlan(B, "cuda", max_chunks)
+        ops.plan_rows(plan, None, _i32(indptr), _i32(indices), _i32(last), B, B, ps, chunk)
+        ws = ops.paged_attn_workspace(B, max_chunks, hq, hkv, D, "cuda")
+        out = ops.paged_attn(q, cache.cuda(), 0, plan, B, hkv, ps, chunk, ws)
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(out.float()).all())
+        outs.append(out.cpu())
+    assert torch.equal(outs[0], outs[1])
