@@ -291,8 +291,62 @@ def golden_orpheus_e2e(ref):
     print("min top1-top2 margin over logged steps:", min(float((t[:, 1] - t[:, 0]).min()) for t in tops))
 
 
+def golden_cosyvoice2_lm():
+    """BASELINE.json configs[0] plumbing: the reference's ``CosyVoice2ForCausalLM`` (model/cosyvoice2.py:285-315) at
+    a tiny configuration on CPU -- prefill with ``inputs_embeds``, then greedy decode steps fed with
+    ``speech_embedding(id)`` -- through the paged CPU wrapper.  Stored: the prompt embeddings' seed, per-step logits
+    (fp32 copies of the bf16 outputs) and the greedy ids."""
+    from . import cosyvoice2 as ocv
+    from .ref_import import import_reference_cosyvoice2
+
+    mod = import_reference_cosyvoice2()
+    dims = ocv.CosyVoice2Dims.tiny()
+    cfg = mod.CosyVoice2Config(hidden_size=dims.hidden_size, intermediate_size=dims.intermediate_size,
+                               num_attention_heads=dims.num_attention_heads,
+                               num_key_value_heads=dims.num_key_value_heads,
+                               num_hidden_layers=dims.num_hidden_layers, vocab_size=dims.vocab_size,
+                               rope_theta=dims.rope_theta, rms_norm_eps=dims.rms_norm_eps)
+    cfg.llm_input_size = cfg.llm_output_size = dims.hidden_size
+    cfg.speech_token_size = dims.speech_token_size
+    weights = ocv.synth_weights(dims, seed=3)
+    lm = mod.CosyVoice2ForCausalLM(cfg)
+    lm.load_state_dict(weights, strict=True)
+    lm = lm.to(torch.bfloat16).eval()
+    page_size, T0, n_steps, seed = 16, 21, 14, 1        # 21 + 14 tokens cross two page boundaries
+    emb = torch.randn(T0, dims.hidden_size, generator=torch.Generator().manual_seed(seed)).to(torch.bfloat16)
+    n_pages = (T0 + n_steps + page_size - 1) // page_size + 1
+    kv = torch.zeros(dims.num_hidden_layers, n_pages, 2, page_size, dims.num_key_value_heads, dims.head_dim,
+                     dtype=torch.bfloat16)
+    pages = list(range((T0 + page_size - 1) // page_size))
+    with torch.no_grad():
+        pre = lm_ops.PagedWrapperCPU("prefill", page_size)
+        pre.plan([0, T0], [0, len(pages)], pages, [T0 - (len(pages) - 1) * page_size])
+        logits = lm(inputs_embeds=emb, position_ids=torch.arange(T0, dtype=torch.int32), attn_wrapper=pre,
+                    kv_cache=kv)[-1:]
+        ids, logs, kv_len = [], [logits[0].float().numpy()], T0
+        for _ in range(n_steps):
+            tok = int(torch.argmax(logits[0].float()))
+            ids.append(tok)
+            kv_len += 1
+            if (kv_len + page_size - 1) // page_size > len(pages):
+                pages.append(len(pages))
+            dec = lm_ops.PagedWrapperCPU("decode", page_size)
+            dec.plan([0, len(pages)], pages, [kv_len - (len(pages) - 1) * page_size])
+            step_emb = lm.embed_tokens_speech(torch.tensor([tok]))
+            logits = lm(inputs_embeds=step_emb, position_ids=torch.tensor([kv_len - 1], dtype=torch.int32),
+                        attn_wrapper=dec, kv_cache=kv)
+            logs.append(logits[0].float().numpy())
+    np.savez_compressed(os.path.join(OUT, "cosyvoice2_tiny_lm.npz"), ids=np.array(ids, dtype=np.int64),
+                        logits=np.stack(logs), prompt_seed=seed, prompt_len=T0, page_size=page_size, weight_seed=3)
+    tops = np.sort(np.stack(logs), axis=-1)[:, -2:]
+    print("cosyvoice2_tiny_lm.npz ids", ids, "min top1-top2 margin", float((tops[:, 1] - tops[:, 0]).min()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "cosyvoice2":
+        golden_cosyvoice2_lm()
+        return
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     ref = import_reference()
     orig_sync = torch.cuda.synchronize
@@ -301,6 +355,7 @@ def main():
         golden_sampler(ref)
         golden_snac(ref)
         golden_orpheus_e2e(ref)
+        golden_cosyvoice2_lm()
     finally:
         torch.cuda.synchronize = orig_sync
 

@@ -59,3 +59,34 @@ def import_reference():
     return types.SimpleNamespace(
         orpheus=ref_orpheus, sampling=ref_sampling, snac=ref_snac, requests=ref_requests,
         worker_base=ref_worker_base, graph_worker=ref_graph_worker, sched_base=ref_sched_base)
+
+
+def import_reference_cosyvoice2():
+    """The reference's ``vox_serve/model/cosyvoice2.py`` itself (``import_reference`` only stubs it): its LM classes
+    need nothing beyond torch, but the module imports librosa / onnxruntime / onnx at the top for the audio front end,
+    so those three are stubbed with empty modules.  ``rms_norm`` / ``apply_rope_pos_ids`` are re-pointed at the oracle
+    restatements as for Orpheus."""
+    import importlib
+
+    import_reference()
+
+    class _Any(types.ModuleType):
+        def __getattr__(self, k):
+            if k.startswith("__"):
+                raise AttributeError(k)
+            return type(k, (), {})
+
+    for name in ("librosa", "librosa.filters", "onnxruntime", "onnx"):
+        try:
+            importlib.import_module(name)
+        except Exception:
+            sys.modules[name] = _Any(name)
+    sys.modules.pop("vox_serve.model.cosyvoice2", None)
+    mod = importlib.import_module("vox_serve.model.cosyvoice2")
+    from . import lm_ops
+
+    mod.rms_norm = lambda hidden_states, weight, eps: lm_ops.rms_norm(hidden_states, weight, eps)
+    mod.apply_rope_pos_ids = (
+        lambda query_states, key_states, position_ids, **kw: lm_ops.apply_rope_pos_ids(
+            query_states, key_states, position_ids, **kw))
+    return mod

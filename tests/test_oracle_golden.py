@@ -95,3 +95,26 @@ def test_orpheus_tiny_end_to_end(golden_dir):
         assert audio.shape == g[f"audio{i}"].shape
         diff = np.abs(audio.astype(np.int32) - g[f"audio{i}"].astype(np.int32))
         assert diff.max() <= 1, (i, diff.max())
+
+
+def test_cosyvoice2_lm_oracle_matches_reference_golden(golden_dir):
+    """BASELINE.json configs[0] (CosyVoice2 speech LM, single prompt, greedy, CPU): oracle/cosyvoice2.py against the
+    logits and ids the reference's own CosyVoice2ForCausalLM produced (oracle/gen_golden.py:golden_cosyvoice2_lm) --
+    q/k/v bias, plain RoPE at theta 1e6, inputs_embeds prefill, speech-embedding feedback, biased llm_decoder, paged
+    KV growing across two page boundaries.  Same torch CPU kernels on both sides: bit-exact."""
+    from oracle import cosyvoice2 as ocv
+
+    gd = _load(golden_dir, "cosyvoice2_tiny_lm.npz")
+    dims = ocv.CosyVoice2Dims.tiny()
+    w = ocv.synth_weights(dims, seed=int(gd["weight_seed"]))
+    emb = torch.randn(int(gd["prompt_len"]), dims.hidden_size,
+                      generator=torch.Generator().manual_seed(int(gd["prompt_seed"]))).to(torch.bfloat16)
+    out = ocv.greedy_decode(w, dims, emb, len(gd["ids"]), page_size=int(gd["page_size"]), stop_ids=[])
+    assert out["ids"] == gd["ids"].tolist()
+    got = torch.stack(out["logits"]).numpy()
+    assert got.shape == gd["logits"].shape
+    assert np.array_equal(got, gd["logits"])
+    # the full-size dims are the reference's (cosyvoice2.py:26-38)
+    full = ocv.CosyVoice2Dims()
+    assert (full.hidden_size, full.num_hidden_layers, full.num_attention_heads, full.num_key_value_heads,
+            full.head_dim, full.intermediate_size, full.speech_vocab) == (896, 24, 14, 2, 64, 4864, 6564)
