@@ -4,7 +4,9 @@
 // (or, for the residual stream, into the depthwise conv's tile load), so the decoder is
 //   from_codes -> dwconv7 -> pwconv(+snake) -> 4 x [ convtr -> pwconv(noise) -> 3 x (dwconv7(snake in,
 //   snake out) -> pwconv(+residual[, +snake])) ] -> final conv7 + tanh.
-// The two GEMM-shaped stages (1x1 convs, transposed convs) share one register-tiled fp32 kernel.
+// The two GEMM-shaped stages (1x1 convs, transposed convs) share one register-tiled fp32 kernel here; layers with at
+// least 128 input channels (a multiple of 32) run on the tensor cores instead (snac_mma.cu, tf32 hi/lo split), the
+// caller chooses per layer (vox_serve_b200/tokenizer/snac.py).
 #include "../../include/vb_api.h"
 #include "common.cuh"
 
