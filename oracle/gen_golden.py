@@ -342,10 +342,67 @@ def golden_cosyvoice2_lm():
     print("cosyvoice2_tiny_lm.npz ids", ids, "min top1-top2 margin", float((tops[:, 1] - tops[:, 0]).min()))
 
 
+def golden_glm_voice_lm():
+    """BASELINE.json configs[4]'s decoder: the reference's ``GLMVoiceForCausalLM`` (model/glm_voice.py:281-304) at a
+    tiny configuration on CPU -- fused biased QKV, interleaved partial RoPE, fused SwiGLU -- prefill on prompt ids,
+    then greedy decode steps through the paged CPU wrapper."""
+    import importlib
+
+    from . import glm_voice as oglm
+
+    import_reference()
+    mod = importlib.import_module("vox_serve.model.glm_voice")
+    mod.rms_norm = lambda hidden_states, weight, eps: lm_ops.rms_norm(hidden_states, weight, eps)
+    mod.apply_rope_pos_ids = (
+        lambda query_states, key_states, position_ids, **kw: lm_ops.apply_rope_pos_ids(
+            query_states, key_states, position_ids, **kw))
+    dims = oglm.GLMVoiceDims.tiny()
+    cfg = mod.GLMVoiceConfig(ffn_hidden_size=dims.ffn_hidden_size, hidden_size=dims.hidden_size,
+                             layernorm_epsilon=dims.layernorm_epsilon,
+                             multi_query_group_num=dims.multi_query_group_num,
+                             num_attention_heads=dims.num_attention_heads, num_hidden_layers=dims.num_layers,
+                             num_layers=dims.num_layers, padded_vocab_size=dims.padded_vocab_size,
+                             vocab_size=dims.padded_vocab_size, rope_ratio=int(dims.rope_ratio))
+    weights = oglm.synth_weights(dims, seed=4)
+    lm = mod.GLMVoiceForCausalLM(cfg)
+    lm.load_state_dict(weights, strict=True)
+    lm = lm.to(torch.bfloat16).eval()
+    page_size, T0, n_steps, seed = 16, 27, 12, 2           # 27 + 12 tokens cross two page boundaries
+    prompt = torch.randint(0, dims.padded_vocab_size, (T0,), generator=torch.Generator().manual_seed(seed))
+    n_pages = (T0 + n_steps + page_size - 1) // page_size + 1
+    kv = torch.zeros(dims.num_layers, n_pages, 2, page_size, dims.multi_query_group_num, dims.head_dim,
+                     dtype=torch.bfloat16)
+    pages = list(range((T0 + page_size - 1) // page_size))
+    with torch.no_grad():
+        pre = lm_ops.PagedWrapperCPU("prefill", page_size)
+        pre.plan([0, T0], [0, len(pages)], pages, [T0 - (len(pages) - 1) * page_size])
+        logits = lm(inputs_embeds=lm.embed_tokens(prompt), position_ids=torch.arange(T0, dtype=torch.int32),
+                    attn_wrapper=pre, kv_cache=kv)[-1:]
+        ids, logs, kv_len = [], [logits[0].float().numpy()], T0
+        for _ in range(n_steps):
+            tok = int(torch.argmax(logits[0].float()))
+            ids.append(tok)
+            kv_len += 1
+            if (kv_len + page_size - 1) // page_size > len(pages):
+                pages.append(len(pages))
+            dec = lm_ops.PagedWrapperCPU("decode", page_size)
+            dec.plan([0, len(pages)], pages, [kv_len - (len(pages) - 1) * page_size])
+            logits = lm(inputs_embeds=lm.embed_tokens(torch.tensor([tok])),
+                        position_ids=torch.tensor([kv_len - 1], dtype=torch.int32), attn_wrapper=dec, kv_cache=kv)
+            logs.append(logits[0].float().numpy())
+    np.savez_compressed(os.path.join(OUT, "glm_voice_tiny_lm.npz"), ids=np.array(ids, dtype=np.int64),
+                        logits=np.stack(logs), prompt=prompt.numpy(), page_size=page_size, weight_seed=4)
+    tops = np.sort(np.stack(logs), axis=-1)[:, -2:]
+    print("glm_voice_tiny_lm.npz ids", ids, "min top1-top2 margin", float((tops[:, 1] - tops[:, 0]).min()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "cosyvoice2":
         golden_cosyvoice2_lm()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "glm_voice":
+        golden_glm_voice_lm()
         return
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     ref = import_reference()
@@ -356,6 +413,7 @@ def main():
         golden_snac(ref)
         golden_orpheus_e2e(ref)
         golden_cosyvoice2_lm()
+        golden_glm_voice_lm()
     finally:
         torch.cuda.synchronize = orig_sync
 

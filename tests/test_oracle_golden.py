@@ -118,3 +118,20 @@ def test_cosyvoice2_lm_oracle_matches_reference_golden(golden_dir):
     full = ocv.CosyVoice2Dims()
     assert (full.hidden_size, full.num_hidden_layers, full.num_attention_heads, full.num_key_value_heads,
             full.head_dim, full.intermediate_size, full.speech_vocab) == (896, 24, 14, 2, 64, 4864, 6564)
+
+
+def test_glm_voice_lm_oracle_matches_reference_golden(golden_dir):
+    """BASELINE.json configs[4]'s decoder (GLM-4-Voice): oracle/glm_voice.py against the logits and ids of the
+    reference's own GLMVoiceForCausalLM on CPU (oracle/gen_golden.py:golden_glm_voice_lm) -- fused biased QKV,
+    interleaved RoPE on half of head_dim, fused SwiGLU, paged KV growing across two page boundaries.  Bit-exact."""
+    from oracle import glm_voice as oglm
+
+    gd = _load(golden_dir, "glm_voice_tiny_lm.npz")
+    dims = oglm.GLMVoiceDims.tiny()
+    w = oglm.synth_weights(dims, seed=int(gd["weight_seed"]))
+    out = oglm.greedy_decode(w, dims, torch.from_numpy(gd["prompt"]), len(gd["ids"]), page_size=int(gd["page_size"]))
+    assert out["ids"] == gd["ids"].tolist()
+    assert np.array_equal(torch.stack(out["logits"]).numpy(), gd["logits"])
+    full = oglm.GLMVoiceDims()       # the reference's dims (glm_voice.py:22-54)
+    assert (full.hidden_size, full.num_layers, full.num_attention_heads, full.multi_query_group_num, full.head_dim,
+            full.ffn_hidden_size, full.padded_vocab_size) == (4096, 40, 32, 2, 128, 13696, 168960)
