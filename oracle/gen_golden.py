@@ -396,8 +396,122 @@ def golden_glm_voice_lm():
     print("glm_voice_tiny_lm.npz ids", ids, "min top1-top2 margin", float((tops[:, 1] - tops[:, 0]).min()))
 
 
+def golden_csm_frames():
+    """BASELINE.json configs[3] / SURVEY row a24: the reference's ``CsmBackboneModel``, ``CsmDepthDecoderForCausalLM``
+    and ``CsmCodebooksHead`` (model/csm.py:171-272) at a tiny configuration on CPU, driven the way
+    ``CSMModel.forward / sampling / depth_sampling`` (:637-769) and ``CudaGraphWorker.run_lm_depth``
+    (cuda_graph_worker.py:1058-1160) drive them: backbone prefill on a text + audio prompt, then greedy frames --
+    codebook 0 from the backbone, the 2-row depth prefill and the 1-row depth decodes on a zeroed per-frame cache."""
+    import importlib
+
+    from torch import nn
+    from transformers import CsmConfig
+
+    from . import csm as ocsm
+
+    import_reference()
+    mod = importlib.import_module("vox_serve.model.csm")
+    mod.rms_norm = lambda hidden_states, weight, eps: lm_ops.rms_norm(hidden_states, weight, eps)
+    mod.apply_rope_pos_ids = (
+        lambda query_states, key_states, position_ids, **kw: lm_ops.apply_rope_pos_ids(
+            query_states, key_states, position_ids, **kw))
+    d = ocsm.CsmDims.tiny()
+    dcfg = dict(num_codebooks=d.num_codebooks, vocab_size=d.vocab_size, backbone_hidden_size=d.hidden_size,
+                hidden_size=d.depth_hidden_size, intermediate_size=d.depth_intermediate_size,
+                num_hidden_layers=d.depth_num_hidden_layers, num_attention_heads=d.depth_num_attention_heads,
+                num_key_value_heads=d.depth_num_key_value_heads, head_dim=d.depth_head_dim, rms_norm_eps=d.rms_norm_eps)
+    cfg = CsmConfig(num_codebooks=d.num_codebooks, vocab_size=d.vocab_size, text_vocab_size=d.text_vocab_size,
+                    hidden_size=d.hidden_size, intermediate_size=d.intermediate_size,
+                    num_hidden_layers=d.num_hidden_layers, num_attention_heads=d.num_attention_heads,
+                    num_key_value_heads=d.num_key_value_heads, head_dim=d.head_dim, rms_norm_eps=d.rms_norm_eps,
+                    depth_decoder_config=dcfg)
+    for c in (cfg, cfg.depth_decoder_config):       # transformers 5.x keeps theta inside rope_parameters (SURVEY 8c)
+        c.rope_theta = d.rope_theta
+    w = ocsm.synth_weights(d, seed=6)
+    backbone = mod.CsmBackboneModel(cfg)
+    depth = mod.CsmDepthDecoderForCausalLM(cfg.depth_decoder_config)
+    lm_head = nn.Linear(d.hidden_size, d.vocab_size, bias=False)
+    text_emb = nn.Embedding(d.text_vocab_size, d.hidden_size)
+    backbone.load_state_dict({k[len("backbone_model."):]: v for k, v in w.items() if k.startswith("backbone_model.")},
+                             strict=True)
+    depth.load_state_dict({k[len("depth_decoder."):]: v for k, v in w.items() if k.startswith("depth_decoder.")},
+                          strict=True)
+    lm_head.load_state_dict({"weight": w["lm_head.weight"]})
+    text_emb.load_state_dict({"weight": w["embed_text_tokens.weight"]})
+    for m_ in (backbone, depth, lm_head, text_emb):
+        m_.to(torch.bfloat16).eval()
+    N, V = d.num_codebooks, d.vocab_size
+    g = torch.Generator().manual_seed(3)
+    T0, n_text, n_frames, page_size, depth_page = 19, 12, 5, 16, 32
+    ids = torch.zeros(T0, N + 1, dtype=torch.long)
+    masks = torch.zeros(T0, N + 1, dtype=torch.bool)
+    ids[:n_text, -1] = torch.randint(0, d.text_vocab_size, (n_text,), generator=g)
+    masks[:n_text, -1] = True
+    ids[n_text:, :-1] = torch.randint(0, V, (T0 - n_text, N), generator=g)
+    masks[n_text:, :-1] = True
+
+    def embeds(row_ids, row_masks):          # CSMModel.forward, csm.py:647-654
+        e = torch.cat([backbone.embed_tokens(row_ids[:, :-1]), text_emb(row_ids[:, -1:])], dim=1)
+        return (e * row_masks[:, :, None]).sum(dim=1)
+
+    def single(tok, i):                      # embed_audio_tokens_single, csm.py:456-458
+        return backbone.embed_tokens.embed_audio_tokens(tok + i * V)
+
+    n_pages = (T0 + n_frames + page_size - 1) // page_size + 1
+    kv = torch.zeros(d.num_hidden_layers, n_pages, 2, page_size, d.num_key_value_heads, d.head_dim, dtype=torch.bfloat16)
+    dkv = torch.zeros(d.depth_num_hidden_layers, 1, 2, depth_page, d.depth_num_key_value_heads, d.depth_head_dim,
+                      dtype=torch.bfloat16)
+    pages = list(range((T0 + page_size - 1) // page_size))
+    frames, cb0_logits, depth_logits = [], [], []
+    with torch.no_grad():
+        pre = lm_ops.PagedWrapperCPU("prefill", page_size)
+        pre.plan([0, T0], [0, len(pages)], pages, [T0 - (len(pages) - 1) * page_size])
+        hidden = backbone(embeds(ids, masks), torch.arange(T0, dtype=torch.int32), pre, kv)
+        logits, hidden = lm_head(hidden)[-1], hidden[-1]
+        kv_len = T0
+        dmask = torch.ones(1, N + 1, dtype=torch.bool)
+        dmask[0, -1] = False
+        for _ in range(n_frames):
+            cb0_logits.append(logits.float().numpy())
+            cb0 = torch.argmax(logits.float()).view(1)
+            frame, dl = [int(cb0)], []
+            dkv.zero_()                                                                   # :1076
+            x = torch.cat([hidden[None, None, :], single(cb0, 0)[:, None, :]], dim=1).view(2, -1)   # :701-702
+            dpre = lm_ops.PagedWrapperCPU("prefill", depth_page)
+            dpre.plan([0, 2], [0, 1], [0], [2])
+            pos = torch.tensor([0, 1], dtype=torch.int32)
+            out = depth.codebooks_head(depth(x, pos, dpre, dkv), cache_position=pos)[-1:]
+            for i in range(1, N):
+                dl.append(out[0].float().numpy())
+                tok = torch.argmax(out[0].float()).view(1)
+                frame.append(int(tok))
+                if i == N - 1:
+                    break
+                ddec = lm_ops.PagedWrapperCPU("decode", depth_page)
+                ddec.plan([0, 1], [0], [i + 2])
+                pos = torch.tensor([i + 1], dtype=torch.int32)
+                out = depth.codebooks_head(depth(single(tok, i), pos, ddec, dkv), cache_position=pos)
+            frames.append(frame)
+            depth_logits.append(np.stack(dl))
+            kv_len += 1
+            if (kv_len + page_size - 1) // page_size > len(pages):
+                pages.append(len(pages))
+            dec = lm_ops.PagedWrapperCPU("decode", page_size)
+            dec.plan([0, len(pages)], pages, [kv_len - (len(pages) - 1) * page_size])
+            row = torch.tensor([frame + [0]], dtype=torch.long)
+            hidden = backbone(embeds(row, dmask), torch.tensor([kv_len - 1], dtype=torch.int32), dec, kv)
+            logits, hidden = lm_head(hidden)[0], hidden[0]
+    np.savez_compressed(os.path.join(OUT, "csm_tiny_frames.npz"), frames=np.array(frames, dtype=np.int64),
+                        cb0_logits=np.stack(cb0_logits), depth_logits=np.stack(depth_logits), prompt_ids=ids.numpy(),
+                        prompt_masks=masks.numpy(), page_size=page_size, weight_seed=6)
+    print("csm_tiny_frames.npz frames", frames)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "csm":
+        golden_csm_frames()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "cosyvoice2":
         golden_cosyvoice2_lm()
         return
@@ -414,6 +528,7 @@ def main():
         golden_orpheus_e2e(ref)
         golden_cosyvoice2_lm()
         golden_glm_voice_lm()
+        golden_csm_frames()
     finally:
         torch.cuda.synchronize = orig_sync
 

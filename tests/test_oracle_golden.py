@@ -135,3 +135,20 @@ def test_glm_voice_lm_oracle_matches_reference_golden(golden_dir):
     full = oglm.GLMVoiceDims()       # the reference's dims (glm_voice.py:22-54)
     assert (full.hidden_size, full.num_layers, full.num_attention_heads, full.multi_query_group_num, full.head_dim,
             full.ffn_hidden_size, full.padded_vocab_size) == (4096, 40, 32, 2, 128, 13696, 168960)
+
+
+def test_csm_depth_loop_oracle_matches_reference_golden(golden_dir):
+    """BASELINE.json configs[3] / SURVEY row a24 (the first "next" row): oracle/csm.py -- masked multi-codebook frame
+    embedding, Llama-style backbone, 2-row depth prefill + 1-row depth decodes with the per-position codebook heads on
+    a per-frame cache -- against the reference's own CsmBackboneModel / CsmDepthDecoderForCausalLM / CsmCodebooksHead
+    on CPU (oracle/gen_golden.py:golden_csm_frames).  All ids and all logits bit-exact over 5 frames x 8 codebooks."""
+    from oracle import csm as ocsm
+
+    gd = _load(golden_dir, "csm_tiny_frames.npz")
+    dims = ocsm.CsmDims.tiny()
+    w = ocsm.synth_weights(dims, seed=int(gd["weight_seed"]))
+    out = ocsm.generate_frames(w, dims, torch.from_numpy(gd["prompt_ids"]), torch.from_numpy(gd["prompt_masks"]),
+                               len(gd["frames"]), page_size=int(gd["page_size"]))
+    assert out["frames"] == gd["frames"].tolist()
+    assert np.array_equal(torch.stack(out["cb0_logits"]).numpy(), gd["cb0_logits"])
+    assert np.array_equal(torch.stack(out["depth_logits"]).numpy(), gd["depth_logits"])
