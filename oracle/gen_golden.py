@@ -507,8 +507,107 @@ def golden_csm_frames():
     print("csm_tiny_frames.npz frames", frames)
 
 
+def golden_qwen3_tts_frames():
+    """BASELINE.json configs[2] / SURVEY row a24: the reference's ``Qwen3TTSTalkerForConditionalGeneration`` (talker,
+    text projection, codec head, code predictor; model/qwen3_tts.py:707-833) at a tiny configuration on CPU, driven
+    through ``Qwen3TTSForCausalLM.forward / forward_depth`` (:906-944, called unbound on a namespace holding the
+    talker) with the glue of ``Qwen3TTSModel.forward / sampling / depth_sampling`` (:1805-2004) and the worker's
+    depth loop (cuda_graph_worker.py:1058-1160)."""
+    from . import qwen3_tts as oq
+    from .ref_import import import_reference_qwen3_tts
+
+    mod = import_reference_qwen3_tts()
+    d = oq.Qwen3TTSDims.tiny()
+    cp = mod.Qwen3TTSCodePredictorConfig(head_dim=d.cp_head_dim, hidden_size=d.cp_hidden_size,
+                                         intermediate_size=d.cp_intermediate_size,
+                                         num_attention_heads=d.cp_num_attention_heads,
+                                         num_code_groups=d.num_code_groups, num_hidden_layers=d.cp_num_hidden_layers,
+                                         num_key_value_heads=d.cp_num_key_value_heads, rms_norm_eps=d.rms_norm_eps,
+                                         rope_theta=int(d.rope_theta), vocab_size=d.cp_vocab_size)
+    tk = mod.Qwen3TTSTalkerConfig(code_predictor_config=cp, head_dim=d.head_dim, hidden_size=d.hidden_size,
+                                  intermediate_size=d.intermediate_size, num_attention_heads=d.num_attention_heads,
+                                  num_code_groups=d.num_code_groups, num_hidden_layers=d.num_hidden_layers,
+                                  num_key_value_heads=d.num_key_value_heads, rms_norm_eps=d.rms_norm_eps,
+                                  rope_theta=int(d.rope_theta), text_hidden_size=d.text_hidden_size,
+                                  text_vocab_size=d.text_vocab_size, vocab_size=d.vocab_size)
+    w = oq.synth_weights(d, seed=8)
+    talker = mod.Qwen3TTSTalkerForConditionalGeneration(tk)
+    r = talker.load_state_dict({k[len("talker."):]: v for k, v in w.items()}, strict=False)
+    assert not r.unexpected_keys and r.missing_keys == ["code_predictor.lm_head_weight"], (r.missing_keys, r.unexpected_keys)
+    talker = talker.to(torch.bfloat16).eval()
+    talker.code_predictor.lm_head_weight = torch.stack([h.weight.detach() for h in talker.code_predictor.lm_head], 0)
+    lm = types.SimpleNamespace(talker=talker)                        # what Qwen3TTSForCausalLM.forward* use of self
+    fwd, fwd_depth = mod.Qwen3TTSForCausalLM.forward, mod.Qwen3TTSForCausalLM.forward_depth
+    N = d.num_code_groups
+    g = torch.Generator().manual_seed(5)
+    T0, n_frames, page_size, depth_page = 18, 5, 16, 32
+    text = torch.randint(0, d.text_vocab_size, (T0,), generator=g)
+    cb0p = torch.randint(0, d.vocab_size, (T0,), generator=g)
+    need = torch.zeros(T0, dtype=torch.bool)
+    need[10:] = True
+    feat = torch.zeros(T0, d.hidden_size, dtype=torch.bfloat16)
+    feat[3] = torch.randn(d.hidden_size, generator=g).to(torch.bfloat16)      # a speaker-embedding position
+
+    def embeds(text_ids, cb0_ids, needs_codec, feats):                # Qwen3TTSModel.forward :1835-1853
+        t = talker.text_projection(talker.model.text_embedding(text_ids))
+        c = talker.model.codec_embedding(cb0_ids)
+        return torch.where(needs_codec.unsqueeze(-1), t + c, t) + feats
+
+    n_pages = (T0 + n_frames + page_size - 1) // page_size + 1
+    kv = torch.zeros(d.num_hidden_layers, n_pages, 2, page_size, d.num_key_value_heads, d.head_dim, dtype=torch.bfloat16)
+    dkv = torch.zeros(d.cp_num_hidden_layers, 1, 2, depth_page, d.cp_num_key_value_heads, d.cp_head_dim,
+                      dtype=torch.bfloat16)
+    pages = list(range((T0 + page_size - 1) // page_size))
+    frames, cb0_logits, cp_logits = [], [], []
+    with torch.no_grad():
+        pre = lm_ops.PagedWrapperCPU("prefill", page_size)
+        pre.plan([0, T0], [0, len(pages)], pages, [T0 - (len(pages) - 1) * page_size])
+        logits, hidden = fwd(lm, embeds(text, cb0p, need, feat), torch.arange(T0, dtype=torch.int32), pre, kv)
+        logits, hidden = logits[-1], hidden[-1]
+        kv_len = T0
+        for _ in range(n_frames):
+            cb0_logits.append(logits.float().numpy())
+            cb0 = torch.argmax(logits.float()).view(1)
+            frame, cl = [int(cb0)], []
+            dkv.zero_()
+            x = torch.cat([hidden[None, None, :], talker.model.codec_embedding(cb0)[:, None, :]], dim=1).view(2, -1)
+            dpre = lm_ops.PagedWrapperCPU("prefill", depth_page)
+            dpre.plan([0, 2], [0, 1], [0], [2])
+            out = fwd_depth(lm, x, torch.tensor([0, 1], dtype=torch.int32), dpre, dkv)[-1:]
+            in_feat = torch.zeros(1, d.hidden_size, dtype=torch.bfloat16)          # :1942
+            for i in range(1, N):
+                cl.append(out[0].float().numpy())
+                tok = torch.argmax(out[0].float()).view(1)
+                frame.append(int(tok))
+                ci = talker.code_predictor.model.codec_embedding[i - 1](tok)       # depth_sampling :1995
+                in_feat[:] += ci                                                   # :2002
+                if i == N - 1:
+                    break
+                ddec = lm_ops.PagedWrapperCPU("decode", depth_page)
+                ddec.plan([0, 1], [0], [i + 2])
+                out = fwd_depth(lm, ci, torch.tensor([i + 1], dtype=torch.int32), ddec, dkv)
+            frames.append(frame)
+            cp_logits.append(np.stack(cl))
+            kv_len += 1
+            if (kv_len + page_size - 1) // page_size > len(pages):
+                pages.append(len(pages))
+            dec = lm_ops.PagedWrapperCPU("decode", page_size)
+            dec.plan([0, len(pages)], pages, [kv_len - (len(pages) - 1) * page_size])
+            e = embeds(torch.tensor([d.tts_pad_token_id]), cb0, torch.tensor([True]), in_feat)
+            logits, hidden = fwd(lm, e, torch.tensor([kv_len - 1], dtype=torch.int32), dec, kv)
+            logits, hidden = logits[0], hidden[0]
+    np.savez_compressed(os.path.join(OUT, "qwen3_tts_tiny_frames.npz"), frames=np.array(frames, dtype=np.int64),
+                        cb0_logits=np.stack(cb0_logits), cp_logits=np.stack(cp_logits), text=text.numpy(),
+                        cb0=cb0p.numpy(), needs_codec=need.numpy(), features=feat.float().numpy(),
+                        page_size=page_size, weight_seed=8)
+    print("qwen3_tts_tiny_frames.npz frames", frames)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "qwen3_tts":
+        golden_qwen3_tts_frames()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "csm":
         golden_csm_frames()
         return
@@ -529,6 +628,7 @@ def main():
         golden_cosyvoice2_lm()
         golden_glm_voice_lm()
         golden_csm_frames()
+        golden_qwen3_tts_frames()
     finally:
         torch.cuda.synchronize = orig_sync
 

@@ -90,3 +90,32 @@ def import_reference_cosyvoice2():
         lambda query_states, key_states, position_ids, **kw: lm_ops.apply_rope_pos_ids(
             query_states, key_states, position_ids, **kw))
     return mod
+
+
+def import_reference_qwen3_tts():
+    """The reference's ``vox_serve/model/qwen3_tts.py`` itself (``import_reference`` only stubs it): only librosa is
+    missing here, and only its audio front end uses it."""
+    import importlib
+
+    import_reference()
+
+    class _Any(types.ModuleType):
+        def __getattr__(self, k):
+            if k.startswith("__"):
+                raise AttributeError(k)
+            return type(k, (), {})
+
+    for name in ("librosa", "librosa.filters"):
+        try:
+            importlib.import_module(name)
+        except Exception:
+            sys.modules[name] = _Any(name)
+    sys.modules.pop("vox_serve.model.qwen3_tts", None)
+    mod = importlib.import_module("vox_serve.model.qwen3_tts")
+    from . import lm_ops
+
+    mod.rms_norm = lambda hidden_states, weight, eps: lm_ops.rms_norm(hidden_states, weight, eps)
+    mod.apply_rope_pos_ids = (
+        lambda query_states, key_states, position_ids, **kw: lm_ops.apply_rope_pos_ids(
+            query_states, key_states, position_ids, **kw))
+    return mod

@@ -152,3 +152,24 @@ def test_csm_depth_loop_oracle_matches_reference_golden(golden_dir):
     assert out["frames"] == gd["frames"].tolist()
     assert np.array_equal(torch.stack(out["cb0_logits"]).numpy(), gd["cb0_logits"])
     assert np.array_equal(torch.stack(out["depth_logits"]).numpy(), gd["depth_logits"])
+
+
+def test_qwen3_tts_frame_oracle_matches_reference_golden(golden_dir):
+    """BASELINE.json configs[2] / SURVEY row a24: oracle/qwen3_tts.py -- q/k RMSNorm per head before a plain RoPE,
+    text-projection MLP + codec embedding + input_features as the talker input, code predictor with the head chosen by
+    the largest depth position, the sum of the predictor embeddings fed back -- against the reference's own talker and
+    code predictor on CPU (oracle/gen_golden.py:golden_qwen3_tts_frames).  5 frames x 6 codebooks, bit-exact."""
+    from oracle import qwen3_tts as oq
+
+    gd = _load(golden_dir, "qwen3_tts_tiny_frames.npz")
+    d = oq.Qwen3TTSDims.tiny()
+    w = oq.synth_weights(d, seed=int(gd["weight_seed"]))
+    out = oq.generate_frames(w, d, torch.from_numpy(gd["text"]), torch.from_numpy(gd["cb0"]),
+                             torch.from_numpy(gd["needs_codec"]), torch.from_numpy(gd["features"]).to(torch.bfloat16),
+                             len(gd["frames"]), page_size=int(gd["page_size"]))
+    assert out["frames"] == gd["frames"].tolist()
+    assert np.array_equal(torch.stack(out["cb0_logits"]).numpy(), gd["cb0_logits"])
+    assert np.array_equal(torch.stack(out["cp_logits"]).numpy(), gd["cp_logits"])
+    full = oq.Qwen3TTSDims()         # the reference's defaults (qwen3_tts.py:113-253)
+    assert (full.hidden_size, full.num_hidden_layers, full.num_code_groups, full.cp_hidden_size,
+            full.cp_num_hidden_layers, full.vocab_size, full.cp_vocab_size) == (2048, 28, 16, 1024, 5, 3072, 2048)
