@@ -21,6 +21,10 @@ Pinning status per piece
     ``pyproject.toml:36``, 0.6.11.post2 installed here): CUDA-only, cannot execute in the authoring
     container.  Restated from the installed headers (``include/flashinfer/norm.cuh:64-101``,
     ``pos_enc.cuh:594-617,1538-1539``) and cross-checked against FlashInfer itself on the GPU box
-    by ``tests/test_flashinfer_xcheck.py`` (skipped when FlashInfer's JIT is unavailable).
-    Until that test has run green these three ops are "parity unpinned".
+    by ``tests/test_gpu_flashinfer_xcheck.py`` (skipped when FlashInfer's JIT is unavailable): green on the B200
+    (5 tests), so these three ops are pinned there.
+  * the other BASELINE.json configs' language models (groundwork for the rows SURVEY.md 8f marks "next"; no CUDA
+    path serves them yet): ``cosyvoice2.py`` (configs[0]), ``glm_voice.py`` (configs[4]), ``csm.py`` (configs[3],
+    backbone + depth-transformer loop), ``qwen3_tts.py`` (configs[2], talker + code predictor) -- each PINNED bit for
+    bit to a golden file produced by the reference's own modules on CPU (``gen_golden.py``).
 """
