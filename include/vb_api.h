@@ -217,7 +217,8 @@ int vb_qkv_rope_append(void* d_q_out, void* d_layer_kv, const float* d_partials,
  * in Python every step, worker/base.py:312-325, orpheus.py:447-458):
  *   vb_decode_advance:  kv_len[b] += 1, position[b] += 1 for active rows (d_active NULL = all);
  *   vb_token_feedback:  sampled id of batch row b (int64) -> slot s = d_slots[b] (NULL = b):
- *                       next_input[s] = id; history[s][n_out[s] % cap] = id; ++n_out[s];
+ *                       next_input[s] = id; unless id == skip_token (the stop id, -1 = none: it is fed back but is
+ *                       not an audio token, orpheus.py:461-463): history[s][n_out[s] % cap] = id; ++n_out[s];
  *   vb_gather_i32:      out[i] = src[idx[i]] (next step's input ids by slot);
  *   vb_build_input_ids: out[i] = row_slot[i] >= 0 ? next_input[row_slot[i]] : host_ids[i]  (decode rows feed
  *                       back the id sampled last step, prefill rows use the uploaded prompt ids; replaces the
@@ -227,7 +228,7 @@ int vb_qkv_rope_append(void* d_q_out, void* d_layer_kv, const float* d_partials,
  *                       (the detokenize window of cuda_graph_worker.py:1176-1190 incl. last-token padding). */
 int vb_decode_advance(int32_t* d_kv_len, int32_t* d_pos, const int32_t* d_active, int B, void* stream);
 int vb_token_feedback(const int64_t* d_ids, const int32_t* d_slots, int32_t* d_next_input, int32_t* d_history,
-                      int32_t* d_n_out, int B, int history_cap, void* stream);
+                      int32_t* d_n_out, int B, int history_cap, int skip_token, void* stream);
 int vb_gather_i32(int32_t* d_out, const int32_t* d_src, const int32_t* d_idx, int n, void* stream);
 int vb_build_input_ids(int32_t* d_out, const int32_t* d_host_ids, const int32_t* d_next_input,
                        const int32_t* d_row_slot, int n, void* stream);

@@ -13,7 +13,9 @@ import torch
 from oracle import orpheus as oorph, sampler as osampler, snac as osnac, worker as oworker
 
 
-def build_models(dims, snac_cfg, seed, max_bs, page_size, max_pages, greedy=True, lm_head_scale=8.0):
+def build_models(dims, snac_cfg, seed, max_bs, page_size, max_pages, greedy=True, lm_head_scale=8.0, stop_boost=None):
+    """stop_boost: scale of the stop id's lm_head row; with it the stop id is NOT masked (it wins the greedy argmax
+    every ~10-20 steps), so the stop / trim / release paths run (orpheus.py:456-466, cuda_graph_worker.py:1176-1277)."""
     from vox_serve_b200.engine import LlamaDims
     from vox_serve_b200.model.orpheus import OrpheusModel
     from vox_serve_b200.sampling import SamplingConfig
@@ -21,6 +23,8 @@ def build_models(dims, snac_cfg, seed, max_bs, page_size, max_pages, greedy=True
     from vox_serve_b200.worker import ModelWorker
 
     weights = oorph.synth_weights(dims, seed=seed, lm_head_scale=lm_head_scale)
+    if stop_boost is not None:
+        weights["lm_head.weight"][dims.stop_token_id] *= stop_boost
     snac_sd = osnac.synth_state_dict(snac_cfg, seed=seed + 1)
     ld = LlamaDims(dims.hidden_size, dims.num_hidden_layers, dims.num_attention_heads, dims.num_key_value_heads,
                    dims.head_dim, dims.intermediate_size, dims.vocab_size, dims.rms_norm_eps, dims.rope_theta,
@@ -31,7 +35,7 @@ def build_models(dims, snac_cfg, seed, max_bs, page_size, max_pages, greedy=True
                 codebook_dim=snac_cfg.codebook_dim, vq_strides=snac_cfg.vq_strides, device="cuda")
     snac.load_state_dict(snac_sd)
     model = OrpheusModel("orpheus-test", state_dict=weights, dims=ld, snac=snac, stop_token_id=dims.stop_token_id,
-                         audio_id_base=dims.audio_id_base, max_tokens=dims.max_tokens, mask_stop_token=True)
+                         audio_id_base=dims.audio_id_base, max_tokens=dims.max_tokens, mask_stop_token=stop_boost is None)
     model.default_sampling_config = SamplingConfig(top_p=0.8, temperature=0.6, repetition_penalty=1.3,
                                                    repetition_window=-1, greedy=greedy, max_tokens=dims.max_tokens)
     worker = ModelWorker("orpheus-test", max_batch_size=max_bs, max_num_pages=max_pages, page_size=page_size,
@@ -39,12 +43,12 @@ def build_models(dims, snac_cfg, seed, max_bs, page_size, max_pages, greedy=True
     ocfg = osampler.SamplingConfig(top_p=0.8, temperature=0.6, repetition_penalty=1.3, repetition_window=-1,
                                    greedy=greedy, max_tokens=dims.max_tokens)
     ow = oworker.OracleWorker(weights, dims, ocfg, page_size=page_size, max_num_pages=max_pages, snac_sd=snac_sd,
-                              snac_cfg=snac_cfg, max_batch_size=max_bs, ignore_stop=True)
+                              snac_cfg=snac_cfg, max_batch_size=max_bs, ignore_stop=stop_boost is None)
     return worker, ow
 
 
 def run_e2e_parity(prompt_lens=(5, 16, 30, 33), n_tokens=40, seed=3, dims=None, page_size=16, max_pages=128,
-                   noise_seed=1234):
+                   noise_seed=1234, stop_boost=None):
     from vox_serve_b200.requests import Request
     from vox_serve_b200.scheduler import Scheduler
 
@@ -52,7 +56,7 @@ def run_e2e_parity(prompt_lens=(5, 16, 30, 33), n_tokens=40, seed=3, dims=None, 
     dims.max_tokens = max(prompt_lens) + n_tokens
     snac_cfg = osnac.SnacConfig.tiny()
     max_bs = len(prompt_lens)
-    worker, ow = build_models(dims, snac_cfg, seed, max_bs, page_size, max_pages)
+    worker, ow = build_models(dims, snac_cfg, seed, max_bs, page_size, max_pages, stop_boost=stop_boost)
     g = torch.Generator().manual_seed(21)
     prompts = [torch.randint(10, dims.vocab_size, (n - 5,), generator=g).tolist() for n in prompt_lens]
 
@@ -115,4 +119,8 @@ def run_e2e_parity(prompt_lens=(5, 16, 30, 33), n_tokens=40, seed=3, dims=None, 
         assert r.finish_reason == o.finish_reason, (r.finish_reason, o.finish_reason)
         assert len(r.lm_output_audio_tokens) == len(o.lm_output_audio_tokens)
     stats["audio_seconds"] = sched.audio_seconds()
+    stats["finish_reasons"] = [r.finish_reason for r in reqs]
+    stats["n_audio_tokens"] = [len(r.lm_output_audio_tokens) for r in reqs]
+    # everything a finished request held is back in the pools
+    assert worker.empty_pages.qsize() == worker.max_num_pages and len(worker.free_slots) == worker.max_batch_size
     return stats

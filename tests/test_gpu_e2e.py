@@ -125,3 +125,79 @@ def test_resident_loop_matches_per_step_api():
             assert worker.res_pcm[:B].abs().max().item() > 0
         tokens[mode] = [[int(t) for t in r.lm_output_audio_tokens] for r in reqs]
     assert tokens["resident"] == tokens["per_step"]
+
+
+def test_e2e_stop_token_sync():
+    """Stop id NOT masked (its lm_head row is boosted so it wins the argmax after 10-50 tokens): the
+    'stop_id_encountered' path, the padded last window with its (n_valid - 0.5) / interval trim, max_tokens for the
+    request that never stops, and slot / page release -- against the oracle worker, teacher-forced."""
+    dims = oorph.OrpheusDims.tiny(vocab_size=156940, stop_token_id=128258, audio_id_base=128266)
+    st = __import__("tests.e2e_harness", fromlist=["x"]).run_e2e_parity(
+        prompt_lens=(9, 16, 30, 33), n_tokens=75, seed=3, dims=dims, page_size=16, max_pages=128, stop_boost=2.5)
+    _check(st)
+    assert st["finish_reasons"].count("stop_id_encountered") >= 2, st
+    assert any(0 < n < 28 for n in st["n_audio_tokens"]), st           # a request shorter than one window
+    assert any(n > 28 and n % 7 != 0 for n in st["n_audio_tokens"]), st  # a stop in the middle of a hop
+
+
+@pytest.mark.parametrize("mode", ["sync", "async"])
+def test_stop_token_ring_matches_host_list(mode):
+    """The device-side token ring that run_detokenize reads must stay index-for-index equal to
+    req.lm_output_audio_tokens when a stop id is sampled -- also when the scheduler runs one step ahead and the
+    stopped request gets one more LM step (scheduler/base.py:168-215).  Every delivered chunk is re-derived from the
+    HOST token list with the same vocoder (zero NoiseBlock noise) and must match byte for byte."""
+    import numpy as np
+    import torch
+
+    from oracle import snac as osnac
+    from tests.e2e_harness import build_models
+    from vox_serve_b200 import ops
+    from vox_serve_b200.requests import Request
+    from vox_serve_b200.scheduler import Scheduler
+
+    dims = oorph.OrpheusDims.tiny(vocab_size=156940, stop_token_id=128258, audio_id_base=128266)
+    prompt_lens = (9, 16, 30, 33)
+    dims.max_tokens = max(prompt_lens) + 75
+    worker, _ = build_models(dims, osnac.SnacConfig.tiny(), 3, len(prompt_lens), 16, 128, stop_boost=2.5)
+    worker.model.audio_decoder.noise_source = lambda shapes: [torch.zeros(s, device="cuda") for s in shapes]
+    g = torch.Generator().manual_seed(21)
+    prompts = [torch.randint(10, dims.vocab_size, (n - 5,), generator=g).tolist() for n in prompt_lens]
+    sched = Scheduler(worker)
+    reqs = [Request(request_id=f"s{i}", prompt=p, model_kwargs={"voice": None}) for i, p in enumerate(prompts)]
+    for r in reqs:
+        sched.submit(r)
+    if mode == "sync":
+        sched.run_until_done(max_steps=4000)
+    else:
+        sched.run_async()
+    torch.cuda.synchronize()
+    assert all(r.done_all for r in reqs)
+    assert [r.finish_reason for r in reqs].count("stop_id_encountered") >= 2
+    assert worker.empty_pages.qsize() == worker.max_num_pages and len(worker.free_slots) == worker.max_batch_size
+    W, hop = worker.detokenize_interval, worker.detokenize_interval - worker.detokenize_overlap
+    n_checked = 0
+    for r in reqs:
+        toks = [int(t[0, 0]) for t in r.lm_output_audio_tokens]
+        assert dims.stop_token_id not in toks
+        want = []
+        d = 0
+        while toks:
+            win = toks[d:d + W]
+            n_valid = len(win)
+            win = win + [win[-1]] * (W - n_valid)
+            pcm = ops.pcm16(worker.model.postprocess(torch.tensor(win, dtype=torch.int64, device="cuda").view(1, W, 1)))
+            a16 = pcm[0].cpu().numpy()
+            if n_valid < W:
+                a16 = a16[:, :int(a16.shape[1] * (n_valid - 0.5) / W)]
+            want.append(a16.tobytes())
+            if d + W >= len(toks):
+                break
+            d += hop
+        got = sched.audio[r.request_id]
+        assert len(got) == len(want), (r.request_id, len(got), len(want), len(toks))
+        for a, b in zip(got, want):
+            assert a == b, (r.request_id, len(a), len(b),
+                            int(np.abs(np.frombuffer(a, np.int16).astype(int) - np.frombuffer(b, np.int16).astype(int)).max())
+                            if len(a) == len(b) else -1)
+            n_checked += 1
+    assert n_checked >= 6

@@ -34,7 +34,7 @@ SIGNATURES = {
     "vb_rope": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_plan_rows": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P]),
     "vb_decode_advance": (c_int, [P, P, P, c_int, P]),
-    "vb_token_feedback": (c_int, [P, P, P, P, P, c_int, c_int, P]),
+    "vb_token_feedback": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
     "vb_gather_i32": (c_int, [P, P, P, c_int, P]),
     "vb_build_input_ids": (c_int, [P, P, P, P, c_int, P]),
     "vb_latest_window": (c_int, [P, P, P, c_int, c_int, P]),

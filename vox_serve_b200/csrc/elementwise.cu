@@ -574,13 +574,16 @@ __global__ void decode_advance_kernel(int32_t* kv_len, int32_t* pos, const int32
 // sampled ids of batch row b (int64) -> slot s = slots[b] (identity when null): next input id, token history
 // ring history[s][n_out[s] % cap], ++n_out[s]   (orpheus.py:447-448, 456-458 keep these in Python lists)
 __global__ void token_feedback_kernel(const int64_t* ids, const int32_t* slots, int32_t* next_input,
-                                      int32_t* history, int32_t* n_out, int B, int cap) {
+                                      int32_t* history, int32_t* n_out, int B, int cap, int skip_token) {
   pdl_sync();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int s = slots ? slots[b] : b;
   const int v = static_cast<int>(ids[b]);
   next_input[s] = v;
+  // the stop id is fed back (a scheduler running one step ahead issues one more LM step) but never becomes an audio
+  // token: the host pops it from lm_output_audio_tokens (orpheus.py:461-463), so the ring must not hold it either
+  if (v == skip_token) return;
   const int n = n_out[s];
   if (history) history[static_cast<size_t>(s) * cap + (n % cap)] = v;
   n_out[s] = n + 1;
@@ -629,11 +632,12 @@ int vb_decode_advance(int32_t* d_kv_len, int32_t* d_pos, const int32_t* d_active
   return 0;
 }
 int vb_token_feedback(const int64_t* d_ids, const int32_t* d_slots, int32_t* d_next_input, int32_t* d_history,
-                      int32_t* d_n_out, int B, int history_cap, void* stream) {
+                      int32_t* d_n_out, int B, int history_cap, int skip_token, void* stream) {
   VB_CHECK_ARG(d_ids && d_next_input && d_n_out, "vb_token_feedback: null pointer");
   VB_CHECK_ARG(history_cap > 0, "vb_token_feedback: history_cap must be positive");
   if (B <= 0) return 0;
-  VB_LAUNCH_PDL(vb::token_feedback_kernel, (B + 127) / 128, 128, 0, stream, d_ids, d_slots, d_next_input, d_history, d_n_out, B, history_cap);
+  VB_LAUNCH_PDL(vb::token_feedback_kernel, (B + 127) / 128, 128, 0, stream, d_ids, d_slots, d_next_input, d_history, d_n_out, B, history_cap,
+                skip_token);
   return 0;
 }
 int vb_gather_i32(int32_t* d_out, const int32_t* d_src, const int32_t* d_idx, int n, void* stream) {

@@ -102,9 +102,16 @@ class OrpheusModel(BaseLM):
             if os.path.isdir(model_name):
                 dims, state_dict = _load_hf_dir(model_name)
             elif model_name.startswith("orpheus-synthetic"):
+                # "orpheus-synthetic[-tiny][:seed]": -tiny = a 2-layer, hidden-768 model with the true vocabulary and
+                # a 64-channel SNAC (integration tests that construct the worker by NAME, like the reference's
+                # Scheduler does: scheduler/base.py:63-91)
                 seed = int(model_name.split(":")[1]) if ":" in model_name else 0
-                dims = dims or LlamaDims.orpheus_3b()
+                tiny = model_name.split(":")[0].endswith("-tiny")
+                dims = dims or (LlamaDims(768, 2, 6, 2, 128, 1024, 156940) if tiny else LlamaDims.orpheus_3b())
                 state_dict = synthetic_state_dict(dims, seed, device)
+                if tiny and snac is None:
+                    snac = SNAC(encoder_dim=4, encoder_rates=(2, 2, 2, 2), decoder_dim=64, device=audio_decoder_device or device)
+                    snac.load_state_dict(snac.synthetic_state_dict(seed=seed + 1))
             else:
                 raise VoxB200Error(
                     f"'{model_name}' is not a local directory: this build has no network access. Pass a local HF "

@@ -698,11 +698,12 @@ def decode_advance(kv_len: torch.Tensor, pos: torch.Tensor, active: Optional[tor
 
 
 def token_feedback(ids: torch.Tensor, slots: Optional[torch.Tensor], next_input: torch.Tensor,
-                   history: Optional[torch.Tensor], n_out: torch.Tensor):
-    """ids int64 [B] -> per-slot next input id, history ring [slots, cap], token counter."""
+                   history: Optional[torch.Tensor], n_out: torch.Tensor, skip_token: int = -1):
+    """ids int64 [B] -> per-slot next input id, history ring [slots, cap], token counter.  An id equal to
+    ``skip_token`` (the stop id) is fed back but not recorded: the ring holds audio tokens only."""
     cap = history.shape[1] if history is not None else 1
     call("vb_token_feedback", ids.data_ptr(), _p(slots), next_input.data_ptr(), _p(history), n_out.data_ptr(),
-         ids.numel(), cap, _stream())
+         ids.numel(), cap, int(skip_token), _stream())
 
 
 def gather_i32(src: torch.Tensor, idx: Optional[torch.Tensor], out: torch.Tensor, n: Optional[int] = None):

@@ -295,7 +295,11 @@ class ModelWorker:
         out = self.out_ids[:B]
         m.sampling_device(logits[:B], None, self.rep_cache, cache_rows=slots if self.rep_cache is not None else None,
                           out=out.view(-1))
-        ops.token_feedback(out.view(-1), slots, self.next_input, self.history, self.n_out)
+        # the ring mirrors req.lm_output_audio_tokens index for index: the stop id is popped from that list on the
+        # host (orpheus.py:461-463), so it is not recorded here either (a request that stopped may still run one more
+        # LM step when the scheduler works one step ahead; its token then lands at the same index on both sides)
+        ops.token_feedback(out.view(-1), slots, self.next_input, self.history, self.n_out,
+                           skip_token=getattr(m, "stop_token_id", -1))
 
     def _run_step(self, requests: List[Request], lm_inputs: LMInputs) -> Optional[Coroutine]:
         if len(requests) == 0:
