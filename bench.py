@@ -8,7 +8,11 @@ token each) plus, every 7th step, the SNAC decode + PCM16 of the newest 28-token
 Metric: audio-sec/sec = seconds of audio emitted / seconds elapsed (benchmark/throughput.py:315-318 of the
 reference); 7 tokens = 2048 samples = 85.33 ms.
 
-Two figures per run, same state (32 requests prefetched to >= 28 tokens), same K steps:
+The timed steps are taken from the STEADY STATE of the continuous batch the config describes (32 requests x 700 decode
+steps each): the requests are staggered in groups of four, 84 tokens apart, so the batch holds the mix of sequence
+lengths a server at batch 32 holds (kv ~190 ... ~780, mean ~490) instead of 32 requests that all just finished prefill.
+
+Two figures per run, same state, same K steps:
   value : device-resident loop (ModelWorker.run_lm_decode_resident) -- inputs in HBM, no host work between
           CUDA-graph replays, PCM left in HBM; timed with CUDA events.
   e2e   : the reference-facing worker API driven by Scheduler._step -- per step a pinned-host -> device copy of
@@ -36,6 +40,15 @@ SEC_PER_FRAME = 2048 / 24000.0
 TOKENS_PER_FRAME = 7
 BATCH = 32
 PROMPT_TOKENS = 128
+PROMPT_ROWS = PROMPT_TOKENS + 5            # [128259] + ids + [128009, 128260, 128261, 128257]  (orpheus.py:356-358)
+SETUP_TOKENS = 28 + BATCH                  # every request past its first vocoded window (one prefill per step)
+STAGGER_GROUP, STAGGER_STEPS = 4, 84       # steady-state mix: group j of four requests is 84 j tokens further along
+
+
+def steady_state_kv_lens():
+    """kv length of every request of the steady-state batch when the timed region starts (both arms use it)."""
+    return [PROMPT_ROWS + SETUP_TOKENS + STAGGER_STEPS * (i // STAGGER_GROUP) for i in range(BATCH)]
+
 WORKLOAD = "Orpheus-3B streaming TTS batch=32 on 1xB200 (SNAC codec path)"
 
 
@@ -98,7 +111,7 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------------------
 # CPU oracle leg (cpu_baseline of the main arm; the whole of --impl reference)
 # --------------------------------------------------------------------------------------------------------------
-def cpu_oracle_sample(n_lm_steps: int = 2, kv_len: int = 161, threads=None):
+def cpu_oracle_sample(n_lm_steps: int = 2, kv_len: int = None, threads=None):
     """Times the oracle port (oracle/: the reference's arithmetic on torch CPU) on a bounded sample of the same
     workload: `n_lm_steps` batch-32 decode steps of Orpheus-3B at kv_len ~ the GPU run's starting length, plus
     one SNAC decode of 32 windows; audio-sec/sec from the steady-state mix (1 SNAC per 7 LM steps)."""
@@ -108,6 +121,8 @@ def cpu_oracle_sample(n_lm_steps: int = 2, kv_len: int = 161, threads=None):
 
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
+    if kv_len is None:          # the mean of the GPU arm's steady-state mix
+        kv_len = int(round(sum(steady_state_kv_lens()) / BATCH))
     dims = oorph.OrpheusDims()
     t0 = time.perf_counter()
     blk = torch.randn(1 << 24, dtype=torch.float32).mul_(0.02).to(torch.bfloat16)   # 32 MB seeded block, tiled
@@ -181,17 +196,19 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_steps = max(1, min(args.steps, 3))       # bounded sample: each step costs seconds of CPU time
+    n_steps = max(1, min(args.steps, 6))       # bounded sample: each step costs ~0.5 s of CPU time
     t0 = time.perf_counter()
     r = cpu_oracle_sample(n_lm_steps=n_steps)
-    line = {"impl": "reference", "metric": "audio-sec/sec", "value": r["value"] * args.gpus, "unit": "audio-sec/sec",
+    # ONE batch-32 replica on the box's host cores, whatever --gpus says: the host does not grow with the GPU count
+    line = {"impl": "reference", "metric": "audio-sec/sec", "value": r["value"], "unit": "audio-sec/sec",
             "n_gpus": args.gpus, "steps": n_steps, "warmup": 1, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "prompt_tokens": PROMPT_TOKENS,
-                       "note": "CPU port of the reference path (the reference has no CPU path and is not importable "
-                               "on the GPU box); value is per replica x n_gpus because replicas are independent"},
+            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "prompt_tokens": PROMPT_ROWS,
+                       "mean_kv_len": round(sum(steady_state_kv_lens()) / BATCH, 1),
+                       "note": "CPU port of the reference path (the reference has no CPU path); one batch-32 replica on "
+                               "all host cores -- NOT multiplied by n_gpus"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "e2e": {"value": r["value"] * args.gpus, "unit": "audio-sec/sec", "h2d_bytes_per_step": 0,
+            "e2e": {"value": r["value"], "unit": "audio-sec/sec", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
     print(json.dumps(line))
@@ -220,8 +237,10 @@ def run_gpu(args):
 
     K, W = args.steps, max(args.warmup, 3)
     hop = TOKENS_PER_FRAME
-    setup_tokens = 28 + BATCH
-    max_tokens = PROMPT_TOKENS + 5 + setup_tokens + W + K + 64
+    n_groups = BATCH // STAGGER_GROUP
+    joins = args.ttfa_joins
+    # longest-lived request: steady-state mix + the longer of (timed steps, the TTFA-join measurement)
+    max_tokens = PROMPT_ROWS + SETUP_TOKENS + STAGGER_STEPS * (n_groups - 1) + W + max(K, 32 * joins) + 96
     torch.manual_seed(1234 + rank)
     model = OrpheusModel(f"orpheus-synthetic:{rank}", device=f"cuda:{local}", mask_stop_token=True, max_tokens=max_tokens)
     pages = max(2048, BATCH * ((max_tokens + 127) // 128 + 1))
@@ -238,7 +257,7 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def fresh_batch(tag, vocoder_batch_steps=1):
+    def fresh_batch(tag, vocoder_batch_steps=1, stagger=True):
         sched = Scheduler(worker, vocoder_batch_steps=vocoder_batch_steps)
         t_sub = {}
         reqs = []
@@ -253,6 +272,13 @@ def run_gpu(args):
             sched._step()
             n += 1
             assert n < 400
+        if stagger:
+            # steady-state mix (untimed): group j of four requests runs 84 j more decode steps than group 0
+            for j in range(1, BATCH // STAGGER_GROUP):
+                worker.run_lm_decode_resident(reqs[j * STAGGER_GROUP:], STAGGER_STEPS, detokenize=False)
+            for r in reqs:      # no vocoder backlog: the newest completed window has been delivered
+                idx = ((len(r.lm_output_audio_tokens) - 28) // hop) * hop
+                r.audio_decode_idx, r.next_audio_decode_idx = [idx], [idx]
         return sched, reqs, n
 
     def drain(sched, reqs):
@@ -265,12 +291,14 @@ def run_gpu(args):
     # one untimed ramp first, like a server's warm-up request burst: first-use costs (allocator growth for every
     # vocoder batch size of the ramp, lazy kernel loading) otherwise land in the burst TTFA and make it jump between
     # 250 and 600 ms from run to run
-    sched, reqs, _ = fresh_batch("w")
+    sched, reqs, _ = fresh_batch("w", stagger=False)
     drain(sched, reqs)
     torch.cuda.synchronize()
     t_setup0 = time.perf_counter()
-    sched, reqs, n_setup = fresh_batch("e")
+    sched, reqs, n_setup = fresh_batch("b", stagger=False)
     ttfa = sorted((sched.first_audio_time[r.request_id] - sched.submit_time[r.request_id]) * 1e3 for r in reqs)
+    drain(sched, reqs)
+    sched, reqs, _ = fresh_batch("e")
     setup_s = time.perf_counter() - t_setup0
     def timed_api_loop(sched, reqs, n_steps, async_mode):
         """n_steps scheduler iterations through the worker API; returns (ms, audio seconds, launches, h2d, d2h)."""
@@ -371,6 +399,33 @@ def run_gpu(args):
         s1.active_requests = []
     ttfa_single.sort()
 
+    # ------------------------------------------------ steady-state TTFA: one request joins 31 running streams ------
+    # ("define TTFA as steady-state (one request joining 31 running streams)"; goodput.py:250-262: first
+    # audio chunk arrival - request start.)  The joining prefill rides in the same step as the 31 decodes.
+    ttfa_join = []
+    if joins > 0:
+        sj, rj, _ = fresh_batch("j")
+        victim = rj.pop()                       # 31 keep running
+        worker.free_kv_cache(victim)
+        sj.active_requests = [r for r in sj.active_requests if r is not victim]
+        for _ in range(W):
+            sj._step()
+        for i in range(joins):
+            ids = torch.randint(0, 128000, (PROMPT_TOKENS,), generator=g).tolist()
+            r1 = Request(request_id=f"join{i}", prompt=ids, model_kwargs={"voice": None})
+            torch.cuda.synchronize()
+            sj.submit(r1)
+            n = 0
+            while not sj.audio[r1.request_id]:
+                sj._step()
+                n += 1
+                assert n < 200
+            ttfa_join.append((sj.first_audio_time[r1.request_id] - sj.submit_time[r1.request_id]) * 1e3)
+            worker.free_kv_cache(r1)
+            sj.active_requests = [r for r in sj.active_requests if r is not r1]
+        drain(sj, rj)
+        ttfa_join.sort()
+
     # ------------------------------------------------ reduce over ranks ----------------------------------------
     from vox_serve_b200.router import reduce_job_metrics
 
@@ -382,7 +437,9 @@ def run_gpu(args):
             "metric": "audio-sec/sec", "value": res_audio_s / (res_ms / 1e3), "unit": "audio-sec/sec", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": res_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "prompt_tokens": PROMPT_TOKENS + 5,
+            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "prompt_tokens": PROMPT_ROWS,
+                       "state": "steady-state continuous batch: request groups staggered 84 tokens apart "
+                                f"(kv {min(steady_state_kv_lens())}..{max(steady_state_kv_lens())} when the timed region starts)",
                        "sampling": "top_p 0.8 T 0.6 repetition_penalty 1.3 (orpheus.py:260-268), stop id masked",
                        "mean_kv_len": round(mean_kv, 1), "page_size": 128, "parallelism": f"dp{world} replicas",
                        "weights": "seeded N(0,0.02) bf16 at Orpheus-3B shapes; SNAC 24 kHz shapes, seeded",
@@ -404,6 +461,11 @@ def run_gpu(args):
             "ttfa_single_ms": {"p50": ttfa_single[len(ttfa_single) // 2], "min": ttfa_single[0], "max": ttfa_single[-1],
                                "note": "one 133-token request on an otherwise idle, warm replica: prefill + the 28 decode "
                                        "steps the first SNAC window needs + vocoder + PCM copy"},
+            "ttfa_join_ms": ({"p50": ttfa_join[len(ttfa_join) // 2], "p90": ttfa_join[int(len(ttfa_join) * 0.9)],
+                              "min": ttfa_join[0], "max": ttfa_join[-1], "joins": len(ttfa_join),
+                              "note": "one 133-token request joins 31 running streams (steady-state kv mix): its prefill "
+                                      "rides with the 31 decodes, then 27 batch-32 decode steps, vocoder, PCM copy"}
+                             if ttfa_join else None),
             "setup_s": setup_s, "graph_capture_s": capture_s, "decode_graphs": n_graphs, "clocks": clk,
         }
         line.update(roof(peak, peak_src))
@@ -519,6 +581,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=7)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ttfa-joins", type=int, default=20, help="joins measured for ttfa_join_ms (0 = skip)")
     ap.add_argument("--profile-steps", type=int, default=0,
                     help="after the timed regions run this many resident steps inside cudaProfilerStart/Stop (ncu)")
     args = ap.parse_args()

@@ -130,6 +130,20 @@ int vb_paged_attn(void* d_out, const void* d_q, const void* d_kv, int64_t slab_b
 size_t vb_weight_tiles_bytes(int N, int K, int tile_rows);
 int vb_pack_weight_tiles(void* d_dst, const void* d_w, int N, int K, int64_t ldw, int tile_rows, void* stream);
 int vb_gemm_t_tile(int T);
+/* L2 weight prefetcher (no counterpart in the reference, whose projections are cuBLAS calls: orpheus.py:41-47, 68-79).
+ *   vb_tag_next_gemm:   the next projection launched by this host thread (vb_gemm_bf16 or a fused variant) publishes
+ *                       its progress through its weights into *d_progress: KiB of the step's virtual weight stream
+ *                       consumed so far = (virt_offset_bytes + stages issued x CTAs x stage bytes) / 1024;
+ *   vb_set_u32:         *d_ptr = value as a kernel of the launch chain (resets the progress word of a step);
+ *   vb_weight_prefetch: one warp per CTA walks d_ops (int64 [n_ops][5] = {virtual offset, offset in d_arena, CTAs,
+ *                       bytes per stage, stages per CTA}; slices of CTA c at phys + c * stages * stage bytes) in
+ *                       consumption order and prefetches into L2 whatever is less than window_bytes ahead of
+ *                       *d_progress; meant for a second stream beside the decode step.  Gives up (returns) when the
+ *                       progress word stops moving. */
+int vb_tag_next_gemm(uint32_t* d_progress, uint64_t virt_offset_bytes);
+int vb_set_u32(uint32_t* d_ptr, uint32_t value, void* stream);
+int vb_weight_prefetch(const void* d_arena, const int64_t* d_ops, int n_ops, const uint32_t* d_progress,
+                       uint64_t window_bytes, int grid_ctas, void* stream);
 /* d_x_tiles (optional): X in the XT(vb_gemm_t_tile(T)) layout -- then x_map may be NULL; y_tiled (mode 2 only): write
  * Y in the XT(vb_gemm_t_tile(T)) layout over n_out columns (it is the down projection's activation). */
 int vb_gemm_bf16(void* d_y, const void* d_w_tiles, const void* x_map, const void* d_x_tiles, int T, int N, int K,
@@ -238,6 +252,18 @@ int vb_gather_windows(int64_t* d_windows, const int32_t* d_history, const int32_
                       const int32_t* d_n_valid, int n, int history_cap, int window, void* stream);
 /* embedding gather: orpheus.py:408 */
 int vb_embedding(void* d_out, const void* d_table, const int32_t* d_ids, int T, int dim, int vocab, void* stream);
+/* Multi-codebook glue of the depth-transformer adapters (vox_serve/model/csm.py:158-168, 637-663, 700-701;
+ * cuda_graph_worker.py:1058-1160 does these with torch ops and host indices between graph replays):
+ *   vb_multi_embed_sum: out[t] = bf16(sum over columns c < C with mask[t][c] != 0 (NULL = all) of
+ *                       c < n_cols_a ? table_a[ids(t,c) + (col0 + c) * col_offset] : table_b[ids(t,c)]), fp32
+ *                       accumulation in column order; ids int64 at d_ids[t * ld_t + c * ld_c];
+ *   vb_interleave_rows: out[2r] = a[r], out[2r+1] = b[r] (the depth decoder's [hidden, embed(cb0)] 2-row prefill);
+ *   vb_transpose_i64:   dst[r][c] = src[c][r] (codebook-major device frame buffer -> request-major ids). */
+int vb_multi_embed_sum(void* d_out, int ld_out, const int64_t* d_ids, int64_t ld_t, int64_t ld_c, const uint8_t* d_mask,
+                       const void* d_table_a, int64_t rows_a, int64_t col_offset, int col0, int n_cols_a,
+                       const void* d_table_b, int64_t rows_b, int T, int C, int dim, void* stream);
+int vb_interleave_rows(void* d_out, const void* d_a, const void* d_b, int n, int row_bytes, void* stream);
+int vb_transpose_i64(int64_t* d_dst, const int64_t* d_src, int B, int C, int ld_dst, int ld_src, void* stream);
 /* rows out[i] = in[idx[i] + idx_offset] (last-token gather qo_indptr[1:] - 1, cuda_graph_worker.py:900-902) */
 int vb_gather_rows(void* d_out, const void* d_in, const int32_t* d_idx, int n, int row_bytes, int idx_offset,
                    void* stream);
@@ -319,6 +345,11 @@ int vb_snac_final(float* d_y, const float* d_x, const float* d_w /*[C][7]*/, con
                   const float* d_alpha_in, int B, int C, int T, int t0, int t1, void* stream);
 /* (audio * 32767) truncated toward zero to int16, no clipping: cuda_graph_worker.py:1252-1253 */
 int vb_pcm16(int16_t* d_out, const float* d_audio, int64_t n, void* stream);
+/* n standard-normal fp32 draws: the NoiseBlock input the reference takes from torch.randn
+ * (vox_serve/tokenizer/snac.py:206-212).  Philox4x32-10 + Box-Muller, counter = (offset, element / 4).
+ * d_rng_state (optional, device u64 {seed, offset, arrivals}) replaces seed / offset and its offset advances by one
+ * per call on the device, so a CUDA-graph replay draws fresh noise without host involvement. */
+int vb_randn(float* d_out, int64_t n, uint64_t seed, uint64_t offset, uint64_t* d_rng_state, void* stream);
 /* LM ids [B][28] -> SNAC codes (orpheus.py:479-500): codes0 [B][4], codes1 [B][8], codes2 [B][16] int32 */
 int vb_orpheus_window_codes(int32_t* d_c0, int32_t* d_c1, int32_t* d_c2, const int64_t* d_ids, int B,
                             int audio_id_base, void* stream);

@@ -103,6 +103,8 @@ def test_reference_orpheus_adapter_runs_on_b200_operator_shims():
             logits = logits[wrapper.qo_indptr[1:].long() - 1]        # cuda_graph_worker.py:900-902
         assert logits.shape == (len(lmr), 1, dims.vocab_size) and logits.dtype == BF
         rep = inp["repetition_cache"].cuda()
+        for r in lmr:                                  # what the reference's prepare_lm_inputs maintains (base.py:299, 325)
+            rreqs[r.request_id].next_position_id = r.next_position_id
         ids, task = m.sampling(logits=logits, requests=[rreqs[r.request_id] for r in lmr], repetition_cache=rep)
         import asyncio
         asyncio.run(task)

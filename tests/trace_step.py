@@ -9,7 +9,7 @@ from vox_serve_b200 import _lib, ops  # noqa: E402
 from vox_serve_b200.engine import LlamaDims, LlamaEngine, LlamaWeights  # noqa: E402
 from vox_serve_b200.model.orpheus import synthetic_state_dict  # noqa: E402
 
-NAMES = {22: " attn:first-tile", 23: " attn:last-tile", 1: "gemm", 2: "attn", 3: "chain", 4: "sample", 10: "rope_tab", 20: " gemm:dep-released", 21: " gemm:acc-done"}
+NAMES = {5: "reduce+norm", 6: "rope+append", 24: " rope:dep-released", 22: " attn:first-tile", 23: " attn:last-tile", 1: "gemm", 2: "attn", 3: "chain", 4: "sample", 10: "rope_tab", 20: " gemm:dep-released", 21: " gemm:acc-done"}
 for p in range(4):
     NAMES[30 + p] = f" chain:x-ready p{p}"
     NAMES[40 + p] = f" chain:acc-done p{p}"

@@ -46,6 +46,9 @@ SIGNATURES = {
                               c_float, P, c_size_t, c_int, c_int, c_int, P]),
     "vb_set_trace": (c_int, [P]),
     "vb_gemm_t_tile": (c_int, [c_int]),
+    "vb_tag_next_gemm": (c_int, [P, c_uint64]),
+    "vb_set_u32": (c_int, [P, C.c_uint32, P]),
+    "vb_weight_prefetch": (c_int, [P, P, c_int, P, c_uint64, c_int, P]),
     "vb_weight_tiles_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vb_pack_weight_tiles": (c_int, [P, P, c_int, c_int, c_int64, c_int, P]),
     "vb_gemm_bf16": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
@@ -62,6 +65,10 @@ SIGNATURES = {
     "vb_qkv_rope_append": (c_int, [P, P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_embedding": (c_int, [P, P, P, c_int, c_int, c_int, P]),
     "vb_gather_rows": (c_int, [P, P, P, c_int, c_int, c_int, P]),
+    "vb_multi_embed_sum": (c_int, [P, c_int, P, c_int64, c_int64, P, P, c_int64, c_int64, c_int, c_int, P, c_int64, c_int,
+                                   c_int, c_int, P]),
+    "vb_interleave_rows": (c_int, [P, P, P, c_int, c_int, P]),
+    "vb_transpose_i64": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "vb_sample_workspace_bytes": (c_size_t, [c_int, c_int]),
     "vb_sample": (c_int, [P, P, c_int, c_int, c_int, P, P, c_int, c_int, c_int, c_float, c_int, c_int, c_float,
                           c_float, c_float, c_uint64, c_uint64, P, c_int, P, c_size_t, P]),
@@ -77,6 +84,7 @@ SIGNATURES = {
     "vb_snac_pwconv_tc": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_snac_convtr_tc": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_pcm16": (c_int, [P, P, c_int64, P]),
+    "vb_randn": (c_int, [P, c_int64, c_uint64, c_uint64, P, P]),
     "vb_orpheus_window_codes": (c_int, [P, P, P, P, c_int, c_int, P]),
 }
 

@@ -8,9 +8,14 @@
 //    long sequential bursts; tiles are linearised (row, tile) and cut into gridDim.x equal contiguous ranges
 //    ("stream-K" over KV): every CTA streams the same number of tiles whatever the mix of sequence lengths;
 //  * one PRODUCER warp per CTA walks its range -- 32 tiles of metadata resolved at a time, one lane each, from
-//    shared-memory copies of the plan -- and feeds a STAGES-deep ring behind full/empty mbarriers with the
-//    TMA unit's LINEAR bulk copies (cp.async.bulk.shared.global): one copy per token row (n_kv * D * 2 bytes,
-//    all heads), the 2 * TOK copies of a tile issued by the warp's lanes in parallel.  Rows land with a 16-byte
+//    shared-memory copies of the plan -- and feeds a ring of HALF-stages (the K rows of a tile, then its V rows:
+//    32 KiB + skew each) behind full/empty mbarriers with the TMA unit's LINEAR bulk copies
+//    (cp.async.bulk.shared.global, L2 evict_first: a layer's KV is not read again before the next step): one
+//    copy per token row (n_kv * D * 2 bytes, all heads), issued by the warp's lanes in parallel.  Three
+//    half-stages (~100 KiB) keep a CTA below half an SM's shared memory, so the CTA of a NEIGHBOURING kernel of
+//    the programmatic-dependent-launch chain (the next layer's attention in a back-to-back run; the O projection's
+//    weight prefetch or the QKV tail in a decode step) is resident beside it: its launch latency, plan look-up
+//    and the KV of tokens that were already in the cache stream in while this kernel is still running.  Rows land with a 16-byte
 //    skew (row stride n_kv * D * 2 + 16) so that the consumers' ldmatrix reads of 8 consecutive tokens are
 //    bank-conflict free without a swizzle.  (A tiled tensor-map box must keep a 128-byte inner extent under the
 //    128B swizzle; measured, the TMA unit then spends ~19 cycles per 128-byte row and caps the kernel below
@@ -28,8 +33,8 @@
 
 namespace vb {
 
-constexpr int ATTN_MAX_STAGES = 4;
-constexpr int ATTN_QBUF = 2;
+constexpr int ATTN_MAX_STAGES = 8;     // half-stages (K rows or V rows of one tile)
+constexpr int ATTN_QBUF = 1;           // consumers copy their Q fragments to registers at the segment start
 
 struct AttnParams {
   __nv_bfloat16* out;
@@ -66,6 +71,14 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
                "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void bulk_copy_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                                   uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -81,21 +94,25 @@ __device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
 struct AttnLayout {
   int stage_bytes, off_q, off_meta, off_bar, off_wml, off_flag, off_ored, off_plan, total;
   __host__ __device__ AttnLayout(int D, int tok, int n_kv, int n_q, int G, int stages, int n_rows) {
-    stage_bytes = 2 * tok * (n_kv * D * 2 + 16);                // K rows then V rows, each skewed by 16 bytes
+    stage_bytes = tok * (n_kv * D * 2 + 16);                    // one half-stage: K (or V) rows, each skewed by 16 bytes
     off_q = stages * stage_bytes;
     off_meta = off_q + ATTN_QBUF * n_q * D * 2;
-    off_bar = off_meta + ATTN_MAX_STAGES * 32;                  // full[4], empty[4], qfull[2], qempty[2]
+    off_bar = off_meta + ATTN_MAX_STAGES * 32;                  // full[8], empty[8], qfull, qempty
     off_wml = off_bar + (2 * ATTN_MAX_STAGES + 2 * ATTN_QBUF) * 8;   // float[n_warps][16][2]
     const int n_warps = n_kv * (tok / 16);
-    off_flag = off_wml + n_warps * 16 * 2 * 4;
+    // (the block-level slab merge only exists when a tile holds several 16-token slabs, i.e. n_kv < 8)
+    const int slabbed = tok > 16 ? 1 : 0;
+    off_flag = off_wml + slabbed * n_warps * 16 * 2 * 4;
     off_ored = (off_flag + 16 + 127) / 128 * 128;               // float[n_warps][G][D]
-    off_plan = off_ored + n_warps * G * D * 4;                  // int[4][n_rows + 1]
+    off_plan = off_ored + slabbed * n_warps * G * D * 4;        // int[4][n_rows + 1]
     total = off_plan + 4 * (n_rows + 1) * 4 + 128;              // + alignment slack
   }
 };
 
-template <int D, bool HI>
-__global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) {
+// MINB = CTAs per SM the register allocation is sized for: 1 -> up to 168 registers, no spills (deep ring, the SM to
+// itself); 2 -> 96 registers (some spills) so that a second CTA -- this kernel's or a neighbouring kernel's -- fits.
+template <int D, bool HI, int MINB>
+__global__ void __launch_bounds__(288, MINB) paged_attn_kernel(const AttnParams p) {
   constexpr int KS = D / 16;            // k-steps of K Q^T
   constexpr int MT = D / 16;            // m-tiles of V^T P^T
   constexpr int NT = HI ? 2 : 1;        // 8-head column tiles of the GQA group
@@ -107,7 +124,6 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
   const int NC = NW * 32;
   const int ROWB = p.n_kv * D * 2;      // bytes of one token row (all heads) in the cache
   const int RS = ROWB + 16;             // its stride in shared memory (16-byte skew)
-  const int KVT = TOK * RS;             // bytes of a K (or V) tile in shared memory
   TileMeta* meta = reinterpret_cast<TileMeta*>(smem + L.off_meta);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
   uint64_t* empty = full + ATTN_MAX_STAGES;
@@ -159,13 +175,12 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
     uint32_t ph = 0;
     bool dep_ok = false;
     int issued = 0, n_pend = 0, pend_row0 = 0, pend_row1 = 0;
+    const uint64_t pol_kv = policy_evict_first();
     auto issue_q = [&](int row, int seg) {
-      const int qs = seg & 1;
-      mbar_wait(&qempty[qs], ((seg >> 1) & 1) ^ 1);
+      mbar_wait(&qempty[0], (seg & 1) ^ 1);
       if (lane == 0) {
-        mbar_arrive_expect_tx(&qfull[qs], p.n_q * D * 2);
-        bulk_copy_g2s(smem + L.off_q + qs * p.n_q * D * 2, p.q + static_cast<size_t>(row) * p.n_q * D, p.n_q * D * 2,
-                      &qfull[qs]);
+        mbar_arrive_expect_tx(&qfull[0], p.n_q * D * 2);
+        bulk_copy_g2s(smem + L.off_q, p.q + static_cast<size_t>(row) * p.n_q * D, p.n_q * D * 2, &qfull[0]);
       }
       __syncwarp();
     };
@@ -201,13 +216,14 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
         const int page = __shfl_sync(0xffffffffu, m_page, k);
         const int old = __shfl_sync(0xffffffffu, m_old, k);
         const bool seg_start = (m.flags & 1) != 0;
-        if (!dep_ok && (m.token0 + TOK > old || issued >= STAGES || (seg_start && n_pend >= ATTN_QBUF))) {
+        auto resolve_dep = [&]() {
           pdl_wait();
           pdl_trigger();
           dep_ok = true;
           for (int i = 0; i < n_pend; ++i) issue_q(i == 0 ? pend_row0 : pend_row1, i);
           n_pend = 0;
-        }
+        };
+        if (!dep_ok && (m.token0 + TOK > old || (seg_start && n_pend >= ATTN_QBUF))) resolve_dep();
         if (seg_start) {
           // the row's Q (all heads) goes into the double buffer; its slot was freed two segments ago
           m.qslot = nseg;
@@ -221,29 +237,32 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
         } else {
           m.qslot = nseg - 1;
         }
-        ++issued;
-        mbar_wait(&empty[stage], ph ^ 1);
-        trace_fine(fine, 0, base + k - c0);
-        if (lane == 0) {
-          meta[stage] = m;
-          mbar_arrive_expect_tx(&full[stage], 2 * TOK * ROWB);
-        }
-        __syncwarp();
         {
-          // 2 * TOK row copies (K rows then V rows), spread over the lanes
-          uint8_t* dst = smem + stage * L.stage_bytes;
           const int slot0 = m.token0 % p.page_size;
           const size_t page_elems = static_cast<size_t>(p.page_size) * p.n_kv * D;
           const __nv_bfloat16* src0 = p.kv + static_cast<size_t>(p.slab_base + page) * 2 * page_elems +
                                       static_cast<size_t>(slot0) * p.n_kv * D;
-          for (int c = lane; c < 2 * TOK; c += 32) {
-            const int kvsel = c >= TOK ? 1 : 0, t = c - kvsel * TOK;
-            bulk_copy_g2s(dst + kvsel * KVT + t * RS, src0 + kvsel * page_elems + static_cast<size_t>(t) * p.n_kv * D,
-                          ROWB, &full[stage]);
+          // two half-stages per tile: the K rows, then the V rows (TOK row copies each, spread over the lanes)
+#pragma unroll
+          for (int kvsel = 0; kvsel < 2; ++kvsel) {
+            // a half-stage that is being re-used is freed by the consumers, who need Q, i.e. the predecessor kernel
+            if (!dep_ok && 2 * issued + kvsel >= STAGES) resolve_dep();
+            mbar_wait(&empty[stage], ph ^ 1);
+            if (kvsel == 0) trace_fine(fine, 0, base + k - c0);
+            if (lane == 0) {
+              if (kvsel == 0) meta[stage] = m;
+              mbar_arrive_expect_tx(&full[stage], TOK * ROWB);
+            }
+            __syncwarp();
+            uint8_t* dst = smem + stage * L.stage_bytes;
+            for (int t = lane; t < TOK; t += 32)
+              bulk_copy_g2s_hint(dst + t * RS, src0 + kvsel * page_elems + static_cast<size_t>(t) * p.n_kv * D, ROWB,
+                                 &full[stage], pol_kv);
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; ph ^= 1; }
           }
+          ++issued;
         }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; ph ^= 1; }
       }
     }
     if (!dep_ok) {
@@ -284,13 +303,11 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
     if (tr >= 0 && Lx == c0) trace_mark(22);          // first tile landed
     const TileMeta m = meta[stage];
     const uint32_t kbase = smem_u32(smem + stage * L.stage_bytes);
-    const uint32_t vbase = kbase + KVT;
 
     if (m.flags & 1) {
       // ---- new segment: reset the running state, pull this head group's Q fragments into registers ----
-      const int qs = m.qslot & 1;
-      mbar_wait(&qfull[qs], (m.qslot >> 1) & 1);
-      const uint8_t* qsm = smem + L.off_q + qs * p.n_q * D * 2 + head * G * D * 2;
+      mbar_wait(&qfull[0], m.qslot & 1);
+      const uint8_t* qsm = smem + L.off_q + head * G * D * 2;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int hq = nt * 8 + g;       // B fragment: column n = head within the group
@@ -303,7 +320,7 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&qempty[qs]);
+      if (lane == 0) mbar_arrive(&qempty[0]);
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -332,6 +349,10 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
         for (int nt = 0; nt < NT; ++nt) mma_bf16_16816(S[nt], a, qb[nt][ks][0], qb[nt][ks][1]);
       }
     }
+    // this warp is done with the K half-stage
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);
+    if (++stage == STAGES) { stage = 0; ph ^= 1; }
     // ---- mask, running max, P = exp2(S - m) rounded to bf16, sums of the rounded values ----
     const int tok_lo = m.token0 + slab * 16 + g;
     const bool in_lo = tok_lo < m.kvlen, in_hi = tok_lo + 8 < m.kvlen;
@@ -364,7 +385,9 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
     }
     rescale = __any_sync(0xffffffffu, rescale);
     // ---- O^T = O^T * alpha + V^T P^T ----
+    mbar_wait(&full[stage], ph);
     {
+      const uint32_t vbase = smem_u32(smem + stage * L.stage_bytes);
       const int trow = slab * 16 + r8 + (mi >> 1) * 8;
       const uint32_t rbase = vbase + trow * RS + hoff + (mi & 1) * 16;
 #pragma unroll
@@ -382,7 +405,7 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
         }
       }
     }
-    // this warp is done with the stage's tiles: hand the slot back to the producer
+    // this warp is done with the V half-stage: hand the slot back to the producer
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[stage]);
     if (warp == 0) trace_fine(fine, 2, Lx - c0);
@@ -478,10 +501,12 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
 #pragma unroll
               for (int j = 0; j < D / 32; ++j) acc[hh][j] = 0.f;
             }
-            for (int cb = 0; cb < n; cb += 4) {
-              float mm[4][4], ll[4][4], v[4][4][D / 32];
+            // (two parts per round keeps the kernel under the 112 registers that let two CTAs share an SM)
+            constexpr int MP = 2;
+            for (int cb = 0; cb < n; cb += MP) {
+              float mm[MP][4], ll[MP][4], v[MP][4][D / 32];
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
+              for (int k = 0; k < MP; ++k) {
                 const bool okc = cb + k < n;
                 const size_t ps = pslot_of(okc ? cb + k : 0);
 #pragma unroll
@@ -495,7 +520,7 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
                 }
               }
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
+              for (int k = 0; k < MP; ++k)
 #pragma unroll
                 for (int hh = 0; hh < 4; ++hh) {
                   const float sc = (mm[k][hh] == -INFINITY) ? 0.f : ex2_approx(mm[k][hh] - Mx[hh]);
@@ -611,12 +636,12 @@ __global__ void __launch_bounds__(288, 1) paged_attn_kernel(const AttnParams p) 
   trace_end(tr);
 }
 
-template <int D, bool HI>
+template <int D, bool HI, int MINB>
 static int launch_attn(const AttnParams& p, int grid, cudaStream_t stream) {
   const AttnLayout L(D, p.tok, p.n_kv, p.n_q, p.G, p.stages, p.n_rows);
   VB_CHECK_ARG(L.total <= VB_MAX_DYN_SMEM, "vb_paged_attn: %d rows / %d-token tiles need %d bytes of shared memory",
                p.n_rows, p.tok, L.total);
-  auto kern = paged_attn_kernel<D, HI>;
+  auto kern = paged_attn_kernel<D, HI, MINB>;
   VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, VB_MAX_DYN_SMEM));
   const int threads = (p.n_kv * (p.tok / 16) + 1) * 32;
   VB_LAUNCH_PDL(kern, grid, threads, L.total, stream, p);
@@ -682,14 +707,31 @@ int vb_paged_attn(void* d_out, const void* d_q, const void* d_kv, int64_t slab_b
   p.tok = chunk_tokens;
   p.out_xt_tile = out_xt_tile;
   p.scale_log2 = sm_scale * 1.4426950408889634f;
-  // deepest ring that fits next to the fixed buffers
+  // deepest ring of half-stages that fits the budget next to the fixed buffers.  Measured on B200 (28 launches back to
+  // back, kv 200 / 500 / 900): a bulk-copied tile lands ~3 us after it was requested once HBM is loaded, so the stream
+  // needs ~190 KiB in flight per SM; three half-stages (two CTAs per SM, VB_ATTN_SMEM_KB=111) reach only 27 GB/s per
+  // SM and lose more in the stream than co-residency with the neighbouring kernel gains (42 vs 20 us per launch).
+  // Default: the whole SM, six half-stages.
+  static int budget = -1;
+  if (budget < 0) {
+    const char* e = getenv("VB_ATTN_SMEM_KB");
+    const int kb = e ? atoi(e) : 224;
+    budget = (kb >= 64 && kb <= 227 ? kb : 224) * 1024;
+  }
   int stages = ATTN_MAX_STAGES;
-  while (stages > 2 && AttnLayout(head_dim, p.tok, n_kv, n_q, p.G, stages, n_rows).total > VB_MAX_DYN_SMEM) --stages;
+  while (stages > 2 && AttnLayout(head_dim, p.tok, n_kv, n_q, p.G, stages, n_rows).total > budget) --stages;
+  VB_CHECK_ARG(AttnLayout(head_dim, p.tok, n_kv, n_q, p.G, stages, n_rows).total <= VB_MAX_DYN_SMEM,
+               "vb_paged_attn: %d rows need more shared memory than an SM has", n_rows);
   p.stages = stages;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool hi = p.G > 8;
-  if (head_dim == 128) return hi ? launch_attn<128, true>(p, grid_ctas, st) : launch_attn<128, false>(p, grid_ctas, st);
-  return hi ? launch_attn<64, true>(p, grid_ctas, st) : launch_attn<64, false>(p, grid_ctas, st);
+  const bool two = 2 * (AttnLayout(head_dim, p.tok, n_kv, n_q, p.G, stages, n_rows).total + 1024) <= 232448;
+  if (two) {
+    if (head_dim == 128) return hi ? launch_attn<128, true, 2>(p, grid_ctas, st) : launch_attn<128, false, 2>(p, grid_ctas, st);
+    return hi ? launch_attn<64, true, 2>(p, grid_ctas, st) : launch_attn<64, false, 2>(p, grid_ctas, st);
+  }
+  if (head_dim == 128) return hi ? launch_attn<128, true, 1>(p, grid_ctas, st) : launch_attn<128, false, 1>(p, grid_ctas, st);
+  return hi ? launch_attn<64, true, 1>(p, grid_ctas, st) : launch_attn<64, false, 1>(p, grid_ctas, st);
 }
 
 }  // extern "C"

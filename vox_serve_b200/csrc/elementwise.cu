@@ -230,6 +230,7 @@ __global__ void __launch_bounds__(RR_THREADS) reduce_residual_rmsnorm_kernel(
   const size_t t = blockIdx.y;
   const int cols = N / parts, c0 = part * cols;
   const size_t plane = static_cast<size_t>(T) * N;
+  const int tr = (threadIdx.x == 0 && trace_block0()) ? trace_begin(5, split_k) : -1;
   // the norm weights are parameters: fetched before the dependency resolves
   uint2 w2[RR_MAX_ITER];
 #pragma unroll
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(RR_THREADS) reduce_residual_rmsnorm_kernel(
       for (int j = 0; j < 4; ++j) ss += h[it][j] * h[it][j];
     }
   }
-  if (!normed_out) return;      // uniform across the cluster: no barrier is pending
+  if (!normed_out) { trace_end(tr); return; }      // uniform across the cluster: no barrier is pending
   ss = block_sum(ss, red);
   float total = ss;
   if (parts > 1) {
@@ -297,6 +298,7 @@ __global__ void __launch_bounds__(RR_THREADS) reduce_residual_rmsnorm_kernel(
       *reinterpret_cast<uint2*>(normed_out + oi) = o;
     }
   }
+  trace_end(tr);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -308,14 +310,16 @@ __global__ void __launch_bounds__(256) qkv_rope_append_kernel(
     int split_k, const int32_t* __restrict__ pos, const float* __restrict__ freq,
     const int32_t* __restrict__ row_page, const int32_t* __restrict__ row_slot, int T, int n_q, int n_kv, int D,
     int page_size, int rotary_dim, int interleave, int heads_per_cta) {
+  const int tr = (threadIdx.x == 0 && trace_block0()) ? trace_begin(6, split_k) : -1;
   pdl_sync();
+  if (tr >= 0) trace_mark(24);
   extern __shared__ float sm[];  // [2*rotary_dim cos/sin][heads_per_cta * D values]
   float* cs = sm;
   float* val = sm + 2 * rotary_dim;
   const size_t t = blockIdx.y;
   const int n_heads = n_q + 2 * n_kv;
   const int h_lo = blockIdx.x * heads_per_cta, h_hi = min(n_heads, h_lo + heads_per_cta);
-  if (h_lo >= h_hi) return;
+  if (h_lo >= h_hi) { trace_end(tr); return; }
   const int W = n_heads * D, w_lo = h_lo * D, w_n = (h_hi - h_lo) * D;
   const size_t plane = static_cast<size_t>(T) * W;
   const float p = static_cast<float>(pos[t]);
@@ -368,6 +372,7 @@ __global__ void __launch_bounds__(256) qkv_rope_append_kernel(
         *reinterpret_cast<uint32_t*>(kd + slab + (j - row_elems)) = packed;
     }
   }
+  trace_end(tr);
 }
 
 __global__ void embedding_kernel(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ table,

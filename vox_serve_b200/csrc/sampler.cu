@@ -436,6 +436,53 @@ __global__ void __launch_bounds__(SMP_THREADS, 1) sample_kernel(const SamplePara
   trace_end(tr);
 }
 
+// Standard normal draws (SNAC NoiseBlock input, vox_serve/tokenizer/snac.py:208 uses torch.randn): one Philox4x32-10
+// block per 4 outputs, counter = (offset, quad index), two Box-Muller pairs.  With a device state {seed, offset,
+// arrivals} the offset advances by one per launch (last block to arrive), so CUDA-graph replays keep drawing.
+__global__ void __launch_bounds__(256) randn_kernel(float* __restrict__ out, long long n, unsigned long long seed_,
+                                                    unsigned long long offset_, unsigned long long* state) {
+  pdl_sync();
+  const unsigned long long seed = state ? state[0] : seed_, offset = state ? state[1] : offset_;
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q * 4 < n) {
+    uint32_t c[4] = {static_cast<uint32_t>(offset), static_cast<uint32_t>(offset >> 32), static_cast<uint32_t>(q),
+                     static_cast<uint32_t>(static_cast<unsigned long long>(q) >> 32) ^ 0x5eed0000u};
+    uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      philox_round(c, k0, k1);
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+    float z[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      // u1 in (0, 1], u2 in [0, 1): 2^-32 granularity (torch's curand path uses the same resolution)
+      const float u1 = (static_cast<float>(c[2 * h]) + 1.0f) * 2.3283064365386963e-10f;
+      const float u2 = static_cast<float>(c[2 * h + 1]) * 2.3283064365386963e-10f;
+      const float rad = sqrtf(-2.0f * logf(u1));
+      float s, co;
+      sincospif(2.0f * u2, &s, &co);
+      z[2 * h] = rad * co;
+      z[2 * h + 1] = rad * s;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (q * 4 + j < n) out[q * 4 + j] = z[j];
+  }
+  if (state) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned long long old = atomicAdd(&state[2], 1ull);
+      if (old == static_cast<unsigned long long>(gridDim.x) - 1ull) {
+        state[2] = 0ull;
+        state[1] = offset + 1ull;
+      }
+    }
+  }
+}
+
 __global__ void penalty_kernel(__nv_bfloat16* out, const SampleParams p) {
   const int row = blockIdx.y;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.vocab; i += gridDim.x * blockDim.x)
@@ -539,6 +586,17 @@ int vb_sample(int64_t* d_out_ids, const void* d_logits, int rows, int vocab, int
   VB_CHECK_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      2 * SMP_PAIRS * SMP_THREADS * static_cast<int>(sizeof(uint32_t))));
   VB_LAUNCH_PDL_CLUSTER(sample_kernel, dim3(S, rows), SMP_THREADS, smem, st, S, p, npairs);
+  return 0;
+}
+
+int vb_randn(float* d_out, int64_t n, uint64_t seed, uint64_t offset, uint64_t* d_rng_state, void* stream) {
+  VB_CHECK_ARG(d_out, "vb_randn: null pointer");
+  VB_CHECK_ARG(n >= 0 && n < (static_cast<int64_t>(1) << 40), "vb_randn: bad element count");
+  if (n == 0) return 0;
+  const long long quads = (n + 3) / 4;
+  const unsigned blocks = static_cast<unsigned>((quads + 255) / 256);
+  VB_LAUNCH_PDL(randn_kernel, blocks, 256, 0, stream, d_out, static_cast<long long>(n), seed, offset,
+                reinterpret_cast<unsigned long long*>(d_rng_state));
   return 0;
 }
 

@@ -46,8 +46,8 @@ class LlamaDims:
         return cls(3072, 28, 24, 8, 128, 8192, 156940)
 
 
-def hf_layer_names(i: int) -> Dict[str, str]:
-    p = f"model.layers.{i}."
+def hf_layer_names(i: int, prefix: str = "model.") -> Dict[str, str]:
+    p = f"{prefix}layers.{i}."
     return {"ln1": p + "input_layernorm.weight", "ln2": p + "post_attention_layernorm.weight",
             "q": p + "self_attn.q_proj.weight", "k": p + "self_attn.k_proj.weight",
             "v": p + "self_attn.v_proj.weight", "o": p + "self_attn.o_proj.weight",
@@ -63,25 +63,60 @@ class LlamaWeights:
         self.dims, self.device = dims, torch.device(device)
         self.gu_half = ops.gate_up_tile_half(dims.intermediate_size) if self.device.type == "cuda" else 64
         self.embed = self.norm = self.lm_head = None
+        self.heads: List[object] = []
+        self.arena: Optional[torch.Tensor] = None
         self.layers: List[Dict[str, torch.Tensor]] = []
 
     @classmethod
-    def from_state_dict(cls, sd, dims: LlamaDims, device="cuda"):
+    def from_state_dict(cls, sd, dims: LlamaDims, device="cuda", prefix: str = "model.",
+                        embed_key: Optional[str] = "model.embed_tokens.weight", head_key: str = "lm_head.weight",
+                        heads: Optional[List[torch.Tensor]] = None):
+        """``prefix`` / ``embed_key`` / ``head_key``: where the decoder stack, the token embedding (None: the caller
+        supplies input embeddings) and the output head live in ``sd`` -- HF Llama names by default; the CSM backbone is
+        ``backbone_model.`` + ``lm_head.weight``, its depth decoder ``depth_decoder.model.`` with ``heads`` = one
+        [vocab, hidden] matrix per depth position (csm.py:235-255) instead of a single lm_head."""
         self = cls(dims, device)
         dev = self.device
 
         def put(t):
             return t.to(device=dev, dtype=BF16).contiguous()
 
-        self.embed = put(sd["model.embed_tokens.weight"])
-        self.norm = put(sd["model.norm.weight"])
-        self.lm_head = ops.pack_weight(put(sd["lm_head.weight"] if "lm_head.weight" in sd
-                                           else sd["model.embed_tokens.weight"]), 128)
+        self.embed = put(sd[embed_key]) if embed_key is not None else None
+        self.norm = put(sd[prefix + "norm.weight"])
+        # every projection of a step lives in ONE arena in the order a decode step streams it (per layer qkv, o,
+        # gate/up, down; then lm_head): the L2 prefetcher walks it front to back (ops.weight_prefetch)
+        H, I, D = dims.hidden_size, dims.intermediate_size, dims.head_dim
+        qkv_rows = (dims.num_attention_heads + 2 * dims.num_key_value_heads) * D
+        gu_tiles = (I + self.gu_half - 1) // self.gu_half
+        per_layer = [ops.weight_tiles_bytes(qkv_rows, H, D), ops.weight_tiles_bytes(H, dims.num_attention_heads * D, 128),
+                     ops.weight_tiles_bytes(2 * gu_tiles * self.gu_half, H, 2 * self.gu_half),
+                     ops.weight_tiles_bytes(H, I, 128)]
+        head_bytes = ops.weight_tiles_bytes(dims.vocab_size, H, 128)
+        n_heads_out = len(heads) if heads is not None else 1
+        if dev.type == "cuda":
+            self.arena = torch.empty(dims.num_hidden_layers * sum(per_layer) + n_heads_out * head_bytes, dtype=torch.uint8,
+                                     device=dev)
+            assert self.arena.data_ptr() % 1024 == 0
+        off = 0
         for i in range(dims.num_hidden_layers):
-            n = hf_layer_names(i)
+            n = hf_layer_names(i, prefix)
+            slots = []
+            for nb in per_layer:
+                slots.append(self.arena[off:off + nb] if self.arena is not None else None)
+                off += nb
             self.layers.append(self.pack_layer(put(sd[n["ln1"]]), put(sd[n["q"]]), put(sd[n["k"]]), put(sd[n["v"]]),
                                                put(sd[n["o"]]), put(sd[n["ln2"]]), put(sd[n["gate"]]),
-                                               put(sd[n["up"]]), put(sd[n["down"]]), self.gu_half, dims.head_dim))
+                                               put(sd[n["up"]]), put(sd[n["down"]]), self.gu_half, dims.head_dim,
+                                               out=slots))
+        if heads is None:
+            heads = [sd[head_key] if head_key in sd else sd[embed_key]]
+        self.heads = []
+        for hw in heads:
+            assert tuple(hw.shape) == (dims.vocab_size, H), (tuple(hw.shape), dims.vocab_size, H)
+            self.heads.append(ops.pack_weight(put(hw), 128,
+                                              out=self.arena[off:off + head_bytes] if self.arena is not None else None))
+            off += head_bytes
+        self.lm_head = self.heads[0]
         if dev.type == "cuda":
             # the row-major originals were just dropped: hand their blocks back NOW, not inside the first CUDA-graph
             # capture on the request path (capture_begin empties the allocator cache: ~1 s for 6.6 GB of blocks)
@@ -90,26 +125,30 @@ class LlamaWeights:
         return self
 
     @staticmethod
-    def pack_layer(ln1, q, k, v, o, ln2, gate, up, down, gu_half: int = 64, head_dim: int = 128) -> Dict[str, object]:
+    def pack_layer(ln1, q, k, v, o, ln2, gate, up, down, gu_half: int = 64, head_dim: int = 128,
+                   out=None) -> Dict[str, object]:
         """Projection weights leave here re-tiled for the GEMM kernel (ops.pack_weight): one head per QKV tile,
-        128-row O / down tiles, gu_half gate + gu_half up rows per gate/up tile.  The row-major copies are dropped."""
-        return {"ln1": ln1, "ln2": ln2, "qkv": ops.pack_weight(torch.cat((q, k, v), 0).contiguous(), head_dim),
-                "o": ops.pack_weight(o, 128),
-                "gu": ops.pack_weight(ops.interleave_gate_up(gate, up, gu_half), 2 * gu_half),
-                "down": ops.pack_weight(down, 128)}
+        128-row O / down tiles, gu_half gate + gu_half up rows per gate/up tile.  The row-major copies are dropped.
+        out: four uint8 slices (qkv, o, gate/up, down) to pack into, e.g. of the weight arena."""
+        out = out or [None] * 4
+        return {"ln1": ln1, "ln2": ln2,
+                "qkv": ops.pack_weight(torch.cat((q, k, v), 0).contiguous(), head_dim, out=out[0]),
+                "o": ops.pack_weight(o, 128, out=out[1]),
+                "gu": ops.pack_weight(ops.interleave_gate_up(gate, up, gu_half), 2 * gu_half, out=out[2]),
+                "down": ops.pack_weight(down, 128, out=out[3])}
 
     def nbytes(self) -> int:
         """logical bf16 bytes (N * K * 2 per projection; the packed tiles add only tail padding)"""
         def nb(t):
             return t.logical_bytes() if isinstance(t, ops.PackedWeight) else 2 * t.numel()
-        n = nb(self.embed) + nb(self.norm) + nb(self.lm_head)
+        n = (nb(self.embed) if self.embed is not None else 0) + nb(self.norm) + sum(nb(h) for h in self.heads)
         for l in self.layers:
             n += sum(nb(t) for t in l.values())
         return n
 
     def streamed_bytes_per_step(self) -> int:
         """Weight bytes one decode step must read (everything but the embedding table)."""
-        return self.nbytes() - 2 * self.embed.numel()
+        return self.nbytes() - (2 * self.embed.numel() if self.embed is not None else 0)
 
 
 class LlamaEngine:
@@ -172,6 +211,43 @@ class LlamaEngine:
             if self.chain_ok else None
         self.ssq = torch.zeros(max(1, (H + 127) // 128) * self.FUSED_MAX_ROWS, dtype=torch.float32, device=dev)
         self.rope_cs = torch.zeros(self.FUSED_MAX_ROWS, 2, D, dtype=torch.float32, device=dev)
+        self._init_prefetch()
+
+    # ---- L2 weight prefetcher (decode-sized steps, default layer mode) ----------------------------------
+    # VB_L2_PREFETCH=0 disables it; VB_L2_WINDOW_MB = how far ahead of the projections' consumption it may run
+    l2_prefetch = os.environ.get("VB_L2_PREFETCH", "1") != "0"
+    l2_window_mb = int(os.environ.get("VB_L2_WINDOW_MB", "64"))
+
+    def _init_prefetch(self) -> None:
+        """Consumption-order table of the decode step's weight stream for ops.weight_prefetch: one row per projection
+        launch {virtual offset, offset in the arena, CTAs, bytes per stage, stages per CTA}."""
+        w, d = self.w, self.dims
+        self.pf_table = self.pf_virt = None
+        if w.arena is None or self.device.type != "cuda":
+            return
+        base = w.arena.data_ptr()
+        rows, virt_of, virt = [], {}, 0
+        plan = [("qkv", self.split_qkv), ("o", self.split_o), ("gu", 1), ("down", self.split_down)]
+        launches = [(i, k, L[k], s) for i, L in enumerate(w.layers) for k, s in plan] + [(-1, "lm_head", w.lm_head, 1)]
+        for i, k, pw, split in launches:
+            num_kb = (pw.K + 63) // 64
+            if num_kb % split != 0 or pw.data.data_ptr() < base:
+                return                      # uneven split-K ranges: no simple slice arithmetic -> no prefetcher
+            n_ctas = (pw.N + pw.tile_rows - 1) // pw.tile_rows * split
+            a_stage, stages = pw.tile_rows * 128, num_kb // split
+            rows.append([virt, pw.data.data_ptr() - base, n_ctas, a_stage, stages])
+            virt_of[(i, k)] = virt
+            virt += n_ctas * a_stage * stages
+        self.pf_table = torch.tensor(rows, dtype=torch.int64, device=self.device)
+        self.pf_virt = virt_of
+        self.pf_progress = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self.pf_stream = torch.cuda.Stream(device=self.device)
+
+    def _tag(self, layer: int, key: str) -> None:
+        if self._pf_live:
+            ops.tag_next_gemm(self.pf_progress, self.pf_virt[(layer, key)])
+
+    _pf_live = False
 
     FUSED_MAX_ROWS = 64
 
@@ -182,18 +258,34 @@ class LlamaEngine:
         # large-T (prefill) problems already fill the machine with token tiles x N tiles
         return base if rows <= 64 else 1
 
-    def forward(self, input_ids: torch.Tensor, position_ids: torch.Tensor, n_rows: int,
+    def forward(self, input_ids: Optional[torch.Tensor], position_ids: torch.Tensor, n_rows: int,
                 last_rows: Optional[torch.Tensor] = None, n_out: Optional[int] = None,
-                plan: Optional[ops.RowPlan] = None, last_rows_offset: int = 0) -> torch.Tensor:
+                plan: Optional[ops.RowPlan] = None, last_rows_offset: int = 0, head=None, want_hidden: bool = False):
         """input_ids / position_ids int32 [n_rows] on the device; self.plan must hold the step's row plan
         (ops.plan_rows).  Returns logits [n_out or n_rows, vocab] bf16 (a view of the static buffer).
-        last_rows (int32 [n_out]) selects the rows whose logits are needed (prefill: qo_indptr[1:] - 1)."""
+        last_rows (int32 [n_out]) selects the rows whose logits are needed (prefill: qo_indptr[1:] - 1).
+        input_ids None: the caller has already written the input embeddings into ``self.hidden[:n_rows]`` (models
+        whose inputs are sums of several embeddings or projected features, csm.py:647-654).  ``head``: the packed
+        output head to use instead of ``w.lm_head`` (per-position heads of a depth decoder).  ``want_hidden``: also
+        return the final-normed rows [n_out or n_rows, hidden] bf16, row-major (the backbone state a depth decoder
+        starts from, csm.py:290-300)."""
         d, w, R = self.dims, self.w, n_rows
         plan = self.plan if plan is None else plan
         if R > self.max_rows:
             raise VoxB200Error(f"{R} rows exceed the engine's max_rows {self.max_rows}")
         hidden, normed = self.hidden[:R], self.normed[:R]
-        ops.embedding(w.embed, input_ids, out=hidden)
+        # decode-sized steps in the default layer mode run with the L2 weight prefetcher beside them (own stream):
+        # reset the progress word in the launch chain, fork, and join after lm_head
+        self._pf_live = (self.l2_prefetch and self.pf_table is not None and R <= self.FUSED_MAX_ROWS and self.tiled_acts
+                         and (self.force_unfused or not self.fused_ok) and head is None)
+        if self._pf_live:
+            main = torch.cuda.current_stream()
+            ops.set_u32(self.pf_progress, 0)
+            self.pf_stream.wait_stream(main)
+            with torch.cuda.stream(self.pf_stream):
+                ops.weight_prefetch(w.arena, self.pf_table, self.pf_progress, self.l2_window_mb << 20, self.sms)
+        if input_ids is not None:
+            ops.embedding(w.embed, input_ids, out=hidden)
         x_final = normed
         if R <= self.FUSED_MAX_ROWS and self.fused_ok and not self.force_unfused:
             self._layers_fused(position_ids, R, plan)
@@ -202,16 +294,25 @@ class LlamaEngine:
             ops.rmsnorm(hidden, w.norm, d.rms_norm_eps, out=x_final)
         else:
             x_final = self._layers_unfused(position_ids, R, plan)
+        hidden_rows = None
+        if last_rows is not None or want_hidden:
+            if isinstance(x_final, ops.TiledAct):      # a gather needs rows: redo the final norm row-major
+                ops.rmsnorm(hidden, w.norm, d.rms_norm_eps, out=normed)
         if last_rows is not None:
             n_out = last_rows.numel() if n_out is None else n_out
-            if isinstance(x_final, ops.TiledAct):      # a gather needs rows: redo the final norm row-major (prefill-only path)
-                ops.rmsnorm(hidden, w.norm, d.rms_norm_eps, out=normed)
             x = ops.gather_rows(normed, last_rows, out=self.last_normed[:n_out], idx_offset=last_rows_offset)
+            hidden_rows = x
         else:
             n_out, x = R, x_final
+            hidden_rows = normed
         if n_out > self.max_out_rows:
             raise VoxB200Error(f"logits requested for {n_out} rows; pass last_rows (max {self.max_out_rows})")
-        return ops.gemm(x, w.lm_head, mode=0, out=self.logits[:n_out])
+        self._tag(-1, "lm_head")
+        logits = ops.gemm(x, w.lm_head if head is None else head, mode=0, out=self.logits[:n_out])
+        if self._pf_live:
+            torch.cuda.current_stream().wait_stream(self.pf_stream)
+            self._pf_live = False
+        return (logits, hidden_rows) if want_hidden else logits
 
     # How decode-sized steps (<= FUSED_MAX_ROWS rows) run their layers.  Measured on B200 (tests/ablate_step.py,
     # Orpheus-3B, 32 rows, kv 728): separate kernels 2.72 ms, fused projections 2.96 ms, persistent chain 3.42 ms per
@@ -283,14 +384,18 @@ class LlamaEngine:
         q = self.q[:R]
         n_layers = len(w.layers)
         for i, L in enumerate(w.layers):
+            self._tag(i, "qkv")
             p = ops.gemm(normed, L["qkv"], mode=1, split_k=s_qkv, out=self._partials(s_qkv, R, self.qkv_w), tile_rows=D)
             ops.qkv_rope_append(p, self.kv_cache[i], position_ids, self.freq, plan, hq, hkv, D, q_out=q)
             ops.paged_attn(q, self.kv_map, i * self.pages_per_layer, plan, R, hkv, self.page_size, self.chunk,
                            self.attn_ws, out=attn_o, grid_ctas=self.attn_grid)
+            self._tag(i, "o")
             p = ops.gemm(attn_o if attn_tiled else attn_o.view(R, hq * D), L["o"], mode=1, split_k=s_o,
                          out=self._partials(s_o, R, H))
             ops.reduce_residual_rmsnorm(p, hidden, L["ln2"], d.rms_norm_eps, hidden_out=hidden, normed_out=normed)
+            self._tag(i, "gu")
             ops.gemm(normed, L["gu"], mode=2, out=act, tile_rows=2 * self.gu_half, n_out=I)
+            self._tag(i, "down")
             p = ops.gemm(act, L["down"], mode=1, split_k=s_dn, out=self._partials(s_dn, R, H))
             nxt = w.layers[i + 1]["ln1"] if i + 1 < n_layers else w.norm
             ops.reduce_residual_rmsnorm(p, hidden, nxt, d.rms_norm_eps, hidden_out=hidden, normed_out=normed)

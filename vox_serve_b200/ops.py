@@ -319,15 +319,46 @@ class PackedWeight:
         return 2 * self.N * self.K
 
 
-def pack_weight(w: torch.Tensor, tile_rows: int = 128) -> PackedWeight:
+def weight_tiles_bytes(N: int, K: int, tile_rows: int) -> int:
+    n = _lib.load().vb_weight_tiles_bytes(int(N), int(K), int(tile_rows))
+    assert n > 0, (N, K, tile_rows)
+    return n
+
+
+def pack_weight(w: torch.Tensor, tile_rows: int = 128, out: Optional[torch.Tensor] = None) -> PackedWeight:
+    """out: a uint8 slice of exactly weight_tiles_bytes(N, K, tile_rows) bytes (e.g. of the engine's weight arena)."""
     _need_cuda(w)
     assert w.dtype == BF16 and w.dim() == 2 and w.stride(1) == 1
     N, K = w.shape
-    n = _lib.load().vb_weight_tiles_bytes(N, K, tile_rows)
-    assert n > 0, (N, K, tile_rows)
-    dst = torch.empty(n, dtype=torch.uint8, device=w.device)
+    n = weight_tiles_bytes(N, K, tile_rows)
+    if out is None:
+        dst = torch.empty(n, dtype=torch.uint8, device=w.device)
+    else:
+        assert out.dtype == torch.uint8 and out.numel() == n and out.is_contiguous() and out.data_ptr() % 1024 == 0
+        dst = out
     call("vb_pack_weight_tiles", dst.data_ptr(), w.data_ptr(), N, K, w.stride(0), tile_rows, _stream())
     return PackedWeight(dst, N, K, tile_rows)
+
+
+def tag_next_gemm(progress: Optional[torch.Tensor], virt_offset: int = 0) -> None:
+    """The next projection launched from this thread publishes its weight-stream progress into ``progress`` (uint32
+    scalar viewed as int32, device); None clears a pending tag."""
+    call("vb_tag_next_gemm", _p(progress), int(virt_offset))
+
+
+def set_u32(t: torch.Tensor, value: int) -> None:
+    call("vb_set_u32", t.data_ptr(), int(value), _stream())
+
+
+def weight_prefetch(arena: torch.Tensor, op_table: torch.Tensor, progress: torch.Tensor, window_bytes: int,
+                    grid_ctas: Optional[int] = None) -> None:
+    """Launch the L2 weight prefetcher (vb_weight_prefetch) on the CURRENT stream: meant for a side stream that runs
+    beside the decode step.  op_table: int64 [n_ops, 5] on the device."""
+    _need_cuda(arena, op_table, progress)
+    assert op_table.dtype == torch.int64 and op_table.dim() == 2 and op_table.shape[1] == 5 and op_table.is_contiguous()
+    grid = device_info()[0] if grid_ctas is None else int(grid_ctas)
+    call("vb_weight_prefetch", arena.data_ptr(), op_table.data_ptr(), op_table.shape[0], progress.data_ptr(),
+         int(window_bytes), grid, _stream())
 
 
 _pack_cache: Dict[Tuple, PackedWeight] = {}
@@ -604,6 +635,50 @@ def embedding(table: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tensor
     return out
 
 
+def multi_embed_sum(out: torch.Tensor, ids: torch.Tensor, table_a: Optional[torch.Tensor], col_offset: int = 0,
+                    col0: int = 0, n_cols_a: Optional[int] = None, table_b: Optional[torch.Tensor] = None,
+                    mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out [T, dim] bf16 = masked sum over the C columns of ids [T, C] (int64, any strides) of embedding rows:
+    columns < n_cols_a from table_a at row ids + (col0 + c) * col_offset, the rest from table_b.  mask [T, C] bool/uint8
+    contiguous or None.  (vb_multi_embed_sum; csm.py:637-663)"""
+    _need_cuda(out, ids, table_a, table_b, mask)
+    assert ids.dtype == torch.int64 and ids.dim() == 2 and out.dtype == BF16 and out.dim() == 2 and out.stride(1) == 1
+    T, C = ids.shape
+    n_cols_a = C if n_cols_a is None else n_cols_a
+    m8 = None
+    if mask is not None:
+        assert mask.shape == (T, C) and mask.is_contiguous()
+        m8 = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+    dim = out.shape[1]
+    for tb in (table_a, table_b):
+        assert tb is None or (tb.dtype == BF16 and tb.is_contiguous() and tb.shape[1] == dim)
+    call("vb_multi_embed_sum", out.data_ptr(), out.stride(0), ids.data_ptr(), ids.stride(0), ids.stride(1), _p(m8),
+         _p(table_a), table_a.shape[0] if table_a is not None else 0, int(col_offset), int(col0), int(n_cols_a),
+         _p(table_b), table_b.shape[0] if table_b is not None else 0, T, C, dim, _stream())
+    return out
+
+
+def interleave_rows(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[n, d] x 2 -> [2n, d] with rows a0, b0, a1, b1, ..."""
+    _need_cuda(a, b)
+    assert a.shape == b.shape and a.dtype == b.dtype and a.is_contiguous() and b.is_contiguous() and a.dim() == 2
+    n, d = a.shape
+    out = torch.empty(2 * n, d, dtype=a.dtype, device=a.device) if out is None else out
+    call("vb_interleave_rows", out.data_ptr(), a.data_ptr(), b.data_ptr(), n, d * a.element_size(), _stream())
+    return out
+
+
+def transpose_i64(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """src int64 [C, B] (row stride arbitrary) -> [B, C]"""
+    _need_cuda(src)
+    assert src.dtype == torch.int64 and src.dim() == 2 and src.stride(1) == 1
+    C, B = src.shape
+    out = torch.empty(B, C, dtype=torch.int64, device=src.device) if out is None else out
+    assert out.stride(1) == 1
+    call("vb_transpose_i64", out.data_ptr(), src.data_ptr(), B, C, out.stride(0), src.stride(0), _stream())
+    return out
+
+
 def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None,
                 idx_offset: int = 0) -> torch.Tensor:
     _need_cuda(src, idx)
@@ -741,6 +816,23 @@ def pcm16(audio: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tens
     assert a.dtype == torch.float32
     out = torch.empty(a.shape, dtype=torch.int16, device=a.device) if out is None else out
     call("vb_pcm16", out.data_ptr(), a.data_ptr(), a.numel(), _stream())
+    return out
+
+
+def randn(n_or_out, seed: int = 0, offset: int = 0, rng_state: Optional[torch.Tensor] = None,
+          device=None) -> torch.Tensor:
+    """Standard-normal fp32 draws on the device (vb_randn): ``n_or_out`` = element count or a preallocated fp32
+    tensor.  ``rng_state`` (int64 {seed, offset, 0}, device) makes successive calls / graph replays draw fresh values."""
+    if isinstance(n_or_out, torch.Tensor):
+        out = n_or_out
+        _need_cuda(out)
+        assert out.dtype == torch.float32 and out.is_contiguous()
+    else:
+        out = torch.empty(int(n_or_out), dtype=torch.float32,
+                          device=device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+    if rng_state is not None:
+        assert rng_state.dtype == torch.int64 and rng_state.numel() >= 3 and rng_state.is_cuda
+    call("vb_randn", out.data_ptr(), out.numel(), int(seed) & ((1 << 64) - 1), int(offset), _p(rng_state), _stream())
     return out
 
 

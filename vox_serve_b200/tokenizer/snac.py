@@ -4,8 +4,9 @@
 Only the decoder + RVQ ``from_codes`` exist here (the encoder is not on the serving path).  At load time
 the weight-norm parametrisation is folded once (the reference re-derives ``g*v/||v||`` on every forward,
 snac.py:244-249), transposed-conv weights are repacked per output phase, and every Snake is assigned to
-the epilogue of the stage that produces its input.  ``NoiseBlock`` noise is drawn with ``torch.randn`` on
-the current CUDA generator like the reference (snac.py:208) unless explicit noise tensors are passed.
+the epilogue of the stage that produces its input.  ``NoiseBlock`` noise (``torch.randn`` in the reference,
+snac.py:208) comes from the library's own Philox normal generator (``vb_randn``: one launch for the four blocks,
+device-side offset, CUDA-graph replayable) unless explicit noise tensors / a ``noise_source`` are given.
 """
 from __future__ import annotations
 
@@ -48,6 +49,7 @@ class SNAC:
         # NoiseBlock input (snac.py:206-212): None = torch.randn on the current CUDA generator like the reference;
         # a callable(shapes) -> tensors lets tests inject the oracle's noise
         self.noise_source = None
+        self.noise_state = None          # device {seed, offset, arrivals} of the default noise stream (ops.randn)
 
     # ---- loading -----------------------------------------------------------------------------
     @classmethod
@@ -111,7 +113,17 @@ class SNAC:
         self.w = {k: v.contiguous().to(dev) for k, v in w.items()}
         self._pack_tensor_core_weights()
         self.loaded = True
+        self.noise_state = None
         return self
+
+    def ensure_noise_state(self) -> torch.Tensor:
+        """Create the device {seed, offset, arrivals} of the default noise stream now (a host -> device copy: must not
+        happen inside a CUDA-graph capture)."""
+        if self.noise_state is None:
+            dev = self.device
+            seed = torch.cuda.default_generators[dev.index or 0].initial_seed() & ((1 << 62) - 1)
+            self.noise_state = torch.tensor([seed ^ 0x534E4143, 0, 0], dtype=torch.int64, device=dev)
+        return self.noise_state
 
     def _pack_tensor_core_weights(self):
         """The 1x1 and transposed-conv weights whose input width is a multiple of 32 channels are re-tiled for the
@@ -249,7 +261,14 @@ class SNAC:
         nb = len(self.decoder_rates)
         if noises is None:
             shapes = self.noise_shapes(B, T)
-            noises = self.noise_source(shapes) if self.noise_source is not None else [torch.randn(s, **f32) for s in shapes]
+            if self.noise_source is not None:
+                noises = self.noise_source(shapes)
+            else:
+                # one launch for the four NoiseBlock inputs (the reference draws torch.randn per block, snac.py:208);
+                # the device-side offset advances per call, so a captured vocoder graph draws fresh noise every replay
+                sizes = [math.prod(s) for s in shapes]
+                flat = ops.randn(torch.empty(sum(sizes), **f32), rng_state=self.ensure_noise_state())
+                noises = [t.view(s) for t, s in zip(torch.split(flat, sizes), shapes)]
         for bi, s in enumerate(self.decoder_rates):
             (c_lo, c_hi), units = blocks[bi]
             cin, cout = ch, ch // 2

@@ -179,6 +179,13 @@ class ModelWorker:
         # the vocoder runs on its own stream: it only needs tokens the host has already seen, so it does not have to
         # queue behind the LM step that is still in flight when the scheduler runs one step ahead
         self.detok_stream = torch.cuda.Stream()
+        # one CUDA graph per vocoder batch size: window gather -> frame de-interleave -> SNAC -> PCM16 as ONE replay
+        # (the reference captures its detokenizer the same way, cuda_graph_worker.py:560-700); own memory pool because
+        # these replays overlap LM steps on the main stream
+        self.voc_graphs: Dict[int, tuple] = {}
+        self.voc_pool = None
+        self.voc_win = torch.zeros(self.max_chunks, m.detokenize_interval, dtype=torch.int64, device=dev)
+        self.voc_pcm = torch.zeros(self.max_chunks, m.n_channels, m.output_audio_length, dtype=torch.int16, device=dev)
         self.gpu_launches = 0     # launches issued by this worker's own kernels (graph nodes counted at capture)
         self._graph_nodes: Dict[int, int] = {}
 
@@ -192,7 +199,38 @@ class ModelWorker:
             if B not in self.decode_graphs:
                 self._capture_decode(int(B))
                 n += 1
+            if self._vocoder_graphable() and B not in self.voc_graphs:
+                self._capture_vocoder(int(B))
         return n
+
+    def _vocoder_graphable(self) -> bool:
+        dec = getattr(self.model, "audio_decoder", None)
+        return self.use_cuda_graph and dec is not None and getattr(dec, "noise_source", None) is None
+
+    def _vocoder_body(self, n: int):
+        interval = self.detokenize_interval
+        ops.gather_windows(self.history, self.win_dev[0], self.win_dev[1], self.win_dev[2], interval,
+                           out=self.voc_win[:n], n=n)
+        audio = self.model.postprocess(self.voc_win[:n].view(n, interval, 1))
+        ops.pcm16(audio, out=self.voc_pcm[:n])
+
+    def _capture_vocoder(self, n: int):
+        dec = self.model.audio_decoder
+        if hasattr(dec, "ensure_noise_state"):
+            dec.ensure_noise_state()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        ds = self.detok_stream
+        ds.wait_stream(torch.cuda.current_stream())
+        before = ops.launch_count()
+        with torch.cuda.stream(ds):
+            with torch.cuda.graph(g, pool=self.voc_pool, stream=ds):
+                self._vocoder_body(n)
+        torch.cuda.current_stream().wait_stream(ds)
+        if self.voc_pool is None:
+            self.voc_pool = g.pool()
+        self.voc_graphs[n] = (g, ops.launch_count() - before)
+        return self.voc_graphs[n]
 
     # ---- step inputs (worker/base.py:210-360) ---------------------------------------------------
     def prepare_lm_inputs(self, lm_requests: List[Request], detokenize_requests: List[Request]) -> Optional[LMInputs]:
@@ -372,13 +410,18 @@ class ModelWorker:
             ds = self.detok_stream
             # no cross-stream wait: every token a window refers to has already been read back by the host (its
             # step's ids-ready event was synchronised), so the history writes of those steps are complete
+            graphable = self._vocoder_graphable()
+            if graphable and n not in self.voc_graphs:
+                self._capture_vocoder(n)             # (start-up normally captured 1..max_batch_size already)
             with torch.cuda.stream(ds):
                 self.win_dev.copy_(self.win_host, non_blocking=True)
-                windows = ops.gather_windows(self.history, self.win_dev[0], self.win_dev[1], self.win_dev[2], interval,
-                                             n=n)
-                audio = self.model.postprocess(windows.view(n, interval, 1))
-                pcm = ops.pcm16(audio)
-                self.pcm_host[:n].copy_(pcm, non_blocking=True)
+                if graphable:
+                    g, nodes = self.voc_graphs[n]
+                    g.replay()
+                    self.gpu_launches += nodes
+                else:                                # injected noise (parity tests): the eager launch sequence
+                    self._vocoder_body(n)
+                self.pcm_host[:n].copy_(self.voc_pcm[:n], non_blocking=True)
             ds.synchronize()
             self.nvtx_range_pop()
             pcm_np = self.pcm_host.numpy()
