@@ -135,19 +135,30 @@ int vb_gemm_t_tile(int T);
  *                       its progress through its weights into *d_progress: KiB of the step's virtual weight stream
  *                       consumed so far = (virt_offset_bytes + stages issued x CTAs x stage bytes) / 1024;
  *   vb_set_u32:         *d_ptr = value as a kernel of the launch chain (resets the progress word of a step);
- *   vb_weight_prefetch: one warp per CTA walks d_ops (int64 [n_ops][5] = {virtual offset, offset in d_arena, CTAs,
- *                       bytes per stage, stages per CTA}; slices of CTA c at phys + c * stages * stage bytes) in
- *                       consumption order and prefetches into L2 whatever is less than window_bytes ahead of
- *                       *d_progress; meant for a second stream beside the decode step.  Gives up (returns) when the
- *                       progress word stops moving. */
+ *   vb_tag_next_attn:   the next vb_paged_attn of this host thread publishes into *d_progress_tiles the number of KV
+ *                       tiles the step has consumed: layer_ordinal * (tiles of one layer) + tiles issued so far;
+ *   vb_weight_prefetch: one warp per CTA walks d_ops in consumption order and prefetches into L2 whatever is less than
+ *                       window_bytes ahead of what has been consumed (d_progress[0] KiB of weights + d_progress[1] KV
+ *                       tiles); meant for a second stream beside the decode step.  d_ops: int64 [n_ops][6] =
+ *                       {weight bytes before the op, attention ops before it, offset, CTAs, bytes per stage, stages
+ *                       per CTA}.  A projection (bytes per stage > 0) owns slices at d_arena + offset + c * stages *
+ *                       stage bytes; an attention op (bytes per stage == 0) stands for one layer's KV (offset = the
+ *                       layer's first slab), resolved through the step's row plan (vb_plan_rows outputs) exactly as
+ *                       vb_paged_attn tiles it over attn_grid_ctas CTAs; d_kv NULL skips those ops.  Gives up
+ *                       (returns) when the progress words stop moving. */
 int vb_tag_next_gemm(uint32_t* d_progress, uint64_t virt_offset_bytes);
+int vb_tag_next_attn(uint32_t* d_progress_tiles, int layer_ordinal);
 int vb_set_u32(uint32_t* d_ptr, uint32_t value, void* stream);
 int vb_weight_prefetch(const void* d_arena, const int64_t* d_ops, int n_ops, const uint32_t* d_progress,
-                       uint64_t window_bytes, int grid_ctas, void* stream);
+                       uint64_t window_bytes, int grid_ctas, const void* d_kv, const int32_t* d_row_chunk_start,
+                       const int32_t* d_row_kvlen, const int32_t* d_row_pagebase, const int32_t* d_kv_indices, int n_rows,
+                       int page_size, int chunk_tokens, int kv_row_bytes, int attn_grid_ctas, void* stream);
 /* d_x_tiles (optional): X in the XT(vb_gemm_t_tile(T)) layout -- then x_map may be NULL; y_tiled (mode 2 only): write
  * Y in the XT(vb_gemm_t_tile(T)) layout over n_out columns (it is the down projection's activation). */
 int vb_gemm_bf16(void* d_y, const void* d_w_tiles, const void* x_map, const void* d_x_tiles, int T, int N, int K,
-                 int ldy, int mode, int split_k, int tile_rows, int n_out, int y_tiled, void* stream);
+                 int ldy, int mode, int split_k, int tile_rows, int n_out, int y_tiled, const void* d_bias, void* stream);
+/* (d_bias: optional bf16 [N], mode 0 only: y = bf16(x w^T + bias), one rounding -- nn.Linear with bias, e.g.
+ * Qwen3-TTS small_to_mtp_projection, vox_serve/model/qwen3_tts.py:923-930) */
 
 /* ---- fused decode projections (T <= 64): one launch each for what orpheus.py:81-151 does between Linears ----
  * x_map: vb_tensor_map_2d_bf16(X, T, K, ldx, t_tile) with t_tile = 16 / 32 / 64 (smallest >= T).
@@ -226,7 +237,10 @@ int vb_reduce_residual_rmsnorm(void* d_hidden_out, void* d_normed_out, const flo
  * layer cache (orpheus.py:91-106 + flashinfer_utils.py:243-244).  partials [split_k][T][(n_q+2 n_kv) D]. */
 int vb_qkv_rope_append(void* d_q_out, void* d_layer_kv, const float* d_partials, int split_k, const int32_t* d_pos,
                        const float* d_freq, const int32_t* d_row_page, const int32_t* d_row_slot, int T, int n_q,
-                       int n_kv, int head_dim, int page_size, int rotary_dim, int interleave, void* stream);
+                       int n_kv, int head_dim, int page_size, int rotary_dim, int interleave, const void* d_q_norm,
+                       const void* d_k_norm, float norm_eps, void* stream);
+/* (d_q_norm / d_k_norm: optional bf16 [head_dim] weights of a per-head RMSNorm applied to every q and k head between the
+ * bf16 rounding of the projection and the rotation -- Qwen3's q_norm / k_norm, vox_serve/model/qwen3_tts.py:603-625) */
 /* slot-resident decode state (no host work between CUDA-graph replays; the reference does this bookkeeping
  * in Python every step, worker/base.py:312-325, orpheus.py:447-458):
  *   vb_decode_advance:  kv_len[b] += 1, position[b] += 1 for active rows (d_active NULL = all);
@@ -261,7 +275,14 @@ int vb_embedding(void* d_out, const void* d_table, const int32_t* d_ids, int T, 
  *   vb_transpose_i64:   dst[r][c] = src[c][r] (codebook-major device frame buffer -> request-major ids). */
 int vb_multi_embed_sum(void* d_out, int ld_out, const int64_t* d_ids, int64_t ld_t, int64_t ld_c, const uint8_t* d_mask,
                        const void* d_table_a, int64_t rows_a, int64_t col_offset, int col0, int n_cols_a,
-                       const void* d_table_b, int64_t rows_b, int T, int C, int dim, void* stream);
+                       const void* d_table_b, int64_t rows_b, int T, int C, int dim, int round_each, void* stream);
+/* (round_each != 0: the running sum is rounded to bf16 after every column -- a chain of bf16 `+=`, qwen3_tts.py:2002)
+ * vb_talker_embed: Qwen3-TTS talker input (qwen3_tts.py:1835-1853):
+ *   out[t] = bf16((needs_codec[t] ? bf16(text[t] + codec[cb0[t]]) : text[t]) + features[t]); text row stride ld_text
+ *   (0 = broadcast one row), cb0 int64 with stride ld_id, needs_codec NULL = all, features NULL = none. */
+int vb_talker_embed(void* d_out, int ld_out, const void* d_text, int64_t ld_text, const void* d_codec, int64_t codec_rows,
+                    const int64_t* d_cb0, int64_t ld_id, const uint8_t* d_needs_codec, const void* d_features,
+                    int64_t ld_feat, int T, int dim, void* stream);
 int vb_interleave_rows(void* d_out, const void* d_a, const void* d_b, int n, int row_bytes, void* stream);
 int vb_transpose_i64(int64_t* d_dst, const int64_t* d_src, int B, int C, int ld_dst, int ld_src, void* stream);
 /* rows out[i] = in[idx[i] + idx_offset] (last-token gather qo_indptr[1:] - 1, cuda_graph_worker.py:900-902) */

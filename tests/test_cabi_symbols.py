@@ -44,7 +44,7 @@ def test_error_reporting_without_gpu(lib):
     # argument validation happens before any CUDA call
     rc = lib.vb_rmsnorm(None, None, None, 1, 8, ctypes.c_float(1e-5), 0, None)
     assert rc != 0 and b"null" in lib.vb_last_error()
-    rc = lib.vb_gemm_bf16(None, None, None, None, 1, 1, 1, 1, 0, 1, 128, 0, 0, None)
+    rc = lib.vb_gemm_bf16(None, None, None, None, 1, 1, 1, 1, 0, 1, 128, 0, 0, None, None)
     assert rc != 0
 
 

@@ -180,3 +180,72 @@ def test_csm_batch_frames_one_graph_against_oracle():
             out = out_g
     print("csm batch frames vs oracle:", st)
     assert st["max_err"] < 2e-2 and st["flips"] <= 3 and st["graph_nodes"] > 100, st
+
+
+def test_csm_adapter_frame_device_equals_step_at_a_time_surface():
+    """CSMModel (the reference adapter's contract, csm.py:315-789): the fused ``frame_device`` against the reference-style
+    loop driven from outside -- ``forward`` -> ``sampling`` -> 2-row depth prefill -> ``depth_sampling`` -> 1-row depth
+    decodes (cuda_graph_worker.py:1058-1160) -- through the FlashInfer-compatible wrappers; greedy ids must be equal."""
+    from vox_serve_b200.flashinfer_utils import FlashInferDecodeWrapper, FlashInferPrefillWrapper
+    from vox_serve_b200.model import load_model
+    from vox_serve_b200.requests import Request
+    from vox_serve_b200.sampling import SamplingConfig
+
+    model = load_model("csm-synthetic-tiny:1", device="cuda:0", greedy=True)
+    assert model.has_depth_transformer and model.n_codebooks == 9 and model.depth_n_codebooks == 8
+    d, N, page, B = model.dims, model.dims.num_codebooks, 16, 2
+    cfg = SamplingConfig(greedy=True)
+    kw = dict(attn_buffer=None, n_qo_head=d.num_attention_heads, n_kv_head=d.num_key_value_heads,
+              n_state=d.num_attention_heads * d.head_dim, page_size=page, device="cuda")
+    g = torch.Generator().manual_seed(2)
+    lens = [21, 7]
+    ids = torch.randint(0, d.vocab_size, (sum(lens), N + 1), generator=g)
+    ids[:, -1] = torch.randint(0, d.text_vocab_size, (sum(lens),), generator=g)
+    masks = torch.ones(sum(lens), N + 1, dtype=torch.bool)
+    masks[:, -1] = False
+    masks[:5] = False
+    masks[:5, -1] = True
+    qo = [0, lens[0], sum(lens)]
+    pages = [[0, 1], [2]]
+    results = {}
+    for mode in ("fused", "stepwise"):
+        kv = torch.zeros(d.num_hidden_layers, 8, 2, page, d.num_key_value_heads, d.head_dim, dtype=BF, device="cuda")
+        eng = model.engine_for(kv, page)
+        pre = FlashInferPrefillWrapper(batch_size=B, max_seq_len=64, **kw)
+        pre.plan(torch.tensor(qo, dtype=torch.int32), torch.tensor([0, 2, 3], dtype=torch.int32),
+                 torch.tensor([0, 1, 2], dtype=torch.int32), torch.tensor([lens[0] - page, lens[1]], dtype=torch.int32))
+        pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens]).cuda()
+        last = torch.tensor([q - 1 for q in qo[1:]], dtype=torch.int32, device="cuda")
+        frames = []
+        if mode == "fused":
+            frames.append(model.frame_device(kv, pre, pos, B, ids.cuda(), masks.cuda(), last_rows=last, sampling_params=cfg).cpu())
+        else:
+            reqs = [Request(request_id=f"c{i}", prompt=None) for i in range(B)]
+            for r, n in zip(reqs, lens):
+                r.next_position_id = n + 1
+            logits, hidden = model.forward(ids.cuda(), pos, pre, kv, input_masks=masks.cuda())
+            out, x2 = model.sampling(logits[last.long()], hidden[last.long()], reqs, sampling_params=cfg)
+            dpre = FlashInferPrefillWrapper(batch_size=B, max_seq_len=2 * B, n_qo_head=d.depth_num_attention_heads,
+                                            n_kv_head=d.depth_num_key_value_heads, attn_buffer=None,
+                                            n_state=d.depth_num_attention_heads * d.depth_head_dim, page_size=eng.depth_page,
+                                            device="cuda")
+            ddec = FlashInferDecodeWrapper(batch_size=B, n_qo_head=d.depth_num_attention_heads, attn_buffer=None,
+                                           n_kv_head=d.depth_num_key_value_heads,
+                                           n_state=d.depth_num_attention_heads * d.depth_head_dim, page_size=eng.depth_page,
+                                           device="cuda")
+            i32 = lambda x: torch.tensor(x, dtype=torch.int32)     # noqa: E731
+            out = out.clone()
+            for i in range(1, N):
+                if i == 1:
+                    dpre.plan(i32([0, 2, 4]), i32([0, 1, 2]), i32([0, 1]), i32([2, 2]))
+                    lg = model.depth_forward(x2.view(2 * B, -1), torch.tensor([0, 1] * B, dtype=torch.int32, device="cuda"),
+                                             dpre, eng.depth_kv)[1::2]
+                else:
+                    ddec.plan(i32([0, 1, 2]), i32([0, 1]), i32([i + 1, i + 1]))
+                    lg = model.depth_forward(x, torch.full((B,), i, dtype=torch.int32, device="cuda"), ddec, eng.depth_kv)
+                out[:, i], x = model.depth_sampling(lg, i, reqs, sampling_params=cfg)
+            frames.append(out.cpu())
+            assert [int(v) for v in reqs[0].lm_output_tokens[-1][0, :N]] == out[0, :N].tolist()
+        results[mode] = frames
+    assert torch.equal(results["fused"][0][:, :N], results["stepwise"][0][:, :N]), (results["fused"][0], results["stepwise"][0])
+    assert torch.equal(results["fused"][0][:, N], results["fused"][0][:, 0])

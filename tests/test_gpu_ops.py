@@ -813,7 +813,7 @@ def test_gemm_progress_tag_and_weight_prefetch(ops):
     assert int(prog[0]) == (virt + nb) // 1024, (int(prog[0]), (virt + nb) // 1024)
     # ---- prefetcher over [launch 0 | launch 1] ----
     n_ctas, stages = (N // 128) * split, (K // 64) // split
-    table = torch.tensor([[0, base, n_ctas, 128 * 128, stages], [nb, base + nb, n_ctas, 128 * 128, stages]],
+    table = torch.tensor([[0, 0, base, n_ctas, 128 * 128, stages], [nb, 0, base + nb, n_ctas, 128 * 128, stages]],
                          dtype=torch.int64, device="cuda")
     prog.zero_()
     prog[0] = (2 * nb) // 1024                                  # everything consumed already: nothing to wait for

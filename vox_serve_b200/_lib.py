@@ -48,10 +48,11 @@ SIGNATURES = {
     "vb_gemm_t_tile": (c_int, [c_int]),
     "vb_tag_next_gemm": (c_int, [P, c_uint64]),
     "vb_set_u32": (c_int, [P, C.c_uint32, P]),
-    "vb_weight_prefetch": (c_int, [P, P, c_int, P, c_uint64, c_int, P]),
+    "vb_tag_next_attn": (c_int, [P, c_int]),
+    "vb_weight_prefetch": (c_int, [P, P, c_int, P, c_uint64, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_weight_tiles_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vb_pack_weight_tiles": (c_int, [P, P, c_int, c_int, c_int64, c_int, P]),
-    "vb_gemm_bf16": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_gemm_bf16": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
     "vb_proj_residual": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_proj_norm_gateup_silu": (c_int, [P, P, P, P, P, c_int, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_proj_norm_qkv_rope_append": (c_int, [P, P, P, P, P, P, c_int, P, c_float, P, P, P, c_int, c_int, c_int, c_int,
@@ -62,11 +63,13 @@ SIGNATURES = {
     "vb_rope_table": (c_int, [P, P, P, c_int, c_int, P]),
     "vb_row_ssq": (c_int, [P, P, c_int, c_int, P]),
     "vb_reduce_residual_rmsnorm": (c_int, [P, P, P, c_int, P, P, c_int, c_int, c_float, c_int, P]),
-    "vb_qkv_rope_append": (c_int, [P, P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_qkv_rope_append": (c_int, [P, P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P,
+                                   c_float, P]),
     "vb_embedding": (c_int, [P, P, P, c_int, c_int, c_int, P]),
     "vb_gather_rows": (c_int, [P, P, P, c_int, c_int, c_int, P]),
     "vb_multi_embed_sum": (c_int, [P, c_int, P, c_int64, c_int64, P, P, c_int64, c_int64, c_int, c_int, P, c_int64, c_int,
-                                   c_int, c_int, P]),
+                                   c_int, c_int, c_int, P]),
+    "vb_talker_embed": (c_int, [P, c_int, P, c_int64, P, c_int64, P, c_int64, P, P, c_int64, c_int, c_int, P]),
     "vb_interleave_rows": (c_int, [P, P, P, c_int, c_int, P]),
     "vb_transpose_i64": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "vb_sample_workspace_bytes": (c_size_t, [c_int, c_int]),

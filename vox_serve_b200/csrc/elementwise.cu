@@ -309,7 +309,8 @@ __global__ void __launch_bounds__(256) qkv_rope_append_kernel(
     __nv_bfloat16* __restrict__ q_out, __nv_bfloat16* __restrict__ kv, const float* __restrict__ partials,
     int split_k, const int32_t* __restrict__ pos, const float* __restrict__ freq,
     const int32_t* __restrict__ row_page, const int32_t* __restrict__ row_slot, int T, int n_q, int n_kv, int D,
-    int page_size, int rotary_dim, int interleave, int heads_per_cta) {
+    int page_size, int rotary_dim, int interleave, int heads_per_cta, const __nv_bfloat16* __restrict__ q_norm_w,
+    const __nv_bfloat16* __restrict__ k_norm_w, float norm_eps) {
   const int tr = (threadIdx.x == 0 && trace_block0()) ? trace_begin(6, split_k) : -1;
   pdl_sync();
   if (tr >= 0) trace_mark(24);
@@ -345,6 +346,23 @@ __global__ void __launch_bounds__(256) qkv_rope_append_kernel(
     val[n + 3] = round_bf16(acc.w);
   }
   __syncthreads();
+  if (q_norm_w) {
+    // per-head RMSNorm of every q and k head before the rotation (Qwen3: q_norm / k_norm over head_dim,
+    // vox_serve/model/qwen3_tts.py:603-604, 620-625): fp32 statistics over the bf16-rounded projection output, result
+    // rounded to bf16 like flashinfer.norm.rmsnorm; one warp per head
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    for (int hl = warp; hl < h_hi - h_lo; hl += n_warps) {
+      const int h = h_lo + hl;
+      if (h >= n_q + n_kv) continue;                      // V heads are not normalised
+      const __nv_bfloat16* nw = h < n_q ? q_norm_w : k_norm_w;
+      float ss = 0.f;
+      for (int e = lane; e < D; e += 32) ss += val[hl * D + e] * val[hl * D + e];
+      ss = warp_sum(ss);
+      const float rcp = rsqrtf(ss / static_cast<float>(D) + norm_eps);
+      for (int e = lane; e < D; e += 32) val[hl * D + e] = round_bf16((val[hl * D + e] * rcp) * __bfloat162float(nw[e]));
+    }
+    __syncthreads();
+  }
   const int page = row_page[t];
   const size_t row_elems = static_cast<size_t>(n_kv) * D;
   const size_t slab = static_cast<size_t>(page_size) * row_elems;
@@ -508,7 +526,9 @@ int vb_reduce_residual_rmsnorm(void* d_hidden_out, void* d_normed_out, const flo
 
 int vb_qkv_rope_append(void* d_q_out, void* d_layer_kv, const float* d_partials, int split_k, const int32_t* d_pos,
                        const float* d_freq, const int32_t* d_row_page, const int32_t* d_row_slot, int T, int n_q,
-                       int n_kv, int head_dim, int page_size, int rotary_dim, int interleave, void* stream) {
+                       int n_kv, int head_dim, int page_size, int rotary_dim, int interleave, const void* d_q_norm,
+                       const void* d_k_norm, float norm_eps, void* stream) {
+  VB_CHECK_ARG((d_q_norm == nullptr) == (d_k_norm == nullptr), "vb_qkv_rope_append: q_norm and k_norm come together");
   VB_CHECK_ARG(d_q_out && d_layer_kv && d_partials && d_pos && d_freq && d_row_page && d_row_slot,
                "vb_qkv_rope_append: null pointer");
   VB_CHECK_ARG(head_dim % 4 == 0 && rotary_dim % 2 == 0 && rotary_dim <= head_dim, "vb_qkv_rope_append: bad dims");
@@ -526,7 +546,8 @@ int vb_qkv_rope_append(void* d_q_out, void* d_layer_kv, const float* d_partials,
                                        VB_MAX_DYN_SMEM));
   VB_LAUNCH_PDL(qkv_rope_append_kernel, dim3(parts, T), 256, smem, stream, static_cast<__nv_bfloat16*>(d_q_out),
                 static_cast<__nv_bfloat16*>(d_layer_kv), d_partials, split_k, d_pos, d_freq, d_row_page, d_row_slot, T,
-                n_q, n_kv, head_dim, page_size, rotary_dim, interleave, heads_per_cta);
+                n_q, n_kv, head_dim, page_size, rotary_dim, interleave, heads_per_cta,
+                static_cast<const __nv_bfloat16*>(d_q_norm), static_cast<const __nv_bfloat16*>(d_k_norm), norm_eps);
   return 0;
 }
 

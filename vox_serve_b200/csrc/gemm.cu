@@ -64,6 +64,8 @@ struct GemmParams {
   // its weights, in KiB of the step's virtual weight stream, for the L2 prefetcher (weight_prefetch_kernel)
   unsigned int* progress;
   unsigned int progress_base, progress_inc;
+  // mode 0: optional bias [N] added in fp32 before the single bf16 rounding (nn.Linear with bias)
+  const __nv_bfloat16* bias;
 };
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -367,10 +369,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
         if (valid) {
           if (p.mode == GM_BF16) {
             __nv_bfloat16* y = static_cast<__nv_bfloat16*>(p.y);
+            const float bv = p.bias ? __bfloat162float(p.bias[n]) : 0.f;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int t = t_base + c0 + j;
-              if (t < p.T) y[static_cast<size_t>(t) * p.ldy + n] = __float2bfloat16_rn(__uint_as_float(v[j]));
+              if (t < p.T) y[static_cast<size_t>(t) * p.ldy + n] = __float2bfloat16_rn(__uint_as_float(v[j]) + bv);
             }
           } else {
             float* y = static_cast<float*>(p.y) + static_cast<size_t>(split) * p.T * p.ldy;
@@ -670,22 +673,50 @@ static int fused_t_tile(int T) { return T <= 16 ? 16 : (T <= 32 ? 32 : 64); }
 // The virtual weight stream: launch after launch; inside a launch stage-major, CTA-minor (all CTAs of a projection
 // advance through their slices together), which is the order the bytes are needed in.
 // ---------------------------------------------------------------------------------------------------------------
-struct PrefetchOp {            // mirrors the int64 [n_ops][5] table built by the host
-  long long virt_off, phys_off, n_ctas, a_stage, stages_per_cta;
+struct PrefetchOp {            // mirrors the int64 [n_ops][6] table built by the host
+  // projection: weights of one launch: slices of CTA c at phys_off + c * stages_per_cta * a_stage (a_stage > 0)
+  // attention (a_stage == 0): the KV of one layer; phys_off = first slab of the layer (layer * pages)
+  long long w_before, attn_before, phys_off, n_ctas, a_stage, stages_per_cta;
 };
+struct PrefetchKV {            // the step's attention plan (vb_plan_rows) + cache geometry; kv == nullptr: no KV ops
+  const uint8_t* kv;           // whole cache [slabs][2][page_size][n_kv][D] bf16
+  const int32_t* row_chunk_start;
+  const int32_t* row_kvlen;
+  const int32_t* row_pagebase;
+  const int32_t* kv_indices;
+  int n_rows, page_size, tok, row_bytes, attn_grid;
+};
+// consumed bytes of the step's virtual stream: progress[0] = KiB of weights, progress[1] = KV tiles
+__device__ __forceinline__ unsigned long long pf_consumed(const unsigned int* progress, unsigned long long tile_bytes) {
+  const volatile unsigned int* p = progress;
+  return (static_cast<unsigned long long>(p[0]) << 10) + static_cast<unsigned long long>(p[1]) * tile_bytes;
+}
 __global__ void __launch_bounds__(32) weight_prefetch_kernel(const uint8_t* __restrict__ arena,
                                                              const PrefetchOp* __restrict__ ops, int n_ops,
-                                                             const unsigned int* progress, unsigned long long window) {
+                                                             const unsigned int* progress, unsigned long long window,
+                                                             const PrefetchKV kvp) {
   const int lane = threadIdx.x;
+  // the KV part of the stream has this step's size: every layer reads total_tiles tiles of 2 * tok rows
+  const unsigned long long tile_bytes = kvp.kv ? 2ull * kvp.tok * kvp.row_bytes : 0ull;
+  const int total_tiles = kvp.kv ? kvp.row_chunk_start[kvp.n_rows] : 0;
+  const int per = kvp.kv ? (total_tiles + kvp.attn_grid - 1) / kvp.attn_grid : 0;
+  const unsigned long long s_kv = static_cast<unsigned long long>(total_tiles) * tile_bytes;
   unsigned long long g = blockIdx.x, op_first = 0;
   unsigned long long consumed = 0;
   for (int op = 0; op < n_ops; ++op) {
     const PrefetchOp o = ops[op];
-    const unsigned long long n_p = static_cast<unsigned long long>(o.n_ctas) * o.stages_per_cta;
+    const bool is_kv = o.a_stage == 0;
+    if (is_kv && !kvp.kv) continue;
+    const unsigned long long piece = is_kv ? tile_bytes : static_cast<unsigned long long>(o.a_stage);
+    const unsigned long long n_ctas = is_kv ? static_cast<unsigned long long>(kvp.attn_grid) : o.n_ctas;
+    const unsigned long long n_p = n_ctas * (is_kv ? static_cast<unsigned long long>(per) : o.stages_per_cta);
+    const unsigned long long v0 = static_cast<unsigned long long>(o.w_before) + static_cast<unsigned long long>(o.attn_before) * s_kv;
     for (; g < op_first + n_p; g += gridDim.x) {
       const unsigned long long j = g - op_first;
-      const unsigned long long s = j / o.n_ctas, c = j - s * o.n_ctas;
-      const unsigned long long virt = o.virt_off + j * o.a_stage;
+      const unsigned long long s = j / n_ctas, c = j - s * n_ctas;
+      // (a KV op's virtual size is total_tiles tiles although it is walked as grid x per pieces: scale the offset)
+      const unsigned long long virt = v0 + (is_kv ? (s * n_ctas < static_cast<unsigned long long>(total_tiles) ? s * n_ctas : total_tiles) * tile_bytes
+                                                  : j * piece);
       // pace: stay less than `window` ahead of consumption.  Bounded: if nobody publishes progress (a launch outside
       // its step) the kernel gives up instead of spinning forever.
       int give_up = 0;
@@ -693,7 +724,7 @@ __global__ void __launch_bounds__(32) weight_prefetch_kernel(const uint8_t* __re
         if (lane == 0) {
           unsigned int spins = 0;
           while (true) {
-            consumed = static_cast<unsigned long long>(*reinterpret_cast<const volatile unsigned int*>(progress)) << 10;
+            consumed = pf_consumed(progress, tile_bytes);
             if (virt < consumed + window) break;
             if (++spins > (1u << 21)) { give_up = 1; break; }
             __nanosleep(256);
@@ -703,10 +734,33 @@ __global__ void __launch_bounds__(32) weight_prefetch_kernel(const uint8_t* __re
         give_up = __shfl_sync(0xffffffffu, give_up, 0);
         if (give_up) return;
       }
-      if (virt + o.a_stage <= consumed) continue;        // the projection got there first
-      const uint8_t* src = arena + o.phys_off + (c * o.stages_per_cta + s) * o.a_stage;
-      for (unsigned int l = lane * 128u; l < static_cast<unsigned int>(o.a_stage); l += 32u * 128u)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<uint64_t>(src + l)) : "memory");
+      if (virt + piece <= consumed) continue;        // the consumer got there first
+      if (!is_kv) {
+        const uint8_t* src = arena + o.phys_off + (c * o.stages_per_cta + s) * o.a_stage;
+        for (unsigned int l = lane * 128u; l < static_cast<unsigned int>(o.a_stage); l += 32u * 128u)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<uint64_t>(src + l)) : "memory");
+      } else {
+        // tile Lx of the attention kernel's CTA c (its s-th): row by binary search over the tile prefix, then the page
+        const long long Lx = static_cast<long long>(c) * per + static_cast<long long>(s);
+        if (static_cast<long long>(s) >= per || Lx >= total_tiles) continue;
+        int lo = 0, hi = kvp.n_rows;
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (kvp.row_chunk_start[mid] <= Lx) lo = mid; else hi = mid;
+        }
+        const int token0 = static_cast<int>(Lx - kvp.row_chunk_start[lo]) * kvp.tok;
+        const int n_tok = min(kvp.tok, kvp.row_kvlen[lo] - token0);
+        if (n_tok <= 0) continue;
+        const int page = kvp.kv_indices[kvp.row_pagebase[lo] + token0 / kvp.page_size];
+        const unsigned long long page_bytes = static_cast<unsigned long long>(kvp.page_size) * kvp.row_bytes;
+        const uint8_t* k0 = kvp.kv + (static_cast<unsigned long long>(o.phys_off + page) * 2ull) * page_bytes +
+                            static_cast<unsigned long long>(token0 % kvp.page_size) * kvp.row_bytes;
+        const unsigned int bytes = static_cast<unsigned int>(n_tok) * kvp.row_bytes;
+        for (unsigned int l = lane * 128u; l < bytes; l += 32u * 128u) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<uint64_t>(k0 + l)) : "memory");
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<uint64_t>(k0 + page_bytes + l)) : "memory");
+        }
+      }
     }
     op_first += n_p;
   }
@@ -754,13 +808,24 @@ int vb_set_u32(uint32_t* d_ptr, uint32_t value, void* stream) {
 }
 
 int vb_weight_prefetch(const void* d_arena, const int64_t* d_ops, int n_ops, const uint32_t* d_progress,
-                       uint64_t window_bytes, int grid_ctas, void* stream) {
+                       uint64_t window_bytes, int grid_ctas, const void* d_kv, const int32_t* d_row_chunk_start,
+                       const int32_t* d_row_kvlen, const int32_t* d_row_pagebase, const int32_t* d_kv_indices, int n_rows,
+                       int page_size, int chunk_tokens, int kv_row_bytes, int attn_grid_ctas, void* stream) {
   VB_CHECK_ARG(d_arena && d_ops && d_progress, "vb_weight_prefetch: null pointer");
   VB_CHECK_ARG(n_ops > 0 && grid_ctas > 0 && window_bytes > 0, "vb_weight_prefetch: bad arguments");
-  static_assert(sizeof(PrefetchOp) == 5 * sizeof(int64_t), "PrefetchOp mirrors an int64 [n][5] table");
+  VB_CHECK_ARG(!d_kv || (d_row_chunk_start && d_row_kvlen && d_row_pagebase && d_kv_indices && n_rows > 0 && page_size > 0 &&
+                         chunk_tokens > 0 && kv_row_bytes > 0 && kv_row_bytes % 128 == 0 && attn_grid_ctas > 0),
+               "vb_weight_prefetch: incomplete KV description");
+  static_assert(sizeof(PrefetchOp) == 6 * sizeof(int64_t), "PrefetchOp mirrors an int64 [n][6] table");
+  PrefetchKV kvp = {};
+  kvp.kv = static_cast<const uint8_t*>(d_kv);
+  kvp.row_chunk_start = d_row_chunk_start; kvp.row_kvlen = d_row_kvlen; kvp.row_pagebase = d_row_pagebase;
+  kvp.kv_indices = d_kv_indices;
+  kvp.n_rows = n_rows; kvp.page_size = page_size; kvp.tok = chunk_tokens; kvp.row_bytes = kv_row_bytes;
+  kvp.attn_grid = attn_grid_ctas;
   VB_LAUNCH_PLAIN(weight_prefetch_kernel, grid_ctas, 32, 0, stream, static_cast<const uint8_t*>(d_arena),
                   reinterpret_cast<const PrefetchOp*>(d_ops), n_ops, d_progress,
-                  static_cast<unsigned long long>(window_bytes));
+                  static_cast<unsigned long long>(window_bytes), kvp);
   return 0;
 }
 
@@ -775,8 +840,9 @@ int vb_gemm_t_tile(int T) {
 }
 
 int vb_gemm_bf16(void* d_y, const void* d_w_tiles, const void* x_map, const void* d_x_tiles, int T, int N, int K,
-                 int ldy, int mode, int split_k, int tile_rows, int n_out, int y_tiled, void* stream) {
+                 int ldy, int mode, int split_k, int tile_rows, int n_out, int y_tiled, const void* d_bias, void* stream) {
   VB_CHECK_ARG(d_y && d_w_tiles && (x_map || d_x_tiles), "vb_gemm_bf16: null pointer");
+  VB_CHECK_ARG(!d_bias || mode == 0, "vb_gemm_bf16: bias is a mode 0 option");
   VB_CHECK_ARG(!y_tiled || mode == 2, "vb_gemm_bf16: tiled output is a mode 2 option");
   VB_CHECK_ARG(mode >= 0 && mode <= 2, "vb_gemm_bf16: mode %d", mode);
   VB_CHECK_ARG(mode == 1 || split_k == 1, "vb_gemm_bf16: split_k > 1 needs mode 1 (fp32 partials)");
@@ -788,6 +854,7 @@ int vb_gemm_bf16(void* d_y, const void* d_w_tiles, const void* x_map, const void
   p.n_out = n_out > 0 ? n_out : (mode == 2 ? N / 2 : N);
   p.t_tile = vb_gemm_t_tile(T);
   p.y_tiled = y_tiled;
+  p.bias = static_cast<const __nv_bfloat16*>(d_bias);
   return launch_gemm(p, d_w_tiles, x_map, static_cast<cudaStream_t>(stream), d_x_tiles);
 }
 

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(256) multi_embed_sum_kernel(__nv_bfloat16* __r
                                                               const __nv_bfloat16* __restrict__ table_a, long long rows_a,
                                                               long long col_offset, int col0, int n_cols_a,
                                                               const __nv_bfloat16* __restrict__ table_b, long long rows_b,
-                                                              int C, int dim) {
+                                                              int C, int dim, int round_each) {
   pdl_sync();
   extern __shared__ long long s_row[];          // [C] source row of every column, -1 = masked off
   const size_t t = blockIdx.x;
@@ -52,11 +52,41 @@ __global__ void __launch_bounds__(256) multi_embed_sum_kernel(__nv_bfloat16* __r
         acc[2 * j] += bf16_lo(u[j]);
         acc[2 * j + 1] += bf16_hi(u[j]);
       }
+      if (round_each) {        // a chain of bf16 `+=` (qwen3_tts.py:2002) rounds after every term
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = round_bf16(acc[j]);
+      }
     }
     uint4 o;
     o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
     o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
     reinterpret_cast<uint4*>(out + t * ld_out)[i] = o;
+  }
+}
+
+// Qwen3-TTS talker input row (vox_serve/model/qwen3_tts.py:1835-1853):
+//   out[t] = bf16( (needs_codec[t] ? bf16(text[t] + codec[cb0[t]]) : text[t]) + features[t] )
+// text rows come with stride ld_text (0 = one row broadcast: decode rows all carry text_projection(embed(tts_pad)));
+// cb0 int64 with element stride ld_id; needs_codec NULL = all rows; features NULL = zeros.
+__global__ void __launch_bounds__(256) talker_embed_kernel(__nv_bfloat16* __restrict__ out, int ld_out,
+                                                           const __nv_bfloat16* __restrict__ text, long long ld_text,
+                                                           const __nv_bfloat16* __restrict__ codec, long long codec_rows,
+                                                           const long long* __restrict__ cb0, long long ld_id,
+                                                           const uint8_t* __restrict__ needs_codec,
+                                                           const __nv_bfloat16* __restrict__ features, long long ld_feat,
+                                                           int dim) {
+  pdl_sync();
+  const size_t t = blockIdx.x;
+  const bool use_c = !needs_codec || needs_codec[t];
+  long long id = use_c ? cb0[t * ld_id] : 0;
+  id = id < 0 ? 0 : (id >= codec_rows ? codec_rows - 1 : id);
+  const __nv_bfloat16* tx = text + t * ld_text;
+  const __nv_bfloat16* cx = codec + static_cast<size_t>(id) * dim;
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+    float v = __bfloat162float(tx[i]);
+    if (use_c) v = round_bf16(v + __bfloat162float(cx[i]));
+    if (features) v = round_bf16(v + __bfloat162float(features[t * ld_feat + i]));
+    out[t * ld_out + i] = __float2bfloat16_rn(v);
   }
 }
 
@@ -91,7 +121,7 @@ extern "C" {
 
 int vb_multi_embed_sum(void* d_out, int ld_out, const int64_t* d_ids, int64_t ld_t, int64_t ld_c, const uint8_t* d_mask,
                        const void* d_table_a, int64_t rows_a, int64_t col_offset, int col0, int n_cols_a,
-                       const void* d_table_b, int64_t rows_b, int T, int C, int dim, void* stream) {
+                       const void* d_table_b, int64_t rows_b, int T, int C, int dim, int round_each, void* stream) {
   VB_CHECK_ARG(d_out && d_ids && (d_table_a || n_cols_a == 0) && (d_table_b || n_cols_a >= C),
                "vb_multi_embed_sum: null pointer");
   VB_CHECK_ARG(dim > 0 && dim % 8 == 0 && ld_out >= dim && C > 0 && C <= 1024 && n_cols_a >= 0 && n_cols_a <= C,
@@ -102,7 +132,20 @@ int vb_multi_embed_sum(void* d_out, int ld_out, const int64_t* d_ids, int64_t ld
                 static_cast<long long>(ld_t), static_cast<long long>(ld_c), d_mask,
                 static_cast<const __nv_bfloat16*>(d_table_a), static_cast<long long>(rows_a),
                 static_cast<long long>(col_offset), col0, n_cols_a, static_cast<const __nv_bfloat16*>(d_table_b),
-                static_cast<long long>(rows_b), C, dim);
+                static_cast<long long>(rows_b), C, dim, round_each);
+  return 0;
+}
+
+int vb_talker_embed(void* d_out, int ld_out, const void* d_text, int64_t ld_text, const void* d_codec, int64_t codec_rows,
+                    const int64_t* d_cb0, int64_t ld_id, const uint8_t* d_needs_codec, const void* d_features,
+                    int64_t ld_feat, int T, int dim, void* stream) {
+  VB_CHECK_ARG(d_out && d_text && d_codec && d_cb0 && dim > 0 && ld_out >= dim, "vb_talker_embed: bad arguments");
+  if (T <= 0) return 0;
+  VB_LAUNCH_PDL(talker_embed_kernel, T, 256, 0, stream, static_cast<__nv_bfloat16*>(d_out), ld_out,
+                static_cast<const __nv_bfloat16*>(d_text), static_cast<long long>(ld_text),
+                static_cast<const __nv_bfloat16*>(d_codec), static_cast<long long>(codec_rows),
+                reinterpret_cast<const long long*>(d_cb0), static_cast<long long>(ld_id), d_needs_codec,
+                static_cast<const __nv_bfloat16*>(d_features), static_cast<long long>(ld_feat), dim);
   return 0;
 }
 

@@ -40,6 +40,7 @@ class LlamaDims:
     low_freq_factor: Optional[float] = 1.0
     high_freq_factor: Optional[float] = 4.0
     old_context_len: Optional[float] = 8192
+    qk_norm: bool = False      # per-head RMSNorm of q and k before RoPE (Qwen3: self_attn.q_norm / k_norm)
 
     @classmethod
     def orpheus_3b(cls):
@@ -108,6 +109,9 @@ class LlamaWeights:
                                                put(sd[n["o"]]), put(sd[n["ln2"]]), put(sd[n["gate"]]),
                                                put(sd[n["up"]]), put(sd[n["down"]]), self.gu_half, dims.head_dim,
                                                out=slots))
+            if dims.qk_norm:
+                lp = f"{prefix}layers.{i}.self_attn."
+                self.layers[-1]["qn"], self.layers[-1]["kn"] = put(sd[lp + "q_norm.weight"]), put(sd[lp + "k_norm.weight"])
         if heads is None:
             heads = [sd[head_key] if head_key in sd else sd[embed_key]]
         self.heads = []
@@ -197,7 +201,7 @@ class LlamaEngine:
         self.attn_grid = self.attn_ws.grid
         # ---- fused decode path (<= FUSED_MAX_ROWS rows) ----
         self.gu_half = weights.gu_half
-        self.fused_ok = D in (64, 128) and H % 64 == 0
+        self.fused_ok = D in (64, 128) and H % 64 == 0 and not d.qk_norm      # (the fused QKV tail has no q/k norm)
         # split-K of the fused QKV projection: one head per tile
         self.fsplit_qkv = ops.proj_split_k(hq + 2 * hkv, H, self.sms)
         self.fsplit_o = ops.proj_split_k((H + 127) // 128, hq * D, self.sms)
@@ -216,6 +220,7 @@ class LlamaEngine:
     # ---- L2 weight prefetcher (decode-sized steps, default layer mode) ----------------------------------
     # VB_L2_PREFETCH=0 disables it; VB_L2_WINDOW_MB = how far ahead of the projections' consumption it may run
     l2_prefetch = os.environ.get("VB_L2_PREFETCH", "1") != "0"
+    l2_prefetch_kv = os.environ.get("VB_L2_PREFETCH_KV", "1") != "0"      # also the step's KV (attention rows of the table)
     l2_window_mb = int(os.environ.get("VB_L2_WINDOW_MB", "64"))
 
     def _init_prefetch(self) -> None:
@@ -226,16 +231,20 @@ class LlamaEngine:
         if w.arena is None or self.device.type != "cuda":
             return
         base = w.arena.data_ptr()
-        rows, virt_of, virt = [], {}, 0
-        plan = [("qkv", self.split_qkv), ("o", self.split_o), ("gu", 1), ("down", self.split_down)]
-        launches = [(i, k, L[k], s) for i, L in enumerate(w.layers) for k, s in plan] + [(-1, "lm_head", w.lm_head, 1)]
+        rows, virt_of, virt, n_attn = [], {}, 0, 0
+        plan = [("qkv", self.split_qkv), ("attn", 0), ("o", self.split_o), ("gu", 1), ("down", self.split_down)]
+        launches = [(i, k, L.get(k), s) for i, L in enumerate(w.layers) for k, s in plan] + [(-1, "lm_head", w.lm_head, 1)]
         for i, k, pw, split in launches:
+            if k == "attn":                 # one layer's KV, sized per step by the prefetcher from the row plan
+                rows.append([virt, n_attn, i * self.pages_per_layer, 0, 0, 0])
+                n_attn += 1
+                continue
             num_kb = (pw.K + 63) // 64
             if num_kb % split != 0 or pw.data.data_ptr() < base:
                 return                      # uneven split-K ranges: no simple slice arithmetic -> no prefetcher
             n_ctas = (pw.N + pw.tile_rows - 1) // pw.tile_rows * split
             a_stage, stages = pw.tile_rows * 128, num_kb // split
-            rows.append([virt, pw.data.data_ptr() - base, n_ctas, a_stage, stages])
+            rows.append([virt, n_attn, pw.data.data_ptr() - base, n_ctas, a_stage, stages])
             virt_of[(i, k)] = virt
             virt += n_ctas * a_stage * stages
         self.pf_table = torch.tensor(rows, dtype=torch.int64, device=self.device)
@@ -280,10 +289,14 @@ class LlamaEngine:
                          and (self.force_unfused or not self.fused_ok) and head is None)
         if self._pf_live:
             main = torch.cuda.current_stream()
-            ops.set_u32(self.pf_progress, 0)
+            ops.set_u32(self.pf_progress[0:1], 0)
+            ops.set_u32(self.pf_progress[1:2], 0)
             self.pf_stream.wait_stream(main)
             with torch.cuda.stream(self.pf_stream):
-                ops.weight_prefetch(w.arena, self.pf_table, self.pf_progress, self.l2_window_mb << 20, self.sms)
+                kv = self.kv_cache if self.l2_prefetch_kv else None
+                ops.weight_prefetch(w.arena, self.pf_table, self.pf_progress, self.l2_window_mb << 20, self.sms,
+                                    kv_cache=kv, plan=plan, n_rows=R, page_size=self.page_size, chunk_tokens=self.chunk,
+                                    attn_grid_ctas=self.attn_grid)
         if input_ids is not None:
             ops.embedding(w.embed, input_ids, out=hidden)
         x_final = normed
@@ -386,7 +399,10 @@ class LlamaEngine:
         for i, L in enumerate(w.layers):
             self._tag(i, "qkv")
             p = ops.gemm(normed, L["qkv"], mode=1, split_k=s_qkv, out=self._partials(s_qkv, R, self.qkv_w), tile_rows=D)
-            ops.qkv_rope_append(p, self.kv_cache[i], position_ids, self.freq, plan, hq, hkv, D, q_out=q)
+            ops.qkv_rope_append(p, self.kv_cache[i], position_ids, self.freq, plan, hq, hkv, D, q_out=q,
+                                q_norm=L.get("qn"), k_norm=L.get("kn"), norm_eps=d.rms_norm_eps)
+            if self._pf_live and self.l2_prefetch_kv:
+                ops.tag_next_attn(self.pf_progress[1:2], i)
             ops.paged_attn(q, self.kv_map, i * self.pages_per_layer, plan, R, hkv, self.page_size, self.chunk,
                            self.attn_ws, out=attn_o, grid_ctas=self.attn_grid)
             self._tag(i, "o")

@@ -8,12 +8,15 @@ from typing import Any, Dict, Type
 import torch
 
 from ..sampling import SamplingConfig
-from .base import BaseLM, PreprocessOutput
+from .base import BaseLM, BaseLMWithDepth, PreprocessOutput
+from .csm import CSMModel
 from .orpheus import OrpheusModel
 
 MODEL_REGISTRY: Dict[str, Type[BaseLM]] = {
     "orpheus": OrpheusModel,
     "canopylabs/orpheus-3b-0.1-ft": OrpheusModel,
+    "csm": CSMModel,              # LM side only (backbone + depth decoder); its Mimi vocoder is not built yet
+    "sesame/csm-1b": CSMModel,
 }
 
 

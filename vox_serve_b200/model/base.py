@@ -113,3 +113,47 @@ class BaseLM(ABC):
 
     @abstractmethod
     def postprocess(self, token_ids: torch.Tensor, **kwargs) -> torch.Tensor: ...
+
+
+class BaseLMWithDepth(BaseLM):
+    """Adapters with a depth transformer (``vox_serve/model/base.py:280-447``): the backbone's ``forward`` also
+    returns the hidden state the depth decoder starts from, ``sampling`` returns the depth decoder's first input,
+    and ``depth_forward`` / ``depth_sampling`` run one codebook step.  The B200 adapters additionally expose
+    ``frame_device``: the whole frame (backbone sample + every depth step) as one capturable launch sequence."""
+    has_depth_transformer = True
+
+    @property
+    @abstractmethod
+    def depth_n_codebooks(self) -> int: ...
+
+    @property
+    @abstractmethod
+    def depth_num_attention_heads(self) -> int: ...
+
+    @property
+    @abstractmethod
+    def depth_num_key_value_heads(self) -> int: ...
+
+    @property
+    @abstractmethod
+    def depth_num_hidden_layers(self) -> int: ...
+
+    @property
+    @abstractmethod
+    def depth_hidden_size(self) -> int: ...
+
+    @property
+    @abstractmethod
+    def depth_head_dim(self) -> int: ...
+
+    @property
+    @abstractmethod
+    def depth_vocab_size(self) -> int: ...
+
+    @abstractmethod
+    def depth_forward(self, hidden_states: torch.Tensor, position_ids: torch.Tensor, attn_wrapper, kv_cache: torch.Tensor,
+                      **kwargs) -> torch.Tensor: ...
+
+    @abstractmethod
+    def depth_sampling(self, logits: torch.Tensor, i_iteration: int, requests: List[Request],
+                       sampling_params: Optional[SamplingConfig] = None, cfg_scale: Optional[float] = None, **kwargs): ...

@@ -350,15 +350,31 @@ def set_u32(t: torch.Tensor, value: int) -> None:
     call("vb_set_u32", t.data_ptr(), int(value), _stream())
 
 
+def tag_next_attn(progress_tiles: Optional[torch.Tensor], layer_ordinal: int = 0) -> None:
+    """The next paged_attn launched from this thread publishes the KV tiles the step has consumed (vb_tag_next_attn)."""
+    call("vb_tag_next_attn", _p(progress_tiles), int(layer_ordinal))
+
+
 def weight_prefetch(arena: torch.Tensor, op_table: torch.Tensor, progress: torch.Tensor, window_bytes: int,
-                    grid_ctas: Optional[int] = None) -> None:
-    """Launch the L2 weight prefetcher (vb_weight_prefetch) on the CURRENT stream: meant for a side stream that runs
-    beside the decode step.  op_table: int64 [n_ops, 5] on the device."""
-    _need_cuda(arena, op_table, progress)
-    assert op_table.dtype == torch.int64 and op_table.dim() == 2 and op_table.shape[1] == 5 and op_table.is_contiguous()
+                    grid_ctas: Optional[int] = None, kv_cache: Optional[torch.Tensor] = None,
+                    plan: Optional["RowPlan"] = None, n_rows: int = 0, page_size: int = 0, chunk_tokens: int = 0,
+                    attn_grid_ctas: int = 0) -> None:
+    """Launch the L2 prefetcher (vb_weight_prefetch) on the CURRENT stream: meant for a side stream that runs beside
+    the decode step.  op_table: int64 [n_ops, 6] on the device; progress: int32 [>= 2] = {KiB of weights, KV tiles}.
+    With ``kv_cache`` + ``plan`` the table's attention rows prefetch the step's KV as well."""
+    _need_cuda(arena, op_table, progress, kv_cache)
+    assert op_table.dtype == torch.int64 and op_table.dim() == 2 and op_table.shape[1] == 6 and op_table.is_contiguous()
     grid = device_info()[0] if grid_ctas is None else int(grid_ctas)
-    call("vb_weight_prefetch", arena.data_ptr(), op_table.data_ptr(), op_table.shape[0], progress.data_ptr(),
-         int(window_bytes), grid, _stream())
+    if kv_cache is not None:
+        assert plan is not None and plan.kv_indices is not None and kv_cache.is_contiguous()
+        row_bytes = kv_cache.shape[-2] * kv_cache.shape[-1] * kv_cache.element_size()
+        call("vb_weight_prefetch", arena.data_ptr(), op_table.data_ptr(), op_table.shape[0], progress.data_ptr(),
+             int(window_bytes), grid, kv_cache.data_ptr(), plan.row_chunk_start.data_ptr(), plan.row_kvlen.data_ptr(),
+             plan.row_pagebase.data_ptr(), plan.kv_indices.data_ptr(), int(n_rows), int(page_size), int(chunk_tokens),
+             int(row_bytes), int(attn_grid_ctas), _stream())
+    else:
+        call("vb_weight_prefetch", arena.data_ptr(), op_table.data_ptr(), op_table.shape[0], progress.data_ptr(),
+             int(window_bytes), grid, None, None, None, None, None, 0, 0, 0, 0, 0, _stream())
 
 
 _pack_cache: Dict[Tuple, PackedWeight] = {}
@@ -379,8 +395,10 @@ def _packed(w, tile_rows: int) -> PackedWeight:
     return pw
 
 
-def gemm(x, w, mode: int = 0, split_k: int = 1, out=None, tile_rows: int = 128, n_out: Optional[int] = None):
-    """x [T, K] bf16, w [N, K] bf16 (nn.Linear.weight layout, or a PackedWeight).
+def gemm(x, w, mode: int = 0, split_k: int = 1, out=None, tile_rows: int = 128, n_out: Optional[int] = None,
+         bias: Optional[torch.Tensor] = None):
+    """x [T, K] bf16, w [N, K] bf16 (nn.Linear.weight layout, or a PackedWeight).  bias (bf16 [N], mode 0 only) is added
+    in fp32 before the single bf16 rounding.
     mode 0 -> bf16 [T, N]; mode 1 -> fp32 partials [split_k, T, N]; mode 2 -> bf16 [T, n_out] = silu(gate)*up
     with w rows packed per tile_rows-row tile (see interleave_gate_up; n_out defaults to N/2)."""
     pw = _packed(w, tile_rows)
@@ -398,15 +416,18 @@ def gemm(x, w, mode: int = 0, split_k: int = 1, out=None, tile_rows: int = 128, 
     if isinstance(out, TiledAct):
         assert mode == 2 and out.T == T and out.K == n_out
         call("vb_gemm_bf16", out.data.data_ptr(), pw.data.data_ptr(), x_map_ptr, x_tiles_ptr, T, N, K, n_out, mode, split_k,
-             tile_rows, n_out, 1, _stream())
+             tile_rows, n_out, 1, None, _stream())
         return out
     if out is None:
         if mode == 1:
             out = torch.empty(split_k, T, n_out, dtype=torch.float32, device=dev)
         else:
             out = torch.empty(T, n_out, dtype=BF16, device=dev)
+    if bias is not None:
+        _need_cuda(bias)
+        assert mode == 0 and bias.dtype == BF16 and bias.numel() == N and bias.is_contiguous()
     call("vb_gemm_bf16", out.data_ptr(), pw.data.data_ptr(), x_map_ptr, x_tiles_ptr, T, N, K, n_out, mode, split_k,
-         tile_rows, n_out, 0, _stream())
+         tile_rows, n_out, 0, _p(bias), _stream())
     return out
 
 
@@ -614,15 +635,17 @@ def reduce_residual_rmsnorm(partials: torch.Tensor, residual: Optional[torch.Ten
 
 def qkv_rope_append(partials: torch.Tensor, layer_kv: torch.Tensor, pos: torch.Tensor, freq: torch.Tensor,
                     plan: RowPlan, n_q: int, n_kv: int, head_dim: int, interleave: bool = False,
-                    q_out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    _need_cuda(partials, layer_kv, pos, freq)
+                    q_out: Optional[torch.Tensor] = None, q_norm: Optional[torch.Tensor] = None,
+                    k_norm: Optional[torch.Tensor] = None, norm_eps: float = 1e-6) -> torch.Tensor:
+    """q_norm / k_norm (bf16 [head_dim]): per-head RMSNorm of q and k before the rotation (Qwen3)."""
+    _need_cuda(partials, layer_kv, pos, freq, q_norm, k_norm)
     S, T, W = partials.shape
     assert W == (n_q + 2 * n_kv) * head_dim
     if q_out is None:
         q_out = torch.empty(T, n_q, head_dim, dtype=BF16, device=partials.device)
     call("vb_qkv_rope_append", q_out.data_ptr(), layer_kv.data_ptr(), partials.data_ptr(), S, pos.data_ptr(),
          freq.data_ptr(), plan.row_page.data_ptr(), plan.row_slot.data_ptr(), T, n_q, n_kv, head_dim,
-         layer_kv.shape[-3], freq.numel(), int(bool(interleave)), _stream())
+         layer_kv.shape[-3], freq.numel(), int(bool(interleave)), _p(q_norm), _p(k_norm), float(norm_eps), _stream())
     return q_out
 
 
@@ -637,7 +660,7 @@ def embedding(table: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tensor
 
 def multi_embed_sum(out: torch.Tensor, ids: torch.Tensor, table_a: Optional[torch.Tensor], col_offset: int = 0,
                     col0: int = 0, n_cols_a: Optional[int] = None, table_b: Optional[torch.Tensor] = None,
-                    mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    mask: Optional[torch.Tensor] = None, round_each: bool = False) -> torch.Tensor:
     """out [T, dim] bf16 = masked sum over the C columns of ids [T, C] (int64, any strides) of embedding rows:
     columns < n_cols_a from table_a at row ids + (col0 + c) * col_offset, the rest from table_b.  mask [T, C] bool/uint8
     contiguous or None.  (vb_multi_embed_sum; csm.py:637-663)"""
@@ -654,7 +677,25 @@ def multi_embed_sum(out: torch.Tensor, ids: torch.Tensor, table_a: Optional[torc
         assert tb is None or (tb.dtype == BF16 and tb.is_contiguous() and tb.shape[1] == dim)
     call("vb_multi_embed_sum", out.data_ptr(), out.stride(0), ids.data_ptr(), ids.stride(0), ids.stride(1), _p(m8),
          _p(table_a), table_a.shape[0] if table_a is not None else 0, int(col_offset), int(col0), int(n_cols_a),
-         _p(table_b), table_b.shape[0] if table_b is not None else 0, T, C, dim, _stream())
+         _p(table_b), table_b.shape[0] if table_b is not None else 0, T, C, dim, int(bool(round_each)), _stream())
+    return out
+
+
+def talker_embed(out: torch.Tensor, text: torch.Tensor, codec: torch.Tensor, cb0: torch.Tensor,
+                 needs_codec: Optional[torch.Tensor] = None, features: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Qwen3-TTS talker input rows (vb_talker_embed).  text: [T, H] or [H] (broadcast); cb0 int64 [T] (any stride);
+    needs_codec bool [T] or None (all); features [T, H] or None."""
+    _need_cuda(out, text, codec, cb0, needs_codec, features)
+    T, H = out.shape
+    assert cb0.dtype == torch.int64 and cb0.dim() == 1 and cb0.numel() == T and codec.is_contiguous()
+    ld_text = 0 if text.dim() == 1 else text.stride(0)
+    nc = None
+    if needs_codec is not None:
+        assert needs_codec.numel() == T and needs_codec.is_contiguous()
+        nc = needs_codec.view(torch.uint8) if needs_codec.dtype == torch.bool else needs_codec
+    call("vb_talker_embed", out.data_ptr(), out.stride(0), text.data_ptr(), ld_text, codec.data_ptr(), codec.shape[0],
+         cb0.data_ptr(), cb0.stride(0), _p(nc), _p(features), features.stride(0) if features is not None else 0, T, H,
+         _stream())
     return out
 
 
