@@ -146,13 +146,23 @@ int vb_gemm_t_tile(int T);
  *                       layer's first slab), resolved through the step's row plan (vb_plan_rows outputs) exactly as
  *                       vb_paged_attn tiles it over attn_grid_ctas CTAs; d_kv NULL skips those ops.  Gives up
  *                       (returns) when the progress words stop moving. */
+/*   vb_tag_next_l2_prefetch: the next vb_reduce_residual_rmsnorm / vb_qkv_rope_append of this host thread issues an L2
+ *                       prefetch of [d_ptr, d_ptr + bytes) from all its threads BEFORE its dependency wait: these kernels
+ *                       become resident ~5 us before their input exists, which is idle HBM time in a decode step; the
+ *                       engine points them at the NEXT projections' weights. */
+int vb_tag_next_l2_prefetch(const void* d_ptr, uint64_t bytes);
+/* shared-memory budget of the projection kernel's operand ring in KiB (0 = keep): ring_kb for every projection (default
+ * 104: two CTAs per SM, so a programmatic dependent sits beside its predecessor), gate_up_ring_kb for the gate/up
+ * projection (default 200: the long stream gets the whole SM).  Process-wide tuning knobs (env VB_GEMM_SMEM_KB[_GU]). */
+int vb_set_gemm_smem_kb(int ring_kb, int gate_up_ring_kb);
 int vb_tag_next_gemm(uint32_t* d_progress, uint64_t virt_offset_bytes);
 int vb_tag_next_attn(uint32_t* d_progress_tiles, int layer_ordinal);
 int vb_set_u32(uint32_t* d_ptr, uint32_t value, void* stream);
 int vb_weight_prefetch(const void* d_arena, const int64_t* d_ops, int n_ops, const uint32_t* d_progress,
                        uint64_t window_bytes, int grid_ctas, const void* d_kv, const int32_t* d_row_chunk_start,
                        const int32_t* d_row_kvlen, const int32_t* d_row_pagebase, const int32_t* d_kv_indices, int n_rows,
-                       int page_size, int chunk_tokens, int kv_row_bytes, int attn_grid_ctas, void* stream);
+                       int page_size, int chunk_tokens, int kv_row_bytes, int attn_grid_ctas, int flags, void* stream);
+/* (flags bit 0: dry run -- walk and pace, issue no prefetch: a development switch) */
 /* d_x_tiles (optional): X in the XT(vb_gemm_t_tile(T)) layout -- then x_map may be NULL; y_tiled (mode 2 only): write
  * Y in the XT(vb_gemm_t_tile(T)) layout over n_out columns (it is the down projection's activation). */
 int vb_gemm_bf16(void* d_y, const void* d_w_tiles, const void* x_map, const void* d_x_tiles, int T, int N, int K,

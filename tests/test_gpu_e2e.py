@@ -207,3 +207,40 @@ def test_stop_token_ring_matches_host_list(mode):
                             if len(a) == len(b) else -1)
             n_checked += 1
     assert n_checked >= 6 and n_padded >= 2
+
+
+def test_capacity_errors_finish_the_request_not_the_loop():
+    """A prompt longer than the worker accepts and a request that runs out of KV pages end with an ``error: ...``
+    finish reason and give back their slot / pages; the other streams keep running and complete normally.  (The
+    reference raises queue.Empty / index errors out of prepare_lm_inputs with half-updated state, worker/base.py:237-249.)"""
+    import torch
+
+    from oracle import snac as osnac
+    from tests.e2e_harness import build_models
+    from vox_serve_b200.requests import Request
+    from vox_serve_b200.scheduler import Scheduler
+
+    dims = oorph.OrpheusDims.tiny(vocab_size=156940, stop_token_id=128258, audio_id_base=128266)
+    dims.max_tokens = 120
+    # 9 pages of 16 tokens: r0 (20-token prompt -> 2 pages, grows to 8) and r2 (12 -> 1 page) cannot both run to 120
+    worker, _ = build_models(dims, osnac.SnacConfig.tiny(), 3, 4, 16, 9)
+    worker.max_prefill_tokens = 64
+    g = torch.Generator().manual_seed(5)
+    mk = lambda n: torch.randint(10, dims.vocab_size, (n - 5,), generator=g).tolist()   # noqa: E731
+    reqs = [Request(request_id="ok", prompt=mk(20), model_kwargs={"voice": None}),
+            Request(request_id="too_long", prompt=mk(100), model_kwargs={"voice": None}),
+            Request(request_id="starved", prompt=mk(12), model_kwargs={"voice": None})]
+    sched = Scheduler(worker)
+    for r in reqs:
+        sched.submit(r)
+    n = sched.run_until_done(max_steps=2000)
+    torch.cuda.synchronize()
+    by = {r.request_id: r for r in reqs}
+    assert n < 2000 and all(r.done_all for r in reqs)
+    assert by["too_long"].finish_reason.startswith("error: prompt of 100 tokens") and not sched.audio["too_long"]
+    reasons = {by["ok"].finish_reason, by["starved"].finish_reason}
+    assert any(x.startswith("error: out of KV pages") for x in reasons) and "max_tokens_reached" in reasons, reasons
+    winner = "ok" if by["ok"].finish_reason == "max_tokens_reached" else "starved"
+    assert len(sched.audio[winner]) >= 10
+    assert {r.request_id for r in sched.finished} == {"ok", "too_long", "starved"}
+    assert worker.empty_pages.qsize() == worker.max_num_pages and len(worker.free_slots) == worker.max_batch_size

@@ -47,9 +47,12 @@ SIGNATURES = {
     "vb_set_trace": (c_int, [P]),
     "vb_gemm_t_tile": (c_int, [c_int]),
     "vb_tag_next_gemm": (c_int, [P, c_uint64]),
+    "vb_set_gemm_smem_kb": (c_int, [c_int, c_int]),
     "vb_set_u32": (c_int, [P, C.c_uint32, P]),
     "vb_tag_next_attn": (c_int, [P, c_int]),
-    "vb_weight_prefetch": (c_int, [P, P, c_int, P, c_uint64, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_tag_next_l2_prefetch": (c_int, [P, c_uint64]),
+    "vb_weight_prefetch": (c_int, [P, P, c_int, P, c_uint64, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int,
+                                   P]),
     "vb_weight_tiles_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vb_pack_weight_tiles": (c_int, [P, P, c_int, c_int, c_int64, c_int, P]),
     "vb_gemm_bf16": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
@@ -133,7 +136,8 @@ def check(rc: int, what: str = ""):
 # kernels (+ memset nodes) each entry point enqueues; everything not listed launches exactly one
 LAUNCHES = {"vb_set_pdl": 0, "vb_set_trace": 0, "vb_weight_tiles_bytes": 0, "vb_decode_chain_workspace_bytes": 0,
             "vb_decode_chain_flags_bytes": 0, "vb_tensor_map_kv": 0, "vb_tensor_map_2d_bf16": 0, "vb_device_info": 0, "vb_sample": 1,
-            "vb_update_repetition_cache": 1}
+            "vb_update_repetition_cache": 1, "vb_tag_next_gemm": 0, "vb_tag_next_attn": 0, "vb_tag_next_l2_prefetch": 0,
+            "vb_set_gemm_smem_kb": 0}
 launch_counter = [0]
 
 

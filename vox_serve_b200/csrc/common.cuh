@@ -211,6 +211,17 @@ __device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(p)), "r"(bytes)
                : "memory");
 }
+// Per-thread L2 prefetch of a linear range, one 128-byte line per instruction (CCTL.E.PF2): thread `t` of `n` takes
+// lines t, t + n, ...  Fire and forget; used by the latency-bound kernels of the decode chain BEFORE their dependency
+// wait to pull the next projection's weights into L2 while HBM would otherwise idle (measured: a 100 MB range issued
+// by 37 k threads is in flight within ~10 us; a dedicated polling prefetch kernel beside the chain cost 0.14 us per
+// resident CTA at every kernel boundary instead -- tests/ablate_prefetch.py).
+__device__ __forceinline__ void prefetch_l2_lines(const void* base, unsigned long long bytes, unsigned long long t,
+                                                  unsigned long long n) {
+  const char* b = static_cast<const char*>(base);
+  for (unsigned long long off = t * 128ull; off < bytes; off += n * 128ull)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<uint64_t>(b + off)) : "memory");
+}
 // This CTA's share of a [base, base + bytes) prefetch, issued by `nthreads` cooperating threads (index `t`) in
 // 8 KiB pieces.  Used to pull the NEXT projection's weights into L2 while the current kernel is not using HBM.
 __device__ __forceinline__ void prefetch_l2_slice(const void* base, size_t bytes, int cta, int n_ctas, int t,

@@ -584,6 +584,7 @@ __global__ void __launch_bounds__(256) row_ssq_kernel(float* __restrict__ ssq, c
 }
 
 static int g_gemm_smem_budget = -1;
+static int g_gemm_gu_kb = -1;
 // tag of the NEXT projection launch of this host thread (vb_tag_next_gemm); consumed by launch_gemm
 static thread_local unsigned int* t_progress_ptr = nullptr;
 static thread_local unsigned long long t_progress_virt = 0;
@@ -631,9 +632,8 @@ static int launch_gemm(GemmParams& p, const void* w_tiles, const void* x_map, cu
   if (p.mode == GM_SILU && !p.norm) {
     // the gate/up stream is the long one (48 stages per CTA) and it follows a small kernel: a 10-stage ring on the
     // whole SM beats co-residency here (forward 2.68 -> 2.64 ms; VB_GEMM_SMEM_KB_GU overrides)
-    static int gu_kb = -1;
-    if (gu_kb < 0) { const char* e = getenv("VB_GEMM_SMEM_KB_GU"); gu_kb = e ? atoi(e) : 200; }
-    if (gu_kb >= 48 && gu_kb <= 220) budget = gu_kb * 1024;
+    if (g_gemm_gu_kb < 0) { const char* e = getenv("VB_GEMM_SMEM_KB_GU"); g_gemm_gu_kb = e ? atoi(e) : 200; }
+    if (g_gemm_gu_kb >= 48 && g_gemm_gu_kb <= 220) budget = g_gemm_gu_kb * 1024;
   }
   int stages = (budget - extra) / stage_bytes;
   if (stages > 12) stages = 12;
@@ -694,7 +694,8 @@ __device__ __forceinline__ unsigned long long pf_consumed(const unsigned int* pr
 __global__ void __launch_bounds__(32) weight_prefetch_kernel(const uint8_t* __restrict__ arena,
                                                              const PrefetchOp* __restrict__ ops, int n_ops,
                                                              const unsigned int* progress, unsigned long long window,
-                                                             const PrefetchKV kvp) {
+                                                             const PrefetchKV kvp, int flags) {
+  const bool dry = (flags & 1) != 0;       // (dev) walk and pace, but issue no prefetch
   const int lane = threadIdx.x;
   // the KV part of the stream has this step's size: every layer reads total_tiles tiles of 2 * tok rows
   const unsigned long long tile_bytes = kvp.kv ? 2ull * kvp.tok * kvp.row_bytes : 0ull;
@@ -735,6 +736,7 @@ __global__ void __launch_bounds__(32) weight_prefetch_kernel(const uint8_t* __re
         if (give_up) return;
       }
       if (virt + piece <= consumed) continue;        // the consumer got there first
+      if (dry) continue;
       if (!is_kv) {
         const uint8_t* src = arena + o.phys_off + (c * o.stages_per_cta + s) * o.a_stage;
         for (unsigned int l = lane * 128u; l < static_cast<unsigned int>(o.a_stage); l += 32u * 128u)
@@ -794,6 +796,14 @@ int vb_pack_weight_tiles(void* d_dst, const void* d_w, int N, int K, int64_t ldw
   return 0;
 }
 
+int vb_set_gemm_smem_kb(int ring_kb, int gate_up_ring_kb) {
+  VB_CHECK_ARG((ring_kb == 0 || (ring_kb >= 48 && ring_kb <= 220)) && (gate_up_ring_kb == 0 || (gate_up_ring_kb >= 48 && gate_up_ring_kb <= 220)),
+               "vb_set_gemm_smem_kb: budgets are 0 (keep) or 48..220 KiB");
+  if (ring_kb) g_gemm_smem_budget = ring_kb * 1024;
+  if (gate_up_ring_kb) g_gemm_gu_kb = gate_up_ring_kb;
+  return 0;
+}
+
 int vb_tag_next_gemm(uint32_t* d_progress, uint64_t virt_offset_bytes) {
   VB_CHECK_ARG((virt_offset_bytes & 1023) == 0, "vb_tag_next_gemm: offset must be a multiple of 1 KiB");
   t_progress_ptr = d_progress;
@@ -810,7 +820,7 @@ int vb_set_u32(uint32_t* d_ptr, uint32_t value, void* stream) {
 int vb_weight_prefetch(const void* d_arena, const int64_t* d_ops, int n_ops, const uint32_t* d_progress,
                        uint64_t window_bytes, int grid_ctas, const void* d_kv, const int32_t* d_row_chunk_start,
                        const int32_t* d_row_kvlen, const int32_t* d_row_pagebase, const int32_t* d_kv_indices, int n_rows,
-                       int page_size, int chunk_tokens, int kv_row_bytes, int attn_grid_ctas, void* stream) {
+                       int page_size, int chunk_tokens, int kv_row_bytes, int attn_grid_ctas, int flags, void* stream) {
   VB_CHECK_ARG(d_arena && d_ops && d_progress, "vb_weight_prefetch: null pointer");
   VB_CHECK_ARG(n_ops > 0 && grid_ctas > 0 && window_bytes > 0, "vb_weight_prefetch: bad arguments");
   VB_CHECK_ARG(!d_kv || (d_row_chunk_start && d_row_kvlen && d_row_pagebase && d_kv_indices && n_rows > 0 && page_size > 0 &&
@@ -825,7 +835,7 @@ int vb_weight_prefetch(const void* d_arena, const int64_t* d_ops, int n_ops, con
   kvp.attn_grid = attn_grid_ctas;
   VB_LAUNCH_PLAIN(weight_prefetch_kernel, grid_ctas, 32, 0, stream, static_cast<const uint8_t*>(d_arena),
                   reinterpret_cast<const PrefetchOp*>(d_ops), n_ops, d_progress,
-                  static_cast<unsigned long long>(window_bytes), kvp);
+                  static_cast<unsigned long long>(window_bytes), kvp, flags);
   return 0;
 }
 

@@ -95,9 +95,10 @@ class LlamaWeights:
         head_bytes = ops.weight_tiles_bytes(dims.vocab_size, H, 128)
         n_heads_out = len(heads) if heads is not None else 1
         if dev.type == "cuda":
-            self.arena = torch.empty(dims.num_hidden_layers * sum(per_layer) + n_heads_out * head_bytes, dtype=torch.uint8,
-                                     device=dev)
-            assert self.arena.data_ptr() % 1024 == 0
+            raw = torch.empty(dims.num_hidden_layers * sum(per_layer) + n_heads_out * head_bytes + 1024, dtype=torch.uint8,
+                              device=dev)
+            pad = (-raw.data_ptr()) % 1024           # (small allocations are only 512-byte aligned)
+            self.arena = raw[pad:pad + raw.numel() - 1024]
         off = 0
         for i in range(dims.num_hidden_layers):
             n = hf_layer_names(i, prefix)
@@ -219,9 +220,12 @@ class LlamaEngine:
 
     # ---- L2 weight prefetcher (decode-sized steps, default layer mode) ----------------------------------
     # VB_L2_PREFETCH=0 disables it; VB_L2_WINDOW_MB = how far ahead of the projections' consumption it may run
-    l2_prefetch = os.environ.get("VB_L2_PREFETCH", "1") != "0"
+    l2_prefetch = os.environ.get("VB_L2_PREFETCH", "0") != "0"      # (off until it wins: see tests/ablate_prefetch.py)
     l2_prefetch_kv = os.environ.get("VB_L2_PREFETCH_KV", "1") != "0"      # also the step's KV (attention rows of the table)
     l2_window_mb = int(os.environ.get("VB_L2_WINDOW_MB", "64"))
+    l2_prefetch_ctas = int(os.environ.get("VB_L2_PREFETCH_CTAS", "0"))      # 0 = one per SM
+    l2_prefetch_flags = int(os.environ.get("VB_L2_PREFETCH_FLAGS", "0"))    # bit 0: dry run (dev)
+    l2_prefetch_kernel = os.environ.get("VB_L2_PREFETCH_KERNEL", "1") != "0"   # 0: publish progress only (dev)
 
     def _init_prefetch(self) -> None:
         """Consumption-order table of the decode step's weight stream for ops.weight_prefetch: one row per projection
@@ -251,6 +255,15 @@ class LlamaEngine:
         self.pf_virt = virt_of
         self.pf_progress = torch.zeros(4, dtype=torch.int32, device=self.device)
         self.pf_stream = torch.cuda.Stream(device=self.device)
+
+    # In-kernel L2 prefetch (vb_tag_next_l2_prefetch): the reduce / norm and RoPE kernels of a decode-sized step are
+    # resident several microseconds before their inputs exist; they spend that time asking L2 for the weights the NEXT
+    # projections will stream.  pf_inline_gu_mb: how much of gate/up the O-projection's reduce kernel requests;
+    # the down-projection's reduce kernel requests the next layer's QKV + O weights (contiguous in the arena);
+    # pf_inline_down_mb: how much of down the RoPE kernel requests (HBM idles during a short-context attention).
+    pf_inline = os.environ.get("VB_L2_INLINE_PREFETCH", "0") != "0"
+    pf_inline_gu_mb = int(os.environ.get("VB_L2_INLINE_GU_MB", "64"))
+    pf_inline_down_mb = int(os.environ.get("VB_L2_INLINE_DOWN_MB", "0"))
 
     def _tag(self, layer: int, key: str) -> None:
         if self._pf_live:
@@ -294,9 +307,11 @@ class LlamaEngine:
             self.pf_stream.wait_stream(main)
             with torch.cuda.stream(self.pf_stream):
                 kv = self.kv_cache if self.l2_prefetch_kv else None
-                ops.weight_prefetch(w.arena, self.pf_table, self.pf_progress, self.l2_window_mb << 20, self.sms,
-                                    kv_cache=kv, plan=plan, n_rows=R, page_size=self.page_size, chunk_tokens=self.chunk,
-                                    attn_grid_ctas=self.attn_grid)
+                if self.l2_prefetch_kernel:
+                    ops.weight_prefetch(w.arena, self.pf_table, self.pf_progress, self.l2_window_mb << 20,
+                                        self.l2_prefetch_ctas or self.sms, kv_cache=kv, plan=plan, n_rows=R,
+                                        page_size=self.page_size, chunk_tokens=self.chunk,
+                                        attn_grid_ctas=self.attn_grid, flags=self.l2_prefetch_flags)
         if input_ids is not None:
             ops.embedding(w.embed, input_ids, out=hidden)
         x_final = normed
@@ -396,9 +411,12 @@ class LlamaEngine:
         s_qkv, s_o, s_dn = self._split(self.split_qkv, R), self._split(self.split_o, R), self._split(self.split_down, R)
         q = self.q[:R]
         n_layers = len(w.layers)
+        inline = self.pf_inline and tiled and w.arena is not None
         for i, L in enumerate(w.layers):
             self._tag(i, "qkv")
             p = ops.gemm(normed, L["qkv"], mode=1, split_k=s_qkv, out=self._partials(s_qkv, R, self.qkv_w), tile_rows=D)
+            if inline and self.pf_inline_down_mb:
+                ops.tag_next_l2_prefetch(L["down"].data, self.pf_inline_down_mb << 20)
             ops.qkv_rope_append(p, self.kv_cache[i], position_ids, self.freq, plan, hq, hkv, D, q_out=q,
                                 q_norm=L.get("qn"), k_norm=L.get("kn"), norm_eps=d.rms_norm_eps)
             if self._pf_live and self.l2_prefetch_kv:
@@ -408,12 +426,20 @@ class LlamaEngine:
             self._tag(i, "o")
             p = ops.gemm(attn_o if attn_tiled else attn_o.view(R, hq * D), L["o"], mode=1, split_k=s_o,
                          out=self._partials(s_o, R, H))
+            if inline and self.pf_inline_gu_mb:
+                ops.tag_next_l2_prefetch(L["gu"].data, self.pf_inline_gu_mb << 20)
             ops.reduce_residual_rmsnorm(p, hidden, L["ln2"], d.rms_norm_eps, hidden_out=hidden, normed_out=normed)
             self._tag(i, "gu")
             ops.gemm(normed, L["gu"], mode=2, out=act, tile_rows=2 * self.gu_half, n_out=I)
             self._tag(i, "down")
             p = ops.gemm(act, L["down"], mode=1, split_k=s_dn, out=self._partials(s_dn, R, H))
             nxt = w.layers[i + 1]["ln1"] if i + 1 < n_layers else w.norm
+            if inline:
+                if i + 1 < n_layers:       # qkv and o of the next layer follow each other in the arena
+                    N = w.layers[i + 1]
+                    ops.tag_next_l2_prefetch(N["qkv"].data, N["qkv"].data.numel() + N["o"].data.numel())
+                else:
+                    ops.tag_next_l2_prefetch(w.lm_head.data, 64 << 20)
             ops.reduce_residual_rmsnorm(p, hidden, nxt, d.rms_norm_eps, hidden_out=hidden, normed_out=normed)
         return normed
 

@@ -81,19 +81,30 @@ def tensor_map_kv(kv_cache: torch.Tensor, box_tokens: int) -> TensorMap:
     return tm
 
 
-_map2d_cache: Dict[Tuple, TensorMap] = {}
+# tensor maps of the engine's static activation buffers; bounded: ad-hoc callers (tests, the operator shims on
+# transient tensors) would otherwise pin every tensor they ever passed
+_map2d_cache: "OrderedDict[Tuple, TensorMap]" = None
+_MAP2D_CACHE_MAX = 256
 
 
 def tensor_map_2d(t: torch.Tensor, box_rows: int, cache: bool = True) -> TensorMap:
     _need_cuda(t)
     assert t.dtype == BF16 and t.dim() == 2 and t.stride(1) == 1
+    global _map2d_cache
+    if _map2d_cache is None:
+        from collections import OrderedDict
+
+        _map2d_cache = OrderedDict()
     key = (t.data_ptr(), t.shape[0], t.shape[1], t.stride(0), box_rows)
     if cache and key in _map2d_cache:
+        _map2d_cache.move_to_end(key)
         return _map2d_cache[key]
     tm = TensorMap(t)
     call("vb_tensor_map_2d_bf16", tm.ptr, t.data_ptr(), t.shape[0], t.shape[1], t.stride(0), box_rows)
     if cache:
         _map2d_cache[key] = tm
+        while len(_map2d_cache) > _MAP2D_CACHE_MAX:
+            _map2d_cache.popitem(last=False)
     return tm
 
 
@@ -350,6 +361,17 @@ def set_u32(t: torch.Tensor, value: int) -> None:
     call("vb_set_u32", t.data_ptr(), int(value), _stream())
 
 
+def tag_next_l2_prefetch(t: Optional[torch.Tensor], nbytes: Optional[int] = None, offset: int = 0) -> None:
+    """The next reduce_residual_rmsnorm / qkv_rope_append launched from this thread prefetches ``nbytes`` of ``t`` (uint8
+    view semantics: bytes from ``offset``) into L2 before its dependency wait (vb_tag_next_l2_prefetch); None clears."""
+    if t is None:
+        call("vb_tag_next_l2_prefetch", None, 0)
+        return
+    total = t.numel() * t.element_size()
+    n = total - offset if nbytes is None else min(int(nbytes), total - offset)
+    call("vb_tag_next_l2_prefetch", t.data_ptr() + int(offset), max(0, n))
+
+
 def tag_next_attn(progress_tiles: Optional[torch.Tensor], layer_ordinal: int = 0) -> None:
     """The next paged_attn launched from this thread publishes the KV tiles the step has consumed (vb_tag_next_attn)."""
     call("vb_tag_next_attn", _p(progress_tiles), int(layer_ordinal))
@@ -358,7 +380,7 @@ def tag_next_attn(progress_tiles: Optional[torch.Tensor], layer_ordinal: int = 0
 def weight_prefetch(arena: torch.Tensor, op_table: torch.Tensor, progress: torch.Tensor, window_bytes: int,
                     grid_ctas: Optional[int] = None, kv_cache: Optional[torch.Tensor] = None,
                     plan: Optional["RowPlan"] = None, n_rows: int = 0, page_size: int = 0, chunk_tokens: int = 0,
-                    attn_grid_ctas: int = 0) -> None:
+                    attn_grid_ctas: int = 0, flags: int = 0) -> None:
     """Launch the L2 prefetcher (vb_weight_prefetch) on the CURRENT stream: meant for a side stream that runs beside
     the decode step.  op_table: int64 [n_ops, 6] on the device; progress: int32 [>= 2] = {KiB of weights, KV tiles}.
     With ``kv_cache`` + ``plan`` the table's attention rows prefetch the step's KV as well."""
@@ -371,13 +393,13 @@ def weight_prefetch(arena: torch.Tensor, op_table: torch.Tensor, progress: torch
         call("vb_weight_prefetch", arena.data_ptr(), op_table.data_ptr(), op_table.shape[0], progress.data_ptr(),
              int(window_bytes), grid, kv_cache.data_ptr(), plan.row_chunk_start.data_ptr(), plan.row_kvlen.data_ptr(),
              plan.row_pagebase.data_ptr(), plan.kv_indices.data_ptr(), int(n_rows), int(page_size), int(chunk_tokens),
-             int(row_bytes), int(attn_grid_ctas), _stream())
+             int(row_bytes), int(attn_grid_ctas), int(flags), _stream())
     else:
         call("vb_weight_prefetch", arena.data_ptr(), op_table.data_ptr(), op_table.shape[0], progress.data_ptr(),
-             int(window_bytes), grid, None, None, None, None, None, 0, 0, 0, 0, 0, _stream())
+             int(window_bytes), grid, None, None, None, None, None, 0, 0, 0, 0, 0, int(flags), _stream())
 
 
-_pack_cache: Dict[Tuple, PackedWeight] = {}
+_pack_cache: Dict[Tuple, Tuple[PackedWeight, torch.Tensor]] = {}
 
 
 def _packed(w, tile_rows: int) -> PackedWeight:
@@ -387,12 +409,14 @@ def _packed(w, tile_rows: int) -> PackedWeight:
         assert w.tile_rows == tile_rows, f"weight packed for tile_rows {w.tile_rows}, kernel wants {tile_rows}"
         return w
     key = (w.data_ptr(), tuple(w.shape), w.stride(0), tile_rows, w._version)
-    pw = _pack_cache.get(key)
-    if pw is None:
-        if len(_pack_cache) > 64:
+    hit = _pack_cache.get(key)
+    if hit is None:
+        if len(_pack_cache) > 16:
             _pack_cache.clear()
-        pw = _pack_cache[key] = pack_weight(w, tile_rows)
-    return pw
+        # the entry keeps the SOURCE tensor alive: a freed tensor's address can be handed to a different weight of the
+        # same shape, which would otherwise hit this key and get the old packed copy
+        hit = _pack_cache[key] = (pack_weight(w, tile_rows), w)
+    return hit[0]
 
 
 def gemm(x, w, mode: int = 0, split_k: int = 1, out=None, tile_rows: int = 128, n_out: Optional[int] = None,

@@ -44,6 +44,11 @@ class Scheduler:
         self.pending.append(req)
 
     def _prepare_requests(self):
+        for r in self.active_requests:
+            # a request the worker FAILED (finish_reason "error: ...": prompt too long, out of KV pages) never reaches
+            # _send_responses: its completion is recorded here (the worker has already released what it held)
+            if r.done_all and (r.finish_reason or "").startswith("error") and r not in self.finished:
+                self.finished.append(r)
         self.active_requests = [r for r in self.active_requests if not r.done_all]
         while self.pending and len(self.active_requests) < self.max_batch_size:
             self.active_requests.append(self.pending.popleft())

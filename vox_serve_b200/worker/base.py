@@ -95,6 +95,9 @@ class ModelWorker:
                                enable_torch_compile=enable_torch_compile, audio_decoder_device=self.device,
                                detokenize_interval=detokenize_interval, **model_kwargs)
         self.model = model
+        if not 1 <= max_batch_size <= 64:
+            raise VoxB200Error(f"max_batch_size {max_batch_size} outside [1, 64]: decode-sized steps (one row per request) are "
+                               "what the projection kernels tile for; run more replicas for more streams")
         self.max_batch_size, self.dp_rank, self.dp_size = max_batch_size, dp_rank, dp_size
         self.max_num_pages, self.page_size = max_num_pages, page_size
         self.nvtx_enabled = enable_nvtx
@@ -104,7 +107,8 @@ class ModelWorker:
 
         self.logger = logging.getLogger(__name__)
         if self.model.has_depth_transformer or self.model.needs_watermarking:
-            raise VoxB200Error("depth-transformer / watermarked models are not on the B200 path yet (SURVEY.md §8f)")
+            raise VoxB200Error("this worker serves single-codebook LMs with a built vocoder (Orpheus); the depth-transformer "
+                               "LMs run through depth_engine / model.csm.frame_device until their codecs exist (SURVEY.md §8f)")
         self.needs_watermarking = False
         self.has_depth_transformer = False
         self.empty_pages: "queue.Queue[int]" = queue.Queue()
@@ -245,6 +249,8 @@ class ModelWorker:
         if len(lm_requests) > self.max_batch_size:
             raise VoxB200Error(f"{len(lm_requests)} LM requests exceed max_batch_size {self.max_batch_size}")
         is_prefill = any(not r.done_lm_prefill for r in lm_requests)
+        failed: List[int] = []
+        n_prefill_ok = 0
         t = 0         # rows so far
         npg = 0       # pages so far
         qo[0] = 0
@@ -264,22 +270,39 @@ class ModelWorker:
                 req.input_length = n
                 if out.repetition_cache is not None:
                     req.repetition_cache = out.repetition_cache
-                if t + n > self.max_rows:
-                    raise VoxB200Error(f"prefill of {t + n} rows exceeds the worker's max_rows {self.max_rows}")
+                n_pages = (n + self.page_size - 1) // self.page_size
+                # capacity: a request that cannot be served is finished with an error reason and everything it held
+                # is released -- the scheduler loop (and the other streams) keep running.  (The reference raises out of
+                # prepare_lm_inputs with half-updated state: queue.Empty / CUDA errors, worker/base.py:237-249.)
+                why = None
+                if n > self.max_prefill_tokens or t + n > self.max_rows - (len(lm_requests) - i - 1):
+                    why = f"error: prompt of {n} tokens exceeds max_prefill_tokens {self.max_prefill_tokens}"
+                elif self.empty_pages.qsize() < n_pages:
+                    why = f"error: out of KV pages ({n_pages} needed, {self.empty_pages.qsize()} free)"
+                if why is not None:
+                    self._fail_request(req, why)
+                    failed.append(i)
+                    qo[i + 1], ip[i + 1], last[i], slots[i] = t, npg, 1, slot
+                    continue
                 ids[t:t + n] = req.input_tokens[:, 0].numpy() if not req.input_tokens.is_cuda else \
                     req.input_tokens[:, 0].cpu().numpy()
                 pos[t:t + n] = np.arange(n, dtype=np.int32)
                 row_slot[t:t + n] = -1
-                n_pages = (n + self.page_size - 1) // self.page_size
                 req.kv_token_len = n
                 req.kv_pages = [self.empty_pages.get_nowait() for _ in range(n_pages)]
                 req.kv_last_page_len = n % self.page_size or self.page_size
                 req.next_position_id = n + 1          # position n is skipped, as in worker/base.py:299
                 req.done_lm_prefill = True
+                n_prefill_ok += 1
                 self.n_out[slot:slot + 1].zero_()
                 t += n
             else:
                 slot = self.slot_of[req.request_id]
+                if req.kv_last_page_len + 1 > self.page_size and self.empty_pages.empty():
+                    self._fail_request(req, "error: out of KV pages")
+                    failed.append(i)
+                    qo[i + 1], ip[i + 1], last[i], slots[i] = t, npg, 1, slot
+                    continue
                 req.kv_token_len += 1
                 req.kv_last_page_len += 1
                 if req.kv_last_page_len > self.page_size:
@@ -297,15 +320,36 @@ class ModelWorker:
             ip[i + 1] = npg
             last[i] = req.kv_last_page_len
             slots[i] = slot
+        if failed:
+            # drop the failed requests from the step (the caller's list is edited in place: it is what
+            # run_lm_prefill / run_lm_decode receive) and rebuild the packed tables without their (empty) entries
+            keep = [i for i in range(len(lm_requests)) if i not in failed]
+            for dst, src in enumerate(keep):
+                qo[dst + 1], ip[dst + 1], last[dst], slots[dst] = qo[src + 1], ip[src + 1], last[src], slots[src]
+            lm_requests[:] = [lm_requests[i] for i in keep]
+            if not lm_requests:
+                return None
+            is_prefill = n_prefill_ok > 0
         B = len(lm_requests)
         rep = None
         if self.rep_cache is not None:
             rep = self.rep_cache       # slot-resident; rows selected through `slots` (no per-step torch.stack)
-        return {"qo_indptr": qo[:B + 1].tolist(), "paged_kv_indptr": ip[:B + 1].tolist(),
-                "paged_kv_indices": indices[:npg].tolist(),
-                "paged_kv_last_page_len": last[:B].tolist(), "input_ids": self.input_ids[:t].view(t, 1),
-                "position_ids": st.d("pos", t), "input_features": None, "input_masks": None,
-                "repetition_cache": rep, "is_prefill": is_prefill, "n_rows": t, "n_pages": npg}
+        lm_inputs = {"qo_indptr": qo[:B + 1].tolist(), "paged_kv_indptr": ip[:B + 1].tolist(),
+                     "paged_kv_indices": indices[:npg].tolist(),
+                     "paged_kv_last_page_len": last[:B].tolist(), "input_ids": self.input_ids[:t].view(t, 1),
+                     "position_ids": st.d("pos", t), "input_features": None, "input_masks": None,
+                     "repetition_cache": rep, "is_prefill": is_prefill, "n_rows": t, "n_pages": npg}
+        if self.early_launch:
+            lm_inputs["_launched"] = self._launch_step(B, t, is_prefill)
+        return lm_inputs
+
+    def _fail_request(self, req: Request, reason: str) -> None:
+        """Finish a request the worker cannot serve: no audio, an ``error: ...`` finish reason, slot and pages back in
+        the pools.  The scheduler sends the completion message and drops it at its next step."""
+        req.done_lm_prefill = req.done_lm_generation = req.done_all = True
+        req.finish_reason = reason
+        self.logger.error("request %s: %s", req.request_id, reason)
+        self.free_kv_cache(req)
 
     def _acquire_slot(self, req: Request) -> int:
         if req.request_id in self.slot_of:
@@ -339,10 +383,14 @@ class ModelWorker:
         ops.token_feedback(out.view(-1), slots, self.next_input, self.history, self.n_out,
                            skip_token=getattr(m, "stop_token_id", -1))
 
-    def _run_step(self, requests: List[Request], lm_inputs: LMInputs) -> Optional[Coroutine]:
-        if len(requests) == 0:
-            return None
-        B, T, is_prefill = len(requests), lm_inputs["n_rows"], lm_inputs["is_prefill"]
+    # The schedulers call prepare_lm_inputs -> run_detokenize -> (send responses) -> run_lm_* (scheduler/base.py:149-162).
+    # Everything the LM step needs is known when prepare_lm_inputs returns, so the step's device work is ENQUEUED there:
+    # the vocoder pass of run_detokenize (side stream) and the host's wait for its PCM then overlap the LM step instead
+    # of preceding it, also under the synchronous Scheduler._step.  run_lm_prefill / run_lm_decode hand back the
+    # request-state coroutine of the step that is already in flight.  VB_EARLY_LAUNCH=0 restores launch-at-run_lm.
+    early_launch = os.environ.get("VB_EARLY_LAUNCH", "1") != "0"
+
+    def _launch_step(self, B: int, T: int, is_prefill: bool):
         self.nvtx_range_push(f"lm_{'prefill' if is_prefill else 'decode'}_bs{B}")
         self.staging.upload()
         if not is_prefill and self.use_cuda_graph:
@@ -358,7 +406,14 @@ class ModelWorker:
         ids_host[:B].copy_(self.out_ids[:B], non_blocking=True)
         ready.record()
         self.nvtx_range_pop()
-        slots_host = self.staging.h("slots")[:B].tolist()
+        return ids_host, ready, self.staging.h("slots")[:B].tolist()
+
+    def _run_step(self, requests: List[Request], lm_inputs: LMInputs) -> Optional[Coroutine]:
+        if len(requests) == 0:
+            return None
+        B, T, is_prefill = len(requests), lm_inputs["n_rows"], lm_inputs["is_prefill"]
+        launched = lm_inputs.pop("_launched", None)
+        ids_host, ready, slots_host = launched if launched is not None else self._launch_step(B, T, is_prefill)
         return self.model.sampling_host(self.out_ids[:B], requests, self.rep_cache, ids_host=ids_host, ready=ready,
                                         cache_rows_host=slots_host)
 
