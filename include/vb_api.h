@@ -376,6 +376,36 @@ int vb_snac_final(float* d_y, const float* d_x, const float* d_w /*[C][7]*/, con
                   const float* d_alpha_in, int B, int C, int T, int t0, int t1, void* stream);
 /* (audio * 32767) truncated toward zero to int16, no clipping: cuda_graph_worker.py:1252-1253 */
 int vb_pcm16(int16_t* d_out, const float* d_audio, int64_t n, void* stream);
+
+/* ---- Mimi decode stages (CSM's vocoder: vox_serve/tokenizer/mimi.py:2993-3018), fp32, activations [B][C][T] ----------
+ * Each chunk is decoded with zero left context, as the reference's stateless StreamingConv1d / ConvTranspose1d do
+ * (mimi.py:2116-2148, 2192-2215).
+ *   vb_mimi_codes_sum:  z[b][d][t] = sum_{k0 <= k < k1} emb[k][codes[b][k][t]][d]  (ResidualVectorQuantization.decode
+ *                       :482-490; emb [K_total][bins][D] = embedding_sum / clamp(cluster_usage, eps), codes int64
+ *                       [B][K_total][T]);
+ *   vb_mimi_conv:       causal Conv1d with kernel ksize / dilation (left zero pad (ksize-1) * dilation), weight
+ *                       [Cout][Cin][ksize]; ksize 1 = the transformer's Linear layers and the 1x1 projections.
+ *                       elu_in: ELU on the input while it is fetched (SEANet puts ELU in front of every conv :2343-2400).
+ *                       epilogue 0: y = conv (+ bias); 1: y = resid + conv (+ bias) (SEANetResnetBlock true skip; the
+ *                       sum of the two RVQ branches :830-836); 2: y = resid + scale[co] * conv (LayerScale :1097-1129);
+ *                       3: y = gelu(conv) (exact erf GELU of the transformer FFN :1687-1703);
+ *   vb_mimi_convtr:     causal ConvTranspose1d kernel 2 s / stride s, rightmost K - S outputs dropped (:2192-2215), weight
+ *                       re-packed per output phase [s][Cout][2 Cin] (w[r][co][tap Cin + ci] = W[ci][co][r + tap s]);
+ *   vb_mimi_upsample:   the learnt channel-wise x s ConvTrUpsample1d (:2272-2323), weight [C][2 s];
+ *   vb_mimi_layernorm:  nn.LayerNorm over the channel axis of [B][C][T] (the [B, T, C] view of :1705-1712);
+ *   vb_mimi_attention:  causal self-attention of a chunk (T <= 64) with interleaved-pair RoPE at offset 0 (:874-930) on
+ *                       qkv [B][3 C][T] packed "(p h d)" (:1519-1523) -> [B][C][T]. */
+int vb_mimi_codes_sum(float* d_z, const int64_t* d_codes, const float* d_emb, int B, int K_total, int k0, int k1, int bins,
+                      int D, int T, void* stream);
+int vb_mimi_conv(float* d_y, const float* d_x, const float* d_w, const float* d_bias, const float* d_resid,
+                 const float* d_scale, int epilogue, int elu_in, int B, int Cin, int Cout, int T, int ksize, int dilation,
+                 void* stream);
+int vb_mimi_convtr(float* d_y, const float* d_x, const float* d_w_packed, const float* d_bias, int elu_in, int B, int Cin,
+                   int Cout, int T, int stride, void* stream);
+int vb_mimi_upsample(float* d_y, const float* d_x, const float* d_w, int B, int C, int T, int stride, void* stream);
+int vb_mimi_layernorm(float* d_y, const float* d_x, const float* d_w, const float* d_bias, int B, int C, int T, float eps,
+                      void* stream);
+int vb_mimi_attention(float* d_out, const float* d_qkv, int B, int C, int H, int T, float max_period, void* stream);
 /* n standard-normal fp32 draws: the NoiseBlock input the reference takes from torch.randn
  * (vox_serve/tokenizer/snac.py:206-212).  Philox4x32-10 + Box-Muller, counter = (offset, element / 4).
  * d_rng_state (optional, device u64 {seed, offset, arrivals}) replaces seed / offset and its offset advances by one

@@ -120,8 +120,10 @@ def depth_forward(w, dims: CsmDims, inputs_embeds, position_ids, wrapper, kv_cac
     return torch.stack([F.linear(h[r], head[r].T) for r in range(h.shape[0])], dim=0)
 
 
-def depth_loop_greedy(w, dims: CsmDims, hidden: torch.Tensor, cb0: int, page_size: int = 32):
-    """One request's codebooks 1 .. N-1 for one frame (greedy).  Returns (ids [N-1], logits [N-1, vocab])."""
+def depth_loop_greedy(w, dims: CsmDims, hidden: torch.Tensor, cb0: int, page_size: int = 32, forced=None):
+    """One request's codebooks 1 .. N-1 for one frame (greedy).  Returns (ids [N-1], logits [N-1, vocab]).  ``forced``
+    (ids of codebooks 1 .. N-1): feed these back instead of the argmax (teacher forcing; the returned ids stay the
+    oracle's own argmax of every step)."""
     N = dims.num_codebooks
     assert page_size >= N
     emb = w[BB + "embed_tokens.embed_audio_tokens.weight"]
@@ -140,7 +142,8 @@ def depth_loop_greedy(w, dims: CsmDims, hidden: torch.Tensor, cb0: int, page_siz
             break
         dec = lm_ops.PagedWrapperCPU("decode", page_size)
         dec.plan([0, 1], [0], [i + 2])                                              # kv length after this row
-        x = emb[tok + i * dims.vocab_size][None, :]
+        fed = tok if forced is None else int(forced[i - 1])
+        x = emb[fed + i * dims.vocab_size][None, :]
         logits = depth_forward(w, dims, x, torch.tensor([i + 1], dtype=torch.int32), dec, kv)[0]
     return ids, torch.stack(logs)
 

@@ -603,6 +603,48 @@ def golden_qwen3_tts_frames():
     print("qwen3_tts_tiny_frames.npz frames", frames)
 
 
+def golden_mimi():
+    """The reference's own ``MimiModel.decode`` (tokenizer/mimi.py:2993-3018) on CPU at a tiny configuration with all four
+    SEANet ratios, seeded weights from oracle.mimi.synth_state_dict loaded with ``load_state_dict(strict=False)`` (the
+    encoder side keeps its default initialisation: decode never touches it) -> tests/golden/mimi_tiny.npz."""
+    from . import mimi as omimi
+    from .ref_import import REFERENCE_ROOT
+
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    from vox_serve.tokenizer import mimi as rm
+
+    cfg = omimi.MimiConfig.tiny()
+    seanet = dict(rm._seanet_kwargs)
+    seanet.update(dimension=cfg.dimension, n_filters=cfg.n_filters, ratios=list(cfg.ratios))
+    quant = dict(dimension=cfg.codebook_dim, n_q=cfg.n_q, bins=cfg.bins, input_dimension=cfg.dimension,
+                 output_dimension=cfg.dimension)
+    tr = dict(rm._transformer_kwargs)
+    tr.update(d_model=cfg.dimension, num_heads=cfg.num_heads, num_layers=cfg.num_layers, dim_feedforward=cfg.dim_feedforward,
+              input_dimension=cfg.dimension, output_dimensions=[cfg.dimension])
+    enc, dec = rm.SEANetEncoder(**seanet), rm.SEANetDecoder(**seanet)
+    model = rm.MimiModel(enc, dec, rm.SplitResidualVectorQuantizer(**quant), channels=1, sample_rate=24000, frame_rate=12.5,
+                         encoder_frame_rate=24000 / enc.hop_length, causal=True, resample_method="conv",
+                         encoder_transformer=rm.ProjectedTransformer(device="cpu", **tr),
+                         decoder_transformer=rm.ProjectedTransformer(device="cpu", **tr)).eval()
+    seed = 17
+    sd = omimi.synth_state_dict(cfg, seed)
+    r = model.load_state_dict(sd, strict=False)
+    assert not r.unexpected_keys, r.unexpected_keys
+    assert all(k.startswith(("encoder", "downsample")) for k in r.missing_keys), r.missing_keys
+    model.set_num_codebooks(cfg.n_q)
+    g = torch.Generator().manual_seed(3)
+    codes = torch.randint(0, cfg.bins, (3, cfg.n_q, 5), generator=g)
+    with torch.no_grad():
+        wav = model.decode(codes)
+        latent = model._to_encoder_framerate(model.decode_latent(codes))
+        (tr_out,) = model.decoder_transformer(latent)
+    assert wav.shape == (3, 1, 5 * cfg.hop)
+    np.savez_compressed(os.path.join(OUT, "mimi_tiny.npz"), weight_seed=seed, codes=codes.numpy(), wav=wav.numpy(),
+                        latent=latent.numpy(), transformer_out=tr_out.numpy())
+    print("mimi_tiny.npz:", tuple(wav.shape), "abs max %.4f" % float(wav.abs().max()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "qwen3_tts":
@@ -610,6 +652,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "csm":
         golden_csm_frames()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "mimi":
+        golden_mimi()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "cosyvoice2":
         golden_cosyvoice2_lm()
@@ -629,6 +674,7 @@ def main():
         golden_glm_voice_lm()
         golden_csm_frames()
         golden_qwen3_tts_frames()
+        golden_mimi()
     finally:
         torch.cuda.synchronize = orig_sync
 

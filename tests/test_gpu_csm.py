@@ -249,3 +249,24 @@ def test_csm_adapter_frame_device_equals_step_at_a_time_surface():
         results[mode] = frames
     assert torch.equal(results["fused"][0][:, :N], results["stepwise"][0][:, :N]), (results["fused"][0], results["stepwise"][0])
     assert torch.equal(results["fused"][0][:, N], results["fused"][0][:, 0])
+
+
+def test_csm_postprocess_runs_the_mimi_decoder():
+    """csm.py:771-785: [B, 10, 33] frame rows -> drop the text column, clamp to the Mimi tables, decode every chunk on
+    its own -> [B, 1, 19200]; checked against the Mimi oracle on the adapter's own (seeded) decoder weights."""
+    from oracle import mimi as omimi
+    from vox_serve_b200.model.csm import CSMModel
+    from vox_serve_b200.tokenizer.mimi import synthetic_state_dict
+
+    model = CSMModel("csm-synthetic-tiny:4")
+    mc = model.audio_decoder.cfg
+    assert model.detokenize_interval == 10 and model.output_audio_length == 10 * mc.hop == 19200
+    g = torch.Generator().manual_seed(0)
+    N = model.dims.num_codebooks
+    rows = torch.randint(0, model.dims.vocab_size, (3, 10, N + 1), generator=g)
+    rows[0, 0, 0] = 5000                    # beyond the table: clamped to 2047 like the reference
+    wav = model.postprocess(rows.cuda())
+    assert wav.shape == (3, 1, 19200)
+    ocfg = omimi.MimiConfig(**{f.name: getattr(mc, f.name) for f in __import__("dataclasses").fields(omimi.MimiConfig)})
+    ref = omimi.decode(synthetic_state_dict(mc, 4), ocfg, rows[:, :, :-1].transpose(1, 2).clamp(0, 2047))
+    assert float((wav.cpu() - ref).abs().max() / ref.abs().max()) < 2e-4

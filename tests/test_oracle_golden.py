@@ -173,3 +173,23 @@ def test_qwen3_tts_frame_oracle_matches_reference_golden(golden_dir):
     full = oq.Qwen3TTSDims()         # the reference's defaults (qwen3_tts.py:113-253)
     assert (full.hidden_size, full.num_hidden_layers, full.num_code_groups, full.cp_hidden_size,
             full.cp_num_hidden_layers, full.vocab_size, full.cp_vocab_size) == (2048, 28, 16, 1024, 5, 3072, 2048)
+
+
+def test_mimi_decode_oracle_matches_reference_golden(golden_dir):
+    """SURVEY row a25 (CSM's vocoder): oracle/mimi.py -- split RVQ decode, learnt channel-wise x2 upsampling, the
+    8-layer causal RoPE transformer with LayerScale, the SEANet decoder with causal convs / transposed convs on a
+    zero left context -- against the reference's own MimiModel.decode on CPU (oracle/gen_golden.py:golden_mimi), all
+    four SEANet ratios, 3 x 8 x 5 codes -> 3 x 9600 samples: latent, transformer output and waveform bit-exact."""
+    from oracle import mimi as omimi
+
+    gd = _load(golden_dir, "mimi_tiny.npz")
+    cfg = omimi.MimiConfig.tiny()
+    sd = omimi.synth_state_dict(cfg, int(gd["weight_seed"]))
+    codes = torch.from_numpy(gd["codes"])
+    with torch.no_grad():
+        lat = omimi.upsample(sd, cfg, omimi.quantizer_decode(sd, cfg, codes))
+        tro = omimi.transformer(sd, cfg, lat)
+    assert np.array_equal(lat.numpy(), gd["latent"]) and np.array_equal(tro.numpy(), gd["transformer_out"])
+    wav = omimi.decode(sd, cfg, codes)
+    assert wav.shape == (3, 1, 5 * cfg.hop) and cfg.hop == 1920 and omimi.MimiConfig().hop == 1920
+    assert np.array_equal(wav.numpy(), gd["wav"])

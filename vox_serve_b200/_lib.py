@@ -91,6 +91,12 @@ SIGNATURES = {
     "vb_snac_convtr_tc": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_pcm16": (c_int, [P, P, c_int64, P]),
     "vb_randn": (c_int, [P, c_int64, c_uint64, c_uint64, P, P]),
+    "vb_mimi_codes_sum": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_mimi_conv": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_mimi_convtr": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_mimi_upsample": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
+    "vb_mimi_layernorm": (c_int, [P, P, P, P, c_int, c_int, c_int, c_float, P]),
+    "vb_mimi_attention": (c_int, [P, P, c_int, c_int, c_int, c_int, c_float, P]),
     "vb_orpheus_window_codes": (c_int, [P, P, P, P, c_int, c_int, P]),
 }
 

@@ -116,6 +116,10 @@ class DepthFrameEngine:
         seed = torch.cuda.default_generators[dev.index or 0].initial_seed() & ((1 << 62) - 1)
         self.rng_state = torch.tensor([seed, 0, 0], dtype=torch.int64, device=dev)
 
+    @property
+    def max_rows(self) -> int:
+        return self.bb.max_rows
+
     # ---- static depth-decoder plans ---------------------------------------------------------------------
     def depth_plans(self, B: int):
         """[(row plan, positions, last_rows)] for depth steps 1 .. N-1 at batch B (cuda_graph_worker.py:1070-1160:

@@ -10,8 +10,8 @@ What differs from the reference adapter:
     text with the Llama-3.2 tokenizer and prepends two built-in voice prompts encoded with the Mimi ENCODER
     (csm.py:511-568, 613-615); neither the tokenizer files nor that checkpoint exist offline;
   * weights: a local HF directory or ``state_dict=``, or ``csm-synthetic[-tiny][:seed]`` (seeded weights);
-  * ``postprocess`` needs the Mimi decoder (``vox_serve/tokenizer/mimi.py:2993-3018``), which is not built yet: it
-    raises.  The LM side (this file) is complete and parity-tested against the reference's modules.
+  * ``postprocess`` runs ``tokenizer.mimi.MimiDecoder`` (csrc/mimi.cu); its weights come from a local safetensors file,
+    ``audio_decoder_state_dict=`` or, for ``csm-synthetic`` names, a seeded generator.
 """
 from __future__ import annotations
 
@@ -71,7 +71,8 @@ TINY = dict(hidden_size=512, num_hidden_layers=2, num_attention_heads=8, num_key
 class CSMModel(BaseLMWithDepth):
     def __init__(self, model_name, dtype=BF16, device="cuda:0", tokenizer_path="meta-llama/Llama-3.2-1B",
                  enable_torch_compile=False, audio_decoder_device=None, state_dict: Optional[Dict] = None,
-                 dims: Optional[CsmDims] = None, max_tokens: Optional[int] = None):
+                 dims: Optional[CsmDims] = None, max_tokens: Optional[int] = None,
+                 audio_decoder_state_dict: Optional[Dict] = None, mimi_config=None):
         if model_name == "csm":
             model_name = "sesame/csm-1b"
         if dtype != BF16:
@@ -92,7 +93,17 @@ class CSMModel(BaseLMWithDepth):
         self.weights = CsmWeights(state_dict, self.dims, device)
         del state_dict
         self.text_tokenizer = None
-        self.audio_decoder = None            # MimiDecoder (tokenizer/mimi.py) is not on the CUDA path yet
+        from ..tokenizer.mimi import MimiConfig, MimiDecoder, synthetic_state_dict as mimi_synthetic
+
+        synthetic = model_name.startswith("csm-synthetic")
+        if mimi_config is None:
+            mimi_config = (MimiConfig(dimension=64, n_filters=8, codebook_dim=32, num_heads=2, num_layers=2, dim_feedforward=128)
+                           if synthetic and model_name.split(":")[0].endswith("-tiny") else MimiConfig())
+        if audio_decoder_state_dict is None and synthetic:
+            audio_decoder_state_dict = mimi_synthetic(mimi_config, int(model_name.split(":")[1]) if ":" in model_name else 0)
+        # csm.py:349-353: MimiDecoder(model_repo="kyutai/moshiko-pytorch-bf16", ..., num_codebooks=32)
+        self.audio_decoder = MimiDecoder(num_codebooks=self.dims.num_codebooks, mimi_config=mimi_config,
+                                         device=audio_decoder_device or device, state_dict=audio_decoder_state_dict)
         self.stop_token_id = 0               # csm.py:355
         self._max_tokens = max_tokens
         self.default_sampling_config = SamplingConfig(top_k=50, top_p=None, min_p=None, temperature=0.9,
@@ -275,4 +286,7 @@ class CSMModel(BaseLMWithDepth):
         return ids, emb
 
     def postprocess(self, token_ids: torch.Tensor, **kwargs) -> torch.Tensor:
-        raise VoxB200Error("CSM's vocoder (MimiDecoder, vox_serve/tokenizer/mimi.py:2993-3018) is not on the CUDA path yet")
+        """[B, interval, 33] frame rows -> [B, 1, interval * 1920] (csm.py:771-785): the text column is dropped, codes
+        are clamped to the Mimi tables and every chunk is decoded on its own (no state between chunks)."""
+        codes = token_ids[:, :, :-1].transpose(1, 2).clamp(0, self.audio_decoder.cfg.bins - 1)
+        return self.audio_decoder.decode(codes)

@@ -74,6 +74,8 @@ class _Staging:
 
 
 class ModelWorker:
+    _serves_depth = False
+
     def __init__(self, model_name: str, max_batch_size: int, max_num_pages: int, page_size: int, top_p: float = None,
                  top_k: int = None, min_p: float = None, temperature: float = None, max_tokens: int = None,
                  repetition_penalty: float = None, repetition_window: int = None, cfg_scale: float = None,
@@ -106,11 +108,17 @@ class ModelWorker:
         import logging
 
         self.logger = logging.getLogger(__name__)
-        if self.model.has_depth_transformer or self.model.needs_watermarking:
-            raise VoxB200Error("this worker serves single-codebook LMs with a built vocoder (Orpheus); the depth-transformer "
-                               "LMs run through depth_engine / model.csm.frame_device until their codecs exist (SURVEY.md §8f)")
+        if self.model.has_depth_transformer and not self._serves_depth:
+            # the reference builds ``CudaGraphWorker(model_name, ...)`` for every model (scheduler/base.py:57-77); the
+            # multi-codebook step lives in a subclass here, selected once the model is known
+            from .depth import DepthModelWorker
+
+            self.__class__ = DepthModelWorker
+        elif self._serves_depth and not self.model.has_depth_transformer:
+            raise VoxB200Error("DepthModelWorker serves depth-transformer LMs only")
+        # watermarking (silentcipher, worker/base.py:683-720) is a third-party post-filter outside the hot path: not applied
         self.needs_watermarking = False
-        self.has_depth_transformer = False
+        self.has_depth_transformer = self._serves_depth
         self.empty_pages: "queue.Queue[int]" = queue.Queue()
         for i in range(max_num_pages):
             self.empty_pages.put(i)
@@ -284,8 +292,7 @@ class ModelWorker:
                     failed.append(i)
                     qo[i + 1], ip[i + 1], last[i], slots[i] = t, npg, 1, slot
                     continue
-                ids[t:t + n] = req.input_tokens[:, 0].numpy() if not req.input_tokens.is_cuda else \
-                    req.input_tokens[:, 0].cpu().numpy()
+                self._stage_prompt_rows(req, out, t, n)
                 pos[t:t + n] = np.arange(n, dtype=np.int32)
                 row_slot[t:t + n] = -1
                 req.kv_token_len = n
@@ -308,7 +315,7 @@ class ModelWorker:
                 if req.kv_last_page_len > self.page_size:
                     req.kv_pages.append(self.empty_pages.get_nowait())
                     req.kv_last_page_len = 1
-                ids[t] = 0
+                self._stage_decode_row(t)
                 pos[t] = req.next_position_id
                 row_slot[t] = slot
                 req.next_position_id += 1
@@ -336,12 +343,26 @@ class ModelWorker:
             rep = self.rep_cache       # slot-resident; rows selected through `slots` (no per-step torch.stack)
         lm_inputs = {"qo_indptr": qo[:B + 1].tolist(), "paged_kv_indptr": ip[:B + 1].tolist(),
                      "paged_kv_indices": indices[:npg].tolist(),
-                     "paged_kv_last_page_len": last[:B].tolist(), "input_ids": self.input_ids[:t].view(t, 1),
-                     "position_ids": st.d("pos", t), "input_features": None, "input_masks": None,
+                     "paged_kv_last_page_len": last[:B].tolist(), "input_ids": self._step_input_ids(t),
+                     "position_ids": st.d("pos", t), "input_features": None, "input_masks": self._step_input_masks(t),
                      "repetition_cache": rep, "is_prefill": is_prefill, "n_rows": t, "n_pages": npg}
         if self.early_launch:
             lm_inputs["_launched"] = self._launch_step(B, t, is_prefill)
         return lm_inputs
+
+    # ---- where a step's token rows come from (overridden by the multi-codebook worker) ----
+    def _stage_prompt_rows(self, req: Request, out, t: int, n: int) -> None:
+        tok = req.input_tokens[:, 0]
+        self.staging.h("ids")[t:t + n] = (tok.cpu() if tok.is_cuda else tok).numpy()
+
+    def _stage_decode_row(self, t: int) -> None:
+        self.staging.h("ids")[t] = 0         # the row's id is the slot's last sampled token (build_input_ids)
+
+    def _step_input_ids(self, t: int) -> torch.Tensor:
+        return self.input_ids[:t].view(t, 1)
+
+    def _step_input_masks(self, t: int) -> Optional[torch.Tensor]:
+        return None
 
     def _fail_request(self, req: Request, reason: str) -> None:
         """Finish a request the worker cannot serve: no audio, an ``error: ...`` finish reason, slot and pages back in
