@@ -27,7 +27,7 @@ def _rel(a, b):
 
 
 def test_mimi_decode_matches_reference_golden(golden_dir):
-    gd = np.load(golden_dir / "mimi_tiny.npz")
+    gd = np.load(f"{golden_dir}/mimi_tiny.npz")
     cfg = omimi.MimiConfig.tiny()
     dec, _ = _decoder(cfg, int(gd["weight_seed"]))
     codes = torch.from_numpy(gd["codes"]).cuda()
