@@ -130,39 +130,10 @@ int vb_paged_attn(void* d_out, const void* d_q, const void* d_kv, int64_t slab_b
 size_t vb_weight_tiles_bytes(int N, int K, int tile_rows);
 int vb_pack_weight_tiles(void* d_dst, const void* d_w, int N, int K, int64_t ldw, int tile_rows, void* stream);
 int vb_gemm_t_tile(int T);
-/* L2 weight prefetcher (no counterpart in the reference, whose projections are cuBLAS calls: orpheus.py:41-47, 68-79).
- *   vb_tag_next_gemm:   the next projection launched by this host thread (vb_gemm_bf16 or a fused variant) publishes
- *                       its progress through its weights into *d_progress: KiB of the step's virtual weight stream
- *                       consumed so far = (virt_offset_bytes + stages issued x CTAs x stage bytes) / 1024;
- *   vb_set_u32:         *d_ptr = value as a kernel of the launch chain (resets the progress word of a step);
- *   vb_tag_next_attn:   the next vb_paged_attn of this host thread publishes into *d_progress_tiles the number of KV
- *                       tiles the step has consumed: layer_ordinal * (tiles of one layer) + tiles issued so far;
- *   vb_weight_prefetch: one warp per CTA walks d_ops in consumption order and prefetches into L2 whatever is less than
- *                       window_bytes ahead of what has been consumed (d_progress[0] KiB of weights + d_progress[1] KV
- *                       tiles); meant for a second stream beside the decode step.  d_ops: int64 [n_ops][6] =
- *                       {weight bytes before the op, attention ops before it, offset, CTAs, bytes per stage, stages
- *                       per CTA}.  A projection (bytes per stage > 0) owns slices at d_arena + offset + c * stages *
- *                       stage bytes; an attention op (bytes per stage == 0) stands for one layer's KV (offset = the
- *                       layer's first slab), resolved through the step's row plan (vb_plan_rows outputs) exactly as
- *                       vb_paged_attn tiles it over attn_grid_ctas CTAs; d_kv NULL skips those ops.  Gives up
- *                       (returns) when the progress words stop moving. */
-/*   vb_tag_next_l2_prefetch: the next vb_reduce_residual_rmsnorm / vb_qkv_rope_append of this host thread issues an L2
- *                       prefetch of [d_ptr, d_ptr + bytes) from all its threads BEFORE its dependency wait: these kernels
- *                       become resident ~5 us before their input exists, which is idle HBM time in a decode step; the
- *                       engine points them at the NEXT projections' weights. */
-int vb_tag_next_l2_prefetch(const void* d_ptr, uint64_t bytes);
 /* shared-memory budget of the projection kernel's operand ring in KiB (0 = keep): ring_kb for every projection (default
  * 104: two CTAs per SM, so a programmatic dependent sits beside its predecessor), gate_up_ring_kb for the gate/up
  * projection (default 200: the long stream gets the whole SM).  Process-wide tuning knobs (env VB_GEMM_SMEM_KB[_GU]). */
 int vb_set_gemm_smem_kb(int ring_kb, int gate_up_ring_kb);
-int vb_tag_next_gemm(uint32_t* d_progress, uint64_t virt_offset_bytes);
-int vb_tag_next_attn(uint32_t* d_progress_tiles, int layer_ordinal);
-int vb_set_u32(uint32_t* d_ptr, uint32_t value, void* stream);
-int vb_weight_prefetch(const void* d_arena, const int64_t* d_ops, int n_ops, const uint32_t* d_progress,
-                       uint64_t window_bytes, int grid_ctas, const void* d_kv, const int32_t* d_row_chunk_start,
-                       const int32_t* d_row_kvlen, const int32_t* d_row_pagebase, const int32_t* d_kv_indices, int n_rows,
-                       int page_size, int chunk_tokens, int kv_row_bytes, int attn_grid_ctas, int flags, void* stream);
-/* (flags bit 0: dry run -- walk and pace, issue no prefetch: a development switch) */
 /* d_x_tiles (optional): X in the XT(vb_gemm_t_tile(T)) layout -- then x_map may be NULL; y_tiled (mode 2 only): write
  * Y in the XT(vb_gemm_t_tile(T)) layout over n_out columns (it is the down projection's activation). */
 int vb_gemm_bf16(void* d_y, const void* d_w_tiles, const void* x_map, const void* d_x_tiles, int T, int N, int K,
@@ -198,37 +169,6 @@ int vb_proj_norm_qkv_rope_append(void* d_q_out, void* d_layer_kv, const void* d_
                                  const void* d_x_tiles, const float* d_ssq, int n_ssq_parts, const void* d_norm_weight, float eps,
                                  const float* d_rope_cs, const int32_t* d_row_page, const int32_t* d_row_slot, int T,
                                  int K, int n_q, int n_kv, int head_dim, int page_size, int split_k, void* stream);
-/* ---- persistent projection chain (T <= 64): up to 4 dependent fused projections in ONE launch --------------------
- * The part of a decoder layer between two attention calls -- O-proj + residual -> RMSNorm + gate/up + SiLU*up ->
- * down-proj + residual -> RMSNorm + QKV(next layer) + RoPE + KV append (orpheus.py:81-151) -- as one kernel of at
- * most one CTA per SM whose weight stream runs ahead across the phase boundaries (the dependencies are grid-wide
- * arrival counters in d_flags, the weights of the next phase are already in shared memory when they resolve).
- * Each phase is one of the fused projections above (same arguments, same arithmetic):
- *   kind 0 = vb_proj_residual, kind 1 = vb_proj_norm_gateup_silu, kind 2 = vb_proj_norm_qkv_rope_append.
- * Every phase needs n_tiles * split_k <= SM count.  d_flags (vb_decode_chain_flags_bytes(max_tiles)) must be ZERO at
- * launch; d_workspace (vb_decode_chain_workspace_bytes(max n_tiles * split_k)) holds the split-K partial tiles. */
-typedef struct vb_chain_phase {
-  int32_t kind;
-  int32_t N, K, tile_rows, split_k;
-  int32_t n_out;             /* kind 1: gate/up outputs (intermediate size); others: 0 */
-  int32_t n_ssq_parts;       /* kinds 1, 2 */
-  float eps;                 /* kinds 1, 2 */
-  const void* w_tiles;       /* vb_pack_weight_tiles(W, N, K, ldw, tile_rows) */
-  const void* x;             /* phase input [T][K] bf16, row-major */
-  int64_t ldx;               /* its leading dimension in elements (>= K, multiple of 8) */
-  void* out;                 /* kind 0: hidden_out [T][N]; kind 1: act [T][n_out]; kind 2: q_out [T][n_q][D] */
-  const void* residual;      /* kind 0 (may alias out, may be NULL) */
-  float* ssq_out;            /* kind 0: [tiles][T] or NULL */
-  const float* ssq_in;       /* kinds 1, 2: [n_ssq_parts][T] */
-  const void* norm_weight;   /* kinds 1, 2 */
-  void* layer_kv;            /* kind 2 */
-} vb_chain_phase;
-size_t vb_decode_chain_workspace_bytes(int max_items);
-size_t vb_decode_chain_flags_bytes(int max_tiles);
-int vb_decode_chain(const vb_chain_phase* phases, int n_phases, int T, const float* d_rope_cs,
-                    const int32_t* d_row_page, const int32_t* d_row_slot, int n_q, int n_kv, int page_size,
-                    void* d_workspace, size_t workspace_bytes, void* d_flags, size_t flags_bytes, int max_tiles,
-                    void* stream);
 
 /* cs[T][2][head_dim] = cos | sin of pos[t] * freq[e]: computed once per step, shared by all layers */
 int vb_rope_table(float* d_cs, const int32_t* d_pos, const float* d_freq, int T, int head_dim, void* stream);

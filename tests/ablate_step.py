@@ -96,24 +96,21 @@ def main():
     }
 
     def unfused():
-        eng.force_unfused = True
         eng.forward(ids, pos, B)
-        eng.force_unfused = False
 
-    def nochain():
-        eng.use_chain = False
+    def fused():
+        eng.force_unfused = False
         eng.forward(ids, pos, B)
-        eng.use_chain = True
+        eng.force_unfused = True
 
     def unfused_rows():
-        eng.force_unfused, eng.tiled_acts = True, False
+        eng.tiled_acts = False
         eng.forward(ids, pos, B)
-        eng.force_unfused, eng.tiled_acts = False, True
+        eng.tiled_acts = True
 
     variants["unfused_rows_forward"] = unfused_rows
     variants["unfused_forward"] = unfused
-    variants["fused_forward"] = nochain
-    variants["chain_forward"] = lambda: eng.forward(ids, pos, B)
+    variants["fused_forward"] = fused
 
     res = {}
     if only:

@@ -19,7 +19,7 @@ def _i32(x):
     return torch.tensor(x, dtype=torch.int32, device="cuda")
 
 
-def _run(dims, page_size, max_pages, prompt_lens, n_steps, seed, max_bs=4, mode="chain"):
+def _run(dims, page_size, max_pages, prompt_lens, n_steps, seed, max_bs=4, mode="unfused"):
     from vox_serve_b200 import ops
     from vox_serve_b200.engine import LlamaDims, LlamaEngine, LlamaWeights
 
@@ -37,8 +37,7 @@ def _run(dims, page_size, max_pages, prompt_lens, n_steps, seed, max_bs=4, mode=
     eng = LlamaEngine(gw, kv, page_size, max_rows=256)
     eng.force_unfused = mode.startswith("unfused")
     eng.tiled_acts = mode != "unfused-rows"
-    eng.use_chain = mode == "chain"
-    assert eng.chain_ok
+    assert eng.fused_ok
     g = torch.Generator().manual_seed(21)
     reqs = [oworker.Req(f"r{i}", torch.randint(10, dims.vocab_size, (n,), generator=g)) for i, n in enumerate(prompt_lens)]
     active = []
@@ -87,8 +86,8 @@ def _run(dims, page_size, max_pages, prompt_lens, n_steps, seed, max_bs=4, mode=
     return stats
 
 
-# persistent chain (2 launches per layer) / one launch per fused projection (5) / prefill-style layers (8)
-@pytest.mark.parametrize("mode", ["chain", "fused", "unfused", "unfused-rows"])
+# the default 8-launch layer (tiled / row-major activations) and the fused projections (5 launches per layer)
+@pytest.mark.parametrize("mode", ["unfused", "unfused-rows", "fused"])
 def test_tiny_orpheus_teacher_forced_greedy(mode):
     dims = oorph.OrpheusDims.tiny()
     dims.max_tokens = 400
@@ -99,7 +98,7 @@ def test_tiny_orpheus_teacher_forced_greedy(mode):
     assert st["id_mismatch"] <= max(2, st["rows"] // 50)
 
 
-@pytest.mark.parametrize("mode", ["chain", "fused"])
+@pytest.mark.parametrize("mode", ["unfused", "fused"])
 def test_medium_orpheus_page128_teacher_forced(mode):
     # head_dim 128, GQA 3, page 128: the Orpheus attention geometry with a prompt crossing a page
     dims = oorph.OrpheusDims.tiny(hidden_size=1536, num_hidden_layers=3, num_attention_heads=12,

@@ -61,7 +61,7 @@ def test_orpheus_3b_true_dims_free_running_greedy_bit_exact():
     worker = ModelWorker("orpheus-test", max_batch_size=n_req, max_num_pages=pages, page_size=page, model=model,
                          max_prefill_tokens=256)
     eng = model.engine_for(worker.kv_cache, page)
-    assert not eng.use_chain and eng.force_unfused, "the default decode mode is what bench.py times"
+    assert eng.force_unfused, "the default decode mode is what bench.py times"
     assert (eng.split_qkv, eng.split_o, eng.split_down) == (4, 4, 8), "production split-K of Orpheus-3B at 32 rows"
     ow = oworker.OracleWorker(weights, dims, osampler.SamplingConfig(**kw), page_size=page, max_num_pages=pages,
                               max_batch_size=n_req, ignore_stop=True)

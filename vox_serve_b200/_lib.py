@@ -13,15 +13,6 @@ c_void_p, c_int, c_int64, c_float, c_size_t, c_uint64 = C.c_void_p, C.c_int, C.c
 P = c_void_p
 
 # name -> (restype, argtypes); mirrors include/vb_api.h one to one
-class ChainPhase(C.Structure):
-    """vb_chain_phase of include/vb_api.h"""
-    _fields_ = [("kind", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("tile_rows", C.c_int32),
-                ("split_k", C.c_int32), ("n_out", C.c_int32), ("n_ssq_parts", C.c_int32), ("eps", C.c_float),
-                ("w_tiles", C.c_void_p), ("x", C.c_void_p), ("ldx", C.c_int64), ("out", C.c_void_p), ("residual", C.c_void_p),
-                ("ssq_out", C.c_void_p), ("ssq_in", C.c_void_p), ("norm_weight", C.c_void_p),
-                ("layer_kv", C.c_void_p)]
-
-
 SIGNATURES = {
     "vb_last_error": (C.c_char_p, []),
     "vb_version": (c_int, []),
@@ -46,13 +37,7 @@ SIGNATURES = {
                               c_float, P, c_size_t, c_int, c_int, c_int, P]),
     "vb_set_trace": (c_int, [P]),
     "vb_gemm_t_tile": (c_int, [c_int]),
-    "vb_tag_next_gemm": (c_int, [P, c_uint64]),
     "vb_set_gemm_smem_kb": (c_int, [c_int, c_int]),
-    "vb_set_u32": (c_int, [P, C.c_uint32, P]),
-    "vb_tag_next_attn": (c_int, [P, c_int]),
-    "vb_tag_next_l2_prefetch": (c_int, [P, c_uint64]),
-    "vb_weight_prefetch": (c_int, [P, P, c_int, P, c_uint64, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int,
-                                   P]),
     "vb_weight_tiles_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vb_pack_weight_tiles": (c_int, [P, P, c_int, c_int, c_int64, c_int, P]),
     "vb_gemm_bf16": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
@@ -60,9 +45,6 @@ SIGNATURES = {
     "vb_proj_norm_gateup_silu": (c_int, [P, P, P, P, P, c_int, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_proj_norm_qkv_rope_append": (c_int, [P, P, P, P, P, P, c_int, P, c_float, P, P, P, c_int, c_int, c_int, c_int,
                                              c_int, c_int, c_int, P]),
-    "vb_decode_chain_workspace_bytes": (c_size_t, [c_int]),
-    "vb_decode_chain_flags_bytes": (c_size_t, [c_int]),
-    "vb_decode_chain": (c_int, [P, c_int, c_int, P, P, P, c_int, c_int, c_int, P, c_size_t, P, c_size_t, c_int, P]),
     "vb_rope_table": (c_int, [P, P, P, c_int, c_int, P]),
     "vb_row_ssq": (c_int, [P, P, c_int, c_int, P]),
     "vb_reduce_residual_rmsnorm": (c_int, [P, P, P, c_int, P, P, c_int, c_int, c_float, c_int, P]),
@@ -140,9 +122,8 @@ def check(rc: int, what: str = ""):
 
 
 # kernels (+ memset nodes) each entry point enqueues; everything not listed launches exactly one
-LAUNCHES = {"vb_set_pdl": 0, "vb_set_trace": 0, "vb_weight_tiles_bytes": 0, "vb_decode_chain_workspace_bytes": 0,
-            "vb_decode_chain_flags_bytes": 0, "vb_tensor_map_kv": 0, "vb_tensor_map_2d_bf16": 0, "vb_device_info": 0, "vb_sample": 1,
-            "vb_update_repetition_cache": 1, "vb_tag_next_gemm": 0, "vb_tag_next_attn": 0, "vb_tag_next_l2_prefetch": 0,
+LAUNCHES = {"vb_set_pdl": 0, "vb_set_trace": 0, "vb_weight_tiles_bytes": 0, "vb_tensor_map_kv": 0,
+            "vb_tensor_map_2d_bf16": 0, "vb_device_info": 0, "vb_sample": 1, "vb_update_repetition_cache": 1,
             "vb_set_gemm_smem_kb": 0}
 launch_counter = [0]
 

@@ -43,7 +43,6 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 cudaError_t trace_set_elementwise(unsigned long long*);
 cudaError_t trace_set_attn(unsigned long long*);
 cudaError_t trace_set_gemm(unsigned long long*);
-cudaError_t trace_set_chain(unsigned long long*);
 cudaError_t trace_set_sampler(unsigned long long*);
 cudaError_t trace_set_snac(unsigned long long*);
 }  // namespace vb
@@ -55,7 +54,6 @@ int vb_set_trace(void* d_buffer) {
   VB_CHECK_CUDA(vb::trace_set_elementwise(p));
   VB_CHECK_CUDA(vb::trace_set_attn(p));
   VB_CHECK_CUDA(vb::trace_set_gemm(p));
-  VB_CHECK_CUDA(vb::trace_set_chain(p));
   VB_CHECK_CUDA(vb::trace_set_sampler(p));
   VB_CHECK_CUDA(vb::trace_set_snac(p));
   return 0;

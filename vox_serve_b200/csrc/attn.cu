@@ -52,10 +52,6 @@ struct AttnParams {
   int n_rows, n_q, n_kv, G, page_size, tok, stages;
   int out_xt_tile;               // 0: out is [row][n_q][D]; else the tiled XT(out_xt_tile) layout of [row][n_q * D]
   float scale_log2;
-  // KV-stream progress for the L2 prefetcher (vb_tag_next_attn): block 0's producer publishes the number of KV tiles
-  // the step has consumed so far = progress_layer * total tiles + tiles issued per CTA * CTAs
-  unsigned int* progress;
-  int progress_layer;
 };
 
 struct TileMeta {   // 32 bytes, one per ring stage
@@ -266,8 +262,6 @@ __global__ void __launch_bounds__(288, MINB) paged_attn_kernel(const AttnParams 
             if (++stage == STAGES) { stage = 0; ph ^= 1; }
           }
           ++issued;
-          if (p.progress && lane == 0 && blockIdx.x == 0)
-            atomicMax(p.progress, static_cast<unsigned>(p.progress_layer * total + min(total, issued * static_cast<int>(gridDim.x))));
         }
       }
     }
@@ -658,16 +652,7 @@ static int launch_attn(const AttnParams& p, int grid, cudaStream_t stream) {
 
 using namespace vb;
 
-static thread_local unsigned int* t_attn_progress = nullptr;
-static thread_local int t_attn_layer = 0;
-
 extern "C" {
-
-int vb_tag_next_attn(uint32_t* d_progress_tiles, int layer_ordinal) {
-  t_attn_progress = d_progress_tiles;
-  t_attn_layer = layer_ordinal;
-  return 0;
-}
 
 int vb_attn_tile_tokens(int page_size, int n_kv) {
   if (page_size < 16 || page_size % 16 != 0 || n_kv < 1 || n_kv > 8) return -1;
@@ -700,12 +685,8 @@ int vb_paged_attn(void* d_out, const void* d_q, const void* d_kv, int64_t slab_b
                ws_grid_ctas);
   VB_CHECK_ARG(workspace_bytes >= vb_paged_attn_workspace_bytes(n_rows, ws_grid_ctas, n_q, n_kv, head_dim),
                "vb_paged_attn: workspace too small for %d rows x %d CTAs", n_rows, ws_grid_ctas);
-  unsigned int* const tag_ptr = t_attn_progress;       // (the tag belongs to THIS launch)
-  t_attn_progress = nullptr;
   if (n_rows <= 0) return 0;
   AttnParams p;
-  p.progress = tag_ptr;
-  p.progress_layer = t_attn_layer;
   p.out = static_cast<__nv_bfloat16*>(d_out);
   p.q = static_cast<const __nv_bfloat16*>(d_q);
   p.row_kvlen = d_row_kvlen;

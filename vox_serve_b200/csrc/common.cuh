@@ -206,39 +206,6 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// L2 prefetch of a linear byte range (fire and forget; size multiple of 16, 16-byte aligned address)
-__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(p)), "r"(bytes)
-               : "memory");
-}
-// Per-thread L2 prefetch of a linear range, one 128-byte line per instruction (CCTL.E.PF2): thread `t` of `n` takes
-// lines t, t + n, ...  Fire and forget; used by the latency-bound kernels of the decode chain BEFORE their dependency
-// wait to pull the next projection's weights into L2 while HBM would otherwise idle (measured: a 100 MB range issued
-// by 37 k threads is in flight within ~10 us; a dedicated polling prefetch kernel beside the chain cost 0.14 us per
-// resident CTA at every kernel boundary instead -- tests/ablate_prefetch.py).
-__device__ __forceinline__ void prefetch_l2_lines(const void* base, unsigned long long bytes, unsigned long long t,
-                                                  unsigned long long n) {
-  const char* b = static_cast<const char*>(base);
-  for (unsigned long long off = t * 128ull; off < bytes; off += n * 128ull)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<uint64_t>(b + off)) : "memory");
-}
-// This CTA's share of a [base, base + bytes) prefetch, issued by `nthreads` cooperating threads (index `t`) in
-// 8 KiB pieces.  Used to pull the NEXT projection's weights into L2 while the current kernel is not using HBM.
-__device__ __forceinline__ void prefetch_l2_slice(const void* base, size_t bytes, int cta, int n_ctas, int t,
-                                                  int nthreads) {
-  if (base == nullptr || bytes == 0) return;
-  constexpr size_t PIECE = 8192;
-  const size_t n_pieces = (bytes + PIECE - 1) / PIECE;
-  const size_t per_cta = (n_pieces + n_ctas - 1) / n_ctas;
-  const size_t p0 = static_cast<size_t>(cta) * per_cta, p1 = min(n_pieces, p0 + per_cta);
-  const char* b = static_cast<const char*>(base);
-  for (size_t i = p0 + t; i < p1; i += nthreads) {
-    const size_t off = i * PIECE;
-    const size_t len = min(PIECE, bytes - off) & ~static_cast<size_t>(15);
-    if (len) prefetch_l2(b + off, static_cast<uint32_t>(len));
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // thread-block cluster helpers (distributed shared memory)
 // ---------------------------------------------------------------------------------------------

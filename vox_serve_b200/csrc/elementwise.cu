@@ -223,8 +223,7 @@ constexpr int RR_MAX_ITER = 4;      // columns per CTA <= RR_THREADS * 4 * RR_MA
 __global__ void __launch_bounds__(RR_THREADS) reduce_residual_rmsnorm_kernel(
     __nv_bfloat16* __restrict__ hidden_out, __nv_bfloat16* __restrict__ normed_out,
     const float* __restrict__ partials, int split_k, const __nv_bfloat16* __restrict__ residual,
-    const __nv_bfloat16* __restrict__ norm_w, int T, int N, float eps, int xt_tile, const void* pf_ptr,
-    unsigned long long pf_bytes) {
+    const __nv_bfloat16* __restrict__ norm_w, int T, int N, float eps, int xt_tile) {
   __shared__ float red[32];
   __shared__ float part_ss[8];        // one slot per CTA of the cluster, written by the peers
   const int parts = gridDim.x, part = blockIdx.x;
@@ -239,10 +238,6 @@ __global__ void __launch_bounds__(RR_THREADS) reduce_residual_rmsnorm_kernel(
     const int n = c0 + (it * RR_THREADS + threadIdx.x) * 4;
     w2[it] = (normed_out && n < c0 + cols) ? __ldg(reinterpret_cast<const uint2*>(norm_w + n)) : make_uint2(0u, 0u);
   }
-  // (the kernel is resident ~5 us before its input exists: that is idle HBM time -- vb_tag_next_l2_prefetch)
-  if (pf_bytes)
-    prefetch_l2_lines(pf_ptr, pf_bytes, (static_cast<unsigned long long>(blockIdx.y) * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x,
-                      static_cast<unsigned long long>(gridDim.x) * gridDim.y * blockDim.x);
   pdl_sync();
   float h[RR_MAX_ITER][4];
   float ss = 0.f;
@@ -315,11 +310,8 @@ __global__ void __launch_bounds__(256) qkv_rope_append_kernel(
     int split_k, const int32_t* __restrict__ pos, const float* __restrict__ freq,
     const int32_t* __restrict__ row_page, const int32_t* __restrict__ row_slot, int T, int n_q, int n_kv, int D,
     int page_size, int rotary_dim, int interleave, int heads_per_cta, const __nv_bfloat16* __restrict__ q_norm_w,
-    const __nv_bfloat16* __restrict__ k_norm_w, float norm_eps, const void* pf_ptr, unsigned long long pf_bytes) {
+    const __nv_bfloat16* __restrict__ k_norm_w, float norm_eps) {
   const int tr = (threadIdx.x == 0 && trace_block0()) ? trace_begin(6, split_k) : -1;
-  if (pf_bytes)
-    prefetch_l2_lines(pf_ptr, pf_bytes, (static_cast<unsigned long long>(blockIdx.y) * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x,
-                      static_cast<unsigned long long>(gridDim.x) * gridDim.y * blockDim.x);
   pdl_sync();
   if (tr >= 0) trace_mark(24);
   extern __shared__ float sm[];  // [2*rotary_dim cos/sin][heads_per_cta * D values]
@@ -450,19 +442,6 @@ __global__ void orpheus_window_codes_kernel(int32_t* __restrict__ c0, int32_t* _
 
 using namespace vb;
 
-// range the next tagged launch of this host thread prefetches into L2 before its dependency wait
-static thread_local const void* t_pf_ptr = nullptr;
-static thread_local unsigned long long t_pf_bytes = 0;
-static void take_l2_prefetch_tag(const void*& ptr, unsigned long long& bytes) {
-  ptr = t_pf_ptr; bytes = t_pf_ptr ? t_pf_bytes : 0ull;
-  t_pf_ptr = nullptr; t_pf_bytes = 0;
-}
-extern "C" int vb_tag_next_l2_prefetch(const void* d_ptr, uint64_t bytes) {
-  t_pf_ptr = d_ptr;
-  t_pf_bytes = bytes;
-  return 0;
-}
-
 extern "C" {
 
 int vb_rmsnorm(void* d_out, const void* d_x, const void* d_weight, int rows, int dim, float eps, int xt_tile,
@@ -525,8 +504,6 @@ int vb_kv_append(void* d_layer_kv, const void* d_k, const void* d_v, const int32
 int vb_reduce_residual_rmsnorm(void* d_hidden_out, void* d_normed_out, const float* d_partials, int split_k,
                                const void* d_residual, const void* d_norm_weight, int T, int N, float eps,
                                int normed_xt_tile, void* stream) {
-  const void* pf_ptr = nullptr; unsigned long long pf_bytes = 0;
-  take_l2_prefetch_tag(pf_ptr, pf_bytes);      // (the tag belongs to THIS launch)
   VB_CHECK_ARG(d_partials && split_k >= 1, "vb_reduce_residual_rmsnorm: bad partials");
   VB_CHECK_ARG(N % 4 == 0, "vb_reduce_residual_rmsnorm: N %d must be a multiple of 4", N);
   VB_CHECK_ARG(!d_normed_out || d_norm_weight, "vb_reduce_residual_rmsnorm: norm output needs a weight");
@@ -543,7 +520,7 @@ int vb_reduce_residual_rmsnorm(void* d_hidden_out, void* d_normed_out, const flo
   VB_LAUNCH_PDL_CLUSTER(reduce_residual_rmsnorm_kernel, dim3(parts, T), RR_THREADS, 0, stream, parts,
                         static_cast<__nv_bfloat16*>(d_hidden_out), static_cast<__nv_bfloat16*>(d_normed_out),
                         d_partials, split_k, static_cast<const __nv_bfloat16*>(d_residual),
-                        static_cast<const __nv_bfloat16*>(d_norm_weight), T, N, eps, normed_xt_tile, pf_ptr, pf_bytes);
+                        static_cast<const __nv_bfloat16*>(d_norm_weight), T, N, eps, normed_xt_tile);
   return 0;
 }
 
@@ -551,8 +528,6 @@ int vb_qkv_rope_append(void* d_q_out, void* d_layer_kv, const float* d_partials,
                        const float* d_freq, const int32_t* d_row_page, const int32_t* d_row_slot, int T, int n_q,
                        int n_kv, int head_dim, int page_size, int rotary_dim, int interleave, const void* d_q_norm,
                        const void* d_k_norm, float norm_eps, void* stream) {
-  const void* pf_ptr = nullptr; unsigned long long pf_bytes = 0;
-  take_l2_prefetch_tag(pf_ptr, pf_bytes);
   VB_CHECK_ARG((d_q_norm == nullptr) == (d_k_norm == nullptr), "vb_qkv_rope_append: q_norm and k_norm come together");
   VB_CHECK_ARG(d_q_out && d_layer_kv && d_partials && d_pos && d_freq && d_row_page && d_row_slot,
                "vb_qkv_rope_append: null pointer");
@@ -572,8 +547,7 @@ int vb_qkv_rope_append(void* d_q_out, void* d_layer_kv, const float* d_partials,
   VB_LAUNCH_PDL(qkv_rope_append_kernel, dim3(parts, T), 256, smem, stream, static_cast<__nv_bfloat16*>(d_q_out),
                 static_cast<__nv_bfloat16*>(d_layer_kv), d_partials, split_k, d_pos, d_freq, d_row_page, d_row_slot, T,
                 n_q, n_kv, head_dim, page_size, rotary_dim, interleave, heads_per_cta,
-                static_cast<const __nv_bfloat16*>(d_q_norm), static_cast<const __nv_bfloat16*>(d_k_norm), norm_eps, pf_ptr,
-                pf_bytes);
+                static_cast<const __nv_bfloat16*>(d_q_norm), static_cast<const __nv_bfloat16*>(d_k_norm), norm_eps);
   return 0;
 }
 

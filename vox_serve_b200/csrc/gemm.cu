@@ -60,10 +60,6 @@ struct GemmParams {
   const int32_t* row_page;
   const int32_t* row_slot;
   int n_q, n_kv, page_size;
-  // weight-stream progress (vb_tag_next_gemm): block (0,0,0)'s producer publishes how far this launch has consumed
-  // its weights, in KiB of the step's virtual weight stream, for the L2 prefetcher (weight_prefetch_kernel)
-  unsigned int* progress;
-  unsigned int progress_base, progress_inc;
   // mode 0: optional bias [N] added in fp32 before the single bf16 rounding (nn.Linear with bias)
   const __nv_bfloat16* bias;
 };
@@ -157,12 +153,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
       // k-blocks follow each other: a single linear bulk copy per stage, sequential DRAM bursts.
       const uint8_t* wsrc = p.w_tiles + (static_cast<size_t>(n_tile) * num_kb + kb0) * a_stage;
       const int npre = min(p.stages, kb1 - kb0);
-      unsigned int* prog = (p.progress && trace_block0()) ? p.progress : nullptr;
       for (int i = 0; i < npre; ++i) {
         mbar_arrive_expect_tx(&full[i], stage_bytes);
         bulk_g2s_hint(smem + i * stage_bytes, wsrc + static_cast<size_t>(i) * a_stage, a_stage, &full[i], pol_w);
       }
-      if (prog) atomicMax(prog, p.progress_base + static_cast<unsigned>(npre) * p.progress_inc);
       pdl_wait();
       pdl_trigger();
       trace_fine(fine, 1, 0);
@@ -188,7 +182,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const GemmPa
         bulk_g2s_hint(a, wsrc + static_cast<size_t>(kb - kb0) * a_stage, a_stage, &full[s], pol_w);
         if (xsrc) bulk_g2s_hint(a + a_stage, xsrc + static_cast<size_t>(kb) * b_stage, b_stage, &full[s], pol_x);
         else tma_load_2d_hint(a + a_stage, &x_map, &full[s], kb * GEMM_BLOCK_K, t_blk * p.t_tile, pol_x);
-        if (prog) atomicMax(prog, p.progress_base + static_cast<unsigned>(kb - kb0 + 1) * p.progress_inc);
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
     }
@@ -585,9 +578,6 @@ __global__ void __launch_bounds__(256) row_ssq_kernel(float* __restrict__ ssq, c
 
 static int g_gemm_smem_budget = -1;
 static int g_gemm_gu_kb = -1;
-// tag of the NEXT projection launch of this host thread (vb_tag_next_gemm); consumed by launch_gemm
-static thread_local unsigned int* t_progress_ptr = nullptr;
-static thread_local unsigned long long t_progress_virt = 0;
 
 static int gemm_smem_budget() {
   if (g_gemm_smem_budget < 0) {
@@ -605,10 +595,6 @@ static int gemm_smem_budget() {
 static int launch_gemm(GemmParams& p, const void* w_tiles, const void* x_map, cudaStream_t stream,
                        const void* x_tiles = nullptr) {
   static const CUtensorMap dummy_map = {};
-  // (the tag belongs to THIS launch whether or not it passes validation)
-  unsigned int* const tag_ptr = t_progress_ptr;
-  const unsigned long long tag_virt = t_progress_virt;
-  t_progress_ptr = nullptr;
   p.w_tiles = static_cast<const uint8_t*>(w_tiles);
   p.x_tiles = static_cast<const uint8_t*>(x_tiles);
   if (!x_map) x_map = &dummy_map;      // never dereferenced by the kernel when x_tiles is set
@@ -646,13 +632,6 @@ static int launch_gemm(GemmParams& p, const void* w_tiles, const void* x_map, cu
   p.stages = stages;
   VB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VB_MAX_DYN_SMEM));
   dim3 grid((p.N + p.tile_rows - 1) / p.tile_rows, p.split_k, (p.T + p.t_tile - 1) / p.t_tile);
-  p.progress = tag_ptr;
-  if (p.progress) {
-    // every CTA of the launch advances through its own weight slice at the same pace: after block 0 has issued s
-    // stages the launch has consumed s stages of all grid.x * grid.y slices
-    p.progress_base = static_cast<unsigned>(tag_virt >> 10);
-    p.progress_inc = static_cast<unsigned>((static_cast<unsigned long long>(grid.x) * grid.y * p.tile_rows * 128) >> 10);
-  }
   // the fused modes reduce split-K through distributed shared memory: cluster = the split_k CTAs of a tile
   const dim3 cluster(1, reducing ? p.split_k : 1, 1);
   VB_CHECK_CUDA(launch_kernel_cluster3(gemm_bf16_kernel, grid, dim3(GEMM_THREADS), smem, stream, true, cluster, p,
@@ -661,116 +640,6 @@ static int launch_gemm(GemmParams& p, const void* w_tiles, const void* x_map, cu
 }
 
 static int fused_t_tile(int T) { return T <= 16 ? 16 : (T <= 32 ? 32 : 64); }
-
-// ---------------------------------------------------------------------------------------------------------------
-// L2 weight prefetcher.  A decode step is a chain of ~230 short kernels, most of them latency-bound; HBM idles
-// between the weight streams (measured: 35 us of streaming in a 77 us layer).  This kernel runs BESIDE the chain
-// (own stream, one warp per SM, no shared memory) and walks the step's weights in consumption order, issuing
-// prefetch.global.L2 for pieces that lie less than `window` bytes ahead of what the projections have consumed
-// (GemmParams::progress, published by every tagged launch).  The projections then find their weights in the
-// 126 MB L2 (measured 9-10 TB/s from L2 against 6.5 TB/s from HBM, tests/micro/l2_prefetch.cu) and HBM keeps
-// streaming while the attention / reduce / norm kernels run.
-// The virtual weight stream: launch after launch; inside a launch stage-major, CTA-minor (all CTAs of a projection
-// advance through their slices together), which is the order the bytes are needed in.
-// ---------------------------------------------------------------------------------------------------------------
-struct PrefetchOp {            // mirrors the int64 [n_ops][6] table built by the host
-  // projection: weights of one launch: slices of CTA c at phys_off + c * stages_per_cta * a_stage (a_stage > 0)
-  // attention (a_stage == 0): the KV of one layer; phys_off = first slab of the layer (layer * pages)
-  long long w_before, attn_before, phys_off, n_ctas, a_stage, stages_per_cta;
-};
-struct PrefetchKV {            // the step's attention plan (vb_plan_rows) + cache geometry; kv == nullptr: no KV ops
-  const uint8_t* kv;           // whole cache [slabs][2][page_size][n_kv][D] bf16
-  const int32_t* row_chunk_start;
-  const int32_t* row_kvlen;
-  const int32_t* row_pagebase;
-  const int32_t* kv_indices;
-  int n_rows, page_size, tok, row_bytes, attn_grid;
-};
-// consumed bytes of the step's virtual stream: progress[0] = KiB of weights, progress[1] = KV tiles
-__device__ __forceinline__ unsigned long long pf_consumed(const unsigned int* progress, unsigned long long tile_bytes) {
-  const volatile unsigned int* p = progress;
-  return (static_cast<unsigned long long>(p[0]) << 10) + static_cast<unsigned long long>(p[1]) * tile_bytes;
-}
-__global__ void __launch_bounds__(32) weight_prefetch_kernel(const uint8_t* __restrict__ arena,
-                                                             const PrefetchOp* __restrict__ ops, int n_ops,
-                                                             const unsigned int* progress, unsigned long long window,
-                                                             const PrefetchKV kvp, int flags) {
-  const bool dry = (flags & 1) != 0;       // (dev) walk and pace, but issue no prefetch
-  const int lane = threadIdx.x;
-  // the KV part of the stream has this step's size: every layer reads total_tiles tiles of 2 * tok rows
-  const unsigned long long tile_bytes = kvp.kv ? 2ull * kvp.tok * kvp.row_bytes : 0ull;
-  const int total_tiles = kvp.kv ? kvp.row_chunk_start[kvp.n_rows] : 0;
-  const int per = kvp.kv ? (total_tiles + kvp.attn_grid - 1) / kvp.attn_grid : 0;
-  const unsigned long long s_kv = static_cast<unsigned long long>(total_tiles) * tile_bytes;
-  unsigned long long g = blockIdx.x, op_first = 0;
-  unsigned long long consumed = 0;
-  for (int op = 0; op < n_ops; ++op) {
-    const PrefetchOp o = ops[op];
-    const bool is_kv = o.a_stage == 0;
-    if (is_kv && !kvp.kv) continue;
-    const unsigned long long piece = is_kv ? tile_bytes : static_cast<unsigned long long>(o.a_stage);
-    const unsigned long long n_ctas = is_kv ? static_cast<unsigned long long>(kvp.attn_grid) : o.n_ctas;
-    const unsigned long long n_p = n_ctas * (is_kv ? static_cast<unsigned long long>(per) : o.stages_per_cta);
-    const unsigned long long v0 = static_cast<unsigned long long>(o.w_before) + static_cast<unsigned long long>(o.attn_before) * s_kv;
-    for (; g < op_first + n_p; g += gridDim.x) {
-      const unsigned long long j = g - op_first;
-      const unsigned long long s = j / n_ctas, c = j - s * n_ctas;
-      // (a KV op's virtual size is total_tiles tiles although it is walked as grid x per pieces: scale the offset)
-      const unsigned long long virt = v0 + (is_kv ? (s * n_ctas < static_cast<unsigned long long>(total_tiles) ? s * n_ctas : total_tiles) * tile_bytes
-                                                  : j * piece);
-      // pace: stay less than `window` ahead of consumption.  Bounded: if nobody publishes progress (a launch outside
-      // its step) the kernel gives up instead of spinning forever.
-      int give_up = 0;
-      if (virt >= consumed + window) {
-        if (lane == 0) {
-          unsigned int spins = 0;
-          while (true) {
-            consumed = pf_consumed(progress, tile_bytes);
-            if (virt < consumed + window) break;
-            if (++spins > (1u << 21)) { give_up = 1; break; }
-            __nanosleep(256);
-          }
-        }
-        consumed = __shfl_sync(0xffffffffu, consumed, 0);
-        give_up = __shfl_sync(0xffffffffu, give_up, 0);
-        if (give_up) return;
-      }
-      if (virt + piece <= consumed) continue;        // the consumer got there first
-      if (dry) continue;
-      if (!is_kv) {
-        const uint8_t* src = arena + o.phys_off + (c * o.stages_per_cta + s) * o.a_stage;
-        for (unsigned int l = lane * 128u; l < static_cast<unsigned int>(o.a_stage); l += 32u * 128u)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<uint64_t>(src + l)) : "memory");
-      } else {
-        // tile Lx of the attention kernel's CTA c (its s-th): row by binary search over the tile prefix, then the page
-        const long long Lx = static_cast<long long>(c) * per + static_cast<long long>(s);
-        if (static_cast<long long>(s) >= per || Lx >= total_tiles) continue;
-        int lo = 0, hi = kvp.n_rows;
-        while (hi - lo > 1) {
-          const int mid = (lo + hi) >> 1;
-          if (kvp.row_chunk_start[mid] <= Lx) lo = mid; else hi = mid;
-        }
-        const int token0 = static_cast<int>(Lx - kvp.row_chunk_start[lo]) * kvp.tok;
-        const int n_tok = min(kvp.tok, kvp.row_kvlen[lo] - token0);
-        if (n_tok <= 0) continue;
-        const int page = kvp.kv_indices[kvp.row_pagebase[lo] + token0 / kvp.page_size];
-        const unsigned long long page_bytes = static_cast<unsigned long long>(kvp.page_size) * kvp.row_bytes;
-        const uint8_t* k0 = kvp.kv + (static_cast<unsigned long long>(o.phys_off + page) * 2ull) * page_bytes +
-                            static_cast<unsigned long long>(token0 % kvp.page_size) * kvp.row_bytes;
-        const unsigned int bytes = static_cast<unsigned int>(n_tok) * kvp.row_bytes;
-        for (unsigned int l = lane * 128u; l < bytes; l += 32u * 128u) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<uint64_t>(k0 + l)) : "memory");
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<uint64_t>(k0 + page_bytes + l)) : "memory");
-        }
-      }
-    }
-    op_first += n_p;
-  }
-}
-__global__ void set_u32_kernel(unsigned int* p, unsigned int v) {
-  pdl_sync();
-  if (threadIdx.x == 0) *p = v;
-}
 
 }  // namespace vb
 
@@ -801,41 +670,6 @@ int vb_set_gemm_smem_kb(int ring_kb, int gate_up_ring_kb) {
                "vb_set_gemm_smem_kb: budgets are 0 (keep) or 48..220 KiB");
   if (ring_kb) g_gemm_smem_budget = ring_kb * 1024;
   if (gate_up_ring_kb) g_gemm_gu_kb = gate_up_ring_kb;
-  return 0;
-}
-
-int vb_tag_next_gemm(uint32_t* d_progress, uint64_t virt_offset_bytes) {
-  VB_CHECK_ARG((virt_offset_bytes & 1023) == 0, "vb_tag_next_gemm: offset must be a multiple of 1 KiB");
-  t_progress_ptr = d_progress;
-  t_progress_virt = virt_offset_bytes;
-  return 0;
-}
-
-int vb_set_u32(uint32_t* d_ptr, uint32_t value, void* stream) {
-  VB_CHECK_ARG(d_ptr, "vb_set_u32: null pointer");
-  VB_LAUNCH_PDL(set_u32_kernel, 1, 32, 0, stream, d_ptr, value);
-  return 0;
-}
-
-int vb_weight_prefetch(const void* d_arena, const int64_t* d_ops, int n_ops, const uint32_t* d_progress,
-                       uint64_t window_bytes, int grid_ctas, const void* d_kv, const int32_t* d_row_chunk_start,
-                       const int32_t* d_row_kvlen, const int32_t* d_row_pagebase, const int32_t* d_kv_indices, int n_rows,
-                       int page_size, int chunk_tokens, int kv_row_bytes, int attn_grid_ctas, int flags, void* stream) {
-  VB_CHECK_ARG(d_arena && d_ops && d_progress, "vb_weight_prefetch: null pointer");
-  VB_CHECK_ARG(n_ops > 0 && grid_ctas > 0 && window_bytes > 0, "vb_weight_prefetch: bad arguments");
-  VB_CHECK_ARG(!d_kv || (d_row_chunk_start && d_row_kvlen && d_row_pagebase && d_kv_indices && n_rows > 0 && page_size > 0 &&
-                         chunk_tokens > 0 && kv_row_bytes > 0 && kv_row_bytes % 128 == 0 && attn_grid_ctas > 0),
-               "vb_weight_prefetch: incomplete KV description");
-  static_assert(sizeof(PrefetchOp) == 6 * sizeof(int64_t), "PrefetchOp mirrors an int64 [n][6] table");
-  PrefetchKV kvp = {};
-  kvp.kv = static_cast<const uint8_t*>(d_kv);
-  kvp.row_chunk_start = d_row_chunk_start; kvp.row_kvlen = d_row_kvlen; kvp.row_pagebase = d_row_pagebase;
-  kvp.kv_indices = d_kv_indices;
-  kvp.n_rows = n_rows; kvp.page_size = page_size; kvp.tok = chunk_tokens; kvp.row_bytes = kv_row_bytes;
-  kvp.attn_grid = attn_grid_ctas;
-  VB_LAUNCH_PLAIN(weight_prefetch_kernel, grid_ctas, 32, 0, stream, static_cast<const uint8_t*>(d_arena),
-                  reinterpret_cast<const PrefetchOp*>(d_ops), n_ops, d_progress,
-                  static_cast<unsigned long long>(window_bytes), kvp, flags);
   return 0;
 }
 

@@ -104,7 +104,6 @@ class DepthFrameEngine:
         self.depth_kv = torch.zeros(dd.num_hidden_layers, max_batch, 2, self.depth_page, dd.num_key_value_heads, dd.head_dim,
                                     dtype=BF16, device=dev)
         self.dp = LlamaEngine(depth_w, self.depth_kv, self.depth_page, max_rows=2 * max_batch)
-        self.dp.l2_prefetch = False          # N - 1 short steps with a different head each: no single weight stream
         self.projector, self.projector_bias, self.depth_heads = projector, projector_bias, depth_w.heads
         H = backbone_w.dims.hidden_size
         # frame[c][b]: ids of the frame being generated / fed back

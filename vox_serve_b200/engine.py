@@ -63,6 +63,7 @@ class LlamaWeights:
     def __init__(self, dims: LlamaDims, device="cuda"):
         self.dims, self.device = dims, torch.device(device)
         self.gu_half = ops.gate_up_tile_half(dims.intermediate_size) if self.device.type == "cuda" else 64
+        self.gu_half = int(os.environ.get("VB_GU_HALF", self.gu_half))          # (dev: tile-height experiments)
         self.embed = self.norm = self.lm_head = None
         self.heads: List[object] = []
         self.arena: Optional[torch.Tensor] = None
@@ -209,67 +210,8 @@ class LlamaEngine:
         self.fsplit_down = ops.proj_split_k((H + 127) // 128, I, self.sms)
         tiles_h = (H + 127) // 128
         gu_tiles = (I + self.gu_half - 1) // self.gu_half
-        items = [(hq + 2 * hkv) * self.fsplit_qkv, tiles_h * self.fsplit_o, gu_tiles, tiles_h * self.fsplit_down]
-        # persistent chain (one launch for O -> gate/up -> down -> next QKV): every phase must fit one CTA per SM
-        self.chain_ok = self.fused_ok and max(items) <= self.sms
-        self.chain_ws = ops.ChainWorkspace(d.num_hidden_layers, max(hq + 2 * hkv, tiles_h, gu_tiles), max(items), dev) \
-            if self.chain_ok else None
         self.ssq = torch.zeros(max(1, (H + 127) // 128) * self.FUSED_MAX_ROWS, dtype=torch.float32, device=dev)
         self.rope_cs = torch.zeros(self.FUSED_MAX_ROWS, 2, D, dtype=torch.float32, device=dev)
-        self._init_prefetch()
-
-    # ---- L2 weight prefetcher (decode-sized steps, default layer mode) ----------------------------------
-    # VB_L2_PREFETCH=0 disables it; VB_L2_WINDOW_MB = how far ahead of the projections' consumption it may run
-    l2_prefetch = os.environ.get("VB_L2_PREFETCH", "0") != "0"      # (off until it wins: see tests/ablate_prefetch.py)
-    l2_prefetch_kv = os.environ.get("VB_L2_PREFETCH_KV", "1") != "0"      # also the step's KV (attention rows of the table)
-    l2_window_mb = int(os.environ.get("VB_L2_WINDOW_MB", "64"))
-    l2_prefetch_ctas = int(os.environ.get("VB_L2_PREFETCH_CTAS", "0"))      # 0 = one per SM
-    l2_prefetch_flags = int(os.environ.get("VB_L2_PREFETCH_FLAGS", "0"))    # bit 0: dry run (dev)
-    l2_prefetch_kernel = os.environ.get("VB_L2_PREFETCH_KERNEL", "1") != "0"   # 0: publish progress only (dev)
-
-    def _init_prefetch(self) -> None:
-        """Consumption-order table of the decode step's weight stream for ops.weight_prefetch: one row per projection
-        launch {virtual offset, offset in the arena, CTAs, bytes per stage, stages per CTA}."""
-        w, d = self.w, self.dims
-        self.pf_table = self.pf_virt = None
-        if w.arena is None or self.device.type != "cuda":
-            return
-        base = w.arena.data_ptr()
-        rows, virt_of, virt, n_attn = [], {}, 0, 0
-        plan = [("qkv", self.split_qkv), ("attn", 0), ("o", self.split_o), ("gu", 1), ("down", self.split_down)]
-        launches = [(i, k, L.get(k), s) for i, L in enumerate(w.layers) for k, s in plan] + [(-1, "lm_head", w.lm_head, 1)]
-        for i, k, pw, split in launches:
-            if k == "attn":                 # one layer's KV, sized per step by the prefetcher from the row plan
-                rows.append([virt, n_attn, i * self.pages_per_layer, 0, 0, 0])
-                n_attn += 1
-                continue
-            num_kb = (pw.K + 63) // 64
-            if num_kb % split != 0 or pw.data.data_ptr() < base:
-                return                      # uneven split-K ranges: no simple slice arithmetic -> no prefetcher
-            n_ctas = (pw.N + pw.tile_rows - 1) // pw.tile_rows * split
-            a_stage, stages = pw.tile_rows * 128, num_kb // split
-            rows.append([virt, n_attn, pw.data.data_ptr() - base, n_ctas, a_stage, stages])
-            virt_of[(i, k)] = virt
-            virt += n_ctas * a_stage * stages
-        self.pf_table = torch.tensor(rows, dtype=torch.int64, device=self.device)
-        self.pf_virt = virt_of
-        self.pf_progress = torch.zeros(4, dtype=torch.int32, device=self.device)
-        self.pf_stream = torch.cuda.Stream(device=self.device)
-
-    # In-kernel L2 prefetch (vb_tag_next_l2_prefetch): the reduce / norm and RoPE kernels of a decode-sized step are
-    # resident several microseconds before their inputs exist; they spend that time asking L2 for the weights the NEXT
-    # projections will stream.  pf_inline_gu_mb: how much of gate/up the O-projection's reduce kernel requests;
-    # the down-projection's reduce kernel requests the next layer's QKV + O weights (contiguous in the arena);
-    # pf_inline_down_mb: how much of down the RoPE kernel requests (HBM idles during a short-context attention).
-    pf_inline = os.environ.get("VB_L2_INLINE_PREFETCH", "0") != "0"
-    pf_inline_gu_mb = int(os.environ.get("VB_L2_INLINE_GU_MB", "64"))
-    pf_inline_down_mb = int(os.environ.get("VB_L2_INLINE_DOWN_MB", "0"))
-
-    def _tag(self, layer: int, key: str) -> None:
-        if self._pf_live:
-            ops.tag_next_gemm(self.pf_progress, self.pf_virt[(layer, key)])
-
-    _pf_live = False
 
     FUSED_MAX_ROWS = 64
 
@@ -296,22 +238,6 @@ class LlamaEngine:
         if R > self.max_rows:
             raise VoxB200Error(f"{R} rows exceed the engine's max_rows {self.max_rows}")
         hidden, normed = self.hidden[:R], self.normed[:R]
-        # decode-sized steps in the default layer mode run with the L2 weight prefetcher beside them (own stream):
-        # reset the progress word in the launch chain, fork, and join after lm_head
-        self._pf_live = (self.l2_prefetch and self.pf_table is not None and R <= self.FUSED_MAX_ROWS and self.tiled_acts
-                         and (self.force_unfused or not self.fused_ok) and head is None)
-        if self._pf_live:
-            main = torch.cuda.current_stream()
-            ops.set_u32(self.pf_progress[0:1], 0)
-            ops.set_u32(self.pf_progress[1:2], 0)
-            self.pf_stream.wait_stream(main)
-            with torch.cuda.stream(self.pf_stream):
-                kv = self.kv_cache if self.l2_prefetch_kv else None
-                if self.l2_prefetch_kernel:
-                    ops.weight_prefetch(w.arena, self.pf_table, self.pf_progress, self.l2_window_mb << 20,
-                                        self.l2_prefetch_ctas or self.sms, kv_cache=kv, plan=plan, n_rows=R,
-                                        page_size=self.page_size, chunk_tokens=self.chunk,
-                                        attn_grid_ctas=self.attn_grid, flags=self.l2_prefetch_flags)
         if input_ids is not None:
             ops.embedding(w.embed, input_ids, out=hidden)
         x_final = normed
@@ -335,25 +261,20 @@ class LlamaEngine:
             hidden_rows = normed
         if n_out > self.max_out_rows:
             raise VoxB200Error(f"logits requested for {n_out} rows; pass last_rows (max {self.max_out_rows})")
-        self._tag(-1, "lm_head")
         logits = ops.gemm(x, w.lm_head if head is None else head, mode=0, out=self.logits[:n_out])
-        if self._pf_live:
-            torch.cuda.current_stream().wait_stream(self.pf_stream)
-            self._pf_live = False
         return (logits, hidden_rows) if want_hidden else logits
 
-    # How decode-sized steps (<= FUSED_MAX_ROWS rows) run their layers.  Measured on B200 (tests/ablate_step.py,
-    # Orpheus-3B, 32 rows, kv 728): separate kernels 2.72 ms, fused projections 2.96 ms, persistent chain 3.42 ms per
-    # forward -- the fused variants still pay more in their serial epilogue / dependency chains than they save in
-    # launches (profiles/r01_chain_trace.txt), so the 8-launch layer stays the default until they do not.
+    # How decode-sized steps (<= FUSED_MAX_ROWS rows) run their layers.  Measured on B200 (Orpheus-3B, 32 rows): separate
+    # kernels 2.61 ms per forward, the norm-/residual-fused projections 2.95 ms (VB_DECODE_MODE=fused; value 130 vs 142.7
+    # audio-s/s, batch-1 TTFA 68 vs 62 ms): their cluster-reduced epilogues cost more than the launches they save
+    # (profiles/r02_decode_modes.txt).  A third variant -- one persistent kernel per layer -- measured 3.2 ms and was
+    # removed in round 2.  The fused projections stay as parity-tested C-ABI operators.
     force_unfused = os.environ.get("VB_DECODE_MODE", "unfused") == "unfused"
-    use_chain = os.environ.get("VB_DECODE_MODE", "unfused") == "chain"
 
     def _layers_fused(self, position_ids: torch.Tensor, R: int, plan: ops.RowPlan) -> None:
         """hidden is updated in place, the RMSNorm statistics travel as per-tile sums of squares written by the
-        residual projections (ssq[parts][R]).  Per layer: paged attention + ONE persistent chain launch
-        (O + residual -> norm + gate/up + SiLU -> down + residual -> norm + next layer's QKV + RoPE + append);
-        without the chain, one launch per fused projection (5 per layer)."""
+        residual projections (ssq[parts][R]).  Per layer: norm + QKV + RoPE + append, paged attention, O + residual,
+        norm + gate/up + SiLU, down + residual: one launch per fused projection (5 per layer)."""
         d, w = self.dims, self.w
         hq, hkv, D, H, I = d.num_attention_heads, d.num_key_value_heads, d.head_dim, d.hidden_size, d.intermediate_size
         hidden, q, attn, act = self.hidden[:R], self.q[:R], self.attn[:R], self.act[:R]
@@ -361,40 +282,25 @@ class LlamaEngine:
         ssq = self.ssq[: tiles_h * R].view(tiles_h, R)
         cs = ops.rope_table(position_ids[:R], self.freq, D, out=self.rope_cs[:R])
         ops.row_ssq(hidden, out=ssq[0])
-        chain = self.chain_ok and self.use_chain
-        tiled = self.tiled_acts and not chain
+        tiled = self.tiled_acts
         hidden_t = self.hidden_t.view_rows(R) if tiled else None
         attn_x_out = self.attn_t.view_rows(R) if tiled else attn          # what attention writes
         attn_x = attn_x_out if tiled else attn.view(R, hq * D)           # ... as the O projection reads it
         act_x = self.act_t.view_rows(R) if tiled else act
-        if chain:
-            self.chain_ws.zero()
-        n_layers = len(w.layers)
         eps = d.rms_norm_eps
         for i, L in enumerate(w.layers):
-            if i == 0 or not chain:
-                # (layer 0 reads the embedding rows through the tensor map; later layers the tiled copy)
-                ops.proj_norm_qkv_rope_append(hidden if (i == 0 or not tiled) else hidden_t, ssq, 1 if i == 0 else tiles_h,
-                                              L["ln1"], eps, L["qkv"], self.kv_cache[i], cs, plan, hq, hkv, D,
-                                              self.fsplit_qkv, q_out=q)
+            # (layer 0 reads the embedding rows through the tensor map; later layers the tiled copy)
+            ops.proj_norm_qkv_rope_append(hidden if (i == 0 or not tiled) else hidden_t, ssq, 1 if i == 0 else tiles_h,
+                                          L["ln1"], eps, L["qkv"], self.kv_cache[i], cs, plan, hq, hkv, D,
+                                          self.fsplit_qkv, q_out=q)
             ops.paged_attn(q, self.kv_map, i * self.pages_per_layer, plan, R, hkv, self.page_size, self.chunk,
-                           self.attn_ws, out=attn if chain else attn_x_out, grid_ctas=self.attn_grid)
-            if chain:
-                phases = [ops.chain_phase_residual(attn.view(R, hq * D), L["o"], hidden, hidden, ssq, self.fsplit_o),
-                          ops.chain_phase_gateup(hidden, ssq, tiles_h, L["ln2"], eps, L["gu"], I, act),
-                          ops.chain_phase_residual(act, L["down"], hidden, hidden, ssq, self.fsplit_down)]
-                if i + 1 < n_layers:
-                    N = w.layers[i + 1]
-                    phases.append(ops.chain_phase_qkv(hidden, ssq, tiles_h, N["ln1"], eps, N["qkv"], self.kv_cache[i + 1],
-                                                      q, self.fsplit_qkv))
-                ops.decode_chain(phases, R, cs, plan, hq, hkv, self.page_size, self.chain_ws, i)
-            else:
-                ops.proj_residual(attn_x, L["o"], hidden, self.fsplit_o, hidden_out=hidden, ssq_out=ssq,
-                                  hidden_tiles_out=hidden_t)
-                ops.proj_norm_gateup_silu(hidden_t if tiled else hidden, ssq, tiles_h, L["ln2"], eps, L["gu"], self.gu_half,
-                                          I, out=act_x)
-                ops.proj_residual(act_x, L["down"], hidden, self.fsplit_down, hidden_out=hidden, ssq_out=ssq,
-                                  hidden_tiles_out=hidden_t)
+                           self.attn_ws, out=attn_x_out, grid_ctas=self.attn_grid)
+            ops.proj_residual(attn_x, L["o"], hidden, self.fsplit_o, hidden_out=hidden, ssq_out=ssq,
+                              hidden_tiles_out=hidden_t)
+            ops.proj_norm_gateup_silu(hidden_t if tiled else hidden, ssq, tiles_h, L["ln2"], eps, L["gu"], self.gu_half,
+                                      I, out=act_x)
+            ops.proj_residual(act_x, L["down"], hidden, self.fsplit_down, hidden_out=hidden, ssq_out=ssq,
+                              hidden_tiles_out=hidden_t)
 
     def _layers_unfused(self, position_ids: torch.Tensor, R: int, plan: ops.RowPlan):
         """8 launches per layer.  Decode-sized steps (R <= FUSED_MAX_ROWS) pass activations between kernels in the
@@ -411,35 +317,18 @@ class LlamaEngine:
         s_qkv, s_o, s_dn = self._split(self.split_qkv, R), self._split(self.split_o, R), self._split(self.split_down, R)
         q = self.q[:R]
         n_layers = len(w.layers)
-        inline = self.pf_inline and tiled and w.arena is not None
         for i, L in enumerate(w.layers):
-            self._tag(i, "qkv")
             p = ops.gemm(normed, L["qkv"], mode=1, split_k=s_qkv, out=self._partials(s_qkv, R, self.qkv_w), tile_rows=D)
-            if inline and self.pf_inline_down_mb:
-                ops.tag_next_l2_prefetch(L["down"].data, self.pf_inline_down_mb << 20)
             ops.qkv_rope_append(p, self.kv_cache[i], position_ids, self.freq, plan, hq, hkv, D, q_out=q,
                                 q_norm=L.get("qn"), k_norm=L.get("kn"), norm_eps=d.rms_norm_eps)
-            if self._pf_live and self.l2_prefetch_kv:
-                ops.tag_next_attn(self.pf_progress[1:2], i)
             ops.paged_attn(q, self.kv_map, i * self.pages_per_layer, plan, R, hkv, self.page_size, self.chunk,
                            self.attn_ws, out=attn_o, grid_ctas=self.attn_grid)
-            self._tag(i, "o")
             p = ops.gemm(attn_o if attn_tiled else attn_o.view(R, hq * D), L["o"], mode=1, split_k=s_o,
                          out=self._partials(s_o, R, H))
-            if inline and self.pf_inline_gu_mb:
-                ops.tag_next_l2_prefetch(L["gu"].data, self.pf_inline_gu_mb << 20)
             ops.reduce_residual_rmsnorm(p, hidden, L["ln2"], d.rms_norm_eps, hidden_out=hidden, normed_out=normed)
-            self._tag(i, "gu")
             ops.gemm(normed, L["gu"], mode=2, out=act, tile_rows=2 * self.gu_half, n_out=I)
-            self._tag(i, "down")
             p = ops.gemm(act, L["down"], mode=1, split_k=s_dn, out=self._partials(s_dn, R, H))
             nxt = w.layers[i + 1]["ln1"] if i + 1 < n_layers else w.norm
-            if inline:
-                if i + 1 < n_layers:       # qkv and o of the next layer follow each other in the arena
-                    N = w.layers[i + 1]
-                    ops.tag_next_l2_prefetch(N["qkv"].data, N["qkv"].data.numel() + N["o"].data.numel())
-                else:
-                    ops.tag_next_l2_prefetch(w.lm_head.data, 64 << 20)
             ops.reduce_residual_rmsnorm(p, hidden, nxt, d.rms_norm_eps, hidden_out=hidden, normed_out=normed)
         return normed
 

@@ -351,57 +351,6 @@ def pack_weight(w: torch.Tensor, tile_rows: int = 128, out: Optional[torch.Tenso
     return PackedWeight(dst, N, K, tile_rows)
 
 
-def tag_next_gemm(progress: Optional[torch.Tensor], virt_offset: int = 0) -> None:
-    """The next projection launched from this thread publishes its weight-stream progress into ``progress`` (uint32
-    scalar viewed as int32, device); None clears a pending tag."""
-    call("vb_tag_next_gemm", _p(progress), int(virt_offset))
-
-
-def set_u32(t: torch.Tensor, value: int) -> None:
-    call("vb_set_u32", t.data_ptr(), int(value), _stream())
-
-
-def tag_next_l2_prefetch(t: Optional[torch.Tensor], nbytes: Optional[int] = None, offset: int = 0) -> None:
-    """The next reduce_residual_rmsnorm / qkv_rope_append launched from this thread prefetches ``nbytes`` of ``t`` (uint8
-    view semantics: bytes from ``offset``) into L2 before its dependency wait (vb_tag_next_l2_prefetch); None clears."""
-    if t is None:
-        call("vb_tag_next_l2_prefetch", None, 0)
-        return
-    total = t.numel() * t.element_size()
-    n = total - offset if nbytes is None else min(int(nbytes), total - offset)
-    call("vb_tag_next_l2_prefetch", t.data_ptr() + int(offset), max(0, n))
-
-
-def tag_next_attn(progress_tiles: Optional[torch.Tensor], layer_ordinal: int = 0) -> None:
-    """The next paged_attn launched from this thread publishes the KV tiles the step has consumed (vb_tag_next_attn)."""
-    call("vb_tag_next_attn", _p(progress_tiles), int(layer_ordinal))
-
-
-def weight_prefetch(arena: torch.Tensor, op_table: torch.Tensor, progress: torch.Tensor, window_bytes: int,
-                    grid_ctas: Optional[int] = None, kv_cache: Optional[torch.Tensor] = None,
-                    plan: Optional["RowPlan"] = None, n_rows: int = 0, page_size: int = 0, chunk_tokens: int = 0,
-                    attn_grid_ctas: int = 0, flags: int = 0) -> None:
-    """Launch the L2 prefetcher (vb_weight_prefetch) on the CURRENT stream: meant for a side stream that runs beside
-    the decode step.  op_table: int64 [n_ops, 6] on the device; progress: int32 [>= 2] = {KiB of weights, KV tiles}.
-    With ``kv_cache`` + ``plan`` the table's attention rows prefetch the step's KV as well."""
-    _need_cuda(arena, op_table, progress, kv_cache)
-    assert op_table.dtype == torch.int64 and op_table.dim() == 2 and op_table.shape[1] == 6 and op_table.is_contiguous()
-    grid = device_info()[0] if grid_ctas is None else int(grid_ctas)
-    if kv_cache is not None:
-        assert plan is not None and plan.kv_indices is not None and kv_cache.is_contiguous()
-        row_bytes = kv_cache.shape[-2] * kv_cache.shape[-1] * kv_cache.element_size()
-        call("vb_weight_prefetch", arena.data_ptr(), op_table.data_ptr(), op_table.shape[0], progress.data_ptr(),
-             int(window_bytes), grid, kv_cache.data_ptr(), plan.row_chunk_start.data_ptr(), plan.row_kvlen.data_ptr(),
-             plan.row_pagebase.data_ptr(), plan.kv_indices.data_ptr(), int(n_rows), int(page_size), int(chunk_tokens),
-             int(row_bytes), int(attn_grid_ctas), int(flags), _stream())
-    else:
-        call("vb_weight_prefetch", arena.data_ptr(), op_table.data_ptr(), op_table.shape[0], progress.data_ptr(),
-             int(window_bytes), grid, None, None, None, None, None, 0, 0, 0, 0, 0, int(flags), _stream())
-
-
-_pack_cache: Dict[Tuple, Tuple[PackedWeight, torch.Tensor]] = {}
-
-
 def _packed(w, tile_rows: int) -> PackedWeight:
     """PackedWeight as is; a plain [N, K] tensor is packed on first use (convenience for tests / one-off calls --
     the engine packs at load time and drops the row-major copy)."""
@@ -554,68 +503,6 @@ def proj_norm_qkv_rope_append(hidden, ssq: torch.Tensor, n_parts: int, norm_w: t
          ssq.data_ptr(), n_parts, norm_w.data_ptr(), float(eps), rope_cs.data_ptr(), plan.row_page.data_ptr(),
          plan.row_slot.data_ptr(), T, K, n_q, n_kv, head_dim, page_size, split_k, _stream())
     return q_out
-
-
-class ChainWorkspace:
-    """Scratch of the persistent projection chains of one step: split-K partial tiles (shared by all launches) and
-    one block of arrival counters per launch; `zero()` (one memset) must run before the step's first chain."""
-
-    def __init__(self, n_launches: int, max_tiles: int, max_items: int, device):
-        lib = _lib.load()
-        self.max_tiles, self.max_items, self.n_launches = int(max_tiles), int(max_items), int(n_launches)
-        self.ws = torch.empty(lib.vb_decode_chain_workspace_bytes(self.max_items), dtype=torch.uint8, device=device)
-        self.flag_bytes = (lib.vb_decode_chain_flags_bytes(self.max_tiles) + 255) // 256 * 256
-        self.flags = torch.zeros(self.n_launches * self.flag_bytes, dtype=torch.uint8, device=device)
-
-    def zero(self):
-        self.flags.zero_()
-
-    def flags_ptr(self, launch: int) -> int:
-        assert 0 <= launch < self.n_launches
-        return self.flags.data_ptr() + launch * self.flag_bytes
-
-
-def chain_phase_residual(x: torch.Tensor, w: "PackedWeight", residual: Optional[torch.Tensor], hidden_out: torch.Tensor,
-                         ssq_out: Optional[torch.Tensor], split_k: int) -> "_lib.ChainPhase":
-    ph = _lib.ChainPhase()
-    ph.kind, ph.N, ph.K, ph.tile_rows, ph.split_k = 0, w.N, w.K, w.tile_rows, split_k
-    ph.w_tiles, ph.x, ph.ldx = w.data.data_ptr(), x.data_ptr(), x.stride(0)
-    ph.out, ph.residual, ph.ssq_out = hidden_out.data_ptr(), _p(residual), _p(ssq_out)
-    return ph
-
-
-def chain_phase_gateup(hidden: torch.Tensor, ssq: torch.Tensor, n_parts: int, norm_w: torch.Tensor, eps: float,
-                       w: "PackedWeight", n_out: int, act_out: torch.Tensor) -> "_lib.ChainPhase":
-    ph = _lib.ChainPhase()
-    ph.kind, ph.N, ph.K, ph.tile_rows, ph.split_k, ph.n_out = 1, w.N, w.K, w.tile_rows, 1, n_out
-    ph.n_ssq_parts, ph.eps = n_parts, float(eps)
-    ph.w_tiles, ph.x, ph.ldx = w.data.data_ptr(), hidden.data_ptr(), hidden.stride(0)
-    ph.out, ph.ssq_in, ph.norm_weight = act_out.data_ptr(), ssq.data_ptr(), norm_w.data_ptr()
-    return ph
-
-
-def chain_phase_qkv(hidden: torch.Tensor, ssq: torch.Tensor, n_parts: int, norm_w: torch.Tensor, eps: float,
-                    w: "PackedWeight", layer_kv: torch.Tensor, q_out: torch.Tensor, split_k: int) -> "_lib.ChainPhase":
-    ph = _lib.ChainPhase()
-    ph.kind, ph.N, ph.K, ph.tile_rows, ph.split_k = 2, w.N, w.K, w.tile_rows, split_k
-    ph.n_ssq_parts, ph.eps = n_parts, float(eps)
-    ph.w_tiles, ph.x, ph.ldx = w.data.data_ptr(), hidden.data_ptr(), hidden.stride(0)
-    ph.out, ph.ssq_in, ph.norm_weight, ph.layer_kv = q_out.data_ptr(), ssq.data_ptr(), norm_w.data_ptr(), layer_kv.data_ptr()
-    return ph
-
-
-def decode_chain(phases, T: int, rope_cs: Optional[torch.Tensor], plan: Optional["RowPlan"], n_q: int, n_kv: int,
-                 page_size: int, cws: ChainWorkspace, launch: int) -> None:
-    """One persistent launch running `phases` (1..4 _lib.ChainPhase, each depending on the one before)."""
-    arr = (_lib.ChainPhase * len(phases))(*phases)
-    call("vb_decode_chain", C_addr(arr), len(phases), T, _p(rope_cs), _p(plan.row_page) if plan is not None else None,
-         _p(plan.row_slot) if plan is not None else None, n_q, n_kv, page_size, cws.ws.data_ptr(), cws.ws.numel(),
-         cws.flags_ptr(launch), cws.flag_bytes, cws.max_tiles, _stream())
-
-
-def C_addr(obj) -> int:
-    import ctypes
-    return ctypes.addressof(obj)
 
 
 def rope_table(pos: torch.Tensor, freq: torch.Tensor, head_dim: int, out: Optional[torch.Tensor] = None):
