@@ -351,6 +351,9 @@ def pack_weight(w: torch.Tensor, tile_rows: int = 128, out: Optional[torch.Tenso
     return PackedWeight(dst, N, K, tile_rows)
 
 
+_pack_cache: Dict[Tuple, Tuple[PackedWeight, torch.Tensor]] = {}
+
+
 def _packed(w, tile_rows: int) -> PackedWeight:
     """PackedWeight as is; a plain [N, K] tensor is packed on first use (convenience for tests / one-off calls --
     the engine packs at load time and drops the row-major copy)."""
