@@ -783,51 +783,3 @@ def test_paged_attention_is_invariant_to_physical_page_placement(ops):
         assert bool(torch.isfinite(out.float()).all())
         outs.append(out.cpu())
     assert torch.equal(outs[0], outs[1])
-
-
-# --------------------------------------------------------------------------------------------
-# L2 weight prefetcher plumbing (vb_tag_next_gemm / vb_weight_prefetch)
-# --------------------------------------------------------------------------------------------
-def test_gemm_progress_tag_and_weight_prefetch(ops):
-    """A tagged projection publishes (virtual offset + everything it streamed) in KiB; an untagged one publishes
-    nothing; the prefetcher walks a two-launch table to the end when the progress word allows it, skips what is already
-    consumed, and gives up (instead of hanging) when nobody publishes progress."""
-    import time
-
-    T, N, K, split = 32, 1024, 1536, 2
-    x = torch.randn(T, K, generator=g(1)).to(BF).cuda()
-    w = (torch.randn(N, K, generator=g(2)) * 0.05).to(BF).cuda()
-    arena = torch.empty(2 * ops.weight_tiles_bytes(N, K, 128) + 1024, dtype=torch.uint8, device="cuda")
-    base = (-arena.data_ptr()) % 1024
-    nb = ops.weight_tiles_bytes(N, K, 128)
-    pw0 = ops.pack_weight(w, 128, out=arena[base:base + nb])
-    pw1 = ops.pack_weight(w, 128, out=arena[base + nb:base + 2 * nb])
-    ref = ops.gemm(x, w, mode=1, split_k=split).sum(0)
-    prog = torch.zeros(4, dtype=torch.int32, device="cuda")
-    virt = 7 << 20
-    ops.tag_next_gemm(prog, virt)
-    got = ops.gemm(x, pw0, mode=1, split_k=split).sum(0)
-    ops.gemm(x, pw1, mode=1, split_k=split)                     # untagged: must not touch the word
-    torch.cuda.synchronize()
-    assert torch.equal(got, ref)
-    assert int(prog[0]) == (virt + nb) // 1024, (int(prog[0]), (virt + nb) // 1024)
-    # ---- prefetcher over [launch 0 | launch 1] ----
-    n_ctas, stages = (N // 128) * split, (K // 64) // split
-    table = torch.tensor([[0, 0, base, n_ctas, 128 * 128, stages], [nb, 0, base + nb, n_ctas, 128 * 128, stages]],
-                         dtype=torch.int64, device="cuda")
-    prog.zero_()
-    prog[0] = (2 * nb) // 1024                                  # everything consumed already: nothing to wait for
-    torch.cuda.synchronize()
-    t0 = time.time()
-    ops.weight_prefetch(arena, table, prog, 1 << 20, grid_ctas=8)
-    torch.cuda.synchronize()
-    assert time.time() - t0 < 0.5
-    prog.zero_()                                                # nothing consumed, 64 KiB window: stalls, then gives up
-    torch.cuda.synchronize()
-    t0 = time.time()
-    ops.weight_prefetch(arena, table, prog, 64 << 10, grid_ctas=2)
-    torch.cuda.synchronize()
-    dt = time.time() - t0
-    assert 0.2 < dt < 20.0, dt
-    # the arena is untouched by any of this
-    assert torch.equal(ops.gemm(x, pw1, mode=1, split_k=split).sum(0), ref)
