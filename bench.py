@@ -52,6 +52,18 @@ def steady_state_kv_lens():
 WORKLOAD = "Orpheus-3B streaming TTS batch=32 on 1xB200 (SNAC codec path)"
 
 
+def workload_config(world: int) -> dict:
+    """The `config` object of the JSON line: ONE definition for both arms (`--impl b200` and `--impl reference`)."""
+    kv = steady_state_kv_lens()
+    return {"workload": WORKLOAD, "batch_per_gpu": BATCH, "prompt_tokens": PROMPT_ROWS,
+            "state": "steady-state continuous batch: request groups staggered 84 tokens apart "
+                     f"(kv {min(kv)}..{max(kv)}, mean {sum(kv) / BATCH:.1f}, when the timed region starts)",
+            "sampling": "top_p 0.8 T 0.6 repetition_penalty 1.3 (orpheus.py:260-268), stop id masked",
+            "page_size": 128, "parallelism": f"dp{world} replicas",
+            "weights": "seeded N(0,0.02) bf16 at Orpheus-3B shapes; SNAC 24 kHz shapes, seeded",
+            "l2": "inputs larger than L2: 6.6 GB of weights stream from HBM every step (126 MB L2)"}
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -111,7 +123,7 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------------------
 # CPU oracle leg (cpu_baseline of the main arm; the whole of --impl reference)
 # --------------------------------------------------------------------------------------------------------------
-def cpu_oracle_sample(n_lm_steps: int = 2, kv_len: int = None, threads=None):
+def cpu_oracle_sample(n_lm_steps: int = 2, kv_len: int = None, threads=None, warmup: int = 1):
     """Times the oracle port (oracle/: the reference's arithmetic on torch CPU) on a bounded sample of the same
     workload: `n_lm_steps` batch-32 decode steps of Orpheus-3B at kv_len ~ the GPU run's starting length, plus
     one SNAC decode of 32 windows; audio-sec/sec from the steady-state mix (1 SNAC per 7 LM steps)."""
@@ -148,7 +160,8 @@ def cpu_oracle_sample(n_lm_steps: int = 2, kv_len: int = None, threads=None):
         w[n["q"]], w[n["k"]], w[n["v"]], w[n["o"]] = mat(hq, H), mat(hkv, H), mat(hkv, H), mat(H, hq)
         w[n["gate"]], w[n["up"]], w[n["down"]] = mat(I, H), mat(I, H), mat(H, I)
     page = 128
-    n_pages_req = (kv_len + n_lm_steps + page) // page
+    warmup = max(1, warmup)
+    n_pages_req = (kv_len + n_lm_steps + warmup + page) // page
     kv = mat(dims.num_hidden_layers, BATCH * n_pages_req, 2, page, dims.num_key_value_heads, dims.head_dim)
     setup_s = time.perf_counter() - t0
     cfg = osampler.SamplingConfig(top_p=0.8, temperature=0.6, repetition_penalty=1.3, repetition_window=-1)
@@ -157,7 +170,7 @@ def cpu_oracle_sample(n_lm_steps: int = 2, kv_len: int = None, threads=None):
     gen = torch.Generator().manual_seed(0)
     lm_times = []
     with torch.no_grad():
-        for step in range(n_lm_steps + 1):          # first step is the warm-up
+        for step in range(n_lm_steps + warmup):     # the first `warmup` steps are not timed
             L = kv_len + step + 1
             npg = (L + page - 1) // page
             ip = [i * npg for i in range(BATCH + 1)]
@@ -170,7 +183,7 @@ def cpu_oracle_sample(n_lm_steps: int = 2, kv_len: int = None, threads=None):
             out = oorph.sampling_step(logits[:, None, :], cfg, rep, generator=gen)
             dt = time.perf_counter() - t1
             ids = out[:, 0]
-            if step > 0:
+            if step >= warmup:
                 lm_times.append(dt)
         scfg = osnac.SnacConfig()
         ssd = osnac.synth_state_dict(scfg, seed=1)
@@ -196,17 +209,19 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_steps = max(1, min(args.steps, 6))       # bounded sample: each step costs ~0.5 s of CPU time
+    # a step = one batch-32 decode step of the same workload on the host cores (~0.5 s each): --steps / --warmup are
+    # honoured exactly up to 60 steps in total (~30 s); beyond that the sample is cut and `steps` says what ran
+    n_warm = max(1, min(args.warmup, 10))
+    n_steps = max(1, min(args.steps, 60 - n_warm))
     t0 = time.perf_counter()
-    r = cpu_oracle_sample(n_lm_steps=n_steps)
+    r = cpu_oracle_sample(n_lm_steps=n_steps, warmup=n_warm)
     # ONE batch-32 replica on the box's host cores, whatever --gpus says: the host does not grow with the GPU count
     line = {"impl": "reference", "metric": "audio-sec/sec", "value": r["value"], "unit": "audio-sec/sec",
-            "n_gpus": args.gpus, "steps": n_steps, "warmup": 1, "ms_per_step": r["ms_per_step"],
+            "n_gpus": args.gpus, "steps": n_steps, "warmup": n_warm, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "prompt_tokens": PROMPT_ROWS,
-                       "mean_kv_len": round(sum(steady_state_kv_lens()) / BATCH, 1),
-                       "note": "CPU port of the reference path (the reference has no CPU path); one batch-32 replica on "
-                               "all host cores -- NOT multiplied by n_gpus"},
+            "config": workload_config(args.gpus),
+            "note": "CPU port of the reference path (the reference has no CPU path); one batch-32 replica on all host "
+                    "cores -- NOT multiplied by n_gpus; every request at the mean kv length of the steady-state mix",
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "audio-sec/sec", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
@@ -437,13 +452,7 @@ def run_gpu(args):
             "metric": "audio-sec/sec", "value": res_audio_s / (res_ms / 1e3), "unit": "audio-sec/sec", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": res_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "prompt_tokens": PROMPT_ROWS,
-                       "state": "steady-state continuous batch: request groups staggered 84 tokens apart "
-                                f"(kv {min(steady_state_kv_lens())}..{max(steady_state_kv_lens())} when the timed region starts)",
-                       "sampling": "top_p 0.8 T 0.6 repetition_penalty 1.3 (orpheus.py:260-268), stop id masked",
-                       "mean_kv_len": round(mean_kv, 1), "page_size": 128, "parallelism": f"dp{world} replicas",
-                       "weights": "seeded N(0,0.02) bf16 at Orpheus-3B shapes; SNAC 24 kHz shapes, seeded",
-                       "l2": "inputs larger than L2: 6.6 GB of weights stream from HBM every step (126 MB L2)"},
+            "config": workload_config(world), "mean_kv_len_timed": round(mean_kv, 1),
             "e2e": {"value": e2e_audio_s / (e2e_ms / 1e3), "unit": "audio-sec/sec", "h2d_bytes_per_step": int(h2d_step),
                     "d2h_bytes_per_step": int(d2h_step), "ms_per_step": e2e_ms / K,
                     "api": "Scheduler._step_async (scheduler/base.py:168-215 ordering) -> ModelWorker."
@@ -577,7 +586,9 @@ def kernel_rooflines(worker, model, reqs, torch, ops):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=700)
+    ap.add_argument("--steps", type=int, default=140,
+                    help="timed steps; the batch is not refilled inside the timed region, so long runs drift towards "
+                         "longer contexts than the steady-state mix (700 steps: mean kv 830 instead of 490-560)")
     ap.add_argument("--warmup", type=int, default=7)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
