@@ -1,36 +1,58 @@
 #!/bin/bash
-# One GPU-box pass of round 2: parity tests, prefetcher ablation, traces.   usage: tests/gpu_round2.sh <tag> [quick]
+# One GPU-box pass of round 2 (evidence for profiles/): parity tests, smoke, both bench arms as the driver runs them,
+# the default bench line, ncu launch list of resident steps, ncu --set full captures, in-situ layer timelines.
+# usage: tests/gpu_round2.sh <tag> [notests]
 tag=${1:-r02x}
 o=gpurun_out
 mkdir -p $o
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $o/${tag}_smi.txt 2>&1
-# the new / changed tests first, then the rest
-timeout 1500 python -m pytest tests/test_gpu_ops.py tests/test_gpu_engine.py tests/test_gpu_csm.py tests/test_gpu_qwen3_tts.py \
-  tests/test_gpu_e2e.py tests/test_gpu_reference_dropin.py tests/test_gpu_vocoder_graph.py tests/test_gpu_true_dims.py \
-  -q --timeout 600 -p no:cacheprovider -s > $o/${tag}_pytest.log 2>&1
-echo "pytest exit $?" >> $o/${tag}_pytest.log
-grep -E "passed|failed|FAILED|true-dims|reference adapter|csm |qwen3" $o/${tag}_pytest.log | tail -20
-run_bench() {   # name, env...
-  name=$1; shift
-  env "$@" timeout 400 python bench.py --steps 70 --warmup 3 --no-cpu --ttfa-joins 0 > $o/${tag}_bench_$name.json 2> $o/${tag}_bench_$name.err
-  python - "$o/${tag}_bench_$name.json" "$name" <<'PY'
+nproc >> $o/${tag}_smi.txt
+if [ "$2" != "notests" ]; then
+  timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider > $o/${tag}_pytest.log 2>&1
+  echo "pytest exit $?" >> $o/${tag}_pytest.log
+  tail -4 $o/${tag}_pytest.log
+  timeout 600 python __graft_entry__.py smoke > $o/${tag}_smoke.log 2>&1
+  echo "smoke exit $?"; tail -2 $o/${tag}_smoke.log
+fi
+timeout 300 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > $o/${tag}_bench_reference_s20.json 2> $o/${tag}_bench_reference_s20.err
+echo "reference arm exit $?"
+timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 > $o/${tag}_bench_s20.json 2> $o/${tag}_bench_s20.err
+echo "bench (driver flags) exit $?"; tail -2 $o/${tag}_bench_s20.err
+timeout 900 python bench.py > $o/${tag}_bench.json 2> $o/${tag}_bench.err
+echo "bench (default) exit $?"; tail -2 $o/${tag}_bench.err
+python - $o/${tag}_bench_s20.json $o/${tag}_bench.json $o/${tag}_bench_reference_s20.json <<'PY'
 import json, sys
-try:
-    d = json.load(open(sys.argv[1]))
-    print(f"{sys.argv[2]:>14}: value {d['value']:.1f} ms/step {d['ms_per_step']:.3f} e2e {d['e2e']['value']:.1f} "
-          f"sync {d['e2e']['sync_scheduler']['value']:.1f} attn {d['roofline_attention']['frac']:.3f} "
-          f"({d['roofline_attention']['avg_launch_us']:.1f} us) gemm {d['roofline']['frac']:.3f} ttfa1 {d['ttfa_single_ms']['p50']:.1f}")
-except Exception as e:
-    print(sys.argv[2], "FAILED", e)
+for f in sys.argv[1:]:
+    try:
+        d = json.load(open(f))
+        e = d.get("e2e", {})
+        print(f"{f}: value {d['value']:.2f} ms/step {d['ms_per_step']:.3f} e2e {e.get('value', 0):.2f}",
+              "sync", e.get("sync_scheduler", {}).get("value"), "gemm", d.get("roofline", {}).get("frac"),
+              "attn", d.get("roofline_attention", {}).get("frac"), d.get("roofline_attention", {}).get("avg_launch_us"),
+              "ttfa1", d.get("ttfa_single_ms", {}).get("p50"), "join", d.get("ttfa_join_ms", {}).get("p50"),
+              "cpu", d.get("cpu_baseline", {}).get("value"))
+    except Exception as ex:
+        print(f, "FAILED", ex)
 PY
-}
-run_bench pf_all VB_L2_PREFETCH=1
-run_bench pf_off VB_L2_PREFETCH=0
-run_bench pf_w_only VB_L2_PREFETCH_KV=0
-run_bench pf_win32 VB_L2_WINDOW_MB=32
-run_bench pf_win96 VB_L2_WINDOW_MB=96
-run_bench pf_attn111 VB_ATTN_SMEM_KB=111
-tail -3 $o/${tag}_bench_pf_all.err
-timeout 200 python tests/trace_step.py 500 unfused 60 34 > $o/${tag}_trace_kv500.txt 2>&1
-VB_L2_PREFETCH=0 timeout 200 python tests/trace_step.py 500 unfused 60 34 > $o/${tag}_trace_kv500_nopf.txt 2>&1
-head -40 $o/${tag}_trace_kv500.txt
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+  --log-file $o/${tag}_launches.csv python bench.py --steps 14 --warmup 3 --no-cpu --ttfa-joins 0 --profile-steps 7 > $o/${tag}_ncu_bench.log 2>&1
+echo "ncu launches exit $?"
+for kv in 200 500 900; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:paged_attn -c 3 -o $o/${tag}_attn_kv${kv}_full -f \
+    python tests/prof_attn.py $kv > $o/${tag}_ncu_attn_kv$kv.log 2>&1
+  echo "ncu attn kv $kv exit $?"
+done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -c 3 -o $o/${tag}_gemm_full -f \
+  python tests/prof_gemm.py > $o/${tag}_ncu_gemm.log 2>&1
+echo "ncu gemm exit $?"
+timeout 300 python tests/prof_mimi.py 64 10 > $o/${tag}_mimi_timing.txt 2>&1; cat $o/${tag}_mimi_timing.txt
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:mimi_conv -s 40 -c 6 -o $o/${tag}_mimi_full -f \
+  python tests/prof_mimi.py 64 1 > $o/${tag}_ncu_mimi.log 2>&1
+echo "ncu mimi exit $?"
+for kv in 200 500; do
+  timeout 200 python tests/trace_step.py $kv unfused 60 34 > $o/${tag}_trace_kv$kv.txt 2>&1
+  head -18 $o/${tag}_trace_kv$kv.txt
+done
+VB_DECODE_MODE=fused timeout 400 python bench.py --steps 70 --warmup 3 --no-cpu --ttfa-joins 0 > $o/${tag}_bench_fused.json 2> $o/${tag}_bench_fused.err
+echo "fused-mode bench exit $?"
+ls -la $o | grep ${tag} | awk '{print $5, $9}'

@@ -18,13 +18,14 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-static int g_pdl = -1;
-bool pdl_enabled() {
+static int g_pdl = -1, g_pdl_off = 0;
+bool pdl_enabled(int family) {
   if (g_pdl < 0) {
     const char* e = getenv("VB_PDL");
     g_pdl = (e && e[0] == '0') ? 0 : 1;
+    if (const char* m = getenv("VB_PDL_OFF")) g_pdl_off = atoi(m);
   }
-  return g_pdl != 0;
+  return g_pdl != 0 && (family & g_pdl_off) == 0;
 }
 
 // cuTensorMapEncodeTiled comes from the driver; resolve it at run time so the library links without
@@ -62,7 +63,7 @@ int vb_set_trace(void* d_buffer) {
 const char* vb_last_error(void) { return vb::g_err; }
 int vb_version(void) { return 100; }
 int vb_set_pdl(int enabled) {
-  const int old = vb::pdl_enabled() ? 1 : 0;
+  const int old = vb::pdl_enabled(0) ? 1 : 0;
   vb::g_pdl = enabled ? 1 : 0;
   return old;
 }

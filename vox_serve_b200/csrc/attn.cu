@@ -29,6 +29,7 @@
 //  * a row that spans several CTAs leaves one partial per CTA; the last CTA to arrive (one atomic per segment)
 //    merges them in CTA order (deterministic) and restores the arrival counter to 0.
 #include "../../include/vb_api.h"
+#define VB_PDL_FAMILY 1
 #include "common.cuh"
 
 namespace vb {

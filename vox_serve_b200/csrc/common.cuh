@@ -42,7 +42,12 @@ constexpr int VB_MAX_DYN_SMEM = 227 * 1024;
 // whatever does not depend on k: launch latency, barrier / TMEM set-up, and above all streaming WEIGHTS (GEMM)
 // and the KV of earlier steps (attention) into shared memory.  Because the trigger comes after the wait, when
 // k+1 starts every kernel <= k-1 has completed: pre-wait code may read anything but k's outputs.
-bool pdl_enabled();
+// (VB_PDL=0 disables it everywhere; VB_PDL_OFF=<mask> per source file, a debugging aid: 1 attention, 2 projections,
+// 4 elementwise, 8 multi-codebook glue, 16 sampler)
+#ifndef VB_PDL_FAMILY
+#define VB_PDL_FAMILY 0
+#endif
+bool pdl_enabled(int family);
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                          cudaStream_t stream, bool pdl, int cluster_x, Args... args) {
@@ -53,7 +58,7 @@ inline cudaError_t launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, di
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   int n = 0;
-  if (pdl && pdl_enabled()) {
+  if (pdl && pdl_enabled(VB_PDL_FAMILY)) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;
@@ -79,7 +84,7 @@ inline cudaError_t launch_kernel_cluster3(void (*kernel)(KArgs...), dim3 grid, d
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   int n = 0;
-  if (pdl && pdl_enabled()) {
+  if (pdl && pdl_enabled(VB_PDL_FAMILY)) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;

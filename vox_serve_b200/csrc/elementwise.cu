@@ -2,6 +2,7 @@
 // split-K reduction fused with residual + RMSNorm, fused QKV tail (reduce -> RoPE -> cache scatter),
 // embedding / row gathers, PCM16, Orpheus window de-interleave.  All HBM/latency-bound CUDA-core work.
 #include "../../include/vb_api.h"
+#define VB_PDL_FAMILY 4
 #include "common.cuh"
 
 namespace vb {

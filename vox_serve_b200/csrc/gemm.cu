@@ -21,6 +21,7 @@
 // workspace, the last CTA of a tile to arrive (one atomic per CTA) sums the partials in split order --
 // deterministic -- and runs the epilogue.
 #include "../../include/vb_api.h"
+#define VB_PDL_FAMILY 2
 #include "common.cuh"
 
 namespace vb {

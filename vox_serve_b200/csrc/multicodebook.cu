@@ -3,6 +3,7 @@
 // vox_serve/worker/cuda_graph_worker.py:1058-1160), as single launches that read their indices from device memory, so
 // that a whole frame -- backbone step, codebook-0 sample, 31 depth steps with their samples -- is one CUDA graph.
 #include "../../include/vb_api.h"
+#define VB_PDL_FAMILY 8
 #include "common.cuh"
 
 namespace vb {
@@ -20,7 +21,7 @@ __global__ void __launch_bounds__(256) multi_embed_sum_kernel(__nv_bfloat16* __r
                                                               const __nv_bfloat16* __restrict__ table_b, long long rows_b,
                                                               int C, int dim, int round_each) {
   pdl_sync();
-  extern __shared__ long long s_row[];          // [C] source row of every column, -1 = masked off
+  extern __shared__ __align__(16) long long s_row[];   // [C (+1: the compiler reads pairs)] source row of every column, -1 = masked off
   const size_t t = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     long long r = -1;
@@ -127,7 +128,7 @@ int vb_multi_embed_sum(void* d_out, int ld_out, const int64_t* d_ids, int64_t ld
   VB_CHECK_ARG(dim > 0 && dim % 8 == 0 && ld_out >= dim && C > 0 && C <= 1024 && n_cols_a >= 0 && n_cols_a <= C,
                "vb_multi_embed_sum: bad shape (dim %d, C %d, n_cols_a %d)", dim, C, n_cols_a);
   if (T <= 0) return 0;
-  VB_LAUNCH_PDL(multi_embed_sum_kernel, T, 256, static_cast<size_t>(C) * sizeof(long long), stream,
+  VB_LAUNCH_PDL(multi_embed_sum_kernel, T, 256, static_cast<size_t>((C + 2) & ~1) * sizeof(long long), stream,
                 static_cast<__nv_bfloat16*>(d_out), ld_out, reinterpret_cast<const long long*>(d_ids),
                 static_cast<long long>(ld_t), static_cast<long long>(ld_c), d_mask,
                 static_cast<const __nv_bfloat16*>(d_table_a), static_cast<long long>(rows_a),

@@ -9,6 +9,7 @@
 //     integer masses, fixed reduction trees, no atomics -- the result does not depend on thread scheduling;
 //   * greedy = largest key, smallest index on ties: exactly torch.argmax on the penalised bf16 logits.
 #include "../../include/vb_api.h"
+#define VB_PDL_FAMILY 16
 #include "common.cuh"
 
 namespace vb {
