@@ -561,6 +561,9 @@ def kernel_rooflines(worker, model, reqs, torch, ops):
         except Exception:
             ncu = {}
         gu_traffic = ncu.get("gemm_gate_up", {}).get("dram_bytes_per_launch")
+        mean_kv = sum(kv_lens) / len(kv_lens)
+        caps = ncu.get("paged_attn") or []
+        cap = min(caps, key=lambda c: abs(c["kv_len"] - mean_kv)) if caps else {}
         return {
             "roofline_gate_up": {"kernel": "gemm_bf16_kernel, gate/up projection launches only (28 per step, the largest "
                                            "projection: 100.7 MB of weights each)", "bound": "hbm", "achieved": gua,
@@ -574,9 +577,14 @@ def kernel_rooflines(worker, model, reqs, torch, ops):
                          "avg_launch_us": gemm_ms * 1e3 / max(1, n_gemm[0]),
                          "algorithmic_bytes_per_step": int(gemm_bytes)},
             "roofline_attention": {"kernel": "paged_attn_kernel (28 launches of one decode step)", "bound": "hbm",
-                                   "achieved": aa, "peak": peak, "unit": "GB/s", "frac": aa / peak, "traffic": None,
+                                   "achieved": aa, "peak": peak, "unit": "GB/s", "frac": aa / peak,
+                                   "traffic": cap.get("dram_bytes_per_launch"),
+                                   "traffic_source": (f"{cap.get('source')}: the capture nearest in kv length (all 32 rows at "
+                                                      f"kv {cap.get('kv_len')}, {cap.get('algorithmic_bytes_per_launch')} "
+                                                      "algorithmic bytes per launch)") if cap else None,
                                    "avg_launch_us": attn_ms * 1e3 / d.num_hidden_layers,
-                                   "mean_kv_len": sum(kv_lens) / len(kv_lens),
+                                   "mean_kv_len": mean_kv,
+                                   "algorithmic_bytes_per_launch": int(attn_bytes / d.num_hidden_layers),
                                    "algorithmic_bytes_per_step": int(attn_bytes)},
         }
 
