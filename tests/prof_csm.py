@@ -67,3 +67,5 @@ print(json.dumps({"workload": f"CSM-1B synthetic, batch {B}, {T0}-row prompts, M
                   "ms_per_frame_step": ms / F, "frames_per_s": B * F / (ms / 1e3), "audio_sec_per_sec": audio / (ms / 1e3),
                   "audio_sec_per_sec_from_frames": B * F * 0.08 / (ms / 1e3), "decode_frame_graph_ms": e0.elapsed_time(e1) / 10,
                   "graph_nodes": worker._graph_nodes.get(B), "setup_s": setup_s, "prefill_phase_s": prefill_s}))
+if state[0] is not None:
+    state[0].close()          # the carried request-state coroutine of the last step
