@@ -243,6 +243,8 @@ def run_gpu(args):
     if world > 1:
         # stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # its one-line banner goes to stdout regardless
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from vox_serve_b200 import ops
     from vox_serve_b200.model.orpheus import OrpheusModel

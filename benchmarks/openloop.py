@@ -71,6 +71,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # its one-line banner goes to stdout regardless
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from vox_serve_b200.model.orpheus import OrpheusModel
     from vox_serve_b200.requests import Request

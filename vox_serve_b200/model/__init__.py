@@ -1,6 +1,8 @@
 """Model-adapter registry with the reference's public surface (``vox_serve/model/__init__.py:17-179``):
 ``MODEL_REGISTRY``, ``get_model_class``, ``load_model``, ``register_model``, ``list_supported_models``.
-Only adapters whose whole decode + vocoder path runs on the sm_100a kernels are registered."""
+Only adapters whose whole decode + vocoder path runs on the sm_100a kernels are registered: Orpheus (+ SNAC) and CSM
+(+ Mimi).  The Qwen3-TTS talker + code-predictor frame exists as ``depth_engine.Qwen3TTSEngine`` but has no adapter yet
+(its codec decoder is not built)."""
 from __future__ import annotations
 
 from typing import Any, Dict, Type
@@ -15,7 +17,7 @@ from .orpheus import OrpheusModel
 MODEL_REGISTRY: Dict[str, Type[BaseLM]] = {
     "orpheus": OrpheusModel,
     "canopylabs/orpheus-3b-0.1-ft": OrpheusModel,
-    "csm": CSMModel,              # LM side only (backbone + depth decoder); its Mimi vocoder is not built yet
+    "csm": CSMModel,
     "sesame/csm-1b": CSMModel,
 }
 
