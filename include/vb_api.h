@@ -188,9 +188,13 @@ int vb_reduce_residual_rmsnorm(void* d_hidden_out, void* d_normed_out, const flo
 int vb_qkv_rope_append(void* d_q_out, void* d_layer_kv, const float* d_partials, int split_k, const int32_t* d_pos,
                        const float* d_freq, const int32_t* d_row_page, const int32_t* d_row_slot, int T, int n_q,
                        int n_kv, int head_dim, int page_size, int rotary_dim, int interleave, const void* d_q_norm,
-                       const void* d_k_norm, float norm_eps, void* stream);
+                       const void* d_k_norm, float norm_eps, const void* d_qkv_bias, void* stream);
 /* (d_q_norm / d_k_norm: optional bf16 [head_dim] weights of a per-head RMSNorm applied to every q and k head between the
- * bf16 rounding of the projection and the rotation -- Qwen3's q_norm / k_norm, vox_serve/model/qwen3_tts.py:603-625) */
+ * bf16 rounding of the projection and the rotation -- Qwen3's q_norm / k_norm, vox_serve/model/qwen3_tts.py:603-625;
+ * d_qkv_bias: optional bf16 [(n_q + 2 n_kv) head_dim] bias of the q | k | v projections, added in fp32 before the bf16
+ * rounding -- CosyVoice2's q/k/v_proj (model/cosyvoice2.py:139-143) and GLM-4-Voice's fused query_key_value
+ * (model/glm_voice.py:123-140); rotary_dim < head_dim / interleave = 1: GLM's rotation of the first half of every head in
+ * (even, odd) pairs, model/glm_voice.py:148-156) */
 /* slot-resident decode state (no host work between CUDA-graph replays; the reference does this bookkeeping
  * in Python every step, worker/base.py:312-325, orpheus.py:447-458):
  *   vb_decode_advance:  kv_len[b] += 1, position[b] += 1 for active rows (d_active NULL = all);

@@ -49,7 +49,7 @@ SIGNATURES = {
     "vb_row_ssq": (c_int, [P, P, c_int, c_int, P]),
     "vb_reduce_residual_rmsnorm": (c_int, [P, P, P, c_int, P, P, c_int, c_int, c_float, c_int, P]),
     "vb_qkv_rope_append": (c_int, [P, P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P,
-                                   c_float, P]),
+                                   c_float, P, P]),
     "vb_embedding": (c_int, [P, P, P, c_int, c_int, c_int, P]),
     "vb_gather_rows": (c_int, [P, P, P, c_int, c_int, c_int, P]),
     "vb_multi_embed_sum": (c_int, [P, c_int, P, c_int64, c_int64, P, P, c_int64, c_int64, c_int, c_int, P, c_int64, c_int,

@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(256) qkv_rope_append_kernel(
     int split_k, const int32_t* __restrict__ pos, const float* __restrict__ freq,
     const int32_t* __restrict__ row_page, const int32_t* __restrict__ row_slot, int T, int n_q, int n_kv, int D,
     int page_size, int rotary_dim, int interleave, int heads_per_cta, const __nv_bfloat16* __restrict__ q_norm_w,
-    const __nv_bfloat16* __restrict__ k_norm_w, float norm_eps) {
+    const __nv_bfloat16* __restrict__ k_norm_w, float norm_eps, const __nv_bfloat16* __restrict__ qkv_bias) {
   const int tr = (threadIdx.x == 0 && trace_block0()) ? trace_begin(6, split_k) : -1;
   pdl_sync();
   if (tr >= 0) trace_mark(24);
@@ -340,6 +340,10 @@ __global__ void __launch_bounds__(256) qkv_rope_append_kernel(
     for (int s = 1; s < split_k; ++s) {
       const float4 q4 = *reinterpret_cast<const float4*>(src + s * plane);
       acc.x += q4.x; acc.y += q4.y; acc.z += q4.z; acc.w += q4.w;
+    }
+    if (qkv_bias) {      // nn.Linear with bias: added in fp32 before the single bf16 rounding (cosyvoice2.py:139-143)
+      const uint2 b2 = __ldg(reinterpret_cast<const uint2*>(qkv_bias + w_lo + n));
+      acc.x += bf16_lo(b2.x); acc.y += bf16_hi(b2.x); acc.z += bf16_lo(b2.y); acc.w += bf16_hi(b2.y);
     }
     val[n] = round_bf16(acc.x);
     val[n + 1] = round_bf16(acc.y);
@@ -528,7 +532,7 @@ int vb_reduce_residual_rmsnorm(void* d_hidden_out, void* d_normed_out, const flo
 int vb_qkv_rope_append(void* d_q_out, void* d_layer_kv, const float* d_partials, int split_k, const int32_t* d_pos,
                        const float* d_freq, const int32_t* d_row_page, const int32_t* d_row_slot, int T, int n_q,
                        int n_kv, int head_dim, int page_size, int rotary_dim, int interleave, const void* d_q_norm,
-                       const void* d_k_norm, float norm_eps, void* stream) {
+                       const void* d_k_norm, float norm_eps, const void* d_qkv_bias, void* stream) {
   VB_CHECK_ARG((d_q_norm == nullptr) == (d_k_norm == nullptr), "vb_qkv_rope_append: q_norm and k_norm come together");
   VB_CHECK_ARG(d_q_out && d_layer_kv && d_partials && d_pos && d_freq && d_row_page && d_row_slot,
                "vb_qkv_rope_append: null pointer");
@@ -548,7 +552,8 @@ int vb_qkv_rope_append(void* d_q_out, void* d_layer_kv, const float* d_partials,
   VB_LAUNCH_PDL(qkv_rope_append_kernel, dim3(parts, T), 256, smem, stream, static_cast<__nv_bfloat16*>(d_q_out),
                 static_cast<__nv_bfloat16*>(d_layer_kv), d_partials, split_k, d_pos, d_freq, d_row_page, d_row_slot, T,
                 n_q, n_kv, head_dim, page_size, rotary_dim, interleave, heads_per_cta,
-                static_cast<const __nv_bfloat16*>(d_q_norm), static_cast<const __nv_bfloat16*>(d_k_norm), norm_eps);
+                static_cast<const __nv_bfloat16*>(d_q_norm), static_cast<const __nv_bfloat16*>(d_k_norm), norm_eps,
+                static_cast<const __nv_bfloat16*>(d_qkv_bias));
   return 0;
 }
 

@@ -41,6 +41,10 @@ class LlamaDims:
     high_freq_factor: Optional[float] = 4.0
     old_context_len: Optional[float] = 8192
     qk_norm: bool = False      # per-head RMSNorm of q and k before RoPE (Qwen3: self_attn.q_norm / k_norm)
+    qkv_bias: bool = False     # q / k / v projections with bias (CosyVoice2 / Qwen2, GLM-4-Voice)
+    head_bias: bool = False    # output head with bias (CosyVoice2's llm_decoder)
+    rotary_dim: Optional[int] = None     # elements of every head that are rotated (None = head_dim; GLM: head_dim / 2)
+    rope_interleave: bool = False        # rotate (even, odd) pairs instead of the two halves (GLM)
 
     @classmethod
     def orpheus_3b(cls):
@@ -64,7 +68,7 @@ class LlamaWeights:
         self.dims, self.device = dims, torch.device(device)
         self.gu_half = ops.gate_up_tile_half(dims.intermediate_size) if self.device.type == "cuda" else 64
         self.gu_half = int(os.environ.get("VB_GU_HALF", self.gu_half))          # (dev: tile-height experiments)
-        self.embed = self.norm = self.lm_head = None
+        self.embed = self.norm = self.lm_head = self.head_bias = None
         self.heads: List[object] = []
         self.arena: Optional[torch.Tensor] = None
         self.layers: List[Dict[str, torch.Tensor]] = []
@@ -72,7 +76,7 @@ class LlamaWeights:
     @classmethod
     def from_state_dict(cls, sd, dims: LlamaDims, device="cuda", prefix: str = "model.",
                         embed_key: Optional[str] = "model.embed_tokens.weight", head_key: str = "lm_head.weight",
-                        heads: Optional[List[torch.Tensor]] = None):
+                        heads: Optional[List[torch.Tensor]] = None, head_bias_key: Optional[str] = None):
         """``prefix`` / ``embed_key`` / ``head_key``: where the decoder stack, the token embedding (None: the caller
         supplies input embeddings) and the output head live in ``sd`` -- HF Llama names by default; the CSM backbone is
         ``backbone_model.`` + ``lm_head.weight``, its depth decoder ``depth_decoder.model.`` with ``heads`` = one
@@ -114,6 +118,9 @@ class LlamaWeights:
             if dims.qk_norm:
                 lp = f"{prefix}layers.{i}.self_attn."
                 self.layers[-1]["qn"], self.layers[-1]["kn"] = put(sd[lp + "q_norm.weight"]), put(sd[lp + "k_norm.weight"])
+            if dims.qkv_bias:
+                lp = f"{prefix}layers.{i}.self_attn."
+                self.layers[-1]["qkv_b"] = put(torch.cat([sd[lp + f"{x}_proj.bias"].reshape(-1) for x in "qkv"]))
         if heads is None:
             heads = [sd[head_key] if head_key in sd else sd[embed_key]]
         self.heads = []
@@ -123,6 +130,7 @@ class LlamaWeights:
                                               out=self.arena[off:off + head_bytes] if self.arena is not None else None))
             off += head_bytes
         self.lm_head = self.heads[0]
+        self.head_bias = put(sd[head_bias_key]) if dims.head_bias else None
         if dev.type == "cuda":
             # the row-major originals were just dropped: hand their blocks back NOW, not inside the first CUDA-graph
             # capture on the request path (capture_begin empties the allocator cache: ~1 s for 6.6 GB of blocks)
@@ -197,13 +205,15 @@ class LlamaEngine:
         self.last_normed = torch.zeros(self.max_out_rows, H, dtype=BF16, device=dev)
         self.logits = torch.zeros(self.max_out_rows, d.vocab_size, dtype=BF16, device=dev)
         self.attn_ws = ops.AttnWorkspace(R, hq, hkv, D, dev)
-        self.freq = ops.rope_freq_table(D, d.rope_factor, d.rope_theta, False, d.low_freq_factor,
+        self.freq = ops.rope_freq_table(d.rotary_dim or D, d.rope_factor, d.rope_theta, d.rope_interleave, d.low_freq_factor,
                                         d.high_freq_factor, d.old_context_len, device=dev)
         self.plan = ops.RowPlan(R, dev)
         self.attn_grid = self.attn_ws.grid
         # ---- fused decode path (<= FUSED_MAX_ROWS rows) ----
         self.gu_half = weights.gu_half
-        self.fused_ok = D in (64, 128) and H % 64 == 0 and not d.qk_norm      # (the fused QKV tail has no q/k norm)
+        # (the fused QKV tail has no q/k norm, no bias and rotates whole heads)
+        self.fused_ok = (D in (64, 128) and H % 64 == 0 and not d.qk_norm and not d.qkv_bias and d.rotary_dim in (None, D)
+                         and not d.rope_interleave)
         # split-K of the fused QKV projection: one head per tile
         self.fsplit_qkv = ops.proj_split_k(hq + 2 * hkv, H, self.sms)
         self.fsplit_o = ops.proj_split_k((H + 127) // 128, hq * D, self.sms)
@@ -261,7 +271,8 @@ class LlamaEngine:
             hidden_rows = normed
         if n_out > self.max_out_rows:
             raise VoxB200Error(f"logits requested for {n_out} rows; pass last_rows (max {self.max_out_rows})")
-        logits = ops.gemm(x, w.lm_head if head is None else head, mode=0, out=self.logits[:n_out])
+        logits = ops.gemm(x, w.lm_head if head is None else head, mode=0, out=self.logits[:n_out],
+                          bias=w.head_bias if head is None else None)
         return (logits, hidden_rows) if want_hidden else logits
 
     # How decode-sized steps (<= FUSED_MAX_ROWS rows) run their layers.  Measured on B200 (Orpheus-3B, 32 rows): separate
@@ -320,7 +331,8 @@ class LlamaEngine:
         for i, L in enumerate(w.layers):
             p = ops.gemm(normed, L["qkv"], mode=1, split_k=s_qkv, out=self._partials(s_qkv, R, self.qkv_w), tile_rows=D)
             ops.qkv_rope_append(p, self.kv_cache[i], position_ids, self.freq, plan, hq, hkv, D, q_out=q,
-                                q_norm=L.get("qn"), k_norm=L.get("kn"), norm_eps=d.rms_norm_eps)
+                                interleave=d.rope_interleave, q_norm=L.get("qn"), k_norm=L.get("kn"),
+                                norm_eps=d.rms_norm_eps, qkv_bias=L.get("qkv_b"))
             ops.paged_attn(q, self.kv_map, i * self.pages_per_layer, plan, R, hkv, self.page_size, self.chunk,
                            self.attn_ws, out=attn_o, grid_ctas=self.attn_grid)
             p = ops.gemm(attn_o if attn_tiled else attn_o.view(R, hq * D), L["o"], mode=1, split_k=s_o,

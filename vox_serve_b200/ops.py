@@ -550,16 +550,21 @@ def reduce_residual_rmsnorm(partials: torch.Tensor, residual: Optional[torch.Ten
 def qkv_rope_append(partials: torch.Tensor, layer_kv: torch.Tensor, pos: torch.Tensor, freq: torch.Tensor,
                     plan: RowPlan, n_q: int, n_kv: int, head_dim: int, interleave: bool = False,
                     q_out: Optional[torch.Tensor] = None, q_norm: Optional[torch.Tensor] = None,
-                    k_norm: Optional[torch.Tensor] = None, norm_eps: float = 1e-6) -> torch.Tensor:
-    """q_norm / k_norm (bf16 [head_dim]): per-head RMSNorm of q and k before the rotation (Qwen3)."""
-    _need_cuda(partials, layer_kv, pos, freq, q_norm, k_norm)
+                    k_norm: Optional[torch.Tensor] = None, norm_eps: float = 1e-6,
+                    qkv_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q_norm / k_norm (bf16 [head_dim]): per-head RMSNorm of q and k before the rotation (Qwen3).  qkv_bias (bf16
+    [(n_q + 2 n_kv) head_dim]): bias of the q | k | v projections (CosyVoice2, GLM-4-Voice).  freq may hold fewer than
+    head_dim entries: only the first freq.numel() elements of every head are rotated (GLM: half of the head)."""
+    _need_cuda(partials, layer_kv, pos, freq, q_norm, k_norm, qkv_bias)
+    assert qkv_bias is None or (qkv_bias.dtype == BF16 and qkv_bias.numel() == (n_q + 2 * n_kv) * head_dim)
     S, T, W = partials.shape
     assert W == (n_q + 2 * n_kv) * head_dim
     if q_out is None:
         q_out = torch.empty(T, n_q, head_dim, dtype=BF16, device=partials.device)
     call("vb_qkv_rope_append", q_out.data_ptr(), layer_kv.data_ptr(), partials.data_ptr(), S, pos.data_ptr(),
          freq.data_ptr(), plan.row_page.data_ptr(), plan.row_slot.data_ptr(), T, n_q, n_kv, head_dim,
-         layer_kv.shape[-3], freq.numel(), int(bool(interleave)), _p(q_norm), _p(k_norm), float(norm_eps), _stream())
+         layer_kv.shape[-3], freq.numel(), int(bool(interleave)), _p(q_norm), _p(k_norm), float(norm_eps), _p(qkv_bias),
+         _stream())
     return q_out
 
 
