@@ -620,7 +620,11 @@ static int launch_gemm(GemmParams& p, const void* w_tiles, const void* x_map, cu
     // the gate/up stream is the long one (48 stages per CTA) and it follows a small kernel: a 10-stage ring on the
     // whole SM beats co-residency here (forward 2.68 -> 2.64 ms; VB_GEMM_SMEM_KB_GU overrides)
     if (g_gemm_gu_kb < 0) { const char* e = getenv("VB_GEMM_SMEM_KB_GU"); g_gemm_gu_kb = e ? atoi(e) : 200; }
-    if (g_gemm_gu_kb >= 48 && g_gemm_gu_kb <= 220) budget = g_gemm_gu_kb * 1024;
+    // more tiles than SMs (GLM-4-Voice: 286): two CTAs per SM in one wave beat 1.9 waves of whole-SM CTAs
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int n_tiles = (p.N + p.tile_rows - 1) / p.tile_rows;
+    if (g_gemm_gu_kb >= 48 && g_gemm_gu_kb <= 220 && (n_tiles <= sms || sms <= 0)) budget = g_gemm_gu_kb * 1024;
   }
   int stages = (budget - extra) / stage_bytes;
   if (stages > 12) stages = 12;

@@ -408,11 +408,19 @@ def gemm(x, w, mode: int = 0, split_k: int = 1, out=None, tile_rows: int = 128, 
 
 
 def gate_up_tile_half(I: int, sms: Optional[int] = None) -> int:
-    """Gate rows per tile (h): a multiple of 16 (each epilogue warp pairs 16 gate with 16 up rows), at most 64, the
-    smallest with ceil(I / h) <= SMs so that the gate/up projection is about one CTA per SM."""
+    """Gate rows per tile (h): a multiple of 16 (each epilogue warp pairs 16 gate with 16 up rows), at most 64, chosen for
+    the fullest waves: up to one CTA per SM runs with the whole-SM ring, more tiles than SMs run two per SM (the kernel
+    then takes the 104 KB ring).  Orpheus / CSM (8192): 64 -> 128 CTAs; GLM-4-Voice (13696): 48 -> 286 CTAs on 296 slots
+    (64 would leave 214 on 296: measured 6.28 -> 5.75 ms per step); CosyVoice2 (4864): 48; Qwen3-TTS (6144): 48."""
     sms = device_info()[0] if sms is None else sms
-    h = max(16, ((I + sms - 1) // sms + 15) // 16 * 16)
-    return min(h, 64)
+    best, best_eff = 64, -1.0
+    for h in (64, 48, 32, 16):
+        tiles = (I + h - 1) // h
+        slots = sms if tiles <= sms else 2 * sms
+        eff = tiles / float((tiles + slots - 1) // slots * slots)
+        if eff > best_eff + 1e-9:
+            best, best_eff = h, eff
+    return best
 
 
 def interleave_gate_up(gate_w: torch.Tensor, up_w: torch.Tensor, h: int = 64) -> torch.Tensor:
