@@ -201,10 +201,12 @@ def test_orpheus_3b_true_dims_teacher_forced_iid_weights():
                 e = float((got[r, g_id] - ref_logits[r, g_id]).abs() + (got[r, o_id] - ref_logits[r, o_id]).abs())
                 margin = float(pen[r, o_id] - pen[r, g_id])
                 assert 0 <= margin <= 1.3 * e + 1e-6, (step, r, margin, e)
-                assert e <= 2 * 2e-2 * float(ref_logits[r].abs().max()), (step, r, e)
+                # (the two deviations are each bounded by the measured noise floor below, once it is known)
+                st["max_pair_err"] = max(st.get("max_pair_err", 0.0), e / float(ref_logits[r].abs().max()))
                 st["low_margin"] += 1
                 st["max_flip_margin"] = max(st.get("max_flip_margin", 0.0), margin)
     print("true-dims teacher-forced:", st)
     assert st["oracle_floor"] > 5e-3, st                 # (if this ever drops, tighten the bound below to 2e-2)
     assert st["max_logit_err"] < 2 * st["oracle_floor"], st
+    assert st.get("max_pair_err", 0.0) <= 2 * 2 * st["oracle_floor"], st
     assert st["id_mismatch"] <= 3 * max(st["oracle_flip_frac"], 0.05) * st["rows"], st

@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import os
 from dataclasses import dataclass
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Tuple
 
 import torch
 
@@ -189,10 +189,13 @@ class LlamaEngine:
         self.split_qkv = int(os.environ.get("VB_SPLIT_QKV", self.split_qkv))
         self.split_o = int(os.environ.get("VB_SPLIT_O", self.split_o))
         self.split_down = int(os.environ.get("VB_SPLIT_DOWN", self.split_down))
-        smax = max(self.split_qkv, self.split_o, self.split_down)
+        self._split_cache: Dict[Tuple[int, int], Tuple[int, int, int]] = {}
+        # split-K partials: the largest (split x rows) any step size up to R needs (prefill-sized steps split as well, see
+        # _splits: 24-40 weight tiles x one or two token tiles do not fill 148 SMs)
+        need = max(max(self._splits(t)) * t for t in sorted({min(R, t) for t in (64, 256, 512, 768, 1024, R)}))
         self.hidden = torch.zeros(R, H, dtype=BF16, device=dev)
         self.normed = torch.zeros(R, H, dtype=BF16, device=dev)
-        self.partials = torch.zeros(max(smax * min(R, 64), R) * max(self.qkv_w, H), dtype=torch.float32, device=dev)
+        self.partials = torch.zeros(max(need, R) * max(self.qkv_w, H), dtype=torch.float32, device=dev)
         self.q = torch.zeros(R, hq, D, dtype=BF16, device=dev)
         self.attn = torch.zeros(R, hq, D, dtype=BF16, device=dev)
         self.act = torch.zeros(R, I, dtype=BF16, device=dev)
@@ -228,9 +231,22 @@ class LlamaEngine:
     def _partials(self, split: int, rows: int, width: int) -> torch.Tensor:
         return self.partials[: split * rows * width].view(split, rows, width)
 
-    def _split(self, base: int, rows: int) -> int:
-        # large-T (prefill) problems already fill the machine with token tiles x N tiles
-        return base if rows <= 64 else 1
+    def _splits(self, rows: int) -> Tuple[int, int, int]:
+        """split-K of the QKV / O / down projections of a step with ``rows`` token rows.  Decode-sized steps use the tuned
+        values; larger steps re-apply the same rule to (weight tiles x 256-row token tiles): a 133-row prefill is ONE token
+        tile, i.e. 24-40 CTAs per projection without split-K (measured: the 133-token Orpheus prefill took ~7 ms of a 63 ms
+        TTFA that way)."""
+        if rows <= self.FUSED_MAX_ROWS:
+            return self.split_qkv, self.split_o, self.split_down
+        if os.environ.get("VB_PREFILL_SPLIT", "1") == "0":           # (A/B switch: round-1 behaviour)
+            return 1, 1, 1
+        key = (rows + 255) // 256
+        if key not in self._split_cache:
+            d = self.dims
+            H, I, hqD = d.hidden_size, d.intermediate_size, d.num_attention_heads * d.head_dim
+            self._split_cache[key] = (ops.choose_split_k(self.qkv_w, H, rows, self.sms), ops.choose_split_k(H, hqD, rows, self.sms),
+                                      ops.choose_split_k(H, I, rows, self.sms))
+        return self._split_cache[key]
 
     def forward(self, input_ids: Optional[torch.Tensor], position_ids: torch.Tensor, n_rows: int,
                 last_rows: Optional[torch.Tensor] = None, n_out: Optional[int] = None,
@@ -325,7 +341,7 @@ class LlamaEngine:
         attn_o = self.attn_t.view_rows(R) if attn_tiled else self.attn[:R]
         act = self.act_t.view_rows(R) if tiled else self.act[:R]
         ops.rmsnorm(hidden, w.layers[0]["ln1"], d.rms_norm_eps, out=normed)
-        s_qkv, s_o, s_dn = self._split(self.split_qkv, R), self._split(self.split_o, R), self._split(self.split_down, R)
+        s_qkv, s_o, s_dn = self._splits(R)
         q = self.q[:R]
         n_layers = len(w.layers)
         for i, L in enumerate(w.layers):
@@ -362,7 +378,7 @@ class LlamaEngine:
             normed = self.normed_t.view_rows(R) if tiled else self.normed[:R]
             attn_o = self.attn_t.view_rows(R) if tiled else self.attn[:R].view(R, hq * D)
             act = self.act_t.view_rows(R) if tiled else self.act[:R]
-            s_qkv, s_o, s_dn = self._split(self.split_qkv, R), self._split(self.split_o, R), self._split(self.split_down, R)
+            s_qkv, s_o, s_dn = self._splits(R)
             for L in w.layers:
                 ops.gemm(normed, L["qkv"], mode=1, split_k=s_qkv, out=self._partials(s_qkv, R, self.qkv_w), tile_rows=D)
                 ops.gemm(attn_o, L["o"], mode=1, split_k=s_o, out=self._partials(s_o, R, H))
