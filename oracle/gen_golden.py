@@ -645,8 +645,63 @@ def golden_mimi():
     print("mimi_tiny.npz:", tuple(wav.shape), "abs max %.4f" % float(wav.abs().max()))
 
 
+def golden_qwen3_codec():
+    """The reference's own ``Qwen3TTSTokenizerV2Decoder`` (tokenizer/qwen3_codec.py:1307-1667) on CPU at a tiny configuration
+    (GQA 2, sliding window 12, all four decoder rates): ``init_cache`` + three consecutive ``forward_chunk`` calls of 5, 5 and
+    3 frames -- the window wraps, the short last chunk takes the "chunk shorter than the conv cache" branch of the
+    dilation-9 convolutions -> tests/golden/qwen3_codec_tiny.npz (waveforms + the final cache)."""
+    from . import qwen3_codec as oq
+    from .ref_import import REFERENCE_ROOT
+
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    from vox_serve.tokenizer import qwen3_codec as rq
+
+    rq.ROPE_INIT_FUNCTIONS = None      # transformers 5 dropped the "default" entry; the module's own fallback is the same formula
+    cfg = oq.Qwen3CodecConfig.tiny()
+    rcfg = rq.Qwen3TTSTokenizerV2DecoderConfig(
+        latent_dim=cfg.latent_dim, codebook_dim=cfg.codebook_dim, codebook_size=cfg.codebook_size, decoder_dim=cfg.decoder_dim,
+        hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size, head_dim=cfg.head_dim,
+        num_attention_heads=cfg.num_attention_heads, num_hidden_layers=cfg.num_hidden_layers,
+        num_key_value_heads=cfg.num_key_value_heads, num_quantizers=cfg.num_quantizers, rms_norm_eps=cfg.rms_norm_eps,
+        rope_theta=cfg.rope_theta, sliding_window=cfg.sliding_window, upsample_rates=list(cfg.upsample_rates),
+        upsampling_ratios=list(cfg.upsampling_ratios))
+    dec = rq.Qwen3TTSTokenizerV2Decoder(rcfg).eval()
+    seed, B = 23, 2
+    sd = oq.synth_state_dict(cfg, seed)
+    dec.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(5)
+    chunks = [torch.randint(0, cfg.codebook_size, (B, cfg.num_quantizers, t), generator=g) for t in (5, 5, 3)]
+    out = {}
+    with torch.no_grad():
+        cache = dec.init_cache(B, torch.device("cpu"), torch.float32, detokenize_interval=5)
+        for i, c in enumerate(chunks):
+            if c.shape[2] != 5:       # the work buffers are sized per chunk length: the state tensors carry over
+                fresh = dec.init_cache(B, torch.device("cpu"), torch.float32, detokenize_interval=c.shape[2])
+                for name in ("attention_cache", "position_offset", "pre_conv_cache"):
+                    getattr(fresh, name).copy_(getattr(cache, name))
+                for name in ("upsample_conv_caches", "decoder_conv_caches", "transconv_caches"):
+                    for a, b in zip(getattr(fresh, name), getattr(cache, name)):
+                        a.copy_(b)
+                cache = fresh
+            wav, cache = dec.forward_chunk(c, cache)
+            assert wav.shape == (B, 1, c.shape[2] * cfg.hop), wav.shape
+            out[f"codes{i}"], out[f"wav{i}"] = c.numpy(), wav.numpy().copy()
+    out["attention_cache"], out["position_offset"] = cache.attention_cache.numpy(), cache.position_offset.numpy()
+    out["pre_conv_cache"] = cache.pre_conv_cache.numpy()
+    for name in ("upsample_conv_caches", "decoder_conv_caches", "transconv_caches"):
+        for j, t in enumerate(getattr(cache, name)):
+            out[f"{name}.{j}"] = t.numpy()
+    np.savez_compressed(os.path.join(OUT, "qwen3_codec_tiny.npz"), weight_seed=seed, **out)
+    print("qwen3_codec_tiny.npz:", [tuple(out[f"wav{i}"].shape) for i in range(3)],
+          "abs max %.4f" % max(float(np.abs(out[f"wav{i}"]).max()) for i in range(3)))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "qwen3_codec":
+        golden_qwen3_codec()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "qwen3_tts":
         golden_qwen3_tts_frames()
         return
@@ -675,6 +730,7 @@ def main():
         golden_csm_frames()
         golden_qwen3_tts_frames()
         golden_mimi()
+        golden_qwen3_codec()
     finally:
         torch.cuda.synchronize = orig_sync
 

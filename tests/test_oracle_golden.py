@@ -193,3 +193,28 @@ def test_mimi_decode_oracle_matches_reference_golden(golden_dir):
     wav = omimi.decode(sd, cfg, codes)
     assert wav.shape == (3, 1, 5 * cfg.hop) and cfg.hop == 1920 and omimi.MimiConfig().hop == 1920
     assert np.array_equal(wav.numpy(), gd["wav"])
+
+
+def test_qwen3_codec_streaming_decoder_oracle_matches_reference_golden(golden_dir):
+    """SURVEY rows a25 / f2 (Qwen3-TTS 12 Hz codec, streaming): oracle/qwen3_codec.py against the reference's own
+    Qwen3TTSTokenizerV2Decoder.forward_chunk on CPU (oracle/gen_golden.py:golden_qwen3_codec): three consecutive chunks (5, 5, 3
+    frames: the 12-slot attention window wraps, the last chunk is shorter than the dilation-9 conv caches), every waveform
+    and every tensor of the final cache bit-exact."""
+    from oracle import qwen3_codec as oq
+
+    gd = _load(golden_dir, "qwen3_codec_tiny.npz")
+    cfg = oq.Qwen3CodecConfig.tiny()
+    sd = oq.synth_state_dict(cfg, int(gd["weight_seed"]))
+    cache = oq.init_cache(cfg, 2)
+    for i in range(3):
+        codes = torch.from_numpy(gd[f"codes{i}"])
+        wav, cache = oq.forward_chunk(sd, cfg, codes, cache)
+        assert wav.shape == (2, 1, codes.shape[2] * cfg.hop)
+        assert np.array_equal(wav.numpy(), gd[f"wav{i}"]), i
+    assert np.array_equal(cache["attention"].numpy(), gd["attention_cache"])
+    assert np.array_equal(cache["position_offset"].numpy(), gd["position_offset"]) and int(cache["position_offset"][0]) == 13
+    assert np.array_equal(cache["pre_conv"].numpy(), gd["pre_conv_cache"])
+    for name, key in (("upsample", "upsample_conv_caches"), ("decoder_conv", "decoder_conv_caches"), ("transconv", "transconv_caches")):
+        for j, t in enumerate(cache[name]):
+            assert np.array_equal(t.numpy(), gd[f"{key}.{j}"]), (name, j)
+    assert cfg.hop == 192 and oq.Qwen3CodecConfig().hop == 1920
