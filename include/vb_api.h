@@ -359,6 +359,39 @@ int vb_randn(float* d_out, int64_t n, uint64_t seed, uint64_t offset, uint64_t* 
 int vb_orpheus_window_codes(int32_t* d_c0, int32_t* d_c1, int32_t* d_c2, const int64_t* d_ids, int B,
                             int audio_id_base, void* stream);
 
+/* ---- streaming codec decoder stages with per-request caches: the Qwen3-TTS 12 Hz decoder ------------------------------
+ * vox_serve/tokenizer/qwen3_codec.py:1541-1667 (forward_chunk).  fp32, activations [B][C][T].  act_in: 0 none, 1 ELU,
+ * 2 SnakeBeta with d_act_a = exp(alpha), d_act_ib = 1 / (exp(beta) + 1e-9) per input channel (:1004-1018).  The caches hold
+ * ACTIVATED inputs (as the reference's do), context reads are not activated again.
+ *   vb_codec_conv:   causal Conv1d / Linear (ksize 1); d_ctx [B][Cin][(ksize-1) dilation] = left context (NULL: zeros,
+ *                    :274-340); epilogue 0 plain, 1 resid + v, 2 resid + scale[m] v (LayerScale / ConvNeXt gamma), 3 GELU,
+ *                    4 SiLU, 5 resid * v (the gated MLP's product), 6 clamp(-1, 1) (:1667); bias added before the epilogue.
+ *   vb_codec_convtr: causal ConvTranspose1d, kernel 2 s, stride s, weights packed [s][Cout][2 Cin] (tap 0 | tap 1);
+ *                    d_ctx [B][Cin][1] = the previous chunk's last activated input (NULL: zero, :359-397).  A transposed
+ *                    convolution with kernel == stride is the same call with a zero tap-1 half.
+ *   vb_codec_cache_update: cache [B][C][pad] <- last pad activated inputs after appending x [B][C][L] (:318-325, 391); run
+ *                    it AFTER the convolution that reads the old cache.
+ *   vb_codec_dwconv: depthwise causal Conv1d with left context (ConvNeXt dwconv, :434-451); w [C][ksize].
+ *   vb_codec_rmsnorm: RMSNorm over the channel axis (:713-718).
+ *   vb_codec_attn_chunk: one chunk of the sliding-window attention (:573-655): qkv [B][(H + 2 Hkv) D][T], rotate-half RoPE at
+ *                    positions d_pos0[b] + t, cache [Hkv][W][2 D] per item (items cache_batch_stride floats apart: one layer of
+ *                    the reference's [B][layers][Hkv][W][2 D] tensor) shifted left by T with the new K | V appended, every
+ *                    query attends to all W slots (never-written slots hold zeros, as in the reference) under the mask
+ *                    j <= W - T + t; out [B][H D][T]; T < W. */
+int vb_codec_conv(float* d_y, const float* d_x, const float* d_w, const float* d_bias, const float* d_resid,
+                  const float* d_scale, const float* d_ctx, const float* d_act_a, const float* d_act_ib, int epilogue,
+                  int act_in, int B, int Cin, int Cout, int T, int ksize, int dilation, void* stream);
+int vb_codec_convtr(float* d_y, const float* d_x, const float* d_w_packed, const float* d_bias, const float* d_ctx,
+                    const float* d_act_a, const float* d_act_ib, int act_in, int B, int Cin, int Cout, int T, int stride,
+                    void* stream);
+int vb_codec_cache_update(float* d_cache, const float* d_x, const float* d_act_a, const float* d_act_ib, int act_in, int B,
+                          int C, int L, int pad, void* stream);
+int vb_codec_dwconv(float* d_y, const float* d_x, const float* d_w, const float* d_bias, const float* d_ctx, int B, int C,
+                    int T, int ksize, void* stream);
+int vb_codec_rmsnorm(float* d_y, const float* d_x, const float* d_w, int B, int C, int T, float eps, void* stream);
+int vb_codec_attn_chunk(float* d_out, const float* d_qkv, float* d_cache, int64_t cache_batch_stride, const int64_t* d_pos0,
+                        int B, int H, int Hkv, int D, int T, int W, float theta, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,7 +55,7 @@ class Qwen3CodecConfig:
 
     @classmethod
     def tiny(cls, **kw):
-        d = dict(latent_dim=64, codebook_dim=32, codebook_size=64, decoder_dim=96, hidden_size=32, intermediate_size=64,
+        d = dict(latent_dim=64, codebook_dim=32, codebook_size=64, decoder_dim=128, hidden_size=32, intermediate_size=64,
                  head_dim=8, num_attention_heads=4, num_hidden_layers=2, num_key_value_heads=2, num_quantizers=4,
                  sliding_window=12, upsample_rates=(4, 3, 2, 2), upsampling_ratios=(2, 2))
         d.update(kw)

@@ -79,6 +79,12 @@ SIGNATURES = {
     "vb_mimi_upsample": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     "vb_mimi_layernorm": (c_int, [P, P, P, P, c_int, c_int, c_int, c_float, P]),
     "vb_mimi_attention": (c_int, [P, P, c_int, c_int, c_int, c_int, c_float, P]),
+    "vb_codec_conv": (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_codec_convtr": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_codec_cache_update": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_codec_dwconv": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    "vb_codec_rmsnorm": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P]),
+    "vb_codec_attn_chunk": (c_int, [P, P, P, c_int64, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P]),
     "vb_orpheus_window_codes": (c_int, [P, P, P, P, c_int, c_int, P]),
 }
 

@@ -21,7 +21,7 @@ LIB = os.path.join(LIBDIR, "libvoxb200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 SOURCES = ["api.cu", "elementwise.cu", "attn.cu", "gemm.cu", "sampler.cu", "snac.cu", "snac_mma.cu",
-           "multicodebook.cu", "mimi.cu"]
+           "multicodebook.cu", "mimi.cu", "codec.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
