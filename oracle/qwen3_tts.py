@@ -122,8 +122,10 @@ def predictor_forward(w, d: Qwen3TTSDims, inputs_embeds, position_ids, wrapper, 
     return F.linear(h, w[f"talker.code_predictor.lm_head.{idx}.weight"])
 
 
-def predictor_loop_greedy(w, d: Qwen3TTSDims, hidden: torch.Tensor, cb0: int, page_size: int = 32):
-    """codebooks 1 .. N-1 of one frame for one request; returns (ids, logits [N-1, V], sum of their embeddings)"""
+def predictor_loop_greedy(w, d: Qwen3TTSDims, hidden: torch.Tensor, cb0: int, page_size: int = 32, forced=None):
+    """codebooks 1 .. N-1 of one frame for one request; returns (ids, logits [N-1, V], sum of their embeddings).
+    ``forced`` (ids of codebooks 1 .. N-1): feed these back (and sum THEIR embeddings) instead of the argmax -- teacher
+    forcing; the returned ids stay the oracle's own argmax of every step."""
     N = d.num_code_groups
     kv = torch.zeros(d.cp_num_hidden_layers, 1, 2, page_size, d.cp_num_key_value_heads, d.cp_head_dim,
                      dtype=hidden.dtype)
@@ -137,7 +139,8 @@ def predictor_loop_greedy(w, d: Qwen3TTSDims, hidden: torch.Tensor, cb0: int, pa
         logs.append(logits.float())
         tok = int(torch.argmax(logits.float()))
         ids.append(tok)
-        emb = w[f"{CP}codec_embedding.{i - 1}.weight"][tok][None, :]
+        fed = tok if forced is None else int(forced[i - 1])
+        emb = w[f"{CP}codec_embedding.{i - 1}.weight"][fed][None, :]
         feat += emb                                                                  # :2002 (in-place bf16 adds)
         if i == N - 1:
             break

@@ -86,3 +86,24 @@ def test_decoder_cache_matches_reference_class():
             res.append(_flat(r) + [r.inner.steps, r.name])
         for x, y in zip(*res):
             assert torch.equal(x, y) if torch.is_tensor(x) else x == y
+
+
+def test_index_copy_and_zero_rows_round_trip():
+    from vox_serve_b200.tokenizer.qwen3_codec import Qwen3TTSDecoderCache
+
+    def mk(B, v):
+        return Qwen3TTSDecoderCache(attention_cache=torch.full((B, 2, 3), v), position_offset=torch.full((B,), int(v), dtype=torch.long),
+                                    pre_conv_cache=torch.full((B, 4), v), upsample_conv_caches=[torch.full((B, 2), v)],
+                                    decoder_conv_caches=[torch.full((B, 1), v), torch.full((B, 5), v)], transconv_caches=[])
+
+    slots = mk(4, 0.0)
+    part = mk(2, 7.0)
+    idx = torch.tensor([3, 1])
+    slots.index_copy_(idx, part)
+    assert slots.attention_cache[:, 0, 0].tolist() == [0.0, 7.0, 0.0, 7.0] and slots.position_offset.tolist() == [0, 7, 0, 7]
+    back = slots[idx]
+    assert torch.equal(back.decoder_conv_caches[1], part.decoder_conv_caches[1])
+    slots.zero_rows_(torch.tensor([1]))
+    assert slots.pre_conv_cache[:, 0].tolist() == [0.0, 0.0, 0.0, 7.0]
+    slots.zero_rows_(3)
+    assert float(slots.upsample_conv_caches[0].abs().sum()) == 0.0

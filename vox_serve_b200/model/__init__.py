@@ -1,8 +1,7 @@
 """Model-adapter registry with the reference's public surface (``vox_serve/model/__init__.py:17-179``):
 ``MODEL_REGISTRY``, ``get_model_class``, ``load_model``, ``register_model``, ``list_supported_models``.
 Only adapters whose whole decode + vocoder path runs on the sm_100a kernels are registered: Orpheus (+ SNAC) and CSM
-(+ Mimi).  The Qwen3-TTS talker + code-predictor frame exists as ``depth_engine.Qwen3TTSEngine`` but has no adapter yet
-(its codec decoder is not built)."""
+(+ Mimi) and Qwen3-TTS (+ its streaming 12 Hz codec decoder)."""
 from __future__ import annotations
 
 from typing import Any, Dict, Type
@@ -13,12 +12,15 @@ from ..sampling import SamplingConfig
 from .base import BaseLM, BaseLMWithDepth, PreprocessOutput
 from .csm import CSMModel
 from .orpheus import OrpheusModel
+from .qwen3_tts import Qwen3TTSModel
 
 MODEL_REGISTRY: Dict[str, Type[BaseLM]] = {
     "orpheus": OrpheusModel,
     "canopylabs/orpheus-3b-0.1-ft": OrpheusModel,
     "csm": CSMModel,
     "sesame/csm-1b": CSMModel,
+    "qwen3-tts": Qwen3TTSModel,
+    "qwen/qwen3-tts": Qwen3TTSModel,
 }
 
 

@@ -64,6 +64,20 @@ class DecoderCache:
             raise TypeError("All caches must be instances of the same cache class")
         return _tree_map(lambda ts: torch.cat(ts, dim=0), list(caches))
 
+    @torch.no_grad()
+    def index_copy_(self, index: torch.Tensor, src: "DecoderCache") -> None:
+        """Write the batch rows of ``src`` into rows ``index`` (int64 tensor) of this cache: the inverse of
+        ``self[index]``.  The worker keeps ONE cache for all its batch slots and moves the rows of the streams a vocoder
+        call serves in and out with these two (no host synchronisation, CUDA-graph capturable)."""
+        if type(self) is not type(src):
+            raise TypeError(f"Cannot copy from {type(src)} to {type(self)}")
+        _tree_map(lambda ts: ts[0].index_copy_(0, index, ts[1]), [self, src])
+
+    @torch.no_grad()
+    def zero_rows_(self, index: Any) -> None:
+        """Reset the state of the batch rows ``index`` (a stream that starts on a recycled slot)."""
+        _tree_map(lambda ts: ts[0][index].zero_() if not isinstance(index, torch.Tensor) else ts[0].index_fill_(0, index, 0), [self])
+
     def to(self, device) -> "DecoderCache":
         """A copy with every tensor on ``device``."""
         return _tree_map(lambda ts: ts[0].to(device), [self])

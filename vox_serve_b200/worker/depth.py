@@ -50,16 +50,42 @@ class DepthModelWorker(CudaGraphWorker):
         self.ids_dev = torch.zeros(self.max_rows, C, dtype=I64, device=dev)
         self.mask_dev = torch.zeros(self.max_rows, C, dtype=torch.bool, device=dev)
         self.decode_mask = torch.ones(C, dtype=torch.bool)
-        self.decode_mask[-1] = False             # only the audio streams are fed back in decode (csm.py:711-712)
+        # mask of a decode row: CSM feeds back only the audio streams (csm.py:711-712); Qwen3-TTS rows keep the last column
+        # set = "this row carries a codec embedding" (qwen3_tts.py:1941)
+        self.decode_mask[-1] = bool(getattr(m, "decode_text_column_mask", False))
         self._win_j = torch.arange(m.detokenize_interval, dtype=I64, device=dev)
         self.voc_win = torch.zeros(self.max_chunks, m.detokenize_interval, C, dtype=I64, device=dev)
+        # models whose rows carry input_features (Qwen3-TTS: speaker / ICL sums in the prompt, the predictor-embedding sum of
+        # the previous frame in decode, qwen3_tts.py:1835-1853, 2002): per-slot feature row + prompt staging
+        self.feats = None
+        if m.needs_input_features:
+            H = m.hidden_size
+            self.feats = torch.zeros(B, H, dtype=torch.bfloat16, device=dev)
+            self.prompt_feat_host = torch.zeros(self.max_rows, H, dtype=torch.bfloat16, pin_memory=True)
+            self.feat_dev = torch.zeros(self.max_rows, H, dtype=torch.bfloat16, device=dev)
+        # codecs with streaming state (Qwen3-TTS: Qwen3TTSDecoderCache): ONE cache over all batch slots; a vocoder call moves
+        # the rows of the streams it serves out and back in (DecoderCache.__getitem__ / index_copy_), a stream that starts on
+        # a recycled slot gets its rows zeroed.  (The reference keeps one cache per request and cats them per call,
+        # cuda_graph_worker.py:1195-1240.)
+        init = getattr(m, "audio_decoder_initial_cache", None)
+        self.voc_cache = init(B) if init is not None else None
 
     # ---- token rows ---------------------------------------------------------------------------------------
+    def _acquire_slot(self, req: Request) -> int:
+        new = req.request_id not in self.slot_of
+        s = super()._acquire_slot(req)
+        if new and self.voc_cache is not None:
+            self.voc_cache.zero_rows_(s)
+        return s
+
     def _stage_prompt_rows(self, req: Request, out, t: int, n: int) -> None:
         if out.input_masks is not None:
             req.input_masks = out.input_masks
         self.prompt_ids_host[t:t + n] = req.input_tokens
         self.prompt_mask_host[t:t + n] = req.input_masks
+        if self.feats is not None:
+            req.input_features = out.input_features
+            self.prompt_feat_host[t:t + n] = out.input_features.to(torch.bfloat16)
 
     def _stage_decode_row(self, t: int) -> None:
         self.prompt_ids_host[t] = 0              # replaced on the device by the slot's last frame (row_slot >= 0)
@@ -84,11 +110,20 @@ class DepthModelWorker(CudaGraphWorker):
             st.consumed.record()                 # the pinned prompt rows may be refilled only after these copies
             # rows of requests that are already decoding carry their slot: their ids are the slot's last frame
             rs = st.d("row_slot", T)
-            ids = torch.where((rs >= 0)[:, None], self.frames[rs.clamp(min=0).long()], self.ids_dev[:T])
+            is_dec, rs64 = (rs >= 0)[:, None], rs.clamp(min=0).long()
+            ids = torch.where(is_dec, self.frames[rs64], self.ids_dev[:T])
             last_rows = (st.d("qo", B + 1)[1:] - 1).contiguous()
-            out = m.frame_device(self.kv_cache, wrapper, st.d("pos", T), B, ids, self.mask_dev[:T], last_rows=last_rows)
+            kw = {}
+            if self.feats is not None:
+                self.feat_dev[:T].copy_(self.prompt_feat_host[:T], non_blocking=True)
+                st.consumed.record()
+                kw["input_features"] = torch.where(is_dec, self.feats[rs64], self.feat_dev[:T])
+            out = m.frame_device(self.kv_cache, wrapper, st.d("pos", T), B, ids, self.mask_dev[:T], last_rows=last_rows, **kw)
         else:
-            out = m.frame_device(self.kv_cache, wrapper, st.d("pos", T), B, self.frames[slots])
+            kw = {"input_features": self.feats[slots]} if self.feats is not None else {}
+            out = m.frame_device(self.kv_cache, wrapper, st.d("pos", T), B, self.frames[slots], **kw)
+        if self.feats is not None:
+            self.feats.index_copy_(0, slots, m.slot_features(self.kv_cache, B))
         self.out_ids[:B].copy_(out)
         # feedback: the frame becomes the slot's next input and is appended to the slot's history unless it is the stop
         # frame (the host does not append that one to lm_output_audio_tokens either, csm.py:713-722)
@@ -123,7 +158,10 @@ class DepthModelWorker(CudaGraphWorker):
             for i, req in enumerate(requests):
                 row = host[i:i + 1]
                 req.input_tokens = row.clone()
-                req.input_tokens[0, -1] = 0
+                if self.feats is None:
+                    req.input_tokens[0, -1] = 0            # CSM: the text column of a decode row is unused (csm.py:707-712)
+                else:
+                    req.input_features = None              # the next row's features live in the slot state on the device
                 req.input_masks = mask
                 req.lm_output_tokens.append(row)
                 if cb0[i] != stop:
@@ -143,7 +181,12 @@ class DepthModelWorker(CudaGraphWorker):
         # (worker/base.py:629-632)
         idx = first[:, None] + torch.minimum(self._win_j[None, :], n_valid[:, None] - 1)
         self.voc_win[:n].copy_(self.history[slot[:, None], idx % self.history_cap])
-        audio = self.model.postprocess(self.voc_win[:n])
+        if self.voc_cache is not None:
+            sub = self.voc_cache[slot]
+            audio = self.model.postprocess(self.voc_win[:n], decoder_cache=sub)
+            self.voc_cache.index_copy_(slot, sub)
+        else:
+            audio = self.model.postprocess(self.voc_win[:n])
         ops.pcm16(audio, out=self.voc_pcm[:n])
 
     def run_lm_decode_resident(self, *a, **kw):
