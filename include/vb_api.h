@@ -384,6 +384,15 @@ int vb_codec_conv(float* d_y, const float* d_x, const float* d_w, const float* d
 int vb_codec_convtr(float* d_y, const float* d_x, const float* d_w_packed, const float* d_bias, const float* d_ctx,
                     const float* d_act_a, const float* d_act_ib, int act_in, int B, int Cin, int Cout, int T, int stride,
                     void* stream);
+/* the same two calls on the tcgen05 tf32 hi/lo kernel of the SNAC stages (fp32-grade results): weights packed by
+ * vb_snac_pack_tf32x3(phases = 1, M = Cout, K = ksize * Cin) from the TAP-MAJOR matrix [Cout][ksize][Cin] (conv) or
+ * (phases = stride, M = Cout, K = 2 Cin) from the per-phase matrix above (transposed conv); Cin must be a multiple of 32 */
+int vb_codec_conv_tc(float* d_y, const float* d_x, const void* d_w_tiles, const float* d_bias, const float* d_resid,
+                     const float* d_scale, const float* d_ctx, const float* d_act_a, const float* d_act_ib, int epilogue,
+                     int act_in, int B, int Cin, int Cout, int T, int ksize, int dilation, void* stream);
+int vb_codec_convtr_tc(float* d_y, const float* d_x, const void* d_w_tiles, const float* d_bias, const float* d_ctx,
+                       const float* d_act_a, const float* d_act_ib, int act_in, int B, int Cin, int Cout, int T, int stride,
+                       void* stream);
 int vb_codec_cache_update(float* d_cache, const float* d_x, const float* d_act_a, const float* d_act_ib, int act_in, int B,
                           int C, int L, int pad, void* stream);
 int vb_codec_dwconv(float* d_y, const float* d_x, const float* d_w, const float* d_bias, const float* d_ctx, int B, int C,

@@ -38,11 +38,18 @@ struct SnacGemmParams {
   const float* resid;
   const float* noise;
   const float* alpha_out;
-  int kind;      // 0 pointwise conv, 1 transposed conv (grid.z = phase)
-  int epi;       // pointwise: 0 plain, 1 + resid, 2 noise block
+  int kind;      // 0 pointwise conv, 1 transposed conv (grid.z = phase), 2 causal conv with ksize taps (K = ksize * Cin, tap-major)
+  int epi;       // 0 plain, 1 + resid, 2 noise block, 3 resid + scale[m] v, 4 GELU, 5 SiLU, 6 resid * v, 7 clamp(-1, 1)
   int B, Cin, Cout, T, K;
   int n_lo, nr, n_total;
   int s, pad;
+  // streaming codecs (codec.cu): left context instead of zeros, input activation in the B-operand fetch
+  const float* ctx;      // kind 2: [B][Cin][(ksize-1) dil]; kind 1: [B][Cin][1]; NULL = zeros.  Holds ACTIVATED values
+  const float* act_a;    // SnakeBeta tables per input channel (act_in == 2)
+  const float* act_ib;
+  const float* scale;    // epi 3
+  int act_in;            // 0 none, 1 ELU, 2 SnakeBeta
+  int ksize, dil;        // kind 2
 };
 
 __device__ __forceinline__ float snake_tc(float x, float alpha) {
@@ -138,14 +145,32 @@ __global__ void __launch_bounds__(SM_THREADS, 1) snac_gemm_tf32x3_kernel(const S
       const int sw = j & 7;
       // software-pipelined: the 32 loads of this group's NEXT stage are in flight while the current one is split
       // and stored
+      const int ctx_pad = p.kind == 2 ? (p.ksize - 1) * p.dil : 1;
       auto fetch = [&](int it, float (&v)[SM_BLOCK_K]) {
         const int kbase = it * SM_BLOCK_K;
-        const int tap = (p.kind == 1 && kbase >= p.Cin) ? 1 : 0;
-        const int ti = n - tap;
+        const int tap = p.kind == 2 ? kbase / p.Cin : ((p.kind == 1 && kbase >= p.Cin) ? 1 : 0);
+        const int cb = kbase - tap * p.Cin;                 // first input channel of this k-block
+        const int ti = n - (p.kind == 2 ? (p.ksize - 1 - tap) * p.dil : tap);
         const bool ok = it < num_kb && colok && ti >= 0 && ti < p.T;
-        const float* src = xb + static_cast<size_t>(kbase - tap * p.Cin) * p.T + ti;
+        if (ok || !(p.ctx && it < num_kb && colok && ti < 0)) {
+          const float* src = xb + static_cast<size_t>(cb) * p.T + ti;
 #pragma unroll
-        for (int kk = 0; kk < SM_BLOCK_K; ++kk) v[kk] = ok ? __ldg(src + static_cast<size_t>(kk) * p.T) : 0.f;
+          for (int kk = 0; kk < SM_BLOCK_K; ++kk) v[kk] = ok ? __ldg(src + static_cast<size_t>(kk) * p.T) : 0.f;
+          if (ok && p.act_in == 2) {
+#pragma unroll
+            for (int kk = 0; kk < SM_BLOCK_K; ++kk) {
+              const float sn = sinf(v[kk] * __ldg(&p.act_a[cb + kk]));
+              v[kk] += __ldg(&p.act_ib[cb + kk]) * (sn * sn);
+            }
+          } else if (ok && p.act_in == 1) {
+#pragma unroll
+            for (int kk = 0; kk < SM_BLOCK_K; ++kk) v[kk] = v[kk] > 0.f ? v[kk] : expm1f(v[kk]);
+          }
+        } else {                                            // left context of the previous chunk (already activated)
+          const float* src = p.ctx + (static_cast<size_t>(b) * p.Cin + cb) * ctx_pad + (ctx_pad + ti);
+#pragma unroll
+          for (int kk = 0; kk < SM_BLOCK_K; ++kk) v[kk] = __ldg(src + static_cast<size_t>(kk) * ctx_pad);
+        }
       };
       auto store = [&](int it, const float (&v)[SM_BLOCK_K]) {
         const int s = it % SM_STAGES;
@@ -194,7 +219,9 @@ __global__ void __launch_bounds__(SM_THREADS, 1) snac_gemm_tf32x3_kernel(const S
     // the batch is finished and stored.
     const float bias_l = (p.bias && lane < rows) ? __ldg(&p.bias[m_base + lane]) : 0.f;
     const float alpha_l = (p.alpha_out && lane < rows) ? __ldg(&p.alpha_out[m_base + lane]) : 1.f;
-    const float* e = p.epi == 1 ? p.resid : p.x;
+    const float scale_l = (p.epi == 3 && lane < rows) ? __ldg(&p.scale[m_base + lane]) : 1.f;
+    const float* e = (p.epi == 1 || p.epi == 3 || p.epi == 6) ? p.resid : p.x;
+    const bool need_ext = p.epi == 1 || p.epi == 2 || p.epi == 3 || p.epi == 6;
     mbar_wait(tmem_full, 0);          // all MMAs done: the accumulator is complete and the ring is idle
     tc_fence_after();
     if (warp == 2 && lane == 0 && trace_block0()) trace_mark(64);
@@ -225,16 +252,25 @@ __global__ void __launch_bounds__(SM_THREADS, 1) snac_gemm_tf32x3_kernel(const S
         float ext[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          ext[i] = (p.epi != 0 && ok && r0 + i < rows) ? __ldcg(e + obase + static_cast<size_t>(r0 + i) * Tout) : 0.f;
+          ext[i] = (need_ext && ok && r0 + i < rows) ? __ldcg(e + obase + static_cast<size_t>(r0 + i) * Tout) : 0.f;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int r = r0 + i;
           const float bias_r = __shfl_sync(0xffffffffu, bias_l, r & 31);
           const float alpha_r = __shfl_sync(0xffffffffu, alpha_l, r & 31);
+          const float scale_r = __shfl_sync(0xffffffffu, scale_l, r & 31);
           if (ok && r < rows) {
             float val = st[r * 33 + lane] + bias_r;
-            if (p.epi == 1) val += ext[i];
-            else if (p.epi == 2) val = ext[i] + nz * val;
+            switch (p.epi) {
+              case 1: val += ext[i]; break;
+              case 2: val = ext[i] + nz * val; break;
+              case 3: val = ext[i] + scale_r * val; break;
+              case 4: val = 0.5f * val * (1.f + erff(val * 0.70710678118654752f)); break;
+              case 5: val = val / (1.f + expf(-val)); break;
+              case 6: val = ext[i] * val; break;
+              case 7: val = fminf(1.f, fmaxf(-1.f, val)); break;
+              default: break;
+            }
             if (p.alpha_out) val = snake_tc(val, alpha_r);
             p.y[obase + static_cast<size_t>(r) * Tout] = val;
           }
@@ -347,6 +383,45 @@ int vb_snac_convtr_tc(float* d_y, const float* d_x, const void* d_w_tiles, const
   p.x = d_x; p.y = d_y; p.bias = d_bias; p.alpha_out = d_alpha_out;
   p.kind = 1; p.epi = 0; p.B = B; p.Cin = Cin; p.Cout = Cout; p.T = T; p.K = 2 * Cin;
   p.n_lo = n_lo; p.nr = n_hi - n_lo; p.n_total = B * (n_hi - n_lo); p.s = stride; p.pad = pad;
+  return launch_snac_gemm(p, stride, static_cast<cudaStream_t>(stream));
+}
+
+// ---- streaming codec stages on the same kernel (codec.cu holds the fp32 SIMT forms with identical arguments) ----
+int vb_codec_conv_tc(float* d_y, const float* d_x, const void* d_w_tiles, const float* d_bias, const float* d_resid,
+                     const float* d_scale, const float* d_ctx, const float* d_act_a, const float* d_act_ib, int epilogue,
+                     int act_in, int B, int Cin, int Cout, int T, int ksize, int dilation, void* stream) {
+  VB_CHECK_ARG(d_y && d_x && d_w_tiles, "vb_codec_conv_tc: null pointer");
+  VB_CHECK_ARG(epilogue >= 0 && epilogue <= 6 && act_in >= 0 && act_in <= 2, "vb_codec_conv_tc: epilogue %d / activation %d",
+               epilogue, act_in);
+  VB_CHECK_ARG((epilogue != 1 && epilogue != 2 && epilogue != 5) || d_resid, "vb_codec_conv_tc: this epilogue needs d_resid");
+  VB_CHECK_ARG(epilogue != 2 || d_scale, "vb_codec_conv_tc: LayerScale epilogue needs d_scale");
+  VB_CHECK_ARG(act_in != 2 || (d_act_a && d_act_ib), "vb_codec_conv_tc: SnakeBeta needs its two per-channel tables");
+  VB_CHECK_ARG(ksize >= 1 && dilation >= 1 && Cin % SM_BLOCK_K == 0, "vb_codec_conv_tc: Cin must be a multiple of %d", SM_BLOCK_K);
+  if (B <= 0 || T <= 0) return 0;
+  // codec.cu epilogue codes -> this kernel's: 0 plain, 1 resid, 2 scale_resid, 3 gelu, 4 silu, 5 mul, 6 clamp
+  static const int epi_map[7] = {0, 1, 3, 4, 5, 6, 7};
+  SnacGemmParams p = {};
+  p.w_tiles = static_cast<const uint8_t*>(d_w_tiles);
+  p.x = d_x; p.y = d_y; p.bias = d_bias; p.resid = d_resid; p.scale = d_scale; p.ctx = d_ctx; p.act_a = d_act_a; p.act_ib = d_act_ib;
+  p.kind = ksize == 1 ? 0 : 2; p.epi = epi_map[epilogue]; p.act_in = act_in; p.ksize = ksize; p.dil = dilation;
+  p.B = B; p.Cin = Cin; p.Cout = Cout; p.T = T; p.K = Cin * ksize;
+  p.n_lo = 0; p.nr = T; p.n_total = B * T; p.s = 1; p.pad = 0;
+  return launch_snac_gemm(p, 1, static_cast<cudaStream_t>(stream));
+}
+
+int vb_codec_convtr_tc(float* d_y, const float* d_x, const void* d_w_tiles, const float* d_bias, const float* d_ctx,
+                       const float* d_act_a, const float* d_act_ib, int act_in, int B, int Cin, int Cout, int T, int stride,
+                       void* stream) {
+  VB_CHECK_ARG(d_y && d_x && d_w_tiles, "vb_codec_convtr_tc: null pointer");
+  VB_CHECK_ARG(stride >= 1 && Cin % SM_BLOCK_K == 0 && act_in >= 0 && act_in <= 2, "vb_codec_convtr_tc: Cin must be a multiple of %d",
+               SM_BLOCK_K);
+  VB_CHECK_ARG(act_in != 2 || (d_act_a && d_act_ib), "vb_codec_convtr_tc: SnakeBeta needs its two per-channel tables");
+  if (B <= 0 || T <= 0) return 0;
+  SnacGemmParams p = {};
+  p.w_tiles = static_cast<const uint8_t*>(d_w_tiles);
+  p.x = d_x; p.y = d_y; p.bias = d_bias; p.ctx = d_ctx; p.act_a = d_act_a; p.act_ib = d_act_ib;
+  p.kind = 1; p.epi = 0; p.act_in = act_in; p.B = B; p.Cin = Cin; p.Cout = Cout; p.T = T; p.K = 2 * Cin;
+  p.n_lo = 0; p.nr = T; p.n_total = B * T; p.s = stride; p.pad = 0;       // causal: output n s + r, inputs n and n - 1
   return launch_snac_gemm(p, stride, static_cast<cudaStream_t>(stream));
 }
 

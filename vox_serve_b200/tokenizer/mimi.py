@@ -22,6 +22,7 @@ import torch
 
 from .. import ops
 from .._lib import VoxB200Error, call
+from . import _tc
 
 F32 = torch.float32
 
@@ -171,14 +172,38 @@ class MimiDecoder:
                 w[f"d{idx}.w1"], w[f"d{idx}.b1"] = w1.reshape(w1.shape[0], -1), f(p + "block.1.conv.conv.bias")
                 w[f"d{idx}.w3"], w[f"d{idx}.b3"] = w3.reshape(w3.shape[0], -1), f(p + "block.3.conv.conv.bias")
         self.w = {k: v.contiguous().to(dev) for k, v in w.items()}
+        # tensor-core copies (tf32 hi/lo tiles, csrc/snac_mma.cu) of the wide convolutions: key -> packed tiles
+        self.tc: Dict[str, torch.Tensor] = {}
+        kinds = {idx: kd for kd, idx in self.layout}
+        for k, v in self.w.items():
+            t = None
+            if k in ("rvq_first.proj", "rvq_rest.proj") or (k[0] == "t" and k.split(".")[-1] in ("in", "out", "l1", "l2")):
+                t = _tc.pack_conv(v, v.shape[1], 1)
+            elif k[0] == "d" and k.endswith((".w", ".w1", ".w3")):
+                kind = kinds[int(k[1:].split(".")[0])]
+                if kind == "convtr":
+                    t = _tc.pack_convtr(v, v.shape[2] // 2)
+                else:
+                    ks = {"conv_in": cfg.kernel_size, "conv_out": cfg.last_kernel_size}.get(
+                        kind, cfg.residual_kernel_size if k.endswith(".w1") else 1)
+                    t = _tc.pack_conv(v, v.shape[1] // ks, ks)
+            if t is not None:
+                self.tc[k] = t
         self.loaded = True
         return self
 
     # ---- kernels ------------------------------------------------------------------------------------------
-    def _conv(self, y, x, wt, bias, B, cin, cout, T, ksize=1, dil=1, epi=0, resid=None, scale=None, elu_in=False):
-        call("vb_mimi_conv", y.data_ptr(), x.data_ptr(), wt.data_ptr(), None if bias is None else bias.data_ptr(),
-             None if resid is None else resid.data_ptr(), None if scale is None else scale.data_ptr(), epi, int(elu_in), B,
-             cin, cout, T, ksize, dil, ops._stream())
+    def _conv(self, y, x, key, bias, B, cin, cout, T, ksize=1, dil=1, epi=0, resid=None, scale=None, elu_in=False):
+        """``key``: name of the weight in self.w; wide layers run on the tcgen05 kernel (zero left context: every chunk is
+        decoded on its own), the rest on the fp32 SIMT kernel."""
+        p = lambda t: None if t is None else t.data_ptr()            # noqa: E731
+        tc = self.tc.get(key)
+        if tc is not None:
+            call("vb_codec_conv_tc", y.data_ptr(), x.data_ptr(), tc.data_ptr(), p(bias), p(resid), p(scale), None, None, None, epi,
+                 int(elu_in), B, cin, cout, T, ksize, dil, ops._stream())
+        else:
+            call("vb_mimi_conv", y.data_ptr(), x.data_ptr(), self.w[key].data_ptr(), p(bias), p(resid), p(scale), epi, int(elu_in), B,
+                 cin, cout, T, ksize, dil, ops._stream())
         return y
 
     @torch.no_grad()
@@ -199,11 +224,11 @@ class MimiDecoder:
         # ---- split RVQ decode: rvq_first(codebook 0) + rvq_rest(codebooks 1..) ----
         z = torch.empty(B, D, T, **e)
         call("vb_mimi_codes_sum", z.data_ptr(), c.data_ptr(), w["codebooks"].data_ptr(), B, K, 0, 1, cfg.bins, D, T, st)
-        x = self._conv(torch.empty(B, C, T, **e), z, w["rvq_first.proj"], None, B, D, C, T)
+        x = self._conv(torch.empty(B, C, T, **e), z, "rvq_first.proj", None, B, D, C, T)
         if K > 1:
             z2 = torch.empty(B, D, T, **e)
             call("vb_mimi_codes_sum", z2.data_ptr(), c.data_ptr(), w["codebooks"].data_ptr(), B, K, 1, K, cfg.bins, D, T, st)
-            x = self._conv(torch.empty(B, C, T, **e), z2, w["rvq_rest.proj"], None, B, D, C, T, epi=1, resid=x)
+            x = self._conv(torch.empty(B, C, T, **e), z2, "rvq_rest.proj", None, B, D, C, T, epi=1, resid=x)
         # ---- learnt channel-wise x2 upsampling (12.5 Hz -> 25 Hz) ----
         s = cfg.upsample_stride
         u = torch.empty(B, C, T * s, **e)
@@ -219,14 +244,14 @@ class MimiDecoder:
             h = torch.empty(B, C, T, **e)
             call("vb_mimi_layernorm", h.data_ptr(), x.data_ptr(), w[f"t{i}.n1w"].data_ptr(), w[f"t{i}.n1b"].data_ptr(), B, C, T,
                  1e-5, st)
-            qkv = self._conv(torch.empty(B, 3 * C, T, **e), h, w[f"t{i}.in"], None, B, C, 3 * C, T)
+            qkv = self._conv(torch.empty(B, 3 * C, T, **e), h, f"t{i}.in", None, B, C, 3 * C, T)
             a = torch.empty(B, C, T, **e)
             call("vb_mimi_attention", a.data_ptr(), qkv.data_ptr(), B, C, H, T, float(cfg.max_period), st)
-            x = self._conv(torch.empty(B, C, T, **e), a, w[f"t{i}.out"], None, B, C, C, T, epi=2, resid=x, scale=w[f"t{i}.s1"])
+            x = self._conv(torch.empty(B, C, T, **e), a, f"t{i}.out", None, B, C, C, T, epi=2, resid=x, scale=w[f"t{i}.s1"])
             call("vb_mimi_layernorm", h.data_ptr(), x.data_ptr(), w[f"t{i}.n2w"].data_ptr(), w[f"t{i}.n2b"].data_ptr(), B, C, T,
                  1e-5, st)
-            m = self._conv(torch.empty(B, Fd, T, **e), h, w[f"t{i}.l1"], None, B, C, Fd, T, epi=3)
-            x = self._conv(torch.empty(B, C, T, **e), m, w[f"t{i}.l2"], None, B, Fd, C, T, epi=2, resid=x, scale=w[f"t{i}.s2"])
+            m = self._conv(torch.empty(B, Fd, T, **e), h, f"t{i}.l1", None, B, C, Fd, T, epi=3)
+            x = self._conv(torch.empty(B, C, T, **e), m, f"t{i}.l2", None, B, Fd, C, T, epi=2, resid=x, scale=w[f"t{i}.s2"])
         if taps is not None:
             taps["transformer_out"] = x
         # ---- SEANet decoder ----
@@ -234,20 +259,25 @@ class MimiDecoder:
         ratios = list(cfg.ratios)
         for kind, idx in self.layout:
             if kind == "conv_in":
-                x = self._conv(torch.empty(B, ch, T, **e), x, w[f"d{idx}.w"], w[f"d{idx}.b"], B, C, ch, T, ksize=cfg.kernel_size)
+                x = self._conv(torch.empty(B, ch, T, **e), x, f"d{idx}.w", w[f"d{idx}.b"], B, C, ch, T, ksize=cfg.kernel_size)
             elif kind == "convtr":
                 r = ratios.pop(0)
                 y = torch.empty(B, ch // 2, T * r, **e)
-                call("vb_mimi_convtr", y.data_ptr(), x.data_ptr(), w[f"d{idx}.w"].data_ptr(), w[f"d{idx}.b"].data_ptr(), 1, B, ch,
-                     ch // 2, T, r, st)
+                tcw = self.tc.get(f"d{idx}.w")
+                if tcw is not None:
+                    call("vb_codec_convtr_tc", y.data_ptr(), x.data_ptr(), tcw.data_ptr(), w[f"d{idx}.b"].data_ptr(), None, None, None,
+                         1, B, ch, ch // 2, T, r, st)
+                else:
+                    call("vb_mimi_convtr", y.data_ptr(), x.data_ptr(), w[f"d{idx}.w"].data_ptr(), w[f"d{idx}.b"].data_ptr(), 1, B, ch,
+                         ch // 2, T, r, st)
                 x, ch, T = y, ch // 2, T * r
             elif kind == "res":
                 hid = ch // cfg.compress
-                h = self._conv(torch.empty(B, hid, T, **e), x, w[f"d{idx}.w1"], w[f"d{idx}.b1"], B, ch, hid, T,
+                h = self._conv(torch.empty(B, hid, T, **e), x, f"d{idx}.w1", w[f"d{idx}.b1"], B, ch, hid, T,
                                ksize=cfg.residual_kernel_size, elu_in=True)
-                x = self._conv(torch.empty(B, ch, T, **e), h, w[f"d{idx}.w3"], w[f"d{idx}.b3"], B, hid, ch, T, epi=1, resid=x,
+                x = self._conv(torch.empty(B, ch, T, **e), h, f"d{idx}.w3", w[f"d{idx}.b3"], B, hid, ch, T, epi=1, resid=x,
                                elu_in=True)
             else:
-                x = self._conv(torch.empty(B, 1, T, **e), x, w[f"d{idx}.w"], w[f"d{idx}.b"], B, ch, 1, T,
+                x = self._conv(torch.empty(B, 1, T, **e), x, f"d{idx}.w", w[f"d{idx}.b"], B, ch, 1, T,
                                ksize=cfg.last_kernel_size, elu_in=True)
         return x

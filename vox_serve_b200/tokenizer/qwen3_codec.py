@@ -23,6 +23,7 @@ import torch
 
 from .. import ops
 from .._lib import VoxB200Error, call
+from . import _tc
 from .base import DecoderCache
 
 F32 = torch.float32
@@ -146,6 +147,25 @@ class Qwen3TTSDecoder:
         w["d.out.a"], w["d.out.ib"] = snake(f"decoder.{n}.")
         w["d.out.w"], w["d.out.b"] = f(f"decoder.{n + 1}.conv.weight").flatten(1), f(f"decoder.{n + 1}.conv.bias")
         self.w = {k: v.contiguous().to(dev) for k, v in w.items()}
+        # tensor-core copies (tf32 hi/lo tiles) of the wide convolutions: key -> packed tiles
+        convs = {"rvq_first.proj": 1, "rvq_rest.proj": 1, "pre_conv.w": 3, "t.input_proj.w": 1, "t.output_proj.w": 1, "d.in.w": 7,
+                 "d.out.w": 7}
+        for i in range(cfg.num_hidden_layers):
+            convs.update({f"t{i}.{k}": 1 for k in ("qkv", "o", "gate", "up", "down")})
+        for j in range(len(cfg.upsampling_ratios)):
+            convs.update({f"u{j}.pw1.w": 1, f"u{j}.pw2.w": 1})
+        for bi in range(len(cfg.upsample_rates)):
+            for u in range(3):
+                convs.update({f"d{bi}.{u}.w1": 7, f"d{bi}.{u}.w2": 1})
+        self.tc: Dict[str, torch.Tensor] = {}
+        for k, ks in convs.items():
+            t = _tc.pack_conv(self.w[k], self.w[k].shape[1] // ks, ks)
+            if t is not None:
+                self.tc[k] = t
+        for k in [f"u{j}.tr.w" for j in range(len(cfg.upsampling_ratios))] + [f"d{bi}.tr.w" for bi in range(len(cfg.upsample_rates))]:
+            t = _tc.pack_convtr(self.w[k], self.w[k].shape[2] // 2)
+            if t is not None:
+                self.tc[k] = t
         return self
 
     # ---- cache --------------------------------------------------------------------------------------------
@@ -168,11 +188,23 @@ class Qwen3TTSDecoder:
         return c
 
     # ---- kernels ------------------------------------------------------------------------------------------
-    def _conv(self, x, wt, bias, B, cin, cout, T, ksize=1, dil=1, epi=0, resid=None, scale=None, ctx=None, act=0, a=None, ib=None):
+    def _conv(self, x, key, bias, B, cin, cout, T, ksize=1, dil=1, epi=0, resid=None, scale=None, ctx=None, act=0, a=None, ib=None):
+        """``key``: name of the weight in self.w; the tcgen05 kernel takes the layer when a packed copy exists."""
         y = torch.empty(B, cout, T, dtype=F32, device=self.device)
         p = lambda t: None if t is None else t.data_ptr()            # noqa: E731
-        call("vb_codec_conv", y.data_ptr(), x.data_ptr(), wt.data_ptr(), p(bias), p(resid), p(scale), p(ctx), p(a), p(ib), epi,
-             act, B, cin, cout, T, ksize, dil, ops._stream())
+        tc = self.tc.get(key)
+        call("vb_codec_conv_tc" if tc is not None else "vb_codec_conv", y.data_ptr(), x.data_ptr(),
+             (tc if tc is not None else self.w[key]).data_ptr(), p(bias), p(resid), p(scale), p(ctx), p(a), p(ib), epi, act, B, cin,
+             cout, T, ksize, dil, ops._stream())
+        return y
+
+    def _convtr(self, x, key, bias, B, cin, cout, T, stride, ctx=None, act=0, a=None, ib=None):
+        y = torch.empty(B, cout, T * stride, dtype=F32, device=self.device)
+        p = lambda t: None if t is None else t.data_ptr()            # noqa: E731
+        tc = self.tc.get(key)
+        call("vb_codec_convtr_tc" if tc is not None else "vb_codec_convtr", y.data_ptr(), x.data_ptr(),
+             (tc if tc is not None else self.w[key]).data_ptr(), p(bias), p(ctx), p(a), p(ib), act, B, cin, cout, T, stride,
+             ops._stream())
         return y
 
     def _cache_update(self, cache, x, B, C, L, act=0, a=None, ib=None):
@@ -200,39 +232,36 @@ class Qwen3TTSDecoder:
         dq = Cb // 2
         z = torch.empty(B, dq, T, **e)
         call("vb_mimi_codes_sum", z.data_ptr(), c.data_ptr(), w["codebooks"].data_ptr(), B, K, 0, 1, cfg.codebook_size, dq, T, st)
-        h = self._conv(z, w["rvq_first.proj"], None, B, dq, Cb, T)
+        h = self._conv(z, "rvq_first.proj", None, B, dq, Cb, T)
         z2 = torch.empty(B, dq, T, **e)
         call("vb_mimi_codes_sum", z2.data_ptr(), c.data_ptr(), w["codebooks"].data_ptr(), B, K, 1, K, cfg.codebook_size, dq, T, st)
-        h = self._conv(z2, w["rvq_rest.proj"], None, B, dq, Cb, T, epi=1, resid=h)
+        h = self._conv(z2, "rvq_rest.proj", None, B, dq, Cb, T, epi=1, resid=h)
         # ---- pre_conv (k3, cache 2) ----
-        x = self._conv(h, w["pre_conv.w"], w["pre_conv.b"], B, Cb, Lt, T, ksize=3, ctx=cache.pre_conv_cache)
+        x = self._conv(h, "pre_conv.w", w["pre_conv.b"], B, Cb, Lt, T, ksize=3, ctx=cache.pre_conv_cache)
         self._cache_update(cache.pre_conv_cache, h, B, Cb, T)
         # ---- transformer ----
         H, Hkv, D, I = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim, cfg.intermediate_size
-        x = self._conv(x, w["t.input_proj.w"], w["t.input_proj.b"], B, Lt, Hd, T)
+        x = self._conv(x, "t.input_proj.w", w["t.input_proj.b"], B, Lt, Hd, T)
         for i in range(cfg.num_hidden_layers):
             n = torch.empty(B, Hd, T, **e)
             call("vb_codec_rmsnorm", n.data_ptr(), x.data_ptr(), w[f"t{i}.n1"].data_ptr(), B, Hd, T, cfg.rms_norm_eps, st)
-            qkv = self._conv(n, w[f"t{i}.qkv"], None, B, Hd, (H + 2 * Hkv) * D, T)
+            qkv = self._conv(n, f"t{i}.qkv", None, B, Hd, (H + 2 * Hkv) * D, T)
             a = torch.empty(B, H * D, T, **e)
             lc = cache.attention_cache[:, i]                # one layer of [B, layers, Hkv, W, 2 D]: items stride(0) apart
             call("vb_codec_attn_chunk", a.data_ptr(), qkv.data_ptr(), lc.data_ptr(), lc.stride(0), cache.position_offset.data_ptr(),
                  B, H, Hkv, D, T, cfg.sliding_window, float(cfg.rope_theta), st)
-            x = self._conv(a, w[f"t{i}.o"], None, B, H * D, Hd, T, epi=2, resid=x, scale=w[f"t{i}.s1"])
+            x = self._conv(a, f"t{i}.o", None, B, H * D, Hd, T, epi=2, resid=x, scale=w[f"t{i}.s1"])
             call("vb_codec_rmsnorm", n.data_ptr(), x.data_ptr(), w[f"t{i}.n2"].data_ptr(), B, Hd, T, cfg.rms_norm_eps, st)
-            g = self._conv(n, w[f"t{i}.gate"], None, B, Hd, I, T, epi=4)
-            m = self._conv(n, w[f"t{i}.up"], None, B, Hd, I, T, epi=5, resid=g)
-            x = self._conv(m, w[f"t{i}.down"], None, B, I, Hd, T, epi=2, resid=x, scale=w[f"t{i}.s2"])
+            g = self._conv(n, f"t{i}.gate", None, B, Hd, I, T, epi=4)
+            m = self._conv(n, f"t{i}.up", None, B, Hd, I, T, epi=5, resid=g)
+            x = self._conv(m, f"t{i}.down", None, B, I, Hd, T, epi=2, resid=x, scale=w[f"t{i}.s2"])
         cache.position_offset.add_(T)
         n = torch.empty(B, Hd, T, **e)
         call("vb_codec_rmsnorm", n.data_ptr(), x.data_ptr(), w["t.norm"].data_ptr(), B, Hd, T, cfg.rms_norm_eps, st)
-        x = self._conv(n, w["t.output_proj.w"], w["t.output_proj.b"], B, Hd, Lt, T)
+        x = self._conv(n, "t.output_proj.w", w["t.output_proj.b"], B, Hd, Lt, T)
         # ---- upsampling: ConvTranspose (kernel == stride) + ConvNeXt ----
         for j, f in enumerate(cfg.upsampling_ratios):
-            y = torch.empty(B, Lt, T * f, **e)
-            call("vb_codec_convtr", y.data_ptr(), x.data_ptr(), w[f"u{j}.tr.w"].data_ptr(), w[f"u{j}.tr.b"].data_ptr(), None, None,
-                 None, 0, B, Lt, Lt, T, f, st)
-            x, T = y, T * f
+            x, T = self._convtr(x, f"u{j}.tr.w", w[f"u{j}.tr.b"], B, Lt, Lt, T, f), T * f
             uc = cache.upsample_conv_caches[j]
             d = torch.empty(B, Lt, T, **e)
             call("vb_codec_dwconv", d.data_ptr(), x.data_ptr(), w[f"u{j}.dw.w"].data_ptr(), w[f"u{j}.dw.b"].data_ptr(), uc.data_ptr(),
@@ -241,29 +270,27 @@ class Qwen3TTSDecoder:
             ln = torch.empty(B, Lt, T, **e)
             call("vb_mimi_layernorm", ln.data_ptr(), d.data_ptr(), w[f"u{j}.ln.w"].data_ptr(), w[f"u{j}.ln.b"].data_ptr(), B, Lt, T,
                  1e-6, st)
-            m = self._conv(ln, w[f"u{j}.pw1.w"], w[f"u{j}.pw1.b"], B, Lt, 4 * Lt, T, epi=3)
-            x = self._conv(m, w[f"u{j}.pw2.w"], w[f"u{j}.pw2.b"], B, 4 * Lt, Lt, T, epi=2, resid=x, scale=w[f"u{j}.gamma"])
+            m = self._conv(ln, f"u{j}.pw1.w", w[f"u{j}.pw1.b"], B, Lt, 4 * Lt, T, epi=3)
+            x = self._conv(m, f"u{j}.pw2.w", w[f"u{j}.pw2.b"], B, 4 * Lt, Lt, T, epi=2, resid=x, scale=w[f"u{j}.gamma"])
         # ---- decoder ----
         dc, ci, ch = cache.decoder_conv_caches, 0, cfg.decoder_dim
-        y = self._conv(x, w["d.in.w"], w["d.in.b"], B, Lt, ch, T, ksize=7, ctx=dc[ci])
+        y = self._conv(x, "d.in.w", w["d.in.b"], B, Lt, ch, T, ksize=7, ctx=dc[ci])
         self._cache_update(dc[ci], x, B, Lt, T)
         x, ci = y, ci + 1
         for bi, rate in enumerate(cfg.upsample_rates):
             a_, ib_ = w[f"d{bi}.a"], w[f"d{bi}.ib"]
             tc = cache.transconv_caches[bi]
-            y = torch.empty(B, ch // 2, T * rate, **e)
-            call("vb_codec_convtr", y.data_ptr(), x.data_ptr(), w[f"d{bi}.tr.w"].data_ptr(), w[f"d{bi}.tr.b"].data_ptr(), tc.data_ptr(),
-                 a_.data_ptr(), ib_.data_ptr(), 2, B, ch, ch // 2, T, rate, st)
+            y = self._convtr(x, f"d{bi}.tr.w", w[f"d{bi}.tr.b"], B, ch, ch // 2, T, rate, ctx=tc, act=2, a=a_, ib=ib_)
             self._cache_update(tc, x, B, ch, T, act=2, a=a_, ib=ib_)
             x, ch, T = y, ch // 2, T * rate
             for u, dil in enumerate((1, 3, 9)):
                 a1, ib1, a2, ib2 = (w[f"d{bi}.{u}.{k}"] for k in ("a1", "ib1", "a2", "ib2"))
-                r = self._conv(x, w[f"d{bi}.{u}.w1"], w[f"d{bi}.{u}.b1"], B, ch, ch, T, ksize=7, dil=dil, ctx=dc[ci], act=2, a=a1,
+                r = self._conv(x, f"d{bi}.{u}.w1", w[f"d{bi}.{u}.b1"], B, ch, ch, T, ksize=7, dil=dil, ctx=dc[ci], act=2, a=a1,
                                ib=ib1)
                 self._cache_update(dc[ci], x, B, ch, T, act=2, a=a1, ib=ib1)
                 ci += 1
-                x = self._conv(r, w[f"d{bi}.{u}.w2"], w[f"d{bi}.{u}.b2"], B, ch, ch, T, epi=1, resid=x, act=2, a=a2, ib=ib2)
-        wav = self._conv(x, w["d.out.w"], w["d.out.b"], B, ch, 1, T, ksize=7, epi=6, ctx=dc[ci], act=2, a=w["d.out.a"],
+                x = self._conv(r, f"d{bi}.{u}.w2", w[f"d{bi}.{u}.b2"], B, ch, ch, T, epi=1, resid=x, act=2, a=a2, ib=ib2)
+        wav = self._conv(x, "d.out.w", w["d.out.b"], B, ch, 1, T, ksize=7, epi=6, ctx=dc[ci], act=2, a=w["d.out.a"],
                          ib=w["d.out.ib"])
         self._cache_update(dc[ci], x, B, ch, T, act=2, a=w["d.out.a"], ib=w["d.out.ib"])
         return wav, cache
