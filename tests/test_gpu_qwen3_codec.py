@@ -11,7 +11,9 @@ import torch
 from oracle import qwen3_codec as oq
 
 pytestmark = pytest.mark.gpu
-REL_TOL = 5e-4        # fp32 pipeline of ~90 contractions with sin / exp activations (measured ~1e-5)
+REL_TOL = 5e-4        # fp32 pipeline of ~90 contractions with sin / exp activations (fp32 SIMT kernels: measured ~1e-5)
+REL_TOL_TC = 1e-3     # layers >= 64 channels wide run on the tcgen05 tf32 hi/lo kernel (~2e-5 per layer; measured 8e-4 after
+#                       ~60 such layers with SnakeBeta between them): the waveform contract of north_star is 1e-3
 
 
 def _decoder(cfg, seed):
@@ -82,7 +84,8 @@ def test_qwen3_codec_deployed_head_geometry_matches_oracle(B, T):
         ref, ocache = oq.forward_chunk(sd, cfg, codes, ocache)
         wav, cache = dec.decode_chunk(codes.cuda(), cache)
         assert wav.shape == ref.shape == (B, 1, T * 1920)
-        assert _rel(wav.cpu(), ref) < REL_TOL, _rel(wav.cpu(), ref)
+        assert dec.tc, "this configuration must exercise the tensor-core convolutions"
+        assert _rel(wav.cpu(), ref) < REL_TOL_TC, _rel(wav.cpu(), ref)
 
 
 def test_qwen3_codec_rejects_what_it_cannot_decode():

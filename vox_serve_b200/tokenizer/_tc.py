@@ -1,5 +1,5 @@
 """tcgen05 tf32 hi/lo weight packing shared by the codec decoders (Mimi, Qwen3 codec): a convolution whose input width is a
-multiple of 32 channels and at least ``VB_CODEC_TC_MIN_CIN`` (128) runs on ``snac_gemm_tf32x3_kernel`` (csrc/snac_mma.cu);
+multiple of 32 channels and at least ``VB_CODEC_TC_MIN_CIN`` (64) runs on ``snac_gemm_tf32x3_kernel`` (csrc/snac_mma.cu);
 narrower layers (test-sized configurations, the last SEANet / decoder blocks) stay on the fp32 SIMT kernels with the same
 arguments.  ``VB_CODEC_FP32=1`` keeps everything on the SIMT kernels."""
 from __future__ import annotations
@@ -18,7 +18,7 @@ def tc_enabled() -> bool:
 
 
 def min_cin() -> int:
-    return int(os.environ.get("VB_CODEC_TC_MIN_CIN", "128"))
+    return int(os.environ.get("VB_CODEC_TC_MIN_CIN", "64"))
 
 
 def pack_conv(w: torch.Tensor, cin: int, ksize: int) -> Optional[torch.Tensor]:
