@@ -159,11 +159,11 @@ class Qwen3TTSDecoder:
                 convs.update({f"d{bi}.{u}.w1": 7, f"d{bi}.{u}.w2": 1})
         self.tc: Dict[str, torch.Tensor] = {}
         for k, ks in convs.items():
-            t = _tc.pack_conv(self.w[k], self.w[k].shape[1] // ks, ks)
+            t = _tc.pack_conv(self.w[k], self.w[k].shape[1] // ks, ks, min_cin=96)
             if t is not None:
                 self.tc[k] = t
         for k in [f"u{j}.tr.w" for j in range(len(cfg.upsampling_ratios))] + [f"d{bi}.tr.w" for bi in range(len(cfg.upsample_rates))]:
-            t = _tc.pack_convtr(self.w[k], self.w[k].shape[2] // 2)
+            t = _tc.pack_convtr(self.w[k], self.w[k].shape[2] // 2, min_cin=96)
             if t is not None:
                 self.tc[k] = t
         return self
