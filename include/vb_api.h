@@ -393,6 +393,9 @@ int vb_codec_conv_tc(float* d_y, const float* d_x, const void* d_w_tiles, const 
 int vb_codec_convtr_tc(float* d_y, const float* d_x, const void* d_w_tiles, const float* d_bias, const float* d_ctx,
                        const float* d_act_a, const float* d_act_ib, int act_in, int B, int Cin, int Cout, int T, int stride,
                        void* stream);
+/* y = act(x) over [B][C][T] (what the tensor-core calls take as input when the layer has an input activation) */
+int vb_codec_activate(float* d_y, const float* d_x, const float* d_act_a, const float* d_act_ib, int act_in, int B, int C, int T,
+                      void* stream);
 int vb_codec_cache_update(float* d_cache, const float* d_x, const float* d_act_a, const float* d_act_ib, int act_in, int B,
                           int C, int L, int pad, void* stream);
 int vb_codec_dwconv(float* d_y, const float* d_x, const float* d_w, const float* d_bias, const float* d_ctx, int B, int C,

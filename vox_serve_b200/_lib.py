@@ -83,6 +83,7 @@ SIGNATURES = {
     "vb_codec_convtr": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_codec_conv_tc": (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_codec_convtr_tc": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "vb_codec_activate": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
     "vb_codec_cache_update": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_codec_dwconv": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     "vb_codec_rmsnorm": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P]),

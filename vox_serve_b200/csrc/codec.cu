@@ -104,6 +104,17 @@ __global__ void codec_cache_update_kernel(float* __restrict__ cache, const float
   }
 }
 
+// y = act(x) elementwise over [B][C][T]: the tensor-core convolutions take pre-activated input (a k-tap convolution would
+// otherwise evaluate SnakeBeta k times per element in its operand loaders, which made them loader-bound)
+__global__ void __launch_bounds__(256) codec_activate_kernel(float* __restrict__ y, const float* __restrict__ x,
+                                                             const float* __restrict__ act_a, const float* __restrict__ act_ib,
+                                                             int act, int C, int T) {
+  const int c = blockIdx.x % C;
+  const size_t row = static_cast<size_t>(blockIdx.x) * T;
+  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < T; t += gridDim.y * blockDim.x)
+    y[row + t] = codec_act(x[row + t], act, act_a, act_ib, c);
+}
+
 // depthwise causal Conv1d (groups = C, kernel ksize, dilation 1) with left context: the ConvNeXt block's dwconv
 __global__ void __launch_bounds__(256) codec_dwconv_kernel(float* __restrict__ y, const float* __restrict__ x,
                                                            const float* __restrict__ w, const float* __restrict__ bias,
@@ -301,6 +312,17 @@ int vb_codec_cache_update(float* d_cache, const float* d_x, const float* d_act_a
   if (B <= 0 || C <= 0) return 0;
   codec_cache_update_kernel<<<(B * C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_cache, d_x, d_act_a, d_act_ib,
                                                                                               act_in, B, C, L, pad);
+  VB_CHECK_LAUNCH();
+  return 0;
+}
+
+int vb_codec_activate(float* d_y, const float* d_x, const float* d_act_a, const float* d_act_ib, int act_in, int B, int C, int T,
+                      void* stream) {
+  VB_CHECK_ARG(d_y && d_x && act_in >= 0 && act_in <= 2, "vb_codec_activate: bad arguments");
+  VB_CHECK_ARG(act_in != CA_SNAKE || (d_act_a && d_act_ib), "vb_codec_activate: SnakeBeta needs its two per-channel tables");
+  if (B <= 0 || C <= 0 || T <= 0) return 0;
+  const int gy = T >= 4096 ? 8 : (T >= 1024 ? 2 : 1);
+  codec_activate_kernel<<<dim3(B * C, gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_y, d_x, d_act_a, d_act_ib, act_in, C, T);
   VB_CHECK_LAUNCH();
   return 0;
 }

@@ -193,6 +193,8 @@ class Qwen3TTSDecoder:
         y = torch.empty(B, cout, T, dtype=F32, device=self.device)
         p = lambda t: None if t is None else t.data_ptr()            # noqa: E731
         tc = self.tc.get(key)
+        if tc is not None and act:
+            x, act, a, ib = self._activate(x, act, a, ib, B, cin, T), 0, None, None
         call("vb_codec_conv_tc" if tc is not None else "vb_codec_conv", y.data_ptr(), x.data_ptr(),
              (tc if tc is not None else self.w[key]).data_ptr(), p(bias), p(resid), p(scale), p(ctx), p(a), p(ib), epi, act, B, cin,
              cout, T, ksize, dil, ops._stream())
@@ -202,9 +204,17 @@ class Qwen3TTSDecoder:
         y = torch.empty(B, cout, T * stride, dtype=F32, device=self.device)
         p = lambda t: None if t is None else t.data_ptr()            # noqa: E731
         tc = self.tc.get(key)
+        if tc is not None and act:
+            x, act, a, ib = self._activate(x, act, a, ib, B, cin, T), 0, None, None
         call("vb_codec_convtr_tc" if tc is not None else "vb_codec_convtr", y.data_ptr(), x.data_ptr(),
              (tc if tc is not None else self.w[key]).data_ptr(), p(bias), p(ctx), p(a), p(ib), act, B, cin, cout, T, stride,
              ops._stream())
+        return y
+
+    def _activate(self, x, act, a, ib, B, C, T):
+        """act(x) once, for a tensor-core convolution (its k taps would otherwise each re-evaluate it in the loaders)"""
+        y = torch.empty_like(x)
+        call("vb_codec_activate", y.data_ptr(), x.data_ptr(), a.data_ptr(), ib.data_ptr(), act, B, C, T, ops._stream())
         return y
 
     def _cache_update(self, cache, x, B, C, L, act=0, a=None, ib=None):
