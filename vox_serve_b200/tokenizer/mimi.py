@@ -199,6 +199,10 @@ class MimiDecoder:
         p = lambda t: None if t is None else t.data_ptr()            # noqa: E731
         tc = self.tc.get(key)
         if tc is not None:
+            if elu_in and ksize > 1:       # ELU once, not once per tap in the tensor-core kernel's loaders
+                xa = torch.empty_like(x)
+                call("vb_codec_activate", xa.data_ptr(), x.data_ptr(), None, None, 1, B, cin, T, ops._stream())
+                x, elu_in = xa, False
             call("vb_codec_conv_tc", y.data_ptr(), x.data_ptr(), tc.data_ptr(), p(bias), p(resid), p(scale), None, None, None, epi,
                  int(elu_in), B, cin, cout, T, ksize, dil, ops._stream())
         else:
