@@ -46,9 +46,13 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm
   python tests/prof_gemm.py > $o/${tag}_ncu_gemm.log 2>&1
 echo "ncu gemm exit $?"
 timeout 300 python tests/prof_mimi.py 64 10 > $o/${tag}_mimi_timing.txt 2>&1; cat $o/${tag}_mimi_timing.txt
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:mimi_conv -s 40 -c 6 -o $o/${tag}_mimi_full -f \
-  python tests/prof_mimi.py 64 1 > $o/${tag}_ncu_mimi.log 2>&1
-echo "ncu mimi exit $?"
+timeout 300 python tests/prof_qwen3_codec.py 16 3 > $o/${tag}_qwen3_codec_timing.txt 2>&1; cat $o/${tag}_qwen3_codec_timing.txt
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:snac_gemm_tf32x3 -s 45 -c 4 -o $o/${tag}_codec_tc_full -f \
+  python tests/prof_qwen3_codec.py 16 1 > $o/${tag}_ncu_codec.log 2>&1
+echo "ncu codec (tcgen05 conv kernel) exit $?"
+for b in 64; do timeout 400 python tests/prof_csm.py $b 600 60 2>&1 | grep "^{" > $o/${tag}_csm_b$b.json; done
+for b in 16 32; do timeout 300 python tests/prof_qwen3_tts.py $b 50 60 2>&1 | grep "^{" > $o/${tag}_qwen3_tts_b$b.json; done
+cat $o/${tag}_csm_b64.json $o/${tag}_qwen3_tts_b16.json | cut -c1-300
 for kv in 200 500; do
   timeout 200 python tests/trace_step.py $kv unfused 60 34 > $o/${tag}_trace_kv$kv.txt 2>&1
   head -18 $o/${tag}_trace_kv$kv.txt
