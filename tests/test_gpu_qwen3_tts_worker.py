@@ -92,11 +92,21 @@ def _replay(od, w, prompt, frames, page=16):
 
 @pytest.mark.parametrize("async_mode", [False, True], ids=["sync", "async"])
 def test_qwen3_tts_worker_e2e(async_mode):
+    _serve_and_check((9, 21, 5), 3, async_mode)
+
+
+def test_qwen3_tts_worker_recycles_slots_and_codec_state():
+    """More requests than batch slots: a stream that starts on a recycled slot must see zeroed codec state (attention
+    window, position offset, every conv cache) and its own input_features -- its audio is compared with the oracle codec
+    started from a fresh cache."""
+    _serve_and_check((7, 12, 5, 9, 6), 2, False)
+
+
+def _serve_and_check(lens, max_bs, async_mode):
     from vox_serve_b200.requests import Request
     from vox_serve_b200.scheduler import Scheduler
 
-    lens = (9, 21, 5)
-    worker, od, w, ccfg, csd = _build(seed=11, max_bs=3, max_tokens=max(lens) + 26)
+    worker, od, w, ccfg, csd = _build(seed=11, max_bs=max_bs, max_tokens=max(lens) + 26)
     prompts = _prompts(od, lens)
     sched = Scheduler(worker)
     reqs = [Request(request_id=f"q{i}", prompt=p) for i, p in enumerate(prompts)]
@@ -142,4 +152,4 @@ def test_qwen3_tts_worker_e2e(async_mode):
     print("qwen3-tts worker e2e:", tot, "chunks", n_chunks, "steps", sched.steps, "launches", worker.gpu_launches)
     assert tot["flips"] <= max(2, tot["rows"] // 100), tot
     assert n_chunks >= 2 * len(lens)
-    assert worker.empty_pages.qsize() == worker.max_num_pages and len(worker.free_slots) == 3
+    assert worker.empty_pages.qsize() == worker.max_num_pages and len(worker.free_slots) == max_bs
