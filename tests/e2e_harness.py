@@ -13,16 +13,19 @@ import torch
 from oracle import orpheus as oorph, sampler as osampler, snac as osnac, worker as oworker
 
 
-def build_models(dims, snac_cfg, seed, max_bs, page_size, max_pages, greedy=True, lm_head_scale=8.0, stop_boost=None):
+def build_models(dims, snac_cfg, seed, max_bs, page_size, max_pages, greedy=True, lm_head_scale=8.0, stop_boost=None,
+                 planted=None):
     """stop_boost: scale of the stop id's lm_head row; with it the stop id is NOT masked (it wins the greedy argmax
-    every ~10-20 steps), so the stop / trim / release paths run (orpheus.py:456-466, cuda_graph_worker.py:1176-1277)."""
+    every ~10-20 steps), so the stop / trim / release paths run (orpheus.py:456-466, cuda_graph_worker.py:1176-1277).
+    planted: "confident-model" weights (oracle.orpheus.synth_weights): top-1/top-2 margins far above bf16 noise, so the
+    ids must match with ZERO mismatches."""
     from vox_serve_b200.engine import LlamaDims
     from vox_serve_b200.model.orpheus import OrpheusModel
     from vox_serve_b200.sampling import SamplingConfig
     from vox_serve_b200.tokenizer.snac import SNAC
     from vox_serve_b200.worker import ModelWorker
 
-    weights = oorph.synth_weights(dims, seed=seed, lm_head_scale=lm_head_scale)
+    weights = oorph.synth_weights(dims, seed=seed, lm_head_scale=lm_head_scale, planted=planted)
     if stop_boost is not None:
         weights["lm_head.weight"][dims.stop_token_id] *= stop_boost
     snac_sd = osnac.synth_state_dict(snac_cfg, seed=seed + 1)
@@ -48,7 +51,7 @@ def build_models(dims, snac_cfg, seed, max_bs, page_size, max_pages, greedy=True
 
 
 def run_e2e_parity(prompt_lens=(5, 16, 30, 33), n_tokens=40, seed=3, dims=None, page_size=16, max_pages=128,
-                   noise_seed=1234, stop_boost=None):
+                   noise_seed=1234, stop_boost=None, planted=None):
     from vox_serve_b200.requests import Request
     from vox_serve_b200.scheduler import Scheduler
 
@@ -56,7 +59,7 @@ def run_e2e_parity(prompt_lens=(5, 16, 30, 33), n_tokens=40, seed=3, dims=None, 
     dims.max_tokens = max(prompt_lens) + n_tokens
     snac_cfg = osnac.SnacConfig.tiny()
     max_bs = len(prompt_lens)
-    worker, ow = build_models(dims, snac_cfg, seed, max_bs, page_size, max_pages, stop_boost=stop_boost)
+    worker, ow = build_models(dims, snac_cfg, seed, max_bs, page_size, max_pages, stop_boost=stop_boost, planted=planted)
     g = torch.Generator().manual_seed(21)
     prompts = [torch.randint(10, dims.vocab_size, (n - 5,), generator=g).tolist() for n in prompt_lens]
 
@@ -100,6 +103,7 @@ def run_e2e_parity(prompt_lens=(5, 16, 30, 33), n_tokens=40, seed=3, dims=None, 
         for i in range(len(lm)):
             stats["rows"] += 1
             stats["min_margin"] = min(stats["min_margin"], float(margin[i]))
+            stats["min_margin_ulps"] = min(stats.get("min_margin_ulps", 1e9), float(margin[i] / ulp[i]))
             if int(ow.last_own_ids[i, 0]) != int(forced[i, 0]):
                 stats["id_mismatch"] += 1
                 if margin[i] <= 4 * ulp[i] and int(forced[i, 0]) in torch.topk(pen[i], 3).indices.tolist():
