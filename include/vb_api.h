@@ -111,6 +111,20 @@ int vb_paged_attn(void* d_out, const void* d_q, const void* d_kv, int64_t slab_b
                   int chunk_tokens, float sm_scale, void* d_workspace, size_t workspace_bytes, int grid_ctas,
                   int ws_grid_ctas, int out_xt_tile, void* stream);
 
+/* ---- tiled paged attention for prefill-shaped steps: FlashInferPrefillWrapper.run (flashinfer_utils.py:68-80,
+ * 132; causal=True).  Same inputs and result as vb_paged_attn on a prefill plan, but a Q tile of up to
+ * vb_prefill_attn_tile_rows(n_q, n_kv) consecutive rows of ONE request shares every K/V tile it reads (mma.sync
+ * tensor-core tiles, FlashAttention-2 schedule), so a request's K/V is read once per tile instead of once per row.
+ * d_qo_indptr / d_kv_indptr [n_req + 1] and d_kv_indices: the step's page table as given to vb_plan_rows;
+ * d_row_kvlen [n_rows]: keys visible to each row (vb_plan_rows' output: the causal prefix; any per-row bound that
+ * does not decrease inside a request is honoured as is).  Rows >= qo_indptr[n_req] (graph padding) are zeroed.
+ * No workspace, no split-KV: a CTA owns (Q tile, kv head, <= 8 grouped query heads). */
+int vb_prefill_attn_tile_rows(int n_q, int n_kv);
+int vb_paged_prefill_attn(void* d_out, const void* d_q, const void* d_kv, int64_t slab_base,
+                          const int32_t* d_qo_indptr, const int32_t* d_kv_indptr, const int32_t* d_kv_indices,
+                          const int32_t* d_row_kvlen, int n_req, int n_rows, int n_q, int n_kv, int head_dim,
+                          int page_size, float sm_scale, int out_xt_tile, void* stream);
+
 /* ---- dense projections (nn.Linear, bias-free): model/orpheus.py:41-47, 68-79, 197 -------------
  * Y[T][N] = X[T][K] * W[N][K]^T on tcgen05: a tile of tile_rows (<= 128, multiple of 8; 0 = 128) weight rows is
  * the M side of the MMA, the tokens are the N side.  tile_rows is free so that a projection can be cut into
@@ -169,6 +183,16 @@ int vb_proj_norm_qkv_rope_append(void* d_q_out, void* d_layer_kv, const void* d_
                                  const void* d_x_tiles, const float* d_ssq, int n_ssq_parts, const void* d_norm_weight, float eps,
                                  const float* d_rope_cs, const int32_t* d_row_page, const int32_t* d_row_slot, int T,
                                  int K, int n_q, int n_kv, int head_dim, int page_size, int split_k, void* stream);
+
+/* final norm -> lm_head as one operator (orpheus.py:193-197, 219-221: `self.norm(hidden)` then `self.lm_head`):
+ * logits[T][ldy] = bf16(rmsnorm(hidden[T][K]) * norm_weight . W^T (+ bias)).  d_workspace holds the normed rows in the
+ * tiled activation layout (vb_norm_lmhead_workspace_bytes(T, K) bytes); two launches, the projection a programmatic
+ * dependent of the norm.  (The decode engine gets the final norm for free from the last layer's
+ * vb_reduce_residual_rmsnorm; this entry point is the operator for callers that hold a plain hidden state.) */
+size_t vb_norm_lmhead_workspace_bytes(int T, int K);
+int vb_norm_lmhead(void* d_logits, const void* d_hidden, const void* d_norm_weight, float eps, const void* d_w_tiles,
+                   const void* d_bias, int T, int N, int K, int ldy, int tile_rows, void* d_workspace,
+                   size_t workspace_bytes, void* stream);
 
 /* cs[T][2][head_dim] = cos | sin of pos[t] * freq[e]: computed once per step, shared by all layers */
 int vb_rope_table(float* d_cs, const int32_t* d_pos, const float* d_freq, int T, int head_dim, void* stream);

@@ -218,6 +218,69 @@ def test_paged_attention_prefill_ragged_causal(ops):
     _attn_case(ops, [5, 36, 40], 16, 6, 2, 128, 15, prefill_new=[5, 20, 1])
 
 
+def _prefill_tiles_case(ops, kv_lens, new, page_size, hq, hkv, D, seed, pad_rows=0, xt=False):
+    """The tiled tensor-core prefill kernel (vb_paged_prefill_attn) against the oracle's ragged causal prefill
+    (flashinfer_utils.py:68-80, 132) and against the one-stream-per-row kernel on the same plan."""
+    n_pages = sum((L + page_size - 1) // page_size for L in kv_lens) + 3
+    indptr, indices, last = _random_page_table(kv_lens, page_size, n_pages, seed)
+    layer = 1
+    cache = torch.randn(2, n_pages, 2, page_size, hkv, D, generator=g(seed + 1)).to(BF)
+    qo = [0] + [int(x) for x in np.cumsum(new)]
+    R = qo[-1]
+    Rp = R + pad_rows
+    q = torch.randn(Rp, hq, D, generator=g(seed + 2)).to(BF)
+    ref = lm_ops.paged_attention_prefill(q[:R], cache[layer], qo, indptr, indices, last, page_size).float()
+    chunk = ops.attn_chunk_tokens(page_size, hkv)
+    plan = ops.RowPlan(max(Rp, 8), "cuda")
+    ops.plan_rows(plan, _i32(qo), _i32(indptr), _i32(indices), _i32(last), len(kv_lens), Rp, page_size, chunk)
+    ws = ops.paged_attn_workspace(Rp, None, hq, hkv, D, "cuda")
+    dq, dc = q.cuda(), cache.cuda()
+    out = torch.full((Rp, hq, D), 7.0, dtype=BF, device="cuda")
+    ops.paged_attn(dq, dc, layer * n_pages, plan, Rp, hkv, page_size, chunk, ws, out=out, prefill_tiles=True)
+    torch.cuda.synchronize()
+    got = out.float().cpu()
+    err = (got[:R] - ref).abs()
+    rel = (err.pow(2).sum() / ref.pow(2).sum()).sqrt().item()
+    assert rel < 8e-3, f"tiled prefill: rel l2 {rel}"
+    assert err.max().item() < 0.4 * max(ref.abs().mean().item(), 1e-3), f"tiled prefill: max err {err.max().item()}"
+    if pad_rows:
+        assert torch.count_nonzero(got[R:]) == 0, "padded rows must be zero"
+    old = ops.paged_attn(dq, dc, layer * n_pages, plan, Rp, hkv, page_size, chunk, ws, prefill_tiles=False).float().cpu()
+    assert (old[:R] - got[:R]).abs().max().item() < 0.1 * max(ref.abs().mean().item(), 1e-3) * 4
+    if xt:
+        out_t = ops.paged_attn(dq, dc, layer * n_pages, plan, Rp, hkv, page_size, chunk, ws,
+                               out=ops.TiledAct(Rp, hq * D, "cuda"), prefill_tiles=True)
+        assert torch.equal(out_t.to_rows(), out.view(Rp, hq * D)), "tiled-layout output differs"
+    return rel
+
+
+@pytest.mark.parametrize("kv_lens,new,page_size,hq,hkv,D", [
+    ([133, 201, 140], [133, 1, 40], 128, 24, 8, 128),        # Orpheus: fresh prompt, decode row, continued context
+    ([5, 36, 40], [5, 20, 1], 16, 6, 2, 128),                # 16-token pages: 16-token K/V tiles
+    ([70, 50, 64], [70, 3, 33], 32, 32, 8, 64),              # CSM backbone geometry (group 4, head_dim 64)
+    ([435], [435], 128, 32, 2, 128),                         # GLM-4-Voice: group 16 -> two head chunks per kv head
+    ([40, 30], [40, 17], 16, 14, 2, 64),                     # CosyVoice2: group 7
+    ([130, 64], [100, 64], 64, 16, 8, 128),                  # Qwen3-TTS talker: group 2, 64-row Q tiles
+    ([150], [130], 16, 4, 4, 64),                            # no grouping: 128-row Q tiles
+    ([600, 333], [600, 333], 32, 32, 8, 64),                 # long prompts, many K/V tiles per Q tile
+])
+def test_paged_prefill_attention_tiles(ops, kv_lens, new, page_size, hq, hkv, D):
+    _prefill_tiles_case(ops, kv_lens, new, page_size, hq, hkv, D, 31, xt=True)
+    _prefill_tiles_case(ops, kv_lens, new, page_size, hq, hkv, D, 32, pad_rows=5)
+
+
+def test_paged_prefill_attention_many_requests(ops):
+    # more requests than threads in a CTA (the tile lookup scans them in sweeps); a joining prompt among decode rows
+    rng = np.random.default_rng(5)
+    new = [int(x) for x in rng.integers(1, 4, size=300)]
+    kv = [n + int(x) for n, x in zip(new, rng.integers(0, 70, size=300))]
+    _prefill_tiles_case(ops, kv, new, 16, 6, 2, 128, 41)
+    new = [1] * 31 + [133]
+    kv = [193 + 19 * i for i in range(31)] + [133]
+    _prefill_tiles_case(ops, kv, new, 128, 24, 8, 128, 42, pad_rows=3, xt=True)
+    assert ops.prefill_attn_tile_rows(24, 8) == 32 and ops.prefill_attn_tile_rows(32, 2) == 16
+
+
 # --------------------------------------------------------------------------------------------
 def _gemm_ref(x, w):
     return x.float() @ w.float().t()
@@ -246,6 +309,22 @@ def test_gemm_lm_head_tail_tile(ops):
     y = ops.gemm(x.cuda(), w.cuda(), mode=0)
     ref = _gemm_ref(x, w)
     assert_bf16_close(y, ref.to(BF), 1, 2e-2, "lm_head", atol=2e-3 * ref.abs().max().item())
+
+
+@pytest.mark.parametrize("T,N,K,bias", [(32, 128 * 9 + 12, 768, False), (1, 3072, 1024, True), (133, 640, 3072, False)])
+def test_norm_lmhead(ops, T, N, K, bias):
+    """final norm -> lm_head as one operator (vb_norm_lmhead) = the oracle's rms_norm followed by the Linear
+    (orpheus.py:193-197, 219-221), and bit-identical to the two separate operators."""
+    h = torch.randn(T, K, generator=g(T)).to(BF)
+    nw = (1.0 + 0.1 * torch.randn(K, generator=g(N))).to(BF)
+    w = (torch.randn(N, K, generator=g(K)) * 0.05).to(BF)
+    b = (torch.randn(N, generator=g(7)) * 0.5).to(BF) if bias else None
+    xn = lm_ops.rms_norm(h, nw, 1e-5)
+    ref = xn.float() @ w.float().t() + (b.float() if bias else 0.0)
+    got = ops.norm_lmhead(h.cuda(), nw.cuda(), 1e-5, w.cuda(), bias=None if b is None else b.cuda())
+    assert_bf16_close(got, ref.to(BF), 1, 2e-2, "norm_lmhead", atol=4e-3 * ref.abs().max().item())
+    two = ops.gemm(ops.rmsnorm(h.cuda(), nw.cuda(), 1e-5), w.cuda(), mode=0, bias=None if b is None else b.cuda())
+    assert torch.equal(got, two)
 
 
 def test_gemm_gate_up_silu(ops):

@@ -35,6 +35,9 @@ SIGNATURES = {
     "vb_paged_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "vb_paged_attn": (c_int, [P, P, P, c_int64, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_float, P, c_size_t, c_int, c_int, c_int, P]),
+    "vb_prefill_attn_tile_rows": (c_int, [c_int, c_int]),
+    "vb_paged_prefill_attn": (c_int, [P, P, P, c_int64, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                      c_int, P]),
     "vb_set_trace": (c_int, [P]),
     "vb_gemm_t_tile": (c_int, [c_int]),
     "vb_set_gemm_smem_kb": (c_int, [c_int, c_int]),
@@ -45,6 +48,8 @@ SIGNATURES = {
     "vb_proj_norm_gateup_silu": (c_int, [P, P, P, P, P, c_int, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "vb_proj_norm_qkv_rope_append": (c_int, [P, P, P, P, P, P, c_int, P, c_float, P, P, P, c_int, c_int, c_int, c_int,
                                              c_int, c_int, c_int, P]),
+    "vb_norm_lmhead_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "vb_norm_lmhead": (c_int, [P, P, P, c_float, P, P, c_int, c_int, c_int, c_int, c_int, P, c_size_t, P]),
     "vb_rope_table": (c_int, [P, P, P, c_int, c_int, P]),
     "vb_row_ssq": (c_int, [P, P, c_int, c_int, P]),
     "vb_reduce_residual_rmsnorm": (c_int, [P, P, P, c_int, P, P, c_int, c_int, c_float, c_int, P]),

@@ -707,6 +707,26 @@ int vb_gemm_bf16(void* d_y, const void* d_w_tiles, const void* x_map, const void
   return launch_gemm(p, d_w_tiles, x_map, static_cast<cudaStream_t>(stream), d_x_tiles);
 }
 
+size_t vb_norm_lmhead_workspace_bytes(int T, int K) {
+  if (T <= 0 || K <= 0) return 0;
+  const int t_tile = vb_gemm_t_tile(T);
+  return static_cast<size_t>((T + t_tile - 1) / t_tile) * ((K + 63) / 64) * t_tile * 64 * sizeof(__nv_bfloat16);
+}
+
+// logits = lm_head(rmsnorm(hidden) * norm_weight) (+ bias): the normed rows go straight into the tiled activation
+// layout the projection streams (no row-major round trip), the projection is a programmatic dependent launch of the
+// norm and has its first ring pass of lm_head tiles in flight before the normed rows exist.
+int vb_norm_lmhead(void* d_logits, const void* d_hidden, const void* d_norm_weight, float eps, const void* d_w_tiles,
+                   const void* d_bias, int T, int N, int K, int ldy, int tile_rows, void* d_workspace,
+                   size_t workspace_bytes, void* stream) {
+  VB_CHECK_ARG(d_logits && d_hidden && d_norm_weight && d_w_tiles && d_workspace, "vb_norm_lmhead: null pointer");
+  VB_CHECK_ARG(workspace_bytes >= vb_norm_lmhead_workspace_bytes(T, K), "vb_norm_lmhead: workspace too small");
+  if (T <= 0) return 0;
+  const int rc = vb_rmsnorm(d_workspace, d_hidden, d_norm_weight, T, K, eps, vb_gemm_t_tile(T), stream);
+  if (rc != 0) return rc;
+  return vb_gemm_bf16(d_logits, d_w_tiles, nullptr, d_workspace, T, N, K, ldy, 0, 1, tile_rows, 0, 0, d_bias, stream);
+}
+
 int vb_proj_residual(void* d_hidden_out, void* d_hidden_tiles_out, float* d_ssq_out, const void* d_w_tiles,
                      const void* x_map, const void* d_x_tiles, const void* d_residual, int T, int N, int K, int split_k,
                      int tile_rows, void* stream) {

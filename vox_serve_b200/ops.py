@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -218,7 +219,10 @@ class RowPlan:
         self.row_old = self.buf[5 * m:6 * m]
         self.row_chunk_start = self.buf[6 * m:7 * m + 1]
         self.kv_indices: Optional[torch.Tensor] = None
+        self.qo_indptr: Optional[torch.Tensor] = None      # None: a decode plan (one row per request)
+        self.kv_indptr: Optional[torch.Tensor] = None
         self.n_rows = 0
+        self.n_req = 0
 
 
 def plan_rows(plan: RowPlan, qo_indptr: Optional[torch.Tensor], kv_indptr: torch.Tensor, kv_indices: torch.Tensor,
@@ -231,7 +235,9 @@ def plan_rows(plan: RowPlan, qo_indptr: Optional[torch.Tensor], kv_indptr: torch
          plan.row_page.data_ptr(), plan.row_slot.data_ptr(), plan.row_chunk_start.data_ptr(),
          plan.row_pagebase.data_ptr(), plan.row_old.data_ptr(), _stream())
     plan.n_rows = n_rows
+    plan.n_req = n_req
     plan.kv_indices = kv_indices
+    plan.qo_indptr, plan.kv_indptr = qo_indptr, kv_indptr
     return plan
 
 
@@ -263,12 +269,34 @@ def paged_attn_workspace(max_rows: int, max_chunks, n_q: int, n_kv: int, head_di
     return AttnWorkspace(max_rows, n_q, n_kv, head_dim, device, grid_ctas)
 
 
+def prefill_attn_tile_rows(n_q: int, n_kv: int) -> int:
+    """Rows of one request that share a K/V tile in the tiled prefill kernel (vb_prefill_attn_tile_rows)."""
+    return _lib.load().vb_prefill_attn_tile_rows(int(n_q), int(n_kv))
+
+
+_PREFILL_TILES = os.environ.get("VB_PREFILL_TILES", "auto")      # "0": never, "1": every prefill plan, "auto": by shape
+
+
+def use_prefill_tiles(plan: RowPlan, n_rows: int, head_dim: int, page_size: int) -> bool:
+    """Tiled prefill kernel or one KV stream per row?  A host-side decision on shapes only (stable under CUDA-graph
+    capture): the step must be a prefill plan whose rows are mostly prompt rows -- a joining prompt riding with a batch
+    of decodes (133 + 31 rows) qualifies, the 2-row depth-decoder prefill of a multi-codebook frame does not."""
+    if plan.qo_indptr is None or _PREFILL_TILES == "0" or head_dim not in (64, 128) or page_size % 16 != 0:
+        return False
+    if _PREFILL_TILES == "1":
+        return True
+    return n_rows >= 4 * plan.n_req or n_rows - plan.n_req >= 96
+
+
 def paged_attn(q: torch.Tensor, kv_cache, slab_base: int, plan: RowPlan, n_rows: int, n_kv: int,
                page_size: int, chunk_tokens: int, workspace: AttnWorkspace, sm_scale: Optional[float] = None,
-               out: Optional[torch.Tensor] = None, grid_ctas: Optional[int] = None) -> torch.Tensor:
+               out: Optional[torch.Tensor] = None, grid_ctas: Optional[int] = None,
+               prefill_tiles: Optional[bool] = None) -> torch.Tensor:
     """q [R, Hq, D] bf16 -> [R, Hq, D].  `kv_cache`: the whole cache tensor [L, pages, 2, P, Hkv, D] (or one layer
     [pages, 2, P, Hkv, D]); slab_base = layer * pages.  `plan` must come from plan_rows with the same
-    chunk_tokens (= attn_chunk_tokens(page_size, n_kv))."""
+    chunk_tokens (= attn_chunk_tokens(page_size, n_kv)).  Prefill-shaped plans (use_prefill_tiles, or
+    ``prefill_tiles=True``) run on the tiled tensor-core kernel (vb_paged_prefill_attn), everything else on the
+    one-stream-per-row kernel (vb_paged_attn)."""
     if isinstance(kv_cache, TensorMap):      # older call sites pass tensor_map_kv(...): use the tensor behind it
         kv_cache = kv_cache.owner
     _need_cuda(q, kv_cache)
@@ -282,8 +310,15 @@ def paged_attn(q: torch.Tensor, kv_cache, slab_base: int, plan: RowPlan, n_rows:
     else:
         out = torch.empty_like(q) if out is None else out
         out_ptr = out.data_ptr()
-    grid = workspace.grid if grid_ctas is None else min(int(grid_ctas), workspace.grid)
     sc = 1.0 / math.sqrt(d) if sm_scale is None else float(sm_scale)
+    tiles = use_prefill_tiles(plan, n_rows, d, page_size) if prefill_tiles is None else bool(prefill_tiles)
+    if tiles:
+        assert plan.qo_indptr is not None, "the tiled prefill kernel needs a prefill plan (qo_indptr)"
+        call("vb_paged_prefill_attn", out_ptr, q.data_ptr(), kv_cache.data_ptr(), int(slab_base),
+             plan.qo_indptr.data_ptr(), plan.kv_indptr.data_ptr(), plan.kv_indices.data_ptr(),
+             plan.row_kvlen.data_ptr(), plan.n_req, n_rows, n_q, n_kv, d, page_size, sc, xt, _stream())
+        return out
+    grid = workspace.grid if grid_ctas is None else min(int(grid_ctas), workspace.grid)
     call("vb_paged_attn", out_ptr, q.data_ptr(), kv_cache.data_ptr(), int(slab_base), plan.row_kvlen.data_ptr(),
          plan.row_chunk_start.data_ptr(), plan.row_pagebase.data_ptr(), plan.row_old.data_ptr(),
          plan.kv_indices.data_ptr(), n_rows, n_q, n_kv,
@@ -404,6 +439,25 @@ def gemm(x, w, mode: int = 0, split_k: int = 1, out=None, tile_rows: int = 128, 
         assert mode == 0 and bias.dtype == BF16 and bias.numel() == N and bias.is_contiguous()
     call("vb_gemm_bf16", out.data_ptr(), pw.data.data_ptr(), x_map_ptr, x_tiles_ptr, T, N, K, n_out, mode, split_k,
          tile_rows, n_out, 0, _p(bias), _stream())
+    return out
+
+
+def norm_lmhead(hidden: torch.Tensor, norm_weight: torch.Tensor, eps: float, w, bias: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """logits = lm_head(rmsnorm(hidden) * norm_weight) (+ bias) as one C-ABI operator (vb_norm_lmhead; orpheus.py:193-197,
+    219-221).  hidden [T, K] bf16, w [N, K] (or a PackedWeight) -> bf16 [T, N]."""
+    pw = _packed(w, 128)
+    _need_cuda(hidden, norm_weight)
+    assert hidden.dtype == BF16 and hidden.dim() == 2 and hidden.is_contiguous() and hidden.shape[1] == pw.K
+    T, K = hidden.shape
+    n = _lib.load().vb_norm_lmhead_workspace_bytes(T, K)
+    if workspace is None:
+        workspace = torch.empty(n, dtype=torch.uint8, device=hidden.device)
+    assert workspace.numel() * workspace.element_size() >= n
+    out = torch.empty(T, pw.N, dtype=BF16, device=hidden.device) if out is None else out
+    call("vb_norm_lmhead", out.data_ptr(), hidden.data_ptr(), norm_weight.data_ptr(), float(eps), pw.data.data_ptr(),
+         _p(bias), T, pw.N, K, out.stride(0), pw.tile_rows, workspace.data_ptr(),
+         workspace.numel() * workspace.element_size(), _stream())
     return out
 
 
