@@ -93,6 +93,13 @@ int vb_plan_rows(const int32_t* d_qo_indptr, const int32_t* d_kv_indptr, const i
 int vb_kv_append(void* d_layer_kv, const void* d_k, const void* d_v, const int32_t* d_row_page,
                  const int32_t* d_row_slot, int T, int page_size, int n_kv, int head_dim, void* stream);
 
+/* ---- whole-page gather / scatter (prefill-KV hand-off between replicas; the reference pins a
+ * request to one replica, launch.py:471-474, and has no such transfer).  d_cache: the whole cache
+ * [n_layers][pages_per_layer][page_bytes]; d_staging: [n_layers][n_pages][page_bytes] contiguous (what goes on the
+ * wire); d_page_ids [n_pages] int32 (device).  to_cache = 0: staging <- cache (sender), 1: cache <- staging (receiver). */
+int vb_copy_pages(void* d_cache, void* d_staging, const int32_t* d_page_ids, int n_pages, int n_layers,
+                  int64_t pages_per_layer, int64_t page_bytes, int to_cache, void* stream);
+
 /* ---- paged attention: FlashInferDecodeWrapper.run / FlashInferPrefillWrapper.run
  * (flashinfer_utils.py:132, 228-230).  One query row per entry of the plan; causal by construction
  * (row kv length).  q/out [R][n_q][D] bf16.  d_kv = base of the WHOLE cache [slabs][2][page][n_kv][D];

@@ -37,7 +37,8 @@ def build_models(dims, snac_cfg, seed, max_bs, page_size, max_pages, greedy=True
                 decoder_rates=snac_cfg.decoder_rates, codebook_size=snac_cfg.codebook_size,
                 codebook_dim=snac_cfg.codebook_dim, vq_strides=snac_cfg.vq_strides, device="cuda")
     snac.load_state_dict(snac_sd)
-    model = OrpheusModel("orpheus-test", state_dict=weights, dims=ld, snac=snac, stop_token_id=dims.stop_token_id,
+    model = OrpheusModel("orpheus-test", device=f"cuda:{torch.cuda.current_device()}", state_dict=weights, dims=ld,
+                         snac=snac, stop_token_id=dims.stop_token_id,
                          audio_id_base=dims.audio_id_base, max_tokens=dims.max_tokens, mask_stop_token=stop_boost is None)
     model.default_sampling_config = SamplingConfig(top_p=0.8, temperature=0.6, repetition_penalty=1.3,
                                                    repetition_window=-1, greedy=greedy, max_tokens=dims.max_tokens)

@@ -31,6 +31,7 @@ SIGNATURES = {
     "vb_latest_window": (c_int, [P, P, P, c_int, c_int, P]),
     "vb_gather_windows": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
     "vb_kv_append": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    "vb_copy_pages": (c_int, [P, P, P, c_int, c_int, c_int64, c_int64, c_int, P]),
     "vb_attn_tile_tokens": (c_int, [c_int, c_int]),
     "vb_paged_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "vb_paged_attn": (c_int, [P, P, P, c_int64, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int,

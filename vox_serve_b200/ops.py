@@ -249,6 +249,26 @@ def kv_append(layer_kv: torch.Tensor, k: torch.Tensor, v: torch.Tensor, plan: Ro
          plan.row_slot.data_ptr(), T, layer_kv.shape[-3], layer_kv.shape[-2], layer_kv.shape[-1], _stream())
 
 
+def copy_pages(kv_cache: torch.Tensor, page_ids: torch.Tensor, staging: Optional[torch.Tensor] = None,
+               to_cache: bool = False) -> torch.Tensor:
+    """Whole pages of every layer between the paged cache [L, pages, 2, P, Hkv, D] and a contiguous staging buffer
+    [L, n, 2, P, Hkv, D] (vb_copy_pages): ``to_cache=False`` gathers (the sender of a KV hand-off), ``True`` scatters
+    (the receiver).  page_ids: int32 on the device."""
+    _need_cuda(kv_cache, page_ids)
+    assert kv_cache.is_contiguous() and kv_cache.dim() == 6 and page_ids.dtype == torch.int32
+    L, P = kv_cache.shape[0], kv_cache.shape[1]
+    n = page_ids.numel()
+    if staging is None:
+        assert not to_cache
+        staging = torch.empty((L, n) + tuple(kv_cache.shape[2:]), dtype=kv_cache.dtype, device=kv_cache.device)
+    _need_cuda(staging)
+    assert staging.is_contiguous() and staging.dtype == kv_cache.dtype and staging.numel() == L * n * kv_cache[0, 0].numel()
+    page_bytes = kv_cache[0, 0].numel() * kv_cache.element_size()
+    call("vb_copy_pages", kv_cache.data_ptr(), staging.data_ptr(), page_ids.data_ptr(), n, L, P, page_bytes,
+         int(bool(to_cache)), _stream())
+    return staging
+
+
 def attn_grid_ctas() -> int:
     """Persistent grid of the attention kernel: one CTA per SM (a 3-stage ring of 64 KiB tiles each)."""
     return device_info()[0]

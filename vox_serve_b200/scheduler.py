@@ -43,6 +43,23 @@ class Scheduler:
         self.audio[req.request_id] = []
         self.pending.append(req)
 
+    def detach(self, request_id: str) -> Request:
+        """Take a request out of this loop WITHOUT finishing it (it is being handed to another replica,
+        vox_serve_b200/kv_handoff.py); the caller releases or transfers what the worker holds for it."""
+        for pool in (self.active_requests, self.pending):
+            for r in list(pool):
+                if r.request_id == request_id:
+                    pool.remove(r)
+                    return r
+        raise KeyError(request_id)
+
+    def adopt(self, req: Request) -> None:
+        """Continue a request that arrived through a KV hand-off: its prefill is done and the worker already holds its
+        pages, batch slot and decode state, so it joins the active set directly."""
+        self.submit_time.setdefault(req.request_id, time.perf_counter())
+        self.audio.setdefault(req.request_id, [])
+        self.active_requests.append(req)
+
     def _prepare_requests(self):
         for r in self.active_requests:
             # a request the worker FAILED (finish_reason "error: ...": prompt too long, out of KV pages) never reaches

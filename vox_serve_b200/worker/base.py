@@ -97,6 +97,10 @@ class ModelWorker:
                                enable_torch_compile=enable_torch_compile, audio_decoder_device=self.device,
                                detokenize_interval=detokenize_interval, **model_kwargs)
         self.model = model
+        mdev = torch.device(getattr(model, "device", self.device))
+        if mdev.type == "cuda" and mdev.index is not None and mdev.index != torch.cuda.current_device():
+            raise VoxB200Error(f"model lives on {mdev}, the worker on {self.device}: build the model on the replica's own "
+                               "GPU (kernels are launched on the current device and read the weights directly)")
         if not 1 <= max_batch_size <= 64:
             raise VoxB200Error(f"max_batch_size {max_batch_size} outside [1, 64]: decode-sized steps (one row per request) are "
                                "what the projection kernels tile for; run more replicas for more streams")
