@@ -93,6 +93,25 @@ int vb_plan_rows(const int32_t* d_qo_indptr, const int32_t* d_kv_indptr, const i
 int vb_kv_append(void* d_layer_kv, const void* d_k, const void* d_v, const int32_t* d_row_page,
                  const int32_t* d_row_slot, int T, int page_size, int n_kv, int head_dim, void* stream);
 
+/* ---- GLM-4-Voice speech tokenizer (Whisper-style VQ encoder, vox_serve/encoder/glm.py:84-323): the stages that are not
+ * a GEMM or the block-causal attention.  Token-major [T][C] bf16 activations; every op rounds where the reference's
+ * bf16 modules round.
+ * vb_add_layernorm: h = bf16(h + delta) in place (delta may be NULL), y = LayerNorm(h) * w + b (y may be NULL: only
+ *   the residual add) -- glm.py:195-214.
+ * vb_gelu_add: y = bf16(gelu_erf(x)), then y = bf16(y + add) when add != NULL (positions, glm.py:288-295).
+ * vb_chw_to_rows: out[pad + t][c] = in[c][t], rows [0, pad) zero: the causal convolutions read their taps as
+ *   overlapping rows of this buffer (glm.py:84-107) -- no im2col copy.
+ * vb_avgpool_rows: out[t] = mean of rows [t k, t k + k) with rows >= T counting as zeros (glm.py:303-313).
+ * vb_vq_argmin: ids[t] = first arg-min_n bf16(bf16(c2[n] + |x_t|^2) - 2 acc[t][n]) with acc = x c^T in fp32 (a mode-1
+ *   vb_gemm_bf16 over the codebook) -- vector_quantize, glm.py:247-258. */
+int vb_add_layernorm(void* d_y, void* d_h, const void* d_delta, const void* d_w, const void* d_b, int rows, int dim,
+                     float eps, void* stream);
+int vb_gelu_add(void* d_y, const void* d_x, const void* d_add, int64_t n, void* stream);
+int vb_chw_to_rows(void* d_out, const void* d_in, int C, int T, int pad, void* stream);
+int vb_avgpool_rows(void* d_out, const void* d_in, int T, int D, int k, void* stream);
+int vb_vq_argmin(int64_t* d_ids, const float* d_acc, const void* d_x, const void* d_c2, int T, int N, int D,
+                 void* stream);
+
 /* ---- whole-page gather / scatter (prefill-KV hand-off between replicas; the reference pins a
  * request to one replica, launch.py:471-474, and has no such transfer).  d_cache: the whole cache
  * [n_layers][pages_per_layer][page_bytes]; d_staging: [n_layers][n_pages][page_bytes] contiguous (what goes on the

@@ -697,8 +697,56 @@ def golden_qwen3_codec():
           "abs max %.4f" % max(float(np.abs(out[f"wav{i}"]).max()) for i in range(3)))
 
 
+def golden_glm_encoder():
+    """The reference's own ``GLMWhisperVQEncoder`` (vox_serve/encoder/glm.py:217-323) in bf16 on CPU, tiny config,
+    seeded weights from oracle.glm_encoder.synth_state_dict; two inputs: a full-length one and one whose tail is
+    padding (attention_mask 0) with a length that is not a multiple of the pooling width after the convolutions."""
+    from .ref_import import REFERENCE_ROOT
+
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    from vox_serve.encoder.glm import GLMEncoderConfig, GLMWhisperVQEncoder
+
+    from . import glm_encoder as oenc
+
+    d = oenc.GLMEncoderDims.tiny()
+    seed = 11
+    sd = oenc.synth_state_dict(d, seed)
+    cfg = GLMEncoderConfig(d_model=d.d_model, encoder_attention_heads=d.encoder_attention_heads,
+                           encoder_ffn_dim=d.encoder_ffn_dim, num_mel_bins=d.num_mel_bins,
+                           max_source_positions=d.max_source_positions, pooling_kernel_size=d.pooling_kernel_size,
+                           pooling_position=d.pooling_position, quantize_position=d.quantize_position,
+                           quantize_vocab_size=d.quantize_vocab_size,
+                           quantize_causal_block_size=d.quantize_causal_block_size)
+    m = GLMWhisperVQEncoder(cfg).to(torch.bfloat16).eval()
+    missing = m.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    out = {"weight_seed": seed}
+    g = torch.Generator().manual_seed(5)
+    cases = {"full": (160, 160), "padded": (148, 132)}          # (frames, valid frames)
+    for tag, (frames, valid) in cases.items():
+        feats = torch.randn(1, d.num_mel_bins, frames, generator=g).to(torch.bfloat16)
+        mask = torch.zeros(1, frames, dtype=torch.long)
+        mask[:, :valid] = 1
+        states = {}
+        hook = m.layers[-1].register_forward_hook(lambda mod, i, o: states.__setitem__("last", o))
+        with torch.no_grad():
+            ids = m(feats, mask)
+        hook.remove()
+        out[f"{tag}_features"] = feats.float().numpy()
+        out[f"{tag}_mask"] = mask.numpy()
+        out[f"{tag}_ids"] = ids.numpy()
+        out[f"{tag}_hidden"] = states["last"].float().numpy()
+    np.savez_compressed(os.path.join(OUT, "glm_encoder_tiny.npz"), **out)
+    print("glm_encoder_tiny.npz:", {k: v.shape for k, v in out.items() if hasattr(v, "shape")},
+          "distinct ids:", len(set(out["full_ids"].reshape(-1).tolist())))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "glm_encoder":
+        golden_glm_encoder()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "qwen3_codec":
         golden_qwen3_codec()
         return
@@ -731,6 +779,7 @@ def main():
         golden_qwen3_tts_frames()
         golden_mimi()
         golden_qwen3_codec()
+        golden_glm_encoder()
     finally:
         torch.cuda.synchronize = orig_sync
 

@@ -218,3 +218,26 @@ def test_qwen3_codec_streaming_decoder_oracle_matches_reference_golden(golden_di
         for j, t in enumerate(cache[name]):
             assert np.array_equal(t.numpy(), gd[f"{key}.{j}"]), (name, j)
     assert cfg.hop == 192 and oq.Qwen3CodecConfig().hop == 1920
+
+
+def test_glm_encoder_oracle_matches_reference_golden(golden_dir):
+    """oracle/glm_encoder.py against the reference's own GLMWhisperVQEncoder outputs (bf16 on CPU): ids and the last
+    layer's hidden state bit for bit, for a full-length input and one with a padded tail."""
+    from oracle import glm_encoder as oenc
+
+    gd = _load(golden_dir, "glm_encoder_tiny.npz")
+    d = oenc.GLMEncoderDims.tiny()
+    sd = oenc.synth_state_dict(d, int(gd["weight_seed"]))
+    for tag in ("full", "padded"):
+        feats = torch.from_numpy(gd[f"{tag}_features"]).to(torch.bfloat16)
+        mask = torch.from_numpy(gd[f"{tag}_mask"])
+        ids, hidden, pooled, dist = oenc.encode(sd, d, feats, mask, return_states=True)
+        assert np.array_equal(ids.numpy(), gd[f"{tag}_ids"])
+        assert np.array_equal(hidden.float().numpy(), gd[f"{tag}_hidden"])
+        # the per-row key bound the CUDA kernel takes IS the reference's additive mask
+        am = mask[:, ::2]
+        bounds = oenc.block_causal_bounds(am, d.quantize_causal_block_size)
+        full = oenc.block_causal_mask(am, d.quantize_causal_block_size)[0, 0]
+        T = am.shape[1]
+        visible = torch.arange(T)[None, :] < bounds[:, None].long()
+        assert torch.equal(full == 0, visible)
