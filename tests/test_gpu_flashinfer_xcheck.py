@@ -121,3 +121,49 @@ def test_paged_decode_attention_matches_flashinfer(fi, ops, use_tensor_cores):
         rel = (err.pow(2).sum() / ref.pow(2).sum()).sqrt().item()
         assert rel < 8e-3 and err.max().item() < 0.04 * scale, (name, rel, err.max().item(), scale)
     assert math.isfinite(scale)
+
+
+def test_paged_prefill_attention_matches_flashinfer(fi, ops):
+    """ragged causal prefill batch (fresh prompt, decode row, continued context) in the Orpheus geometry through
+    FlashInfer's BatchPrefillWithPagedKVCacheWrapper with the reference's own plan keywords
+    (flashinfer_utils.py:68-80, 132): BOTH prefill kernels -- the tiled tensor-core one and the one-stream-per-row
+    one -- and the CPU oracle are held to it."""
+    hq, hkv, D, ps = 24, 8, 128, 128
+    kv_lens, new = [133, 201, 140, 300], [133, 1, 40, 300]
+    n_pages = sum((L + ps - 1) // ps for L in kv_lens) + 3
+    perm = torch.randperm(n_pages, generator=g(13)).tolist()
+    indptr, indices, last = [0], [], []
+    for L in kv_lens:
+        n = (L + ps - 1) // ps
+        indices += [perm.pop() for _ in range(n)]
+        indptr.append(len(indices))
+        last.append(L - (n - 1) * ps)
+    qo = [0]
+    for n in new:
+        qo.append(qo[-1] + n)
+    R = qo[-1]
+    cache = (torch.randn(n_pages, 2, ps, hkv, D, generator=g(14)) * 0.7).to(BF).cuda()
+    q = torch.randn(R, hq, D, generator=g(15)).to(BF).cuda()
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device="cuda")      # noqa: E731
+    ws = torch.empty(128 << 20, dtype=torch.uint8, device="cuda")
+    try:
+        w = fi.BatchPrefillWithPagedKVCacheWrapper(ws, "NHD")
+        w.plan(qo_indptr=i32(qo), paged_kv_indptr=i32(indptr), paged_kv_indices=i32(indices),
+               paged_kv_last_page_len=i32(last), num_qo_heads=hq, num_kv_heads=hkv, head_dim_qk=D, page_size=ps,
+               causal=True, q_data_type=BF, kv_data_type=BF)
+        ref = w.run(q, cache).float().cpu()
+    except Exception as e:  # pragma: no cover
+        pytest.skip(f"flashinfer prefill kernels unavailable on this box: {type(e).__name__}: {str(e)[:200]}")
+    plan = ops.RowPlan(R, "cuda")
+    chunk = ops.attn_chunk_tokens(ps, hkv)
+    ops.plan_rows(plan, i32(qo), i32(indptr), i32(indices), i32(last), len(kv_lens), R, ps, chunk)
+    aws = ops.AttnWorkspace(R, hq, hkv, D, "cuda")
+    c6 = cache.view(1, *cache.shape)
+    tiles = ops.paged_attn(q, c6, 0, plan, R, hkv, ps, chunk, aws, prefill_tiles=True).float().cpu()
+    rows = ops.paged_attn(q, c6, 0, plan, R, hkv, ps, chunk, aws, prefill_tiles=False).float().cpu()
+    orc = lm_ops.paged_attention_prefill(q.cpu(), cache.cpu(), qo, indptr, indices, last, ps).float()
+    scale = ref.abs().max().item()
+    for name, a in (("tiled kernel", tiles), ("row kernel", rows), ("oracle", orc)):
+        err = (a - ref).abs()
+        rel = (err.pow(2).sum() / ref.pow(2).sum()).sqrt().item()
+        assert rel < 8e-3 and err.max().item() < 0.04 * scale, (name, rel, err.max().item(), scale)
