@@ -482,27 +482,36 @@ __global__ void __launch_bounds__(288, MINB) paged_attn_kernel(const AttnParams 
           auto pslot_of = [&](int c) {
             return static_cast<size_t>(m.cta_a + c) * 2 + ((c == 0 && Ls > m.cta_a * per) ? 1 : 0);
           };
-          // One pass with a running maximum (the rescaling of online softmax): a round needs ONE L2 round trip for
-          // MP parts -- no separate pass for the maxima -- so a row cut into <= MP parts merges in a single round.
-          constexpr int MP = (MINB == 1) ? 4 : 2;   // (two parts per round keep the 2-CTAs-per-SM variant at 96 registers)
-          constexpr int HC = 3;                     // heads per sweep: Orpheus' group of 3 in one sweep, 12 values per lane and part
-          for (int g0 = 0; g0 < G; g0 += HC) {
-            float Mrun[HC], acc[HC][D / 32], den[HC];
+          for (int g0 = 0; g0 < G; g0 += 4) {
+            float Mx[4];
 #pragma unroll
-            for (int hh = 0; hh < HC; ++hh) {
-              Mrun[hh] = -INFINITY;
+            for (int hh = 0; hh < 4; ++hh) Mx[hh] = -INFINITY;
+            for (int cb = 0; cb < n; cb += 32) {
+              const int c = cb + lane;
+              float mm[4];
+#pragma unroll
+              for (int hh = 0; hh < 4; ++hh)
+                mm[hh] = (c < n && g0 + hh < G) ? __ldcg(&p.part_ml[(pslot_of(c) * p.n_q + hq0 + g0 + hh) * 2]) : -INFINITY;
+#pragma unroll
+              for (int hh = 0; hh < 4; ++hh) Mx[hh] = fmaxf(Mx[hh], warp_max(mm[hh]));
+            }
+            float acc[4][D / 32], den[4];
+#pragma unroll
+            for (int hh = 0; hh < 4; ++hh) {
               den[hh] = 0.f;
 #pragma unroll
               for (int j = 0; j < D / 32; ++j) acc[hh][j] = 0.f;
             }
+            // (two parts per round keeps the kernel under the 112 registers that let two CTAs share an SM)
+            constexpr int MP = 2;
             for (int cb = 0; cb < n; cb += MP) {
-              float mm[MP][HC], ll[MP][HC], v[MP][HC][D / 32];
+              float mm[MP][4], ll[MP][4], v[MP][4][D / 32];
 #pragma unroll
               for (int k = 0; k < MP; ++k) {
                 const bool okc = cb + k < n;
                 const size_t ps = pslot_of(okc ? cb + k : 0);
 #pragma unroll
-                for (int hh = 0; hh < HC; ++hh) {
+                for (int hh = 0; hh < 4; ++hh) {
                   const bool ok = okc && g0 + hh < G;
                   const size_t hb = ps * p.n_q + hq0 + g0 + hh;
                   mm[k][hh] = ok ? __ldcg(&p.part_ml[hb * 2]) : -INFINITY;
@@ -512,26 +521,17 @@ __global__ void __launch_bounds__(288, MINB) paged_attn_kernel(const AttnParams 
                 }
               }
 #pragma unroll
-              for (int hh = 0; hh < HC; ++hh) {
-                float Mn = Mrun[hh];
+              for (int k = 0; k < MP; ++k)
 #pragma unroll
-                for (int k = 0; k < MP; ++k) Mn = fmaxf(Mn, mm[k][hh]);
-                const float rs = (Mrun[hh] == -INFINITY) ? 0.f : ex2_approx(Mrun[hh] - Mn);
-                Mrun[hh] = Mn;
-                den[hh] *= rs;
-#pragma unroll
-                for (int j = 0; j < D / 32; ++j) acc[hh][j] *= rs;
-#pragma unroll
-                for (int k = 0; k < MP; ++k) {
-                  const float sc = (mm[k][hh] == -INFINITY) ? 0.f : ex2_approx(mm[k][hh] - Mn);
+                for (int hh = 0; hh < 4; ++hh) {
+                  const float sc = (mm[k][hh] == -INFINITY) ? 0.f : ex2_approx(mm[k][hh] - Mx[hh]);
                   den[hh] += sc * ll[k][hh];
 #pragma unroll
                   for (int j = 0; j < D / 32; ++j) acc[hh][j] += sc * v[k][hh][j];
                 }
-              }
             }
 #pragma unroll
-            for (int hh = 0; hh < HC; ++hh) {
+            for (int hh = 0; hh < 4; ++hh) {
               if (g0 + hh < G) {
                 const float inv = 1.f / den[hh];
 #pragma unroll
