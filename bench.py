@@ -574,7 +574,10 @@ def kernel_rooflines(worker, model, reqs, torch, ops):
                                  "avg_launch_us": gu_ms * 1e3 / d.num_hidden_layers,
                                  "algorithmic_bytes_per_launch": int(gu_bytes / d.num_hidden_layers)},
             "roofline": {"kernel": "gemm_bf16_kernel (all projection launches of one decode step)", "bound": "hbm",
-                         "achieved": ga, "peak": peak, "unit": "GB/s", "frac": ga / peak, "traffic": None,
+                         "achieved": ga, "peak": peak, "unit": "GB/s", "frac": ga / peak,
+                         "traffic": ncu.get("gemm_all", {}).get("dram_bytes_per_launch"),
+                         "traffic_per_step": ncu.get("gemm_all", {}).get("dram_bytes_per_step"),
+                         "traffic_source": ncu.get("gemm_all", {}).get("source"),
                          "peak_source": peak_src, "launches_per_step": n_gemm[0],
                          "avg_launch_us": gemm_ms * 1e3 / max(1, n_gemm[0]),
                          "algorithmic_bytes_per_step": int(gemm_bytes)},

@@ -97,16 +97,17 @@ int vb_kv_append(void* d_layer_kv, const void* d_k, const void* d_v, const int32
  * a GEMM or the block-causal attention.  Token-major [T][C] bf16 activations; every op rounds where the reference's
  * bf16 modules round.
  * vb_add_layernorm: h = bf16(h + delta) in place (delta may be NULL), y = LayerNorm(h) * w + b (y may be NULL: only
- *   the residual add) -- glm.py:195-214.
- * vb_gelu_add: y = bf16(gelu_erf(x)), then y = bf16(y + add) when add != NULL (positions, glm.py:288-295).
+ *   the residual add) -- glm.py:195-214.  y_xt_tile > 0: y in the tiled activation layout XT(y_xt_tile).
+ * vb_gelu_add: y = bf16(gelu_erf(x)), then y = bf16(y + add) when add != NULL (positions, glm.py:288-295); n elements
+ *   in rows of dim; y_xt_tile > 0: y in the tiled layout (y must not alias x).
  * vb_chw_to_rows: out[pad + t][c] = in[c][t], rows [0, pad) zero: the causal convolutions read their taps as
  *   overlapping rows of this buffer (glm.py:84-107) -- no im2col copy.
  * vb_avgpool_rows: out[t] = mean of rows [t k, t k + k) with rows >= T counting as zeros (glm.py:303-313).
  * vb_vq_argmin: ids[t] = first arg-min_n bf16(bf16(c2[n] + |x_t|^2) - 2 acc[t][n]) with acc = x c^T in fp32 (a mode-1
  *   vb_gemm_bf16 over the codebook) -- vector_quantize, glm.py:247-258. */
 int vb_add_layernorm(void* d_y, void* d_h, const void* d_delta, const void* d_w, const void* d_b, int rows, int dim,
-                     float eps, void* stream);
-int vb_gelu_add(void* d_y, const void* d_x, const void* d_add, int64_t n, void* stream);
+                     float eps, int y_xt_tile, void* stream);
+int vb_gelu_add(void* d_y, const void* d_x, const void* d_add, int64_t n, int dim, int y_xt_tile, void* stream);
 int vb_chw_to_rows(void* d_out, const void* d_in, int C, int T, int pad, void* stream);
 int vb_avgpool_rows(void* d_out, const void* d_in, int T, int D, int k, void* stream);
 int vb_vq_argmin(int64_t* d_ids, const float* d_acc, const void* d_x, const void* d_c2, int T, int N, int D,

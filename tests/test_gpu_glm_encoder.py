@@ -72,7 +72,12 @@ def test_encoder_stage_kernels_exact():
     dh, y = h.cuda().clone(), torch.empty(T, D, dtype=BF, device="cuda")
     d_delta, d_w, d_b = delta.cuda(), w.cuda(), b.cuda()       # (kept alive: the calls take raw pointers)
     call("vb_add_layernorm", y.data_ptr(), dh.data_ptr(), d_delta.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), T, D,
-         1e-5, st)
+         1e-5, 0, st)
+    yt = ops.TiledAct(T, D, "cuda")                 # the tiled output layout holds the same numbers
+    dh2 = h.cuda().clone()
+    call("vb_add_layernorm", yt.data.data_ptr(), dh2.data_ptr(), d_delta.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), T, D,
+         1e-5, yt.t_tile, st)
+    assert torch.equal(yt.to_rows(), y)
     hs = h + delta
     assert torch.equal(dh.cpu(), hs)
     ref = F.layer_norm(hs.float(), (D,), w.float(), b.float()).to(BF)
@@ -82,7 +87,10 @@ def test_encoder_stage_kernels_exact():
     x = (3 * torch.randn(T, D, generator=g)).to(BF)
     out = torch.empty(T, D, dtype=BF, device="cuda")
     d_x = x.cuda()
-    call("vb_gelu_add", out.data_ptr(), d_x.data_ptr(), d_delta.data_ptr(), T * D, st)
+    call("vb_gelu_add", out.data_ptr(), d_x.data_ptr(), d_delta.data_ptr(), T * D, D, 0, st)
+    gt = ops.TiledAct(T, D, "cuda")
+    call("vb_gelu_add", gt.data.data_ptr(), d_x.data_ptr(), d_delta.data_ptr(), T * D, D, gt.t_tile, st)
+    assert torch.equal(gt.to_rows(), out)
     ref = F.gelu(x.float()).to(BF) + delta
     diff = (out.cpu().float() - ref.float()).abs()
     assert (diff > 0).float().mean().item() < 0.01 and diff.max().item() <= 0.07

@@ -31,8 +31,8 @@ SIGNATURES = {
     "vb_latest_window": (c_int, [P, P, P, c_int, c_int, P]),
     "vb_gather_windows": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
     "vb_kv_append": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
-    "vb_add_layernorm": (c_int, [P, P, P, P, P, c_int, c_int, c_float, P]),
-    "vb_gelu_add": (c_int, [P, P, P, c_int64, P]),
+    "vb_add_layernorm": (c_int, [P, P, P, P, P, c_int, c_int, c_float, c_int, P]),
+    "vb_gelu_add": (c_int, [P, P, P, c_int64, c_int, c_int, P]),
     "vb_chw_to_rows": (c_int, [P, P, c_int, c_int, c_int, P]),
     "vb_avgpool_rows": (c_int, [P, P, c_int, c_int, c_int, P]),
     "vb_vq_argmin": (c_int, [P, P, P, P, c_int, c_int, c_int, P]),

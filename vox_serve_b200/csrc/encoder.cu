@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(ENC_THREADS) add_layernorm_kernel(__nv_bfloat1
                                                                     const __nv_bfloat16* __restrict__ delta,
                                                                     const __nv_bfloat16* __restrict__ w,
                                                                     const __nv_bfloat16* __restrict__ b, int dim,
-                                                                    float eps) {
+                                                                    float eps, int y_xt_tile) {
   pdl_sync();
   __shared__ float red[ENC_THREADS / 32];
   __nv_bfloat16* hr = h + static_cast<size_t>(blockIdx.x) * dim;
@@ -50,22 +50,32 @@ __global__ void __launch_bounds__(ENC_THREADS) add_layernorm_kernel(__nv_bfloat1
     q += v * v;
   }
   const float rstd = rsqrtf(block_sum(q, red) / dim + eps);
-  __nv_bfloat16* yr = y + static_cast<size_t>(blockIdx.x) * dim;
-  for (int i = threadIdx.x; i < dim; i += ENC_THREADS)
-    yr[i] = __float2bfloat16_rn((__bfloat162float(hr[i]) - mean) * rstd * __bfloat162float(w[i]) + __bfloat162float(b[i]));
+  // row-major, or the tiled activation layout the consuming projection streams with linear bulk copies
+  const int row = blockIdx.x, num_kb = (dim + 63) >> 6;
+  for (int i = threadIdx.x; i < dim; i += ENC_THREADS) {
+    const size_t o = y_xt_tile ? xt_index(row, i, y_xt_tile, num_kb) : static_cast<size_t>(row) * dim + i;
+    y[o] = __float2bfloat16_rn((__bfloat162float(hr[i]) - mean) * rstd * __bfloat162float(w[i]) + __bfloat162float(b[i]));
+  }
 }
 
 // y = bf16(gelu(x)) (exact erf form, nn.GELU / F.gelu default) ; then y = bf16(y + add) if add     glm.py:288-295
 __global__ void __launch_bounds__(ENC_THREADS) gelu_add_kernel(__nv_bfloat16* __restrict__ y,
                                                                const __nv_bfloat16* __restrict__ x,
-                                                               const __nv_bfloat16* __restrict__ add, long long n) {
+                                                               const __nv_bfloat16* __restrict__ add, long long n,
+                                                               int dim, int y_xt_tile) {
   pdl_sync();
   const long long stride = static_cast<long long>(gridDim.x) * ENC_THREADS;
+  const int num_kb = (dim + 63) >> 6;
   for (long long i = static_cast<long long>(blockIdx.x) * ENC_THREADS + threadIdx.x; i < n; i += stride) {
     const float v = __bfloat162float(x[i]);
     float g = round_bf16(0.5f * v * (1.f + erff(v * 0.70710678118654752440f)));
     if (add) g = round_bf16(g + __bfloat162float(add[i]));
-    y[i] = __float2bfloat16_rn(g);
+    size_t o = static_cast<size_t>(i);
+    if (y_xt_tile) {
+      const int row = static_cast<int>(i / dim);
+      o = xt_index(row, static_cast<int>(i - static_cast<long long>(row) * dim), y_xt_tile, num_kb);
+    }
+    y[o] = __float2bfloat16_rn(g);
   }
 }
 
@@ -156,24 +166,25 @@ using namespace vb;
 extern "C" {
 
 int vb_add_layernorm(void* d_y, void* d_h, const void* d_delta, const void* d_w, const void* d_b, int rows, int dim,
-                     float eps, void* stream) {
+                     float eps, int y_xt_tile, void* stream) {
   VB_CHECK_ARG(d_h && (d_y || d_delta), "vb_add_layernorm: nothing to do");
   VB_CHECK_ARG(!d_y || (d_w && d_b), "vb_add_layernorm: the norm output needs weight and bias");
   if (rows <= 0) return 0;
   VB_LAUNCH_PDL(add_layernorm_kernel, rows, ENC_THREADS, 0, stream, static_cast<__nv_bfloat16*>(d_y),
                 static_cast<__nv_bfloat16*>(d_h), static_cast<const __nv_bfloat16*>(d_delta),
-                static_cast<const __nv_bfloat16*>(d_w), static_cast<const __nv_bfloat16*>(d_b), dim, eps);
+                static_cast<const __nv_bfloat16*>(d_w), static_cast<const __nv_bfloat16*>(d_b), dim, eps, y_xt_tile);
   return 0;
 }
 
-int vb_gelu_add(void* d_y, const void* d_x, const void* d_add, int64_t n, void* stream) {
+int vb_gelu_add(void* d_y, const void* d_x, const void* d_add, int64_t n, int dim, int y_xt_tile, void* stream) {
   VB_CHECK_ARG(d_y && d_x, "vb_gelu_add: null pointer");
+  VB_CHECK_ARG(!y_xt_tile || (dim > 0 && n % dim == 0 && d_y != d_x), "vb_gelu_add: the tiled output needs the row width and its own buffer");
   if (n <= 0) return 0;
   long long blocks = (n + ENC_THREADS - 1) / ENC_THREADS;
   if (blocks > 148 * 16) blocks = 148 * 16;
   VB_LAUNCH_PDL(gelu_add_kernel, static_cast<unsigned>(blocks), ENC_THREADS, 0, stream, static_cast<__nv_bfloat16*>(d_y),
                 static_cast<const __nv_bfloat16*>(d_x), static_cast<const __nv_bfloat16*>(d_add),
-                static_cast<long long>(n));
+                static_cast<long long>(n), dim > 0 ? dim : 1, y_xt_tile);
   return 0;
 }
 

@@ -120,16 +120,20 @@ class GLMWhisperVQEncoder:
         return self
 
     # ---- pieces ---------------------------------------------------------------------------------------
-    def _add_layernorm(self, h, delta, wname, L, want_y=True):
-        y = torch.empty_like(h) if want_y else None
-        call("vb_add_layernorm", None if y is None else y.data_ptr(), h.data_ptr(),
+    def _add_layernorm(self, h, delta, wname, L, y: Optional[ops.TiledAct] = None):
+        """h += delta (in place); y = LayerNorm(h) in the tiled layout the next projection streams (None: add only)."""
+        call("vb_add_layernorm", None if y is None else y.data.data_ptr(), h.data_ptr(),
              None if delta is None else delta.data_ptr(), None if y is None else L[wname + "_w"].data_ptr(),
-             None if y is None else L[wname + "_b"].data_ptr(), h.shape[0], h.shape[1], 1e-5, _stream())
+             None if y is None else L[wname + "_b"].data_ptr(), h.shape[0], h.shape[1], 1e-5,
+             0 if y is None else y.t_tile, _stream())
         return y
 
     def _gelu(self, x, out=None, add=None):
+        """out = gelu(x) (+ add); ``out`` a row-major tensor (default: in place) or a TiledAct."""
         out = x if out is None else out
-        call("vb_gelu_add", out.data_ptr(), x.data_ptr(), None if add is None else add.data_ptr(), x.numel(), _stream())
+        tiled = isinstance(out, ops.TiledAct)
+        call("vb_gelu_add", out.data.data_ptr() if tiled else out.data_ptr(), x.data_ptr(),
+             None if add is None else add.data_ptr(), x.numel(), x.shape[-1], out.t_tile if tiled else 0, _stream())
         return out
 
     @staticmethod
@@ -150,17 +154,25 @@ class GLMWhisperVQEncoder:
         kv = torch.zeros(1, 1, 2, page, self.n_heads, self.head_dim, dtype=BF16, device=self.device)
         return plan, kv, page
 
-    def _layer(self, h, y, L, plan, kv, page, T):
+    def _layer(self, h, y, L, plan, kv, page, T, buf):
+        """One encoder layer after its first LayerNorm (y); returns the MLP output the caller adds to h.  Every
+        projection reads its activations in the tiled layout (one linear bulk copy per pipeline stage; a row-major
+        operand costs the TMA unit one request per token row, 256 per stage at these widths)."""
         D, H, hd = self.d_model, self.n_heads, self.head_dim
         q = ops.gemm(y, L["q_proj"], bias=L["q_proj_b"])
         ops.gemm(y, L["k_proj"], out=kv[0, 0, 0].view(page, D)[:T])
         ops.gemm(y, L["v_proj"], out=kv[0, 0, 1].view(page, D)[:T], bias=L["v_proj_b"])
-        a = ops.paged_attn(q.view(T, H, hd), kv, 0, plan, T, H, page, 0, None, prefill_tiles=True)
-        o = ops.gemm(a.view(T, D), L["out_proj"], bias=L["out_proj_b"])
-        y2 = self._add_layernorm(h, o, "final_layer_norm", L)                 # h += attn ; y2 = LN2(h)
+        a = ops.paged_attn(q.view(T, H, hd), kv, 0, plan, T, H, page, 0, None, out=buf["a"], prefill_tiles=True)
+        o = ops.gemm(a, L["out_proj"], bias=L["out_proj_b"])
+        y2 = self._add_layernorm(h, o, "final_layer_norm", L, y=buf["y"])     # h += attn ; y2 = LN2(h)
         f = ops.gemm(y2, L["fc1"], bias=L["fc1_b"])
-        self._gelu(f)
-        return ops.gemm(f, L["fc2"], bias=L["fc2_b"])                         # the caller adds it to h
+        g = self._gelu(f, out=buf["f"])
+        return ops.gemm(g, L["fc2"], bias=L["fc2_b"])                         # the caller adds it to h
+
+    def _buffers(self, T: int):
+        D, F = self.d_model, self.config.encoder_ffn_dim
+        return {"y": ops.TiledAct(T, D, self.device), "a": ops.TiledAct(T, D, self.device),
+                "f": ops.TiledAct(T, F, self.device)}
 
     # ---- forward (glm.py:279-323) ---------------------------------------------------------------------
     def forward(self, input_features: torch.Tensor, attention_mask: torch.Tensor, return_states: bool = False):
@@ -190,13 +202,14 @@ class GLMWhisperVQEncoder:
             h = self._gelu(c2, add=self.embed_positions[:T].contiguous())
             block = cfg.quantize_causal_block_size
             plan, kv, page = self._attention_plan(T, self.block_causal_bounds(valid, T, block, self.device))
+            buf = self._buffers(T)
             ids = hidden_last = pooled = None
             delta = None
             for i, L in enumerate(self.layers):
-                y = self._add_layernorm(h, delta, "self_attn_layer_norm", L)  # h += previous MLP ; y = LN1(h)
-                delta = self._layer(h, y, L, plan, kv, page, T)
+                y = self._add_layernorm(h, delta, "self_attn_layer_norm", L, y=buf["y"])  # h += previous MLP ; y = LN1(h)
+                delta = self._layer(h, y, L, plan, kv, page, T, buf)
                 if i + 1 == cfg.pooling_position and cfg.pooling_kernel_size is not None:
-                    self._add_layernorm(h, delta, "", L, want_y=False)
+                    self._add_layernorm(h, delta, "", L)
                     delta = None
                     hidden_last = h
                     k = cfg.pooling_kernel_size
@@ -206,9 +219,10 @@ class GLMWhisperVQEncoder:
                     h, T = hp, Tp
                     valid = int(attention_mask[b, ::2][::k].sum())
                     plan, kv, page = self._attention_plan(T, self.block_causal_bounds(valid, T, block // k, self.device))
+                    buf = self._buffers(T)
                 if i + 1 == cfg.quantize_position and cfg.quantize_vocab_size is not None:
                     if delta is not None:
-                        self._add_layernorm(h, delta, "", L, want_y=False)
+                        self._add_layernorm(h, delta, "", L)
                         delta = None
                     pooled = h
                     acc = ops.gemm(h, self.codebook, mode=1)                  # fp32 [1][T][vocab] = x c^T

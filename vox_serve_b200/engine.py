@@ -199,10 +199,13 @@ class LlamaEngine:
         self.q = torch.zeros(R, hq, D, dtype=BF16, device=dev)
         self.attn = torch.zeros(R, hq, D, dtype=BF16, device=dev)
         self.act = torch.zeros(R, I, dtype=BF16, device=dev)
-        # decode-sized steps keep the projections' activations in the tiled layout (one bulk copy per GEMM stage)
-        self.normed_t = ops.TiledAct(self.FUSED_MAX_ROWS, H, dev)
+        # the projections read their activations in the tiled layout (one linear bulk copy per GEMM stage; a row-major
+        # operand costs the TMA unit one request per token row -- 133 to 256 per stage in a prefill step, several times
+        # the 16 KiB weight tile beside it): decode-sized AND prefill-sized steps (VB_PREFILL_TILED_ACTS=0: decode only)
+        self.tiled_max_rows = R if os.environ.get("VB_PREFILL_TILED_ACTS", "1") != "0" else self.FUSED_MAX_ROWS
+        self.normed_t = ops.TiledAct(self.FUSED_MAX_ROWS, H, dev, max_T=self.tiled_max_rows)
         self.attn_t = ops.TiledAct(self.FUSED_MAX_ROWS, hq * D, dev)
-        self.act_t = ops.TiledAct(self.FUSED_MAX_ROWS, I, dev)
+        self.act_t = ops.TiledAct(self.FUSED_MAX_ROWS, I, dev, max_T=self.tiled_max_rows)
         self.hidden_t = ops.TiledAct(self.FUSED_MAX_ROWS, H, dev)
         self.max_out_rows = min(R, 64)     # logits are only ever needed for one row per request
         self.last_normed = torch.zeros(self.max_out_rows, H, dtype=BF16, device=dev)
@@ -330,14 +333,15 @@ class LlamaEngine:
                               hidden_tiles_out=hidden_t)
 
     def _layers_unfused(self, position_ids: torch.Tensor, R: int, plan: ops.RowPlan):
-        """8 launches per layer.  Decode-sized steps (R <= FUSED_MAX_ROWS) pass activations between kernels in the
-        tiled layout; returns what holds the final normed rows (a TiledAct then, else self.normed[:R])."""
+        """8 launches per layer.  Activations travel between kernels in the tiled layout (the attention output only in
+        decode-sized steps and only with VB_ATTN_TILED=1); returns what holds the final normed rows (a TiledAct then,
+        else self.normed[:R])."""
         d, w = self.dims, self.w
         hq, hkv, D, H, I = d.num_attention_heads, d.num_key_value_heads, d.head_dim, d.hidden_size, d.intermediate_size
         hidden = self.hidden[:R]
-        tiled = R <= self.FUSED_MAX_ROWS and self.tiled_acts
+        tiled = R <= self.tiled_max_rows and self.tiled_acts
         normed = self.normed_t.view_rows(R) if tiled else self.normed[:R]
-        attn_tiled = tiled and self.attn_tiled
+        attn_tiled = tiled and self.attn_tiled and R <= self.FUSED_MAX_ROWS
         attn_o = self.attn_t.view_rows(R) if attn_tiled else self.attn[:R]
         act = self.act_t.view_rows(R) if tiled else self.act[:R]
         ops.rmsnorm(hidden, w.layers[0]["ln1"], d.rms_norm_eps, out=normed)
