@@ -244,3 +244,40 @@ def test_capacity_errors_finish_the_request_not_the_loop():
     assert len(sched.audio[winner]) >= 10
     assert {r.request_id for r in sched.finished} == {"ok", "too_long", "starved"}
     assert worker.empty_pages.qsize() == worker.max_num_pages and len(worker.free_slots) == worker.max_batch_size
+
+
+def test_batched_prefill_defers_prompts_that_do_not_fit_the_step():
+    """Scheduler(one_prefill_per_step=False) selects every waiting prompt (their lengths are unknown before preprocess):
+    the worker takes as many as fit max_prefill_tokens rows and leaves the rest un-prefilled for the next step -- nobody
+    fails, and every request generates exactly the tokens of the one-prefill-per-step schedule."""
+    import torch
+
+    from oracle import snac as osnac
+    from tests.e2e_harness import build_models
+    from vox_serve_b200.requests import Request
+    from vox_serve_b200.scheduler import Scheduler
+
+    dims = oorph.OrpheusDims.tiny(vocab_size=156940, stop_token_id=128258, audio_id_base=128266)
+    prompt_lens, n_tokens = (100, 90, 110, 70, 12), 30
+    dims.max_tokens = max(prompt_lens) + n_tokens
+    worker, _ = build_models(dims, osnac.SnacConfig.tiny(), 3, len(prompt_lens), 16, 256, planted=2.0)   # 256-row prefill steps
+    g = torch.Generator().manual_seed(21)
+    prompts = [torch.randint(10, dims.vocab_size, (n - 5,), generator=g).tolist() for n in prompt_lens]
+    out = {}
+    for mode, one in (("single", True), ("batched", False)):
+        sched = Scheduler(worker, one_prefill_per_step=one)
+        sched.trace = []
+        reqs = [Request(request_id=f"{mode}{i}", prompt=p, model_kwargs={"voice": None}) for i, p in enumerate(prompts)]
+        for r in reqs:
+            sched.submit(r)
+        sched.run_until_done(max_steps=4000)
+        torch.cuda.synchronize()
+        assert all(r.finish_reason == "max_tokens_reached" for r in reqs), [r.finish_reason for r in reqs]
+        out[mode] = ([[int(t[0, 0]) for t in r.lm_output_tokens] for r in reqs], sched.trace)
+        assert worker.empty_pages.qsize() == worker.max_num_pages and len(worker.free_slots) == worker.max_batch_size
+    assert out["single"][0] == out["batched"][0]
+    first = [rid for rid, _ in out["batched"][1][0]]
+    # 100 + 90 rows fit the 256-row step (+ one row reserved per remaining request), 110 more do not, the 70-row prompt after
+    # it still does; the 12-row one no longer
+    assert first == ["batched0", "batched1", "batched3"], first
+    assert len(out["batched"][1]) < len(out["single"][1])    # fewer scheduler steps overall

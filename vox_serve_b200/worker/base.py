@@ -287,8 +287,18 @@ class ModelWorker:
                 # is released -- the scheduler loop (and the other streams) keep running.  (The reference raises out of
                 # prepare_lm_inputs with half-updated state: queue.Empty / CUDA errors, worker/base.py:237-249.)
                 why = None
-                if n > self.max_prefill_tokens or t + n > self.max_rows - (len(lm_requests) - i - 1):
+                if n > self.max_prefill_tokens:
                     why = f"error: prompt of {n} tokens exceeds max_prefill_tokens {self.max_prefill_tokens}"
+                elif t + n > self.max_rows - (len(lm_requests) - i - 1):
+                    # fits a step of its own but not THIS one (several prompts selected at once: a scheduler that batches
+                    # prefills does not know a prompt's length before preprocess has run): left un-prefilled for a later
+                    # step, nothing held
+                    s_ = self.slot_of.pop(req.request_id, None)
+                    if s_ is not None:
+                        self.free_slots.append(s_)
+                    failed.append(i)
+                    qo[i + 1], ip[i + 1], last[i], slots[i] = t, npg, 1, slot
+                    continue
                 elif self.empty_pages.qsize() < n_pages:
                     why = f"error: out of KV pages ({n_pages} needed, {self.empty_pages.qsize()} free)"
                 if why is not None:
