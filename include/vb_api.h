@@ -152,6 +152,16 @@ int vb_paged_prefill_attn(void* d_out, const void* d_q, const void* d_kv, int64_
                           const int32_t* d_row_kvlen, int n_req, int n_rows, int n_q, int n_kv, int head_dim,
                           int page_size, float sm_scale, int out_xt_tile, void* stream);
 
+/* The same operator on the 5th-generation tensor cores: both contractions as tcgen05.mma from swizzled shared-memory
+ * operand tiles, S and the per-tile P V product in TMEM, the GQA group folded into the MMA's 128 accumulator rows (a Q
+ * tile = 128 / group prompt rows of one request), K/V tiles of 128 tokens (any page size).  Arguments as
+ * vb_paged_prefill_attn. */
+int vb_prefill_attn_tc_tile_rows(int n_q, int n_kv);
+int vb_paged_prefill_attn_tc(void* d_out, const void* d_q, const void* d_kv, int64_t slab_base,
+                             const int32_t* d_qo_indptr, const int32_t* d_kv_indptr, const int32_t* d_kv_indices,
+                             const int32_t* d_row_kvlen, int n_req, int n_rows, int n_q, int n_kv, int head_dim,
+                             int page_size, float sm_scale, int out_xt_tile, void* stream);
+
 /* ---- dense projections (nn.Linear, bias-free): model/orpheus.py:41-47, 68-79, 197 -------------
  * Y[T][N] = X[T][K] * W[N][K]^T on tcgen05: a tile of tile_rows (<= 128, multiple of 8; 0 = 128) weight rows is
  * the M side of the MMA, the tokens are the N side.  tile_rows is free so that a projection can be cut into

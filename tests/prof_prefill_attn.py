@@ -55,7 +55,7 @@ def main():
                "kv_bytes_once": int(sum(kv) * hkv * D * 2 * 2),
                "auto_choice": "tiles" if ops.use_prefill_tiles(plan, R, D, page) else "rows"}
         outs = {}
-        for label, tiles in (("tiles", True), ("rows", False)):
+        for label, tiles in (("tiles", True), ("tc", "tc"), ("rows", False)):
             def run():
                 ops.paged_attn(q, cache, 0, plan, R, hkv, page, chunk, ws, out=out, prefill_tiles=tiles)
             for _ in range(5):
@@ -80,6 +80,7 @@ def main():
             res[f"{label}_us_per_launch"] = round(e0.elapsed_time(e1) * 1e3 / 280, 2)
             outs[label] = out.float().clone()
         res["max_abs_diff"] = float((outs["tiles"] - outs["rows"]).abs().max())
+        res["max_abs_diff_tc"] = float((outs["tc"] - outs["rows"]).abs().max())
         print(json.dumps(res), flush=True)
 
 

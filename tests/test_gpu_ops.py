@@ -218,7 +218,7 @@ def test_paged_attention_prefill_ragged_causal(ops):
     _attn_case(ops, [5, 36, 40], 16, 6, 2, 128, 15, prefill_new=[5, 20, 1])
 
 
-def _prefill_tiles_case(ops, kv_lens, new, page_size, hq, hkv, D, seed, pad_rows=0, xt=False):
+def _prefill_tiles_case(ops, kv_lens, new, page_size, hq, hkv, D, seed, pad_rows=0, xt=False, kernel=True):
     """The tiled tensor-core prefill kernel (vb_paged_prefill_attn) against the oracle's ragged causal prefill
     (flashinfer_utils.py:68-80, 132) and against the one-stream-per-row kernel on the same plan."""
     n_pages = sum((L + page_size - 1) // page_size for L in kv_lens) + 3
@@ -236,7 +236,7 @@ def _prefill_tiles_case(ops, kv_lens, new, page_size, hq, hkv, D, seed, pad_rows
     ws = ops.paged_attn_workspace(Rp, None, hq, hkv, D, "cuda")
     dq, dc = q.cuda(), cache.cuda()
     out = torch.full((Rp, hq, D), 7.0, dtype=BF, device="cuda")
-    ops.paged_attn(dq, dc, layer * n_pages, plan, Rp, hkv, page_size, chunk, ws, out=out, prefill_tiles=True)
+    ops.paged_attn(dq, dc, layer * n_pages, plan, Rp, hkv, page_size, chunk, ws, out=out, prefill_tiles=kernel)
     torch.cuda.synchronize()
     got = out.float().cpu()
     err = (got[:R] - ref).abs()
@@ -249,7 +249,7 @@ def _prefill_tiles_case(ops, kv_lens, new, page_size, hq, hkv, D, seed, pad_rows
     assert (old[:R] - got[:R]).abs().max().item() < 0.1 * max(ref.abs().mean().item(), 1e-3) * 4
     if xt:
         out_t = ops.paged_attn(dq, dc, layer * n_pages, plan, Rp, hkv, page_size, chunk, ws,
-                               out=ops.TiledAct(Rp, hq * D, "cuda"), prefill_tiles=True)
+                               out=ops.TiledAct(Rp, hq * D, "cuda"), prefill_tiles=kernel)
         assert torch.equal(out_t.to_rows(), out.view(Rp, hq * D)), "tiled-layout output differs"
     return rel
 
@@ -267,6 +267,21 @@ def _prefill_tiles_case(ops, kv_lens, new, page_size, hq, hkv, D, seed, pad_rows
 def test_paged_prefill_attention_tiles(ops, kv_lens, new, page_size, hq, hkv, D):
     _prefill_tiles_case(ops, kv_lens, new, page_size, hq, hkv, D, 31, xt=True)
     _prefill_tiles_case(ops, kv_lens, new, page_size, hq, hkv, D, 32, pad_rows=5)
+
+
+@pytest.mark.parametrize("kv_lens,new,page_size,hq,hkv,D", [
+    ([133, 201, 140], [133, 1, 40], 128, 24, 8, 128),        # Orpheus: 42-row Q tiles x 3 heads = 126 of the 128 MMA rows
+    ([5, 36, 40], [5, 20, 1], 16, 6, 2, 128),                # 16-token pages: a 128-token K/V tile spans 8 pages
+    ([70, 50, 64], [70, 3, 33], 32, 32, 8, 64),              # CSM backbone geometry (group 4, head_dim 64)
+    ([435], [435], 128, 32, 2, 128),                         # GLM-4-Voice: group 16 -> 8 prompt rows per Q tile
+    ([40, 30], [40, 17], 16, 14, 2, 64),                     # CosyVoice2: group 7
+    ([150], [130], 16, 4, 4, 64),                            # no grouping: 128 prompt rows per Q tile
+    ([600, 333], [600, 333], 32, 32, 8, 64),                 # long prompts, several K/V tiles per Q tile
+])
+def test_paged_prefill_attention_tcgen05(ops, kv_lens, new, page_size, hq, hkv, D):
+    """The tcgen05 / TMEM variant of the tiled prefill kernel (vb_paged_prefill_attn_tc): same plans, same bounds."""
+    _prefill_tiles_case(ops, kv_lens, new, page_size, hq, hkv, D, 51, xt=True, kernel="tc")
+    _prefill_tiles_case(ops, kv_lens, new, page_size, hq, hkv, D, 52, pad_rows=5, kernel="tc")
 
 
 def test_paged_prefill_attention_many_requests(ops):

@@ -44,6 +44,9 @@ SIGNATURES = {
     "vb_prefill_attn_tile_rows": (c_int, [c_int, c_int]),
     "vb_paged_prefill_attn": (c_int, [P, P, P, c_int64, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                       c_int, P]),
+    "vb_prefill_attn_tc_tile_rows": (c_int, [c_int, c_int]),
+    "vb_paged_prefill_attn_tc": (c_int, [P, P, P, c_int64, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                         c_int, P]),
     "vb_set_trace": (c_int, [P]),
     "vb_gemm_t_tile": (c_int, [c_int]),
     "vb_set_gemm_smem_kb": (c_int, [c_int, c_int]),

@@ -20,7 +20,7 @@ OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libvoxb200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["api.cu", "elementwise.cu", "attn.cu", "prefill_attn.cu", "kvcopy.cu", "encoder.cu", "gemm.cu", "sampler.cu", "snac.cu", "snac_mma.cu",
+SOURCES = ["api.cu", "elementwise.cu", "attn.cu", "prefill_attn.cu", "prefill_attn_tc.cu", "kvcopy.cu", "encoder.cu", "gemm.cu", "sampler.cu", "snac.cu", "snac_mma.cu",
            "multicodebook.cu", "mimi.cu", "codec.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

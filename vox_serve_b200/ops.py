@@ -295,6 +295,7 @@ def prefill_attn_tile_rows(n_q: int, n_kv: int) -> int:
 
 
 _PREFILL_TILES = os.environ.get("VB_PREFILL_TILES", "auto")      # "0": never, "1": every prefill plan, "auto": by shape
+_PREFILL_TC = os.environ.get("VB_PREFILL_TC", "0") != "0"        # tiled prefill steps on the tcgen05 kernel instead of mma.sync
 
 
 def use_prefill_tiles(plan: RowPlan, n_rows: int, head_dim: int, page_size: int) -> bool:
@@ -316,7 +317,8 @@ def paged_attn(q: torch.Tensor, kv_cache, slab_base: int, plan: RowPlan, n_rows:
     [pages, 2, P, Hkv, D]); slab_base = layer * pages.  `plan` must come from plan_rows with the same
     chunk_tokens (= attn_chunk_tokens(page_size, n_kv)).  Prefill-shaped plans (use_prefill_tiles, or
     ``prefill_tiles=True``) run on the tiled tensor-core kernel (vb_paged_prefill_attn), everything else on the
-    one-stream-per-row kernel (vb_paged_attn)."""
+    one-stream-per-row kernel (vb_paged_attn).  ``prefill_tiles="tc"`` selects the tcgen05 / TMEM variant of the tiled
+    kernel (vb_paged_prefill_attn_tc)."""
     if isinstance(kv_cache, TensorMap):      # older call sites pass tensor_map_kv(...): use the tensor behind it
         kv_cache = kv_cache.owner
     _need_cuda(q, kv_cache)
@@ -334,7 +336,9 @@ def paged_attn(q: torch.Tensor, kv_cache, slab_base: int, plan: RowPlan, n_rows:
     tiles = use_prefill_tiles(plan, n_rows, d, page_size) if prefill_tiles is None else bool(prefill_tiles)
     if tiles:
         assert plan.qo_indptr is not None, "the tiled prefill kernel needs a prefill plan (qo_indptr)"
-        call("vb_paged_prefill_attn", out_ptr, q.data_ptr(), kv_cache.data_ptr(), int(slab_base),
+        fn = "vb_paged_prefill_attn_tc" if (prefill_tiles == "tc" or (prefill_tiles is None and _PREFILL_TC)) else \
+            "vb_paged_prefill_attn"
+        call(fn, out_ptr, q.data_ptr(), kv_cache.data_ptr(), int(slab_base),
              plan.qo_indptr.data_ptr(), plan.kv_indptr.data_ptr(), plan.kv_indices.data_ptr(),
              plan.row_kvlen.data_ptr(), plan.n_req, n_rows, n_q, n_kv, d, page_size, sc, xt, _stream())
         return out
