@@ -126,8 +126,8 @@ def test_paged_decode_attention_matches_flashinfer(fi, ops, use_tensor_cores):
 def test_paged_prefill_attention_matches_flashinfer(fi, ops):
     """ragged causal prefill batch (fresh prompt, decode row, continued context) in the Orpheus geometry through
     FlashInfer's BatchPrefillWithPagedKVCacheWrapper with the reference's own plan keywords
-    (flashinfer_utils.py:68-80, 132): BOTH prefill kernels -- the tiled tensor-core one and the one-stream-per-row
-    one -- and the CPU oracle are held to it."""
+    (flashinfer_utils.py:68-80, 132): ALL prefill kernels -- the tiled ones (mma.sync and tcgen05) and the
+    one-stream-per-row one -- and the CPU oracle are held to it."""
     hq, hkv, D, ps = 24, 8, 128, 128
     kv_lens, new = [133, 201, 140, 300], [133, 1, 40, 300]
     n_pages = sum((L + ps - 1) // ps for L in kv_lens) + 3
@@ -160,10 +160,11 @@ def test_paged_prefill_attention_matches_flashinfer(fi, ops):
     aws = ops.AttnWorkspace(R, hq, hkv, D, "cuda")
     c6 = cache.view(1, *cache.shape)
     tiles = ops.paged_attn(q, c6, 0, plan, R, hkv, ps, chunk, aws, prefill_tiles=True).float().cpu()
+    tc = ops.paged_attn(q, c6, 0, plan, R, hkv, ps, chunk, aws, prefill_tiles="tc").float().cpu()
     rows = ops.paged_attn(q, c6, 0, plan, R, hkv, ps, chunk, aws, prefill_tiles=False).float().cpu()
     orc = lm_ops.paged_attention_prefill(q.cpu(), cache.cpu(), qo, indptr, indices, last, ps).float()
     scale = ref.abs().max().item()
-    for name, a in (("tiled kernel", tiles), ("row kernel", rows), ("oracle", orc)):
+    for name, a in (("tiled kernel", tiles), ("tcgen05 tiled kernel", tc), ("row kernel", rows), ("oracle", orc)):
         err = (a - ref).abs()
         rel = (err.pow(2).sum() / ref.pow(2).sum()).sqrt().item()
         assert rel < 8e-3 and err.max().item() < 0.04 * scale, (name, rel, err.max().item(), scale)

@@ -295,7 +295,16 @@ def prefill_attn_tile_rows(n_q: int, n_kv: int) -> int:
 
 
 _PREFILL_TILES = os.environ.get("VB_PREFILL_TILES", "auto")      # "0": never, "1": every prefill plan, "auto": by shape
-_PREFILL_TC = os.environ.get("VB_PREFILL_TC", "0") != "0"        # tiled prefill steps on the tcgen05 kernel instead of mma.sync
+# which tiled prefill kernel: "auto" = tcgen05 for long prompts (>= 512 rows per request on average: measured 61 vs 75 us per
+# layer on 4 x 600 rows, but 17 vs 12 us on one 133-row prompt -- the tcgen05 version pays a fixed V transpose and serial
+# phases per 128-token tile), "1" = always tcgen05, "0" = always mma.sync
+_PREFILL_TC = os.environ.get("VB_PREFILL_TC", "auto")
+
+
+def use_prefill_tc(plan: "RowPlan", n_rows: int) -> bool:
+    if _PREFILL_TC in ("0", "1"):
+        return _PREFILL_TC == "1"
+    return n_rows >= 512 * max(1, plan.n_req)
 
 
 def use_prefill_tiles(plan: RowPlan, n_rows: int, head_dim: int, page_size: int) -> bool:
@@ -336,8 +345,8 @@ def paged_attn(q: torch.Tensor, kv_cache, slab_base: int, plan: RowPlan, n_rows:
     tiles = use_prefill_tiles(plan, n_rows, d, page_size) if prefill_tiles is None else bool(prefill_tiles)
     if tiles:
         assert plan.qo_indptr is not None, "the tiled prefill kernel needs a prefill plan (qo_indptr)"
-        fn = "vb_paged_prefill_attn_tc" if (prefill_tiles == "tc" or (prefill_tiles is None and _PREFILL_TC)) else \
-            "vb_paged_prefill_attn"
+        fn = "vb_paged_prefill_attn_tc" if (prefill_tiles == "tc" or (prefill_tiles is None and use_prefill_tc(plan, n_rows))) \
+            else "vb_paged_prefill_attn"
         call(fn, out_ptr, q.data_ptr(), kv_cache.data_ptr(), int(slab_base),
              plan.qo_indptr.data_ptr(), plan.kv_indptr.data_ptr(), plan.kv_indices.data_ptr(),
              plan.row_kvlen.data_ptr(), plan.n_req, n_rows, n_q, n_kv, d, page_size, sc, xt, _stream())
