@@ -93,3 +93,39 @@ def test_tf32_hi_lo_split_is_fp32_grade():
     err1 = np.abs(plain - exact) / scale
     assert err3.max() < 2.0 ** -19, err3.max()
     assert err1.max() > 50 * err3.max()
+
+
+def test_prefill_kernel_selection_rules():
+    """Which attention kernel a plan runs on is a host-side decision on shapes only (ops.use_prefill_tiles /
+    use_prefill_tc): stable under CUDA-graph capture, no device read."""
+    from types import SimpleNamespace
+
+    def plan(n_req, prefill=True):
+        return SimpleNamespace(qo_indptr=object() if prefill else None, n_req=n_req)
+
+    assert not ops.use_prefill_tiles(plan(32, prefill=False), 32, 128, 128)      # decode plan: one stream per row
+    assert ops.use_prefill_tiles(plan(1), 133, 128, 128)                          # a lone prompt
+    assert ops.use_prefill_tiles(plan(32), 164, 128, 128)                         # a prompt joining 31 decodes
+    assert not ops.use_prefill_tiles(plan(64), 128, 128, 32)                      # 2-row depth-decoder prefill, batch 64
+    assert not ops.use_prefill_tiles(plan(16), 32, 128, 32)
+    assert not ops.use_prefill_tiles(plan(1), 133, 96, 128)                       # head_dim the tiled kernels do not take
+    assert not ops.use_prefill_tc(plan(1), 435) and not ops.use_prefill_tc(plan(8), 1064)
+    assert ops.use_prefill_tc(plan(4), 2400) and ops.use_prefill_tc(plan(1), 600)  # long prompts: the tcgen05 tiles
+
+
+def test_speech_tokenizer_config_and_mask_bounds():
+    """GLMEncoderConfig.from_dict keeps the computation-shaping fields of the checkpoint's config.json and parks the rest;
+    the per-row key bound equals the oracle's (which the golden test proves equal to the reference's additive mask)."""
+    import torch
+
+    from oracle import glm_encoder as oenc
+    from vox_serve_b200.encoder.glm import GLMEncoderConfig, GLMWhisperVQEncoder
+
+    cfg = GLMEncoderConfig.from_dict({"d_model": 1280, "encoder_attention_heads": 20, "quantize_position": 16,
+                                      "vocab_size": 51866, "model_type": "whisper"})
+    assert cfg.d_model == 1280 and cfg.quantize_position == 16 and cfg.extra == {"vocab_size": 51866, "model_type": "whisper"}
+    for T, valid, block in ((80, 80, 16), (74, 66, 16), (1500, 1437, 200), (19, 17, 4)):
+        am = torch.zeros(1, T, dtype=torch.long)
+        am[:, :valid] = 1
+        assert torch.equal(GLMWhisperVQEncoder.block_causal_bounds(valid, T, block, "cpu"),
+                           oenc.block_causal_bounds(am, block))

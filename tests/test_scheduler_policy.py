@@ -41,3 +41,45 @@ def test_vocoder_batching_holds_later_chunks_only():
         held.append("r1" in sel)
     assert held == [False] * 6 + [True]                  # the later chunk waits for the 7th selection
     assert later.next_audio_decode_idx == [7]
+
+
+def test_batched_prefill_selection_packs_prompts_by_length():
+    """Scheduler(one_prefill_per_step=False) (scheduler/base.py:283-286 made selectable): prompts whose length is known
+    (after their first preprocess) are packed up to the worker's prefill row budget; decode requests fill the rest."""
+    w = SimpleNamespace(max_batch_size=8, detokenize_interval=28, detokenize_overlap=21, prefill_graph_batch_size=8,
+                        cuda_graph_seq_len_buckets=[300])
+    s = Scheduler(w, one_prefill_per_step=False)
+    waiting = []
+    for i, n in enumerate((133, 133, 133, 20)):
+        r = Request(request_id=f"p{i}", prompt=[0] * n, model_kwargs={})
+        r.input_length = n
+        waiting.append(r)
+    running = _req(9, 30, 1)
+    s.active_requests = waiting + [running]
+    sel = [r.request_id for r in s._select_lm_requests()]
+    assert sel == ["p0", "p1", "p3", "r9"], sel           # 133 + 133 + 20 <= 300, the third 133 does not fit
+    s1 = Scheduler(w)                                      # the reference's default: one prefill per step
+    s1.active_requests = waiting + [running]
+    assert [r.request_id for r in s1._select_lm_requests()] == ["p0", "r9"]
+
+
+def test_detach_and_adopt_move_a_request_between_loops():
+    """Scheduler.detach / adopt: the scheduler half of a KV hand-off (vox_serve_b200/kv_handoff.py)."""
+    import pytest
+
+    a, b = Scheduler(_worker()), Scheduler(_worker())
+    r0, r1 = _req(0, 30, 1), _req(1, 10)
+    a.submit(r0)
+    a.submit(r1)
+    a._prepare_requests()
+    a.audio["r0"].append(b"x")
+    moved = a.detach("r0")
+    assert moved is r0 and [r.request_id for r in a.active_requests] == ["r1"]
+    assert a.audio["r0"] == [b"x"]                         # what was delivered before the hand-off stays accounted for
+    with pytest.raises(KeyError):
+        a.detach("r0")
+    b.adopt(moved)
+    assert b.active_requests == [r0] and b.audio["r0"] == [] and "r0" in b.submit_time
+    assert b.has_work()
+    sel = b._select_detokenize_requests()                  # the carried vocoder progress decides the next window
+    assert sel == [] and r0.next_audio_decode_idx == [0]   # 30 tokens: the window at 7 needs 35
