@@ -18,6 +18,9 @@ Two figures per run, same state, same K steps:
   e2e   : the reference-facing worker API driven by Scheduler._step -- per step a pinned-host -> device copy of
           the page table / positions / slots and a device -> host read of the sampled ids, plus the PCM chunks
           device -> host; timed with CUDA events around the whole region (host gaps included).
+TTFA (time to first audio chunk, benchmark/goodput.py:250-262) is reported for a lone request, for a request joining
+31 running streams, and for a burst of 32 -- the burst with the reference's one-prefill-per-step policy and, separately,
+with prompts batched into shared prefill steps.
 N > 1: one replica per GPU (request-parallel, no data-path collective), barrier + max over ranks.
 --impl reference: the CPU oracle port of the reference's path (oracle/), all host threads, bounded sample.
 """
