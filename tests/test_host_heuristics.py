@@ -109,8 +109,10 @@ def test_prefill_kernel_selection_rules():
     assert not ops.use_prefill_tiles(plan(64), 128, 128, 32)                      # 2-row depth-decoder prefill, batch 64
     assert not ops.use_prefill_tiles(plan(16), 32, 128, 32)
     assert not ops.use_prefill_tiles(plan(1), 133, 96, 128)                       # head_dim the tiled kernels do not take
-    assert not ops.use_prefill_tc(plan(1), 435) and not ops.use_prefill_tc(plan(8), 1064)
+    assert not ops.use_prefill_tc(plan(1), 435) and not ops.use_prefill_tc(plan(16), 800)
+    assert not ops.use_prefill_tc(plan(32), 956)                                   # 7 prompts among 25 decode rows
     assert ops.use_prefill_tc(plan(4), 2400) and ops.use_prefill_tc(plan(1), 600)  # long prompts: the tcgen05 tiles
+    assert ops.use_prefill_tc(plan(8), 1064)                                       # ... and big batches of prompts
 
 
 def test_speech_tokenizer_config_and_mask_bounds():

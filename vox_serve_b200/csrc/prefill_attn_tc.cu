@@ -36,7 +36,6 @@ struct PrefillTcParams {
   float scale_log2;
 };
 
-constexpr int PTC_KT = 128;        // tokens per K/V tile
 constexpr int PTC_THREADS = 128;
 
 __device__ __forceinline__ void ptc_cp_async16(uint32_t dst, const void* src) {
@@ -53,24 +52,30 @@ __device__ __forceinline__ float ptc_ex2(float x) {
   return y;
 }
 
-template <int D>
+// KT = tokens per K/V tile: 128 at head_dim 64, 64 at head_dim 128 -- either way a CTA stays below half an SM's shared
+// memory (98 KB) and half its tensor memory (256 columns), so TWO CTAs share an SM and one's loads / softmax run under
+// the other's MMAs (the phases inside a CTA are serial).
+template <int D, int KT>
 struct PtcLayout {
   static constexpr int Q = 0;                               // [D/64][128][64] bf16
-  static constexpr int K = Q + 128 * D * 2;                 // [D/64][128][64]
-  static constexpr int VT = K + PTC_KT * D * 2;             // [KT/64][D][64]
-  static constexpr int P = VT + PTC_KT * D * 2;             // [KT/64][128][64]
-  static constexpr int VRAW = P + 128 * PTC_KT * 2;         // [KT][D * 2 + 16 bytes]
+  static constexpr int K = Q + 128 * D * 2;                 // [D/64][KT][64]
+  static constexpr int VT = K + KT * D * 2;                 // [KT/64][D][64]
+  static constexpr int P = VT + KT * D * 2;                 // [KT/64][128][64]
+  static constexpr int VRAW = P + 128 * KT * 2;             // [KT][D * 2 + 16 bytes]
   static constexpr int VRS = D * 2 + 16;
-  static constexpr int BAR = VRAW + PTC_KT * VRS;           // bar_s, bar_o, tmem slot
+  static constexpr int BAR = VRAW + KT * VRS;               // bar_s, bar_o, tmem slot
   static constexpr int TOTAL = BAR + 64 + 1024;             // + alignment slack
 };
 
-template <int D>
+template <int D, int KT>
 __global__ void __launch_bounds__(PTC_THREADS, 1) paged_prefill_attn_tc_kernel(const PrefillTcParams p) {
-  using L = PtcLayout<D>;
+  using L = PtcLayout<D, KT>;
+  constexpr int PTC_KT = KT;
   constexpr int KBD = D / 64;          // 64-element k-blocks of the head dim
   constexpr int KBT = PTC_KT / 64;     // ... of a token tile
   constexpr int CPR = D * 2 / 16;      // 16-byte chunks per K / V row
+  constexpr int TPT = PTC_THREADS / PTC_KT;      // threads that share one token's K / V row (1 or 2)
+  constexpr int CPT = CPR / TPT;                 // 16-byte chunks of the row per thread
   extern __shared__ uint8_t ptc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ptc_smem_raw) + 1023) & ~uintptr_t(1023));
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem + L::Q);
@@ -180,29 +185,30 @@ __global__ void __launch_bounds__(PTC_THREADS, 1) paged_prefill_attn_tc_kernel(c
       return p.kv + static_cast<size_t>(p.slab_base + page) * 2 * page_elems +
              (static_cast<size_t>(tok % p.page_size) * p.n_kv + hk) * D;
     };
+    const int ltok = tid / TPT, lc0 = (tid % TPT) * CPT;      // this thread's token of a tile and its first chunk
     auto load_k = [&](int tile) {
-      const int tok = tile * PTC_KT + tid;
+      const int tok = tile * PTC_KT + ltok;
       if (tok < kmax) {
         const __nv_bfloat16* src = token_src(tok);
 #pragma unroll
-        for (int c = 0; c < CPR; ++c) ptc_cp_async16(smem_u32(sK + xt_index(tid, c * 8, PTC_KT, KBD)), src + c * 8);
+        for (int c = lc0; c < lc0 + CPT; ++c) ptc_cp_async16(smem_u32(sK + xt_index(ltok, c * 8, PTC_KT, KBD)), src + c * 8);
       } else {
 #pragma unroll
-        for (int c = 0; c < CPR; ++c)
-          *reinterpret_cast<uint4*>(sK + xt_index(tid, c * 8, PTC_KT, KBD)) = make_uint4(0u, 0u, 0u, 0u);
+        for (int c = lc0; c < lc0 + CPT; ++c)
+          *reinterpret_cast<uint4*>(sK + xt_index(ltok, c * 8, PTC_KT, KBD)) = make_uint4(0u, 0u, 0u, 0u);
       }
       ptc_cp_commit();
     };
     auto load_v = [&](int tile) {
-      const int tok = tile * PTC_KT + tid;
-      uint8_t* dst = sVraw + tid * L::VRS;
+      const int tok = tile * PTC_KT + ltok;
+      uint8_t* dst = sVraw + ltok * L::VRS;
       if (tok < kmax) {
         const __nv_bfloat16* src = token_src(tok) + page_elems;
 #pragma unroll
-        for (int c = 0; c < CPR; ++c) ptc_cp_async16(smem_u32(dst + c * 16), src + c * 8);
+        for (int c = lc0; c < lc0 + CPT; ++c) ptc_cp_async16(smem_u32(dst + c * 16), src + c * 8);
       } else {
 #pragma unroll
-        for (int c = 0; c < CPR; ++c) *reinterpret_cast<uint4*>(dst + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+        for (int c = lc0; c < lc0 + CPT; ++c) *reinterpret_cast<uint4*>(dst + c * 16) = make_uint4(0u, 0u, 0u, 0u);
       }
       ptc_cp_commit();
     };
@@ -242,16 +248,16 @@ __global__ void __launch_bounds__(PTC_THREADS, 1) paged_prefill_attn_tc_kernel(c
       ptc_cp_wait<0>();
       __syncthreads();               // every thread's V row has landed in the staging buffer
       {
-        // thread j = token j of the tile: its row, 8 dims at a time, scattered to rows d of the [D][KT] tile
-        const uint8_t* srow = sVraw + tid * L::VRS;
+        // this thread's token of the tile: its (part of the) row, 8 dims at a time, scattered to rows d of the [D][KT] tile
+        const uint8_t* srow = sVraw + ltok * L::VRS;
 #pragma unroll 4
-        for (int c = 0; c < CPR; ++c) {
+        for (int c = lc0; c < lc0 + CPT; ++c) {
           const uint4 v = *reinterpret_cast<const uint4*>(srow + c * 16);
           const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const uint16_t h = static_cast<uint16_t>((e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu));
-            *reinterpret_cast<uint16_t*>(sVT + xt_index(c * 8 + e, tid, D, KBT)) = h;
+            *reinterpret_cast<uint16_t*>(sVT + xt_index(c * 8 + e, ltok, D, KBT)) = h;
           }
         }
       }
@@ -349,13 +355,14 @@ __global__ void __launch_bounds__(PTC_THREADS, 1) paged_prefill_attn_tc_kernel(c
   }
 }
 
-template <int D>
+template <int D, int KT>
 static int launch_prefill_tc(const PrefillTcParams& p, dim3 grid, cudaStream_t stream) {
-  auto kern = paged_prefill_attn_tc_kernel<D>;
+  auto kern = paged_prefill_attn_tc_kernel<D, KT>;
   // (a fixed size per instantiation -- safe under CUDA-graph replay -- and below the limit together with the few
   // bytes of static shared memory)
-  VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PtcLayout<D>::TOTAL));
-  VB_LAUNCH_PDL(kern, grid, PTC_THREADS, PtcLayout<D>::TOTAL, stream, p);
+  constexpr int smem_bytes = PtcLayout<D, KT>::TOTAL;
+  VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  VB_LAUNCH_PDL(kern, grid, PTC_THREADS, smem_bytes, stream, p);
   return 0;
 }
 
@@ -396,7 +403,7 @@ int vb_paged_prefill_attn_tc(void* d_out, const void* d_q, const void* d_kv, int
   p.scale_log2 = sm_scale * 1.4426950408889634f;
   const dim3 grid((n_rows + p.TQ - 1) / p.TQ + n_req, n_kv, 1);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return head_dim == 128 ? launch_prefill_tc<128>(p, grid, st) : launch_prefill_tc<64>(p, grid, st);
+  return head_dim == 128 ? launch_prefill_tc<128, 64>(p, grid, st) : launch_prefill_tc<64, 128>(p, grid, st);
 }
 
 }  // extern "C"

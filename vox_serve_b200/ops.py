@@ -295,16 +295,17 @@ def prefill_attn_tile_rows(n_q: int, n_kv: int) -> int:
 
 
 _PREFILL_TILES = os.environ.get("VB_PREFILL_TILES", "auto")      # "0": never, "1": every prefill plan, "auto": by shape
-# which tiled prefill kernel: "auto" = tcgen05 for long prompts (>= 512 rows per request on average: measured 61 vs 75 us per
-# layer on 4 x 600 rows, but 17 vs 12 us on one 133-row prompt -- the tcgen05 version pays a fixed V transpose and serial
-# phases per 128-token tile), "1" = always tcgen05, "0" = always mma.sync
+# which tiled prefill kernel: "auto" = tcgen05 for long prompts and for big batches of prompts (measured per layer: 4 x 600
+# rows 61 vs 75 us, 8 x 133 rows 21 vs 29 us; but one 133-row prompt 15 vs 12 us, 16 x 50 rows 13 vs 10 us -- the tcgen05
+# version pays a V transpose and serial MMA -> softmax -> MMA phases per K/V tile), "1" = always tcgen05, "0" = always mma.sync
 _PREFILL_TC = os.environ.get("VB_PREFILL_TC", "auto")
 
 
 def use_prefill_tc(plan: "RowPlan", n_rows: int) -> bool:
     if _PREFILL_TC in ("0", "1"):
         return _PREFILL_TC == "1"
-    return n_rows >= 512 * max(1, plan.n_req)
+    n_req = max(1, plan.n_req)
+    return n_rows >= 512 * n_req or (n_rows >= 1024 and n_rows >= 128 * n_req)
 
 
 def use_prefill_tiles(plan: RowPlan, n_rows: int, head_dim: int, page_size: int) -> bool:
